@@ -1,0 +1,23 @@
+// kernels.h -- host-callable launchers implemented across the .cu files.
+#pragma once
+#include "common.cuh"
+
+// pretok.cu
+int  pretok_upload_tables();
+void launch_pretok_flags(const uint8_t *text, u64 n, const u32 *spmask, const u32 *spstart, u32 *flags, u64 *err,
+                         int sm_count, cudaStream_t st);
+void launch_newline_translate(const uint8_t *text, u64 n, uint8_t *out, u32 *tile_cnt, u64 *tile_off, u64 *scan_tmp,
+                              cudaStream_t st);
+u64  newline_tiles(u64 n);
+void launch_special_split(const uint8_t *text, u64 n, const uint8_t *sp_blob_dev, const u32 *sp_offs_dev, int n_sp,
+                          u32 max_len, u32 *cand, u32 *spstart, u32 *spmask, u64 n_words, int sm_count, cudaStream_t st);
+void launch_popc_words(const u32 *flags, u64 n_words, u32 *cnt, int sm_count, cudaStream_t st);
+void launch_flags_to_offsets(const u32 *flags, u64 n_words, const u64 *pre, u64 *out, u64 cap, int sm_count, cudaStream_t st);
+void launch_scan_u32(const u32 *in, u64 n, u64 *out, u64 *tmp, cudaStream_t st);
+size_t scan_tmp_elems_host(u64 n);
+
+// Geometry of the padded text arena (see common.cuh): payload at arena + BPE_PAD, 0xFF everywhere else,
+// readable up to arena_bytes(n).
+#define BPE_ARENA_ROUND 32768ull
+static inline size_t arena_bytes(u64 n) { return (size_t)(BPE_PAD + round_up(n + 1, BPE_ARENA_ROUND) + BPE_ARENA_ROUND); }
+static inline u64 flag_words(u64 n) { return round_up(n + 1, BPE_ARENA_ROUND) / 32 + 64; }

@@ -1,0 +1,312 @@
+// pretok.cu -- kernels: UTF-8 validation + class + pretoken-start flags, universal-newline
+// translation, special-token matching, bitmask -> offsets.
+#include "pretok.cuh"
+#include "scan.cuh"
+#include "kernels.h"
+
+// ---------------------------------------------------------------------------------------------
+// flags kernel: one pass over the text.  Per 16-byte chunk a thread classifies its bytes (Unicode
+// class table in shared memory), validates UTF-8, then evaluates the start stencil with its
+// neighbours' classes.  Output: 1 bit per byte (bit set = a pretoken starts on that byte).
+// Algorithmic HBM bytes: n read + n/8 written.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 apply_boundary_mask(uint4 c, u32 m16) {
+    u32 w[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+    for (int j = 0; j < 16; j++)
+        if ((m16 >> j) & 1u) w[j >> 2] = (w[j >> 2] & ~(0xFFu << ((j & 3) * 8))) | ((CLS_B | CLS_LEAD) << ((j & 3) * 8));
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+template <bool HAS_SP>
+__global__ void __launch_bounds__(PT_NT) k_pretok_flags(const uint8_t *__restrict__ text, u64 n, u64 n_tiles,
+                                                       const u32 *__restrict__ spmask, const u32 *__restrict__ spstart,
+                                                       u32 *__restrict__ flags, u64 *__restrict__ err) {
+    __shared__ PretokTables tb;
+    __shared__ uint4 s_text[PT_NT + 2];
+    __shared__ uint4 s_cls[PT_NT + 2];
+    const u32 tid = threadIdx.x;
+    pretok_load_tables(&tb);
+    __syncthreads();
+    const uint4 padchunk = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    for (u64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const u64 tbeg = tile * PT_TILE;
+        const uint4 *g = reinterpret_cast<const uint4 *>(text + tbeg);
+        s_text[1 + tid] = ld_stream_v4(g + tid);
+        if (tid == 0) s_text[0] = ld_stream_v4(g - 1);
+        if (tid == 1) s_text[PT_NT + 1] = ld_stream_v4(g + PT_NT);
+        __syncthreads();
+        u32 m16 = 0, s16 = 0;
+        {
+            u32 e; bool cr;
+            uint4 c = classify_chunk(&tb, s_text[tid], s_text[tid + 1], s_text[tid + 2], &e, &cr);
+            if (HAS_SP) {
+                u64 wi = (tbeg >> 5) + (tid >> 1);
+                u32 sh = (tid & 1u) * 16u;
+                m16 = (spmask[wi] >> sh) & 0xFFFFu;
+                s16 = (spstart[wi] >> sh) & 0xFFFFu;
+                if (m16) c = apply_boundary_mask(c, m16);
+            }
+            s_cls[tid + 1] = c;
+            if (e != 0xFFu) {
+                u64 off = tbeg + (u64)tid * PT_CHUNK + e;
+                if (off < n) atomicMin(reinterpret_cast<u64 *>(&err[0]), off);
+            }
+            if (cr) err[1] = 1;
+            if (tid < 2) {                       // halo chunks (validated by the tile that owns them)
+                const u32 idx = tid == 0 ? 0u : PT_NT + 1u;
+                uint4 hp = idx == 0 ? padchunk : s_text[idx - 1];
+                uint4 hn = idx == 0 ? s_text[1] : padchunk;
+                u32 e2; bool cr2;
+                uint4 hc = classify_chunk(&tb, hp, s_text[idx], hn, &e2, &cr2);
+                if (HAS_SP) {
+                    // halo chunk = last chunk of the previous tile / first chunk of the next one
+                    u32 hm = 0;
+                    if (idx != 0) hm = spmask[(tbeg >> 5) + (PT_NT >> 1)] & 0xFFFFu;
+                    else if (tile > 0) hm = (spmask[(tbeg >> 5) - 1] >> 16) & 0xFFFFu;
+                    if (hm) hc = apply_boundary_mask(hc, hm);
+                }
+                s_cls[idx] = hc;
+            }
+        }
+        __syncthreads();
+        u32 bits = flags_chunk(s_text[tid], s_text[tid + 1], s_text[tid + 2], s_cls[tid], s_cls[tid + 1], s_cls[tid + 2]);
+        if (HAS_SP) bits = (bits & ~m16) | s16;
+        u32 hi = __shfl_down_sync(0xffffffffu, bits, 1);
+        if ((tid & 1u) == 0) flags[(tbeg >> 5) + (tid >> 1)] = bits | (hi << 16);
+        __syncthreads();
+    }
+}
+
+void launch_pretok_flags(const uint8_t *text, u64 n, const u32 *spmask, const u32 *spstart, u32 *flags, u64 *err,
+                         int sm_count, cudaStream_t st) {
+    u64 n_tiles = (n + PT_TILE - 1) / PT_TILE;
+    if (n_tiles == 0) return;
+    u64 grid = (u64)sm_count * 8;
+    if (grid > n_tiles) grid = n_tiles;
+    if (spmask)
+        k_pretok_flags<true><<<(unsigned)grid, PT_NT, 0, st>>>(text, n, n_tiles, spmask, spstart, flags, err);
+    else
+        k_pretok_flags<false><<<(unsigned)grid, PT_NT, 0, st>>>(text, n, n_tiles, nullptr, nullptr, flags, err);
+}
+
+int pretok_upload_tables() {
+    cudaError_t e;
+    e = cudaMemcpyToSymbol(c_uc_pages, bpe_uc_pages, sizeof(bpe_uc_pages)); if (e) return (int)e;
+    e = cudaMemcpyToSymbol(c_uc_index, bpe_uc_index, sizeof(bpe_uc_index)); if (e) return (int)e;
+    e = cudaMemcpyToSymbol(c_uc_ascii, bpe_uc_ascii, sizeof(bpe_uc_ascii)); if (e) return (int)e;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// universal newlines ("\r\n" -> "\n", "\r" -> "\n"): text-mode open() in models/tokenizer/train.py:21-23.
+// Rare slow path (taken only when the flags kernel saw a '\r'): count kept bytes per 4 KiB tile,
+// scan, scatter.
+// ---------------------------------------------------------------------------------------------
+#define NL_NT 256
+#define NL_TILE (NL_NT * 16)
+
+__device__ __forceinline__ u32 nl_keep_mask(const uint8_t *text, u64 base, u64 n, uint8_t *vals) {
+    // bit j set <=> byte base+j survives; vals[j] = translated byte
+    u32 keep = 0;
+    uint8_t prev = base > 0 ? text[base - 1] : 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        u64 i = base + j;
+        uint8_t b = i < n ? text[i] : 0;
+        bool k = i < n && !(b == '\n' && prev == '\r');
+        vals[j] = b == '\r' ? (uint8_t)'\n' : b;
+        keep |= (k ? 1u : 0u) << j;
+        prev = b;
+    }
+    return keep;
+}
+
+__global__ void __launch_bounds__(NL_NT) k_nl_count(const uint8_t *__restrict__ text, u64 n, u32 *__restrict__ tile_cnt) {
+    __shared__ u32 s_warp[33];
+    u64 base = (u64)blockIdx.x * NL_TILE + (u64)threadIdx.x * 16;
+    uint8_t vals[16];
+    u32 keep = nl_keep_mask(text, base, n, vals);
+    u32 tot;
+    block_excl_scan_u32(__popc(keep), &tot, s_warp);
+    if (threadIdx.x == 0) tile_cnt[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(NL_NT) k_nl_scatter(const uint8_t *__restrict__ text, u64 n, const u64 *__restrict__ tile_off,
+                                                     uint8_t *__restrict__ out) {
+    __shared__ u32 s_warp[33];
+    u64 base = (u64)blockIdx.x * NL_TILE + (u64)threadIdx.x * 16;
+    uint8_t vals[16];
+    u32 keep = nl_keep_mask(text, base, n, vals);
+    u32 tot;
+    u32 ex = block_excl_scan_u32(__popc(keep), &tot, s_warp);
+    u64 o = tile_off[blockIdx.x] + ex;
+#pragma unroll
+    for (int j = 0; j < 16; j++)
+        if ((keep >> j) & 1u) out[o++] = vals[j];
+}
+
+// tile_cnt: ceil(n/NL_TILE) u32; tile_off: that + 1 u64; scan_tmp: scan_tmp_elems(n_tiles) u64.
+// *n_out_dev (device u64) = tile_off[n_tiles].
+void launch_newline_translate(const uint8_t *text, u64 n, uint8_t *out, u32 *tile_cnt, u64 *tile_off, u64 *scan_tmp,
+                              cudaStream_t st) {
+    u64 nt = (n + NL_TILE - 1) / NL_TILE;
+    if (nt == 0) { cudaMemsetAsync(tile_off, 0, sizeof(u64), st); return; }
+    k_nl_count<<<(unsigned)nt, NL_NT, 0, st>>>(text, n, tile_cnt);
+    launch_excl_scan_u32_to_u64(tile_cnt, nt, tile_off, scan_tmp, st);
+    k_nl_scatter<<<(unsigned)nt, NL_NT, 0, st>>>(text, n, tile_off, out);
+}
+u64 newline_tiles(u64 n) { return (n + NL_TILE - 1) / NL_TILE; }
+
+// ---------------------------------------------------------------------------------------------
+// special tokens: Tokenizer.segment (models/tokenizer/tokenizer.py:63-66) = re.split on
+// "(s1|s2|...)" with specials sorted longest first => leftmost match, longest special at that
+// position, non-overlapping, scanning resumes after each match.
+//   k_special_candidates: bit i of cand set <=> some special matches at byte i.
+//   k_special_resolve:    chains of candidates closer than max_len are resolved left to right by the
+//                         chain's first candidate; isolated candidates (the normal case) accept themselves.
+// Output: spstart (first byte of an accepted occurrence), spmask (all bytes of accepted occurrences).
+// ---------------------------------------------------------------------------------------------
+struct SpecialsDev {
+    const uint8_t *blob; const u32 *offs; int n; u32 max_len;
+};
+
+__device__ __forceinline__ int special_match_at(const uint8_t *text, u64 n, u64 i, const SpecialsDev &sp) {
+    for (int s = 0; s < sp.n; s++) {             // longest first
+        u32 o = sp.offs[s], l = sp.offs[s + 1] - o;
+        if (l == 0 || i + l > n) continue;
+        bool ok = true;
+        for (u32 k = 0; k < l && ok; k++) ok = text[i + k] == sp.blob[o + k];
+        if (ok) return s;
+    }
+    return -1;
+}
+
+__global__ void __launch_bounds__(256) k_special_candidates(const uint8_t *__restrict__ text, u64 n, SpecialsDev sp,
+                                                           u32 *__restrict__ cand, u64 n_words) {
+    __shared__ u32 s_first[8];                   // 256-bit set of first bytes of the specials
+    if (threadIdx.x < 8) s_first[threadIdx.x] = 0;
+    __syncthreads();
+    if (threadIdx.x < (u32)sp.n) {
+        u32 o = sp.offs[threadIdx.x];
+        if (sp.offs[threadIdx.x + 1] > o) { u32 b = sp.blob[o]; atomicOr(&s_first[b >> 5], 1u << (b & 31)); }
+    }
+    __syncthreads();
+    for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += (u64)gridDim.x * blockDim.x) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(text + w * 32);
+        uint4 a = ld_stream_v4(p), b4 = ld_stream_v4(p + 1);
+        u32 ws[8] = {a.x, a.y, a.z, a.w, b4.x, b4.y, b4.z, b4.w};
+        u32 bits = 0;
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            u32 b = (ws[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
+            if ((s_first[b >> 5] >> (b & 31)) & 1u) {
+                u64 i = w * 32 + j;
+                if (i < n && special_match_at(text, n, i, sp) >= 0) bits |= 1u << j;
+            }
+        }
+        cand[w] = bits;
+    }
+}
+
+__device__ __forceinline__ bool bit_get(const u32 *m, u64 i) { return (m[i >> 5] >> (i & 31)) & 1u; }
+// first set bit at position >= from and < to, or ~0
+__device__ __forceinline__ u64 bit_find_next(const u32 *m, u64 from, u64 to) {
+    if (from >= to) return ~0ull;
+    u64 w = from >> 5;
+    u32 cur = m[w] & (0xFFFFFFFFu << (from & 31));
+    for (;;) {
+        if (cur) { u64 p = (w << 5) + (__ffs(cur) - 1); return p < to ? p : ~0ull; }
+        w++;
+        if ((w << 5) >= to) return ~0ull;
+        cur = m[w];
+    }
+}
+// last set bit at position in [from, to), or ~0
+__device__ __forceinline__ u64 bit_find_last(const u32 *m, u64 from, u64 to) {
+    u64 best = ~0ull;
+    for (u64 p = bit_find_next(m, from, to); p != ~0ull; p = bit_find_next(m, p + 1, to)) best = p;
+    return best;
+}
+__device__ __forceinline__ void bit_set_range(u32 *m, u64 from, u64 to) {
+    for (u64 w = from >> 5; (w << 5) < to; w++) {
+        u64 lo = w << 5;
+        u32 mask = 0xFFFFFFFFu;
+        if (from > lo) mask &= 0xFFFFFFFFu << (from - lo);
+        if (to < lo + 32) mask &= 0xFFFFFFFFu >> (lo + 32 - to);
+        atomicOr(&m[w], mask);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_special_resolve(const uint8_t *__restrict__ text, u64 n, SpecialsDev sp,
+                                                        const u32 *__restrict__ cand, u64 n_words,
+                                                        u32 *__restrict__ spstart, u32 *__restrict__ spmask) {
+    for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += (u64)gridDim.x * blockDim.x) {
+        u32 bits = cand[w];
+        while (bits) {
+            u32 j = __ffs(bits) - 1; bits &= bits - 1;
+            u64 p = w * 32 + j;
+            // chain head <=> no other candidate within max_len-1 bytes before p
+            u64 lo = p >= sp.max_len - 1 ? p - (sp.max_len - 1) : 0;
+            if (sp.max_len > 1 && bit_find_next(cand, lo, p) != ~0ull) continue;
+            u64 reach = p;
+            for (;;) {
+                int s = special_match_at(text, n, p, sp);
+                u32 len = sp.offs[s + 1] - sp.offs[s];
+                atomicOr(&spstart[p >> 5], 1u << (p & 31));
+                bit_set_range(spmask, p, p + len);
+                u64 last_in = bit_find_last(cand, p + 1, p + len);   // suppressed candidates extend the chain
+                if (last_in != ~0ull && last_in > reach) reach = last_in;
+                if (p > reach) reach = p;
+                u64 limit = reach + sp.max_len;                    // q belongs to this chain iff q - reach <= max_len-1
+                if (limit > n) limit = n;
+                u64 q = bit_find_next(cand, p + len, limit);
+                if (q == ~0ull) break;
+                reach = q; p = q;
+            }
+        }
+    }
+}
+
+void launch_special_split(const uint8_t *text, u64 n, const uint8_t *sp_blob_dev, const u32 *sp_offs_dev, int n_sp,
+                          u32 max_len, u32 *cand, u32 *spstart, u32 *spmask, u64 n_words, int sm_count, cudaStream_t st) {
+    SpecialsDev sp{sp_blob_dev, sp_offs_dev, n_sp, max_len};
+    u64 grid = (n_words + 255) / 256;
+    u64 cap = (u64)sm_count * 8;
+    if (grid > cap) grid = cap;
+    if (grid == 0) return;
+    k_special_candidates<<<(unsigned)grid, 256, 0, st>>>(text, n, sp, cand, n_words);
+    k_special_resolve<<<(unsigned)grid, 256, 0, st>>>(text, n, sp, cand, n_words, spstart, spmask);
+}
+
+// ---------------------------------------------------------------------------------------------
+// bitmask -> ascending byte offsets (used by bpe_pretokenize and the encoder)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_popc_words(const u32 *__restrict__ flags, u64 n_words, u32 *__restrict__ cnt) {
+    for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += (u64)gridDim.x * blockDim.x)
+        cnt[w] = __popc(flags[w]);
+}
+__global__ void __launch_bounds__(256) k_flags_to_offsets(const u32 *__restrict__ flags, u64 n_words, const u64 *__restrict__ pre,
+                                                         u64 *__restrict__ out, u64 cap) {
+    for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += (u64)gridDim.x * blockDim.x) {
+        u32 bits = flags[w];
+        u64 o = pre[w];
+        while (bits) {
+            u32 j = __ffs(bits) - 1; bits &= bits - 1;
+            if (o < cap) out[o] = w * 32 + j;
+            o++;
+        }
+    }
+}
+void launch_popc_words(const u32 *flags, u64 n_words, u32 *cnt, int sm_count, cudaStream_t st) {
+    u64 grid = (n_words + 255) / 256, capg = (u64)sm_count * 8;
+    if (grid > capg) grid = capg;
+    if (grid) k_popc_words<<<(unsigned)grid, 256, 0, st>>>(flags, n_words, cnt);
+}
+void launch_flags_to_offsets(const u32 *flags, u64 n_words, const u64 *pre, u64 *out, u64 cap, int sm_count, cudaStream_t st) {
+    u64 grid = (n_words + 255) / 256, capg = (u64)sm_count * 8;
+    if (grid > capg) grid = capg;
+    if (grid) k_flags_to_offsets<<<(unsigned)grid, 256, 0, st>>>(flags, n_words, pre, out, cap);
+}
+void launch_scan_u32(const u32 *in, u64 n, u64 *out, u64 *tmp, cudaStream_t st) { launch_excl_scan_u32_to_u64(in, n, out, tmp, st); }
+size_t scan_tmp_elems_host(u64 n) { return scan_tmp_elems(n); }

@@ -1,0 +1,95 @@
+"""BPE training host: mirrors models/tokenizer/train.py:142-231 of the reference.
+
+train_bpe(input_path, vocab_size, special_tokens) -> (vocab: dict[int, bytes], merges: list[tuple[bytes, bytes]])
+
+The file is read as raw bytes; strict UTF-8 validation, universal-newline translation, GPT-2
+pretokenisation, pretoken counting and the whole merge loop run on the GPU (bpe_train in
+include/bpe_sm100.h).  The host only rebuilds the Python objects from the symbol-id merge list.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+import os
+import time
+from typing import List
+
+import numpy as np
+
+from . import _lib
+from .vocab import Vocab
+
+logger = logging.getLogger(__name__)
+
+_PINNED_READ_THRESHOLD = 64 << 20
+
+
+def _read_file(input_path):
+    """Raw bytes of the file as a uint8 array (page-locked for big files so the H2D copy runs at PCIe speed)."""
+    size = os.path.getsize(input_path)           # FileNotFoundError like open() in the reference
+    if size >= _PINNED_READ_THRESHOLD:
+        buf = _lib.PinnedBuffer(size)
+        with open(input_path, "rb", buffering=0) as f:
+            mv = memoryview(buf.array)
+            got = 0
+            while got < size:
+                k = f.readinto(mv[got:])
+                if not k:
+                    break
+                got += k
+        return buf.array[:got], buf
+    with open(input_path, "rb") as f:
+        data = f.read()
+    return np.frombuffer(data, dtype=np.uint8), data
+
+
+def train_bpe_on_bytes(data, vocab_size: int, special_tokens: List[str] = [], *, ctx=None, return_stats: bool = False,
+                       device_ptr: int | None = None, n_bytes: int | None = None):
+    """train_bpe on an in-memory byte buffer (bytes / numpy uint8) or, with device_ptr, on text already in HBM."""
+    ctx = ctx or _lib.default_context()
+    L = _lib.lib()
+    vocab = Vocab(special_tokens=list(special_tokens))
+    n_merges = max(vocab_size - len(vocab), 0)                    # range(vocab_size - len(vocab)), train.py:183
+    sp_blob, sp_offs = _lib.pack_blobs([s.encode("utf-8") for s in special_tokens])
+    pairs = np.zeros((max(n_merges, 1), 2), dtype=np.int32)
+    n_done = C.c_int(0)
+    stats = _lib.TrainStats()
+    if device_ptr is not None:
+        rc = L.bpe_train_dev(ctx.handle, C.c_void_p(device_ptr), int(n_bytes), _lib.ptr(sp_blob), _lib.ptr(sp_offs),
+                             len(special_tokens), n_merges, _lib.ptr(pairs), C.byref(n_done), C.byref(stats))
+        arr = None
+    else:
+        arr = _lib.as_u8(data)
+        rc = L.bpe_train(ctx.handle, _lib.ptr(arr) if arr.size else None, arr.size, _lib.ptr(sp_blob), _lib.ptr(sp_offs),
+                         len(special_tokens), n_merges, _lib.ptr(pairs), C.byref(n_done), C.byref(stats))
+    if rc == _lib.ERR_UTF8 and arr is not None:
+        bytes(arr).decode("utf-8")                                # raises the reference's UnicodeDecodeError
+        raise AssertionError("device flagged invalid UTF-8 at %d but CPython accepts the data" % L.bpe_last_error_detail(ctx.handle))
+    ctx.check(rc)
+    if stats.duplicate_tokens:
+        # SURVEY A-6: two different merges produced the same byte string while the pair still had a positive
+        # count.  The reference would pool the two symbols; this has never been observed and is not implemented.
+        raise NotImplementedError("two merges produced identical token bytes (SURVEY A-6); not supported")
+    sym = [bytes([i]) for i in range(256)]
+    merges = []
+    for k in range(n_done.value):
+        a, b = sym[pairs[k, 0]], sym[pairs[k, 1]]
+        merges.append((a, b))
+        sym.append(a + b)
+        vocab.add_token(a + b)                                    # dedupes like vocab.py:28-34
+    out = (vocab.get_idx_to_token(), merges)
+    return out + (stats.as_dict(),) if return_stats else out
+
+
+def train_bpe(input_path, vocab_size: int, special_tokens: List[str] = [], **kwargs):
+    """Drop-in for models/tokenizer/train.py:142 train_bpe.  Extra keyword arguments (ctx=, return_stats=)
+    are ours; the reference's adapter never passes any."""
+    t0 = time.time()
+    logger.info("Extracting subword frequencies")
+    arr, _keep = _read_file(input_path)
+    logger.info("Took %s seconds to read %d bytes", round(time.time() - t0, 2), arr.size)
+    t1 = time.time()
+    logger.info("Merging subwords")
+    res = train_bpe_on_bytes(arr, vocab_size, special_tokens, **kwargs)
+    logger.info("Took %s seconds to pretokenize, count and merge subwords on the GPU", round(time.time() - t1, 2))
+    return res
