@@ -45,6 +45,11 @@ const char *bpe_last_error(bpe_ctx *ctx);
 /* Numeric detail of the last error (UTF-8 error offset, offending id, ...). */
 int64_t bpe_last_error_detail(bpe_ctx *ctx);
 int  bpe_device_sync(bpe_ctx *ctx);
+/* Number of CUDA kernels this library has launched in this process (bench.py reports it as gpu_launches). */
+unsigned long long bpe_launch_count(void);
+/* Page-locked host memory for inputs/outputs (H2D / D2H copies from it run at PCIe speed). */
+void *bpe_host_alloc(size_t bytes);
+void  bpe_host_free(void *p);
 
 /* ---- text-mode read semantics -------------------------------------------------------------- */
 /* Replaces open(path, "r", encoding="utf-8").read()'s strict decode: models/tokenizer/train.py:21-23.

@@ -51,7 +51,7 @@ EXPORTS = [
     "bpe_last_error_detail", "bpe_device_sync", "bpe_utf8_validate", "bpe_pretokenize", "bpe_train", "bpe_train_dev",
     "bpe_count_begin", "bpe_count_add_shard", "bpe_count_export_size", "bpe_count_export", "bpe_count_import",
     "bpe_train_from_counts", "bpe_tok_create", "bpe_tok_destroy", "bpe_encode", "bpe_encode_dev", "bpe_tok_key_error",
-    "bpe_tok_cache_reset", "bpe_decode", "bpe_synth_dev", "bpe_synth_host", "bpe_host_alloc", "bpe_host_free",
+    "bpe_tok_cache_reset", "bpe_decode", "bpe_synth_dev", "bpe_synth_host", "bpe_host_alloc", "bpe_host_free", "bpe_launch_count",
 ]
 
 
@@ -97,6 +97,7 @@ def lib():
             L.bpe_host_alloc.restype = vp
             L.bpe_host_free.argtypes = [vp]
             L.bpe_host_free.restype = None
+            L.bpe_launch_count.restype = C.c_ulonglong
             _lib = L
     return _lib
 

@@ -3,6 +3,9 @@
 #include "ctx.h"
 #include "unicode_tables.h"
 
+unsigned long long g_bpe_launches = 0;
+BPE_API unsigned long long bpe_launch_count(void) { return g_bpe_launches; }
+
 int bpe_set_error(bpe_ctx *ctx, int code, const char *fmt, ...) {
     char buf[1024];
     va_list ap;

@@ -66,6 +66,11 @@ void bpe_buf_free(DevBuf &b);
 static inline size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline uint64_t next_pow2(uint64_t x) { uint64_t p = 1; while (p < x) p <<= 1; return p; }
 
+// every kernel launch of the library goes through KLAUNCH so that launches can be counted (bench.py: gpu_launches)
+extern unsigned long long g_bpe_launches;
+#define KLAUNCH(kernel, grid, block, smem, stream, ...) \
+    do { g_bpe_launches++; kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); } while (0)
+
 #ifdef __CUDACC__
 __device__ __forceinline__ u64 mix64(u64 x) {
     x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33;

@@ -85,9 +85,9 @@ void launch_pretok_flags(const uint8_t *text, u64 n, const u32 *spmask, const u3
     u64 grid = (u64)sm_count * 8;
     if (grid > n_tiles) grid = n_tiles;
     if (spmask)
-        k_pretok_flags<true><<<(unsigned)grid, PT_NT, 0, st>>>(text, n, n_tiles, spmask, spstart, flags, err);
+        KLAUNCH(k_pretok_flags<true>, (unsigned)grid, PT_NT, 0, st, text, n, n_tiles, spmask, spstart, flags, err);
     else
-        k_pretok_flags<false><<<(unsigned)grid, PT_NT, 0, st>>>(text, n, n_tiles, nullptr, nullptr, flags, err);
+        KLAUNCH(k_pretok_flags<false>, (unsigned)grid, PT_NT, 0, st, text, n, n_tiles, nullptr, nullptr, flags, err);
 }
 
 int pretok_upload_tables() {
@@ -152,9 +152,9 @@ void launch_newline_translate(const uint8_t *text, u64 n, uint8_t *out, u32 *til
                               cudaStream_t st) {
     u64 nt = (n + NL_TILE - 1) / NL_TILE;
     if (nt == 0) { cudaMemsetAsync(tile_off, 0, sizeof(u64), st); return; }
-    k_nl_count<<<(unsigned)nt, NL_NT, 0, st>>>(text, n, tile_cnt);
+    KLAUNCH(k_nl_count, (unsigned)nt, NL_NT, 0, st, text, n, tile_cnt);
     launch_excl_scan_u32_to_u64(tile_cnt, nt, tile_off, scan_tmp, st);
-    k_nl_scatter<<<(unsigned)nt, NL_NT, 0, st>>>(text, n, tile_off, out);
+    KLAUNCH(k_nl_scatter, (unsigned)nt, NL_NT, 0, st, text, n, tile_off, out);
 }
 u64 newline_tiles(u64 n) { return (n + NL_TILE - 1) / NL_TILE; }
 
@@ -275,8 +275,8 @@ void launch_special_split(const uint8_t *text, u64 n, const uint8_t *sp_blob_dev
     u64 cap = (u64)sm_count * 8;
     if (grid > cap) grid = cap;
     if (grid == 0) return;
-    k_special_candidates<<<(unsigned)grid, 256, 0, st>>>(text, n, sp, cand, n_words);
-    k_special_resolve<<<(unsigned)grid, 256, 0, st>>>(text, n, sp, cand, n_words, spstart, spmask);
+    KLAUNCH(k_special_candidates, (unsigned)grid, 256, 0, st, text, n, sp, cand, n_words);
+    KLAUNCH(k_special_resolve, (unsigned)grid, 256, 0, st, text, n, sp, cand, n_words, spstart, spmask);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -301,12 +301,12 @@ __global__ void __launch_bounds__(256) k_flags_to_offsets(const u32 *__restrict_
 void launch_popc_words(const u32 *flags, u64 n_words, u32 *cnt, int sm_count, cudaStream_t st) {
     u64 grid = (n_words + 255) / 256, capg = (u64)sm_count * 8;
     if (grid > capg) grid = capg;
-    if (grid) k_popc_words<<<(unsigned)grid, 256, 0, st>>>(flags, n_words, cnt);
+    if (grid) KLAUNCH(k_popc_words, (unsigned)grid, 256, 0, st, flags, n_words, cnt);
 }
 void launch_flags_to_offsets(const u32 *flags, u64 n_words, const u64 *pre, u64 *out, u64 cap, int sm_count, cudaStream_t st) {
     u64 grid = (n_words + 255) / 256, capg = (u64)sm_count * 8;
     if (grid > capg) grid = capg;
-    if (grid) k_flags_to_offsets<<<(unsigned)grid, 256, 0, st>>>(flags, n_words, pre, out, cap);
+    if (grid) KLAUNCH(k_flags_to_offsets, (unsigned)grid, 256, 0, st, flags, n_words, pre, out, cap);
 }
 void launch_scan_u32(const u32 *in, u64 n, u64 *out, u64 *tmp, cudaStream_t st) { launch_excl_scan_u32_to_u64(in, n, out, tmp, st); }
 size_t scan_tmp_elems_host(u64 n) { return scan_tmp_elems(n); }

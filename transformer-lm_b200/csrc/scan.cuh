@@ -105,9 +105,9 @@ static __global__ void __launch_bounds__(SCAN_NT) k_scan_apply(const u32 *__rest
 static inline void launch_excl_scan_u32_to_u64(const u32 *in, u64 n, u64 *out, u64 *bsum_tmp, cudaStream_t st) {
     if (n == 0) { cudaMemsetAsync(out, 0, sizeof(u64), st); return; }
     u64 nb = (n + SCAN_TILE - 1) / SCAN_TILE;
-    k_scan_blocksums<<<(unsigned)nb, SCAN_NT, 0, st>>>(in, n, bsum_tmp);
-    k_scan_blocksums_scan<<<1, 1024, 0, st>>>(bsum_tmp, nb);
-    k_scan_apply<<<(unsigned)nb, SCAN_NT, 0, st>>>(in, n, bsum_tmp, out);
+    KLAUNCH(k_scan_blocksums, (unsigned)nb, SCAN_NT, 0, st, in, n, bsum_tmp);
+    KLAUNCH(k_scan_blocksums_scan, 1, 1024, 0, st, bsum_tmp, nb);
+    KLAUNCH(k_scan_apply, (unsigned)nb, SCAN_NT, 0, st, in, n, bsum_tmp, out);
 }
 static inline size_t scan_tmp_elems(u64 n) { return (size_t)((n + SCAN_TILE - 1) / SCAN_TILE + 2); }
 

@@ -2,12 +2,12 @@
 // persistent cooperative merge loop.  Entry points: bpe_train*, bpe_count_* (include/bpe_sm100.h).
 //
 // Reference being replaced: models/tokenizer/train.py:142-231 (see each kernel for the exact lines).
-#include <cooperative_groups.h>
 #include <algorithm>
+#include <cstdlib>
+#include <unordered_set>
 #include "kernels.h"
 #include "ctx.h"
-
-namespace cg = cooperative_groups;
+#include "merge.cuh"
 
 // =============================================================================================
 // 1. Pretoken counting  (extract_subword_frequencies, train.py:16-28)
@@ -270,13 +270,6 @@ __global__ void __launch_bounds__(256) k_export_write(CountTables t, const u32 *
 // 2. Word list + initial pair statistics
 //    encode_subwords (train.py:31-32) and calculate_byte_pair_frequencies (train.py:35-49)
 // =============================================================================================
-struct Words {
-    int32_t *sym;        // symbols of all words, word w occupies [off[w], off[w]+len[w])
-    u32 *off; u32 *len;
-    i64 *cnt;            // word frequency
-    u32 *stamp;          // last merge step (+1) that processed the word
-    u64 *counters;       // [0]=n_words [1]=n_syms [2]=max_len
-};
 
 __device__ __forceinline__ bool equals_special(const uint8_t *p, u32 len, const uint8_t *sp_blob, const u32 *sp_offs, int n_sp) {
     for (int s = 0; s < n_sp; s++) {
@@ -309,7 +302,8 @@ __global__ void __launch_bounds__(256) k_build_words(CountTables t, Words W, con
         u64 w = atomicAdd(&W.counters[0], 1ull);
         u64 o = atomicAdd(&W.counters[1], (u64)l);
         atomicMax(&W.counters[2], (u64)l);
-        W.off[w] = (u32)o; W.len[w] = l; W.cnt[w] = (i64)c; W.stamp[w] = 0;
+        WordMeta wm; wm.off = (u32)o; wm.len = l; wm.stamp = 0; wm.pad0 = 0; wm.cnt = (i64)c; wm.pad1 = 0;
+        W.meta[w] = wm;
         for (u32 j = 0; j < l; j++) W.sym[o + j] = src[j];
     }
 }
@@ -317,7 +311,7 @@ __global__ void __launch_bounds__(256) k_build_words(CountTables t, Words W, con
 __global__ void __launch_bounds__(256) k_init_pair_counts(Words W, u64 n_words, u64 *__restrict__ dense /* 65536 */,
                                                          u32 *__restrict__ hist /* 65536 */) {
     for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += (u64)gridDim.x * blockDim.x) {
-        const int32_t *s = W.sym + W.off[w]; u32 l = W.len[w]; u64 c = (u64)W.cnt[w];
+        const int32_t *s = W.sym + W.meta[w].off; u32 l = W.meta[w].len; u64 c = (u64)W.meta[w].cnt;
         for (u32 j = 0; j + 1 < l; j++) {
             u32 p = ((u32)s[j] << 8) | (u32)s[j + 1];
             atomicAdd(&dense[p], c);
@@ -341,7 +335,7 @@ __global__ void __launch_bounds__(1024) k_csr_scan(u32 *__restrict__ hist, u32 *
 __global__ void __launch_bounds__(256) k_csr_fill(Words W, u64 n_words, const u32 *__restrict__ csr_off, u32 *__restrict__ fill,
                                                  u32 *__restrict__ csr_words) {
     for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += (u64)gridDim.x * blockDim.x) {
-        const int32_t *s = W.sym + W.off[w]; u32 l = W.len[w];
+        const int32_t *s = W.sym + W.meta[w].off; u32 l = W.meta[w].len;
         for (u32 j = 0; j + 1 < l; j++) {
             u32 p = ((u32)s[j] << 8) | (u32)s[j + 1];
             csr_words[csr_off[p] + atomicAdd(&fill[p], 1u)] = (u32)w;
@@ -350,268 +344,19 @@ __global__ void __launch_bounds__(256) k_csr_fill(Words W, u64 n_words, const u3
 }
 
 // =============================================================================================
-// 3. Merge loop  (train.py:183-228)
-// =============================================================================================
-#define PAIR_EMPTY 0xFFFFFFFFFFFFFFFFull
-#define CNT_DEAD ((i64)0x8000000000000000ll)     // key was popped from the dict (train.py:226)
-#define PB 256u                                  // pair-table slots per cached-maximum block
-#define MG_NT 512
-
-struct Best { i64 cnt; u64 key; };
-
-struct MergeState {
-    Words W; u32 n_words;
-    // pair table = byte_pair_frequencies: key (a<<32|b) -> count; a key stays (count 0 allowed) until merged
-    u64 *pkey; i64 *pcnt; u64 pcap;
-    Best *bmax; uint8_t *dirty; u32 n_blocks;   // per-block cached argmax
-    // token_indices for pairs of two initial bytes: CSR over the initial words
-    const u32 *csr_off; const u32 *csr_words;
-    // token_indices for every other pair: per-step append log of (side|other symbol, word)
-    uint2 *log; u64 *log_begin; u64 log_cap;
-    // token byte strings and their lexicographic ranks (tie-break of train.py:187-189)
-    u32 *tok_off; u32 *tok_len; uint8_t *tok_bytes; int32_t *lexrank; u64 tok_bytes_cap;
-    Best *cta_best;
-    int32_t *merges_out; int n_merges;
-    u64 *ctr;      // [0]=log cursor [1]=n_done [2]=pairs created [3]=error flags [4]=tok bytes cursor [5]=duplicate tokens
-};
-
-// (count, (bytes_a, bytes_b)) ordering of train.py:187-189 through the rank table
-__device__ __forceinline__ bool best_greater(const Best &x, const Best &y, const int32_t *__restrict__ rank) {
-    if (x.cnt != y.cnt) return x.cnt > y.cnt;
-    if (x.cnt == CNT_DEAD) return false;
-    u32 xa = (u32)(x.key >> 32), ya = (u32)(y.key >> 32);
-    if (xa != ya) return rank[xa] > rank[ya];
-    u32 xb = (u32)x.key, yb = (u32)y.key;
-    return rank[xb] > rank[yb];
-}
-__device__ __forceinline__ Best best_shfl_xor(const Best &b, int d) {
-    Best o;
-    o.cnt = __shfl_xor_sync(0xffffffffu, b.cnt, d);
-    o.key = __shfl_xor_sync(0xffffffffu, b.key, d);
-    return o;
-}
-__device__ __forceinline__ Best warp_best(Best b, const int32_t *rank) {
-#pragma unroll
-    for (int d = 16; d; d >>= 1) { Best o = best_shfl_xor(b, d); if (best_greater(o, b, rank)) b = o; }
-    return b;
-}
-
-// frequencies[key] += delta with defaultdict semantics (train.py:36,65-78): a missing key is created.
-__device__ __forceinline__ void pair_add(const MergeState &M, u32 a, u32 b, i64 delta) {
-    u64 key = ((u64)a << 32) | b;
-    u64 mask = M.pcap - 1;
-    u64 s = mix64(key) & mask;
-    for (u64 probes = 0; probes < M.pcap; probes++) {
-        u64 k = M.pkey[s];
-        if (k == PAIR_EMPTY) {
-            u64 old = atomicCAS(&M.pkey[s], PAIR_EMPTY, key);
-            if (old == PAIR_EMPTY) { atomicAdd(&M.ctr[2], 1ull); k = key; }
-            else k = old;
-        }
-        if (k == key) {
-            i64 old = (i64)atomicAdd((u64 *)&M.pcnt[s], (u64)delta);
-            if (old == CNT_DEAD) atomicAdd((u64 *)&M.pcnt[s], (u64)CNT_DEAD);   // popped key touched again: back to 0 + delta
-            M.dirty[s / PB] = 1;
-            return;
-        }
-        s = (s + 1) & mask;
-    }
-    M.ctr[3] = 1;                                // table full
-}
-
-__device__ __forceinline__ void log_append(const MergeState &M, u32 key, u32 word) {
-    u64 i = atomicAdd(&M.ctr[0], 1ull);
-    if (i < M.log_cap) M.log[i] = make_uint2(key, word);
-    else M.ctr[3] = 2;
-}
-
-// Apply merge (a,b)->nw to word w: the left-to-right scan of train.py:196-224 with
-// update_frequencies_after_merge (52-78), merge_subwords (132-139) and create_new_token_indices (107-129).
-__device__ __forceinline__ void apply_merge_to_word(const MergeState &M, u32 w, u32 a, u32 b, u32 nw) {
-    int32_t *s = M.W.sym + M.W.off[w];
-    u32 len = M.W.len[w];
-    i64 c = M.W.cnt[w];
-    u32 o = 0, r = 0;
-    while (r + 1 < len) {
-        if ((u32)s[r] == a && (u32)s[r + 1] == b) {
-            if (o > 0) {
-                u32 left = (u32)s[o - 1];
-                pair_add(M, left, a, -c);
-                pair_add(M, left, nw, c);
-                log_append(M, left, w);                          // (left, nw): side L, other = left
-            }
-            if (r + 2 < len) {
-                u32 right = (u32)s[r + 2];
-                pair_add(M, b, right, -c);
-                pair_add(M, nw, right, c);
-                log_append(M, 0x80000000u | right, w);           // (nw, right): side R, other = right
-            }
-            s[o++] = (int32_t)nw; r += 2;
-        } else {
-            s[o++] = s[r++];
-        }
-    }
-    while (r < len) s[o++] = s[r++];
-    M.W.len[w] = o;
-}
-
-__global__ void __launch_bounds__(256) k_insert_initial_pairs(MergeState M, const u64 *__restrict__ dense) {
-    u32 p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < 65536 && dense[p]) pair_add(M, p >> 8, p & 255u, (i64)dense[p]);
-}
-
-__device__ __forceinline__ int bytes_cmp_dev(const uint8_t *x, u32 nx, const uint8_t *y, u32 ny) {
-    u32 m = nx < ny ? nx : ny;
-    for (u32 i = 0; i < m; i++) { if (x[i] != y[i]) return x[i] < y[i] ? -1 : 1; }
-    return nx < ny ? -1 : (nx > ny ? 1 : 0);
-}
-
-__global__ void __launch_bounds__(MG_NT) k_merge_loop(MergeState M) {
-    cg::grid_group grid = cg::this_grid();
-    __shared__ Best s_best[MG_NT / 32];
-    __shared__ Best s_win;
-    __shared__ u32 s_red[MG_NT / 32 + 1];
-    const u32 tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
-    const u32 G = gridDim.x;
-    const u32 warps_per_cta = MG_NT / 32;
-    const u32 gwarp = blockIdx.x * warps_per_cta + warp, total_warps = G * warps_per_cta;
-    const bool token_cta = blockIdx.x == G - 1;
-    const u32 apply_ctas = G - 1;
-    u64 prev_key = PAIR_EMPTY;                   // winner of the previous step: popped lazily during the rescan
-    u32 n_tok = 256;
-
-    for (int step = 0; step < M.n_merges; step++) {
-        if (*((volatile u64 *)&M.ctr[3])) break;  // a table overflowed in the previous step (uniform: read after grid.sync)
-        // ---- phase 1: refresh cached block maxima, reduce to one candidate per CTA ----------------
-        if (blockIdx.x == 0 && tid == 0) M.log_begin[step] = M.ctr[0];
-        Best mine; mine.cnt = CNT_DEAD; mine.key = PAIR_EMPTY;
-        for (u32 base = gwarp * 32; base < M.n_blocks; base += total_warps * 32) {
-            u32 blk = base + lane;
-            bool d = blk < M.n_blocks && M.dirty[blk];
-            u32 dmask = __ballot_sync(0xffffffffu, d);
-            while (dmask) {                      // warp-cooperative rescan of a dirty block
-                u32 l = __ffs(dmask) - 1; dmask &= dmask - 1;
-                u32 bb = base + l;
-                Best bst; bst.cnt = CNT_DEAD; bst.key = PAIR_EMPTY;
-                u64 sbase = (u64)bb * PB;
-#pragma unroll
-                for (u32 k = 0; k < PB / 32; k++) {
-                    u64 s = sbase + k * 32 + lane;
-                    u64 key = M.pkey[s];
-                    if (key == PAIR_EMPTY) continue;
-                    if (key == prev_key) { M.pcnt[s] = CNT_DEAD; continue; }
-                    Best c; c.cnt = M.pcnt[s]; c.key = key;
-                    if (c.cnt != CNT_DEAD && best_greater(c, bst, M.lexrank)) bst = c;
-                }
-                bst = warp_best(bst, M.lexrank);
-                if (lane == 0) { M.bmax[bb] = bst; M.dirty[bb] = 0; }
-            }
-            __syncwarp();
-            if (blk < M.n_blocks) {
-                Best c = M.bmax[blk];
-                if (c.cnt != CNT_DEAD && best_greater(c, mine, M.lexrank)) mine = c;
-            }
-        }
-        mine = warp_best(mine, M.lexrank);
-        if (lane == 0) s_best[warp] = mine;
-        __syncthreads();
-        if (warp == 0) {
-            Best c = lane < warps_per_cta ? s_best[lane] : Best{CNT_DEAD, PAIR_EMPTY};
-            c = warp_best(c, M.lexrank);
-            if (lane == 0) M.cta_best[blockIdx.x] = c;
-        }
-        grid.sync();
-        // ---- phase 2: every CTA derives the same winner ----------------------------------------
-        if (warp == 0) {
-            Best c; c.cnt = CNT_DEAD; c.key = PAIR_EMPTY;
-            for (u32 i = lane; i < G; i += 32) { Best o = M.cta_best[i]; if (o.cnt != CNT_DEAD && best_greater(o, c, M.lexrank)) c = o; }
-            c = warp_best(c, M.lexrank);
-            if (lane == 0) s_win = c;
-        }
-        __syncthreads();
-        const Best win = s_win;
-        if (win.cnt == CNT_DEAD) break;          // len(byte_pair_frequencies) == 0 (train.py:184-185)
-        const u32 a = (u32)(win.key >> 32), b = (u32)win.key;
-        const u32 nw = n_tok;                    // symbol id of new_byte = a + b (train.py:190)
-
-        if (token_cta) {
-            // ---- token bookkeeping: bytes of the new token, its lexicographic rank, outputs -----
-            u32 la = M.tok_len[a], lb = M.tok_len[b];
-            u64 cur = M.ctr[4];
-            __syncthreads();
-            if (cur + la + lb > M.tok_bytes_cap) { if (tid == 0) M.ctr[3] = 4; }
-            else {
-                uint8_t *dst = M.tok_bytes + cur;
-                const uint8_t *pa = M.tok_bytes + M.tok_off[a], *pb = M.tok_bytes + M.tok_off[b];
-                for (u32 i = tid; i < la + lb; i += MG_NT) dst[i] = i < la ? pa[i] : pb[i - la];
-                __syncthreads();
-                u32 less = 0, dup = 0;
-                for (u32 t = tid; t < n_tok; t += MG_NT) {
-                    int c = bytes_cmp_dev(M.tok_bytes + M.tok_off[t], M.tok_len[t], dst, la + lb);
-                    less += c <= 0 ? 1u : 0u;    // equal bytes (never expected): older token ranks first
-                    dup += c == 0 ? 1u : 0u;
-                }
-                for (int d = 16; d; d >>= 1) { less += __shfl_down_sync(0xffffffffu, less, d); dup += __shfl_down_sync(0xffffffffu, dup, d); }
-                if (lane == 0) { s_red[warp] = less | (dup ? 0x80000000u : 0u); }
-                __syncthreads();
-                if (tid == 0) {
-                    u32 tot = 0, anydup = 0;
-                    for (u32 i = 0; i < warps_per_cta; i++) { tot += s_red[i] & 0x7FFFFFFFu; anydup |= s_red[i] >> 31; }
-                    s_red[warps_per_cta] = tot;
-                    if (anydup && win.cnt > 0) atomicAdd(&M.ctr[5], 1ull);
-                    M.tok_off[nw] = (u32)cur; M.tok_len[nw] = la + lb; M.ctr[4] = cur + la + lb;
-                    M.merges_out[2 * step] = (int32_t)a; M.merges_out[2 * step + 1] = (int32_t)b;
-                    M.ctr[1] = (u64)(step + 1);
-                }
-                __syncthreads();
-                const int32_t r = (int32_t)s_red[warps_per_cta];
-                for (u32 t = tid; t < n_tok; t += MG_NT) if (M.lexrank[t] >= r) M.lexrank[t]++;
-                if (tid == 0) M.lexrank[nw] = r;
-            }
-            // make sure the winner's block is rescanned so the key gets popped
-            if (tid == 0) {
-                u64 mask = M.pcap - 1, s = mix64(win.key) & mask;
-                while (M.pkey[s] != win.key) s = (s + 1) & mask;
-                M.dirty[s / PB] = 1;
-            }
-        } else {
-            // ---- apply the merge to every word indexed under (a,b) ------------------------------
-            const u32 T = a > b ? a : b;
-            const u64 gthread = (u64)blockIdx.x * MG_NT + tid, gstride = (u64)apply_ctas * MG_NT;
-            if (T < 256) {
-                u32 p = (a << 8) | b;
-                u32 lo = M.csr_off[p], hi = M.csr_off[p + 1];
-                for (u64 i = lo + gthread; i < hi; i += gstride) {
-                    u32 w = M.csr_words[i];
-                    if (atomicExch(&M.W.stamp[w], (u32)step + 1) != (u32)step + 1) apply_merge_to_word(M, w, a, b, nw);
-                }
-            } else {
-                u32 t = T - 256;
-                u64 lo = M.log_begin[t], hi = M.log_begin[t + 1];
-                u32 want = b >= a ? a : (0x80000000u | b);
-                for (u64 i = lo + gthread; i < hi; i += gstride) {
-                    uint2 rec = M.log[i];
-                    if (rec.x == want && atomicExch(&M.W.stamp[rec.y], (u32)step + 1) != (u32)step + 1)
-                        apply_merge_to_word(M, rec.y, a, b, nw);
-                }
-            }
-        }
-        prev_key = win.key;
-        n_tok++;
-        grid.sync();
-    }
-}
-
-// =============================================================================================
 // host orchestration
 // =============================================================================================
+static u64 g_merge_prof[16];
+// Debug/profiling aid: per-phase nanoseconds and counters of the last merge loop (see MergeState::prof).
+BPE_API void bpe_debug_merge_profile(unsigned long long out[16]) { for (int i = 0; i < 16; i++) out[i] = g_merge_prof[i]; }
+
 struct TrainBufs {
-    DevBuf sym, off, len, cnt, stamp, wctr;
+    DevBuf sym, wmeta, wctr;
     DevBuf dense, hist, csr_off, csr_words;
-    DevBuf pkey, pcnt, bmax, dirty, log, log_begin, tok_off, tok_len, tok_bytes, lexrank, cta_best, merges, ctr;
+    DevBuf pkey, pcnt, bmax, dirty, tok_key, prof, step_prof, merge_cnt, log, log_begin, tok_off, tok_len, tok_bytes, cta_best, merges, ctr;
     void free_all() {
-        for (DevBuf *b : {&sym, &off, &len, &cnt, &stamp, &wctr, &dense, &hist, &csr_off, &csr_words, &pkey, &pcnt, &bmax,
-                          &dirty, &log, &log_begin, &tok_off, &tok_len, &tok_bytes, &lexrank, &cta_best, &merges, &ctr})
+        for (DevBuf *b : {&sym, &wmeta, &wctr, &dense, &hist, &csr_off, &csr_words, &pkey, &pcnt, &bmax,
+                          &dirty, &tok_key, &prof, &step_prof, &merge_cnt, &log, &log_begin, &tok_off, &tok_len, &tok_bytes, &cta_best, &merges, &ctr})
             bpe_buf_free(*b);
     }
 };
@@ -693,9 +438,9 @@ static int count_ensure_capacity(bpe_ctx *ctx, u64 n_short, u64 n_long, u64 new_
     CUDA_TRY(ctx, cudaMemsetAsync(cs->counters.p, 0, sizeof(u64), ctx->stream));
     CountTables t = count_tables(ctx);
     unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (old_view.scap + 255) / 256);
-    k_rehash_short<<<grid, 256, 0, ctx->stream>>>((const u64 *)old_view.skey.p, (const u64 *)old_view.scnt.p, old_view.scap, t);
+    KLAUNCH(k_rehash_short, grid, 256, 0, ctx->stream, (const u64 *)old_view.skey.p, (const u64 *)old_view.scnt.p, old_view.scap, t);
     grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (old_view.lcap + 255) / 256);
-    k_rehash_long<<<grid, 256, 0, ctx->stream>>>((const u64 *)old_view.lmeta.p, (const u64 *)old_view.lhash.p,
+    KLAUNCH(k_rehash_long, grid, 256, 0, ctx->stream, (const u64 *)old_view.lmeta.p, (const u64 *)old_view.lhash.p,
                                                  (const u64 *)old_view.lcnt.p, old_view.lcap, t);
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -720,7 +465,7 @@ static int count_current_text(bpe_ctx *ctx, u64 n, u64 own_begin, u64 own_end) {
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->tmp0.p, 0, n_batches * sizeof(u64), st));
     {
         dim3 grid((unsigned)std::min<u64>(ctx->sm_count * 4, (words_per_batch + 255) / 256), (unsigned)n_batches);
-        k_popc_ranges<<<grid, 256, 0, st>>>((const u32 *)ctx->flags.p + w_lo, w_hi - w_lo, words_per_batch, (u64 *)ctx->tmp0.p);
+        KLAUNCH(k_popc_ranges, grid, 256, 0, st, (const u32 *)ctx->flags.p + w_lo, w_hi - w_lo, words_per_batch, (u64 *)ctx->tmp0.p);
     }
     std::vector<u64> bound(n_batches);
     CUDA_TRY(ctx, cudaMemcpyAsync(bound.data(), ctx->tmp0.p, n_batches * sizeof(u64), cudaMemcpyDeviceToHost, st));
@@ -733,7 +478,7 @@ static int count_current_text(bpe_ctx *ctx, u64 n, u64 own_begin, u64 own_end) {
         BPE_TRY(count_ensure_capacity(ctx, c[0], c[1], bound[bi], std::min(bound[bi], bytes / (SHORT_MAX + 1) + 1)));
         CountTables t = count_tables(ctx);
         unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (b_hi - b_lo + 255) / 256);
-        k_count_pretokens<<<grid, 256, 0, st>>>(t, (const u32 *)ctx->flags.p, n, b_lo, b_hi, own_begin, own_end);
+        KLAUNCH(k_count_pretokens, grid, 256, 0, st, t, (const u32 *)ctx->flags.p, n, b_lo, b_hi, own_begin, own_end);
         CUDA_TRY(ctx, cudaGetLastError());
         if (bi + 1 < n_batches) BPE_TRY(read_counters(ctx, c, 6));
     }
@@ -752,7 +497,7 @@ static int count_rehome(bpe_ctx *ctx) {
     u64 *scr = (u64 *)ctx->scratch.p + 8;
     CUDA_TRY(ctx, cudaMemsetAsync(scr, 0, 16, st));
     unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (cs->lcap + 255) / 256);
-    k_rehome_sizes<<<grid, 256, 0, st>>>(t, scr);
+    KLAUNCH(k_rehome_sizes, grid, 256, 0, st, t, scr);
     u64 *host = (u64 *)ctx->pinned;
     CUDA_TRY(ctx, cudaMemcpyAsync(host, scr, 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
@@ -769,7 +514,7 @@ static int count_rehome(bpe_ctx *ctx) {
     }
     host[0] = cs->pool_used;
     CUDA_TRY(ctx, cudaMemcpyAsync(scr + 1, host, 8, cudaMemcpyHostToDevice, st));
-    k_rehome_copy<<<grid, 256, 0, st>>>(t, (uint8_t *)cs->pool.p, scr + 1);
+    KLAUNCH(k_rehome_copy, grid, 256, 0, st, t, (uint8_t *)cs->pool.p, scr + 1);
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     cs->pool_used += need;
@@ -802,8 +547,8 @@ BPE_API int bpe_count_export_size(bpe_ctx *ctx, uint64_t *n_words, uint64_t *blo
     u64 *boff = (u64 *)((uint8_t *)pres + pres_b); u64 *widx = (u64 *)((uint8_t *)boff + boff_b);
     u64 *tmp = (u64 *)((uint8_t *)widx + widx_b);
     unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (total + 255) / 256);
-    k_export_lens<<<grid, 256, 0, st>>>(t, lens);
-    k_export_flags<<<grid, 256, 0, st>>>(lens, total, pres);
+    KLAUNCH(k_export_lens, grid, 256, 0, st, t, lens);
+    KLAUNCH(k_export_flags, grid, 256, 0, st, lens, total, pres);
     launch_scan_u32(lens, total, boff, tmp, st);
     launch_scan_u32(pres, total, widx, tmp, st);
     u64 *host = (u64 *)ctx->pinned;
@@ -829,7 +574,7 @@ BPE_API int bpe_count_export(bpe_ctx *ctx, uint8_t *blob, uint64_t *offs, int64_
     BPE_TRY(bpe_buf_reserve(ctx, ctx->tmp0, ob + oo + oc));
     uint8_t *dblob = (uint8_t *)ctx->tmp0.p; u64 *doffs = (u64 *)(dblob + ob); i64 *dcnt = (i64 *)(dblob + ob + oo);
     unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (total + 255) / 256);
-    k_export_write<<<grid, 256, 0, st>>>(t, lens, boff, widx, dblob, doffs, dcnt);
+    KLAUNCH(k_export_write, grid, 256, 0, st, t, lens, boff, widx, dblob, doffs, dcnt);
     CUDA_TRY(ctx, cudaGetLastError());
     if (nb && blob) CUDA_TRY(ctx, cudaMemcpyAsync(blob, dblob, nb, cudaMemcpyDeviceToHost, st));
     if (nw) CUDA_TRY(ctx, cudaMemcpyAsync(offs, doffs, nw * 8, cudaMemcpyDeviceToHost, st));
@@ -868,7 +613,7 @@ BPE_API int bpe_count_import(bpe_ctx *ctx, const uint8_t *blob, const uint64_t *
     BPE_TRY(count_ensure_capacity(ctx, c[0], c[1], n_words, n_words));
     CountTables t = count_tables(ctx);
     unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (n_words + 255) / 256);
-    k_import_words<<<grid, 256, 0, st>>>(t, (const uint8_t *)cs->pool.p + base, base, doffs, dcnt, n_words);
+    KLAUNCH(k_import_words, grid, 256, 0, st, t, (const uint8_t *)cs->pool.p + base, base, doffs, dcnt, n_words);
     CUDA_TRY(ctx, cudaGetLastError());
     BPE_TRY(read_counters(ctx, c, 6));
     if (c[3]) return bpe_set_error(ctx, BPE_ERR_CAPACITY, "pretoken table overflow on import");
@@ -891,16 +636,15 @@ static int run_merges(bpe_ctx *ctx, const uint8_t *sp_blob, const u32 *sp_offs, 
     BPE_TRY(ctx_upload_specials(ctx, sp_blob, sp_offs, n_sp, &spb, &spo, &spmax));
 
     int ev_build0 = tm.mark();
-    BPE_TRY(alloc_exact(ctx, B.sym, (max_syms + 1) * 4)); BPE_TRY(alloc_exact(ctx, B.off, (max_words + 1) * 4));
-    BPE_TRY(alloc_exact(ctx, B.len, (max_words + 1) * 4)); BPE_TRY(alloc_exact(ctx, B.cnt, (max_words + 1) * 8));
-    BPE_TRY(alloc_exact(ctx, B.stamp, (max_words + 1) * 4)); BPE_TRY(alloc_exact(ctx, B.wctr, 64));
+    BPE_TRY(alloc_exact(ctx, B.sym, (max_syms + 1) * 4)); BPE_TRY(alloc_exact(ctx, B.wmeta, (max_words + 1) * sizeof(WordMeta)));
+    BPE_TRY(alloc_exact(ctx, B.wctr, 64));
     CUDA_TRY(ctx, cudaMemsetAsync(B.wctr.p, 0, 64, st));
-    Words W{(int32_t *)B.sym.p, (u32 *)B.off.p, (u32 *)B.len.p, (i64 *)B.cnt.p, (u32 *)B.stamp.p, (u64 *)B.wctr.p};
+    Words W{(int32_t *)B.sym.p, (WordMeta *)B.wmeta.p, (u64 *)B.wctr.p};
     CountTables t = count_tables(ctx);
     {
         u64 total = cs->scap + cs->lcap;
         unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (total + 255) / 256);
-        k_build_words<<<grid, 256, 0, st>>>(t, W, spb, spo, n_sp);
+        KLAUNCH(k_build_words, grid, 256, 0, st, t, W, spb, spo, n_sp);
         CUDA_TRY(ctx, cudaGetLastError());
     }
     u64 *host = (u64 *)ctx->pinned;
@@ -912,87 +656,142 @@ static int run_merges(bpe_ctx *ctx, const uint8_t *sp_blob, const u32 *sp_offs, 
     BPE_TRY(alloc_exact(ctx, B.csr_off, 65537 * 4)); BPE_TRY(alloc_exact(ctx, B.csr_words, (n_syms + 1) * 4));
     CUDA_TRY(ctx, cudaMemsetAsync(B.dense.p, 0, 65536 * 8, st)); CUDA_TRY(ctx, cudaMemsetAsync(B.hist.p, 0, 65536 * 4, st));
     unsigned wgrid = (unsigned)std::max<u64>(1, std::min<u64>((u64)ctx->sm_count * 8, (n_words + 255) / 256));
-    k_init_pair_counts<<<wgrid, 256, 0, st>>>(W, n_words, (u64 *)B.dense.p, (u32 *)B.hist.p);
-    k_csr_scan<<<1, 1024, 0, st>>>((u32 *)B.hist.p, (u32 *)B.csr_off.p);
-    k_csr_fill<<<wgrid, 256, 0, st>>>(W, n_words, (const u32 *)B.csr_off.p, (u32 *)B.hist.p, (u32 *)B.csr_words.p);
+    KLAUNCH(k_init_pair_counts, wgrid, 256, 0, st, W, n_words, (u64 *)B.dense.p, (u32 *)B.hist.p);
+    KLAUNCH(k_csr_scan, 1, 1024, 0, st, (u32 *)B.hist.p, (u32 *)B.csr_off.p);
+    KLAUNCH(k_csr_fill, wgrid, 256, 0, st, W, n_words, (const u32 *)B.csr_off.p, (u32 *)B.hist.p, (u32 *)B.csr_words.p);
     CUDA_TRY(ctx, cudaGetLastError());
     std::vector<u64> dense(65536);
     CUDA_TRY(ctx, cudaMemcpyAsync(dense.data(), B.dense.p, 65536 * 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
 
-    // pair table capacity: every key ever created = initial pairs + <= 2 per merge site (<= n_syms sites)
+    // pair table: sized for the keys we expect (initial pairs + a fraction of the symbols), grown x4 by
+    // the host whenever the kernel reports it more than half full (all loop state lives in HBM, so the
+    // persistent kernel is simply relaunched after the rehash).
     u64 n_pairs0 = 0;
     for (u64 v : dense) n_pairs0 += v != 0;
-    u64 pcap = next_pow2(std::max<u64>(1 << 12, 2 * (n_pairs0 + 2 * n_syms)));
-    if (pcap > (1ull << 28)) pcap = 1ull << 28;
+    u64 pcap = next_pow2(std::max<u64>(1 << 12, std::max<u64>(8 * n_pairs0, n_syms / 4)));
     MergeState M;
     memset(&M, 0, sizeof(M));
-    M.W = W; M.n_words = (u32)n_words; M.pcap = pcap; M.n_blocks = (u32)(pcap / PB);
-    BPE_TRY(alloc_exact(ctx, B.pkey, pcap * 8)); BPE_TRY(alloc_exact(ctx, B.pcnt, pcap * 8));
-    BPE_TRY(alloc_exact(ctx, B.bmax, (u64)M.n_blocks * sizeof(Best))); BPE_TRY(alloc_exact(ctx, B.dirty, M.n_blocks));
+    M.W = W; M.n_words = (u32)n_words;
+    auto alloc_pair_table = [&](u64 cap) -> int {
+        M.pcap = cap; M.n_blocks = (u32)(cap / PB);
+        BPE_TRY(alloc_exact(ctx, B.pkey, cap * 8)); BPE_TRY(alloc_exact(ctx, B.pcnt, cap * 8));
+        BPE_TRY(alloc_exact(ctx, B.bmax, (u64)M.n_blocks * sizeof(Best))); BPE_TRY(alloc_exact(ctx, B.dirty, M.n_blocks));
+        CUDA_TRY(ctx, cudaMemsetAsync(B.pkey.p, 0xFF, cap * 8, st)); CUDA_TRY(ctx, cudaMemsetAsync(B.pcnt.p, 0, cap * 8, st));
+        CUDA_TRY(ctx, cudaMemsetAsync(B.dirty.p, 1, M.n_blocks, st));
+        M.pkey = (u64 *)B.pkey.p; M.pcnt = (i64 *)B.pcnt.p; M.bmax = (Best *)B.bmax.p; M.dirty = (uint8_t *)B.dirty.p;
+        return BPE_OK;
+    };
+    BPE_TRY(alloc_pair_table(pcap));
     u64 log_cap = 2 * n_syms + 16;
     BPE_TRY(alloc_exact(ctx, B.log, log_cap * 8)); BPE_TRY(alloc_exact(ctx, B.log_begin, ((u64)n_merges + 2) * 8));
     u64 n_tok_max = 256 + (u64)n_merges;
     u64 tok_bytes_cap = 256 + (u64)n_merges * 2 * std::max<u64>(max_len, 1);
     if (tok_bytes_cap > (4ull << 30)) tok_bytes_cap = 4ull << 30;
     BPE_TRY(alloc_exact(ctx, B.tok_off, n_tok_max * 4)); BPE_TRY(alloc_exact(ctx, B.tok_len, n_tok_max * 4));
-    BPE_TRY(alloc_exact(ctx, B.tok_bytes, tok_bytes_cap)); BPE_TRY(alloc_exact(ctx, B.lexrank, n_tok_max * 4));
+    BPE_TRY(alloc_exact(ctx, B.tok_key, n_tok_max * 8));
+    BPE_TRY(alloc_exact(ctx, B.tok_bytes, tok_bytes_cap)); BPE_TRY(alloc_exact(ctx, B.merge_cnt, ((u64)n_merges + 1) * 8));
     BPE_TRY(alloc_exact(ctx, B.merges, ((u64)n_merges + 1) * 8)); BPE_TRY(alloc_exact(ctx, B.ctr, 64));
-    CUDA_TRY(ctx, cudaMemsetAsync(B.pkey.p, 0xFF, pcap * 8, st)); CUDA_TRY(ctx, cudaMemsetAsync(B.pcnt.p, 0, pcap * 8, st));
-    CUDA_TRY(ctx, cudaMemsetAsync(B.dirty.p, 1, M.n_blocks, st));
-    CUDA_TRY(ctx, cudaMemsetAsync(B.ctr.p, 0, 64, st));
+    BPE_TRY(alloc_exact(ctx, B.prof, 128)); CUDA_TRY(ctx, cudaMemsetAsync(B.prof.p, 0, 128, st));
     CUDA_TRY(ctx, cudaMemsetAsync(B.log_begin.p, 0, ((u64)n_merges + 2) * 8, st));
-    {   // byte tokens: bytes(i) = [i], rank(i) = i
-        std::vector<u32> toff(256), tlen(256, 1); std::vector<int32_t> rk(256); std::vector<uint8_t> tb(256);
-        for (int i = 0; i < 256; i++) { toff[i] = i; rk[i] = i; tb[i] = (uint8_t)i; }
+    {   // byte tokens: bytes(i) = [i], rank(i) = i; counters
+        std::vector<u32> toff(256), tlen(256, 1); std::vector<uint8_t> tb(256); std::vector<u64> tk(256);
+        for (int i = 0; i < 256; i++) { toff[i] = i; tb[i] = (uint8_t)i; tk[i] = (u64)i << 56; }
         CUDA_TRY(ctx, cudaMemcpyAsync(B.tok_off.p, toff.data(), 1024, cudaMemcpyHostToDevice, st));
         CUDA_TRY(ctx, cudaMemcpyAsync(B.tok_len.p, tlen.data(), 1024, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(ctx, cudaMemcpyAsync(B.lexrank.p, rk.data(), 1024, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(ctx, cudaMemcpyAsync(B.tok_key.p, tk.data(), 2048, cudaMemcpyHostToDevice, st));
         CUDA_TRY(ctx, cudaMemcpyAsync(B.tok_bytes.p, tb.data(), 256, cudaMemcpyHostToDevice, st));
-        host[0] = 256;
-        CUDA_TRY(ctx, cudaMemcpyAsync((u64 *)B.ctr.p + 4, host, 8, cudaMemcpyHostToDevice, st));
+        for (int i = 0; i < 8; i++) host[i] = 0;
+        host[4] = 256; host[6] = PAIR_EMPTY;
+        CUDA_TRY(ctx, cudaMemcpyAsync(B.ctr.p, host, 64, cudaMemcpyHostToDevice, st));
         CUDA_TRY(ctx, cudaStreamSynchronize(st));
     }
-    M.pkey = (u64 *)B.pkey.p; M.pcnt = (i64 *)B.pcnt.p; M.bmax = (Best *)B.bmax.p; M.dirty = (uint8_t *)B.dirty.p;
     M.csr_off = (const u32 *)B.csr_off.p; M.csr_words = (const u32 *)B.csr_words.p;
     M.log = (uint2 *)B.log.p; M.log_begin = (u64 *)B.log_begin.p; M.log_cap = log_cap;
-    M.tok_off = (u32 *)B.tok_off.p; M.tok_len = (u32 *)B.tok_len.p; M.tok_bytes = (uint8_t *)B.tok_bytes.p;
-    M.lexrank = (int32_t *)B.lexrank.p; M.tok_bytes_cap = tok_bytes_cap;
-    M.merges_out = (int32_t *)B.merges.p; M.n_merges = n_merges; M.ctr = (u64 *)B.ctr.p;
+    M.tok_off = (u32 *)B.tok_off.p; M.tok_len = (u32 *)B.tok_len.p; M.tok_key = (u64 *)B.tok_key.p; M.tok_bytes = (uint8_t *)B.tok_bytes.p;
+    M.tok_bytes_cap = tok_bytes_cap; M.merge_cnt_out = (i64 *)B.merge_cnt.p;
+    M.merges_out = (int32_t *)B.merges.p; M.n_merges = n_merges; M.ctr = (u64 *)B.ctr.p; M.prof = (u64 *)B.prof.p;
+    M.step_prof = nullptr;
+    if (getenv("BPE_STEP_PROFILE")) { BPE_TRY(alloc_exact(ctx, B.step_prof, ((u64)n_merges + 1) * 16)); CUDA_TRY(ctx, cudaMemsetAsync(B.step_prof.p, 0, ((u64)n_merges + 1) * 16, st)); M.step_prof = (u32 *)B.step_prof.p; }
 
     // initial pair table from the dense 256x256 counts (same device-side insert as the merge loop uses)
-    k_insert_initial_pairs<<<256, 256, 0, st>>>(M, (const u64 *)B.dense.p);
+    CUDA_TRY(ctx, cudaMemcpyToSymbolAsync(cM, &M, sizeof(M), 0, cudaMemcpyHostToDevice, st));
+    KLAUNCH(k_insert_initial_pairs, 256, 256, 0, st, (const u64 *)B.dense.p);
     CUDA_TRY(ctx, cudaGetLastError());
     int ev_build1 = tm.mark();
 
-    int G = ctx->sm_count;
     {
         int per_sm = 0;
         CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_merge_loop, MG_NT, 0));
         if (per_sm < 1) return bpe_set_error(ctx, BPE_ERR_CUDA, "merge kernel does not fit on an SM");
-        int want = (int)std::min<u64>((u64)ctx->sm_count, (u64)M.n_blocks / 64 + 2);
-        G = std::max(2, want);
     }
-    BPE_TRY(alloc_exact(ctx, B.cta_best, (u64)G * sizeof(Best)));
+    BPE_TRY(alloc_exact(ctx, B.cta_best, (u64)ctx->sm_count * CTA_BEST_STRIDE * sizeof(Best)));
     M.cta_best = (Best *)B.cta_best.p;
-    if (n_merges > 0) {
-        void *args[] = {&M};
-        CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_merge_loop, dim3(G), dim3(MG_NT), args, 0, st));
+    u64 ctr[8] = {0};
+    u64 keys_created = 0;
+    for (int round = 0; n_merges > 0 && round < 24; round++) {
+        // grid: one CTA per SM for big tables, fewer for small ones (cheaper grid syncs)
+        int G = std::max(2, (int)std::min<u64>((u64)std::min(ctx->sm_count, 160), (u64)M.n_blocks / 256 + 1 + (n_words + 4095) / 4096));
+        CUDA_TRY(ctx, cudaMemcpyToSymbolAsync(cM, &M, sizeof(M), 0, cudaMemcpyHostToDevice, st));
+        g_bpe_launches++;
+        CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_merge_loop, dim3(G), dim3(MG_NT), nullptr, 0, st));
+        CUDA_TRY(ctx, cudaMemcpyAsync(host, B.ctr.p, 64, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        for (int i = 0; i < 8; i++) ctr[i] = host[i];
+        if (ctr[3] != MG_NEED_GROW) break;
+        // grow x4 and re-insert the live keys; the pending pop (ctr[6]) is applied by dropping that key
+        keys_created += ctr[2];
+        DevBuf okey = B.pkey, ocnt = B.pcnt;
+        u64 ocap = M.pcap;
+        B.pkey = DevBuf(); B.pcnt = DevBuf();
+        int rc = alloc_pair_table(ocap * 4);
+        if (rc != BPE_OK) { bpe_buf_free(okey); bpe_buf_free(ocnt); return rc; }
+        host[2] = 0; host[3] = 0; u64 pending = ctr[6]; host[6] = PAIR_EMPTY;
+        CUDA_TRY(ctx, cudaMemcpyAsync((u64 *)B.ctr.p + 2, host + 2, 16, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(ctx, cudaMemcpyAsync((u64 *)B.ctr.p + 6, host + 6, 8, cudaMemcpyHostToDevice, st));
+        unsigned rg = (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (ocap + 255) / 256);
+        CUDA_TRY(ctx, cudaMemcpyToSymbolAsync(cM, &M, sizeof(M), 0, cudaMemcpyHostToDevice, st));
+        KLAUNCH(k_pairs_rehash, rg, 256, 0, st, (const u64 *)okey.p, (const i64 *)ocnt.p, ocap, pending);
+        CUDA_TRY(ctx, cudaGetLastError());
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        bpe_buf_free(okey); bpe_buf_free(ocnt);
     }
+    keys_created += ctr[2];
+    ctr[2] = keys_created;
     int ev_merge1 = tm.mark();
-    CUDA_TRY(ctx, cudaMemcpyAsync(host, B.ctr.p, 64, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(g_merge_prof, B.prof.p, 128, cudaMemcpyDeviceToHost, st));
+    if (M.step_prof) {
+        std::vector<u32> sp((size_t)n_merges * 4);
+        CUDA_TRY(ctx, cudaMemcpyAsync(sp.data(), B.step_prof.p, sp.size() * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        if (FILE *f = fopen(getenv("BPE_STEP_PROFILE"), "wb")) { fwrite(sp.data(), 4, sp.size(), f); fclose(f); }
+    }
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
-    u64 ctr[8];
-    for (int i = 0; i < 8; i++) ctr[i] = host[i];
     if (ctr[3]) return bpe_set_error(ctx, BPE_ERR_CAPACITY, "merge loop table overflow (code %llu)", (unsigned long long)ctr[3]);
     int done = (int)ctr[1];
     if (done > 0) CUDA_TRY(ctx, cudaMemcpyAsync(merge_pairs_out, B.merges.p, (size_t)done * 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     *n_done = done;
+    // SURVEY A-6: the reference identifies tokens by their byte string.  Detect (never observed) merges with a
+    // positive count whose product bytes already exist; the host refuses to return a result in that case.
+    u64 dup_tokens = 0;
+    if (done > 0) {
+        std::vector<i64> mc(done);
+        CUDA_TRY(ctx, cudaMemcpyAsync(mc.data(), B.merge_cnt.p, (size_t)done * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        std::vector<std::string> sym(256);
+        std::unordered_set<std::string> seen;
+        for (int i = 0; i < 256; i++) { sym[i] = std::string(1, (char)i); seen.insert(sym[i]); }
+        for (int k = 0; k < done; k++) {
+            std::string t = sym[merge_pairs_out[2 * k]] + sym[merge_pairs_out[2 * k + 1]];
+            if (!seen.insert(t).second && mc[k] > 0) dup_tokens++;
+            sym.push_back(std::move(t));
+        }
+    }
     int ev_end = tm.mark();
     if (stats) {
         stats->n_unique = n_words; stats->n_symbols = n_syms; stats->n_pairs_initial = n_pairs0;
-        stats->n_pairs_final = ctr[2]; stats->log_records = ctr[0]; stats->duplicate_tokens = ctr[5];
+        stats->n_pairs_final = ctr[2]; stats->log_records = ctr[0]; stats->duplicate_tokens = dup_tokens;
         stats->n_pretokens = cs->n_pretokens;
         stats->ms_build = tm.ms(ev_build0, ev_build1); stats->ms_merge = tm.ms(ev_build1, ev_merge1);
         stats->ms_total = tm.ms(ev_start, ev_end);
