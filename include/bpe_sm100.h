@@ -125,17 +125,20 @@ int bpe_train_from_counts(bpe_ctx *ctx, const uint8_t *specials_blob, const uint
 
 /* ---- tokenizer ----------------------------------------------------------------------------- */
 /* Replaces Tokenizer.__init__ table building: models/tokenizer/tokenizer.py:12-38 and the per-call
- * inv_merges dict (115).  Symbols: 0..255 bytes, 256+j = product of merge j (the host canonicalises
- * symbols by byte string and resolves duplicate pairs to their LAST rank, SURVEY A-6/A-15).
- *   merge_pairs[2*j], [2*j+1]   operand symbols of merge j, or -1,-1 for a merge that can never apply
- *   merge_rank[j]               rank used for ordering (== j unless a later duplicate overrides it)
- *   merge_result[j]             symbol produced when merge j is applied (canonical id)
- *   sym_to_id[s]                vocab id of symbol s, or -1 when its bytes are not in vocab_inv
+ * inv_merges dict (115).  The reference identifies tokens by their byte strings; the host turns them into
+ * integer symbols: 0..255 = single bytes, 256.. = every distinct byte string a+b over the merge list.
+ *   merge_pairs[2*j], [2*j+1]   operand symbols of merge j (its rank is j), or -1,-1 for an entry that can
+ *                               never apply (operand is not a symbol, or a later duplicate of the same pair
+ *                               overrides it: {pair: i for i, pair in enumerate(merges)} keeps the LAST i)
+ *   merge_result[j]             symbol of a+b
+ *   sym_to_id[s]                vocab_inv[bytes(s)], or -1 when absent (KeyError when such a token is emitted,
+ *                               tokenizer.py:135)
+ *   sym_blob/sym_offs           bytes of every symbol (used to report the KeyError key)
  *   vocab_blob/offs/ids         id -> bytes table for decode (ids need not be dense)
- *   specials                    longest first; special_ids[i] = vocab id (or -1 -> KeyError when met) */
+ *   specials                    longest first; special_ids[i] = vocab_inv[special] (or -1 -> KeyError when met) */
 int bpe_tok_create(bpe_ctx *ctx,
-                   const int32_t *merge_pairs, const int32_t *merge_rank, const int32_t *merge_result, int n_merges,
-                   const int32_t *sym_to_id, int n_syms,
+                   const int32_t *merge_pairs, const int32_t *merge_result, int n_merges,
+                   const int32_t *sym_to_id, const uint8_t *sym_blob, const uint64_t *sym_offs, int n_syms,
                    const uint8_t *vocab_blob, const uint64_t *vocab_offs, const int64_t *vocab_ids, int64_t n_vocab,
                    const uint8_t *specials_blob, const uint32_t *special_offs, const int64_t *special_ids, int n_specials,
                    bpe_tok **out);

@@ -82,7 +82,7 @@ def lib():
             L.bpe_count_export.argtypes = [vp, vp, vp, vp]
             L.bpe_count_import.argtypes = [vp, vp, vp, vp, C.c_uint64]
             L.bpe_train_from_counts.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, C.POINTER(C.c_int), C.POINTER(TrainStats)]
-            L.bpe_tok_create.argtypes = [vp, vp, vp, vp, C.c_int, vp, C.c_int, vp, vp, vp, C.c_int64, vp, vp, vp, C.c_int,
+            L.bpe_tok_create.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int64, vp, vp, vp, C.c_int,
                                          C.POINTER(vp)]
             L.bpe_tok_destroy.argtypes = [vp]
             L.bpe_tok_destroy.restype = None
@@ -123,6 +123,15 @@ def pack_blobs(items: list[bytes]):
     offs = np.zeros(len(items) + 1, dtype=np.uint32)
     if items:
         np.cumsum([len(b) for b in items], out=offs[1:])
+    blob = np.frombuffer(b"".join(items) or b"\0", dtype=np.uint8)
+    return blob, offs
+
+
+def pack_blobs64(items: list[bytes]):
+    """(blob u8[], offs u64[n+1]) for a list of byte strings."""
+    offs = np.zeros(len(items) + 1, dtype=np.uint64)
+    if items:
+        np.cumsum(np.fromiter((len(b) for b in items), dtype=np.uint64, count=len(items)), out=offs[1:])
     blob = np.frombuffer(b"".join(items) or b"\0", dtype=np.uint8)
     return blob, offs
 

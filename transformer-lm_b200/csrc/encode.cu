@@ -1,13 +1,907 @@
-// encode.cu -- placeholder until the encoder lands (every entry point reports BPE_ERR_UNSUPPORTED).
+// encode.cu -- Tokenizer.encode / decode on the device.  Entry points: bpe_tok_*, bpe_encode*, bpe_decode.
+//
+// Reference being replaced: models/tokenizer/tokenizer.py:111-138 (encode), 63-90 (segment / pretokenize),
+// 92-109 (merge), 155-157 (decode).
+//
+// Pipeline of one bpe_encode call (all stages on the context's stream):
+//   1. special-token split + GPT-2 pretoken start flags            (pretok.cu, shared with training)
+//   2. k_enc_lookup   every pretoken occurrence is looked up in the tokenizer's device-resident
+//                     pretoken -> token-ids cache (open addressing, exact keys); unseen pretokens
+//                     claim a slot and are queued
+//   3. k_enc_bpe      one warp per queued (new unique) pretoken applies the merges in rank order
+//                     through the pair -> rank table: repeatedly take the lowest-ranked adjacent
+//                     pair and replace all its non-overlapping occurrences left to right
+//   4. k_enc_count    tokens per 32-byte text word -> exclusive scan = output offsets
+//   5. k_enc_emit     token ids scattered to the uint16 / int32 output
+// The reference re-runs BPE for every occurrence (no memoisation, tokenizer.py:118-136); the result per
+// pretoken is a pure function of its bytes, so caching by exact bytes cannot change the output.
+#include <algorithm>
 #include "kernels.h"
 #include "ctx.h"
-struct bpe_tok { bpe_ctx *ctx; };
-BPE_API int bpe_tok_create(bpe_ctx *ctx, const int32_t *, const int32_t *, const int32_t *, int, const int32_t *, int,
-                           const uint8_t *, const uint64_t *, const int64_t *, int64_t, const uint8_t *, const uint32_t *,
-                           const int64_t *, int, bpe_tok **out) { if (out) *out = nullptr; return bpe_set_error(ctx, BPE_ERR_UNSUPPORTED, "encoder not built"); }
-BPE_API void bpe_tok_destroy(bpe_tok *) {}
-BPE_API int bpe_encode(bpe_tok *, const uint8_t *, uint64_t, int, void *, uint64_t, uint64_t *, bpe_encode_stats *) { return BPE_ERR_UNSUPPORTED; }
-BPE_API int bpe_encode_dev(bpe_tok *, const uint8_t *, uint64_t, int, void *, uint64_t, uint64_t *, bpe_encode_stats *) { return BPE_ERR_UNSUPPORTED; }
-BPE_API int bpe_tok_key_error(bpe_tok *, uint8_t *, uint64_t, uint64_t *) { return BPE_ERR_UNSUPPORTED; }
-BPE_API int bpe_tok_cache_reset(bpe_tok *) { return BPE_ERR_UNSUPPORTED; }
-BPE_API int bpe_decode(bpe_tok *, const int64_t *, uint64_t, uint8_t *, uint64_t, uint64_t *) { return BPE_ERR_UNSUPPORTED; }
+#include "hashtab.cuh"
+
+#define SHORT_MAX 7u
+#define META_EMPTY 0xFFFFFFFFFFFFFFFFull
+#define META_LEN_BITS 24
+#define META_LEN_MASK ((1ull << META_LEN_BITS) - 1)
+#define META_POOL_BIT (1ull << 39)
+#define MAX_TOKEN_LEN ((1u << META_LEN_BITS) - 2)
+#define REF_LONG 0x80000000u
+
+// cached value of a pretoken (u64):
+//   tag = v >> 60
+//   0..3   that many ids inline, 20 bits each at bits 0, 20, 40
+//   4      ids in the id pool: bits 59..24 = offset, bits 23..0 = count
+//   5      KeyError: bits 31..0 = offending symbol (bit 31 set: index of a special token instead)
+//   15     not computed yet
+#define VAL_NONE 0xFFFFFFFFFFFFFFFFull
+#define VAL_TAG(v) ((u32)((v) >> 60))
+#define VAL_EXT 4ull
+#define VAL_ERR 5ull
+#define INLINE_ID_LIMIT (1u << 20)
+#define RANK_NONE 0xFFFFFFFFFFFFFFFFull
+#define MKEY_EMPTY 0xFFFFFFFFFFFFFFFFull
+
+struct EncTables {
+    const ulonglong2 *mtab; u64 mmask;           // pair -> {key = a<<32|b, (rank << 32) | result symbol}
+    const int32_t *mpairs;                       // operand symbols of merge j
+    const int32_t *sym_to_id;
+    u64 *skey, *sval; u64 scap;                  // pretokens of <= 7 bytes: the key is the token (bytes | len << 56)
+    u64 *lmeta, *lhash, *lval; u64 lcap;         // longer pretokens: (offset:40 | len:24) of the bytes, 64-bit hash filter
+    const uint8_t *text;                         // payload of the current text arena
+    uint8_t *kpool;                              // persistent key bytes of long pretokens
+    u32 *ipool;                                  // token ids of pretokens with more than 3 tokens
+    u32 *todo;                                   // slots claimed in this batch (REF_LONG = long table)
+    // [0]=n_short [1]=n_long [2]=todo count [3]=table overflow [4]=kpool cursor [5]=ipool cursor [6]=pretoken too long
+    // [7]=smallest text offset of a pretoken whose value is a KeyError
+    u64 *ctr;
+};
+
+__device__ __forceinline__ const uint8_t *enc_rep_ptr(const EncTables &t, u64 meta) {
+    u64 off = meta >> META_LEN_BITS;
+    return (off & META_POOL_BIT) ? t.kpool + (off & ~META_POOL_BIT) : t.text + off;
+}
+
+// ---- pair -> rank ---------------------------------------------------------------------------------
+__device__ __forceinline__ u64 rank_lookup(const EncTables &t, u32 a, u32 b) {
+    u64 key = ((u64)a << 32) | b;
+    u64 s = mix64(key) & t.mmask;
+    for (;;) {
+        ulonglong2 e = __ldg(&t.mtab[s]);
+        if (e.x == key) return e.y;
+        if (e.x == MKEY_EMPTY) return RANK_NONE;
+        s = (s + 1) & t.mmask;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_enc_build_ranks(ulonglong2 *__restrict__ mtab, u64 mmask, const int32_t *__restrict__ pairs,
+                                                        const int32_t *__restrict__ result, int n_merges) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_merges) return;
+    int32_t a = pairs[2 * j], b = pairs[2 * j + 1];
+    if (a < 0 || b < 0) return;
+    u64 key = ((u64)(u32)a << 32) | (u32)b;
+    u64 s = mix64(key) & mmask;
+    for (;;) {                                   // keys are distinct (the host drops superseded duplicates)
+        u64 old = atomicCAS(&mtab[s].x, MKEY_EMPTY, key);
+        if (old == MKEY_EMPTY) { mtab[s].y = ((u64)(u32)j << 32) | (u32)result[j]; return; }
+        s = (s + 1) & mmask;
+    }
+}
+
+// ---- pretoken cache: lookup or claim -----------------------------------------------------------------
+__device__ __forceinline__ u32 enc_short_ref(const EncTables &t, u64 key) {
+    u64 mask = t.scap - 1;
+    u64 s = mix64(key) & mask;
+    for (u64 probes = 0; probes < t.scap; probes++) {
+        u64 k = t.skey[s];
+        if (k == 0) {
+            u64 old = atomicCAS(&t.skey[s], 0ull, key);
+            if (old == 0) {
+                atomicAdd(&t.ctr[0], 1ull);
+                u64 q = atomicAdd(&t.ctr[2], 1ull);
+                t.todo[q] = (u32)s;
+                return (u32)s;
+            }
+            k = old;
+        }
+        if (k == key) return (u32)s;
+        s = (s + 1) & mask;
+    }
+    t.ctr[3] = 1;
+    return 0;
+}
+
+__device__ __forceinline__ u32 enc_long_ref(const EncTables &t, const uint8_t *p, u32 len, u64 off_meta) {
+    u64 h = hash_long(p, len);
+    u64 mask = t.lcap - 1;
+    u64 s = h & mask;
+    u64 mine = (off_meta << META_LEN_BITS) | len;
+    for (u64 probes = 0; probes < t.lcap; probes++) {
+        u64 m = t.lmeta[s];
+        if (m == META_EMPTY) {
+            u64 old = atomicCAS(&t.lmeta[s], META_EMPTY, mine);
+            if (old == META_EMPTY) {
+                t.lhash[s] = h;
+                atomicAdd(&t.ctr[1], 1ull);
+                u64 q = atomicAdd(&t.ctr[2], 1ull);
+                t.todo[q] = (u32)s | REF_LONG;
+                return (u32)s | REF_LONG;
+            }
+            m = old;
+        }
+        if ((m & META_LEN_MASK) == len) {
+            u64 hh = *((volatile u64 *)&t.lhash[s]);
+            if ((hh == 0 || hh == h) && bytes_equal(enc_rep_ptr(t, m), p, len)) return (u32)s | REF_LONG;
+        }
+        s = (s + 1) & mask;
+    }
+    t.ctr[3] = 1;
+    return 0;
+}
+
+// One thread per 32-byte flag word; slots[ordinal of the pretoken inside the batch] = its cache slot.
+__global__ void __launch_bounds__(256) k_enc_lookup(EncTables t, const u32 *__restrict__ flags, u64 n, u64 word_begin, u64 word_end,
+                                                   const u64 *__restrict__ pre, u32 *__restrict__ slots) {
+    const u64 base_ord = pre[word_begin];
+    for (u64 w = word_begin + (u64)blockIdx.x * blockDim.x + threadIdx.x; w < word_end; w += (u64)gridDim.x * blockDim.x) {
+        u32 bits = flags[w];
+        u64 o = pre[w] - base_ord;
+        while (bits) {
+            u32 j = __ffs(bits) - 1; bits &= bits - 1;
+            u64 pos = (w << 5) + j;
+            u64 end = bits ? (w << 5) + (__ffs(bits) - 1) : flags_next_start(flags, (w + 1) << 5, n);
+            u64 len = end - pos;
+            const uint8_t *p = t.text + pos;
+            u32 ref = 0;
+            if (len <= SHORT_MAX) {
+                u64 key = 0;
+                for (u32 k = 0; k < (u32)len; k++) key |= (u64)p[k] << (8 * k);
+                key |= len << 56;
+                ref = enc_short_ref(t, key);
+            } else if (len <= MAX_TOKEN_LEN) {
+                ref = enc_long_ref(t, p, (u32)len, pos);
+            } else {
+                t.ctr[6] = 1;
+            }
+            slots[o++] = ref;
+        }
+    }
+}
+
+// ---- BPE of the queued pretokens: one warp each ----------------------------------------------------------
+__device__ __forceinline__ u64 warp_min_u64(u64 v) {
+#pragma unroll
+    for (int d = 16; d; d >>= 1) { u64 o = __shfl_xor_sync(0xffffffffu, v, d); v = o < v ? o : v; }
+    return v;
+}
+// positions that start a merge when the matches of (a, a) overlap: left to right, non-overlapping
+// (Tokenizer.merge, tokenizer.py:92-109: after a match the scan resumes two tokens further)
+__device__ __forceinline__ u32 resolve_heads_same(u32 m, u32 prev_head) {
+    u32 heads = 0, prev = prev_head;
+    for (int i = 0; i < 32; i++) {
+        u32 h = ((m >> i) & 1u) & (prev ^ 1u);
+        heads |= h << i;
+        prev = h;
+    }
+    return heads;
+}
+
+__device__ __forceinline__ u64 make_value(const EncTables &t, u32 n, int32_t id, u32 sym, u32 lane) {
+    // n <= 32 tokens, lane i holds id / sym of token i
+    u32 bad = __ballot_sync(0xffffffffu, lane < n && id < 0);
+    if (bad) {
+        u32 first = __ffs(bad) - 1;
+        u32 s = __shfl_sync(0xffffffffu, sym, first);
+        return (VAL_ERR << 60) | s;
+    }
+    u32 big = __ballot_sync(0xffffffffu, lane < n && (u32)id >= INLINE_ID_LIMIT);
+    if (n <= 3 && !big) {
+        u64 i0 = (u32)__shfl_sync(0xffffffffu, id, 0), i1 = (u32)__shfl_sync(0xffffffffu, id, 1), i2 = (u32)__shfl_sync(0xffffffffu, id, 2);
+        u64 v = (u64)n << 60;
+        if (n > 0) v |= i0;
+        if (n > 1) v |= i1 << 20;
+        if (n > 2) v |= i2 << 40;
+        return v;
+    }
+    u64 off = 0;
+    if (lane == 0) off = atomicAdd(&t.ctr[5], (u64)n);
+    off = __shfl_sync(0xffffffffu, off, 0);
+    if (lane < n) t.ipool[off + lane] = (u32)id;
+    return (VAL_EXT << 60) | (off << 24) | n;
+}
+
+__global__ void __launch_bounds__(256) k_enc_bpe(EncTables t, u64 n_todo) {
+    const u32 lane = lane_id();
+    const u64 gwarp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+    for (u64 q = gwarp; q < n_todo; q += nwarps) {
+        const u32 ref = t.todo[q];
+        const bool is_long = ref & REF_LONG;
+        const u32 slot = ref & ~REF_LONG;
+        u32 len; const uint8_t *p = nullptr; u64 skey = 0;
+        if (is_long) {
+            u64 m = t.lmeta[slot];
+            len = (u32)(m & META_LEN_MASK);
+            const uint8_t *src = enc_rep_ptr(t, m);
+            // move the key bytes out of the (transient) text arena into the persistent key pool
+            u64 ko = 0;
+            if (lane == 0) ko = atomicAdd(&t.ctr[4], (u64)len);
+            ko = __shfl_sync(0xffffffffu, ko, 0);
+            for (u32 i = lane; i < len; i += 32) t.kpool[ko + i] = src[i];
+            __syncwarp();
+            if (lane == 0) t.lmeta[slot] = ((ko | META_POOL_BIT) << META_LEN_BITS) | len;
+            p = t.kpool + ko;
+        } else {
+            skey = t.skey[slot];
+            len = (u32)(skey >> 56);
+        }
+        u64 value;
+        if (len <= 32) {
+            // ---- register path: lane i holds token i ----
+            u32 s = 0;
+            if (lane < len) s = is_long ? p[lane] : (u32)((skey >> (8 * lane)) & 0xFFu);
+            u32 n = len;
+            while (n > 1) {
+                u32 nxt = __shfl_down_sync(0xffffffffu, s, 1);
+                u64 r = lane + 1 < n ? rank_lookup(t, s, nxt) : RANK_NONE;
+                u64 best = warp_min_u64(r);
+                if (best == RANK_NONE) break;
+                u32 m = __ballot_sync(0xffffffffu, r == best);
+                u32 j = (u32)(best >> 32);
+                u32 heads = (t.mpairs[2 * j] == t.mpairs[2 * j + 1]) ? resolve_heads_same(m, 0) : m;
+                u32 valid = n == 32 ? 0xFFFFFFFFu : ((1u << n) - 1u);
+                u32 kept = valid & ~(heads << 1);
+                u32 val = ((heads >> lane) & 1u) ? (u32)best : s;
+                u32 src = __fns(kept, 0, lane + 1);              // lane of the (lane+1)-th kept token
+                u32 got = __shfl_sync(0xffffffffu, val, src & 31u);
+                n = __popc(kept);
+                s = lane < n ? got : 0;
+            }
+            int32_t id = lane < n ? t.sym_to_id[s] : 0;
+            value = make_value(t, n, id, s, lane);
+        } else {
+            // ---- long path: tokens in place in the id pool ----
+            u64 off = 0;
+            if (lane == 0) off = atomicAdd(&t.ctr[5], (u64)len);
+            off = __shfl_sync(0xffffffffu, off, 0);
+            u32 *w = t.ipool + off;
+            for (u32 i = lane; i < len; i += 32) w[i] = p[i];
+            __syncwarp();
+            u32 n = len;
+            while (n > 1) {
+                u64 best = RANK_NONE;
+                for (u32 base = 0; base + 1 < n; base += 32) {
+                    u32 i = base + lane;
+                    if (i + 1 < n) { u64 r = rank_lookup(t, w[i], w[i + 1]); best = r < best ? r : best; }
+                }
+                best = warp_min_u64(best);
+                if (best == RANK_NONE) break;
+                const u32 j = (u32)(best >> 32), res = (u32)best;
+                const u32 a = (u32)t.mpairs[2 * j], b = (u32)t.mpairs[2 * j + 1];
+                u32 out = 0, carry = 0;
+                for (u32 base = 0; base < n; base += 32) {
+                    u32 i = base + lane;
+                    u32 cur = i < n ? w[i] : 0xFFFFFFFFu, nx = i + 1 < n ? w[i + 1] : 0xFFFFFFFFu;
+                    u32 m = __ballot_sync(0xffffffffu, cur == a && nx == b);
+                    u32 heads = a == b ? resolve_heads_same(m, carry) : m;
+                    u32 valid = __ballot_sync(0xffffffffu, i < n);
+                    u32 kept = valid & ~((heads << 1) | carry);
+                    carry = heads >> 31;
+                    u32 val = ((heads >> lane) & 1u) ? res : cur;
+                    u32 pos = out + __popc(kept & ((1u << lane) - 1u));
+                    __syncwarp();
+                    if ((kept >> lane) & 1u) w[pos] = val;
+                    out += __popc(kept);
+                    __syncwarp();
+                }
+                n = out;
+            }
+            // ids in place; a token missing from the vocabulary is a KeyError (tokenizer.py:135)
+            u32 bad_idx = 0xFFFFFFFFu;
+            for (u32 i = lane; i < n; i += 32) if (t.sym_to_id[w[i]] < 0 && i < bad_idx) bad_idx = i;
+            for (int d = 16; d; d >>= 1) { u32 o = __shfl_xor_sync(0xffffffffu, bad_idx, d); bad_idx = o < bad_idx ? o : bad_idx; }
+            if (bad_idx != 0xFFFFFFFFu) value = (VAL_ERR << 60) | w[bad_idx];
+            else {
+                for (u32 i = lane; i < n; i += 32) w[i] = (u32)t.sym_to_id[w[i]];
+                value = (VAL_EXT << 60) | (off << 24) | n;
+            }
+        }
+        if (lane == 0) { if (is_long) t.lval[slot] = value; else t.sval[slot] = value; }
+    }
+}
+
+__device__ __forceinline__ u64 enc_value(const EncTables &t, u32 ref) {
+    return (ref & REF_LONG) ? t.lval[ref & ~REF_LONG] : t.sval[ref];
+}
+__device__ __forceinline__ u32 value_count(u64 v) {
+    u32 tag = VAL_TAG(v);
+    return tag <= 3 ? tag : (tag == VAL_EXT ? (u32)(v & 0xFFFFFFu) : 0);
+}
+
+// tokens per flag word
+__global__ void __launch_bounds__(256) k_enc_count(EncTables t, const u32 *__restrict__ flags, u64 word_begin, u64 word_end,
+                                                  const u64 *__restrict__ pre, const u32 *__restrict__ slots, u32 *__restrict__ wcnt) {
+    const u64 base_ord = pre[word_begin];
+    for (u64 w = word_begin + (u64)blockIdx.x * blockDim.x + threadIdx.x; w < word_end; w += (u64)gridDim.x * blockDim.x) {
+        u32 bits = flags[w];
+        u64 o = pre[w] - base_ord;
+        u32 c = 0;
+        while (bits) {
+            u32 j = __ffs(bits) - 1; bits &= bits - 1;
+            u64 v = enc_value(t, slots[o++]);
+            if (VAL_TAG(v) == VAL_ERR) atomicMin(&t.ctr[7], (w << 5) + j);
+            c += value_count(v);
+        }
+        wcnt[w - word_begin] = c;
+    }
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) k_enc_emit(EncTables t, const u32 *__restrict__ flags, u64 word_begin, u64 word_end,
+                                                 const u64 *__restrict__ pre, const u32 *__restrict__ slots,
+                                                 const u64 *__restrict__ woff, OutT *__restrict__ out, u64 out_base, u64 cap) {
+    const u64 base_ord = pre[word_begin];
+    for (u64 w = word_begin + (u64)blockIdx.x * blockDim.x + threadIdx.x; w < word_end; w += (u64)gridDim.x * blockDim.x) {
+        u32 bits = flags[w];
+        u64 o = pre[w] - base_ord;
+        u64 dst = out_base + woff[w - word_begin];
+        while (bits) {
+            bits &= bits - 1;
+            u64 v = enc_value(t, slots[o++]);
+            u32 tag = VAL_TAG(v);
+            if (tag <= 3) {
+                for (u32 k = 0; k < tag; k++) { if (dst < cap) out[dst] = (OutT)((v >> (20 * k)) & 0xFFFFFu); dst++; }
+            } else if (tag == VAL_EXT) {
+                const u32 *src = t.ipool + ((v >> 24) & 0xFFFFFFFFFull);
+                u32 c = (u32)(v & 0xFFFFFFu);
+                for (u32 k = 0; k < c; k++) { if (dst < cap) out[dst] = (OutT)src[k]; dst++; }
+            }
+        }
+    }
+}
+
+// ---- cache maintenance ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_enc_rehash_short(const u64 *__restrict__ okey, const u64 *__restrict__ oval, u64 ocap, EncTables t) {
+    u64 mask = t.scap - 1;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < ocap; i += (u64)gridDim.x * blockDim.x) {
+        u64 k = okey[i];
+        if (!k) continue;
+        u64 s = mix64(k) & mask;
+        for (;;) {
+            if (t.skey[s] == 0 && atomicCAS(&t.skey[s], 0ull, k) == 0) { t.sval[s] = oval[i]; break; }
+            s = (s + 1) & mask;
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_enc_rehash_long(const u64 *__restrict__ ometa, const u64 *__restrict__ ohash,
+                                                        const u64 *__restrict__ oval, u64 ocap, EncTables t) {
+    u64 mask = t.lcap - 1;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < ocap; i += (u64)gridDim.x * blockDim.x) {
+        u64 m = ometa[i];
+        if (m == META_EMPTY) continue;
+        u64 s = ohash[i] & mask;
+        for (;;) {
+            if (t.lmeta[s] == META_EMPTY && atomicCAS(&t.lmeta[s], META_EMPTY, m) == META_EMPTY) {
+                t.lhash[s] = ohash[i]; t.lval[s] = oval[i];
+                break;
+            }
+            s = (s + 1) & mask;
+        }
+    }
+}
+
+// Special tokens are pretokens of their own (tokenizer.py:119-122): pre-insert them with their id.
+// Their bytes sit at the start of the key pool (sp_offs are offsets into it).
+__global__ void k_enc_insert_specials(EncTables t, const u32 *__restrict__ sp_offs, const long long *__restrict__ sp_ids, int n_sp) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_sp) return;
+    u32 o = sp_offs[i], len = sp_offs[i + 1] - o;
+    if (len == 0) return;
+    const uint8_t *p = t.kpool + o;
+    long long id = sp_ids[i];
+    u64 v;
+    if (id < 0) v = (VAL_ERR << 60) | 0x80000000ull | (u32)i;
+    else if ((u64)id < INLINE_ID_LIMIT) v = (1ull << 60) | (u64)id;
+    else { u64 q = atomicAdd(&t.ctr[5], 1ull); t.ipool[q] = (u32)id; v = (VAL_EXT << 60) | (q << 24) | 1ull; }
+    if (len <= SHORT_MAX) {
+        u64 key = 0;
+        for (u32 k = 0; k < len; k++) key |= (u64)p[k] << (8 * k);
+        key |= (u64)len << 56;
+        u64 mask = t.scap - 1, s = mix64(key) & mask;
+        for (;;) {
+            u64 old = atomicCAS(&t.skey[s], 0ull, key);
+            if (old == 0) { atomicAdd(&t.ctr[0], 1ull); t.sval[s] = v; return; }
+            if (old == key) return;              // duplicate special
+            s = (s + 1) & mask;
+        }
+    } else {
+        u64 h = hash_long(p, len), mask = t.lcap - 1, s = h & mask;
+        u64 mine = (((u64)o | META_POOL_BIT) << META_LEN_BITS) | len;
+        for (;;) {
+            u64 old = atomicCAS(&t.lmeta[s], META_EMPTY, mine);
+            if (old == META_EMPTY) { t.lhash[s] = h; atomicAdd(&t.ctr[1], 1ull); t.lval[s] = v; return; }
+            if ((old & META_LEN_MASK) == len && bytes_equal(enc_rep_ptr(t, old), p, len)) return;
+            s = (s + 1) & mask;
+        }
+    }
+}
+
+// ---- decode ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_dec_lens(const long long *__restrict__ ids, u64 n, const u32 *__restrict__ vlen, long long n_dense,
+                                                 u32 *__restrict__ lens, u64 *__restrict__ bad) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        long long id = ids[i];
+        u32 l = (id >= 0 && id < n_dense) ? vlen[id] : 0xFFFFFFFFu;
+        if (l == 0xFFFFFFFFu) { atomicMin(bad, i); l = 0; }
+        lens[i] = l;
+    }
+}
+__global__ void __launch_bounds__(256) k_dec_copy(const long long *__restrict__ ids, u64 n, const u64 *__restrict__ voff,
+                                                 const uint8_t *__restrict__ vblob, const u32 *__restrict__ lens,
+                                                 const u64 *__restrict__ off, uint8_t *__restrict__ out, u64 cap) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        u32 l = lens[i];
+        if (!l) continue;
+        const uint8_t *src = vblob + voff[ids[i]];
+        u64 o = off[i];
+        for (u32 k = 0; k < l; k++) if (o + k < cap) out[o + k] = src[k];
+    }
+}
+
+// =============================================================================================
+// host side
+// =============================================================================================
+struct bpe_tok {
+    bpe_ctx *ctx = nullptr;
+    int n_merges = 0, n_syms = 0, n_sp = 0;
+    long long max_id = -1, n_dense = 0;
+    DevBuf mtab, mpairs, sym_to_id;              // merge tables
+    u64 mcap = 0;
+    DevBuf vlen, voff, vblob;                    // decode tables
+    DevBuf sp_offs, sp_ids;                      // specials (device); their bytes open the key pool
+    std::vector<uint8_t> sp_blob_h; std::vector<u32> sp_offs_h;
+    std::vector<uint8_t> sym_blob_h; std::vector<u64> sym_offs_h;
+    u32 sp_max_len = 0;
+    // pretoken cache
+    DevBuf skey, sval, lmeta, lhash, lval, kpool, ipool, todo, ctr;
+    u64 scap = 0, lcap = 0;
+    bool cache_ready = false;
+    std::vector<uint8_t> key_error;              // bytes of the last KeyError key
+};
+
+static int alloc_exact_e(bpe_ctx *ctx, DevBuf &b, size_t bytes) {
+    if (b.cap >= bytes && b.cap <= bytes * 2 + (1 << 20)) return BPE_OK;
+    bpe_buf_free(b);
+    cudaError_t e = cudaMalloc(&b.p, bytes ? bytes : 256);
+    if (e != cudaSuccess) { cudaGetLastError(); b.p = nullptr; return bpe_set_error(ctx, BPE_ERR_OOM, "cudaMalloc(%zu) failed", bytes); }
+    b.cap = bytes ? bytes : 256;
+    return BPE_OK;
+}
+// grow keeping the first `used` bytes
+static int grow_keep(bpe_ctx *ctx, DevBuf &b, size_t need, size_t used) {
+    if (need <= b.cap) return BPE_OK;
+    DevBuf nb;
+    BPE_TRY(bpe_buf_reserve(ctx, nb, need + need / 2));
+    if (used && b.p) {
+        cudaError_t e = cudaMemcpyAsync(nb.p, b.p, used, cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { bpe_buf_free(nb); return bpe_set_error(ctx, BPE_ERR_CUDA, "pool copy: %s", cudaGetErrorString(e)); }
+    }
+    bpe_buf_free(b);
+    b = nb;
+    return BPE_OK;
+}
+
+static EncTables enc_tables(bpe_tok *tok) {
+    EncTables t;
+    t.mtab = (const ulonglong2 *)tok->mtab.p; t.mmask = tok->mcap - 1;
+    t.mpairs = (const int32_t *)tok->mpairs.p; t.sym_to_id = (const int32_t *)tok->sym_to_id.p;
+    t.skey = (u64 *)tok->skey.p; t.sval = (u64 *)tok->sval.p; t.scap = tok->scap;
+    t.lmeta = (u64 *)tok->lmeta.p; t.lhash = (u64 *)tok->lhash.p; t.lval = (u64 *)tok->lval.p; t.lcap = tok->lcap;
+    t.text = tok->ctx->text.p ? (const uint8_t *)tok->ctx->text.p + BPE_PAD : nullptr;
+    t.kpool = (uint8_t *)tok->kpool.p; t.ipool = (u32 *)tok->ipool.p; t.todo = (u32 *)tok->todo.p;
+    t.ctr = (u64 *)tok->ctr.p;
+    return t;
+}
+
+static int cache_tables_alloc(bpe_tok *tok, u64 scap, u64 lcap) {
+    bpe_ctx *ctx = tok->ctx;
+    cudaStream_t st = ctx->stream;
+    BPE_TRY(alloc_exact_e(ctx, tok->skey, scap * 8)); BPE_TRY(alloc_exact_e(ctx, tok->sval, scap * 8));
+    BPE_TRY(alloc_exact_e(ctx, tok->lmeta, lcap * 8)); BPE_TRY(alloc_exact_e(ctx, tok->lhash, lcap * 8));
+    BPE_TRY(alloc_exact_e(ctx, tok->lval, lcap * 8));
+    CUDA_TRY(ctx, cudaMemsetAsync(tok->skey.p, 0, scap * 8, st)); CUDA_TRY(ctx, cudaMemsetAsync(tok->sval.p, 0xFF, scap * 8, st));
+    CUDA_TRY(ctx, cudaMemsetAsync(tok->lmeta.p, 0xFF, lcap * 8, st)); CUDA_TRY(ctx, cudaMemsetAsync(tok->lhash.p, 0, lcap * 8, st));
+    CUDA_TRY(ctx, cudaMemsetAsync(tok->lval.p, 0xFF, lcap * 8, st));
+    tok->scap = scap; tok->lcap = lcap;
+    return BPE_OK;
+}
+
+// (Re)initialise the pretoken cache: empty tables, the specials pre-inserted with their ids.
+static int cache_reset(bpe_tok *tok) {
+    bpe_ctx *ctx = tok->ctx;
+    cudaStream_t st = ctx->stream;
+    BPE_TRY(bpe_buf_reserve(ctx, tok->ctr, 64 * sizeof(u64)));
+    BPE_TRY(cache_tables_alloc(tok, 1 << 16, 1 << 14));
+    size_t spb = tok->sp_blob_h.size();
+    BPE_TRY(bpe_buf_reserve(ctx, tok->kpool, std::max<size_t>(spb, 1) + (1 << 20)));
+    BPE_TRY(bpe_buf_reserve(ctx, tok->ipool, ((size_t)tok->n_sp + (1 << 18)) * 4));
+    u64 *host = (u64 *)ctx->pinned;
+    for (int i = 0; i < 8; i++) host[i] = 0;
+    host[4] = spb; host[7] = ~0ull;
+    CUDA_TRY(ctx, cudaMemcpyAsync(tok->ctr.p, host, 64, cudaMemcpyHostToDevice, st));
+    if (spb) CUDA_TRY(ctx, cudaMemcpyAsync(tok->kpool.p, tok->sp_blob_h.data(), spb, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));    // host[] is reused below
+    if (tok->n_sp > 0) {
+        EncTables t = enc_tables(tok);
+        KLAUNCH(k_enc_insert_specials, (tok->n_sp + 63) / 64, 64, 0, st, t, (const u32 *)tok->sp_offs.p, (const long long *)tok->sp_ids.p, tok->n_sp);
+        CUDA_TRY(ctx, cudaGetLastError());
+    }
+    tok->cache_ready = true;
+    return BPE_OK;
+}
+
+static int cache_read_ctr(bpe_tok *tok, u64 *out, int k) {
+    bpe_ctx *ctx = tok->ctx;
+    u64 *host = (u64 *)ctx->pinned;
+    CUDA_TRY(ctx, cudaMemcpyAsync(host, tok->ctr.p, k * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < k; i++) out[i] = host[i];
+    return BPE_OK;
+}
+
+static int cache_ensure_capacity(bpe_tok *tok, u64 n_short, u64 n_long, u64 new_short, u64 new_long) {
+    bpe_ctx *ctx = tok->ctx;
+    u64 need_s = next_pow2(std::max<u64>(1 << 16, (n_short + new_short) * 8 / 7 + 64));
+    u64 need_l = next_pow2(std::max<u64>(1 << 14, (n_long + new_long) * 8 / 7 + 64));
+    if (need_s >= (1ull << 31) || need_l >= (1ull << 31)) return bpe_set_error(ctx, BPE_ERR_CAPACITY, "pretoken cache would exceed 2^31 slots");
+    if (need_s <= tok->scap && need_l <= tok->lcap) return BPE_OK;
+    need_s = std::max(need_s, tok->scap); need_l = std::max(need_l, tok->lcap);
+    DevBuf oskey = tok->skey, osval = tok->sval, olmeta = tok->lmeta, olhash = tok->lhash, olval = tok->lval;
+    u64 oscap = tok->scap, olcap = tok->lcap;
+    tok->skey = DevBuf(); tok->sval = DevBuf(); tok->lmeta = DevBuf(); tok->lhash = DevBuf(); tok->lval = DevBuf();
+    int rc = cache_tables_alloc(tok, need_s, need_l);
+    if (rc == BPE_OK) {
+        EncTables t = enc_tables(tok);
+        unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (oscap + 255) / 256);
+        KLAUNCH(k_enc_rehash_short, grid, 256, 0, ctx->stream, (const u64 *)oskey.p, (const u64 *)osval.p, oscap, t);
+        grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (olcap + 255) / 256);
+        KLAUNCH(k_enc_rehash_long, grid, 256, 0, ctx->stream, (const u64 *)olmeta.p, (const u64 *)olhash.p, (const u64 *)olval.p, olcap, t);
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = bpe_set_error(ctx, BPE_ERR_CUDA, "cache rehash: %s", cudaGetErrorString(e));
+    }
+    for (DevBuf *b : {&oskey, &osval, &olmeta, &olhash, &olval}) bpe_buf_free(*b);
+    return rc;
+}
+
+BPE_API int bpe_tok_create(bpe_ctx *ctx, const int32_t *merge_pairs, const int32_t *merge_result, int n_merges,
+                           const int32_t *sym_to_id, const uint8_t *sym_blob, const uint64_t *sym_offs, int n_syms,
+                           const uint8_t *vocab_blob, const uint64_t *vocab_offs, const int64_t *vocab_ids, int64_t n_vocab,
+                           const uint8_t *specials_blob, const uint32_t *special_offs, const int64_t *special_ids, int n_specials,
+                           bpe_tok **out) {
+    if (out) *out = nullptr;
+    if (!ctx || !out || n_merges < 0 || n_syms < 256 || !sym_to_id || !sym_offs || (n_merges > 0 && (!merge_pairs || !merge_result)) ||
+        n_vocab < 0 || (n_vocab > 0 && (!vocab_offs || !vocab_ids)) || n_specials < 0 ||
+        (n_specials > 0 && (!specials_blob || !special_offs || !special_ids)))
+        return BPE_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    for (int j = 0; j < n_merges; j++) {
+        int32_t a = merge_pairs[2 * j], b = merge_pairs[2 * j + 1];
+        if ((a < 0) != (b < 0) || a >= n_syms || b >= n_syms || (a >= 0 && (merge_result[j] < 0 || merge_result[j] >= n_syms)))
+            return bpe_set_error(ctx, BPE_ERR_ARG, "merge %d refers to a symbol outside [0, %d)", j, n_syms);
+    }
+    bpe_tok *tok = new bpe_tok();
+    tok->ctx = ctx; tok->n_merges = n_merges; tok->n_syms = n_syms; tok->n_sp = n_specials;
+    struct Guard { bpe_tok *t; bool ok = false; ~Guard() { if (!ok) bpe_tok_destroy(t); } } guard{tok};
+    cudaStream_t st = ctx->stream;
+    // merge tables
+    tok->mcap = next_pow2(std::max<u64>(1024, (u64)n_merges * 2 + 2));
+    BPE_TRY(bpe_buf_reserve(ctx, tok->mtab, tok->mcap * 16));
+    BPE_TRY(bpe_buf_reserve(ctx, tok->mpairs, std::max<size_t>((size_t)n_merges * 8, 8)));
+    BPE_TRY(bpe_buf_reserve(ctx, tok->sym_to_id, (size_t)n_syms * 4));
+    DevBuf res;
+    BPE_TRY(bpe_buf_reserve(ctx, res, std::max<size_t>((size_t)n_merges * 4, 4)));
+    struct ResGuard { DevBuf &b; ~ResGuard() { bpe_buf_free(b); } } rg{res};
+    CUDA_TRY(ctx, cudaMemsetAsync(tok->mtab.p, 0xFF, tok->mcap * 16, st));
+    if (n_merges) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(tok->mpairs.p, merge_pairs, (size_t)n_merges * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(ctx, cudaMemcpyAsync(res.p, merge_result, (size_t)n_merges * 4, cudaMemcpyHostToDevice, st));
+        KLAUNCH(k_enc_build_ranks, (n_merges + 255) / 256, 256, 0, st, (ulonglong2 *)tok->mtab.p, tok->mcap - 1, (const int32_t *)tok->mpairs.p,
+                (const int32_t *)res.p, n_merges);
+        CUDA_TRY(ctx, cudaGetLastError());
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(tok->sym_to_id.p, sym_to_id, (size_t)n_syms * 4, cudaMemcpyHostToDevice, st));
+    tok->sym_offs_h.assign(sym_offs, sym_offs + n_syms + 1);
+    if (sym_blob && sym_offs[n_syms]) tok->sym_blob_h.assign(sym_blob, sym_blob + sym_offs[n_syms]);
+    long long max_id = -1;
+    for (int s = 0; s < n_syms; s++) max_id = std::max<long long>(max_id, sym_to_id[s]);
+    // specials
+    if (n_specials) {
+        tok->sp_offs_h.assign(special_offs, special_offs + n_specials + 1);
+        tok->sp_blob_h.assign(specials_blob, specials_blob + special_offs[n_specials]);
+        for (int i = 0; i < n_specials; i++) {
+            tok->sp_max_len = std::max(tok->sp_max_len, special_offs[i + 1] - special_offs[i]);
+            max_id = std::max<long long>(max_id, special_ids[i]);
+        }
+        BPE_TRY(bpe_buf_reserve(ctx, tok->sp_offs, (size_t)(n_specials + 1) * 4));
+        BPE_TRY(bpe_buf_reserve(ctx, tok->sp_ids, (size_t)n_specials * 8));
+        CUDA_TRY(ctx, cudaMemcpyAsync(tok->sp_offs.p, special_offs, (size_t)(n_specials + 1) * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(ctx, cudaMemcpyAsync(tok->sp_ids.p, special_ids, (size_t)n_specials * 8, cudaMemcpyHostToDevice, st));
+    }
+    tok->max_id = max_id;
+    // decode tables: dense id -> (offset, length)
+    long long n_dense = 0;
+    for (int64_t i = 0; i < n_vocab; i++) {
+        if (vocab_ids[i] < 0) continue;
+        n_dense = std::max<long long>(n_dense, vocab_ids[i] + 1);
+    }
+    if (n_dense > (1ll << 28)) return bpe_set_error(ctx, BPE_ERR_UNSUPPORTED, "vocab ids up to %lld: decode table too sparse", n_dense);
+    tok->n_dense = n_dense;
+    {
+        std::vector<u32> vlen((size_t)std::max<long long>(n_dense, 1), 0xFFFFFFFFu);
+        std::vector<u64> voff((size_t)std::max<long long>(n_dense, 1), 0);
+        for (int64_t i = 0; i < n_vocab; i++) {
+            if (vocab_ids[i] < 0) continue;
+            vlen[vocab_ids[i]] = (u32)(vocab_offs[i + 1] - vocab_offs[i]);   // later entries win, like a dict
+            voff[vocab_ids[i]] = vocab_offs[i];
+        }
+        size_t vb = n_vocab ? (size_t)vocab_offs[n_vocab] : 0;
+        BPE_TRY(bpe_buf_reserve(ctx, tok->vlen, vlen.size() * 4)); BPE_TRY(bpe_buf_reserve(ctx, tok->voff, voff.size() * 8));
+        BPE_TRY(bpe_buf_reserve(ctx, tok->vblob, std::max<size_t>(vb, 1)));
+        CUDA_TRY(ctx, cudaMemcpyAsync(tok->vlen.p, vlen.data(), vlen.size() * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(ctx, cudaMemcpyAsync(tok->voff.p, voff.data(), voff.size() * 8, cudaMemcpyHostToDevice, st));
+        if (vb) CUDA_TRY(ctx, cudaMemcpyAsync(tok->vblob.p, vocab_blob, vb, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));    // the host vectors go out of scope
+    }
+    BPE_TRY(cache_reset(tok));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    guard.ok = true;
+    *out = tok;
+    return BPE_OK;
+}
+
+BPE_API void bpe_tok_destroy(bpe_tok *tok) {
+    if (!tok) return;
+    if (tok->ctx) { cudaSetDevice(tok->ctx->device); cudaStreamSynchronize(tok->ctx->stream); }
+    for (DevBuf *b : {&tok->mtab, &tok->mpairs, &tok->sym_to_id, &tok->vlen, &tok->voff, &tok->vblob, &tok->sp_offs, &tok->sp_ids,
+                      &tok->skey, &tok->sval, &tok->lmeta, &tok->lhash, &tok->lval, &tok->kpool, &tok->ipool, &tok->todo, &tok->ctr})
+        bpe_buf_free(*b);
+    delete tok;
+}
+
+BPE_API int bpe_tok_cache_reset(bpe_tok *tok) {
+    if (!tok) return BPE_ERR_ARG;
+    CUDA_TRY(tok->ctx, cudaSetDevice(tok->ctx->device));
+    BPE_TRY(cache_reset(tok));
+    CUDA_TRY(tok->ctx, cudaStreamSynchronize(tok->ctx->stream));
+    return BPE_OK;
+}
+
+BPE_API int bpe_tok_key_error(bpe_tok *tok, uint8_t *buf, uint64_t cap, uint64_t *len) {
+    if (!tok || !len) return BPE_ERR_ARG;
+    *len = tok->key_error.size();
+    if (buf) memcpy(buf, tok->key_error.data(), (size_t)std::min<u64>(cap, tok->key_error.size()));
+    return BPE_OK;
+}
+
+#define ENC_BATCH_BYTES (256ull << 20)
+#define ENC_CACHE_MAX_ENTRIES (384ull << 20)
+
+static int encode_impl(bpe_tok *tok, const uint8_t *text, u64 n, bool on_device, int out_dtype, void *out, u64 cap, uint64_t *n_out,
+                       bpe_encode_stats *stats) {
+    if (!tok || (!text && n) || !n_out || (out_dtype != BPE_DTYPE_U16 && out_dtype != BPE_DTYPE_I32)) return BPE_ERR_ARG;
+    bpe_ctx *ctx = tok->ctx;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (out_dtype == BPE_DTYPE_U16 && tok->max_id > 65535)
+        return bpe_set_error(ctx, BPE_ERR_ARG, "vocabulary ids go up to %lld: they do not fit uint16 output", tok->max_id);
+    cudaStream_t st = ctx->stream;
+    *n_out = 0;
+    if (stats) memset(stats, 0, sizeof(*stats));
+    const size_t esz = out_dtype == BPE_DTYPE_U16 ? 2 : 4;
+    EvTimer tm(ctx);
+    int e0 = tm.mark();
+    BPE_TRY(ctx_load_text(ctx, text, n, on_device));
+    int e1 = tm.mark();
+    const uint8_t *spb; const u32 *spo; u32 spmax;
+    BPE_TRY(ctx_upload_specials(ctx, tok->sp_blob_h.data(), tok->sp_offs_h.data(), tok->n_sp, &spb, &spo, &spmax));
+    u64 nn = n;
+    BPE_TRY(ctx_run_flags(ctx, &nn, false, spb, spo, tok->n_sp, spmax));
+    // ordinal of the first pretoken of every flag word
+    const u64 nw = (n + 31) / 32;
+    size_t cnt_b = round_up((nw + 1) * sizeof(u32), 256), pre_b = round_up((nw + 2) * sizeof(u64), 256);
+    BPE_TRY(bpe_buf_reserve(ctx, ctx->tmp0, cnt_b + pre_b + scan_tmp_elems_host(nw) * sizeof(u64)));
+    u32 *cnt = (u32 *)ctx->tmp0.p;
+    u64 *pre = (u64 *)((uint8_t *)ctx->tmp0.p + cnt_b);
+    u64 *scan_tmp = (u64 *)((uint8_t *)ctx->tmp0.p + cnt_b + pre_b);
+    launch_popc_words((const u32 *)ctx->flags.p, nw, cnt, ctx->sm_count, st);
+    launch_scan_u32(cnt, nw, pre, scan_tmp, st);
+    CUDA_TRY(ctx, cudaGetLastError());
+    const u64 words_per_batch = ENC_BATCH_BYTES / 32;
+    const u64 n_batches = (nw + words_per_batch - 1) / words_per_batch;
+    std::vector<u64> ord(n_batches + 1, 0);
+    for (u64 b = 0; b <= n_batches; b++) {
+        u64 w = std::min(nw, b * words_per_batch);
+        CUDA_TRY(ctx, cudaMemcpyAsync(&ord[b], pre + w, 8, cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    int e2 = tm.mark();
+    const u64 n_pretok = ord[n_batches];
+    if (!tok->cache_ready) BPE_TRY(cache_reset(tok));
+
+    // device output buffer when the caller's is on the host
+    void *out_dev = nullptr;
+    u64 dev_cap = cap;
+    if (out) {
+        if (on_device) out_dev = out;
+        else {
+            dev_cap = std::min<u64>(cap, n);                     // a token covers at least one byte
+            BPE_TRY(bpe_buf_reserve(ctx, ctx->tmp2, std::max<size_t>(dev_cap * esz, 16)));
+            out_dev = ctx->tmp2.p;
+        }
+    }
+    float ms_lookup = 0, ms_bpe = 0, ms_emit = 0;
+    u64 total_tokens = 0, new_unique = 0;
+    u64 c[8];
+    cudaEvent_t evs[4];
+    for (auto &e : evs) CUDA_TRY(ctx, cudaEventCreate(&e));
+    struct EvGuard { cudaEvent_t *e; ~EvGuard() { for (int i = 0; i < 4; i++) cudaEventDestroy(e[i]); } } evg{evs};
+    for (u64 b = 0; b < n_batches; b++) {
+        const u64 b_lo = b * words_per_batch, b_hi = std::min(nw, b_lo + words_per_batch);
+        const u64 bound = ord[b + 1] - ord[b];
+        const u64 bytes = (b_hi - b_lo) * 32;
+        BPE_TRY(cache_read_ctr(tok, c, 8));
+        if (c[0] + c[1] + bound > ENC_CACHE_MAX_ENTRIES && c[0] + c[1] > (u64)tok->n_sp) {
+            BPE_TRY(cache_reset(tok));
+            BPE_TRY(cache_read_ctr(tok, c, 8));
+        }
+        BPE_TRY(cache_ensure_capacity(tok, c[0], c[1], bound, std::min(bound, bytes / (SHORT_MAX + 1) + 1)));
+        BPE_TRY(grow_keep(ctx, tok->kpool, c[4] + bytes + 64, c[4]));
+        BPE_TRY(grow_keep(ctx, tok->ipool, (c[5] + bytes + 64) * 4, c[5] * 4));
+        BPE_TRY(bpe_buf_reserve(ctx, tok->todo, std::max<size_t>(bound * 4, 16)));
+        BPE_TRY(bpe_buf_reserve(ctx, ctx->tmp1, std::max<size_t>(bound * 4, 16)));
+        u32 *slots = (u32 *)ctx->tmp1.p;
+        CUDA_TRY(ctx, cudaMemsetAsync((u64 *)tok->ctr.p + 2, 0, 8, st));
+        EncTables t = enc_tables(tok);
+        const unsigned grid = (unsigned)std::max<u64>(1, std::min<u64>((u64)ctx->sm_count * 8, (b_hi - b_lo + 255) / 256));
+        CUDA_TRY(ctx, cudaEventRecord(evs[0], st));
+        KLAUNCH(k_enc_lookup, grid, 256, 0, st, t, (const u32 *)ctx->flags.p, n, b_lo, b_hi, pre, slots);
+        CUDA_TRY(ctx, cudaGetLastError());
+        CUDA_TRY(ctx, cudaEventRecord(evs[1], st));
+        BPE_TRY(cache_read_ctr(tok, c, 8));
+        if (c[3]) return bpe_set_error(ctx, BPE_ERR_CAPACITY, "pretoken cache overflow");
+        if (c[6]) return bpe_set_error(ctx, BPE_ERR_UNSUPPORTED, "a pretoken longer than %u bytes", MAX_TOKEN_LEN);
+        const u64 n_todo = c[2];
+        new_unique += n_todo;
+        if (n_todo) {
+            unsigned g2 = (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (n_todo + 7) / 8);
+            KLAUNCH(k_enc_bpe, g2, 256, 0, st, t, n_todo);
+            CUDA_TRY(ctx, cudaGetLastError());
+        }
+        CUDA_TRY(ctx, cudaEventRecord(evs[2], st));
+        // tokens per word -> offsets
+        const u64 bw = b_hi - b_lo;
+        size_t wc_b = round_up((bw + 1) * 4, 256), wo_b = round_up((bw + 2) * 8, 256);
+        BPE_TRY(bpe_buf_reserve(ctx, ctx->spmask, wc_b + wo_b + scan_tmp_elems_host(bw) * 8));   // spmask is free after the flags pass
+        u32 *wcnt = (u32 *)ctx->spmask.p;
+        u64 *woff = (u64 *)((uint8_t *)ctx->spmask.p + wc_b);
+        u64 *wtmp = (u64 *)((uint8_t *)ctx->spmask.p + wc_b + wo_b);
+        KLAUNCH(k_enc_count, grid, 256, 0, st, t, (const u32 *)ctx->flags.p, b_lo, b_hi, pre, slots, wcnt);
+        launch_scan_u32(wcnt, bw, woff, wtmp, st);
+        CUDA_TRY(ctx, cudaGetLastError());
+        u64 *host = (u64 *)ctx->pinned;
+        CUDA_TRY(ctx, cudaMemcpyAsync(host, woff + bw, 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaMemcpyAsync(host + 1, (u64 *)tok->ctr.p + 7, 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        const u64 batch_tokens = host[0], err_pos = host[1];
+        if (err_pos != ~0ull) {
+            // KeyError (tokenizer.py:120,135): report the key of the first failing pretoken in text order
+            u64 hv[2] = {0, 0};
+            // its value: find the slot through the ordinal of that pretoken
+            u64 w = err_pos >> 5;
+            u64 hpre = 0; u32 hflags = 0;
+            CUDA_TRY(ctx, cudaMemcpy(&hpre, pre + w, 8, cudaMemcpyDeviceToHost));
+            CUDA_TRY(ctx, cudaMemcpy(&hflags, (const u32 *)ctx->flags.p + w, 4, cudaMemcpyDeviceToHost));
+            u64 o = hpre - ord[b] + __builtin_popcount(hflags & ((1u << (err_pos & 31)) - 1u));
+            u32 ref = 0;
+            CUDA_TRY(ctx, cudaMemcpy(&ref, slots + o, 4, cudaMemcpyDeviceToHost));
+            const u64 *vp = (ref & REF_LONG) ? (const u64 *)tok->lval.p + (ref & ~REF_LONG) : (const u64 *)tok->sval.p + ref;
+            CUDA_TRY(ctx, cudaMemcpy(&hv[0], vp, 8, cudaMemcpyDeviceToHost));
+            u32 sym = (u32)hv[0];
+            tok->key_error.clear();
+            if (sym & 0x80000000u) {
+                u32 i = sym & 0x7FFFFFFFu;
+                if ((int)i < tok->n_sp) tok->key_error.assign(tok->sp_blob_h.begin() + tok->sp_offs_h[i], tok->sp_blob_h.begin() + tok->sp_offs_h[i + 1]);
+            } else if ((int)sym < tok->n_syms && !tok->sym_blob_h.empty()) {
+                tok->key_error.assign(tok->sym_blob_h.begin() + tok->sym_offs_h[sym], tok->sym_blob_h.begin() + tok->sym_offs_h[sym + 1]);
+            }
+            u64 reset7 = ~0ull;
+            CUDA_TRY(ctx, cudaMemcpy((u64 *)tok->ctr.p + 7, &reset7, 8, cudaMemcpyHostToDevice));
+            ctx->err_detail = (int64_t)err_pos;
+            return bpe_set_error(ctx, BPE_ERR_KEY, "KeyError: a token of the pretoken at byte %llu is not in the vocabulary", (unsigned long long)err_pos);
+        }
+        if (out_dev && total_tokens < dev_cap) {
+            if (out_dtype == BPE_DTYPE_U16)
+                KLAUNCH(k_enc_emit<uint16_t>, grid, 256, 0, st, t, (const u32 *)ctx->flags.p, b_lo, b_hi, pre, slots, woff, (uint16_t *)out_dev, total_tokens, dev_cap);
+            else
+                KLAUNCH(k_enc_emit<int32_t>, grid, 256, 0, st, t, (const u32 *)ctx->flags.p, b_lo, b_hi, pre, slots, woff, (int32_t *)out_dev, total_tokens, dev_cap);
+            CUDA_TRY(ctx, cudaGetLastError());
+        }
+        CUDA_TRY(ctx, cudaEventRecord(evs[3], st));
+        CUDA_TRY(ctx, cudaEventSynchronize(evs[3]));
+        float f;
+        cudaEventElapsedTime(&f, evs[0], evs[1]); ms_lookup += f;
+        cudaEventElapsedTime(&f, evs[1], evs[2]); ms_bpe += f;
+        cudaEventElapsedTime(&f, evs[2], evs[3]); ms_emit += f;
+        total_tokens += batch_tokens;
+    }
+    int e3 = tm.mark();
+    *n_out = total_tokens;
+    if (out && !on_device) {
+        u64 m = std::min(total_tokens, std::min(cap, dev_cap));
+        if (m) CUDA_TRY(ctx, cudaMemcpyAsync(out, out_dev, m * esz, cudaMemcpyDeviceToHost, st));
+    }
+    int e4 = tm.mark();
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    if (stats) {
+        stats->n_bytes = n; stats->n_pretokens = n_pretok; stats->n_tokens = total_tokens; stats->cache_new_unique = new_unique;
+        stats->ms_h2d = tm.ms(e0, e1); stats->ms_pretok = tm.ms(e1, e2); stats->ms_lookup = ms_lookup; stats->ms_bpe = ms_bpe;
+        stats->ms_emit = ms_emit; stats->ms_d2h = tm.ms(e3, e4); stats->ms_total = tm.ms(e0, e4);
+    }
+    if (out && total_tokens > cap)
+        return bpe_set_error(ctx, BPE_ERR_TOO_SMALL, "need room for %llu ids", (unsigned long long)total_tokens);
+    return BPE_OK;
+}
+
+BPE_API int bpe_encode(bpe_tok *tok, const uint8_t *text_host, uint64_t n, int out_dtype, void *out, uint64_t cap, uint64_t *n_out,
+                       bpe_encode_stats *stats) {
+    return encode_impl(tok, text_host, n, false, out_dtype, out, cap, n_out, stats);
+}
+BPE_API int bpe_encode_dev(bpe_tok *tok, const uint8_t *text_dev, uint64_t n, int out_dtype, void *out_dev, uint64_t cap, uint64_t *n_out,
+                           bpe_encode_stats *stats) {
+    return encode_impl(tok, text_dev, n, true, out_dtype, out_dev, cap, n_out, stats);
+}
+
+BPE_API int bpe_decode(bpe_tok *tok, const int64_t *ids_host, uint64_t n, uint8_t *out, uint64_t cap, uint64_t *n_out) {
+    if (!tok || (!ids_host && n) || !n_out) return BPE_ERR_ARG;
+    bpe_ctx *ctx = tok->ctx;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    *n_out = 0;
+    if (n == 0) return BPE_OK;
+    size_t ids_b = round_up(n * 8, 256), len_b = round_up((n + 1) * 4, 256), off_b = round_up((n + 2) * 8, 256);
+    BPE_TRY(bpe_buf_reserve(ctx, ctx->tmp0, ids_b + len_b + off_b + scan_tmp_elems_host(n) * 8));
+    long long *ids = (long long *)ctx->tmp0.p;
+    u32 *lens = (u32 *)((uint8_t *)ctx->tmp0.p + ids_b);
+    u64 *off = (u64 *)((uint8_t *)ctx->tmp0.p + ids_b + len_b);
+    u64 *tmp = (u64 *)((uint8_t *)ctx->tmp0.p + ids_b + len_b + off_b);
+    u64 *scr = (u64 *)ctx->scratch.p;
+    u64 *host = (u64 *)ctx->pinned;
+    host[0] = ~0ull;
+    CUDA_TRY(ctx, cudaMemcpyAsync(scr, host, 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ids, ids_host, n * 8, cudaMemcpyHostToDevice, st));
+    unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (n + 255) / 256);
+    KLAUNCH(k_dec_lens, grid, 256, 0, st, ids, n, (const u32 *)tok->vlen.p, tok->n_dense, lens, scr);
+    launch_scan_u32(lens, n, off, tmp, st);
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));    // host[0] was the upload source
+    CUDA_TRY(ctx, cudaMemcpyAsync(host, scr, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(host + 1, off + n, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    if (host[0] != ~0ull) {
+        ctx->err_detail = (int64_t)host[0];
+        return bpe_set_error(ctx, BPE_ERR_KEY, "KeyError: id at index %llu is not in the vocabulary", (unsigned long long)host[0]);
+    }
+    u64 total = host[1];
+    *n_out = total;
+    if (!out) return BPE_OK;
+    u64 m = std::min<u64>(total, cap);
+    if (m) {
+        BPE_TRY(bpe_buf_reserve(ctx, ctx->tmp1, m));
+        KLAUNCH(k_dec_copy, grid, 256, 0, st, ids, n, (const u64 *)tok->voff.p, (const uint8_t *)tok->vblob.p, lens, off, (uint8_t *)ctx->tmp1.p, m);
+        CUDA_TRY(ctx, cudaGetLastError());
+        CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->tmp1.p, m, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    }
+    return total > cap ? bpe_set_error(ctx, BPE_ERR_TOO_SMALL, "need room for %llu bytes", (unsigned long long)total) : BPE_OK;
+}
