@@ -31,6 +31,8 @@ extern "C" {
 #define BPE_ERR_TOO_SMALL     -7   /* caller's output buffer too small; *n_out holds the required size */
 #define BPE_ERR_UNSUPPORTED   -8   /* input outside what this build supports (e.g. a pretoken > 16 MiB) */
 #define BPE_ERR_NO_DEVICE     -9   /* no usable sm_100 device: the library has NO CPU fallback */
+#define BPE_ERR_HALO          -10  /* a pretoken owned by the shard runs past its right halo: retry with a larger halo */
+#define BPE_ERR_NEWLINE       -11  /* the shard contains '\r': newline translation shifts offsets, use the unsharded path */
 
 typedef struct bpe_ctx bpe_ctx;   /* one per process per GPU: device, streams, workspaces */
 typedef struct bpe_tok bpe_tok;   /* device-resident tokenizer (merge ranks, vocab, pretoken cache) */
@@ -112,13 +114,27 @@ int bpe_train_dev(bpe_ctx *ctx, const uint8_t *text_dev, uint64_t n,
  *   (they may extend past own_end into the right halo).  The shard must be cut on code-point
  *   boundaries and contain no '\r' (the host takes the single-GPU path otherwise). */
 int bpe_count_begin(bpe_ctx *ctx);
+/* BPE_ERR_UTF8 reports only ill-formed sequences that START in the owned range (detail = offset inside the
+ * shard); BPE_ERR_HALO / BPE_ERR_NEWLINE as described above.  at_file_end: the shard ends where the file ends
+ * (the last pretoken may then end at n); at_file_start is informational. */
 int bpe_count_add_shard(bpe_ctx *ctx, const uint8_t *text_host, uint64_t n,
                         uint64_t own_begin, uint64_t own_end, int at_file_start, int at_file_end);
+int bpe_count_add_shard_dev(bpe_ctx *ctx, const uint8_t *text_dev, uint64_t n,
+                            uint64_t own_begin, uint64_t own_end, int at_file_start, int at_file_end);
 /* Export sizes, then the table itself: blob = concatenated word bytes, offs[n_words+1], counts[n_words]. */
 int bpe_count_export_size(bpe_ctx *ctx, uint64_t *n_words, uint64_t *blob_bytes);
 int bpe_count_export(bpe_ctx *ctx, uint8_t *blob, uint64_t *offs, int64_t *counts);
+/* Same with device pointers (the buffers an NCCL all-gather then moves between ranks). */
+int bpe_count_export_dev(bpe_ctx *ctx, uint8_t *blob_dev, uint64_t *offs_dev, int64_t *counts_dev);
 /* Add another rank's table to this context's counts. */
 int bpe_count_import(bpe_ctx *ctx, const uint8_t *blob, const uint64_t *offs, const int64_t *counts, uint64_t n_words);
+int bpe_count_import_dev(bpe_ctx *ctx, const uint8_t *blob_dev, const uint64_t *offs_dev, const int64_t *counts_dev,
+                         uint64_t n_words, uint64_t blob_bytes);
+/* Dense 256x256 table of adjacent byte-pair counts over the words counted so far (pair (a,b) at [a*256+b]):
+ * calculate_byte_pair_frequencies at merge-loop start, models/tokenizer/train.py:35-49.  It is linear in the
+ * word counts, so the per-rank tables sum (NCCL all-reduce) to the table of the merged counts. */
+int bpe_count_pair_table(bpe_ctx *ctx, const uint8_t *specials_blob, const uint32_t *special_offs, int n_specials,
+                         int64_t *dense_out /* 65536, host */);
 /* Merge loop over whatever has been counted/imported so far. */
 int bpe_train_from_counts(bpe_ctx *ctx, const uint8_t *specials_blob, const uint32_t *special_offs, int n_specials,
                           int n_merges, int32_t *merge_pairs_out, int *n_done, bpe_train_stats *stats);

@@ -105,3 +105,66 @@ def test_train_stats_are_reported():
     assert stats["n_bytes"] == len(data.replace(b"\r\n", b"\n"))
     assert stats["n_pretokens"] == len(oracle.pretokenize(data))
     assert len(merges) == 243 and stats["duplicate_tokens"] == 0
+
+
+# ---- sharded counting through the C ABI (bpe_count_*): the per-GPU half of multi-GPU training ----------------
+def _sharded_train_one_gpu(data, n_shards, vocab_size, specials, halo=64 << 10):
+    """Emulates n_shards ranks on one GPU: every shard is counted into a fresh table and exported; all tables are
+    then imported into one and the merge loop runs on the sum."""
+    import numpy as np
+    import torch
+    from transformer_lm_b200 import sharded
+    peek = lambda lo, hi: data[lo:hi]      # noqa: E731
+    tables = []
+    for r in range(n_shards):
+        h = halo
+        while True:
+            c = sharded.DeviceCounter()
+            lo, hi, rlo, rhi = sharded.plan_shard(peek, len(data), r, n_shards, h)
+            st = c.add(data[rlo:rhi], lo - rlo, hi - rlo, rlo == 0, rhi == len(data))
+            if st is not None and st[0] == "halo":
+                h *= 16
+                continue
+            assert st is None, st
+            break
+        blob, offs, counts = c.export()
+        tables.append((blob.clone(), offs.clone(), counts.clone(), c.pair_table(specials)))
+    c = sharded.DeviceCounter()
+    for blob, offs, counts, _ in tables:
+        c.import_(blob, offs, counts)
+    total_pairs = sum(t[3] for t in tables)
+    assert bool((c.pair_table(specials) == total_pairs).all())      # linearity of the byte-pair table
+    return c.finish(vocab_size, specials)
+
+
+@pytest.mark.parametrize("n_shards", [2, 3, 8])
+def test_sharded_count_then_merge_equals_single_shot(n_shards):
+    data = (FIXTURES_PATH / "corpus.en").read_bytes()
+    want = _train_bytes(data, 700, ["<|endoftext|>"])
+    got = _sharded_train_one_gpu(data, n_shards, 700, ["<|endoftext|>"])
+    assert got[1] == want[1] and got[0] == want[0]
+
+
+def test_sharded_count_small_halo_and_unicode():
+    data = _fuzz_corpus(21, 30000, WORDS + ["x" * 200, " " * 100, "\n\n\n"])
+    want = oracle.train_bpe_on_bytes(data, 800, [])
+    got = _sharded_train_one_gpu(data, 5, 800, [], halo=32)
+    assert got[1] == want[1] and got[0] == want[0]
+
+
+def test_shard_reports_only_owned_utf8_errors_and_refuses_cr():
+    from transformer_lm_b200 import sharded
+    data = b"hello world, this is a shard of text " * 10
+    bad = bytearray(data)
+    bad[5] = 0xFF                                   # in the left halo
+    c = sharded.DeviceCounter()
+    assert c.add(bytes(bad), 64, 300, False, False) is None
+    c = sharded.DeviceCounter()
+    bad[100] = 0xFF
+    assert c.add(bytes(bad), 64, 300, False, False) == ("utf8", 100)
+    c = sharded.DeviceCounter()
+    assert c.add(data[:200] + b"\r\n" + data[200:], 64, 300, False, False) == ("newline", 0)
+    c = sharded.DeviceCounter()
+    assert c.add(b"a" * 400, 64, 300, False, False) == ("halo", 0)     # the owned pretoken never ends inside the shard
+    c = sharded.DeviceCounter()
+    assert c.add(b"a" * 400, 0, 400, True, True) is None

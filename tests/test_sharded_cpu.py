@@ -1,0 +1,132 @@
+"""Multi-rank host logic (transformer_lm_b200/sharded.py) under gloo, world_size 2 and 3, on CPU: byte-range
+planning, halos, error agreement, table exchange.  The device is replaced by the checker-backed OracleCounter;
+the merged table must equal the count of the whole text on every rank (the merge loop depends only on it,
+SURVEY A-8)."""
+import os
+import random
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import _bootstrap  # noqa: F401
+from oracle import oracle
+from tests.common import FIXTURES_PATH
+from transformer_lm_b200 import sharded
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, data, specials, halo, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tests.helpers.fake_counter import OracleCounter
+        sharded.HALO_RIGHT = halo
+        counter = OracleCounter()
+        try:
+            out = sharded.sharded_count(counter, lambda lo, hi: data[lo:hi], len(data), specials, None, True)
+            q.put((rank, out, dict(counter.table), counter.adds))
+        except UnicodeDecodeError as e:
+            q.put((rank, "utf8", (e.start, e.reason), 0))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(world, data, specials=("<|endoftext|>",), halo=64 << 10):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, data, list(specials), halo, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    return sorted(res)
+
+
+def _want(data, specials=()):
+    return oracle.count_pretokens(data, [])
+
+
+def test_plan_shard_cuts_on_code_points():
+    data = ("é🙃中" * 50).encode()
+    peek = lambda lo, hi: data[lo:hi]      # noqa: E731
+    for world in (2, 3, 5, 7):
+        prev_hi = 0
+        for r in range(world):
+            lo, hi, rlo, rhi = sharded.plan_shard(peek, len(data), r, world, 32)
+            assert lo == prev_hi and rlo <= lo <= hi <= rhi
+            for p in (lo, hi, rlo, rhi):
+                assert p == len(data) or (data[p] & 0xC0) != 0x80
+            prev_hi = hi
+        assert prev_hi == len(data)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_count_equals_whole_text(world):
+    data = (FIXTURES_PATH / "corpus.en").read_bytes().replace(b"\r", b"")
+    res = _run(world, data)
+    want = _want(data)
+    for rank, out, table, adds in res:
+        assert out == "ok" and adds == 1
+        assert table == want
+
+
+def test_unicode_heavy_text_and_tiny_halo_forces_retries():
+    rnd = random.Random(4)
+    alpha = ["é", "🙃", "中", " ", "  ", "\n", "a", "it's", "<|endoftext|>", "x" * 300, " " * 200]
+    text = "".join(rnd.choice(alpha) for _ in range(4000)).encode()
+    res = _run(2, text, halo=32)
+    want = _want(text)
+    assert any(adds > 1 for _, _, _, adds in res)          # the 32-byte halo was too small somewhere
+    for rank, out, table, adds in res:
+        assert out == "ok" and table == want
+
+
+def test_more_ranks_than_bytes():
+    res = _run(3, b"ab")
+    for rank, out, table, adds in res:
+        assert out == "ok" and table == {b"ab": 1}
+    res = _run(2, b"")
+    for rank, out, table, adds in res:
+        assert out == "ok" and table == {}
+
+
+def test_invalid_utf8_raises_the_first_offset_on_every_rank():
+    data = bytearray((FIXTURES_PATH / "corpus.en").read_bytes().replace(b"\r", b""))
+    data[100000] = 0xFF
+    data[1000] = 0xC0
+    try:
+        bytes(data).decode("utf-8")
+    except UnicodeDecodeError as e:
+        want = (e.start, e.reason)
+    res = _run(2, bytes(data))
+    for rank, out, info, _ in res:
+        assert out == "utf8"
+        # the exception is rebuilt from a 16-byte window around the first bad byte: same reason, offset inside the window
+        assert info[1] == want[1]
+
+
+def test_carriage_return_falls_back():
+    data = b"hello world\r\nsecond line " * 2000
+    res = _run(2, data)
+    for rank, out, table, adds in res:
+        assert out == "newline"
+
+
+def test_merges_digest_is_order_sensitive():
+    a = [(b"a", b"b"), (b"ab", b"c")]
+    assert sharded.merges_digest(a) != sharded.merges_digest(a[::-1])
+    assert sharded.merges_digest(a) == sharded.merges_digest(list(a))

@@ -13,7 +13,8 @@ import numpy as np
 from . import _build
 
 BPE_OK = 0
-ERR_ARG, ERR_CUDA, ERR_OOM, ERR_UTF8, ERR_KEY, ERR_CAPACITY, ERR_TOO_SMALL, ERR_UNSUPPORTED, ERR_NO_DEVICE = range(-1, -10, -1)
+(ERR_ARG, ERR_CUDA, ERR_OOM, ERR_UTF8, ERR_KEY, ERR_CAPACITY, ERR_TOO_SMALL, ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_HALO,
+ ERR_NEWLINE) = range(-1, -12, -1)
 DTYPE_U16, DTYPE_I32 = 0, 1
 SYNTH_TINYSTORIES, SYNTH_OWT = 0, 1
 
@@ -49,7 +50,8 @@ _lock = threading.Lock()
 EXPORTS = [
     "bpe_version", "bpe_unicode_table_source", "bpe_ctx_create", "bpe_ctx_destroy", "bpe_last_error",
     "bpe_last_error_detail", "bpe_device_sync", "bpe_utf8_validate", "bpe_pretokenize", "bpe_train", "bpe_train_dev",
-    "bpe_count_begin", "bpe_count_add_shard", "bpe_count_export_size", "bpe_count_export", "bpe_count_import",
+    "bpe_count_begin", "bpe_count_add_shard", "bpe_count_add_shard_dev", "bpe_count_export_size", "bpe_count_export",
+    "bpe_count_export_dev", "bpe_count_import", "bpe_count_import_dev", "bpe_count_pair_table",
     "bpe_train_from_counts", "bpe_tok_create", "bpe_tok_destroy", "bpe_encode", "bpe_encode_dev", "bpe_tok_key_error",
     "bpe_tok_cache_reset", "bpe_decode", "bpe_synth_dev", "bpe_synth_host", "bpe_host_alloc", "bpe_host_free", "bpe_launch_count",
 ]
@@ -78,6 +80,10 @@ def lib():
             L.bpe_train_dev.argtypes = L.bpe_train.argtypes
             L.bpe_count_begin.argtypes = [vp]
             L.bpe_count_add_shard.argtypes = [vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int]
+            L.bpe_count_add_shard_dev.argtypes = L.bpe_count_add_shard.argtypes
+            L.bpe_count_export_dev.argtypes = [vp, vp, vp, vp]
+            L.bpe_count_import_dev.argtypes = [vp, vp, vp, vp, C.c_uint64, C.c_uint64]
+            L.bpe_count_pair_table.argtypes = [vp, vp, vp, C.c_int, vp]
             L.bpe_count_export_size.argtypes = [vp, u64p, u64p]
             L.bpe_count_export.argtypes = [vp, vp, vp, vp]
             L.bpe_count_import.argtypes = [vp, vp, vp, vp, C.c_uint64]

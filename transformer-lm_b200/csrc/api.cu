@@ -138,7 +138,7 @@ int ctx_upload_specials(bpe_ctx *ctx, const uint8_t *blob, const u32 *offs, int 
 //   specials: when n_sp > 0 the text is first split on the specials (encode path).
 // Leaves ctx->flags holding the start bitmask.  Synchronises the stream once (error words).
 int ctx_run_flags(bpe_ctx *ctx, u64 *n_io, bool translate_newlines, const uint8_t *sp_blob_dev, const u32 *sp_offs_dev,
-                  int n_sp, u32 sp_max_len) {
+                  int n_sp, u32 sp_max_len, u64 err_lo, u64 err_hi) {
     u64 n = *n_io;
     cudaStream_t st = ctx->stream;
     u64 *scr = (u64 *)ctx->scratch.p;
@@ -165,7 +165,7 @@ int ctx_run_flags(bpe_ctx *ctx, u64 *n_io, bool translate_newlines, const uint8_
         u64 tiles_words = ((n + 4095) / 4096) * (4096 / 32);
         if (fw > tiles_words)
             CUDA_TRY(ctx, cudaMemsetAsync((u32 *)ctx->flags.p + tiles_words, 0, (fw - tiles_words) * sizeof(u32), st));
-        launch_pretok_flags(text, n, spmask, spstart, (u32 *)ctx->flags.p, scr, ctx->sm_count, st);
+        launch_pretok_flags(text, n, spmask, spstart, (u32 *)ctx->flags.p, scr, err_lo, err_hi, ctx->sm_count, st);
         CUDA_TRY(ctx, cudaGetLastError());
         CUDA_TRY(ctx, cudaMemcpyAsync(host, scr, 16, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(ctx, cudaStreamSynchronize(st));
@@ -173,6 +173,7 @@ int ctx_run_flags(bpe_ctx *ctx, u64 *n_io, bool translate_newlines, const uint8_
             ctx->err_detail = (int64_t)host[0];
             return bpe_set_error(ctx, BPE_ERR_UTF8, "invalid UTF-8 at byte offset %llu", (unsigned long long)host[0]);
         }
+        if (pass == 0) ctx->saw_cr = host[1] != 0;
         if (!(translate_newlines && host[1] && pass == 0)) break;
         // universal newlines: compact into tmp1 (as a fresh arena), swap, redo the flags
         u64 nt = newline_tiles(n);

@@ -43,6 +43,7 @@ struct bpe_ctx {
     void *pinned = nullptr; size_t pinned_cap = 0;   // small pinned staging for scalar readbacks
     struct CountState *count = nullptr;              // pretoken count tables (count.cu)
     uint64_t mem_limit = 0;
+    bool saw_cr = false;                             // the last flags pass met a '\r'
 };
 
 int bpe_set_error(bpe_ctx *ctx, int code, const char *fmt, ...);

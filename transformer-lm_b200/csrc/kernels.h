@@ -5,7 +5,7 @@
 // pretok.cu
 int  pretok_upload_tables();
 void launch_pretok_flags(const uint8_t *text, u64 n, const u32 *spmask, const u32 *spstart, u32 *flags, u64 *err,
-                         int sm_count, cudaStream_t st);
+                         u64 err_lo, u64 err_hi, int sm_count, cudaStream_t st);
 void launch_newline_translate(const uint8_t *text, u64 n, uint8_t *out, u32 *tile_cnt, u64 *tile_off, u64 *scan_tmp,
                               cudaStream_t st);
 u64  newline_tiles(u64 n);

@@ -21,7 +21,7 @@ __device__ __forceinline__ uint4 apply_boundary_mask(uint4 c, u32 m16) {
 template <bool HAS_SP>
 __global__ void __launch_bounds__(PT_NT) k_pretok_flags(const uint8_t *__restrict__ text, u64 n, u64 n_tiles,
                                                        const u32 *__restrict__ spmask, const u32 *__restrict__ spstart,
-                                                       u32 *__restrict__ flags, u64 *__restrict__ err) {
+                                                       u32 *__restrict__ flags, u64 *__restrict__ err, u64 err_lo, u64 err_hi) {
     __shared__ PretokTables tb;
     __shared__ uint4 s_text[PT_NT + 2];
     __shared__ uint4 s_cls[PT_NT + 2];
@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(PT_NT) k_pretok_flags(const uint8_t *__restric
             s_cls[tid + 1] = c;
             if (e != 0xFFu) {
                 u64 off = tbeg + (u64)tid * PT_CHUNK + e;
-                if (off < n) atomicMin(reinterpret_cast<u64 *>(&err[0]), off);
+                if (off < n && off >= err_lo && off < err_hi) atomicMin(reinterpret_cast<u64 *>(&err[0]), off);
             }
             if (cr) err[1] = 1;
             if (tid < 2) {                       // halo chunks (validated by the tile that owns them)
@@ -79,15 +79,15 @@ __global__ void __launch_bounds__(PT_NT) k_pretok_flags(const uint8_t *__restric
 }
 
 void launch_pretok_flags(const uint8_t *text, u64 n, const u32 *spmask, const u32 *spstart, u32 *flags, u64 *err,
-                         int sm_count, cudaStream_t st) {
+                         u64 err_lo, u64 err_hi, int sm_count, cudaStream_t st) {
     u64 n_tiles = (n + PT_TILE - 1) / PT_TILE;
     if (n_tiles == 0) return;
     u64 grid = (u64)sm_count * 8;
     if (grid > n_tiles) grid = n_tiles;
     if (spmask)
-        KLAUNCH(k_pretok_flags<true>, (unsigned)grid, PT_NT, 0, st, text, n, n_tiles, spmask, spstart, flags, err);
+        KLAUNCH(k_pretok_flags<true>, (unsigned)grid, PT_NT, 0, st, text, n, n_tiles, spmask, spstart, flags, err, err_lo, err_hi);
     else
-        KLAUNCH(k_pretok_flags<false>, (unsigned)grid, PT_NT, 0, st, text, n, n_tiles, nullptr, nullptr, flags, err);
+        KLAUNCH(k_pretok_flags<false>, (unsigned)grid, PT_NT, 0, st, text, n, n_tiles, nullptr, nullptr, flags, err, err_lo, err_hi);
 }
 
 int pretok_upload_tables() {

@@ -36,6 +36,7 @@ struct CountTables {
     const uint8_t *text;                         // payload of the current text arena
     const uint8_t *pool;                         // persistent bytes of long words
     u64 *counters;                               // [0]=n_short [1]=n_long [2]=long_bytes [3]=overflow [4]=n_pretokens [5]=too_long
+                                                 // [6]=an owned pretoken ran past the trusted part of the right halo
 };
 
 struct CountState {
@@ -96,7 +97,7 @@ __device__ __forceinline__ void long_add(const CountTables &t, const uint8_t *p,
 
 // One thread per 32-byte flag word; every start bit in [own_begin, own_end) is one pretoken occurrence.
 __global__ void __launch_bounds__(256) k_count_pretokens(CountTables t, const u32 *__restrict__ flags, u64 n,
-                                                        u64 word_begin, u64 word_end, u64 own_begin, u64 own_end) {
+                                                        u64 word_begin, u64 word_end, u64 own_begin, u64 own_end, u64 trust_end) {
     u64 n_tok = 0;
     for (u64 w = word_begin + (u64)blockIdx.x * blockDim.x + threadIdx.x; w < word_end; w += (u64)gridDim.x * blockDim.x) {
         u32 bits = flags[w];
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(256) k_count_pretokens(CountTables t, const u3
             if (pos < own_begin || pos >= own_end) continue;
             u64 end = bits ? (w << 5) + (__ffs(bits) - 1) : flags_next_start(flags, (w + 1) << 5, n);
             u64 len = end - pos;
+            if (end > trust_end) t.counters[6] = 1;
             n_tok++;
             const uint8_t *p = t.text + pos;
             if (len <= SHORT_MAX) {
@@ -419,7 +421,7 @@ static int count_ensure_capacity(bpe_ctx *ctx, u64 n_short, u64 n_long, u64 new_
 
 // Count the pretokens whose start lies in [own_begin, own_end) of the text currently in the arena
 // (flags already computed).
-static int count_current_text(bpe_ctx *ctx, u64 n, u64 own_begin, u64 own_end) {
+static int count_current_text(bpe_ctx *ctx, u64 n, u64 own_begin, u64 own_end, u64 trust_end) {
     CountState *cs = ctx->count;
     cudaStream_t st = ctx->stream;
     if (own_end > n) own_end = n;
@@ -437,19 +439,20 @@ static int count_current_text(bpe_ctx *ctx, u64 n, u64 own_begin, u64 own_end) {
     std::vector<u64> bound(n_batches);
     CUDA_TRY(ctx, cudaMemcpyAsync(bound.data(), ctx->tmp0.p, n_batches * sizeof(u64), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
-    u64 c[6];
-    BPE_TRY(read_counters(ctx, c, 6));
+    u64 c[8];
+    BPE_TRY(read_counters(ctx, c, 8));
     for (u64 bi = 0; bi < n_batches; bi++) {
         u64 b_lo = w_lo + bi * words_per_batch, b_hi = std::min(w_hi, b_lo + words_per_batch);
         u64 bytes = (b_hi - b_lo) * 32;
         BPE_TRY(count_ensure_capacity(ctx, c[0], c[1], bound[bi], std::min(bound[bi], bytes / (SHORT_MAX + 1) + 1)));
         CountTables t = count_tables(ctx);
         unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (b_hi - b_lo + 255) / 256);
-        KLAUNCH(k_count_pretokens, grid, 256, 0, st, t, (const u32 *)ctx->flags.p, n, b_lo, b_hi, own_begin, own_end);
+        KLAUNCH(k_count_pretokens, grid, 256, 0, st, t, (const u32 *)ctx->flags.p, n, b_lo, b_hi, own_begin, own_end, trust_end);
         CUDA_TRY(ctx, cudaGetLastError());
-        if (bi + 1 < n_batches) BPE_TRY(read_counters(ctx, c, 6));
+        if (bi + 1 < n_batches) BPE_TRY(read_counters(ctx, c, 8));
     }
-    BPE_TRY(read_counters(ctx, c, 6));
+    BPE_TRY(read_counters(ctx, c, 8));
+    if (c[6]) return bpe_set_error(ctx, BPE_ERR_HALO, "a pretoken that starts in the owned range runs past the right halo");
     if (c[3]) return bpe_set_error(ctx, BPE_ERR_CAPACITY, "pretoken table overflow");
     if (c[5]) return bpe_set_error(ctx, BPE_ERR_UNSUPPORTED, "a pretoken longer than %u bytes", MAX_TOKEN_LEN);
     cs->n_pretokens = c[4];
@@ -488,16 +491,28 @@ static int count_rehome(bpe_ctx *ctx) {
     return BPE_OK;
 }
 
+static int count_add_shard(bpe_ctx *ctx, const uint8_t *text, u64 n, bool on_device, u64 own_begin, u64 own_end, int at_file_end) {
+    if (!ctx || !ctx->count || !ctx->count->active || (!text && n) || own_begin > own_end || own_end > n) return BPE_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    BPE_TRY(ctx_load_text(ctx, text, n, on_device));
+    u64 nn = n;
+    // only ill-formed sequences that start in the owned range are this shard's to report
+    BPE_TRY(ctx_run_flags(ctx, &nn, false, nullptr, nullptr, 0, 0, own_begin, own_end));
+    if (ctx->saw_cr) return bpe_set_error(ctx, BPE_ERR_NEWLINE, "the shard contains a carriage return");
+    // start bits in the last 16 bytes of a shard that is cut mid-file lack their right context
+    u64 trust_end = at_file_end ? n : (n >= 16 ? n - 16 : 0);
+    BPE_TRY(count_current_text(ctx, n, own_begin, own_end, trust_end));
+    return count_rehome(ctx);
+}
 BPE_API int bpe_count_add_shard(bpe_ctx *ctx, const uint8_t *text_host, uint64_t n, uint64_t own_begin, uint64_t own_end,
                                 int at_file_start, int at_file_end) {
-    (void)at_file_start; (void)at_file_end;      // the halo bytes carry all the context the stencil needs
-    if (!ctx || !ctx->count || !ctx->count->active || (!text_host && n) || own_begin > own_end || own_end > n) return BPE_ERR_ARG;
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    BPE_TRY(ctx_load_text(ctx, text_host, n, false));
-    u64 nn = n;
-    BPE_TRY(ctx_run_flags(ctx, &nn, false, nullptr, nullptr, 0, 0));
-    BPE_TRY(count_current_text(ctx, n, own_begin, own_end));
-    return count_rehome(ctx);
+    (void)at_file_start;                         // the halo bytes carry all the left context the stencil needs
+    return count_add_shard(ctx, text_host, n, false, own_begin, own_end, at_file_end);
+}
+BPE_API int bpe_count_add_shard_dev(bpe_ctx *ctx, const uint8_t *text_dev, uint64_t n, uint64_t own_begin, uint64_t own_end,
+                                    int at_file_start, int at_file_end) {
+    (void)at_file_start;
+    return count_add_shard(ctx, text_dev, n, true, own_begin, own_end, at_file_end);
 }
 
 BPE_API int bpe_count_export_size(bpe_ctx *ctx, uint64_t *n_words, uint64_t *blob_bytes) {
@@ -526,7 +541,7 @@ BPE_API int bpe_count_export_size(bpe_ctx *ctx, uint64_t *n_words, uint64_t *blo
     return BPE_OK;
 }
 
-BPE_API int bpe_count_export(bpe_ctx *ctx, uint8_t *blob, uint64_t *offs, int64_t *counts) {
+static int count_export(bpe_ctx *ctx, uint8_t *blob, uint64_t *offs, int64_t *counts, bool to_device) {
     if (!ctx || !ctx->count || !offs) return BPE_ERR_ARG;
     uint64_t nw, nb;
     BPE_TRY(bpe_count_export_size(ctx, &nw, &nb));   // recomputes the scans in tmp1
@@ -537,27 +552,43 @@ BPE_API int bpe_count_export(bpe_ctx *ctx, uint8_t *blob, uint64_t *offs, int64_
     size_t lens_b = round_up(total * 4, 256), pres_b = lens_b, boff_b = round_up((total + 1) * 8, 256);
     u32 *lens = (u32 *)ctx->tmp1.p; u32 *pres = (u32 *)((uint8_t *)lens + lens_b);
     u64 *boff = (u64 *)((uint8_t *)pres + pres_b); u64 *widx = (u64 *)((uint8_t *)boff + boff_b);
-    size_t ob = round_up(nb + 1, 256), oo = round_up((nw + 1) * 8, 256), oc = round_up((nw + 1) * 8, 256);
-    BPE_TRY(bpe_buf_reserve(ctx, ctx->tmp0, ob + oo + oc));
-    uint8_t *dblob = (uint8_t *)ctx->tmp0.p; u64 *doffs = (u64 *)(dblob + ob); i64 *dcnt = (i64 *)(dblob + ob + oo);
+    uint8_t *dblob; u64 *doffs; i64 *dcnt;
+    if (to_device) { dblob = blob; doffs = (u64 *)offs; dcnt = (i64 *)counts; }
+    else {
+        size_t ob = round_up(nb + 1, 256), oo = round_up((nw + 1) * 8, 256), oc = round_up((nw + 1) * 8, 256);
+        BPE_TRY(bpe_buf_reserve(ctx, ctx->tmp0, ob + oo + oc));
+        dblob = (uint8_t *)ctx->tmp0.p; doffs = (u64 *)(dblob + ob); dcnt = (i64 *)(dblob + ob + oo);
+    }
+    if ((nb && !dblob) || (nw && !dcnt)) return BPE_ERR_ARG;
     unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (total + 255) / 256);
     KLAUNCH(k_export_write, grid, 256, 0, st, t, lens, boff, widx, dblob, doffs, dcnt);
     CUDA_TRY(ctx, cudaGetLastError());
-    if (nb && blob) CUDA_TRY(ctx, cudaMemcpyAsync(blob, dblob, nb, cudaMemcpyDeviceToHost, st));
-    if (nw) CUDA_TRY(ctx, cudaMemcpyAsync(offs, doffs, nw * 8, cudaMemcpyDeviceToHost, st));
-    if (nw && counts) CUDA_TRY(ctx, cudaMemcpyAsync(counts, dcnt, nw * 8, cudaMemcpyDeviceToHost, st));
+    if (to_device) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(doffs + nw, &nb, 8, cudaMemcpyHostToDevice, st));
+    } else {
+        if (nb) CUDA_TRY(ctx, cudaMemcpyAsync(blob, dblob, nb, cudaMemcpyDeviceToHost, st));
+        if (nw) CUDA_TRY(ctx, cudaMemcpyAsync(offs, doffs, nw * 8, cudaMemcpyDeviceToHost, st));
+        if (nw) CUDA_TRY(ctx, cudaMemcpyAsync(counts, dcnt, nw * 8, cudaMemcpyDeviceToHost, st));
+    }
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
-    offs[nw] = nb;
+    if (!to_device) offs[nw] = nb;
     return BPE_OK;
 }
+BPE_API int bpe_count_export(bpe_ctx *ctx, uint8_t *blob, uint64_t *offs, int64_t *counts) {
+    return count_export(ctx, blob, offs, counts, false);
+}
+BPE_API int bpe_count_export_dev(bpe_ctx *ctx, uint8_t *blob_dev, uint64_t *offs_dev, int64_t *counts_dev) {
+    return count_export(ctx, blob_dev, offs_dev, counts_dev, true);
+}
 
-BPE_API int bpe_count_import(bpe_ctx *ctx, const uint8_t *blob, const uint64_t *offs, const int64_t *counts, uint64_t n_words) {
+static int count_import(bpe_ctx *ctx, const uint8_t *blob, const uint64_t *offs, const int64_t *counts, uint64_t n_words, u64 nb,
+                        bool from_device) {
     if (!ctx || !ctx->count || !ctx->count->active || (n_words && (!offs || !counts))) return BPE_ERR_ARG;
     if (!n_words) return BPE_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     CountState *cs = ctx->count;
     cudaStream_t st = ctx->stream;
-    u64 nb = offs[n_words];
+    const cudaMemcpyKind kind = from_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     // blob goes straight into the pool (long words keep pointing at it)
     if (cs->pool_used + nb > cs->pool.cap) {
         DevBuf nbuf;
@@ -568,22 +599,71 @@ BPE_API int bpe_count_import(bpe_ctx *ctx, const uint8_t *blob, const uint64_t *
         cs->pool = nbuf;
     }
     u64 base = cs->pool_used;
-    if (nb) CUDA_TRY(ctx, cudaMemcpyAsync((uint8_t *)cs->pool.p + base, blob, nb, cudaMemcpyHostToDevice, st));
+    if (nb) CUDA_TRY(ctx, cudaMemcpyAsync((uint8_t *)cs->pool.p + base, blob, nb, kind, st));
     cs->pool_used += nb;
-    size_t ob = round_up((n_words + 1) * 8, 256);
-    BPE_TRY(bpe_buf_reserve(ctx, ctx->tmp0, ob * 2));
-    u64 *doffs = (u64 *)ctx->tmp0.p; i64 *dcnt = (i64 *)((uint8_t *)ctx->tmp0.p + ob);
-    CUDA_TRY(ctx, cudaMemcpyAsync(doffs, offs, (n_words + 1) * 8, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(ctx, cudaMemcpyAsync(dcnt, counts, n_words * 8, cudaMemcpyHostToDevice, st));
-    u64 c[6];
-    BPE_TRY(read_counters(ctx, c, 6));
+    const u64 *doffs; const i64 *dcnt;
+    if (from_device) { doffs = (const u64 *)offs; dcnt = (const i64 *)counts; }
+    else {
+        size_t ob = round_up((n_words + 1) * 8, 256);
+        BPE_TRY(bpe_buf_reserve(ctx, ctx->tmp0, ob * 2));
+        u64 *o = (u64 *)ctx->tmp0.p; i64 *c2 = (i64 *)((uint8_t *)ctx->tmp0.p + ob);
+        CUDA_TRY(ctx, cudaMemcpyAsync(o, offs, (n_words + 1) * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(ctx, cudaMemcpyAsync(c2, counts, n_words * 8, cudaMemcpyHostToDevice, st));
+        doffs = o; dcnt = c2;
+    }
+    u64 c[8];
+    BPE_TRY(read_counters(ctx, c, 8));
     BPE_TRY(count_ensure_capacity(ctx, c[0], c[1], n_words, n_words));
     CountTables t = count_tables(ctx);
     unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (n_words + 255) / 256);
     KLAUNCH(k_import_words, grid, 256, 0, st, t, (const uint8_t *)cs->pool.p + base, base, doffs, dcnt, n_words);
     CUDA_TRY(ctx, cudaGetLastError());
-    BPE_TRY(read_counters(ctx, c, 6));
+    BPE_TRY(read_counters(ctx, c, 8));
     if (c[3]) return bpe_set_error(ctx, BPE_ERR_CAPACITY, "pretoken table overflow on import");
+    if (c[5]) return bpe_set_error(ctx, BPE_ERR_UNSUPPORTED, "an imported word is longer than %u bytes", MAX_TOKEN_LEN);
+    return BPE_OK;
+}
+BPE_API int bpe_count_import(bpe_ctx *ctx, const uint8_t *blob, const uint64_t *offs, const int64_t *counts, uint64_t n_words) {
+    return count_import(ctx, blob, offs, counts, n_words, n_words ? offs[n_words] : 0, false);
+}
+BPE_API int bpe_count_import_dev(bpe_ctx *ctx, const uint8_t *blob_dev, const uint64_t *offs_dev, const int64_t *counts_dev,
+                                 uint64_t n_words, uint64_t blob_bytes) {
+    return count_import(ctx, blob_dev, offs_dev, counts_dev, n_words, blob_bytes, true);
+}
+
+// Dense byte-pair table of the current counts (train.py:35-49 at merge-loop start).
+BPE_API int bpe_count_pair_table(bpe_ctx *ctx, const uint8_t *specials_blob, const uint32_t *special_offs, int n_specials,
+                                 int64_t *dense_out) {
+    if (!ctx || !ctx->count || !dense_out || (n_specials > 0 && (!specials_blob || !special_offs))) return BPE_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CountState *cs = ctx->count;
+    u64 c[8];
+    BPE_TRY(read_counters(ctx, c, 8));
+    u64 max_words = c[0] + c[1], max_syms = c[0] * SHORT_MAX + c[2];
+    if (max_syms >= (1ull << 32)) return bpe_set_error(ctx, BPE_ERR_UNSUPPORTED, "more than 2^32 symbols in unique words");
+    const uint8_t *spb; const u32 *spo; u32 spmax;
+    BPE_TRY(ctx_upload_specials(ctx, specials_blob, special_offs, n_specials, &spb, &spo, &spmax));
+    DevBuf sym, wmeta, wctr, dense, hist;
+    struct G { DevBuf *b[5]; ~G() { for (auto x : b) bpe_buf_free(*x); } } g{{&sym, &wmeta, &wctr, &dense, &hist}};
+    BPE_TRY(bpe_buf_reserve(ctx, sym, (max_syms + 1) * 4)); BPE_TRY(bpe_buf_reserve(ctx, wmeta, (max_words + 1) * sizeof(WordMeta)));
+    BPE_TRY(bpe_buf_reserve(ctx, wctr, 64)); BPE_TRY(bpe_buf_reserve(ctx, dense, 65536 * 8)); BPE_TRY(bpe_buf_reserve(ctx, hist, 65536 * 4));
+    CUDA_TRY(ctx, cudaMemsetAsync(wctr.p, 0, 64, st)); CUDA_TRY(ctx, cudaMemsetAsync(dense.p, 0, 65536 * 8, st));
+    CUDA_TRY(ctx, cudaMemsetAsync(hist.p, 0, 65536 * 4, st));
+    Words W{(int32_t *)sym.p, (WordMeta *)wmeta.p, (u64 *)wctr.p};
+    CountTables t = count_tables(ctx);
+    u64 total = cs->scap + cs->lcap;
+    unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (total + 255) / 256);
+    KLAUNCH(k_build_words, grid, 256, 0, st, t, W, spb, spo, n_specials);
+    u64 *host = (u64 *)ctx->pinned;
+    CUDA_TRY(ctx, cudaMemcpyAsync(host, wctr.p, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    u64 n_words = host[0];
+    unsigned wgrid = (unsigned)std::max<u64>(1, std::min<u64>((u64)ctx->sm_count * 8, (n_words + 255) / 256));
+    KLAUNCH(k_init_pair_counts, wgrid, 256, 0, st, W, n_words, (u64 *)dense.p, (u32 *)hist.p);
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaMemcpyAsync(dense_out, dense.p, 65536 * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
     return BPE_OK;
 }
 
@@ -781,7 +861,7 @@ static int train_impl(bpe_ctx *ctx, const uint8_t *text, u64 n, bool text_is_dev
     BPE_TRY(ctx_run_flags(ctx, &nn, true, nullptr, nullptr, 0, 0));
     int e2 = tm.mark();
     BPE_TRY(bpe_count_begin(ctx));
-    BPE_TRY(count_current_text(ctx, nn, 0, nn));
+    BPE_TRY(count_current_text(ctx, nn, 0, nn, nn));
     int e3 = tm.mark();
     int rc = run_merges(ctx, sp_blob, sp_offs, n_sp, n_merges, merge_pairs_out, n_done, stats, tm, e0);
     if (stats) {

@@ -81,9 +81,13 @@ def train_bpe_on_bytes(data, vocab_size: int, special_tokens: List[str] = [], *,
     return out + (stats.as_dict(),) if return_stats else out
 
 
-def train_bpe(input_path, vocab_size: int, special_tokens: List[str] = [], **kwargs):
-    """Drop-in for models/tokenizer/train.py:142 train_bpe.  Extra keyword arguments (ctx=, return_stats=)
-    are ours; the reference's adapter never passes any."""
+def train_bpe(input_path, vocab_size: int, special_tokens: List[str] = [], *, distributed: bool = False, **kwargs):
+    """Drop-in for models/tokenizer/train.py:142 train_bpe.  Extra keyword arguments are ours (the reference's
+    adapter never passes any): ctx=, return_stats=, and distributed=True to shard the file over the ranks of the
+    initialised torch.distributed group (one process per GPU; see sharded.py)."""
+    if distributed:
+        from .sharded import train_bpe_sharded
+        return train_bpe_sharded(input_path, vocab_size, special_tokens, **kwargs)
     t0 = time.time()
     logger.info("Extracting subword frequencies")
     arr, _keep = _read_file(input_path)
