@@ -47,6 +47,9 @@ const char *bpe_last_error(bpe_ctx *ctx);
 /* Numeric detail of the last error (UTF-8 error offset, offending id, ...). */
 int64_t bpe_last_error_detail(bpe_ctx *ctx);
 int  bpe_device_sync(bpe_ctx *ctx);
+/* Run all of this context's work on the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream) so
+ * that the caller's events and collectives order with it; NULL restores the context's own stream. */
+int  bpe_ctx_set_stream(bpe_ctx *ctx, void *cuda_stream);
 /* Number of CUDA kernels this library has launched in this process (bench.py reports it as gpu_launches). */
 unsigned long long bpe_launch_count(void);
 /* Page-locked host memory for inputs/outputs (H2D / D2H copies from it run at PCIe speed). */
@@ -78,6 +81,7 @@ typedef struct bpe_train_stats {
     uint64_t n_pairs_final;      /* pair-table keys ever created */
     uint64_t log_records;        /* inverted-index records written by the merge loop */
     uint64_t duplicate_tokens;   /* merges whose product bytes already existed (SURVEY A-6); 0 expected */
+    uint64_t sum_live_pairs;     /* sum over merge steps of the live pair-table keys (what the reference's max() scans) */
     float ms_h2d;                /* host->device copy of the text */
     float ms_validate;           /* UTF-8 validation + CR scan */
     float ms_pretok;             /* boundary-flag kernel */
@@ -197,6 +201,9 @@ int bpe_decode(bpe_tok *tok, const int64_t *ids_host, uint64_t n, uint8_t *out, 
  * the CPU (same code compiled for the host) so CPU oracles can be fed the same input. */
 int bpe_synth_dev(bpe_ctx *ctx, int shape, uint64_t seed, uint8_t *out_dev, uint64_t n);
 int bpe_synth_host(int shape, uint64_t seed, uint8_t *out_host, uint64_t n);
+/* Same, starting at 4096-byte block `first_block` of the corpus (a rank generates only its shard). */
+int bpe_synth_dev_at(bpe_ctx *ctx, int shape, uint64_t seed, uint64_t first_block, uint8_t *out_dev, uint64_t n);
+int bpe_synth_host_at(int shape, uint64_t seed, uint64_t first_block, uint8_t *out_host, uint64_t n);
 
 #ifdef __cplusplus
 }

@@ -165,6 +165,9 @@ def test_shard_reports_only_owned_utf8_errors_and_refuses_cr():
     c = sharded.DeviceCounter()
     assert c.add(data[:200] + b"\r\n" + data[200:], 64, 300, False, False) == ("newline", 0)
     c = sharded.DeviceCounter()
-    assert c.add(b"a" * 400, 64, 300, False, False) == ("halo", 0)     # the owned pretoken never ends inside the shard
+    long_tail = b"x" * 90 + b" " + b"a" * 309                           # " aaa..." starts at 90 (owned) and never ends
+    assert c.add(long_tail, 64, 300, False, False) == ("halo", 0)
     c = sharded.DeviceCounter()
-    assert c.add(b"a" * 400, 0, 400, True, True) is None
+    assert c.add(b"a" * 400, 64, 300, False, False) is None             # its only pretoken starts at 0: not owned
+    c = sharded.DeviceCounter()
+    assert c.add(long_tail, 0, 400, True, True) is None

@@ -34,7 +34,7 @@ def _worker(rank, world, port, data, specials, halo, q):
         sharded.HALO_RIGHT = halo
         counter = OracleCounter()
         try:
-            out = sharded.sharded_count(counter, lambda lo, hi: data[lo:hi], len(data), specials, None, True)
+            out = sharded.sharded_count(counter, sharded.FileShards(lambda lo, hi: data[lo:hi], len(data)), specials, None, True)
             q.put((rank, out, dict(counter.table), counter.adds))
         except UnicodeDecodeError as e:
             q.put((rank, "utf8", (e.start, e.reason), 0))

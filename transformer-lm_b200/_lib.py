@@ -28,7 +28,7 @@ class BpeError(RuntimeError):
 
 class TrainStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("n_bytes", "n_pretokens", "n_unique", "n_symbols", "n_pairs_initial",
-                                          "n_pairs_final", "log_records", "duplicate_tokens")] + \
+                                          "n_pairs_final", "log_records", "duplicate_tokens", "sum_live_pairs")] + \
                [(n, C.c_float) for n in ("ms_h2d", "ms_validate", "ms_pretok", "ms_count", "ms_build", "ms_merge", "ms_total")]
 
     def as_dict(self):
@@ -53,7 +53,7 @@ EXPORTS = [
     "bpe_count_begin", "bpe_count_add_shard", "bpe_count_add_shard_dev", "bpe_count_export_size", "bpe_count_export",
     "bpe_count_export_dev", "bpe_count_import", "bpe_count_import_dev", "bpe_count_pair_table",
     "bpe_train_from_counts", "bpe_tok_create", "bpe_tok_destroy", "bpe_encode", "bpe_encode_dev", "bpe_tok_key_error",
-    "bpe_tok_cache_reset", "bpe_decode", "bpe_synth_dev", "bpe_synth_host", "bpe_host_alloc", "bpe_host_free", "bpe_launch_count",
+    "bpe_tok_cache_reset", "bpe_decode", "bpe_synth_dev", "bpe_synth_host", "bpe_synth_dev_at", "bpe_synth_host_at", "bpe_ctx_set_stream", "bpe_host_alloc", "bpe_host_free", "bpe_launch_count",
 ]
 
 
@@ -99,6 +99,9 @@ def lib():
             L.bpe_decode.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, u64p]
             L.bpe_synth_dev.argtypes = [vp, C.c_int, C.c_uint64, vp, C.c_uint64]
             L.bpe_synth_host.argtypes = [C.c_int, C.c_uint64, vp, C.c_uint64]
+            L.bpe_synth_dev_at.argtypes = [vp, C.c_int, C.c_uint64, C.c_uint64, vp, C.c_uint64]
+            L.bpe_synth_host_at.argtypes = [C.c_int, C.c_uint64, C.c_uint64, vp, C.c_uint64]
+            L.bpe_ctx_set_stream.argtypes = [vp, vp]
             L.bpe_host_alloc.argtypes = [C.c_size_t]
             L.bpe_host_alloc.restype = vp
             L.bpe_host_free.argtypes = [vp]
@@ -162,6 +165,10 @@ class Context:
         if rc != BPE_OK:
             msg = lib().bpe_last_error(self._h)
             raise BpeError(rc, msg.decode("utf-8", "replace") if msg else "", lib().bpe_last_error_detail(self._h))
+
+    def use_stream(self, cuda_stream: int | None):
+        """Enqueue all library work on this CUDA stream (e.g. torch.cuda.current_stream().cuda_stream)."""
+        self.check(lib().bpe_ctx_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
 
     def close(self):
         if self._h:

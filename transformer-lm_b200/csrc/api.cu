@@ -16,27 +16,54 @@ int bpe_set_error(bpe_ctx *ctx, int code, const char *fmt, ...) {
     return code;
 }
 
-int bpe_buf_reserve(bpe_ctx *ctx, DevBuf &b, size_t bytes) {
-    if (bytes <= b.cap) return BPE_OK;
-    if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
-    size_t want = round_up(bytes + bytes / 8, 1 << 20);
-    cudaError_t e = cudaMalloc(&b.p, want);
-    if (e != cudaSuccess) {
+static size_t pool_round(size_t bytes) { return bytes <= (1 << 20) ? round_up(bytes ? bytes : 1, 4096) : round_up(bytes, 1 << 20); }
+
+static int pool_take(bpe_ctx *ctx, DevBuf &out, size_t want) {
+    // smallest cached buffer that fits without wasting more than half
+    int best = -1;
+    for (int i = 0; i < (int)ctx->pool.size(); i++) {
+        size_t c = ctx->pool[i].cap;
+        if (c >= want && c <= 2 * want + (1 << 20) && (best < 0 || c < ctx->pool[best].cap)) best = i;
+    }
+    if (best >= 0) { out = ctx->pool[best]; ctx->pool.erase(ctx->pool.begin() + best); return BPE_OK; }
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {                       // give the cached buffers back to the driver and retry once
         cudaGetLastError();
-        want = round_up(bytes, 1 << 16);
-        e = cudaMalloc(&b.p, want);
+        bpe_pool_trim(ctx);
+        e = cudaMalloc(&p, want);
     }
     if (e != cudaSuccess) {
         cudaGetLastError();
-        b.p = nullptr;
         return bpe_set_error(ctx, BPE_ERR_OOM, "cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
     }
-    b.cap = want;
+    out.p = p; out.cap = want;
     return BPE_OK;
 }
-void bpe_buf_free(DevBuf &b) {
-    if (b.p) cudaFree(b.p);
+
+void bpe_pool_trim(bpe_ctx *ctx) {
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto &b : ctx->pool) if (b.p) cudaFree(b.p);
+    ctx->pool.clear();
+}
+
+void bpe_buf_free(bpe_ctx *ctx, DevBuf &b) {
+    if (!b.p) { b.cap = 0; return; }
+    if (ctx) ctx->pool.push_back(b); else cudaFree(b.p);
     b.p = nullptr; b.cap = 0;
+}
+
+int bpe_buf_reserve(bpe_ctx *ctx, DevBuf &b, size_t bytes) {
+    if (bytes <= b.cap) return BPE_OK;
+    bpe_buf_free(ctx, b);
+    return pool_take(ctx, b, pool_round(bytes + bytes / 8));
+}
+
+int bpe_buf_alloc(bpe_ctx *ctx, DevBuf &b, size_t bytes) {
+    size_t want = pool_round(bytes);
+    if (b.cap >= want && b.cap <= 2 * want + (1 << 20)) return BPE_OK;
+    bpe_buf_free(ctx, b);
+    return pool_take(ctx, b, want);
 }
 
 BPE_API int bpe_version(void) { return 100; }
@@ -55,7 +82,8 @@ BPE_API int bpe_ctx_create(int device, bpe_ctx **out) {
     bpe_ctx *ctx = new bpe_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return BPE_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return BPE_ERR_CUDA; }
+    ctx->stream = ctx->own_stream;
     for (auto &e : ctx->ev) cudaEventCreate(&e);
     if (pretok_upload_tables() != 0) { delete ctx; return BPE_ERR_CUDA; }
     if (cudaMallocHost(&ctx->pinned, 1 << 16) != cudaSuccess) { delete ctx; return BPE_ERR_OOM; }
@@ -72,11 +100,12 @@ BPE_API void bpe_ctx_destroy(bpe_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     count_state_free(ctx);
-    bpe_buf_free(ctx->text); bpe_buf_free(ctx->flags); bpe_buf_free(ctx->spmask); bpe_buf_free(ctx->spstart);
-    bpe_buf_free(ctx->scratch); bpe_buf_free(ctx->tmp0); bpe_buf_free(ctx->tmp1); bpe_buf_free(ctx->tmp2);
+    for (DevBuf *b : {&ctx->text, &ctx->flags, &ctx->spmask, &ctx->spstart, &ctx->scratch, &ctx->tmp0, &ctx->tmp1, &ctx->tmp2})
+        bpe_buf_free(ctx, *b);
+    bpe_pool_trim(ctx);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
 
@@ -86,6 +115,14 @@ BPE_API int bpe_device_sync(bpe_ctx *ctx) {
     if (!ctx) return BPE_ERR_ARG;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return BPE_OK;
+}
+
+BPE_API int bpe_ctx_set_stream(bpe_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return BPE_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
     return BPE_OK;
 }
 

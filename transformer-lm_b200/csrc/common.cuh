@@ -29,7 +29,8 @@ struct DevBuf {
 struct bpe_ctx {
     int device = 0;
     int sm_count = 148;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;                   // stream in use
+    cudaStream_t own_stream = nullptr;               // the one the context created
     cudaEvent_t ev[16] = {};
     std::string err;
     int64_t err_detail = 0;
@@ -43,12 +44,17 @@ struct bpe_ctx {
     void *pinned = nullptr; size_t pinned_cap = 0;   // small pinned staging for scalar readbacks
     struct CountState *count = nullptr;              // pretoken count tables (count.cu)
     uint64_t mem_limit = 0;
+    std::vector<DevBuf> pool;                        // cached free device buffers
     bool saw_cr = false;                             // the last flags pass met a '\r'
 };
 
 int bpe_set_error(bpe_ctx *ctx, int code, const char *fmt, ...);
-int bpe_buf_reserve(bpe_ctx *ctx, DevBuf &b, size_t bytes);
-void bpe_buf_free(DevBuf &b);
+// Device buffers come from a per-context caching pool: cudaMalloc / cudaFree cost milliseconds per GB and
+// synchronise the device, and every call of the library asks for the same sizes again.
+int bpe_buf_reserve(bpe_ctx *ctx, DevBuf &b, size_t bytes);       // grow-only, contents NOT preserved
+int bpe_buf_alloc(bpe_ctx *ctx, DevBuf &b, size_t bytes);         // (re)size to about `bytes` (may shrink), contents NOT preserved
+void bpe_buf_free(bpe_ctx *ctx, DevBuf &b);                       // back to the pool
+void bpe_pool_trim(bpe_ctx *ctx);                                 // cudaFree everything cached
 
 #define CUDA_TRY(ctx, expr)                                                                      \
     do {                                                                                         \

@@ -469,14 +469,7 @@ struct bpe_tok {
     std::vector<uint8_t> key_error;              // bytes of the last KeyError key
 };
 
-static int alloc_exact_e(bpe_ctx *ctx, DevBuf &b, size_t bytes) {
-    if (b.cap >= bytes && b.cap <= bytes * 2 + (1 << 20)) return BPE_OK;
-    bpe_buf_free(b);
-    cudaError_t e = cudaMalloc(&b.p, bytes ? bytes : 256);
-    if (e != cudaSuccess) { cudaGetLastError(); b.p = nullptr; return bpe_set_error(ctx, BPE_ERR_OOM, "cudaMalloc(%zu) failed", bytes); }
-    b.cap = bytes ? bytes : 256;
-    return BPE_OK;
-}
+static int alloc_exact_e(bpe_ctx *ctx, DevBuf &b, size_t bytes) { return bpe_buf_alloc(ctx, b, bytes ? bytes : 256); }
 // grow keeping the first `used` bytes
 static int grow_keep(bpe_ctx *ctx, DevBuf &b, size_t need, size_t used) {
     if (need <= b.cap) return BPE_OK;
@@ -485,9 +478,9 @@ static int grow_keep(bpe_ctx *ctx, DevBuf &b, size_t need, size_t used) {
     if (used && b.p) {
         cudaError_t e = cudaMemcpyAsync(nb.p, b.p, used, cudaMemcpyDeviceToDevice, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) { bpe_buf_free(nb); return bpe_set_error(ctx, BPE_ERR_CUDA, "pool copy: %s", cudaGetErrorString(e)); }
+        if (e != cudaSuccess) { bpe_buf_free(ctx, nb); return bpe_set_error(ctx, BPE_ERR_CUDA, "pool copy: %s", cudaGetErrorString(e)); }
     }
-    bpe_buf_free(b);
+    bpe_buf_free(ctx, b);
     b = nb;
     return BPE_OK;
 }
@@ -571,7 +564,7 @@ static int cache_ensure_capacity(bpe_tok *tok, u64 n_short, u64 n_long, u64 new_
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) rc = bpe_set_error(ctx, BPE_ERR_CUDA, "cache rehash: %s", cudaGetErrorString(e));
     }
-    for (DevBuf *b : {&oskey, &osval, &olmeta, &olhash, &olval}) bpe_buf_free(*b);
+    for (DevBuf *b : {&oskey, &osval, &olmeta, &olhash, &olval}) bpe_buf_free(ctx, *b);
     return rc;
 }
 
@@ -602,7 +595,7 @@ BPE_API int bpe_tok_create(bpe_ctx *ctx, const int32_t *merge_pairs, const int32
     BPE_TRY(bpe_buf_reserve(ctx, tok->sym_to_id, (size_t)n_syms * 4));
     DevBuf res;
     BPE_TRY(bpe_buf_reserve(ctx, res, std::max<size_t>((size_t)n_merges * 4, 4)));
-    struct ResGuard { DevBuf &b; ~ResGuard() { bpe_buf_free(b); } } rg{res};
+    struct ResGuard { bpe_ctx *c; DevBuf &b; ~ResGuard() { bpe_buf_free(c, b); } } rg{ctx, res};
     CUDA_TRY(ctx, cudaMemsetAsync(tok->mtab.p, 0xFF, tok->mcap * 16, st));
     if (n_merges) {
         CUDA_TRY(ctx, cudaMemcpyAsync(tok->mpairs.p, merge_pairs, (size_t)n_merges * 8, cudaMemcpyHostToDevice, st));
@@ -666,7 +659,7 @@ BPE_API void bpe_tok_destroy(bpe_tok *tok) {
     if (tok->ctx) { cudaSetDevice(tok->ctx->device); cudaStreamSynchronize(tok->ctx->stream); }
     for (DevBuf *b : {&tok->mtab, &tok->mpairs, &tok->sym_to_id, &tok->vlen, &tok->voff, &tok->vblob, &tok->sp_offs, &tok->sp_ids,
                       &tok->skey, &tok->sval, &tok->lmeta, &tok->lhash, &tok->lval, &tok->kpool, &tok->ipool, &tok->todo, &tok->ctr})
-        bpe_buf_free(*b);
+        bpe_buf_free(tok->ctx, *b);
     delete tok;
 }
 

@@ -78,7 +78,8 @@ struct MergeState {
     Best *cta_best;
     int32_t *merges_out; i64 *merge_cnt_out; int n_merges;
     // [0]=log cursor [1]=n_done (next step) [2]=pair keys created [3]=status flags [4]=tok bytes cursor
-    // [6]=previous winner key still to be popped (PAIR_EMPTY if none)
+    // [5]=keys popped since the table was last rebuilt [6]=previous winner key still to be popped (PAIR_EMPTY if none)
+    // [7]=sum over steps of the live pair-table keys (the reference's max() scans that many dict entries, train.py:187-189)
     u64 *ctr;
     // profile (ns / counts): [0]=phase1 [1]=sync1 [2]=apply [3]=sync2 on CTA 0; [4]=token CTA work; [5]=index records scanned;
     // [6]=words rewritten; [7]=steps; [9]=dirty blocks rescanned
@@ -368,6 +369,7 @@ __global__ void __launch_bounds__(MG_NT) k_merge_loop() {
                     cM.merges_out[2 * step] = (int32_t)a; cM.merges_out[2 * step + 1] = (int32_t)b;
                     cM.merge_cnt_out[step] = win.cnt;
                     cM.ctr[1] = (u64)(step + 1);
+                    cM.ctr[7] += s_status[1] - cM.ctr[5]; cM.ctr[5] += 1;
                     if (prof_thread) { cM.prof[10] += tA - t2; cM.prof[11] += tB - tA; cM.prof[12] += gtime_ns() - tB; }
                 }
             }

@@ -9,7 +9,7 @@
 // TinyStories shape: 2^15 lowercase word types, Zipf-like (log-uniform magnitude, biased to the head),
 //   short sentences, dialogue in curly and straight quotes, contractions, "\n" paragraphs,
 //   documents separated by "\n<|endoftext|>\n".
-// OWT shape: 2^22 word types with a long tail, mixed case, numbers, URLs / e-mails / hashtags,
+// OWT shape: 2^21 word types with a long tail, mixed case, numbers, URLs / e-mails / hashtags,
 //   ~1.5 % non-ASCII (Latin-1 accents, Cyrillic, CJK, emoji, NBSP / thin space), "\n\n" paragraphs,
 //   occasional space / tab runs and trailing spaces, documents separated by "<|endoftext|>".
 #pragma once
@@ -79,7 +79,7 @@ SYNTH_HD void synth_spell(SynthOut &o, uint32_t k, uint32_t salt, bool capital, 
 SYNTH_HD void synth_number(SynthOut &o, SynthRng &r) {
     uint32_t kind = synth_below(r, 4);
     char buf[12]; int n = 0;
-    uint32_t v = kind == 0 ? 1900 + synth_below(r, 130) : kind == 1 ? synth_below(r, 100) : synth_below(r, 1000000);
+    uint32_t v = kind == 0 ? 1900 + synth_below(r, 130) : kind == 1 ? synth_below(r, 100) : kind == 2 ? synth_below(r, 1000) : synth_word_id(r, 20, false);
     do { buf[n++] = (char)('0' + v % 10); v /= 10; } while (v);
     for (int i = n - 1; i >= 0; i--) {
         synth_put(o, (uint8_t)buf[i]);
@@ -93,7 +93,7 @@ SYNTH_HD void synth_block(int shape, uint64_t seed, uint64_t block, uint8_t *dst
     SynthRng r; r.s = synth_mix(seed ^ synth_mix(block * 2 + (uint64_t)shape));
     SynthOut o; o.p = dst; o.pos = 0; o.limit = limit;
     const bool owt = shape == 1;
-    const uint32_t bits = owt ? 22 : 15;
+    const uint32_t bits = owt ? 21 : 15;
     const uint32_t salt = owt ? 0x4f57u : 0x5453u;
     // documents: separators at a quarter of the block starts and after ~1/18 (tiny) or ~1/90 (owt) of the sentences
     if (synth_below(r, 4u) == 0) {
@@ -130,8 +130,8 @@ SYNTH_HD void synth_block(int shape, uint64_t seed, uint64_t block, uint8_t *dst
             } else if (owt && kind < 41) synth_spell(o, synth_word_id(r, bits, false), salt, cap, 1);      // Latin-1 accents
             else if (owt && kind < 45) synth_spell(o, synth_word_id(r, 14, false), salt, false, 2);        // Cyrillic
             else if (owt && kind < 48) {                     // CJK run
-                uint32_t len = 1 + synth_below(r, 6);
-                for (uint32_t i = 0; i < len; i++) synth_put_cp(o, 0x4E00 + synth_below(r, 3000));
+                uint32_t len = 1 + synth_below(r, 4);
+                for (uint32_t i = 0; i < len; i++) synth_put_cp(o, 0x4E00 + synth_word_id(r, 11, false));
             } else if (kind < (owt ? 50u : 3u)) synth_put_cp(o, 0x1F600 + synth_below(r, 64));             // emoji
             else {
                 synth_spell(o, synth_word_id(r, bits, !owt), salt, cap, 0);

@@ -323,10 +323,10 @@ struct TrainBufs {
     DevBuf sym, wmeta, wctr;
     DevBuf dense, hist, csr_off, csr_words;
     DevBuf pkey, pcnt, bmax, dirty, tok_key, prof, step_prof, merge_cnt, log, log_begin, tok_off, tok_len, tok_bytes, cta_best, merges, ctr;
-    void free_all() {
+    void free_all(bpe_ctx *ctx) {
         for (DevBuf *b : {&sym, &wmeta, &wctr, &dense, &hist, &csr_off, &csr_words, &pkey, &pcnt, &bmax,
                           &dirty, &tok_key, &prof, &step_prof, &merge_cnt, &log, &log_begin, &tok_off, &tok_len, &tok_bytes, &cta_best, &merges, &ctr})
-            bpe_buf_free(*b);
+            bpe_buf_free(ctx, *b);
     }
 };
 
@@ -344,19 +344,12 @@ static CountTables count_tables(bpe_ctx *ctx) {
 void count_state_free(bpe_ctx *ctx) {
     if (!ctx->count) return;
     CountState *cs = ctx->count;
-    for (DevBuf *b : {&cs->skey, &cs->scnt, &cs->lmeta, &cs->lhash, &cs->lcnt, &cs->pool, &cs->counters}) bpe_buf_free(*b);
+    for (DevBuf *b : {&cs->skey, &cs->scnt, &cs->lmeta, &cs->lhash, &cs->lcnt, &cs->pool, &cs->counters}) bpe_buf_free(ctx, *b);
     delete cs;
     ctx->count = nullptr;
 }
 
-static int alloc_exact(bpe_ctx *ctx, DevBuf &b, size_t bytes) {
-    if (b.cap >= bytes && b.cap <= bytes * 2 + (1 << 20)) return BPE_OK;
-    bpe_buf_free(b);
-    cudaError_t e = cudaMalloc(&b.p, bytes ? bytes : 256);
-    if (e != cudaSuccess) { cudaGetLastError(); b.p = nullptr; return bpe_set_error(ctx, BPE_ERR_OOM, "cudaMalloc(%zu) failed", bytes); }
-    b.cap = bytes ? bytes : 256;
-    return BPE_OK;
-}
+static int alloc_exact(bpe_ctx *ctx, DevBuf &b, size_t bytes) { return bpe_buf_alloc(ctx, b, bytes ? bytes : 256); }
 
 static int count_tables_alloc(bpe_ctx *ctx, u64 scap, u64 lcap) {
     CountState *cs = ctx->count;
@@ -413,7 +406,7 @@ static int count_ensure_capacity(bpe_ctx *ctx, u64 n_short, u64 n_long, u64 new_
                                                  (const u64 *)old_view.lcnt.p, old_view.lcap, t);
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    for (DevBuf *b : {&old_view.skey, &old_view.scnt, &old_view.lmeta, &old_view.lhash, &old_view.lcnt}) bpe_buf_free(*b);
+    for (DevBuf *b : {&old_view.skey, &old_view.scnt, &old_view.lmeta, &old_view.lhash, &old_view.lcnt}) bpe_buf_free(ctx, *b);
     return BPE_OK;
 }
 
@@ -478,7 +471,7 @@ static int count_rehome(bpe_ctx *ctx) {
         BPE_TRY(bpe_buf_reserve(ctx, nb, (cs->pool_used + need) * 2 + (1 << 20)));
         if (cs->pool_used) CUDA_TRY(ctx, cudaMemcpyAsync(nb.p, cs->pool.p, cs->pool_used, cudaMemcpyDeviceToDevice, st));
         CUDA_TRY(ctx, cudaStreamSynchronize(st));
-        bpe_buf_free(cs->pool);
+        bpe_buf_free(ctx, cs->pool);
         cs->pool = nb;
         t = count_tables(ctx);
     }
@@ -595,7 +588,7 @@ static int count_import(bpe_ctx *ctx, const uint8_t *blob, const uint64_t *offs,
         BPE_TRY(bpe_buf_reserve(ctx, nbuf, (cs->pool_used + nb) * 2 + (1 << 20)));
         if (cs->pool_used) CUDA_TRY(ctx, cudaMemcpyAsync(nbuf.p, cs->pool.p, cs->pool_used, cudaMemcpyDeviceToDevice, st));
         CUDA_TRY(ctx, cudaStreamSynchronize(st));
-        bpe_buf_free(cs->pool);
+        bpe_buf_free(ctx, cs->pool);
         cs->pool = nbuf;
     }
     u64 base = cs->pool_used;
@@ -645,7 +638,7 @@ BPE_API int bpe_count_pair_table(bpe_ctx *ctx, const uint8_t *specials_blob, con
     const uint8_t *spb; const u32 *spo; u32 spmax;
     BPE_TRY(ctx_upload_specials(ctx, specials_blob, special_offs, n_specials, &spb, &spo, &spmax));
     DevBuf sym, wmeta, wctr, dense, hist;
-    struct G { DevBuf *b[5]; ~G() { for (auto x : b) bpe_buf_free(*x); } } g{{&sym, &wmeta, &wctr, &dense, &hist}};
+    struct G { bpe_ctx *c; DevBuf *b[5]; ~G() { for (auto x : b) bpe_buf_free(c, *x); } } g{ctx, {&sym, &wmeta, &wctr, &dense, &hist}};
     BPE_TRY(bpe_buf_reserve(ctx, sym, (max_syms + 1) * 4)); BPE_TRY(bpe_buf_reserve(ctx, wmeta, (max_words + 1) * sizeof(WordMeta)));
     BPE_TRY(bpe_buf_reserve(ctx, wctr, 64)); BPE_TRY(bpe_buf_reserve(ctx, dense, 65536 * 8)); BPE_TRY(bpe_buf_reserve(ctx, hist, 65536 * 4));
     CUDA_TRY(ctx, cudaMemsetAsync(wctr.p, 0, 64, st)); CUDA_TRY(ctx, cudaMemsetAsync(dense.p, 0, 65536 * 8, st));
@@ -673,7 +666,7 @@ static int run_merges(bpe_ctx *ctx, const uint8_t *sp_blob, const u32 *sp_offs, 
     cudaStream_t st = ctx->stream;
     CountState *cs = ctx->count;
     TrainBufs B;
-    struct Guard { TrainBufs &b; ~Guard() { b.free_all(); } } guard{B};
+    struct Guard { TrainBufs &b; bpe_ctx *c; ~Guard() { b.free_all(c); } } guard{B, ctx};
     u64 c[6];
     BPE_TRY(read_counters(ctx, c, 6));
     u64 n_short = c[0], n_long = c[1], long_bytes = c[2];
@@ -792,16 +785,17 @@ static int run_merges(bpe_ctx *ctx, const uint8_t *sp_blob, const u32 *sp_offs, 
         u64 ocap = M.pcap;
         B.pkey = DevBuf(); B.pcnt = DevBuf();
         int rc = alloc_pair_table(ocap * 4);
-        if (rc != BPE_OK) { bpe_buf_free(okey); bpe_buf_free(ocnt); return rc; }
-        host[2] = 0; host[3] = 0; u64 pending = ctr[6]; host[6] = PAIR_EMPTY;
+        if (rc != BPE_OK) { bpe_buf_free(ctx, okey); bpe_buf_free(ctx, ocnt); return rc; }
+        host[2] = 0; host[3] = 0; u64 pending = ctr[6]; host[6] = PAIR_EMPTY; host[5] = 0;
         CUDA_TRY(ctx, cudaMemcpyAsync((u64 *)B.ctr.p + 2, host + 2, 16, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(ctx, cudaMemcpyAsync((u64 *)B.ctr.p + 5, host + 5, 8, cudaMemcpyHostToDevice, st));
         CUDA_TRY(ctx, cudaMemcpyAsync((u64 *)B.ctr.p + 6, host + 6, 8, cudaMemcpyHostToDevice, st));
         unsigned rg = (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (ocap + 255) / 256);
         CUDA_TRY(ctx, cudaMemcpyToSymbolAsync(cM, &M, sizeof(M), 0, cudaMemcpyHostToDevice, st));
         KLAUNCH(k_pairs_rehash, rg, 256, 0, st, (const u64 *)okey.p, (const i64 *)ocnt.p, ocap, pending);
         CUDA_TRY(ctx, cudaGetLastError());
         CUDA_TRY(ctx, cudaStreamSynchronize(st));
-        bpe_buf_free(okey); bpe_buf_free(ocnt);
+        bpe_buf_free(ctx, okey); bpe_buf_free(ctx, ocnt);
     }
     keys_created += ctr[2];
     ctr[2] = keys_created;
@@ -839,7 +833,7 @@ static int run_merges(bpe_ctx *ctx, const uint8_t *sp_blob, const u32 *sp_offs, 
     if (stats) {
         stats->n_unique = n_words; stats->n_symbols = n_syms; stats->n_pairs_initial = n_pairs0;
         stats->n_pairs_final = ctr[2]; stats->log_records = ctr[0]; stats->duplicate_tokens = dup_tokens;
-        stats->n_pretokens = cs->n_pretokens;
+        stats->n_pretokens = cs->n_pretokens; stats->sum_live_pairs = ctr[7];
         stats->ms_build = tm.ms(ev_build0, ev_build1); stats->ms_merge = tm.ms(ev_build1, ev_merge1);
         stats->ms_total = tm.ms(ev_start, ev_end);
     }

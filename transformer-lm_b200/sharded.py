@@ -199,34 +199,49 @@ def _raise_decode_error(peek, size: int, offset: int):
     raise UnicodeDecodeError("utf-8", window, offset - lo, offset - lo + 1, "invalid start byte")
 
 
-def sharded_count(counter, peek, size: int, special_tokens: List[str], group=None, verify: bool = True):
-    """Count the pretokens of the file bytes [0, size) across the ranks of `group` into `counter` (every rank ends
+class FileShards:
+    """Shard source over a file (or any byte source `peek(lo, hi)` of `size` bytes): rank r owns [size*r/W, size*(r+1)/W)
+    moved back to a code-point boundary and reads a halo on both sides."""
+
+    def __init__(self, peek, size: int):
+        self.peek, self.size = peek, size
+
+    def load(self, rank: int, world: int, halo_right: int):
+        lo, hi, read_lo, read_hi = plan_shard(self.peek, self.size, rank, world, halo_right)
+        return dict(data=self.peek(read_lo, read_hi), device_ptr=None, n_bytes=read_hi - read_lo, own_begin=lo - read_lo, own_end=hi - read_lo,
+                    at_start=read_lo == 0, at_end=read_hi == self.size, base=read_lo)
+
+    def raise_decode_error(self, offset: int):
+        _raise_decode_error(self.peek, self.size, offset)
+
+
+def sharded_count(counter, shards, special_tokens: List[str], group=None, verify: bool = True):
+    """Count the pretokens of the corpus behind `shards` across the ranks of `group` into `counter` (every rank ends
     with the merged table).  Returns "ok", or "newline" when some shard contains a carriage return (the caller
     then takes the unsharded path: universal-newline translation shifts byte offsets)."""
     dist = _dist()
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     halo = HALO_RIGHT
-    status = None
     while True:
-        lo, hi, read_lo, read_hi = plan_shard(peek, size, rank, world, halo)
-        data = peek(read_lo, read_hi)
-        status = counter.add(data, lo - read_lo, hi - read_lo, read_lo == 0, read_hi == size)
-        if status is not None and status[0] == "halo" and read_hi < size:
+        sh = shards.load(rank, world, halo)
+        status = counter.add(sh["data"], sh["own_begin"], sh["own_end"], sh["at_start"], sh["at_end"], device_ptr=sh["device_ptr"],
+                             n_bytes=sh["n_bytes"])
+        if status is not None and status[0] == "halo" and not sh["at_end"]:
             counter.restart()
             halo *= 16
             continue
         break
     err = NO_ERROR
     if status is not None and status[0] == "utf8":
-        err = read_lo + status[1]
+        err = sh["base"] + status[1]
     first_err = _all_reduce_scalar(err, "min", counter.device, group)
     if first_err != NO_ERROR:
-        _raise_decode_error(peek, size, first_err)             # same exception on every rank (train.py:22)
+        shards.raise_decode_error(first_err)                   # same exception on every rank (train.py:22)
     any_cr = _all_reduce_scalar(1 if (status is not None and status[0] == "newline") else 0, "max", counter.device, group)
     if any_cr:
         return "newline"
     if status is not None:
-        raise _lib.BpeError(_lib.ERR_HALO, "pretoken longer than the file tail?")
+        raise _lib.BpeError(_lib.ERR_HALO, "a pretoken runs past the end of the corpus")
     local_pairs = counter.pair_table(special_tokens) if verify else None
     exchange_tables(counter, group)
     if verify:
@@ -270,7 +285,7 @@ def train_bpe_sharded(input_path, vocab_size: int, special_tokens: List[str] = [
     peek, f = _file_peek(input_path)
     try:
         counter = DeviceCounter(ctx)
-        outcome = sharded_count(counter, peek, size, special_tokens, group, verify)
+        outcome = sharded_count(counter, FileShards(peek, size), special_tokens, group, verify)
         if outcome == "newline":
             from .train import train_bpe
             return train_bpe(input_path, vocab_size, special_tokens, ctx=ctx, return_stats=return_stats)

@@ -124,7 +124,8 @@ class Tokenizer:
 
     def close(self):
         if getattr(self, "_tok", None):
-            _lib.lib().bpe_tok_destroy(self._tok)
+            if self._tok_ctx.handle:             # the tokenizer's device memory belongs to its (still open) context
+                _lib.lib().bpe_tok_destroy(self._tok)
             self._tok = None
 
     def __del__(self):
