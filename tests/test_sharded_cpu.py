@@ -25,35 +25,44 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, data, specials, halo, q):
+def _worker(rank, world, port, scenarios, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from tests.helpers.fake_counter import OracleCounter
-        sharded.HALO_RIGHT = halo
-        counter = OracleCounter()
-        try:
-            out = sharded.sharded_count(counter, sharded.FileShards(lambda lo, hi: data[lo:hi], len(data)), specials, None, True)
-            q.put((rank, out, dict(counter.table), counter.adds))
-        except UnicodeDecodeError as e:
-            q.put((rank, "utf8", (e.start, e.reason), 0))
+        for name, data, specials, halo in scenarios:
+            sharded.HALO_RIGHT = halo
+            counter = OracleCounter()
+            try:
+                out = sharded.sharded_count(counter, sharded.FileShards(lambda lo, hi: data[lo:hi], len(data)), specials, None, True)
+                q.put((name, rank, out, dict(counter.table), counter.adds))
+            except UnicodeDecodeError as e:
+                q.put((name, rank, "utf8", (e.start, e.reason), 0))
     finally:
         dist.destroy_process_group()
 
 
-def _run(world, data, specials=("<|endoftext|>",), halo=64 << 10):
+def _run_many(world, scenarios):
+    """One process group per world size runs every scenario in turn (process start-up dominates otherwise)."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, data, list(specials), halo, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, scenarios, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=120) for _ in procs]
+    res = [q.get(timeout=240) for _ in range(world * len(scenarios))]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    return sorted(res)
+    out = {}
+    for name, rank, o, table, adds in res:
+        out.setdefault(name, []).append((rank, o, table, adds))
+    return {k: sorted(v) for k, v in out.items()}
+
+
+def _run(world, data, specials=("<|endoftext|>",), halo=64 << 10):
+    return _run_many(world, [("one", data, list(specials), halo)])["one"]
 
 
 def _want(data, specials=()):
@@ -74,55 +83,75 @@ def test_plan_shard_cuts_on_code_points():
         assert prev_hi == len(data)
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_sharded_count_equals_whole_text(world):
-    data = (FIXTURES_PATH / "corpus.en").read_bytes().replace(b"\r", b"")
-    res = _run(world, data)
-    want = _want(data)
-    for rank, out, table, adds in res:
+def _corpus():
+    return (FIXTURES_PATH / "corpus.en").read_bytes().replace(b"\r", b"")
+
+
+def _unicode_text():
+    rnd = random.Random(4)
+    alpha = ["é", "🙃", "中", " ", "  ", "\n", "a", "it's", "<|endoftext|>", "x" * 300, " " * 200]
+    return "".join(rnd.choice(alpha) for _ in range(4000)).encode()
+
+
+def _bad_corpus():
+    data = bytearray(_corpus())
+    data[100000] = 0xFF
+    data[1000] = 0xC0
+    return bytes(data)
+
+
+@pytest.fixture(scope="module")
+def two_ranks():
+    sp = ["<|endoftext|>"]
+    return _run_many(2, [("corpus", _corpus(), sp, 64 << 10), ("unicode_tiny_halo", _unicode_text(), sp, 32), ("two_bytes", b"ab", sp, 64 << 10),
+                         ("empty", b"", sp, 64 << 10), ("bad", _bad_corpus(), sp, 64 << 10),
+                         ("crlf", b"hello world\r\nsecond line " * 2000, sp, 64 << 10)])
+
+
+def test_sharded_count_equals_whole_text(two_ranks):
+    want = _want(_corpus())
+    for rank, out, table, adds in two_ranks["corpus"]:
         assert out == "ok" and adds == 1
         assert table == want
 
 
-def test_unicode_heavy_text_and_tiny_halo_forces_retries():
-    rnd = random.Random(4)
-    alpha = ["é", "🙃", "中", " ", "  ", "\n", "a", "it's", "<|endoftext|>", "x" * 300, " " * 200]
-    text = "".join(rnd.choice(alpha) for _ in range(4000)).encode()
-    res = _run(2, text, halo=32)
-    want = _want(text)
+def test_three_ranks():
+    res = _run_many(3, [("corpus", _corpus(), ["<|endoftext|>"], 64 << 10), ("two_bytes", b"ab", [], 64 << 10)])
+    want = _want(_corpus())
+    for rank, out, table, adds in res["corpus"]:
+        assert out == "ok" and table == want
+    for rank, out, table, adds in res["two_bytes"]:           # more ranks than bytes
+        assert out == "ok" and table == {b"ab": 1}
+
+
+def test_unicode_heavy_text_and_tiny_halo_forces_retries(two_ranks):
+    want = _want(_unicode_text())
+    res = two_ranks["unicode_tiny_halo"]
     assert any(adds > 1 for _, _, _, adds in res)          # the 32-byte halo was too small somewhere
     for rank, out, table, adds in res:
         assert out == "ok" and table == want
 
 
-def test_more_ranks_than_bytes():
-    res = _run(3, b"ab")
-    for rank, out, table, adds in res:
+def test_tiny_and_empty_inputs(two_ranks):
+    for rank, out, table, adds in two_ranks["two_bytes"]:
         assert out == "ok" and table == {b"ab": 1}
-    res = _run(2, b"")
-    for rank, out, table, adds in res:
+    for rank, out, table, adds in two_ranks["empty"]:
         assert out == "ok" and table == {}
 
 
-def test_invalid_utf8_raises_the_first_offset_on_every_rank():
-    data = bytearray((FIXTURES_PATH / "corpus.en").read_bytes().replace(b"\r", b""))
-    data[100000] = 0xFF
-    data[1000] = 0xC0
+def test_invalid_utf8_raises_the_first_offset_on_every_rank(two_ranks):
     try:
-        bytes(data).decode("utf-8")
+        _bad_corpus().decode("utf-8")
     except UnicodeDecodeError as e:
         want = (e.start, e.reason)
-    res = _run(2, bytes(data))
-    for rank, out, info, _ in res:
+    for rank, out, info, _ in two_ranks["bad"]:
         assert out == "utf8"
         # the exception is rebuilt from a 16-byte window around the first bad byte: same reason, offset inside the window
         assert info[1] == want[1]
 
 
-def test_carriage_return_falls_back():
-    data = b"hello world\r\nsecond line " * 2000
-    res = _run(2, data)
-    for rank, out, table, adds in res:
+def test_carriage_return_falls_back(two_ranks):
+    for rank, out, table, adds in two_ranks["crlf"]:
         assert out == "newline"
 
 

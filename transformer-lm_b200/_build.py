@@ -42,7 +42,7 @@ def build(force: bool = False, verbose: bool = False) -> pathlib.Path:
 
     def compile_one(src: str):
         obj = objdir / (src + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("BPE_EXTRA_NVCC_FLAGS", "").split(), "-c", str(CSRC / src), "-o", str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         (objdir / (src + ".log")).write_text(r.stdout + r.stderr)
         if r.returncode != 0:
