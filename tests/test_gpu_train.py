@@ -171,3 +171,28 @@ def test_shard_reports_only_owned_utf8_errors_and_refuses_cr():
     assert c.add(b"a" * 400, 64, 300, False, False) is None             # its only pretoken starts at 0: not owned
     c = sharded.DeviceCounter()
     assert c.add(long_tail, 0, 400, True, True) is None
+
+
+# ---- the two merge-loop kernels (grid-wide k_merge_loop, single-cluster k_merge_tail) must agree ---------------
+@pytest.mark.parametrize("tail_after", ["0", "1", "37", "1000000"])
+def test_merge_kernels_agree_at_any_switch_point(monkeypatch, tail_after):
+    monkeypatch.setenv("BPE_TAIL_AFTER", tail_after)
+    data = (FIXTURES_PATH / "corpus.en").read_bytes()
+    want = oracle.train_bpe_on_bytes(data, 1500, ["<|endoftext|>"])
+    got = _train_bytes(data, 1500, ["<|endoftext|>"])
+    assert got[1] == want[1] and got[0] == want[0]
+    # exhaustion phase (zero-count pairs, early stop) inside the tail kernel
+    tiny = b"aaaa abab aaaa"
+    assert _train_bytes(tiny, 300, []) == oracle.train_bpe_on_bytes(tiny, 300, [])
+    fz = _fuzz_corpus(31, 3000, WORDS)
+    assert _train_bytes(fz, 5000, []) == oracle.train_bpe_on_bytes(fz, 5000, [])
+
+
+def test_tail_kernel_survives_table_growth(monkeypatch):
+    monkeypatch.setenv("BPE_TAIL_AFTER", "5")
+    rnd = random.Random(77)
+    words = ["".join(rnd.choice("abcdefghijklmnopqrstuvwxyz") for _ in range(rnd.randint(2, 9))) for _ in range(6000)]
+    data = " ".join(rnd.choice(words) for _ in range(40000)).encode()
+    want = oracle.train_bpe_on_bytes(data, 2500, [])
+    got = _train_bytes(data, 2500, [])
+    assert got[1] == want[1] and got[0] == want[0]

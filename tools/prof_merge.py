@@ -10,7 +10,7 @@ t = torch.empty(n, dtype=torch.uint8, device='cuda')
 synth_device('owt', 4321, n, t.data_ptr(), ctx=ctx)
 for it in range(2):
     v, m, st = train_bpe_on_bytes(None, 32000, ["<|endoftext|>"], ctx=ctx, return_stats=True, device_ptr=t.data_ptr(), n_bytes=n)
-out = (C.c_ulonglong * 16)()
+out = (C.c_ulonglong * 32)()
 _lib.lib().bpe_debug_merge_profile(out)
 p = list(out)
 steps = max(p[7], 1)
@@ -18,6 +18,8 @@ print("stages", {k: round(x, 1) for k, x in st.items() if k.startswith('ms_')})
 print("per-step us: phase1 %.2f sync1 %.2f apply %.2f sync2 %.2f | tokenCTA %.2f | records/step %.0f words/step %.1f dirty_sb(n/a) %.1f dirty_blk/step %.1f steps %d" % (
     p[0]/steps/1e3, p[1]/steps/1e3, p[2]/steps/1e3, p[3]/steps/1e3, p[4]/steps/1e3, p[5]/steps, p[6]/steps, p[8]/steps, p[9]/steps, steps))
 print("slow compares per step: %.1f" % (p[8] / steps))
+print("tail detail us/step: p1a %.2f p1b %.2f p1c %.2f p2 %.2f | list blocks %.1f superblocks %.1f | index range %.0f | sort: %d sorts, %.2f us each, ctr10-like" % (
+    p[16]/steps/1e3, p[17]/steps/1e3, p[18]/steps/1e3, p[19]/steps/1e3, p[20]/steps, p[21]/steps, p[22]/steps, p[24], p[23]/max(p[24],1)/1e3))
 print("token CTA us/step: winner %.2f meta %.2f bytes+key %.2f probe %.2f | winner (SM cycles): loads+cmp %.0f warp_best %.0f" % tuple([p[i] / steps / 1e3 for i in (10, 11, 12, 13)] + [p[14] / steps, p[15] / steps]))
 import os
 if os.environ.get("BPE_STEP_PROFILE"):

@@ -28,7 +28,7 @@ namespace cg = cooperative_groups;
 #define PAIR_EMPTY 0xFFFFFFFFFFFFFFFFull
 #define CNT_DEAD ((i64)0x8000000000000000ll)     // key was popped from the dict (train.py:226)
 #define CNT_DEAD_LIMIT ((i64)0xC000000000000000ll) // counts below this are "popped (+ later deltas)"
-#define PB 256u                                  // pair-table slots per block
+#define PB 64u                                   // pair-table slots per block (one rescan = two slots per lane)
 #define MG_NT 512
 #define MG_NEED_GROW 8ull
 #define CTA_BEST_STRIDE 32u                       // Best entries (1 KiB) between per-CTA candidates: spreads the all-read-all
@@ -74,11 +74,18 @@ struct MergeState {
     Best *bmax; uint8_t *dirty; u32 n_blocks;
     const u32 *csr_off; const u32 *csr_words;
     uint2 *log; u64 *log_begin; u64 log_cap;
+    // big log slices are bucket-sorted by hash(neighbour) into log2 right after the step that wrote them:
+    // bk_lg[step] = log2(buckets) (0 = slice left unsorted), bk_start[step] = first of its buckets+1 offsets in bk_off
+    uint2 *log2; u32 *bk_lg; u64 *bk_start; u32 *bk_off; u64 bk_off_cap; u32 *bk_scratch;   // bk_scratch: 2 x (hist, cursor) x SORT_MAX_BK
     u32 *tok_off; u32 *tok_len; u64 *tok_key; uint8_t *tok_bytes; u64 tok_bytes_cap;
     Best *cta_best;
+    // tail kernel (one thread-block cluster): per 64-block superblock a 64-bit mask of dirty blocks
+    u64 *sdirty_mask; u32 n_super; int tail_mode;
+    int stop_at;                                 // this launch runs steps [ctr[1], stop_at)
     int32_t *merges_out; i64 *merge_cnt_out; int n_merges;
     // [0]=log cursor [1]=n_done (next step) [2]=pair keys created [3]=status flags [4]=tok bytes cursor
     // [5]=keys popped since the table was last rebuilt [6]=previous winner key still to be popped (PAIR_EMPTY if none)
+    // [8]=words rewritten (all steps) [9]=bk_off pool cursor [10]=slices sorted
     // [7]=sum over steps of the live pair-table keys (the reference's max() scans that many dict entries, train.py:187-189)
     u64 *ctr;
     // profile (ns / counts): [0]=phase1 [1]=sync1 [2]=apply [3]=sync2 on CTA 0; [4]=token CTA work; [5]=index records scanned;
@@ -127,7 +134,8 @@ __device__ __forceinline__ bool best_greater(const Best &x, const Best &y) {
     if (x.cnt == CNT_DEAD) return false;
     return best_tie_greater(x.key, x.ka, x.kb, y.key, y.ka, y.kb);
 }
-__device__ __forceinline__ Best warp_best(Best b) {
+// butterfly reduction with the full comparison (handles every tie): the slow path of warp_best
+__device__ __noinline__ Best warp_best_butterfly(Best b) {
 #pragma unroll 1
     for (int d = 16; d; d >>= 1) {
         Best o;
@@ -138,6 +146,54 @@ __device__ __forceinline__ Best warp_best(Best b) {
         if (best_greater(o, b)) b = o;
     }
     return b;
+}
+// warp-wide maximum of v over the lanes in `active` (0 elsewhere), two redux.sync steps
+__device__ __forceinline__ u64 warp_max_u64(u64 v, bool active) {
+    const u32 hi = active ? (u32)(v >> 32) : 0u;
+    const u32 mh = __reduce_max_sync(0xffffffffu, hi);
+    const u32 lo = (active && hi == mh) ? (u32)v : 0u;
+    const u32 ml = __reduce_max_sync(0xffffffffu, lo);
+    return ((u64)mh << 32) | ml;
+}
+// Warp arg-max under the (count, (bytes_a, bytes_b)) order; every lane returns the winner.  The common cases -- a
+// unique maximal count, or ties decided by the 8-byte prefix keys -- take a few redux / ballot steps instead of a
+// five-round butterfly of 256-bit shuffles; anything subtler (equal prefixes of different tokens) falls back to it.
+__device__ __forceinline__ Best warp_best(Best b) {
+    // counts: CNT_DEAD (most negative) marks "no candidate"; bias to unsigned order
+    const u64 bc = (u64)b.cnt ^ 0x8000000000000000ull;
+    const u64 mc = warp_max_u64(bc, true);
+    if (mc == 0) return BEST_NONE;               // every lane is empty
+    u32 t = __ballot_sync(0xffffffffu, bc == mc);
+    if (t & (t - 1)) {                           // tie on the count: first tokens by prefix key
+        const bool in1 = (t >> lane_id()) & 1u;
+        const u64 ma = warp_max_u64(b.ka, in1);
+        const u32 t2 = __ballot_sync(0xffffffffu, in1 && b.ka == ma);
+        if (t2 & (t2 - 1)) {
+            const bool in2 = (t2 >> lane_id()) & 1u;
+            const u32 a0 = __shfl_sync(0xffffffffu, (u32)(b.key >> 32), __ffs(t2) - 1);
+            if (__ballot_sync(0xffffffffu, in2 && (u32)(b.key >> 32) != a0)) return warp_best_butterfly(b);   // equal prefix, different tokens
+            const u64 mb = warp_max_u64(b.kb, in2);
+            const u32 t3 = __ballot_sync(0xffffffffu, in2 && b.kb == mb);
+            if (t3 & (t3 - 1)) {
+                const u32 b0 = __shfl_sync(0xffffffffu, (u32)b.key, __ffs(t3) - 1);
+                const bool in3 = (t3 >> lane_id()) & 1u;
+                if (__ballot_sync(0xffffffffu, in3 && (u32)b.key != b0)) return warp_best_butterfly(b);
+            }
+            t = t3;
+        } else t = t2;
+    }
+    const int src = __ffs(t) - 1;
+    Best r;
+    r.cnt = __shfl_sync(0xffffffffu, b.cnt, src); r.key = __shfl_sync(0xffffffffu, b.key, src);
+    r.ka = __shfl_sync(0xffffffffu, b.ka, src); r.kb = __shfl_sync(0xffffffffu, b.kb, src);
+    return r;
+}
+
+// A pair-table slot changed: its block must be rescanned before the next arg-max.
+__device__ __forceinline__ void mark_dirty(u64 slot) {
+    const u32 blk = (u32)(slot / PB);
+    if (cM.tail_mode) atomicOr(&cM.sdirty_mask[blk >> 6], 1ull << (blk & 63u));   // fire-and-forget reduction
+    else cM.dirty[blk] = 1;
 }
 
 // frequencies[key] += delta with defaultdict semantics (train.py:36,65-78): a missing key is created.
@@ -153,7 +209,7 @@ __device__ __noinline__ void pair_add_from(u64 key, i64 delta, u64 s, u64 k) {
         }
         if (k == key) {
             atomicAdd((u64 *)&cM.pcnt[s], (u64)delta);
-            cM.dirty[s / PB] = 1;
+            mark_dirty(s);
             return;
         }
         s = (s + 1) & mask;
@@ -227,6 +283,7 @@ __device__ __noinline__ void apply_merge_to_word(u32 w, u32 a, u32 b, u32 nw) {
 #pragma unroll 1
     while (r < len) s[o++] = s[r++];
     wm->len = o;
+    atomicAdd(&cM.ctr[8], 1ull);
     PROF_ADD(6, 1);
 }
 
@@ -244,12 +301,10 @@ __device__ __forceinline__ Best rescan_block(u32 blk, u64 prev_key) {
         kas[k] = live ? cM.tok_key[(u32)(keys[k] >> 32)] : 0;
         kbs[k] = live ? cM.tok_key[(u32)keys[k]] : 0;
     }
-#pragma unroll 1
-    for (u32 k = 0; k < PB / 32; k++) {          // rolled on purpose (code size); operands picked with a select chain
-        Best c;
-        c.key = keys[0]; c.cnt = cnts[0]; c.ka = kas[0]; c.kb = kbs[0];
 #pragma unroll
-        for (u32 j = 1; j < PB / 32; j++) if (k == j) { c.key = keys[j]; c.cnt = cnts[j]; c.ka = kas[j]; c.kb = kbs[j]; }
+    for (u32 k = 0; k < PB / 32; k++) {
+        Best c;
+        c.key = keys[k]; c.cnt = cnts[k]; c.ka = kas[k]; c.kb = kbs[k];
         if (c.key == PAIR_EMPTY) continue;
         if (c.key == prev_key) { cM.pcnt[sbase + k * 32 + lane_id()] = CNT_DEAD; continue; }
         if (c.cnt == CNT_DEAD) continue;
@@ -259,14 +314,159 @@ __device__ __forceinline__ Best rescan_block(u32 blk, u64 prev_key) {
     return warp_best(bst);
 }
 
+
+// ---- token bookkeeping: bytes and prefix key of the new token, outputs (one CTA, all its threads) -------------
+__device__ __forceinline__ void token_bookkeeping(int step, const Best &win, u32 a, u32 b, u32 nw, bool prof_thread, u64 t2) {
+    const u32 tid = threadIdx.x;
+    u64 tA = prof_thread ? gtime_ns() : 0;
+    const u32 la = cM.tok_len[a], lb = cM.tok_len[b], ln = la + lb;
+    const u32 oa = cM.tok_off[a], ob = cM.tok_off[b];
+    const u64 cur = cM.ctr[4];
+    const u64 live = cM.ctr[2];
+    __syncthreads();
+    u64 tB = prof_thread ? gtime_ns() : 0;
+    if (cur + ln > cM.tok_bytes_cap) { if (tid == 0) cM.ctr[3] = 4; }
+    else {
+        uint8_t *dst = cM.tok_bytes + cur;
+        const uint8_t *pa = cM.tok_bytes + oa, *pb = cM.tok_bytes + ob;
+        for (u32 i = tid; i < ln; i += MG_NT) dst[i] = i < la ? pa[i] : pb[i - la];
+        if (tid == 0) {
+            // first 8 bytes of a+b from the operands' zero-padded big-endian prefix keys
+            u64 nkey = cM.tok_key[a];
+            if (la < 8) nkey |= cM.tok_key[b] >> (8 * la);
+            cM.tok_off[nw] = (u32)cur; cM.tok_len[nw] = ln; cM.tok_key[nw] = nkey; cM.ctr[4] = cur + ln;
+            cM.merges_out[2 * step] = (int32_t)a; cM.merges_out[2 * step + 1] = (int32_t)b;
+            cM.merge_cnt_out[step] = win.cnt;
+            cM.ctr[1] = (u64)(step + 1);
+            cM.ctr[7] += live - cM.ctr[5]; cM.ctr[5] += 1;
+            if (prof_thread) { cM.prof[10] += tA - t2; cM.prof[11] += tB - tA; cM.prof[12] += gtime_ns() - tB; }
+        }
+    }
+    // make sure the winner's block is rescanned so the key gets popped
+    if (tid == 32) {
+        u64 mask = cM.pcap - 1, s = mix64(win.key) & mask;
+        while (cM.pkey[s] != win.key) s = (s + 1) & mask;
+        mark_dirty(s);
+    }
+}
+
+#define SORT_MIN 2048u                           // slices with fewer records are scanned whole
+#define SORT_MAX_LG 12u                          // at most 4096 buckets
+#define SORT_MAX_BK (1u << SORT_MAX_LG)
+__device__ __forceinline__ u32 bucket_of(u32 x, u32 lg) { return (x * 0x9E3779B1u) >> (32u - lg); }
+
+// Index range of the winner (a,b): token_indices[best_pair] of train.py:192.  out[0..1] = record range, out[2] = 1 when
+// the range lies in the bucket-sorted copy (log2).  One thread per CTA.
+__device__ __forceinline__ void winner_range(u64 key, u64 *out) {
+    const u32 wa = (u32)(key >> 32), wb = (u32)key, wT = wa > wb ? wa : wb;
+    if (wT < 256) { u32 pp = (wa << 8) | wb; out[0] = cM.csr_off[pp]; out[1] = cM.csr_off[pp + 1]; out[2] = 0; return; }
+    const u32 t = wT - 256;
+    const u64 lo = cM.log_begin[t], hi = cM.log_begin[t + 1];
+    const u32 lg = cM.bk_lg[t];
+    const u64 st0 = cM.bk_start[t];              // (garbage when the slice is unsorted; loaded alongside, not after)
+    if (!lg) { out[0] = lo; out[1] = hi; out[2] = 0; return; }
+    const u32 want = wb >= wa ? wa : (0x80000000u | wb);
+    const u64 st = st0 + bucket_of(want, lg);
+    out[0] = lo + cM.bk_off[st]; out[1] = lo + cM.bk_off[st + 1]; out[2] = 1;
+}
+
+// Bucket-sort the slice [lo, lo + n) of the log by hash(record.x) into log2 (same offsets) and publish the bucket
+// offsets.  Called by every thread of every CTA between two steps; `sync` is the grid / cluster barrier.
+// s_scan: SORT_MAX_BK u32 of shared memory.  parity alternates so that the scratch of the previous sort can be cleared here.
+template <typename SyncFn>
+__device__ __forceinline__ void sort_slice(int step, u64 lo, u32 n, u32 parity, bool leader_cta, u64 gthread, u64 gstride,
+                                           u32 *s_scan, SyncFn sync) {
+    u32 lg = 4;
+    while ((64u << lg) < n && lg < SORT_MAX_LG) lg++;
+    const u32 nbk = 1u << lg;
+    u32 *hist = cM.bk_scratch + (size_t)parity * 2 * SORT_MAX_BK, *cur = hist + SORT_MAX_BK;
+    u32 *other = cM.bk_scratch + (size_t)(parity ^ 1u) * 2 * SORT_MAX_BK;
+    for (u64 i = gthread; i < n; i += gstride) atomicAdd(&hist[bucket_of(cM.log[lo + i].x, lg)], 1u);
+    for (u64 i = gthread; i < 2 * SORT_MAX_BK; i += gstride) other[i] = 0;       // last used two barriers ago
+    sync();
+    // exclusive scan of the histogram, redundantly in every CTA
+    const u32 tid = threadIdx.x;
+    const u32 per = (nbk + MG_NT - 1) / MG_NT;   // <= 8
+    u32 v[8], sum = 0;
+#pragma unroll
+    for (u32 k = 0; k < 8; k++) { u32 i = tid * per + k; v[k] = (k < per && i < nbk) ? hist[i] : 0; sum += v[k]; }
+    __shared__ u32 s_wsum[MG_NT / 32 + 1];
+    u32 inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, inc, d); if (lane_id() >= (u32)d) inc += t; }
+    if (lane_id() == 31) s_wsum[tid >> 5] = inc;
+    __syncthreads();
+    if (tid < 32) {
+        u32 x = tid < MG_NT / 32 ? s_wsum[tid] : 0, xi = x;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, xi, d); if (tid >= (u32)d) xi += t; }
+        s_wsum[tid] = xi - x;
+    }
+    __syncthreads();
+    u32 base = inc - sum + s_wsum[tid >> 5];
+    u64 pool = 0;
+    if (leader_cta) pool = cM.ctr[9];
+#pragma unroll
+    for (u32 k = 0; k < 8; k++) {
+        u32 i = tid * per + k;
+        if (k < per && i < nbk) { s_scan[i] = base; if (leader_cta) cM.bk_off[pool + i] = base; base += v[k]; }
+    }
+    if (leader_cta && tid == 0) {
+        cM.bk_off[pool + nbk] = n; cM.bk_start[step] = pool; cM.bk_lg[step] = lg; cM.ctr[9] = pool + nbk + 1; cM.ctr[10] += 1;
+    }
+    __syncthreads();
+    for (u64 i = gthread; i < n; i += gstride) {
+        uint2 r = cM.log[lo + i];
+        u32 bk = bucket_of(r.x, lg);
+        cM.log2[lo + s_scan[bk] + atomicAdd(&cur[bk], 1u)] = r;
+    }
+    sync();
+}
+
+// ---- apply the merge to every word indexed under (a,b): index slice [lo, hi) filtered by `gthread` of `gstride` threads
+__device__ __forceinline__ void apply_winner(int step, u32 a, u32 b, u32 nw, u64 lo, u64 hi, const uint2 *__restrict__ logsrc, u64 gthread, u64 gstride) {
+    const u32 T = a > b ? a : b;
+    if (gthread == 0) PROF_ADD(5, hi - lo);
+    if (T < 256) {
+        for (u64 i = lo + gthread; i < hi; i += 4 * gstride) {       // 4 candidates in flight per thread
+            const u32 none = 0xFFFFFFFFu;
+            u32 w0 = cM.csr_words[i];
+            u32 w1 = i + gstride < hi ? cM.csr_words[i + gstride] : none;
+            u32 w2 = i + 2 * gstride < hi ? cM.csr_words[i + 2 * gstride] : none;
+            u32 w3 = i + 3 * gstride < hi ? cM.csr_words[i + 3 * gstride] : none;
+#pragma unroll 1
+            for (int k = 0; k < 4; k++) {
+                u32 w = k == 0 ? w0 : k == 1 ? w1 : k == 2 ? w2 : w3;
+                if (w != none && atomicExch(&cM.W.meta[w].stamp, (u32)step + 1) != (u32)step + 1) apply_merge_to_word(w, a, b, nw);
+            }
+        }
+    } else {
+        u32 want = b >= a ? a : (0x80000000u | b);
+        for (u64 i = lo + gthread; i < hi; i += 4 * gstride) {       // 4 records in flight per thread
+            const uint2 none = make_uint2(0xFFFFFFFFu, 0);
+            uint2 r0 = logsrc[i];
+            uint2 r1 = i + gstride < hi ? logsrc[i + gstride] : none;
+            uint2 r2 = i + 2 * gstride < hi ? logsrc[i + 2 * gstride] : none;
+            uint2 r3 = i + 3 * gstride < hi ? logsrc[i + 3 * gstride] : none;
+#pragma unroll 1
+            for (int k = 0; k < 4; k++) {
+                uint2 r = k == 0 ? r0 : k == 1 ? r1 : k == 2 ? r2 : r3;
+                if (r.x == want && atomicExch(&cM.W.meta[r.y].stamp, (u32)step + 1) != (u32)step + 1) apply_merge_to_word(r.y, a, b, nw);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(MG_NT) k_merge_loop() {
     cg::grid_group grid = cg::this_grid();
     __shared__ Best s_best[MG_NT / 32];
     __shared__ Best s_win;
     __shared__ u64 s_status[2];
-    __shared__ u64 s_range[2];
+    __shared__ u64 s_range[4];
+    __shared__ u32 s_scan[SORT_MAX_BK];
     const u32 tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
     const u32 G = gridDim.x;
+    u32 n_sorts = 0;
     const u32 warps_per_cta = MG_NT / 32;
     const u32 gwarp = blockIdx.x * warps_per_cta + warp, total_warps = G * warps_per_cta;
     const bool token_cta = blockIdx.x == G - 1;
@@ -275,7 +475,7 @@ __global__ void __launch_bounds__(MG_NT) k_merge_loop() {
     const int first_step = (int)cM.ctr[1];
     u32 n_tok = 256 + (u32)first_step;
 
-    for (int step = first_step; step < cM.n_merges; step++) {
+    for (int step = first_step; step < cM.stop_at; step++) {
         // status flags are written before the grid.sync that ends a step and read here: uniform across the grid
         if (tid == 0) { s_status[0] = *((volatile u64 *)&cM.ctr[3]); s_status[1] = *((volatile u64 *)&cM.ctr[2]); }
         __syncthreads();
@@ -335,11 +535,7 @@ __global__ void __launch_bounds__(MG_NT) k_merge_loop() {
             c = warp_best(c);
             if (lane == 0) {
                 s_win = c;
-                if (c.cnt != CNT_DEAD && !token_cta) {           // index range of the winner, read once per CTA
-                    u32 wa = (u32)(c.key >> 32), wb = (u32)c.key, wT = wa > wb ? wa : wb;
-                    if (wT < 256) { u32 pp = (wa << 8) | wb; s_range[0] = cM.csr_off[pp]; s_range[1] = cM.csr_off[pp + 1]; }
-                    else { s_range[0] = cM.log_begin[wT - 256]; s_range[1] = cM.log_begin[wT - 256 + 1]; }
-                }
+                if (c.cnt != CNT_DEAD) winner_range(c.key, s_range);   // index range of the winner, read once per CTA
             }
         }
         __syncthreads();
@@ -347,79 +543,23 @@ __global__ void __launch_bounds__(MG_NT) k_merge_loop() {
         if (win.cnt == CNT_DEAD) break;          // len(byte_pair_frequencies) == 0 (train.py:184-185)
         const u32 a = (u32)(win.key >> 32), b = (u32)win.key;
         const u32 nw = n_tok;                    // symbol id of new_byte = a + b (train.py:190)
+        const u64 r_lo = s_range[0], r_hi = s_range[1];
 
-        if (token_cta) {
-            // ---- token bookkeeping: bytes and prefix key of the new token, outputs -------------------
-            u64 tA = prof_thread ? gtime_ns() : 0;
-            const u32 la = cM.tok_len[a], lb = cM.tok_len[b], ln = la + lb;
-            const u32 oa = cM.tok_off[a], ob = cM.tok_off[b];
-            const u64 cur = cM.ctr[4];
-            __syncthreads();
-            u64 tB = prof_thread ? gtime_ns() : 0;
-            if (cur + ln > cM.tok_bytes_cap) { if (tid == 0) cM.ctr[3] = 4; }
-            else {
-                uint8_t *dst = cM.tok_bytes + cur;
-                const uint8_t *pa = cM.tok_bytes + oa, *pb = cM.tok_bytes + ob;
-                for (u32 i = tid; i < ln; i += MG_NT) dst[i] = i < la ? pa[i] : pb[i - la];
-                if (tid == 0) {
-                    // first 8 bytes of a+b from the operands' zero-padded big-endian prefix keys
-                    u64 nkey = cM.tok_key[a];
-                    if (la < 8) nkey |= cM.tok_key[b] >> (8 * la);
-                    cM.tok_off[nw] = (u32)cur; cM.tok_len[nw] = ln; cM.tok_key[nw] = nkey; cM.ctr[4] = cur + ln;
-                    cM.merges_out[2 * step] = (int32_t)a; cM.merges_out[2 * step + 1] = (int32_t)b;
-                    cM.merge_cnt_out[step] = win.cnt;
-                    cM.ctr[1] = (u64)(step + 1);
-                    cM.ctr[7] += s_status[1] - cM.ctr[5]; cM.ctr[5] += 1;
-                    if (prof_thread) { cM.prof[10] += tA - t2; cM.prof[11] += tB - tA; cM.prof[12] += gtime_ns() - tB; }
-                }
-            }
-            // make sure the winner's block is rescanned so the key gets popped
-            if (tid == 32) {
-                u64 mask = cM.pcap - 1, s = mix64(win.key) & mask;
-                while (cM.pkey[s] != win.key) s = (s + 1) & mask;
-                cM.dirty[s / PB] = 1;
-            }
-        } else {
-            // ---- apply the merge to every word indexed under (a,b) ------------------------------
-            const u32 T = a > b ? a : b;
-            const u64 gthread = (u64)blockIdx.x * MG_NT + tid, gstride = (u64)apply_ctas * MG_NT;
-            if (T < 256) {
-                const u64 lo = s_range[0], hi = s_range[1];
-                if (gthread == 0) PROF_ADD(5, hi - lo);
-                for (u64 i = lo + gthread; i < hi; i += 4 * gstride) {       // 4 candidates in flight per thread
-                    const u32 none = 0xFFFFFFFFu;
-                    u32 w0 = cM.csr_words[i];
-                    u32 w1 = i + gstride < hi ? cM.csr_words[i + gstride] : none;
-                    u32 w2 = i + 2 * gstride < hi ? cM.csr_words[i + 2 * gstride] : none;
-                    u32 w3 = i + 3 * gstride < hi ? cM.csr_words[i + 3 * gstride] : none;
-#pragma unroll 1
-                    for (int k = 0; k < 4; k++) {
-                        u32 w = k == 0 ? w0 : k == 1 ? w1 : k == 2 ? w2 : w3;
-                        if (w != none && atomicExch(&cM.W.meta[w].stamp, (u32)step + 1) != (u32)step + 1) apply_merge_to_word(w, a, b, nw);
-                    }
-                }
-            } else {
-                const u64 lo = s_range[0], hi = s_range[1];
-                u32 want = b >= a ? a : (0x80000000u | b);
-                if (gthread == 0) PROF_ADD(5, hi - lo);
-                for (u64 i = lo + gthread; i < hi; i += 4 * gstride) {       // 4 records in flight per thread
-                    const uint2 none = make_uint2(0xFFFFFFFFu, 0);
-                    uint2 r0 = cM.log[i];
-                    uint2 r1 = i + gstride < hi ? cM.log[i + gstride] : none;
-                    uint2 r2 = i + 2 * gstride < hi ? cM.log[i + 2 * gstride] : none;
-                    uint2 r3 = i + 3 * gstride < hi ? cM.log[i + 3 * gstride] : none;
-#pragma unroll 1
-                    for (int k = 0; k < 4; k++) {
-                        uint2 r = k == 0 ? r0 : k == 1 ? r1 : k == 2 ? r2 : r3;
-                        if (r.x == want && atomicExch(&cM.W.meta[r.y].stamp, (u32)step + 1) != (u32)step + 1) apply_merge_to_word(r.y, a, b, nw);
-                    }
-                }
-            }
-        }
+        if (token_cta) token_bookkeeping(step, win, a, b, nw, prof_thread, t2);
+        else apply_winner(step, a, b, nw, r_lo, r_hi, s_range[2] ? cM.log2 : cM.log, (u64)blockIdx.x * MG_NT + tid, (u64)apply_ctas * MG_NT);
         prev_key = win.key;
         n_tok++;
         u64 t3 = prof_thread ? gtime_ns() : 0;
         grid.sync();
+        if ((r_hi - r_lo) * 2 >= SORT_MIN) {     // heuristic: about two records per index entry visited
+            const u64 lb = *((volatile u64 *)&cM.log_begin[step]), cur = *((volatile u64 *)&cM.ctr[0]);
+            const u64 pool = *((volatile u64 *)&cM.ctr[9]);
+            if (cur - lb >= SORT_MIN && cur <= cM.log_cap && pool + SORT_MAX_BK + 1 <= cM.bk_off_cap) {
+                sort_slice(step, lb, (u32)(cur - lb), n_sorts & 1u, blockIdx.x == 0, (u64)blockIdx.x * MG_NT + tid, (u64)G * MG_NT, s_scan,
+                           [&]() { grid.sync(); });
+                n_sorts++;
+            }
+        }
         if (prof_thread) {
             u64 t4 = gtime_ns();
             if (blockIdx.x == 0) {
@@ -433,6 +573,238 @@ __global__ void __launch_bounds__(MG_NT) k_merge_loop() {
         }
     }
     if (blockIdx.x == 0 && tid == 0) cM.ctr[6] = prev_key;
+}
+
+
+// =============================================================================================
+// Tail kernel: the same loop run by ONE thread-block cluster.
+//
+// After the first ~thousand merges a step touches a handful of words, and its cost in k_merge_loop is the latency
+// of two grid-wide barriers plus the L2 round trips of the cross-CTA arg-max.  Inside one cluster the barrier is the
+// hardware cluster barrier (0.27 us for 16 CTAs against 1.2 us for the grid barrier, tools/bench_gridsync.cu), the
+// per-superblock maxima live in shared memory and the per-CTA candidates travel through distributed shared memory.
+//   level 0  pair-table slots
+//   level 1  bmax[block]          global, PB slots per block
+//   level 2  s_smax[superblock]   shared memory of the CTA that owns the superblock (64 blocks), persistent across steps
+// Updates set a bit in sdirty_mask[superblock] (fire-and-forget atomicOr); a step rescans only those blocks.
+// =============================================================================================
+#define TAIL_MAX_CTAS 16u
+#define MG_STOP_ERROR 1u
+#define MG_STOP_GROW 2u
+
+__global__ void __launch_bounds__(256) k_tail_prepare() {
+    // dirty[] bytes of k_merge_loop -> per-superblock bit masks
+    for (u32 sb = blockIdx.x * blockDim.x + threadIdx.x; sb < cM.n_super; sb += gridDim.x * blockDim.x) {
+        u64 m = 0;
+        for (u32 j = 0; j < 64; j++) { u32 b = sb * 64 + j; if (b < cM.n_blocks && cM.dirty[b]) { m |= 1ull << j; cM.dirty[b] = 0; } }
+        cM.sdirty_mask[sb] = m;
+    }
+}
+
+__device__ __forceinline__ Best load_best_cg(const Best *p) {      // from L2: the entry may just have been written by another warp
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    uint4 lo = __ldcg(q), hi = __ldcg(q + 1);
+    Best b;
+    b.cnt = (i64)(((u64)lo.y << 32) | lo.x); b.key = ((u64)lo.w << 32) | lo.z;
+    b.ka = ((u64)hi.y << 32) | hi.x; b.kb = ((u64)hi.w << 32) | hi.z;
+    return b;
+}
+__device__ __forceinline__ u32 nth_set_bit64(u64 m, u32 n) {       // position of the n-th (0-based) set bit
+    for (u32 i = 0; i < n; i++) m &= m - 1;
+    return __ffsll((long long)m) - 1;
+}
+// maximum of superblock sb from its 64 cached block maxima
+__device__ __forceinline__ Best superblock_max(u32 sb, u32 lane) {
+    const u32 b0 = sb * 64 + lane, b1 = b0 + 32;
+    Best c = BEST_NONE;
+    if (b0 < cM.n_blocks) { Best m = load_best_cg(&cM.bmax[b0]); if (m.cnt != CNT_DEAD) c = m; }
+    if (b1 < cM.n_blocks) { Best m = load_best_cg(&cM.bmax[b1]); if (m.cnt != CNT_DEAD && best_greater(m, c)) c = m; }
+    return warp_best(c);
+}
+
+#define TAIL_LIST_MAX 1024u
+
+__global__ void __launch_bounds__(MG_NT) k_merge_tail() {
+    cg::cluster_group cl = cg::this_cluster();
+    extern __shared__ Best s_smax[];             // maxima of the superblocks this CTA owns: entry k * 16 + warp; then u32 s_sblist[]
+    __shared__ Best s_best[MG_NT / 32];
+    __shared__ Best s_cand[TAIL_MAX_CTAS];       // candidate of every CTA of the cluster (written through DSMEM)
+    __shared__ Best s_win;
+    __shared__ u64 s_range[4];
+    __shared__ u32 s_stop, s_nlist, s_nsb;
+    __shared__ u32 s_list[TAIL_LIST_MAX];        // dirty blocks of this CTA's superblocks (work list of the step)
+    __shared__ u32 s_scan[SORT_MAX_BK];
+    const u32 tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+    const u32 C = cl.num_blocks(), rank = cl.block_rank();
+    const u32 warps_per_cta = MG_NT / 32;
+    const u32 gwarp = rank * warps_per_cta + warp, total_warps = C * warps_per_cta;
+    const u32 KS = (cM.n_super + total_warps - 1) / total_warps;   // superblocks per warp
+    u32 *s_sblist = reinterpret_cast<u32 *>(s_smax + (size_t)KS * warps_per_cta);
+    const bool token_cta = rank == C - 1;
+    const u32 apply_ctas = C - 1;
+    u64 prev_key = cM.ctr[6];
+    const int first_step = (int)cM.ctr[1];
+    u32 n_tok = 256 + (u32)first_step;
+    u32 n_sorts = 0;
+    if (tid == 0) {
+        u64 st = *((volatile u64 *)&cM.ctr[3]), keys = *((volatile u64 *)&cM.ctr[2]);
+        s_stop = st ? MG_STOP_ERROR : (keys * 2 > cM.pcap ? MG_STOP_GROW : 0u);
+        s_nlist = 0; s_nsb = 0;
+    }
+    __syncthreads();
+    bool first = true;
+
+    for (int step = first_step; step < cM.stop_at; step++) {
+        const u32 stop = s_stop;                 // uniform across the cluster (broadcast before the closing barrier)
+        if (stop == MG_STOP_ERROR) break;
+        if (stop == MG_STOP_GROW) {
+            if (rank == 0 && tid == 0) { cM.ctr[6] = prev_key; cM.ctr[3] = MG_NEED_GROW; }
+            break;
+        }
+        if (rank == 0 && tid == MG_NT - 1) cM.log_begin[step] = *((volatile u64 *)&cM.ctr[0]);
+#ifdef BPE_MERGE_PROFILE
+        const bool prof_thread = tid == 0 && (rank == 0 || token_cta);
+#else
+        const bool prof_thread = false;
+#endif
+        u64 t0 = prof_thread ? gtime_ns() : 0;
+        // ---- phase 1a: collect the dirty blocks of the superblocks this CTA owns into a CTA-wide work list -----
+        for (u32 k0 = 0; k0 < KS; k0 += 32) {
+            const u32 kk = k0 + lane;
+            const u32 sbl = gwarp + kk * total_warps;
+            u64 my = (kk < KS && sbl < cM.n_super) ? cM.sdirty_mask[sbl] : 0;      // one round trip for 32 masks
+            const u32 kend = KS - k0 < 32 ? KS - k0 : 32;
+            for (u32 q = 0; q < kend; q++) {
+                const u32 k = k0 + q, sb = gwarp + k * total_warps;
+                u64 dm = __shfl_sync(0xffffffffu, my, q);
+                if (sb >= cM.n_super) { if (first && lane == 0) s_smax[k * warps_per_cta + warp] = BEST_NONE; continue; }
+                if (!first && dm == 0) continue; // (at kernel start every superblock maximum has to be built)
+                const u32 nb = cM.n_blocks - sb * 64;
+                if (nb < 64) dm &= (1ull << nb) - 1;
+                const u32 cnt = __popcll(dm);
+                u32 base = 0;
+                if (lane == 0 && cnt) base = atomicAdd(&s_nlist, cnt);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (lane == 0 && dm) cM.sdirty_mask[sb] = 0;
+                if (cnt && base + cnt > TAIL_LIST_MAX) {
+                    // work list full (table just rebuilt: everything is dirty): this warp does the superblock on its own
+                    for (u32 r = lane; r < cnt && base + r < TAIL_LIST_MAX; r += 32) s_list[base + r] = 0xFFFFFFFFu;
+                    const u32 b0 = sb * 64 + lane, b1 = b0 + 32;
+                    Best m0 = BEST_NONE, m1 = BEST_NONE;
+                    if (b0 < cM.n_blocks) m0 = load_best(&cM.bmax[b0]);
+                    if (b1 < cM.n_blocks) m1 = load_best(&cM.bmax[b1]);
+                    while (dm) {
+                        u32 j = __ffsll((long long)dm) - 1; dm &= dm - 1;
+                        Best bst = rescan_block(sb * 64 + j, prev_key);
+                        if (lane == (j & 31)) { if (j < 32) m0 = bst; else m1 = bst; store_best(&cM.bmax[sb * 64 + j], bst); }
+                    }
+                    Best c = BEST_NONE;
+                    if (m0.cnt != CNT_DEAD) c = m0;
+                    if (m1.cnt != CNT_DEAD && best_greater(m1, c)) c = m1;
+                    c = warp_best(c);
+                    if (lane == 0) s_smax[k * warps_per_cta + warp] = c;
+                    continue;
+                }
+                for (u32 r = lane; r < cnt; r += 32) s_list[base + r] = sb * 64 + nth_set_bit64(dm, r);
+                if (lane == 0) s_sblist[atomicAdd(&s_nsb, 1u)] = k * warps_per_cta + warp;
+            }
+        }
+        first = false;
+        __syncthreads();
+        u64 ta = prof_thread ? gtime_ns() : 0;
+        if (prof_thread && rank == 0) { cM.prof[20] += s_nlist; cM.prof[21] += s_nsb; }
+        // ---- phase 1b: rescan the listed blocks, spread evenly over the warps ---------------------------------
+        {
+            const u32 nl = s_nlist < TAIL_LIST_MAX ? s_nlist : TAIL_LIST_MAX;
+            for (u32 i = warp; i < nl; i += warps_per_cta) {
+                const u32 blk = s_list[i];
+                if (blk == 0xFFFFFFFFu) continue;
+                Best bst = rescan_block(blk, prev_key);
+                if (lane == 0) { store_best(&cM.bmax[blk], bst); PROF_ADD(9, 1); }
+            }
+        }
+        __threadfence_block();
+        __syncthreads();
+        u64 tb = prof_thread ? gtime_ns() : 0;
+        // ---- phase 1c: maxima of the superblocks that had dirty blocks ------------------------------------------
+        {
+            const u32 ns = s_nsb;
+            for (u32 i = warp; i < ns; i += warps_per_cta) {
+                const u32 local = s_sblist[i];
+                const u32 sb = rank * warps_per_cta + (local % warps_per_cta) + (local / warps_per_cta) * total_warps;
+                Best c = superblock_max(sb, lane);
+                if (lane == 0) s_smax[local] = c;
+            }
+        }
+        __syncthreads();
+        u64 tc = prof_thread ? gtime_ns() : 0;
+        if (tid == 0) { s_nlist = 0; s_nsb = 0; }
+        // ---- phase 2: CTA candidate from its superblock maxima, exchanged through distributed shared memory ----
+        {
+            Best mine = BEST_NONE;
+            for (u32 i = tid; i < KS * warps_per_cta; i += MG_NT) { Best e = s_smax[i]; if (e.cnt != CNT_DEAD && best_greater(e, mine)) mine = e; }
+            mine = warp_best(mine);
+            if (lane == 0) s_best[warp] = mine;
+            __syncthreads();
+            if (warp == 0) {
+                Best c = lane < warps_per_cta ? s_best[lane] : BEST_NONE;
+                c = warp_best(c);
+                if (lane < C) store_best(cl.map_shared_rank(&s_cand[rank], lane), c);
+            }
+        }
+        u64 t1 = prof_thread ? gtime_ns() : 0;
+        cl.sync();
+        u64 t2 = prof_thread ? gtime_ns() : 0;
+        if (warp == 0) {
+            Best c = lane < C ? load_best(&s_cand[lane]) : BEST_NONE;
+            c = warp_best(c);
+            if (lane == 0) {
+                s_win = c;
+                if (c.cnt != CNT_DEAD) winner_range(c.key, s_range);   // index range of the winner, read once per CTA
+            }
+        }
+        __syncthreads();
+        const Best win = s_win;
+        if (win.cnt == CNT_DEAD) break;          // len(byte_pair_frequencies) == 0 (train.py:184-185): uniform across the cluster
+        const u32 a = (u32)(win.key >> 32), b = (u32)win.key;
+        const u32 nw = n_tok;
+        const u64 r_lo = s_range[0], r_hi = s_range[1];
+        if (token_cta) {
+            token_bookkeeping(step, win, a, b, nw, prof_thread, t2);
+            if (tid == 0) {                      // stop code for the next step, broadcast to every CTA
+                u64 st = *((volatile u64 *)&cM.ctr[3]), keys = *((volatile u64 *)&cM.ctr[2]);
+                u32 code = st ? MG_STOP_ERROR : (keys * 2 > cM.pcap ? MG_STOP_GROW : 0u);
+                for (u32 r = 0; r < C; r++) *cl.map_shared_rank(&s_stop, r) = code;
+            }
+        } else {
+            apply_winner(step, a, b, nw, r_lo, r_hi, s_range[2] ? cM.log2 : cM.log, (u64)rank * MG_NT + tid, (u64)apply_ctas * MG_NT);
+        }
+        prev_key = win.key;
+        n_tok++;
+        u64 t3 = prof_thread ? gtime_ns() : 0;
+        cl.sync();
+        if (prof_thread) {
+            u64 t4 = gtime_ns();
+            if (rank == 0) {
+                cM.prof[0] += t1 - t0; cM.prof[1] += t2 - t1; cM.prof[2] += t3 - t2; cM.prof[3] += t4 - t3; cM.prof[7] += 1;
+                cM.prof[16] += ta - t0; cM.prof[17] += tb - ta; cM.prof[18] += tc - tb; cM.prof[19] += t1 - tc; cM.prof[22] += r_hi - r_lo;
+            }
+            if (token_cta) cM.prof[4] += t3 - t2;
+        }
+        if ((r_hi - r_lo) * 2 >= SORT_MIN) {     // heuristic: about two records per index entry visited
+            u64 ts = prof_thread ? gtime_ns() : 0;
+            const u64 lb = *((volatile u64 *)&cM.log_begin[step]), cur = *((volatile u64 *)&cM.ctr[0]);
+            const u64 pool = *((volatile u64 *)&cM.ctr[9]);
+            if (cur - lb >= SORT_MIN && cur <= cM.log_cap && pool + SORT_MAX_BK + 1 <= cM.bk_off_cap) {
+                sort_slice(step, lb, (u32)(cur - lb), n_sorts & 1u, rank == 0, (u64)rank * MG_NT + tid, (u64)C * MG_NT, s_scan,
+                           [&]() { cl.sync(); });
+                n_sorts++;
+            }
+            if (prof_thread && rank == 0) { cM.prof[23] += gtime_ns() - ts; cM.prof[24] += 1; }
+        }
+    }
+    if (rank == 0 && tid == 0) cM.ctr[6] = prev_key;
+    cl.sync();                                   // nobody leaves while a peer may still touch its shared memory
 }
 
 __global__ void __launch_bounds__(256) k_insert_initial_pairs(const u64 *__restrict__ dense) {
