@@ -14,10 +14,14 @@
 //   tie-break    (count, (bytes_a, bytes_b)) with python's bytes ordering.  Each token keeps its
 //                first 8 bytes as a big-endian integer (tok_key): comparing the integers decides
 //                almost every tie; equal prefixes fall back to lengths / a byte loop.
-//   token_indices  for pairs of two initial bytes: CSR built once from the initial words; for any
-//                other pair (p,q) every occurrence is created in the step that created the younger
-//                of p,q, so it is found by filtering that step's slice of an append-only log.
-//                Stale entries are harmless (the rewrite re-checks symbols, like the reference).
+//   words        symbols never move: a merge writes the new token over its left operand and a tombstone over the
+//                right one, so an occurrence is addressed by the position of its left symbol for ever.
+//   token_indices  one record (neighbour, position, word count) per pair OCCURRENCE.  Pairs of two initial bytes:
+//                CSR built once; any other pair (p,q): every occurrence is created in the step that created the
+//                younger of p,q, so it is found in that step's slice of an append-only log (bucket-sorted by
+//                neighbour when large).  Stale records are harmless (the symbols are re-checked, like the
+//                reference re-checks its stale index entries, train.py:196-200).  One thread per occurrence:
+//                no per-word serialisation, three dependent memory round trips per merge site.
 #pragma once
 #include <cooperative_groups.h>
 #include <cooperative_groups/scan.h>
@@ -34,19 +38,30 @@ namespace cg = cooperative_groups;
 #define CTA_BEST_STRIDE 32u                       // Best entries (1 KiB) between per-CTA candidates: spreads the all-read-all
                                                  // exchange over many L2 slices instead of hammering a handful of lines                        // ctr[3] code: pair table more than half full, host must grow it
 
-// one 32-byte sector per word: the claim (atomicExch on stamp) pulls in everything the rewrite needs
-struct __align__(32) WordMeta {
-    u32 off, len;        // word w occupies sym[off, off+len)
-    u32 stamp;           // last merge step (+1) that processed the word
-    u32 pad0;
+struct __align__(16) WordMeta {
+    u32 off, len;        // word w occupies sym[off, off+len) at build time
     i64 cnt;             // word frequency
-    i64 pad1;
 };
+// Symbol array: every word is preceded by one SYM_SEP; the array starts and ends with SYM_PAD separators, so the
+// neighbour scans of apply_site never need a bounds check.  Values: >= 0 live symbol, SYM_SEP word boundary,
+// <= -2 tombstone written by merge step (-v - 2).
+#define SYM_SEP (-1)
+#define SYM_PAD 32u
 struct Words {
-    int32_t *sym;        // symbols of all words
+    int32_t *sym;
     WordMeta *meta;
-    u64 *counters;       // [0]=n_words [1]=n_syms [2]=max_len
+    u64 *counters;       // [0]=n_words [1]=sym slots used (symbols + one separator per word) [2]=max_len
 };
+// index record: one pair occurrence.  x = neighbour token (bit 31: the neighbour is on the right), pos = position of
+// the occurrence's left symbol, cnt = frequency of the word it lies in
+struct __align__(16) Rec { u32 x, pos; i64 cnt; };
+__device__ __forceinline__ Rec load_rec(const Rec *p) {
+    uint4 v = *reinterpret_cast<const uint4 *>(p);
+    Rec r; r.x = v.x; r.pos = v.y; r.cnt = (i64)(((u64)v.w << 32) | v.z); return r;
+}
+__device__ __forceinline__ void store_rec(Rec *p, u32 x, u32 pos, i64 cnt) {
+    *reinterpret_cast<uint4 *>(p) = make_uint4(x, pos, (u32)cnt, (u32)((u64)cnt >> 32));
+}
 
 // candidate of the argmax: count, pair key, and the 8-byte prefix keys of both tokens (so that almost every
 // tie is broken in registers, without dependent loads)
@@ -72,11 +87,11 @@ struct MergeState {
     Words W; u32 n_words;
     u64 *pkey; i64 *pcnt; u64 pcap;
     Best *bmax; uint8_t *dirty; u32 n_blocks;
-    const u32 *csr_off; const u32 *csr_words;
-    uint2 *log; u64 *log_begin; u64 log_cap;
+    const u32 *csr_off; const Rec *csr_rec;
+    Rec *log; u64 *log_begin; u64 log_cap;
     // big log slices are bucket-sorted by hash(neighbour) into log2 right after the step that wrote them:
     // bk_lg[step] = log2(buckets) (0 = slice left unsorted), bk_start[step] = first of its buckets+1 offsets in bk_off
-    uint2 *log2; u32 *bk_lg; u64 *bk_start; u32 *bk_off; u64 bk_off_cap; u32 *bk_scratch;   // bk_scratch: 2 x (hist, cursor) x SORT_MAX_BK
+    Rec *log2; u32 *bk_lg; u64 *bk_start; u32 *bk_off; u64 bk_off_cap; u32 *bk_scratch;   // bk_scratch: 2 x (hist, cursor) x SORT_MAX_BK
     u32 *tok_off; u32 *tok_len; u64 *tok_key; uint8_t *tok_bytes; u64 tok_bytes_cap;
     Best *cta_best;
     // tail kernel (one thread-block cluster): per 64-block superblock a 64-bit mask of dirty blocks
@@ -223,26 +238,73 @@ __device__ __forceinline__ void pair_add(u32 a, u32 b, i64 delta) {
     pair_add_from(key, delta, s, cM.pkey[s]);
 }
 
-// Apply merge (a,b)->nw to word w: the left-to-right scan of train.py:196-224 with
-// update_frequencies_after_merge (52-78), merge_subwords (132-139) and create_new_token_indices (107-129).
-__device__ __noinline__ void apply_merge_to_word(u32 w, u32 a, u32 b, u32 nw) {
-    WordMeta *wm = &cM.W.meta[w];
-    int32_t *s = cM.W.sym + wm->off;
-    const u32 len = wm->len;
-    const i64 c = wm->cnt;
-    // pass 1: how many index records will this word append (one per neighbour of every merge site)?
-    u32 n_rec = 0, n_site = 0;
-    {
-        u32 r = 0, o = 0;
-        while (r + 1 < len) {
-            if ((u32)s[r] == a && (u32)s[r + 1] == b) { n_rec += (o > 0) + (r + 2 < len); n_site++; r += 2; }
-            else r++;
-            o++;
+// Apply merge (a,b)->nw at the occurrence whose left symbol sits at position p (word frequency c): one merge site of the
+// left-to-right scan of train.py:196-224 with update_frequencies_after_merge (52-78), merge_subwords (132-139) and
+// create_new_token_indices (107-129).
+//
+// All sites of a step run concurrently, so every thread reasons about the state AT THE START OF THE STEP, which it can
+// always reconstruct: a symbol equal to nw was `a`, a tombstone of this step was `b`.  The reference's sequential
+// semantics in those terms:
+//   * a record is a site iff its symbols are (a,b) and -- for a == b, inside a run of a's -- it sits at an even offset
+//     from the start of the run (non-overlapping, left to right: aaaa -> [aa, aa], aaa -> [aa, a]);
+//   * the left neighbour is the already merged token when the occurrence directly to the left is a site as well
+//     (abab: the second site sees (nw, a), decrements it and creates (nw, nw)); the right neighbour is always the
+//     unmerged symbol (the scan has not reached it yet);
+//   * both new pairs are indexed, even if the right one is merged away later in the same step (stale, harmless).
+__device__ __noinline__ void apply_site(u32 p, i64 c, u32 a, u32 b, u32 nw, int step) {
+    int32_t *s = cM.W.sym;
+    const int32_t dead_now = -(step + 2);
+    const int32_t ia = (int32_t)a, ib = (int32_t)b, inw = (int32_t)nw;
+#define ORIG(e) ((e) == inw ? ia : ((e) == dead_now ? ib : (e)))            /* value at the start of the step */
+#define WAS_LIVE(e) ((e) >= 0 || (e) == dead_now)                          /* live at the start of the step */
+#define SKIP_OLD_LEFT(q) while (s[q] < SYM_SEP && s[q] != dead_now) (q)--   /* tombstones of earlier steps */
+#define SKIP_OLD_RIGHT(q) while (s[q] < SYM_SEP && s[q] != dead_now) (q)++
+    const int32_t e0 = s[p];
+    if (!WAS_LIVE(e0) || ORIG(e0) != ia) return;                           // stale record
+    u32 pb = p + 1;
+    SKIP_OLD_RIGHT(pb);
+    { const int32_t e = s[pb]; if (!WAS_LIVE(e) || ORIG(e) != ib) return; } // stale record
+    // ---- left context ----
+    bool has_l = false; u32 left = 0, pos_l = 0;
+    u32 q = p - 1;
+    SKIP_OLD_LEFT(q);
+    if (a == b) {
+        // run of a's ending just before p: its length decides whether p starts a site
+        u32 n_left = 0, first = p, second = p;                             // positions of the two nearest a's on the left
+        while (WAS_LIVE(s[q]) && ORIG(s[q]) == ia) {
+            n_left++;
+            if (n_left == 1) first = q; else if (n_left == 2) second = q;
+            q--;
+            SKIP_OLD_LEFT(q);
+        }
+        if (n_left & 1u) return;                                           // the a at p is the right half of the previous site
+        if (n_left) { has_l = true; left = nw; pos_l = second; (void)first; }
+        else if (s[q] != SYM_SEP) { has_l = true; left = (u32)ORIG(s[q]); pos_l = q; }
+    } else if (s[q] != SYM_SEP) {
+        const int32_t o1 = ORIG(s[q]);
+        has_l = true; left = (u32)o1; pos_l = q;
+        if (o1 == ib) {                                                    // (.., a, b, [a, b]): the left occurrence is a site too
+            u32 q2 = q - 1;
+            SKIP_OLD_LEFT(q2);
+            if (WAS_LIVE(s[q2]) && ORIG(s[q2]) == ia) { left = nw; pos_l = q2; }
         }
     }
-    if (n_site == 0) return;                     // stale index entry: the pair no longer occurs here
+    // ---- right context: the symbol as it was (it is merged later, if at all) ----
+    u32 qr = pb + 1;
+    SKIP_OLD_RIGHT(qr);
+    const bool has_r = s[qr] != SYM_SEP;
+    const u32 right = has_r ? (u32)ORIG(s[qr]) : 0;
+    // ---- the four dict updates of update_frequencies_after_merge: first probes issued together ----
+    const u64 mask = cM.pcap - 1;
+    const u64 k0 = ((u64)left << 32) | a, k1 = ((u64)left << 32) | nw, k2 = ((u64)b << 32) | right, k3 = ((u64)nw << 32) | right;
+    const u64 s0 = mix64(k0) & mask, s1 = mix64(k1) & mask, s2 = mix64(k2) & mask, s3 = mix64(k3) & mask;
+    u64 v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+    if (has_l) { v0 = cM.pkey[s0]; v1 = cM.pkey[s1]; }
+    if (has_r) { v2 = cM.pkey[s2]; v3 = cM.pkey[s3]; }
+    // index records of the two new pairs: one atomic per group of threads that arrive here together
+    const u32 n_rec = (u32)has_l + (u32)has_r;
     u64 li = 0;
-    if (n_rec) {                                 // one atomic per group of threads that arrive here together
+    if (n_rec) {
         cg::coalesced_group cgp = cg::coalesced_threads();
         u32 pre = cg::exclusive_scan(cgp, n_rec);
         u64 base = 0;
@@ -251,40 +313,24 @@ __device__ __noinline__ void apply_merge_to_word(u32 w, u32 a, u32 b, u32 nw) {
     }
     const bool log_ok = li + n_rec <= cM.log_cap;
     if (!log_ok) cM.ctr[3] = 2;
-    const u64 mask = cM.pcap - 1;
-    u32 o = 0, r = 0;
-    while (r + 1 < len) {
-        if ((u32)s[r] == a && (u32)s[r + 1] == b) {
-            const bool has_l = o > 0, has_r = r + 2 < len;
-            const u32 left = has_l ? (u32)s[o - 1] : 0, right = has_r ? (u32)s[r + 2] : 0;
-            // the four dict updates of update_frequencies_after_merge: first probes issued together
-            u64 k0 = ((u64)left << 32) | a, k1 = ((u64)left << 32) | nw, k2 = ((u64)b << 32) | right, k3 = ((u64)nw << 32) | right;
-            u64 s0 = mix64(k0) & mask, s1 = mix64(k1) & mask, s2 = mix64(k2) & mask, s3 = mix64(k3) & mask;
-            u64 v0 = 0, v1 = 0, v2 = 0, v3 = 0;
-            if (has_l) { v0 = cM.pkey[s0]; v1 = cM.pkey[s1]; }
-            if (has_r) { v2 = cM.pkey[s2]; v3 = cM.pkey[s3]; }
-            if (has_l) {
-                pair_add_from(k0, -c, s0, v0);
-                pair_add_from(k1, c, s1, v1);
-                if (log_ok) cM.log[li] = make_uint2(left, w);                       // (left, nw): side L, other = left
-                li++;
-            }
-            if (has_r) {
-                pair_add_from(k2, -c, s2, v2);
-                pair_add_from(k3, c, s3, v3);
-                if (log_ok) cM.log[li] = make_uint2(0x80000000u | right, w);        // (nw, right): side R, other = right
-                li++;
-            }
-            s[o++] = (int32_t)nw; r += 2;
-        } else {
-            s[o++] = s[r++];
-        }
+    s[p] = inw; s[pb] = dead_now;                                          // merge_subwords: positions never move
+    if (has_l) {
+        pair_add_from(k0, -c, s0, v0);
+        pair_add_from(k1, c, s1, v1);
+        if (log_ok) store_rec(&cM.log[li], left, pos_l, c);                 // (left, nw) at the position of `left`
+        li++;
     }
-#pragma unroll 1
-    while (r < len) s[o++] = s[r++];
-    wm->len = o;
+    if (has_r) {
+        pair_add_from(k2, -c, s2, v2);
+        pair_add_from(k3, c, s3, v3);
+        if (log_ok) store_rec(&cM.log[li], 0x80000000u | right, p, c);      // (nw, right) at p
+    }
     atomicAdd(&cM.ctr[8], 1ull);
     PROF_ADD(6, 1);
+#undef ORIG
+#undef WAS_LIVE
+#undef SKIP_OLD_LEFT
+#undef SKIP_OLD_RIGHT
 }
 
 // Rescan the PB slots of one block with a full warp.  Pops `prev_key` when it meets it and repairs
@@ -350,6 +396,8 @@ __device__ __forceinline__ void token_bookkeeping(int step, const Best &win, u32
     }
 }
 
+// source array of an index range: 0 = log, 1 = bucket-sorted copy, 2 = CSR of the initial byte pairs
+#define T_SRC(code) ((code) == 2 ? cM.csr_rec : ((code) == 1 ? (const Rec *)cM.log2 : (const Rec *)cM.log))
 #define SORT_MIN 2048u                           // slices with fewer records are scanned whole
 #define SORT_MAX_LG 12u                          // at most 4096 buckets
 #define SORT_MAX_BK (1u << SORT_MAX_LG)
@@ -359,7 +407,7 @@ __device__ __forceinline__ u32 bucket_of(u32 x, u32 lg) { return (x * 0x9E3779B1
 // the range lies in the bucket-sorted copy (log2).  One thread per CTA.
 __device__ __forceinline__ void winner_range(u64 key, u64 *out) {
     const u32 wa = (u32)(key >> 32), wb = (u32)key, wT = wa > wb ? wa : wb;
-    if (wT < 256) { u32 pp = (wa << 8) | wb; out[0] = cM.csr_off[pp]; out[1] = cM.csr_off[pp + 1]; out[2] = 0; return; }
+    if (wT < 256) { u32 pp = (wa << 8) | wb; out[0] = cM.csr_off[pp]; out[1] = cM.csr_off[pp + 1]; out[2] = 2; return; }
     const u32 t = wT - 256;
     const u64 lo = cM.log_begin[t], hi = cM.log_begin[t + 1];
     const u32 lg = cM.bk_lg[t];
@@ -416,44 +464,30 @@ __device__ __forceinline__ void sort_slice(int step, u64 lo, u32 n, u32 parity, 
     }
     __syncthreads();
     for (u64 i = gthread; i < n; i += gstride) {
-        uint2 r = cM.log[lo + i];
-        u32 bk = bucket_of(r.x, lg);
-        cM.log2[lo + s_scan[bk] + atomicAdd(&cur[bk], 1u)] = r;
+        const uint4 r = *reinterpret_cast<const uint4 *>(&cM.log[lo + i]);
+        const u32 bk = bucket_of(r.x, lg);
+        *reinterpret_cast<uint4 *>(&cM.log2[lo + s_scan[bk] + atomicAdd(&cur[bk], 1u)]) = r;
     }
     sync();
 }
 
-// ---- apply the merge to every word indexed under (a,b): index slice [lo, hi) filtered by `gthread` of `gstride` threads
-__device__ __forceinline__ void apply_winner(int step, u32 a, u32 b, u32 nw, u64 lo, u64 hi, const uint2 *__restrict__ logsrc, u64 gthread, u64 gstride) {
+// ---- apply the merge at every occurrence indexed under (a,b): index slice [lo, hi) spread over `gstride` threads ----
+__device__ __forceinline__ void apply_winner(int step, u32 a, u32 b, u32 nw, u64 lo, u64 hi, const Rec *__restrict__ src, u64 gthread, u64 gstride) {
     const u32 T = a > b ? a : b;
     if (gthread == 0) PROF_ADD(5, hi - lo);
-    if (T < 256) {
-        for (u64 i = lo + gthread; i < hi; i += 4 * gstride) {       // 4 candidates in flight per thread
-            const u32 none = 0xFFFFFFFFu;
-            u32 w0 = cM.csr_words[i];
-            u32 w1 = i + gstride < hi ? cM.csr_words[i + gstride] : none;
-            u32 w2 = i + 2 * gstride < hi ? cM.csr_words[i + 2 * gstride] : none;
-            u32 w3 = i + 3 * gstride < hi ? cM.csr_words[i + 3 * gstride] : none;
-#pragma unroll 1
-            for (int k = 0; k < 4; k++) {
-                u32 w = k == 0 ? w0 : k == 1 ? w1 : k == 2 ? w2 : w3;
-                if (w != none && atomicExch(&cM.W.meta[w].stamp, (u32)step + 1) != (u32)step + 1) apply_merge_to_word(w, a, b, nw);
-            }
-        }
-    } else {
-        u32 want = b >= a ? a : (0x80000000u | b);
-        for (u64 i = lo + gthread; i < hi; i += 4 * gstride) {       // 4 records in flight per thread
-            const uint2 none = make_uint2(0xFFFFFFFFu, 0);
-            uint2 r0 = logsrc[i];
-            uint2 r1 = i + gstride < hi ? logsrc[i + gstride] : none;
-            uint2 r2 = i + 2 * gstride < hi ? logsrc[i + 2 * gstride] : none;
-            uint2 r3 = i + 3 * gstride < hi ? logsrc[i + 3 * gstride] : none;
-#pragma unroll 1
-            for (int k = 0; k < 4; k++) {
-                uint2 r = k == 0 ? r0 : k == 1 ? r1 : k == 2 ? r2 : r3;
-                if (r.x == want && atomicExch(&cM.W.meta[r.y].stamp, (u32)step + 1) != (u32)step + 1) apply_merge_to_word(r.y, a, b, nw);
-            }
-        }
+    // pairs of two initial bytes: the CSR slice holds exactly the occurrences of (a,b); otherwise filter by neighbour
+    const bool filter = T >= 256;
+    const u32 want = b >= a ? a : (0x80000000u | b);
+    for (u64 i = lo + gthread; i < hi; i += 4 * gstride) {               // 4 records in flight per thread
+        Rec r0 = load_rec(&src[i]), r1, r2, r3;
+        const bool h1 = i + gstride < hi, h2 = i + 2 * gstride < hi, h3 = i + 3 * gstride < hi;
+        if (h1) r1 = load_rec(&src[i + gstride]);
+        if (h2) r2 = load_rec(&src[i + 2 * gstride]);
+        if (h3) r3 = load_rec(&src[i + 3 * gstride]);
+        if (!filter || r0.x == want) apply_site(r0.pos, r0.cnt, a, b, nw, step);
+        if (h1 && (!filter || r1.x == want)) apply_site(r1.pos, r1.cnt, a, b, nw, step);
+        if (h2 && (!filter || r2.x == want)) apply_site(r2.pos, r2.cnt, a, b, nw, step);
+        if (h3 && (!filter || r3.x == want)) apply_site(r3.pos, r3.cnt, a, b, nw, step);
     }
 }
 
@@ -546,7 +580,7 @@ __global__ void __launch_bounds__(MG_NT) k_merge_loop() {
         const u64 r_lo = s_range[0], r_hi = s_range[1];
 
         if (token_cta) token_bookkeeping(step, win, a, b, nw, prof_thread, t2);
-        else apply_winner(step, a, b, nw, r_lo, r_hi, s_range[2] ? cM.log2 : cM.log, (u64)blockIdx.x * MG_NT + tid, (u64)apply_ctas * MG_NT);
+        else apply_winner(step, a, b, nw, r_lo, r_hi, T_SRC(s_range[2]), (u64)blockIdx.x * MG_NT + tid, (u64)apply_ctas * MG_NT);
         prev_key = win.key;
         n_tok++;
         u64 t3 = prof_thread ? gtime_ns() : 0;
@@ -777,7 +811,7 @@ __global__ void __launch_bounds__(MG_NT) k_merge_tail() {
                 for (u32 r = 0; r < C; r++) *cl.map_shared_rank(&s_stop, r) = code;
             }
         } else {
-            apply_winner(step, a, b, nw, r_lo, r_hi, s_range[2] ? cM.log2 : cM.log, (u64)rank * MG_NT + tid, (u64)apply_ctas * MG_NT);
+            apply_winner(step, a, b, nw, r_lo, r_hi, T_SRC(s_range[2]), (u64)rank * MG_NT + tid, (u64)apply_ctas * MG_NT);
         }
         prev_key = win.key;
         n_tok++;
