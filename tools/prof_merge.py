@@ -20,7 +20,8 @@ print("per-step us: phase1 %.2f sync1 %.2f apply %.2f sync2 %.2f | tokenCTA %.2f
 print("slow compares per step: %.1f" % (p[8] / steps))
 print("tail detail us/step: p1a %.2f p1b %.2f p1c %.2f p2 %.2f | list blocks %.1f superblocks %.1f | index range %.0f | sort: %d sorts, %.2f us each, ctr10-like" % (
     p[16]/steps/1e3, p[17]/steps/1e3, p[18]/steps/1e3, p[19]/steps/1e3, p[20]/steps, p[21]/steps, p[22]/steps, p[24], p[23]/max(p[24],1)/1e3))
-print("token CTA us/step: winner %.2f meta %.2f bytes+key %.2f probe %.2f | winner (SM cycles): loads+cmp %.0f warp_best %.0f" % tuple([p[i] / steps / 1e3 for i in (10, 11, 12, 13)] + [p[14] / steps, p[15] / steps]))
+print("token CTA us/step: winner %.2f meta %.2f bytes+key %.2f | CTA0 winner phase us: candidate loads %.2f compare+warp_best %.2f winner_range %.2f" % tuple([p[i] / steps / 1e3 for i in (10, 11, 12, 13, 14, 15)]))
+print("local compares of 5 candidates: %.2f us" % (p[25] / steps / 1e3))
 import os
 if os.environ.get("BPE_STEP_PROFILE"):
     a = np.fromfile(os.environ["BPE_STEP_PROFILE"], dtype=np.uint32).reshape(-1, 4).astype(np.int64)

@@ -35,7 +35,7 @@ namespace cg = cooperative_groups;
 #define PB 64u                                   // pair-table slots per block (one rescan = two slots per lane)
 #define MG_NT 512
 #define MG_NEED_GROW 8ull
-#define CTA_BEST_STRIDE 32u                       // Best entries (1 KiB) between per-CTA candidates: spreads the all-read-all
+#define CTA_BEST_STRIDE 1u                       // Best entries (1 KiB) between per-CTA candidates: spreads the all-read-all
                                                  // exchange over many L2 slices instead of hammering a handful of lines                        // ctr[3] code: pair table more than half full, host must grow it
 
 struct __align__(16) WordMeta {
@@ -116,9 +116,12 @@ __constant__ MergeState cM;
 
 #ifdef BPE_MERGE_PROFILE
 __device__ __forceinline__ u64 gtime_ns() { u64 t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+// timer read that cannot be scheduled before `dep` is available
+__device__ __forceinline__ u64 gtime_after(u64 dep) { u64 t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t) : "l"(dep) : "memory"); return t; }
 #define PROF_ADD(i, v) atomicAdd(&cM.prof[i], (u64)(v))
 #else
 __device__ __forceinline__ u64 gtime_ns() { return 0; }
+__device__ __forceinline__ u64 gtime_after(u64) { return 0; }
 #define PROF_ADD(i, v) do { } while (0)
 #endif
 
@@ -136,7 +139,7 @@ __device__ __noinline__ bool tok_greater_slow(u32 p, u32 q) {
 }
 // Tie-break of two candidates with equal counts: python's ((bytes_a, bytes_b)) tuple order.  A real function
 // (not inlined): the persistent kernel must stay small, see the note at cM.
-__device__ __noinline__ bool best_tie_greater(u64 xkey, u64 xka, u64 xkb, u64 ykey, u64 yka, u64 ykb) {
+__device__ __forceinline__ bool best_tie_greater(u64 xkey, u64 xka, u64 xkb, u64 ykey, u64 yka, u64 ykb) {
     u32 xa = (u32)(xkey >> 32), ya = (u32)(ykey >> 32);
     if (xa != ya) return xka != yka ? xka > yka : tok_greater_slow(xa, ya);
     u32 xb = (u32)xkey, yb = (u32)ykey;
@@ -564,13 +567,18 @@ __global__ void __launch_bounds__(MG_NT) k_merge_loop() {
             Best o5[5];                          // G <= 160: every lane issues its (up to) 5 loads before using any
 #pragma unroll
             for (u32 k = 0; k < 5; k++) { u32 i = lane + 32 * k; o5[k] = i < G ? load_best(&cM.cta_best[i * CTA_BEST_STRIDE]) : BEST_NONE; }
+            u64 tl0 = 0, tl1 = 0, tl2 = 0;
+            if (prof_thread) { u64 d = 0; for (u32 k = 0; k < 5; k++) d ^= (u64)o5[k].cnt ^ o5[k].key ^ o5[k].ka ^ o5[k].kb; tl0 = gtime_after(d); }
 #pragma unroll
             for (u32 k = 0; k < 5; k++) if (o5[k].cnt != CNT_DEAD && best_greater(o5[k], c)) c = o5[k];
+            if (prof_thread && blockIdx.x == 0) cM.prof[25] += gtime_after((u64)c.cnt ^ c.key ^ c.ka ^ c.kb) - tl0;
             c = warp_best(c);
+            if (prof_thread) tl1 = gtime_after((u64)c.cnt ^ c.key ^ c.ka ^ c.kb);
             if (lane == 0) {
                 s_win = c;
                 if (c.cnt != CNT_DEAD) winner_range(c.key, s_range);   // index range of the winner, read once per CTA
             }
+            if (prof_thread && blockIdx.x == 0) { tl2 = gtime_after(s_range[0] ^ s_range[1]); cM.prof[13] += tl0 - t2; cM.prof[14] += tl1 - tl0; cM.prof[15] += tl2 - tl1; }
         }
         __syncthreads();
         const Best win = s_win;

@@ -856,6 +856,7 @@ static int run_merges(bpe_ctx *ctx, const uint8_t *sp_blob, const u32 *sp_offs, 
         } else {
             // grid: one CTA per SM for big tables, fewer for small ones (cheaper grid syncs)
             int G = std::max(2, (int)std::min<u64>((u64)std::min(ctx->sm_count, 160), (u64)M.n_blocks / 256 + 1 + (n_words + 4095) / 4096));
+            if (const char *e = getenv("BPE_MERGE_G")) G = std::max(2, std::min(atoi(e), std::min(ctx->sm_count, 160)));
             g_bpe_launches++;
             CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_merge_loop, dim3(G), dim3(MG_NT), nullptr, 0, st));
         }
