@@ -140,32 +140,18 @@ __device__ __forceinline__ u32 enc_long_ref(const EncTables &t, const uint8_t *p
     return 0;
 }
 
-// One thread per 32-byte flag word; slots[ordinal of the pretoken inside the batch] = its cache slot.
-__global__ void __launch_bounds__(256) k_enc_lookup(EncTables t, const u32 *__restrict__ flags, u64 n, u64 word_begin, u64 word_end,
-                                                   const u64 *__restrict__ pre, u32 *__restrict__ slots) {
-    const u64 base_ord = pre[word_begin];
-    for (u64 w = word_begin + (u64)blockIdx.x * blockDim.x + threadIdx.x; w < word_end; w += (u64)gridDim.x * blockDim.x) {
-        u32 bits = flags[w];
-        u64 o = pre[w] - base_ord;
-        while (bits) {
-            u32 j = __ffs(bits) - 1; bits &= bits - 1;
-            u64 pos = (w << 5) + j;
-            u64 end = bits ? (w << 5) + (__ffs(bits) - 1) : flags_next_start(flags, (w + 1) << 5, n);
-            u64 len = end - pos;
-            const uint8_t *p = t.text + pos;
-            u32 ref = 0;
-            if (len <= SHORT_MAX) {
-                u64 key = 0;
-                for (u32 k = 0; k < (u32)len; k++) key |= (u64)p[k] << (8 * k);
-                key |= len << 56;
-                ref = enc_short_ref(t, key);
-            } else if (len <= MAX_TOKEN_LEN) {
-                ref = enc_long_ref(t, p, (u32)len, pos);
-            } else {
-                t.ctr[6] = 1;
-            }
-            slots[o++] = ref;
-        }
+// One thread per pretoken occurrence i of the batch (bytes [base + offs[i], base + offs[i+1])): slots[i] = its cache slot.
+__global__ void __launch_bounds__(256) k_enc_lookup(EncTables t, const u32 *__restrict__ offs, u64 n_items, u64 base,
+                                                   u32 *__restrict__ slots) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += (u64)gridDim.x * blockDim.x) {
+        const u64 pos = base + offs[i];
+        const u64 len = base + offs[i + 1] - pos;
+        const uint8_t *p = t.text + pos;
+        u32 ref = 0;
+        if (len <= SHORT_MAX) ref = enc_short_ref(t, short_key(p, (u32)len));
+        else if (len <= MAX_TOKEN_LEN) ref = enc_long_ref(t, p, (u32)len, pos);
+        else t.ctr[6] = 1;
+        slots[i] = ref;
     }
 }
 
@@ -318,44 +304,30 @@ __device__ __forceinline__ u32 value_count(u64 v) {
     return tag <= 3 ? tag : (tag == VAL_EXT ? (u32)(v & 0xFFFFFFu) : 0);
 }
 
-// tokens per flag word
-__global__ void __launch_bounds__(256) k_enc_count(EncTables t, const u32 *__restrict__ flags, u64 word_begin, u64 word_end,
-                                                  const u64 *__restrict__ pre, const u32 *__restrict__ slots, u32 *__restrict__ wcnt) {
-    const u64 base_ord = pre[word_begin];
-    for (u64 w = word_begin + (u64)blockIdx.x * blockDim.x + threadIdx.x; w < word_end; w += (u64)gridDim.x * blockDim.x) {
-        u32 bits = flags[w];
-        u64 o = pre[w] - base_ord;
-        u32 c = 0;
-        while (bits) {
-            u32 j = __ffs(bits) - 1; bits &= bits - 1;
-            u64 v = enc_value(t, slots[o++]);
-            if (VAL_TAG(v) == VAL_ERR) atomicMin(&t.ctr[7], (w << 5) + j);
-            c += value_count(v);
-        }
-        wcnt[w - word_begin] = c;
+// tokens per pretoken occurrence (a KeyError value records the smallest text offset it occurs at)
+__global__ void __launch_bounds__(256) k_enc_ntok(EncTables t, const u32 *__restrict__ slots, const u32 *__restrict__ offs, u64 n_items,
+                                                 u64 base, u32 *__restrict__ ntok) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += (u64)gridDim.x * blockDim.x) {
+        const u64 v = enc_value(t, slots[i]);
+        if (VAL_TAG(v) == VAL_ERR) atomicMin(&t.ctr[7], base + offs[i]);
+        ntok[i] = value_count(v);
     }
 }
 
+// ids of pretoken i go to out[out_base + tokoff[i] ...]: neighbouring threads write neighbouring ids
 template <typename OutT>
-__global__ void __launch_bounds__(256) k_enc_emit(EncTables t, const u32 *__restrict__ flags, u64 word_begin, u64 word_end,
-                                                 const u64 *__restrict__ pre, const u32 *__restrict__ slots,
-                                                 const u64 *__restrict__ woff, OutT *__restrict__ out, u64 out_base, u64 cap) {
-    const u64 base_ord = pre[word_begin];
-    for (u64 w = word_begin + (u64)blockIdx.x * blockDim.x + threadIdx.x; w < word_end; w += (u64)gridDim.x * blockDim.x) {
-        u32 bits = flags[w];
-        u64 o = pre[w] - base_ord;
-        u64 dst = out_base + woff[w - word_begin];
-        while (bits) {
-            bits &= bits - 1;
-            u64 v = enc_value(t, slots[o++]);
-            u32 tag = VAL_TAG(v);
-            if (tag <= 3) {
-                for (u32 k = 0; k < tag; k++) { if (dst < cap) out[dst] = (OutT)((v >> (20 * k)) & 0xFFFFFu); dst++; }
-            } else if (tag == VAL_EXT) {
-                const u32 *src = t.ipool + ((v >> 24) & 0xFFFFFFFFFull);
-                u32 c = (u32)(v & 0xFFFFFFu);
-                for (u32 k = 0; k < c; k++) { if (dst < cap) out[dst] = (OutT)src[k]; dst++; }
-            }
+__global__ void __launch_bounds__(256) k_enc_emit(EncTables t, const u32 *__restrict__ slots, u64 n_items, const u64 *__restrict__ tokoff,
+                                                 OutT *__restrict__ out, u64 out_base, u64 cap) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += (u64)gridDim.x * blockDim.x) {
+        const u64 v = enc_value(t, slots[i]);
+        u64 dst = out_base + tokoff[i];
+        const u32 tag = VAL_TAG(v);
+        if (tag <= 3) {
+            for (u32 k = 0; k < tag; k++) { if (dst < cap) out[dst] = (OutT)((v >> (20 * k)) & 0xFFFFFu); dst++; }
+        } else if (tag == VAL_EXT) {
+            const u32 *src = t.ipool + ((v >> 24) & 0xFFFFFFFFFull);
+            const u32 c = (u32)(v & 0xFFFFFFu);
+            for (u32 k = 0; k < c; k++) { if (dst < cap) out[dst] = (OutT)src[k]; dst++; }
         }
     }
 }
@@ -752,13 +724,23 @@ static int encode_impl(bpe_tok *tok, const uint8_t *text, u64 n, bool on_device,
         BPE_TRY(grow_keep(ctx, tok->kpool, c[4] + bytes + 64, c[4]));
         BPE_TRY(grow_keep(ctx, tok->ipool, (c[5] + bytes + 64) * 4, c[5] * 4));
         BPE_TRY(bpe_buf_reserve(ctx, tok->todo, std::max<size_t>(bound * 4, 16)));
-        BPE_TRY(bpe_buf_reserve(ctx, ctx->tmp1, std::max<size_t>(bound * 4, 16)));
-        u32 *slots = (u32 *)ctx->tmp1.p;
+        // per-pretoken arrays of the batch: offsets, cache slots, token counts, token offsets
+        const u64 bw = b_hi - b_lo;
+        size_t off_b = round_up((bound + 2) * 4, 256), slot_b = round_up((bound + 1) * 4, 256), nt_b = round_up((bound + 1) * 4, 256);
+        size_t to_b = round_up((bound + 2) * 8, 256), st_b = round_up(scan_tmp_elems_host(bound) * 8, 256);
+        BPE_TRY(bpe_buf_reserve(ctx, ctx->tmp1, off_b + slot_b + nt_b + to_b + st_b));
+        u32 *offs = (u32 *)ctx->tmp1.p;
+        u32 *slots = (u32 *)((uint8_t *)ctx->tmp1.p + off_b);
+        u32 *ntok = (u32 *)((uint8_t *)ctx->tmp1.p + off_b + slot_b);
+        u64 *tokoff = (u64 *)((uint8_t *)ctx->tmp1.p + off_b + slot_b + nt_b);
+        u64 *stmp = (u64 *)((uint8_t *)ctx->tmp1.p + off_b + slot_b + nt_b + to_b);
         CUDA_TRY(ctx, cudaMemsetAsync((u64 *)tok->ctr.p + 2, 0, 8, st));
         EncTables t = enc_tables(tok);
-        const unsigned grid = (unsigned)std::max<u64>(1, std::min<u64>((u64)ctx->sm_count * 8, (b_hi - b_lo + 255) / 256));
+        const u64 base = b_lo * 32;
+        const unsigned grid = (unsigned)std::max<u64>(1, std::min<u64>((u64)ctx->sm_count * 8, (bound + 255) / 256));
         CUDA_TRY(ctx, cudaEventRecord(evs[0], st));
-        KLAUNCH(k_enc_lookup, grid, 256, 0, st, t, (const u32 *)ctx->flags.p, n, b_lo, b_hi, pre, slots);
+        launch_starts_to_offsets((const u32 *)ctx->flags.p, b_lo, b_hi, n, pre + b_lo, base, offs, bound, ctx->sm_count, st);
+        if (bound) KLAUNCH(k_enc_lookup, grid, 256, 0, st, t, offs, bound, base, slots);
         CUDA_TRY(ctx, cudaGetLastError());
         CUDA_TRY(ctx, cudaEventRecord(evs[1], st));
         BPE_TRY(cache_read_ctr(tok, c, 8));
@@ -772,20 +754,15 @@ static int encode_impl(bpe_tok *tok, const uint8_t *text, u64 n, bool on_device,
             CUDA_TRY(ctx, cudaGetLastError());
         }
         CUDA_TRY(ctx, cudaEventRecord(evs[2], st));
-        // tokens per word -> offsets
-        const u64 bw = b_hi - b_lo;
-        size_t wc_b = round_up((bw + 1) * 4, 256), wo_b = round_up((bw + 2) * 8, 256);
-        BPE_TRY(bpe_buf_reserve(ctx, ctx->spmask, wc_b + wo_b + scan_tmp_elems_host(bw) * 8));   // spmask is free after the flags pass
-        u32 *wcnt = (u32 *)ctx->spmask.p;
-        u64 *woff = (u64 *)((uint8_t *)ctx->spmask.p + wc_b);
-        u64 *wtmp = (u64 *)((uint8_t *)ctx->spmask.p + wc_b + wo_b);
-        KLAUNCH(k_enc_count, grid, 256, 0, st, t, (const u32 *)ctx->flags.p, b_lo, b_hi, pre, slots, wcnt);
-        launch_scan_u32(wcnt, bw, woff, wtmp, st);
+        // tokens per pretoken -> offsets
+        if (bound) KLAUNCH(k_enc_ntok, grid, 256, 0, st, t, slots, offs, bound, base, ntok);
+        launch_scan_u32(ntok, bound, tokoff, stmp, st);
         CUDA_TRY(ctx, cudaGetLastError());
         u64 *host = (u64 *)ctx->pinned;
-        CUDA_TRY(ctx, cudaMemcpyAsync(host, woff + bw, 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaMemcpyAsync(host, tokoff + bound, 8, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(ctx, cudaMemcpyAsync(host + 1, (u64 *)tok->ctr.p + 7, 8, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        (void)bw;
         const u64 batch_tokens = host[0], err_pos = host[1];
         if (err_pos != ~0ull) {
             // KeyError (tokenizer.py:120,135): report the key of the first failing pretoken in text order
@@ -813,11 +790,11 @@ static int encode_impl(bpe_tok *tok, const uint8_t *text, u64 n, bool on_device,
             ctx->err_detail = (int64_t)err_pos;
             return bpe_set_error(ctx, BPE_ERR_KEY, "KeyError: a token of the pretoken at byte %llu is not in the vocabulary", (unsigned long long)err_pos);
         }
-        if (out_dev && total_tokens < dev_cap) {
+        if (out_dev && total_tokens < dev_cap && bound) {
             if (out_dtype == BPE_DTYPE_U16)
-                KLAUNCH(k_enc_emit<uint16_t>, grid, 256, 0, st, t, (const u32 *)ctx->flags.p, b_lo, b_hi, pre, slots, woff, (uint16_t *)out_dev, total_tokens, dev_cap);
+                KLAUNCH(k_enc_emit<uint16_t>, grid, 256, 0, st, t, slots, bound, tokoff, (uint16_t *)out_dev, total_tokens, dev_cap);
             else
-                KLAUNCH(k_enc_emit<int32_t>, grid, 256, 0, st, t, (const u32 *)ctx->flags.p, b_lo, b_hi, pre, slots, woff, (int32_t *)out_dev, total_tokens, dev_cap);
+                KLAUNCH(k_enc_emit<int32_t>, grid, 256, 0, st, t, slots, bound, tokoff, (int32_t *)out_dev, total_tokens, dev_cap);
             CUDA_TRY(ctx, cudaGetLastError());
         }
         CUDA_TRY(ctx, cudaEventRecord(evs[3], st));

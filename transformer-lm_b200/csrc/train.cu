@@ -95,48 +95,41 @@ __device__ __forceinline__ void long_add(const CountTables &t, const uint8_t *p,
     t.counters[3] = 1;
 }
 
-// One thread per 32-byte flag word; every start bit in [own_begin, own_end) is one pretoken occurrence.
+// One thread per pretoken occurrence i of the batch: bytes [base + offs[i], base + offs[i+1]).
 // Short pretokens are first counted in a per-CTA shared-memory table and flushed to the HBM table when the CTA is
 // done: natural-language text is Zipfian, and without this the few hottest words serialise hundreds of millions of
-// same-address L2 atomics (measured: 11.5 ms per 256 MB batch before).
+// same-address L2 atomics.
 #define CNT_SMEM_SLOTS 2048u
 #define CNT_SMEM_PROBES 4u
-__global__ void __launch_bounds__(256) k_count_pretokens(CountTables t, const u32 *__restrict__ flags, u64 n,
-                                                        u64 word_begin, u64 word_end, u64 own_begin, u64 own_end, u64 trust_end) {
+__global__ void __launch_bounds__(256) k_count_pretokens(CountTables t, const u32 *__restrict__ offs, u64 n_items, u64 base,
+                                                        u64 own_begin, u64 own_end, u64 trust_end) {
     __shared__ u64 s_key[CNT_SMEM_SLOTS];
     __shared__ u32 s_cnt[CNT_SMEM_SLOTS];
     for (u32 i = threadIdx.x; i < CNT_SMEM_SLOTS; i += blockDim.x) { s_key[i] = 0; s_cnt[i] = 0; }
     __syncthreads();
     u64 n_tok = 0;
-    for (u64 w = word_begin + (u64)blockIdx.x * blockDim.x + threadIdx.x; w < word_end; w += (u64)gridDim.x * blockDim.x) {
-        u32 bits = flags[w];
-        while (bits) {
-            u32 j = __ffs(bits) - 1; bits &= bits - 1;
-            u64 pos = (w << 5) + j;
-            if (pos < own_begin || pos >= own_end) continue;
-            u64 end = bits ? (w << 5) + (__ffs(bits) - 1) : flags_next_start(flags, (w + 1) << 5, n);
-            u64 len = end - pos;
-            if (end > trust_end) t.counters[6] = 1;
-            n_tok++;
-            const uint8_t *p = t.text + pos;
-            if (len <= SHORT_MAX) {
-                u64 key = 0;
-                for (u32 k = 0; k < (u32)len; k++) key |= (u64)p[k] << (8 * k);
-                key |= len << 56;
-                u32 slot = (u32)mix64(key) & (CNT_SMEM_SLOTS - 1);
-                bool done = false;
-                for (u32 pr = 0; pr < CNT_SMEM_PROBES && !done; pr++) {
-                    u64 k = s_key[slot];
-                    if (k == 0) { u64 old = atomicCAS(&s_key[slot], 0ull, key); k = old ? old : key; }
-                    if (k == key) { atomicAdd(&s_cnt[slot], 1u); done = true; }
-                    slot = (slot + 1) & (CNT_SMEM_SLOTS - 1);
-                }
-                if (!done) short_add(t, key, 1);
-            } else if (len <= MAX_TOKEN_LEN) {
-                long_add(t, p, (u32)len, pos, 1);
-            } else {
-                t.counters[5] = 1;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += (u64)gridDim.x * blockDim.x) {
+        const u64 pos = base + offs[i], end = base + offs[i + 1];
+        if (pos < own_begin || pos >= own_end) continue;
+        const u64 len = end - pos;
+        if (end > trust_end) t.counters[6] = 1;
+        n_tok++;
+        const uint8_t *p = t.text + pos;
+        if (len <= SHORT_MAX) {
+            const u64 key = short_key(p, (u32)len);
+            u32 slot = (u32)mix64(key) & (CNT_SMEM_SLOTS - 1);
+            bool done = false;
+            for (u32 pr = 0; pr < CNT_SMEM_PROBES && !done; pr++) {
+                u64 k = s_key[slot];
+                if (k == 0) { u64 old = atomicCAS(&s_key[slot], 0ull, key); k = old ? old : key; }
+                if (k == key) { atomicAdd(&s_cnt[slot], 1u); done = true; }
+                slot = (slot + 1) & (CNT_SMEM_SLOTS - 1);
             }
+            if (!done) short_add(t, key, 1);
+        } else if (len <= MAX_TOKEN_LEN) {
+            long_add(t, p, (u32)len, pos, 1);
+        } else {
+            t.counters[5] = 1;
         }
     }
     // one atomic per warp for the occurrence counter
@@ -263,7 +256,10 @@ __global__ void __launch_bounds__(256) k_export_write(CountTables t, const u32 *
 __device__ __forceinline__ bool equals_special(const uint8_t *p, u32 len, const uint8_t *sp_blob, const u32 *sp_offs, int n_sp) {
     for (int s = 0; s < n_sp; s++) {
         u32 o = sp_offs[s], l = sp_offs[s + 1] - o;
-        if (l == len && bytes_equal(p, sp_blob + o, len)) return true;
+        if (l != len) continue;
+        bool eq = true;
+        for (u32 k = 0; k < len && eq; k++) eq = p[k] == sp_blob[o + k];     // (p may be a small local array: plain byte loop)
+        if (eq) return true;
     }
     return false;
 }
@@ -458,11 +454,27 @@ static int count_current_text(bpe_ctx *ctx, u64 n, u64 own_begin, u64 own_end, u
     BPE_TRY(read_counters(ctx, c, 8));
     for (u64 bi = 0; bi < n_batches; bi++) {
         u64 b_lo = w_lo + bi * words_per_batch, b_hi = std::min(w_hi, b_lo + words_per_batch);
-        u64 bytes = (b_hi - b_lo) * 32;
+        u64 bytes = (b_hi - b_lo) * 32, bw = b_hi - b_lo;
         BPE_TRY(count_ensure_capacity(ctx, c[0], c[1], bound[bi], std::min(bound[bi], bytes / (SHORT_MAX + 1) + 1)));
+        // ordinals of the batch's pretokens -> explicit offsets
+        size_t cnt_b = round_up((bw + 1) * 4, 256), pre_b = round_up((bw + 2) * 8, 256), tmp_b = round_up(scan_tmp_elems_host(bw) * 8, 256);
+        size_t off_b = round_up((bound[bi] + 2) * 4, 256);
+        BPE_TRY(bpe_buf_reserve(ctx, ctx->tmp1, cnt_b + pre_b + tmp_b + off_b));
+        u32 *wcnt = (u32 *)ctx->tmp1.p;
+        u64 *pre = (u64 *)((uint8_t *)ctx->tmp1.p + cnt_b);
+        u64 *stmp = (u64 *)((uint8_t *)ctx->tmp1.p + cnt_b + pre_b);
+        u32 *offs = (u32 *)((uint8_t *)ctx->tmp1.p + cnt_b + pre_b + tmp_b);
+        const u32 *fl = (const u32 *)ctx->flags.p;
+        launch_popc_words(fl + b_lo, bw, wcnt, ctx->sm_count, st);
+        launch_scan_u32(wcnt, bw, pre, stmp, st);
+        const u64 base = b_lo * 32;
+        // (the end of the batch's last pretoken = first start at or after the batch end, or the end of the text)
+        launch_starts_to_offsets(fl, b_lo, b_hi, n, pre, base, offs, bound[bi], ctx->sm_count, st);
         CountTables t = count_tables(ctx);
-        unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (b_hi - b_lo + 255) / 256);
-        KLAUNCH(k_count_pretokens, grid, 256, 0, st, t, (const u32 *)ctx->flags.p, n, b_lo, b_hi, own_begin, own_end, trust_end);
+        if (bound[bi]) {
+            unsigned g2 = (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (bound[bi] + 255) / 256);
+            KLAUNCH(k_count_pretokens, g2, 256, 0, st, t, offs, bound[bi], base, own_begin, own_end, trust_end);
+        }
         CUDA_TRY(ctx, cudaGetLastError());
         if (bi + 1 < n_batches) BPE_TRY(read_counters(ctx, c, 8));
     }
