@@ -11,44 +11,38 @@
 // neighbours' classes.  Output: 1 bit per byte (bit set = a pretoken starts on that byte).
 // Algorithmic HBM bytes: n read + n/8 written.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 apply_boundary_mask(uint4 c, u32 m16) {
-    u32 w[4] = {c.x, c.y, c.z, c.w};
-#pragma unroll
-    for (int j = 0; j < 16; j++)
-        if ((m16 >> j) & 1u) w[j >> 2] = (w[j >> 2] & ~(0xFFu << ((j & 3) * 8))) | ((CLS_B | CLS_LEAD) << ((j & 3) * 8));
-    return make_uint4(w[0], w[1], w[2], w[3]);
-}
-
 template <bool HAS_SP>
 __global__ void __launch_bounds__(PT_NT) k_pretok_flags(const uint8_t *__restrict__ text, u64 n, u64 n_tiles,
                                                        const u32 *__restrict__ spmask, const u32 *__restrict__ spstart,
                                                        u32 *__restrict__ flags, u64 *__restrict__ err, u64 err_lo, u64 err_hi) {
-    __shared__ PretokTables tb;
-    __shared__ uint4 s_text[PT_NT + 2];
-    __shared__ uint4 s_cls[PT_NT + 2];
+    __shared__ PretokTables2 tb;
+    // text tile, byte-addressable: [16 B of 0xFF][chunk before the tile][PT_NT chunks][chunk after][16 B of 0xFF]
+    __shared__ uint4 s_text[PT_NT + 4];
+    __shared__ uint4 s_mask[PT_NT + 2];          // masks of [chunk before][PT_NT chunks][chunk after]
     const u32 tid = threadIdx.x;
-    pretok_load_tables(&tb);
+    pretok_load_tables2(&tb);
+    if (tid == 0) { s_text[0] = make_uint4(~0u, ~0u, ~0u, ~0u); s_text[PT_NT + 3] = make_uint4(~0u, ~0u, ~0u, ~0u); }
     __syncthreads();
-    const uint4 padchunk = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    const uint8_t *tx = reinterpret_cast<const uint8_t *>(s_text);
     for (u64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const u64 tbeg = tile * PT_TILE;
         const uint4 *g = reinterpret_cast<const uint4 *>(text + tbeg);
-        s_text[1 + tid] = ld_stream_v4(g + tid);
-        if (tid == 0) s_text[0] = ld_stream_v4(g - 1);
-        if (tid == 1) s_text[PT_NT + 1] = ld_stream_v4(g + PT_NT);
+        s_text[2 + tid] = ld_stream_v4(g + tid);
+        if (tid == 0) s_text[1] = ld_stream_v4(g - 1);
+        if (tid == 1) s_text[PT_NT + 2] = ld_stream_v4(g + PT_NT);
         __syncthreads();
         u32 m16 = 0, s16 = 0;
         {
             u32 e; bool cr;
-            uint4 c = classify_chunk(&tb, s_text[tid], s_text[tid + 1], s_text[tid + 2], &e, &cr);
+            uint4 mk = info_to_masks(chunk_info(&tb, tx, 32u + tid * 16u, &e, &cr));
             if (HAS_SP) {
                 u64 wi = (tbeg >> 5) + (tid >> 1);
                 u32 sh = (tid & 1u) * 16u;
                 m16 = (spmask[wi] >> sh) & 0xFFFFu;
                 s16 = (spstart[wi] >> sh) & 0xFFFFu;
-                if (m16) c = apply_boundary_mask(c, m16);
+                if (m16) mk = masks_apply_boundary(mk, m16);
             }
-            s_cls[tid + 1] = c;
+            s_mask[tid + 1] = mk;
             if (e != 0xFFu) {
                 u64 off = tbeg + (u64)tid * PT_CHUNK + e;
                 if (off < n && off >= err_lo && off < err_hi) atomicMin(reinterpret_cast<u64 *>(&err[0]), off);
@@ -56,22 +50,20 @@ __global__ void __launch_bounds__(PT_NT) k_pretok_flags(const uint8_t *__restric
             if (cr) err[1] = 1;
             if (tid < 2) {                       // halo chunks (validated by the tile that owns them)
                 const u32 idx = tid == 0 ? 0u : PT_NT + 1u;
-                uint4 hp = idx == 0 ? padchunk : s_text[idx - 1];
-                uint4 hn = idx == 0 ? s_text[1] : padchunk;
                 u32 e2; bool cr2;
-                uint4 hc = classify_chunk(&tb, hp, s_text[idx], hn, &e2, &cr2);
+                uint4 hk = info_to_masks(chunk_info(&tb, tx, 16u + idx * 16u, &e2, &cr2));
                 if (HAS_SP) {
                     // halo chunk = last chunk of the previous tile / first chunk of the next one
                     u32 hm = 0;
                     if (idx != 0) hm = spmask[(tbeg >> 5) + (PT_NT >> 1)] & 0xFFFFu;
                     else if (tile > 0) hm = (spmask[(tbeg >> 5) - 1] >> 16) & 0xFFFFu;
-                    if (hm) hc = apply_boundary_mask(hc, hm);
+                    if (hm) hk = masks_apply_boundary(hk, hm);
                 }
-                s_cls[idx] = hc;
+                s_mask[idx] = hk;
             }
         }
         __syncthreads();
-        u32 bits = flags_chunk(s_text[tid], s_text[tid + 1], s_text[tid + 2], s_cls[tid], s_cls[tid + 1], s_cls[tid + 2]);
+        u32 bits = flags_from_masks(s_mask[tid], s_mask[tid + 1], s_mask[tid + 2], tx, 32u + tid * 16u);
         if (HAS_SP) bits = (bits & ~m16) | s16;
         u32 hi = __shfl_down_sync(0xffffffffu, bits, 1);
         if ((tid & 1u) == 0) flags[(tbeg >> 5) + (tid >> 1)] = bits | (hi << 16);
