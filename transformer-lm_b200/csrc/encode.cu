@@ -33,8 +33,10 @@
 //   0..3   that many ids inline, 20 bits each at bits 0, 20, 40
 //   4      ids in the id pool: bits 59..24 = offset, bits 23..0 = count
 //   5      KeyError: bits 31..0 = offending symbol (bit 31 set: index of a special token instead)
+//   14     (per-occurrence array only) not computed when looked up: bits 31..0 = cache slot reference
 //   15     not computed yet
 #define VAL_NONE 0xFFFFFFFFFFFFFFFFull
+#define VAL_FWD 14ull
 #define VAL_TAG(v) ((u32)((v) >> 60))
 #define VAL_EXT 4ull
 #define VAL_ERR 5ull
@@ -42,12 +44,16 @@
 #define RANK_NONE 0xFFFFFFFFFFFFFFFFull
 #define MKEY_EMPTY 0xFFFFFFFFFFFFFFFFull
 
+struct __align__(16) SSlot { u64 key, val; };
+struct __align__(32) LSlot { u64 meta, hash, val, pad; };
+
 struct EncTables {
     const ulonglong2 *mtab; u64 mmask;           // pair -> {key = a<<32|b, (rank << 32) | result symbol}
     const int32_t *mpairs;                       // operand symbols of merge j
     const int32_t *sym_to_id;
-    u64 *skey, *sval; u64 scap;                  // pretokens of <= 7 bytes: the key is the token (bytes | len << 56)
-    u64 *lmeta, *lhash, *lval; u64 lcap;         // longer pretokens: (offset:40 | len:24) of the bytes, 64-bit hash filter
+    // key and cached value share a slot, so the lookup brings the value in with the key (one 32-byte sector)
+    SSlot *stab; u64 scap;                       // pretokens of <= 7 bytes: the key is the token (bytes | len << 56)
+    LSlot *ltab; u64 lcap;                       // longer pretokens: (offset:40 | len:24) of the bytes, 64-bit hash filter
     const uint8_t *text;                         // payload of the current text arena
     uint8_t *kpool;                              // persistent key bytes of long pretokens
     u32 *ipool;                                  // token ids of pretokens with more than 3 tokens
@@ -90,49 +96,54 @@ __global__ void __launch_bounds__(256) k_enc_build_ranks(ulonglong2 *__restrict_
 }
 
 // ---- pretoken cache: lookup or claim -----------------------------------------------------------------
-__device__ __forceinline__ u32 enc_short_ref(const EncTables &t, u64 key) {
+// Returns the cached value of the pretoken, or (VAL_FWD << 60 | slot reference) when it is not computed yet.
+__device__ __forceinline__ u64 enc_short_get(const EncTables &t, u64 key) {
     u64 mask = t.scap - 1;
     u64 s = mix64(key) & mask;
     for (u64 probes = 0; probes < t.scap; probes++) {
-        u64 k = t.skey[s];
+        const ulonglong2 kv = *reinterpret_cast<const ulonglong2 *>(&t.stab[s]);
+        u64 k = kv.x;
         if (k == 0) {
-            u64 old = atomicCAS(&t.skey[s], 0ull, key);
+            u64 old = atomicCAS(&t.stab[s].key, 0ull, key);
             if (old == 0) {
                 atomicAdd(&t.ctr[0], 1ull);
                 u64 q = atomicAdd(&t.ctr[2], 1ull);
                 t.todo[q] = (u32)s;
-                return (u32)s;
+                return (VAL_FWD << 60) | (u32)s;
             }
             k = old;
+            if (k == key) return (VAL_FWD << 60) | (u32)s;          // inserted by another thread just now: not computed yet
         }
-        if (k == key) return (u32)s;
+        if (k == key) return kv.y != VAL_NONE ? kv.y : ((VAL_FWD << 60) | (u32)s);
         s = (s + 1) & mask;
     }
     t.ctr[3] = 1;
     return 0;
 }
 
-__device__ __forceinline__ u32 enc_long_ref(const EncTables &t, const uint8_t *p, u32 len, u64 off_meta) {
+__device__ __forceinline__ u64 enc_long_get(const EncTables &t, const uint8_t *p, u32 len, u64 off_meta) {
     u64 h = hash_long(p, len);
     u64 mask = t.lcap - 1;
     u64 s = h & mask;
     u64 mine = (off_meta << META_LEN_BITS) | len;
     for (u64 probes = 0; probes < t.lcap; probes++) {
-        u64 m = t.lmeta[s];
+        const ulonglong2 mh = *reinterpret_cast<const ulonglong2 *>(&t.ltab[s]);
+        u64 m = mh.x, hh = mh.y;
         if (m == META_EMPTY) {
-            u64 old = atomicCAS(&t.lmeta[s], META_EMPTY, mine);
+            u64 old = atomicCAS(&t.ltab[s].meta, META_EMPTY, mine);
             if (old == META_EMPTY) {
-                t.lhash[s] = h;
+                t.ltab[s].hash = h;
                 atomicAdd(&t.ctr[1], 1ull);
                 u64 q = atomicAdd(&t.ctr[2], 1ull);
                 t.todo[q] = (u32)s | REF_LONG;
-                return (u32)s | REF_LONG;
+                return (VAL_FWD << 60) | (u32)s | REF_LONG;
             }
             m = old;
+            hh = *((volatile u64 *)&t.ltab[s].hash);
         }
-        if ((m & META_LEN_MASK) == len) {
-            u64 hh = *((volatile u64 *)&t.lhash[s]);
-            if ((hh == 0 || hh == h) && bytes_equal(enc_rep_ptr(t, m), p, len)) return (u32)s | REF_LONG;
+        if ((m & META_LEN_MASK) == len && (hh == 0 || hh == h) && bytes_equal(enc_rep_ptr(t, m), p, len)) {
+            const u64 v = *((volatile u64 *)&t.ltab[s].val);
+            return v != VAL_NONE ? v : ((VAL_FWD << 60) | (u32)s | REF_LONG);
         }
         s = (s + 1) & mask;
     }
@@ -140,18 +151,19 @@ __device__ __forceinline__ u32 enc_long_ref(const EncTables &t, const uint8_t *p
     return 0;
 }
 
-// One thread per pretoken occurrence i of the batch (bytes [base + offs[i], base + offs[i+1])): slots[i] = its cache slot.
+// One thread per pretoken occurrence i of the batch (bytes [base + offs[i], base + offs[i+1])): vals[i] = its cached
+// value when the cache has it, else a forward reference to its slot (resolved after the BPE kernel).
 __global__ void __launch_bounds__(256) k_enc_lookup(EncTables t, const u32 *__restrict__ offs, u64 n_items, u64 base,
-                                                   u32 *__restrict__ slots) {
+                                                   u64 *__restrict__ vals) {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += (u64)gridDim.x * blockDim.x) {
         const u64 pos = base + offs[i];
         const u64 len = base + offs[i + 1] - pos;
         const uint8_t *p = t.text + pos;
-        u32 ref = 0;
-        if (len <= SHORT_MAX) ref = enc_short_ref(t, short_key(p, (u32)len));
-        else if (len <= MAX_TOKEN_LEN) ref = enc_long_ref(t, p, (u32)len, pos);
+        u64 v = 0;
+        if (len <= SHORT_MAX) v = enc_short_get(t, short_key(p, (u32)len));
+        else if (len <= MAX_TOKEN_LEN) v = enc_long_get(t, p, (u32)len, pos);
         else t.ctr[6] = 1;
-        slots[i] = ref;
+        vals[i] = v;
     }
 }
 
@@ -206,7 +218,7 @@ __global__ void __launch_bounds__(256) k_enc_bpe(EncTables t, u64 n_todo) {
         const u32 slot = ref & ~REF_LONG;
         u32 len; const uint8_t *p = nullptr; u64 skey = 0;
         if (is_long) {
-            u64 m = t.lmeta[slot];
+            u64 m = t.ltab[slot].meta;
             len = (u32)(m & META_LEN_MASK);
             const uint8_t *src = enc_rep_ptr(t, m);
             // move the key bytes out of the (transient) text arena into the persistent key pool
@@ -215,10 +227,10 @@ __global__ void __launch_bounds__(256) k_enc_bpe(EncTables t, u64 n_todo) {
             ko = __shfl_sync(0xffffffffu, ko, 0);
             for (u32 i = lane; i < len; i += 32) t.kpool[ko + i] = src[i];
             __syncwarp();
-            if (lane == 0) t.lmeta[slot] = ((ko | META_POOL_BIT) << META_LEN_BITS) | len;
+            if (lane == 0) t.ltab[slot].meta = ((ko | META_POOL_BIT) << META_LEN_BITS) | len;
             p = t.kpool + ko;
         } else {
-            skey = t.skey[slot];
+            skey = t.stab[slot].key;
             len = (u32)(skey >> 56);
         }
         u64 value;
@@ -292,23 +304,25 @@ __global__ void __launch_bounds__(256) k_enc_bpe(EncTables t, u64 n_todo) {
                 value = (VAL_EXT << 60) | (off << 24) | n;
             }
         }
-        if (lane == 0) { if (is_long) t.lval[slot] = value; else t.sval[slot] = value; }
+        if (lane == 0) { if (is_long) t.ltab[slot].val = value; else t.stab[slot].val = value; }
     }
 }
 
 __device__ __forceinline__ u64 enc_value(const EncTables &t, u32 ref) {
-    return (ref & REF_LONG) ? t.lval[ref & ~REF_LONG] : t.sval[ref];
+    return (ref & REF_LONG) ? t.ltab[ref & ~REF_LONG].val : t.stab[ref].val;
 }
 __device__ __forceinline__ u32 value_count(u64 v) {
     u32 tag = VAL_TAG(v);
     return tag <= 3 ? tag : (tag == VAL_EXT ? (u32)(v & 0xFFFFFFu) : 0);
 }
 
-// tokens per pretoken occurrence (a KeyError value records the smallest text offset it occurs at)
-__global__ void __launch_bounds__(256) k_enc_ntok(EncTables t, const u32 *__restrict__ slots, const u32 *__restrict__ offs, u64 n_items,
+// tokens per pretoken occurrence; forward references are resolved now that the BPE kernel has run (a KeyError value
+// records the smallest text offset it occurs at)
+__global__ void __launch_bounds__(256) k_enc_ntok(EncTables t, u64 *__restrict__ vals, const u32 *__restrict__ offs, u64 n_items,
                                                  u64 base, u32 *__restrict__ ntok) {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += (u64)gridDim.x * blockDim.x) {
-        const u64 v = enc_value(t, slots[i]);
+        u64 v = vals[i];
+        if (VAL_TAG(v) == VAL_FWD) { v = enc_value(t, (u32)v); vals[i] = v; }
         if (VAL_TAG(v) == VAL_ERR) atomicMin(&t.ctr[7], base + offs[i]);
         ntok[i] = value_count(v);
     }
@@ -316,10 +330,10 @@ __global__ void __launch_bounds__(256) k_enc_ntok(EncTables t, const u32 *__rest
 
 // ids of pretoken i go to out[out_base + tokoff[i] ...]: neighbouring threads write neighbouring ids
 template <typename OutT>
-__global__ void __launch_bounds__(256) k_enc_emit(EncTables t, const u32 *__restrict__ slots, u64 n_items, const u64 *__restrict__ tokoff,
+__global__ void __launch_bounds__(256) k_enc_emit(EncTables t, const u64 *__restrict__ vals, u64 n_items, const u64 *__restrict__ tokoff,
                                                  OutT *__restrict__ out, u64 out_base, u64 cap) {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += (u64)gridDim.x * blockDim.x) {
-        const u64 v = enc_value(t, slots[i]);
+        const u64 v = vals[i];
         u64 dst = out_base + tokoff[i];
         const u32 tag = VAL_TAG(v);
         if (tag <= 3) {
@@ -333,32 +347,42 @@ __global__ void __launch_bounds__(256) k_enc_emit(EncTables t, const u32 *__rest
 }
 
 // ---- cache maintenance ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_enc_rehash_short(const u64 *__restrict__ okey, const u64 *__restrict__ oval, u64 ocap, EncTables t) {
+__global__ void __launch_bounds__(256) k_enc_rehash_short(const SSlot *__restrict__ otab, u64 ocap, EncTables t) {
     u64 mask = t.scap - 1;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < ocap; i += (u64)gridDim.x * blockDim.x) {
-        u64 k = okey[i];
+        u64 k = otab[i].key;
         if (!k) continue;
         u64 s = mix64(k) & mask;
         for (;;) {
-            if (t.skey[s] == 0 && atomicCAS(&t.skey[s], 0ull, k) == 0) { t.sval[s] = oval[i]; break; }
+            if (t.stab[s].key == 0 && atomicCAS(&t.stab[s].key, 0ull, k) == 0) { t.stab[s].val = otab[i].val; break; }
             s = (s + 1) & mask;
         }
     }
 }
-__global__ void __launch_bounds__(256) k_enc_rehash_long(const u64 *__restrict__ ometa, const u64 *__restrict__ ohash,
-                                                        const u64 *__restrict__ oval, u64 ocap, EncTables t) {
+__global__ void __launch_bounds__(256) k_enc_rehash_long(const LSlot *__restrict__ otab, u64 ocap, EncTables t) {
     u64 mask = t.lcap - 1;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < ocap; i += (u64)gridDim.x * blockDim.x) {
-        u64 m = ometa[i];
+        u64 m = otab[i].meta;
         if (m == META_EMPTY) continue;
-        u64 s = ohash[i] & mask;
+        u64 s = otab[i].hash & mask;
         for (;;) {
-            if (t.lmeta[s] == META_EMPTY && atomicCAS(&t.lmeta[s], META_EMPTY, m) == META_EMPTY) {
-                t.lhash[s] = ohash[i]; t.lval[s] = oval[i];
+            if (t.ltab[s].meta == META_EMPTY && atomicCAS(&t.ltab[s].meta, META_EMPTY, m) == META_EMPTY) {
+                t.ltab[s].hash = otab[i].hash; t.ltab[s].val = otab[i].val;
                 break;
             }
             s = (s + 1) & mask;
         }
+    }
+}
+
+// empty tables: short {0, VAL_NONE}, long {META_EMPTY, 0, VAL_NONE, 0}
+__global__ void __launch_bounds__(256) k_enc_clear_tables(EncTables t) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < t.scap; i += (u64)gridDim.x * blockDim.x) {
+        *reinterpret_cast<ulonglong2 *>(&t.stab[i]) = make_ulonglong2(0ull, VAL_NONE);
+    }
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < t.lcap; i += (u64)gridDim.x * blockDim.x) {
+        ulonglong2 *q = reinterpret_cast<ulonglong2 *>(&t.ltab[i]);
+        q[0] = make_ulonglong2(META_EMPTY, 0ull); q[1] = make_ulonglong2(VAL_NONE, 0ull);
     }
 }
 
@@ -381,8 +405,8 @@ __global__ void k_enc_insert_specials(EncTables t, const u32 *__restrict__ sp_of
         key |= (u64)len << 56;
         u64 mask = t.scap - 1, s = mix64(key) & mask;
         for (;;) {
-            u64 old = atomicCAS(&t.skey[s], 0ull, key);
-            if (old == 0) { atomicAdd(&t.ctr[0], 1ull); t.sval[s] = v; return; }
+            u64 old = atomicCAS(&t.stab[s].key, 0ull, key);
+            if (old == 0) { atomicAdd(&t.ctr[0], 1ull); t.stab[s].val = v; return; }
             if (old == key) return;              // duplicate special
             s = (s + 1) & mask;
         }
@@ -390,8 +414,8 @@ __global__ void k_enc_insert_specials(EncTables t, const u32 *__restrict__ sp_of
         u64 h = hash_long(p, len), mask = t.lcap - 1, s = h & mask;
         u64 mine = (((u64)o | META_POOL_BIT) << META_LEN_BITS) | len;
         for (;;) {
-            u64 old = atomicCAS(&t.lmeta[s], META_EMPTY, mine);
-            if (old == META_EMPTY) { t.lhash[s] = h; atomicAdd(&t.ctr[1], 1ull); t.lval[s] = v; return; }
+            u64 old = atomicCAS(&t.ltab[s].meta, META_EMPTY, mine);
+            if (old == META_EMPTY) { t.ltab[s].hash = h; atomicAdd(&t.ctr[1], 1ull); t.ltab[s].val = v; return; }
             if ((old & META_LEN_MASK) == len && bytes_equal(enc_rep_ptr(t, old), p, len)) return;
             s = (s + 1) & mask;
         }
@@ -435,7 +459,7 @@ struct bpe_tok {
     std::vector<uint8_t> sym_blob_h; std::vector<u64> sym_offs_h;
     u32 sp_max_len = 0;
     // pretoken cache
-    DevBuf skey, sval, lmeta, lhash, lval, kpool, ipool, todo, ctr;
+    DevBuf stab, ltab, kpool, ipool, todo, ctr;
     u64 scap = 0, lcap = 0;
     bool cache_ready = false;
     std::vector<uint8_t> key_error;              // bytes of the last KeyError key
@@ -461,8 +485,8 @@ static EncTables enc_tables(bpe_tok *tok) {
     EncTables t;
     t.mtab = (const ulonglong2 *)tok->mtab.p; t.mmask = tok->mcap - 1;
     t.mpairs = (const int32_t *)tok->mpairs.p; t.sym_to_id = (const int32_t *)tok->sym_to_id.p;
-    t.skey = (u64 *)tok->skey.p; t.sval = (u64 *)tok->sval.p; t.scap = tok->scap;
-    t.lmeta = (u64 *)tok->lmeta.p; t.lhash = (u64 *)tok->lhash.p; t.lval = (u64 *)tok->lval.p; t.lcap = tok->lcap;
+    t.stab = (SSlot *)tok->stab.p; t.scap = tok->scap;
+    t.ltab = (LSlot *)tok->ltab.p; t.lcap = tok->lcap;
     t.text = tok->ctx->text.p ? (const uint8_t *)tok->ctx->text.p + BPE_PAD : nullptr;
     t.kpool = (uint8_t *)tok->kpool.p; t.ipool = (u32 *)tok->ipool.p; t.todo = (u32 *)tok->todo.p;
     t.ctr = (u64 *)tok->ctr.p;
@@ -471,14 +495,12 @@ static EncTables enc_tables(bpe_tok *tok) {
 
 static int cache_tables_alloc(bpe_tok *tok, u64 scap, u64 lcap) {
     bpe_ctx *ctx = tok->ctx;
-    cudaStream_t st = ctx->stream;
-    BPE_TRY(alloc_exact_e(ctx, tok->skey, scap * 8)); BPE_TRY(alloc_exact_e(ctx, tok->sval, scap * 8));
-    BPE_TRY(alloc_exact_e(ctx, tok->lmeta, lcap * 8)); BPE_TRY(alloc_exact_e(ctx, tok->lhash, lcap * 8));
-    BPE_TRY(alloc_exact_e(ctx, tok->lval, lcap * 8));
-    CUDA_TRY(ctx, cudaMemsetAsync(tok->skey.p, 0, scap * 8, st)); CUDA_TRY(ctx, cudaMemsetAsync(tok->sval.p, 0xFF, scap * 8, st));
-    CUDA_TRY(ctx, cudaMemsetAsync(tok->lmeta.p, 0xFF, lcap * 8, st)); CUDA_TRY(ctx, cudaMemsetAsync(tok->lhash.p, 0, lcap * 8, st));
-    CUDA_TRY(ctx, cudaMemsetAsync(tok->lval.p, 0xFF, lcap * 8, st));
+    BPE_TRY(alloc_exact_e(ctx, tok->stab, scap * sizeof(SSlot)));
+    BPE_TRY(alloc_exact_e(ctx, tok->ltab, lcap * sizeof(LSlot)));
     tok->scap = scap; tok->lcap = lcap;
+    EncTables t = enc_tables(tok);
+    KLAUNCH(k_enc_clear_tables, (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (std::max(scap, lcap) + 255) / 256), 256, 0, ctx->stream, t);
+    CUDA_TRY(ctx, cudaGetLastError());
     return BPE_OK;
 }
 
@@ -522,21 +544,21 @@ static int cache_ensure_capacity(bpe_tok *tok, u64 n_short, u64 n_long, u64 new_
     if (need_s >= (1ull << 31) || need_l >= (1ull << 31)) return bpe_set_error(ctx, BPE_ERR_CAPACITY, "pretoken cache would exceed 2^31 slots");
     if (need_s <= tok->scap && need_l <= tok->lcap) return BPE_OK;
     need_s = std::max(need_s, tok->scap); need_l = std::max(need_l, tok->lcap);
-    DevBuf oskey = tok->skey, osval = tok->sval, olmeta = tok->lmeta, olhash = tok->lhash, olval = tok->lval;
+    DevBuf ostab = tok->stab, oltab = tok->ltab;
     u64 oscap = tok->scap, olcap = tok->lcap;
-    tok->skey = DevBuf(); tok->sval = DevBuf(); tok->lmeta = DevBuf(); tok->lhash = DevBuf(); tok->lval = DevBuf();
+    tok->stab = DevBuf(); tok->ltab = DevBuf();
     int rc = cache_tables_alloc(tok, need_s, need_l);
     if (rc == BPE_OK) {
         EncTables t = enc_tables(tok);
         unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (oscap + 255) / 256);
-        KLAUNCH(k_enc_rehash_short, grid, 256, 0, ctx->stream, (const u64 *)oskey.p, (const u64 *)osval.p, oscap, t);
+        KLAUNCH(k_enc_rehash_short, grid, 256, 0, ctx->stream, (const SSlot *)ostab.p, oscap, t);
         grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (olcap + 255) / 256);
-        KLAUNCH(k_enc_rehash_long, grid, 256, 0, ctx->stream, (const u64 *)olmeta.p, (const u64 *)olhash.p, (const u64 *)olval.p, olcap, t);
+        KLAUNCH(k_enc_rehash_long, grid, 256, 0, ctx->stream, (const LSlot *)oltab.p, olcap, t);
         cudaError_t e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) rc = bpe_set_error(ctx, BPE_ERR_CUDA, "cache rehash: %s", cudaGetErrorString(e));
     }
-    for (DevBuf *b : {&oskey, &osval, &olmeta, &olhash, &olval}) bpe_buf_free(ctx, *b);
+    for (DevBuf *b : {&ostab, &oltab}) bpe_buf_free(ctx, *b);
     return rc;
 }
 
@@ -630,7 +652,7 @@ BPE_API void bpe_tok_destroy(bpe_tok *tok) {
     if (!tok) return;
     if (tok->ctx) { cudaSetDevice(tok->ctx->device); cudaStreamSynchronize(tok->ctx->stream); }
     for (DevBuf *b : {&tok->mtab, &tok->mpairs, &tok->sym_to_id, &tok->vlen, &tok->voff, &tok->vblob, &tok->sp_offs, &tok->sp_ids,
-                      &tok->skey, &tok->sval, &tok->lmeta, &tok->lhash, &tok->lval, &tok->kpool, &tok->ipool, &tok->todo, &tok->ctr})
+                      &tok->stab, &tok->ltab, &tok->kpool, &tok->ipool, &tok->todo, &tok->ctr})
         bpe_buf_free(tok->ctx, *b);
     delete tok;
 }
@@ -726,11 +748,11 @@ static int encode_impl(bpe_tok *tok, const uint8_t *text, u64 n, bool on_device,
         BPE_TRY(bpe_buf_reserve(ctx, tok->todo, std::max<size_t>(bound * 4, 16)));
         // per-pretoken arrays of the batch: offsets, cache slots, token counts, token offsets
         const u64 bw = b_hi - b_lo;
-        size_t off_b = round_up((bound + 2) * 4, 256), slot_b = round_up((bound + 1) * 4, 256), nt_b = round_up((bound + 1) * 4, 256);
+        size_t off_b = round_up((bound + 2) * 4, 256), slot_b = round_up((bound + 1) * 8, 256), nt_b = round_up((bound + 1) * 4, 256);
         size_t to_b = round_up((bound + 2) * 8, 256), st_b = round_up(scan_tmp_elems_host(bound) * 8, 256);
         BPE_TRY(bpe_buf_reserve(ctx, ctx->tmp1, off_b + slot_b + nt_b + to_b + st_b));
         u32 *offs = (u32 *)ctx->tmp1.p;
-        u32 *slots = (u32 *)((uint8_t *)ctx->tmp1.p + off_b);
+        u64 *vals = (u64 *)((uint8_t *)ctx->tmp1.p + off_b);
         u32 *ntok = (u32 *)((uint8_t *)ctx->tmp1.p + off_b + slot_b);
         u64 *tokoff = (u64 *)((uint8_t *)ctx->tmp1.p + off_b + slot_b + nt_b);
         u64 *stmp = (u64 *)((uint8_t *)ctx->tmp1.p + off_b + slot_b + nt_b + to_b);
@@ -740,7 +762,7 @@ static int encode_impl(bpe_tok *tok, const uint8_t *text, u64 n, bool on_device,
         const unsigned grid = (unsigned)std::max<u64>(1, std::min<u64>((u64)ctx->sm_count * 8, (bound + 255) / 256));
         CUDA_TRY(ctx, cudaEventRecord(evs[0], st));
         launch_starts_to_offsets((const u32 *)ctx->flags.p, b_lo, b_hi, n, pre + b_lo, base, offs, bound, ctx->sm_count, st);
-        if (bound) KLAUNCH(k_enc_lookup, grid, 256, 0, st, t, offs, bound, base, slots);
+        if (bound) KLAUNCH(k_enc_lookup, grid, 256, 0, st, t, offs, bound, base, vals);
         CUDA_TRY(ctx, cudaGetLastError());
         CUDA_TRY(ctx, cudaEventRecord(evs[1], st));
         BPE_TRY(cache_read_ctr(tok, c, 8));
@@ -755,7 +777,7 @@ static int encode_impl(bpe_tok *tok, const uint8_t *text, u64 n, bool on_device,
         }
         CUDA_TRY(ctx, cudaEventRecord(evs[2], st));
         // tokens per pretoken -> offsets
-        if (bound) KLAUNCH(k_enc_ntok, grid, 256, 0, st, t, slots, offs, bound, base, ntok);
+        if (bound) KLAUNCH(k_enc_ntok, grid, 256, 0, st, t, vals, offs, bound, base, ntok);
         launch_scan_u32(ntok, bound, tokoff, stmp, st);
         CUDA_TRY(ctx, cudaGetLastError());
         u64 *host = (u64 *)ctx->pinned;
@@ -773,10 +795,7 @@ static int encode_impl(bpe_tok *tok, const uint8_t *text, u64 n, bool on_device,
             CUDA_TRY(ctx, cudaMemcpy(&hpre, pre + w, 8, cudaMemcpyDeviceToHost));
             CUDA_TRY(ctx, cudaMemcpy(&hflags, (const u32 *)ctx->flags.p + w, 4, cudaMemcpyDeviceToHost));
             u64 o = hpre - ord[b] + __builtin_popcount(hflags & ((1u << (err_pos & 31)) - 1u));
-            u32 ref = 0;
-            CUDA_TRY(ctx, cudaMemcpy(&ref, slots + o, 4, cudaMemcpyDeviceToHost));
-            const u64 *vp = (ref & REF_LONG) ? (const u64 *)tok->lval.p + (ref & ~REF_LONG) : (const u64 *)tok->sval.p + ref;
-            CUDA_TRY(ctx, cudaMemcpy(&hv[0], vp, 8, cudaMemcpyDeviceToHost));
+            CUDA_TRY(ctx, cudaMemcpy(&hv[0], vals + o, 8, cudaMemcpyDeviceToHost));   // (forward references were resolved by k_enc_ntok)
             u32 sym = (u32)hv[0];
             tok->key_error.clear();
             if (sym & 0x80000000u) {
@@ -792,9 +811,9 @@ static int encode_impl(bpe_tok *tok, const uint8_t *text, u64 n, bool on_device,
         }
         if (out_dev && total_tokens < dev_cap && bound) {
             if (out_dtype == BPE_DTYPE_U16)
-                KLAUNCH(k_enc_emit<uint16_t>, grid, 256, 0, st, t, slots, bound, tokoff, (uint16_t *)out_dev, total_tokens, dev_cap);
+                KLAUNCH(k_enc_emit<uint16_t>, grid, 256, 0, st, t, vals, bound, tokoff, (uint16_t *)out_dev, total_tokens, dev_cap);
             else
-                KLAUNCH(k_enc_emit<int32_t>, grid, 256, 0, st, t, slots, bound, tokoff, (int32_t *)out_dev, total_tokens, dev_cap);
+                KLAUNCH(k_enc_emit<int32_t>, grid, 256, 0, st, t, vals, bound, tokoff, (int32_t *)out_dev, total_tokens, dev_cap);
             CUDA_TRY(ctx, cudaGetLastError());
         }
         CUDA_TRY(ctx, cudaEventRecord(evs[3], st));

@@ -6,21 +6,22 @@
 #include "hashtab.cuh"
 
 // ---------------------------------------------------------------------------------------------
-// flags kernel: one pass over the text.  Per 16-byte chunk a thread classifies its bytes (Unicode
-// class table in shared memory), validates UTF-8, then evaluates the start stencil with its
-// neighbours' classes.  Output: 1 bit per byte (bit set = a pretoken starts on that byte).
+// flags kernel: one pass over the text.  Per 16-byte chunk a thread turns its bytes into class masks (ASCII
+// through a shared-memory table, non-ASCII characters decoded, validated and looked up in the Unicode class
+// table in shared memory), then evaluates the start rules on 32-bit windows built with its neighbours' masks.
+// Output: 1 bit per byte (bit set = a pretoken starts on that byte).
 // Algorithmic HBM bytes: n read + n/8 written.
 // ---------------------------------------------------------------------------------------------
 template <bool HAS_SP>
 __global__ void __launch_bounds__(PT_NT) k_pretok_flags(const uint8_t *__restrict__ text, u64 n, u64 n_tiles,
                                                        const u32 *__restrict__ spmask, const u32 *__restrict__ spstart,
                                                        u32 *__restrict__ flags, u64 *__restrict__ err, u64 err_lo, u64 err_hi) {
-    __shared__ PretokTables2 tb;
+    __shared__ PretokTables tb;
     // text tile, byte-addressable: [16 B of 0xFF][chunk before the tile][PT_NT chunks][chunk after][16 B of 0xFF]
     __shared__ uint4 s_text[PT_NT + 4];
     __shared__ uint4 s_mask[PT_NT + 2];          // masks of [chunk before][PT_NT chunks][chunk after]
     const u32 tid = threadIdx.x;
-    pretok_load_tables2(&tb);
+    pretok_load_tables(&tb);
     if (tid == 0) { s_text[0] = make_uint4(~0u, ~0u, ~0u, ~0u); s_text[PT_NT + 3] = make_uint4(~0u, ~0u, ~0u, ~0u); }
     __syncthreads();
     const uint8_t *tx = reinterpret_cast<const uint8_t *>(s_text);
