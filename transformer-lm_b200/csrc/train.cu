@@ -24,23 +24,29 @@
 // re-homed words), others the text arena of the current shard.
 // =============================================================================================
 #define SHORT_MAX 7u
-#define META_EMPTY 0xFFFFFFFFFFFFFFFFull
+#define META_EMPTY 0ull                          // a real meta word has len >= 8, never 0: empty tables are all-zero memory
 #define META_LEN_BITS 24
 #define META_LEN_MASK ((1ull << META_LEN_BITS) - 1)
 #define META_POOL_BIT (1ull << 39)
 #define MAX_TOKEN_LEN ((1u << META_LEN_BITS) - 2)
 
 struct CountTables {
-    u64 *skey; u64 *scnt; u64 scap;              // short
-    u64 *lmeta; u64 *lhash; u64 *lcnt; u64 lcap; // long
+    u64 *stab; u64 scap;                         // short: slots of {key, count}            (16 B)
+    u64 *ltab; u64 lcap;                         // long:  slots of {meta, hash, count, pad} (32 B, one sector)
     const uint8_t *text;                         // payload of the current text arena
     const uint8_t *pool;                         // persistent bytes of long words
     u64 *counters;                               // [0]=n_short [1]=n_long [2]=long_bytes [3]=overflow [4]=n_pretokens [5]=too_long
                                                  // [6]=an owned pretoken ran past the trusted part of the right halo
 };
 
+#define SKEY(t, s) ((t).stab[2 * (s)])
+#define SCNT(t, s) ((t).stab[2 * (s) + 1])
+#define LMETA(t, s) ((t).ltab[4 * (s)])
+#define LHASH(t, s) ((t).ltab[4 * (s) + 1])
+#define LCNT(t, s) ((t).ltab[4 * (s) + 2])
+
 struct CountState {
-    DevBuf skey, scnt, lmeta, lhash, lcnt, pool, counters;
+    DevBuf stab, ltab, pool, counters;
     u64 scap = 0, lcap = 0, pool_used = 0;
     bool active = false;
     u64 n_pretokens = 0;
@@ -55,13 +61,13 @@ __device__ __forceinline__ void short_add(const CountTables &t, u64 key, u64 del
     u64 mask = t.scap - 1;
     u64 s = mix64(key) & mask;
     for (u64 probes = 0; probes < t.scap; probes++) {
-        u64 k = t.skey[s];
+        u64 k = SKEY(t, s);
         if (k == 0) {
-            u64 old = atomicCAS(&t.skey[s], 0ull, key);
+            u64 old = atomicCAS(&SKEY(t, s), 0ull, key);
             if (old == 0) { atomicAdd(&t.counters[0], 1ull); k = key; }
             else k = old;
         }
-        if (k == key) { atomicAdd(&t.scnt[s], delta); return; }
+        if (k == key) { atomicAdd(&SCNT(t, s), delta); return; }
         s = (s + 1) & mask;
     }
     t.counters[3] = 1;
@@ -74,21 +80,21 @@ __device__ __forceinline__ void long_add(const CountTables &t, const uint8_t *p,
     u64 s = h & mask;
     u64 mine = (off_meta << META_LEN_BITS) | len;
     for (u64 probes = 0; probes < t.lcap; probes++) {
-        u64 m = t.lmeta[s];
+        u64 m = LMETA(t, s);
         if (m == META_EMPTY) {
-            u64 old = atomicCAS(&t.lmeta[s], META_EMPTY, mine);
+            u64 old = atomicCAS(&LMETA(t, s), META_EMPTY, mine);
             if (old == META_EMPTY) {
-                t.lhash[s] = h;
+                LHASH(t, s) = h;
                 atomicAdd(&t.counters[1], 1ull);
                 atomicAdd(&t.counters[2], (u64)len);
-                atomicAdd(&t.lcnt[s], delta);
+                atomicAdd(&LCNT(t, s), delta);
                 return;
             }
             m = old;
         }
         if ((m & META_LEN_MASK) == len) {
-            u64 hh = *((volatile u64 *)&t.lhash[s]);
-            if ((hh == 0 || hh == h) && bytes_equal(rep_ptr(t, m), p, len)) { atomicAdd(&t.lcnt[s], delta); return; }
+            u64 hh = *((volatile u64 *)&LHASH(t, s));
+            if ((hh == 0 || hh == h) && bytes_equal(rep_ptr(t, m), p, len)) { atomicAdd(&LCNT(t, s), delta); return; }
         }
         s = (s + 1) & mask;
     }
@@ -153,20 +159,19 @@ __global__ void __launch_bounds__(256) k_popc_ranges(const u32 *__restrict__ fla
 }
 
 // ---- table growth: re-insert every entry of an old table into a bigger one -------------------
-__global__ void __launch_bounds__(256) k_rehash_short(const u64 *__restrict__ okey, const u64 *__restrict__ ocnt, u64 ocap, CountTables t) {
+__global__ void __launch_bounds__(256) k_rehash_short(const u64 *__restrict__ otab, u64 ocap, CountTables t) {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < ocap; i += (u64)gridDim.x * blockDim.x)
-        if (okey[i]) short_add(t, okey[i], ocnt[i]);
+        if (otab[2 * i]) short_add(t, otab[2 * i], otab[2 * i + 1]);
 }
-__global__ void __launch_bounds__(256) k_rehash_long(const u64 *__restrict__ ometa, const u64 *__restrict__ ohash,
-                                                    const u64 *__restrict__ ocnt, u64 ocap, CountTables t) {
+__global__ void __launch_bounds__(256) k_rehash_long(const u64 *__restrict__ otab, u64 ocap, CountTables t) {
     u64 mask = t.lcap - 1;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < ocap; i += (u64)gridDim.x * blockDim.x) {
-        u64 m = ometa[i];
+        u64 m = otab[4 * i];
         if (m == META_EMPTY) continue;
-        u64 s = ohash[i] & mask;                 // keys are unique: no comparison needed, just find a hole
+        u64 s = otab[4 * i + 1] & mask;          // keys are unique: no comparison needed, just find a hole
         for (;;) {
-            if (t.lmeta[s] == META_EMPTY && atomicCAS(&t.lmeta[s], META_EMPTY, m) == META_EMPTY) {
-                t.lhash[s] = ohash[i]; t.lcnt[s] = ocnt[i];
+            if (LMETA(t, s) == META_EMPTY && atomicCAS(&LMETA(t, s), META_EMPTY, m) == META_EMPTY) {
+                LHASH(t, s) = otab[4 * i + 1]; LCNT(t, s) = otab[4 * i + 2];
                 break;
             }
             s = (s + 1) & mask;
@@ -178,7 +183,7 @@ __global__ void __launch_bounds__(256) k_rehash_long(const u64 *__restrict__ ome
 __global__ void __launch_bounds__(256) k_rehome_sizes(CountTables t, u64 *__restrict__ need /* [0] */) {
     u64 c = 0;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < t.lcap; i += (u64)gridDim.x * blockDim.x) {
-        u64 m = t.lmeta[i];
+        u64 m = LMETA(t, i);
         if (m != META_EMPTY && !((m >> META_LEN_BITS) & META_POOL_BIT)) c += m & META_LEN_MASK;
     }
     for (int d = 16; d; d >>= 1) c += __shfl_down_sync(0xffffffffu, c, d);
@@ -186,13 +191,13 @@ __global__ void __launch_bounds__(256) k_rehome_sizes(CountTables t, u64 *__rest
 }
 __global__ void __launch_bounds__(256) k_rehome_copy(CountTables t, uint8_t *__restrict__ pool, u64 *__restrict__ cursor) {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < t.lcap; i += (u64)gridDim.x * blockDim.x) {
-        u64 m = t.lmeta[i];
+        u64 m = LMETA(t, i);
         if (m == META_EMPTY || ((m >> META_LEN_BITS) & META_POOL_BIT)) continue;
         u32 len = (u32)(m & META_LEN_MASK);
         u64 o = atomicAdd(cursor, (u64)len);
         const uint8_t *src = t.text + (m >> META_LEN_BITS);
         for (u32 k = 0; k < len; k++) pool[o + k] = src[k];
-        t.lmeta[i] = ((o | META_POOL_BIT) << META_LEN_BITS) | len;
+        LMETA(t, i) = ((o | META_POOL_BIT) << META_LEN_BITS) | len;
     }
 }
 
@@ -219,8 +224,8 @@ __global__ void __launch_bounds__(256) k_export_lens(CountTables t, u32 *__restr
     u64 total = t.scap + t.lcap;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (u64)gridDim.x * blockDim.x) {
         u32 l = 0;
-        if (i < t.scap) { if (t.skey[i]) l = (u32)(t.skey[i] >> 56); }
-        else { u64 m = t.lmeta[i - t.scap]; if (m != META_EMPTY) l = (u32)(m & META_LEN_MASK); }
+        if (i < t.scap) { if (SKEY(t, i)) l = (u32)(SKEY(t, i) >> 56); }
+        else { u64 m = LMETA(t, i - t.scap); if (m != META_EMPTY) l = (u32)(m & META_LEN_MASK); }
         lens[i] = l;
     }
 }
@@ -237,13 +242,13 @@ __global__ void __launch_bounds__(256) k_export_write(CountTables t, const u32 *
         u64 o = byte_off[i], w = word_idx[i];
         offs[w] = o;
         if (i < t.scap) {
-            u64 k = t.skey[i];
+            u64 k = SKEY(t, i);
             for (u32 j = 0; j < l; j++) blob[o + j] = (uint8_t)(k >> (8 * j));
-            counts[w] = (i64)t.scnt[i];
+            counts[w] = (i64)SCNT(t, i);
         } else {
-            const uint8_t *src = rep_ptr(t, t.lmeta[i - t.scap]);
+            const uint8_t *src = rep_ptr(t, LMETA(t, i - t.scap));
             for (u32 j = 0; j < l; j++) blob[o + j] = src[j];
-            counts[w] = (i64)t.lcnt[i - t.scap];
+            counts[w] = (i64)LCNT(t, i - t.scap);
         }
     }
 }
@@ -272,15 +277,15 @@ __global__ void __launch_bounds__(256) k_build_words(CountTables t, Words W, con
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (u64)gridDim.x * blockDim.x) {
         u32 l = 0; const uint8_t *src = nullptr; uint8_t tmp[8]; u64 c = 0;
         if (i < t.scap) {
-            u64 k = t.skey[i];
+            u64 k = SKEY(t, i);
             if (!k) continue;
             l = (u32)(k >> 56);
             for (u32 j = 0; j < l; j++) tmp[j] = (uint8_t)(k >> (8 * j));
-            src = tmp; c = t.scnt[i];
+            src = tmp; c = SCNT(t, i);
         } else {
-            u64 m = t.lmeta[i - t.scap];
+            u64 m = LMETA(t, i - t.scap);
             if (m == META_EMPTY) continue;
-            l = (u32)(m & META_LEN_MASK); src = rep_ptr(t, m); c = t.lcnt[i - t.scap];
+            l = (u32)(m & META_LEN_MASK); src = rep_ptr(t, m); c = LCNT(t, i - t.scap);
         }
         if (l < 2 || c == 0) continue;
         if (n_sp && equals_special(src, l, sp_blob, sp_offs, n_sp)) continue;
@@ -351,8 +356,8 @@ struct TrainBufs {
 static CountTables count_tables(bpe_ctx *ctx) {
     CountState *cs = ctx->count;
     CountTables t;
-    t.skey = (u64 *)cs->skey.p; t.scnt = (u64 *)cs->scnt.p; t.scap = cs->scap;
-    t.lmeta = (u64 *)cs->lmeta.p; t.lhash = (u64 *)cs->lhash.p; t.lcnt = (u64 *)cs->lcnt.p; t.lcap = cs->lcap;
+    t.stab = (u64 *)cs->stab.p; t.scap = cs->scap;
+    t.ltab = (u64 *)cs->ltab.p; t.lcap = cs->lcap;
     t.text = ctx->text.p ? (const uint8_t *)ctx->text.p + BPE_PAD : nullptr;
     t.pool = (const uint8_t *)cs->pool.p;
     t.counters = (u64 *)cs->counters.p;
@@ -362,7 +367,7 @@ static CountTables count_tables(bpe_ctx *ctx) {
 void count_state_free(bpe_ctx *ctx) {
     if (!ctx->count) return;
     CountState *cs = ctx->count;
-    for (DevBuf *b : {&cs->skey, &cs->scnt, &cs->lmeta, &cs->lhash, &cs->lcnt, &cs->pool, &cs->counters}) bpe_buf_free(ctx, *b);
+    for (DevBuf *b : {&cs->stab, &cs->ltab, &cs->pool, &cs->counters}) bpe_buf_free(ctx, *b);
     delete cs;
     ctx->count = nullptr;
 }
@@ -371,13 +376,9 @@ static int alloc_exact(bpe_ctx *ctx, DevBuf &b, size_t bytes) { return bpe_buf_a
 
 static int count_tables_alloc(bpe_ctx *ctx, u64 scap, u64 lcap) {
     CountState *cs = ctx->count;
-    BPE_TRY(alloc_exact(ctx, cs->skey, scap * 8)); BPE_TRY(alloc_exact(ctx, cs->scnt, scap * 8));
-    BPE_TRY(alloc_exact(ctx, cs->lmeta, lcap * 8)); BPE_TRY(alloc_exact(ctx, cs->lhash, lcap * 8));
-    BPE_TRY(alloc_exact(ctx, cs->lcnt, lcap * 8));
+    BPE_TRY(alloc_exact(ctx, cs->stab, scap * 16)); BPE_TRY(alloc_exact(ctx, cs->ltab, lcap * 32));
     cudaStream_t st = ctx->stream;
-    CUDA_TRY(ctx, cudaMemsetAsync(cs->skey.p, 0, scap * 8, st)); CUDA_TRY(ctx, cudaMemsetAsync(cs->scnt.p, 0, scap * 8, st));
-    CUDA_TRY(ctx, cudaMemsetAsync(cs->lmeta.p, 0xFF, lcap * 8, st)); CUDA_TRY(ctx, cudaMemsetAsync(cs->lhash.p, 0, lcap * 8, st));
-    CUDA_TRY(ctx, cudaMemsetAsync(cs->lcnt.p, 0, lcap * 8, st));
+    CUDA_TRY(ctx, cudaMemsetAsync(cs->stab.p, 0, scap * 16, st)); CUDA_TRY(ctx, cudaMemsetAsync(cs->ltab.p, 0, lcap * 32, st));
     cs->scap = scap; cs->lcap = lcap;
     return BPE_OK;
 }
@@ -411,20 +412,19 @@ static int count_ensure_capacity(bpe_ctx *ctx, u64 n_short, u64 n_long, u64 new_
     need_s = std::max(need_s, cs->scap); need_l = std::max(need_l, cs->lcap);
     // grow: move old tables aside, allocate, re-insert
     CountState old_view = *cs;                   // shallow copy of the DevBufs
-    cs->skey = DevBuf(); cs->scnt = DevBuf(); cs->lmeta = DevBuf(); cs->lhash = DevBuf(); cs->lcnt = DevBuf();
+    cs->stab = DevBuf(); cs->ltab = DevBuf();
     int rc = count_tables_alloc(ctx, need_s, need_l);
     if (rc != BPE_OK) return rc;
     // the short rehash re-counts its uniques through short_add: reset [0]; [1],[2] (long) are untouched
     CUDA_TRY(ctx, cudaMemsetAsync(cs->counters.p, 0, sizeof(u64), ctx->stream));
     CountTables t = count_tables(ctx);
     unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (old_view.scap + 255) / 256);
-    KLAUNCH(k_rehash_short, grid, 256, 0, ctx->stream, (const u64 *)old_view.skey.p, (const u64 *)old_view.scnt.p, old_view.scap, t);
+    KLAUNCH(k_rehash_short, grid, 256, 0, ctx->stream, (const u64 *)old_view.stab.p, old_view.scap, t);
     grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (old_view.lcap + 255) / 256);
-    KLAUNCH(k_rehash_long, grid, 256, 0, ctx->stream, (const u64 *)old_view.lmeta.p, (const u64 *)old_view.lhash.p,
-                                                 (const u64 *)old_view.lcnt.p, old_view.lcap, t);
+    KLAUNCH(k_rehash_long, grid, 256, 0, ctx->stream, (const u64 *)old_view.ltab.p, old_view.lcap, t);
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    for (DevBuf *b : {&old_view.skey, &old_view.scnt, &old_view.lmeta, &old_view.lhash, &old_view.lcnt}) bpe_buf_free(ctx, *b);
+    for (DevBuf *b : {&old_view.stab, &old_view.ltab}) bpe_buf_free(ctx, *b);
     return BPE_OK;
 }
 
