@@ -274,3 +274,29 @@ def test_helper_methods_segment_match_pretokenize(gpt2):
     assert gpt2.match("it's  fine\n") == regex.findall(GPT2_PAT, "it's  fine\n")
     assert gpt2.pretokenize(gpt2.segment(text)) == ["Hello", EOT, "world", "'s", " ", " end", EOT]
     assert gpt2.merge([b"a", b"a", b"a", b"b"], (b"a", b"a"), b"aa") == [b"aa", b"a", b"b"]
+
+
+@pytest.mark.parametrize("specials", [[EOT], []])
+def test_pipelined_host_encode_equals_single_pass(specials):
+    """bpe_encode on host memory cuts big inputs at exact boundaries (special tokens, or a lone space between ASCII
+    non-space bytes) and double-buffers the chunks; bpe_encode_dev encodes the same text in one piece."""
+    import ctypes as C
+    import torch
+    from transformer_lm_b200 import _lib
+    from transformer_lm_b200.synth import synth_host
+    vocab, merges = _trained(1000, [EOT])
+    tok = get_tokenizer(dict(vocab), list(merges), specials)
+    n = 300 << 20
+    host = synth_host("owt", 4322, n)
+    got = tok.encode_to_numpy(host, np.uint16)
+    h, ctx, L = tok._device_tok(), tok._tok_ctx, _lib.lib()
+    dev = torch.from_numpy(host).cuda()
+    out = torch.empty(n, dtype=torch.uint16, device="cuda")
+    n_out = C.c_uint64(0)
+    ctx.check(L.bpe_encode_dev(h, C.c_void_p(dev.data_ptr()), n, _lib.DTYPE_U16, C.c_void_p(out.data_ptr()), n, C.byref(n_out), None))
+    want = out[: n_out.value].cpu().numpy()
+    assert got.shape == want.shape and np.array_equal(got, want)
+    # and the first MB against the oracle (cut at a document boundary)
+    piece = host[: 1 << 20].tobytes()
+    piece = piece[: piece.rfind(b"<|endoftext|>")]
+    assert tok.encode_to_numpy(piece, np.int32).tolist() == oracle.OracleTokenizer(dict(vocab), list(merges), specials).encode_bytes(piece).tolist()

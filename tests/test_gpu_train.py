@@ -196,3 +196,30 @@ def test_tail_kernel_survives_table_growth(monkeypatch):
     want = oracle.train_bpe_on_bytes(data, 2500, [])
     got = _train_bytes(data, 2500, [])
     assert got[1] == want[1] and got[0] == want[0]
+
+
+# ---- big host inputs: chunked, double-buffered upload (bpe_train) must equal the one-piece device path -----------------
+def test_pipelined_host_training_equals_one_piece():
+    import numpy as np
+    import torch
+    from transformer_lm_b200.synth import synth_host
+    n = 600 << 20
+    host = synth_host("owt", 4321, n)
+    got = _train_bytes(host, 1500, ["<|endoftext|>"])                       # host path: 3 chunks with halos
+    dev = torch.from_numpy(host).cuda()
+    want = _train_bytes(None, 1500, ["<|endoftext|>"], device_ptr=dev.data_ptr(), n_bytes=n)
+    assert got[1] == want[1] and got[0] == want[0]
+    # a carriage return anywhere sends the whole input down the one-piece path (newline translation shifts offsets)
+    host2 = host[: 200 << 20].copy()
+    host2[150 << 20] = 0x0D
+    dev2 = torch.from_numpy(host2).cuda()
+    assert _train_bytes(host2, 600, []) == _train_bytes(None, 600, [], device_ptr=dev2.data_ptr(), n_bytes=host2.size)
+    # invalid UTF-8 in a later chunk: same exception and offset as CPython
+    host3 = host[: 400 << 20].copy()
+    host3[(300 << 20) + 12345] = 0xFF
+    with pytest.raises(UnicodeDecodeError) as ei:
+        _train_bytes(host3, 600, [])
+    try:
+        host3.tobytes().decode("utf-8")
+    except UnicodeDecodeError as e:
+        assert ei.value.start == e.start

@@ -100,8 +100,16 @@ BPE_API void bpe_ctx_destroy(bpe_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     count_state_free(ctx);
-    for (DevBuf *b : {&ctx->text, &ctx->flags, &ctx->spmask, &ctx->spstart, &ctx->scratch, &ctx->tmp0, &ctx->tmp1, &ctx->tmp2})
+    if (ctx->s_in) { cudaStreamSynchronize(ctx->s_in); cudaStreamSynchronize(ctx->s_out); }
+    for (DevBuf *b : {&ctx->text, &ctx->flags, &ctx->spmask, &ctx->spstart, &ctx->scratch, &ctx->tmp0, &ctx->tmp1, &ctx->tmp2,
+                      &ctx->text_alt, &ctx->out_a, &ctx->out_b})
         bpe_buf_free(ctx, *b);
+    if (ctx->s_in) {
+        cudaStreamDestroy(ctx->s_in); cudaStreamDestroy(ctx->s_out);
+        for (auto &e : ctx->ev_in) if (e) cudaEventDestroy(e);
+        for (auto &e : ctx->ev_out) if (e) cudaEventDestroy(e);
+        if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
+    }
     bpe_pool_trim(ctx);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -136,11 +144,22 @@ BPE_API void bpe_host_free(void *p) { if (p) cudaFreeHost(p); }
 // ---------------------------------------------------------------------------------------------
 // text arena
 // ---------------------------------------------------------------------------------------------
-int ctx_prepare_arena(bpe_ctx *ctx, DevBuf &buf, u64 n) {
+int ctx_prepare_arena(bpe_ctx *ctx, DevBuf &buf, u64 n, cudaStream_t st) {
+    if (!st) st = ctx->stream;
     BPE_TRY(bpe_buf_reserve(ctx, buf, arena_bytes(n)));
     uint8_t *a = (uint8_t *)buf.p;
-    CUDA_TRY(ctx, cudaMemsetAsync(a, BPE_BYTE_PAD, BPE_PAD, ctx->stream));
-    CUDA_TRY(ctx, cudaMemsetAsync(a + BPE_PAD + n, BPE_BYTE_PAD, arena_bytes(n) - BPE_PAD - n, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(a, BPE_BYTE_PAD, BPE_PAD, st));
+    CUDA_TRY(ctx, cudaMemsetAsync(a + BPE_PAD + n, BPE_BYTE_PAD, arena_bytes(n) - BPE_PAD - n, st));
+    return BPE_OK;
+}
+
+int ctx_pipeline_init(bpe_ctx *ctx) {
+    if (ctx->s_in) return BPE_OK;
+    CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+    CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    for (auto &e : ctx->ev_in) CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto &e : ctx->ev_out) CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming));
     return BPE_OK;
 }
 

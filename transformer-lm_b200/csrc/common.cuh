@@ -41,6 +41,10 @@ struct bpe_ctx {
     DevBuf spstart;     // first byte of an accepted special occurrence
     DevBuf scratch;     // small scalars: error words, counters
     DevBuf tmp0, tmp1, tmp2;
+    // double buffering of the host-side entry points: second text arena / output buffers, copy streams, events
+    DevBuf text_alt, out_a, out_b;
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {}, ev_out[2] = {}, ev_done = nullptr;
     void *pinned = nullptr; size_t pinned_cap = 0;   // small pinned staging for scalar readbacks
     struct CountState *count = nullptr;              // pretoken count tables (count.cu)
     uint64_t mem_limit = 0;

@@ -675,20 +675,13 @@ BPE_API int bpe_tok_key_error(bpe_tok *tok, uint8_t *buf, uint64_t cap, uint64_t
 #define ENC_BATCH_BYTES (256ull << 20)
 #define ENC_CACHE_MAX_ENTRIES (384ull << 20)
 
-static int encode_impl(bpe_tok *tok, const uint8_t *text, u64 n, bool on_device, int out_dtype, void *out, u64 cap, uint64_t *n_out,
-                       bpe_encode_stats *stats) {
-    if (!tok || (!text && n) || !n_out || (out_dtype != BPE_DTYPE_U16 && out_dtype != BPE_DTYPE_I32)) return BPE_ERR_ARG;
+// Encode the n bytes in the context's text arena into out_dev (device pointer, may be null: count only).
+// *n_out = number of tokens (may exceed dev_cap; only dev_cap are written).  stats, when given, are ADDED to.
+static int encode_core(bpe_tok *tok, u64 n, int out_dtype, void *out_dev, u64 dev_cap, uint64_t *n_out, bpe_encode_stats *stats) {
     bpe_ctx *ctx = tok->ctx;
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    if (out_dtype == BPE_DTYPE_U16 && tok->max_id > 65535)
-        return bpe_set_error(ctx, BPE_ERR_ARG, "vocabulary ids go up to %lld: they do not fit uint16 output", tok->max_id);
     cudaStream_t st = ctx->stream;
     *n_out = 0;
-    if (stats) memset(stats, 0, sizeof(*stats));
-    const size_t esz = out_dtype == BPE_DTYPE_U16 ? 2 : 4;
-    EvTimer tm(ctx);
-    int e0 = tm.mark();
-    BPE_TRY(ctx_load_text(ctx, text, n, on_device));
+    EvTimer tm(ctx, 8);                           // (the callers' timers use events 0..7)
     int e1 = tm.mark();
     const uint8_t *spb; const u32 *spo; u32 spmax;
     BPE_TRY(ctx_upload_specials(ctx, tok->sp_blob_h.data(), tok->sp_offs_h.data(), tok->n_sp, &spb, &spo, &spmax));
@@ -716,17 +709,6 @@ static int encode_impl(bpe_tok *tok, const uint8_t *text, u64 n, bool on_device,
     const u64 n_pretok = ord[n_batches];
     if (!tok->cache_ready) BPE_TRY(cache_reset(tok));
 
-    // device output buffer when the caller's is on the host
-    void *out_dev = nullptr;
-    u64 dev_cap = cap;
-    if (out) {
-        if (on_device) out_dev = out;
-        else {
-            dev_cap = std::min<u64>(cap, n);                     // a token covers at least one byte
-            BPE_TRY(bpe_buf_reserve(ctx, ctx->tmp2, std::max<size_t>(dev_cap * esz, 16)));
-            out_dev = ctx->tmp2.p;
-        }
-    }
     float ms_lookup = 0, ms_bpe = 0, ms_emit = 0;
     u64 total_tokens = 0, new_unique = 0;
     u64 c[8];
@@ -826,29 +808,154 @@ static int encode_impl(bpe_tok *tok, const uint8_t *text, u64 n, bool on_device,
     }
     int e3 = tm.mark();
     *n_out = total_tokens;
-    if (out && !on_device) {
-        u64 m = std::min(total_tokens, std::min(cap, dev_cap));
-        if (m) CUDA_TRY(ctx, cudaMemcpyAsync(out, out_dev, m * esz, cudaMemcpyDeviceToHost, st));
-    }
-    int e4 = tm.mark();
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     if (stats) {
-        stats->n_bytes = n; stats->n_pretokens = n_pretok; stats->n_tokens = total_tokens; stats->cache_new_unique = new_unique;
-        stats->ms_h2d = tm.ms(e0, e1); stats->ms_pretok = tm.ms(e1, e2); stats->ms_lookup = ms_lookup; stats->ms_bpe = ms_bpe;
-        stats->ms_emit = ms_emit; stats->ms_d2h = tm.ms(e3, e4); stats->ms_total = tm.ms(e0, e4);
+        stats->n_bytes += n; stats->n_pretokens += n_pretok; stats->n_tokens += total_tokens; stats->cache_new_unique += new_unique;
+        stats->ms_pretok += tm.ms(e1, e2); stats->ms_lookup += ms_lookup; stats->ms_bpe += ms_bpe;
+        stats->ms_emit += ms_emit; stats->ms_total += tm.ms(e1, e3);
     }
-    if (out && total_tokens > cap)
-        return bpe_set_error(ctx, BPE_ERR_TOO_SMALL, "need room for %llu ids", (unsigned long long)total_tokens);
     return BPE_OK;
+}
+
+static int encode_check_args(bpe_tok *tok, const uint8_t *text, u64 n, int out_dtype, uint64_t *n_out) {
+    if (!tok || (!text && n) || !n_out || (out_dtype != BPE_DTYPE_U16 && out_dtype != BPE_DTYPE_I32)) return BPE_ERR_ARG;
+    bpe_ctx *ctx = tok->ctx;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (out_dtype == BPE_DTYPE_U16 && tok->max_id > 65535)
+        return bpe_set_error(ctx, BPE_ERR_ARG, "vocabulary ids go up to %lld: they do not fit uint16 output", tok->max_id);
+    *n_out = 0;
+    return BPE_OK;
+}
+
+// ---- host entry point: chunks cut at exact boundaries, double-buffered so that the upload of chunk k+1 and the download
+// of chunk k-1 run while chunk k is encoded ----------------------------------------------------------------------------
+#define ENC_PIPE_CHUNK (256ull << 20)
+#define ENC_PIPE_MIN (96ull << 20)
+#define ENC_CUT_WINDOW (8ull << 20)
+
+static u32 special_len_at(const bpe_tok *tok, const uint8_t *t, u64 n, u64 i) {     // longest special matching at i, or 0
+    for (int s = 0; s < tok->n_sp; s++) {
+        u32 o = tok->sp_offs_h[s], l = tok->sp_offs_h[s + 1] - o;
+        if (l && i + l <= n && memcmp(t + i, tok->sp_blob_h.data() + o, l) == 0) return l;
+    }
+    return 0;
+}
+static bool covered_by_special_from_left(const bpe_tok *tok, const uint8_t *t, u64 n, u64 i) {
+    const u64 ml = tok->sp_max_len;
+    for (u64 q = i >= ml ? i - ml + 1 : 0; q < i; q++) { u32 l = special_len_at(tok, t, n, q); if (l && q + l > i) return true; }
+    return false;
+}
+// A position >= nominal where cutting the text changes nothing: the start of a special-token occurrence (segment()
+// splits there, tokenizer.py:63-66), or a single U+0020 between two ASCII non-space characters.  0 = none.
+static u64 find_exact_cut(const bpe_tok *tok, const uint8_t *t, u64 n, u64 nominal) {
+    const u64 end = std::min(n, nominal + ENC_CUT_WINDOW);
+    if (tok->n_sp > 0) {
+        bool first[256] = {false};
+        for (int s = 0; s < tok->n_sp; s++) if (tok->sp_offs_h[s + 1] > tok->sp_offs_h[s]) first[tok->sp_blob_h[tok->sp_offs_h[s]]] = true;
+        for (u64 i = nominal; i < end; i++)
+            if (first[t[i]] && special_len_at(tok, t, n, i) && !covered_by_special_from_left(tok, t, n, i)) return i;
+    }
+    auto plain = [](uint8_t b) { return b > 0x20 && b < 0x7F; };
+    for (u64 i = std::max<u64>(nominal, 1); i + 1 < end; i++)
+        if (t[i] == ' ' && plain(t[i - 1]) && plain(t[i + 1]) && !(tok->n_sp > 0 && (covered_by_special_from_left(tok, t, n, i) ||
+                                                                                     covered_by_special_from_left(tok, t, n, i + 1))))
+            return i;
+    return 0;
 }
 
 BPE_API int bpe_encode(bpe_tok *tok, const uint8_t *text_host, uint64_t n, int out_dtype, void *out, uint64_t cap, uint64_t *n_out,
                        bpe_encode_stats *stats) {
-    return encode_impl(tok, text_host, n, false, out_dtype, out, cap, n_out, stats);
+    BPE_TRY(encode_check_args(tok, text_host, n, out_dtype, n_out));
+    bpe_ctx *ctx = tok->ctx;
+    cudaStream_t st = ctx->stream;
+    if (stats) memset(stats, 0, sizeof(*stats));
+    const size_t esz = out_dtype == BPE_DTYPE_U16 ? 2 : 4;
+    // chunk boundaries
+    std::vector<u64> cut{0};
+    u64 chunk = ENC_PIPE_CHUNK;
+    if (const char *e = getenv("BPE_ENCODE_CHUNK_MB")) chunk = std::max<u64>(1, strtoull(e, nullptr, 10)) << 20;
+    if (n >= ENC_PIPE_MIN) {
+        for (u64 nominal = chunk; nominal + chunk / 2 < n; ) {
+            u64 c = find_exact_cut(tok, text_host, n, nominal);
+            if (!c || c <= cut.back()) break;     // no exact boundary nearby: the rest goes in one piece
+            cut.push_back(c);
+            nominal = c + chunk;
+        }
+    }
+    cut.push_back(n);
+    const size_t m = cut.size() - 1;
+    BPE_TRY(ctx_pipeline_init(ctx));
+    EvTimer tm(ctx);
+    int e0 = tm.mark();
+    DevBuf *tbuf[2] = {&ctx->text, &ctx->text_alt};
+    DevBuf *obuf[2] = {&ctx->out_a, &ctx->out_b};
+    u64 max_chunk = 0;
+    for (size_t k = 0; k < m; k++) max_chunk = std::max(max_chunk, cut[k + 1] - cut[k]);
+    auto upload = [&](size_t k, DevBuf &dst) -> int {     // chunk k -> arena dst, on the copy-in stream
+        const u64 len = cut[k + 1] - cut[k];
+        BPE_TRY(ctx_prepare_arena(ctx, dst, m > 1 ? max_chunk : len, ctx->s_in));
+        if (m > 1 && len < max_chunk)             // bytes between this chunk's end and the arena padding must read as padding
+            CUDA_TRY(ctx, cudaMemsetAsync((uint8_t *)dst.p + BPE_PAD + len, BPE_BYTE_PAD, max_chunk - len, ctx->s_in));
+        if (len) CUDA_TRY(ctx, cudaMemcpyAsync((uint8_t *)dst.p + BPE_PAD, text_host + cut[k], len, cudaMemcpyHostToDevice, ctx->s_in));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_in[k & 1], ctx->s_in));
+        return BPE_OK;
+    };
+    // (the compute stream must not run ahead of pool (re)allocations done for the other buffer: everything below that
+    // touches a buffer is ordered by events, and every chunk ends with a host-side synchronisation of the compute stream)
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    BPE_TRY(upload(0, *tbuf[0]));
+    u64 total = 0;
+    int rc = BPE_OK;
+    for (size_t k = 0; k < m && rc == BPE_OK; k++) {
+        const int cur = (int)(k & 1);
+        const u64 len = cut[k + 1] - cut[k];
+        if (k + 1 < m) { rc = upload(k + 1, *tbuf[cur ^ 1]); if (rc != BPE_OK) break; }
+        if (cur == 1) std::swap(ctx->text, ctx->text_alt);         // the arena the kernels read is always ctx->text
+        CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_in[cur], 0));
+        void *odev = nullptr;
+        if (out) {
+            rc = bpe_buf_reserve(ctx, *obuf[cur], std::max<size_t>((m > 1 ? max_chunk : len) * esz, 16));
+            if (rc != BPE_OK) { if (cur == 1) std::swap(ctx->text, ctx->text_alt); break; }
+            CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_out[cur], 0));   // its previous download has finished
+            odev = obuf[cur]->p;
+        }
+        uint64_t nt = 0;
+        rc = encode_core(tok, len, out_dtype, odev, len, &nt, stats);
+        if (cur == 1) std::swap(ctx->text, ctx->text_alt);
+        if (rc != BPE_OK) { ctx->err_detail += (int64_t)cut[k]; break; }
+        if (out && total < cap) {
+            const u64 w = std::min<u64>(nt, cap - total);
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_done, st));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_done, 0));
+            if (w) CUDA_TRY(ctx, cudaMemcpyAsync((uint8_t *)out + total * esz, odev, w * esz, cudaMemcpyDeviceToHost, ctx->s_out));
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_out[cur], ctx->s_out));
+        }
+        total += nt;
+    }
+    cudaStreamSynchronize(ctx->s_in);
+    cudaStreamSynchronize(ctx->s_out);
+    if (rc != BPE_OK) return rc;
+    int e1 = tm.mark();
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    *n_out = total;
+    if (stats) { stats->ms_total = tm.ms(e0, e1); stats->ms_h2d = 0; stats->ms_d2h = 0; }
+    if (out && total > cap) return bpe_set_error(ctx, BPE_ERR_TOO_SMALL, "need room for %llu ids", (unsigned long long)total);
+    return BPE_OK;
 }
+
 BPE_API int bpe_encode_dev(bpe_tok *tok, const uint8_t *text_dev, uint64_t n, int out_dtype, void *out_dev, uint64_t cap, uint64_t *n_out,
                            bpe_encode_stats *stats) {
-    return encode_impl(tok, text_dev, n, true, out_dtype, out_dev, cap, n_out, stats);
+    BPE_TRY(encode_check_args(tok, text_dev, n, out_dtype, n_out));
+    bpe_ctx *ctx = tok->ctx;
+    if (stats) memset(stats, 0, sizeof(*stats));
+    EvTimer tm(ctx);
+    int e0 = tm.mark();
+    BPE_TRY(ctx_load_text(ctx, text_dev, n, true));
+    int e1 = tm.mark();
+    BPE_TRY(encode_core(tok, n, out_dtype, out_dev, cap, n_out, stats));
+    if (stats) { stats->ms_h2d = tm.ms(e0, e1); stats->ms_total += stats->ms_h2d; }
+    if (out_dev && *n_out > cap) return bpe_set_error(ctx, BPE_ERR_TOO_SMALL, "need room for %llu ids", (unsigned long long)*n_out);
+    return BPE_OK;
 }
 
 BPE_API int bpe_decode(bpe_tok *tok, const int64_t *ids_host, uint64_t n, uint8_t *out, uint64_t cap, uint64_t *n_out) {

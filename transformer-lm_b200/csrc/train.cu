@@ -969,9 +969,92 @@ static int train_impl(bpe_ctx *ctx, const uint8_t *text, u64 n, bool text_is_dev
     return rc;
 }
 
+// Host entry point for big inputs: the text is uploaded in chunks (each with a small halo, exactly like a rank's shard in
+// the multi-GPU path) on a copy stream while the previous chunk is pretokenised and counted.  Returns 1 when the input
+// needs the one-piece path instead (a carriage return: newline translation shifts offsets; or a pretoken longer than the halo).
+#define TRAIN_PIPE_MIN (96ull << 20)
+#define TRAIN_PIPE_CHUNK (256ull << 20)
+#define TRAIN_HALO_LEFT 64ull
+#define TRAIN_HALO_RIGHT (64ull << 10)
+static u64 align_cut_host(const uint8_t *t, u64 n, u64 pos) {       // largest position <= pos that does not split a UTF-8 sequence
+    if (pos >= n) return n;
+    for (int k = 0; k < 3 && pos > 0 && (t[pos] & 0xC0u) == 0x80u; k++) pos--;
+    return pos;
+}
+static int count_host_pipelined(bpe_ctx *ctx, const uint8_t *text, u64 n, bpe_train_stats *stats, float *ms_pretok, float *ms_count) {
+    BPE_TRY(ctx_pipeline_init(ctx));
+    cudaStream_t st = ctx->stream;
+    std::vector<u64> cut{0};
+    for (u64 p = TRAIN_PIPE_CHUNK; p + TRAIN_PIPE_CHUNK / 2 < n; p += TRAIN_PIPE_CHUNK) cut.push_back(align_cut_host(text, n, p));
+    cut.push_back(n);
+    const size_t m = cut.size() - 1;
+    auto range = [&](size_t k, u64 *rlo, u64 *rhi) {
+        *rlo = align_cut_host(text, n, cut[k] > TRAIN_HALO_LEFT ? cut[k] - TRAIN_HALO_LEFT : 0);
+        *rhi = align_cut_host(text, n, std::min(n, cut[k + 1] + TRAIN_HALO_RIGHT));
+    };
+    u64 max_len = 0;
+    for (size_t k = 0; k < m; k++) { u64 a, b; range(k, &a, &b); max_len = std::max(max_len, b - a); }
+    DevBuf *tbuf[2] = {&ctx->text, &ctx->text_alt};
+    auto upload = [&](size_t k, DevBuf &dst) -> int {
+        u64 a, b; range(k, &a, &b);
+        BPE_TRY(ctx_prepare_arena(ctx, dst, max_len, ctx->s_in));
+        if (b - a < max_len) CUDA_TRY(ctx, cudaMemsetAsync((uint8_t *)dst.p + BPE_PAD + (b - a), BPE_BYTE_PAD, max_len - (b - a), ctx->s_in));
+        CUDA_TRY(ctx, cudaMemcpyAsync((uint8_t *)dst.p + BPE_PAD, text + a, b - a, cudaMemcpyHostToDevice, ctx->s_in));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_in[k & 1], ctx->s_in));
+        return BPE_OK;
+    };
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    BPE_TRY(upload(0, *tbuf[0]));
+    int rc = BPE_OK;
+    for (size_t k = 0; k < m && rc == BPE_OK; k++) {
+        const int cur = (int)(k & 1);
+        u64 a, b; range(k, &a, &b);
+        if (k + 1 < m) { rc = upload(k + 1, *tbuf[cur ^ 1]); if (rc != BPE_OK) break; }
+        if (cur == 1) std::swap(ctx->text, ctx->text_alt);
+        CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_in[cur], 0));
+        EvTimer tm(ctx, 8);
+        int e0 = tm.mark();
+        u64 nn = b - a;
+        rc = ctx_run_flags(ctx, &nn, false, nullptr, nullptr, 0, 0, cut[k] - a, cut[k + 1] - a);
+        int e1 = tm.mark();
+        if (rc == BPE_OK && ctx->saw_cr) rc = 1;
+        if (rc == BPE_OK) {
+            rc = count_current_text(ctx, b - a, cut[k] - a, cut[k + 1] - a, b == n ? b - a : (b - a >= 16 ? b - a - 16 : 0));
+            if (rc == BPE_ERR_HALO) rc = 1;
+        }
+        int e2 = tm.mark();
+        if (rc == BPE_OK) rc = count_rehome(ctx);
+        if (rc == BPE_OK) { *ms_pretok += tm.ms(e0, e1); *ms_count += tm.ms(e1, e2); }
+        if (cur == 1) std::swap(ctx->text, ctx->text_alt);
+        if (rc == BPE_ERR_UTF8) ctx->err_detail += (int64_t)a;
+    }
+    cudaStreamSynchronize(ctx->s_in);
+    (void)stats;
+    return rc;
+}
+
 BPE_API int bpe_train(bpe_ctx *ctx, const uint8_t *text_host, uint64_t n, const uint8_t *specials_blob,
                       const uint32_t *special_offs, int n_specials, int n_merges, int32_t *merge_pairs_out, int *n_done,
                       bpe_train_stats *stats) {
+    if (n >= TRAIN_PIPE_MIN && ctx && text_host && n_done && (n_merges <= 0 || merge_pairs_out) && (n_specials <= 0 || (specials_blob && special_offs))) {
+        CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+        *n_done = 0;
+        if (stats) memset(stats, 0, sizeof(*stats));
+        if (n_merges < 0) n_merges = 0;
+        EvTimer tm(ctx);
+        int e0 = tm.mark();
+        BPE_TRY(bpe_count_begin(ctx));
+        float ms_pretok = 0, ms_count = 0;
+        int rc = count_host_pipelined(ctx, text_host, n, stats, &ms_pretok, &ms_count);
+        if (rc == BPE_OK) {
+            rc = run_merges(ctx, specials_blob, special_offs, n_specials, n_merges, merge_pairs_out, n_done, stats, tm, e0);
+            if (stats) { stats->n_bytes = n; stats->ms_h2d = 0; stats->ms_pretok = ms_pretok; stats->ms_count = ms_count; }
+            ctx->count->active = false;
+            return rc;
+        }
+        ctx->count->active = false;
+        if (rc != 1) return rc;                   // (1 = needs the one-piece path below)
+    }
     return train_impl(ctx, text_host, n, false, specials_blob, special_offs, n_specials, n_merges, merge_pairs_out, n_done, stats);
 }
 BPE_API int bpe_train_dev(bpe_ctx *ctx, const uint8_t *text_dev, uint64_t n, const uint8_t *specials_blob,
