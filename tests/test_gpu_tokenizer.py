@@ -300,3 +300,29 @@ def test_pipelined_host_encode_equals_single_pass(specials):
     piece = host[: 1 << 20].tobytes()
     piece = piece[: piece.rfind(b"<|endoftext|>")]
     assert tok.encode_to_numpy(piece, np.int32).tolist() == oracle.OracleTokenizer(dict(vocab), list(merges), specials).encode_bytes(piece).tolist()
+
+
+def test_bulk_encode_driver_streams_a_file(tmp_path):
+    """encode_file (replaces models/tokenizer/encode.py): pieces cut at exact boundaries, text-mode newline handling,
+    raw little-endian uint16 output that np.memmap reads (train.py:230-232 of the reference)."""
+    from models.tokenizer.encode import encode_file
+    vocab, merges = _trained(1000, [EOT])
+    tok = get_tokenizer(dict(vocab), list(merges), [EOT])
+    body = (FIXTURES_PATH / "tinystories_sample.txt").read_bytes() + (FIXTURES_PATH / "corpus.en").read_bytes()[:40000]
+    raw = (body + b"\r\nline two\rline three\r\n" + EOT.encode()) * 12 + b"tail without newline"
+    src = tmp_path / "in.txt"
+    src.write_bytes(raw)
+    with open(src, "r", encoding="utf-8") as f:
+        text = f.read()                                   # what the reference's text-mode read sees
+    want = tok.encode(text)
+    for piece in (1 << 30, 70000, 9000):                  # one piece, several, many (forces carries and "\r" holds)
+        dst = tmp_path / ("out_%d.bin" % piece)
+        n = encode_file(tok, src, dst, np.uint16, piece_bytes=piece)
+        got = np.memmap(dst, dtype=np.uint16, mode="r")
+        assert n == len(want) == got.size
+        assert got.tolist() == want
+    # no specials in the tokenizer: pieces are cut at lone spaces
+    tok2 = get_tokenizer(dict(vocab), list(merges), [])
+    dst = tmp_path / "out_nosp.bin"
+    encode_file(tok2, src, dst, np.int32, piece_bytes=5000)
+    assert np.fromfile(dst, dtype="<i4").tolist() == tok2.encode(text)

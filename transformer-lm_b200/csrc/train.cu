@@ -9,6 +9,7 @@
 #include "ctx.h"
 #include "merge.cuh"
 #include "hashtab.cuh"
+#include <cooperative_groups/reduce.h>
 
 // =============================================================================================
 // 1. Pretoken counting  (extract_subword_frequencies, train.py:16-28)
@@ -289,9 +290,20 @@ __global__ void __launch_bounds__(256) k_build_words(CountTables t, Words W, con
         }
         if (l < 2 || c == 0) continue;
         if (n_sp && equals_special(src, l, sp_blob, sp_offs, n_sp)) continue;
-        u64 w = atomicAdd(&W.counters[0], 1ull);
-        u64 o = SYM_PAD + atomicAdd(&W.counters[1], (u64)l + 1) + 1;       // one separator in front of every word
-        atomicMax(&W.counters[2], (u64)l);
+        // word index and symbol space: one atomic per group of threads that arrive here together (12 M words would
+        // otherwise serialise on three addresses)
+        cg::coalesced_group g = cg::coalesced_threads();
+        const u32 need = l + 1;                                            // one separator in front of every word
+        const u32 pre = cg::exclusive_scan(g, need);
+        const u32 lmax = cg::reduce(g, l, cg::greater<u32>());
+        u64 w0 = 0, o0 = 0;
+        if (g.thread_rank() == g.size() - 1) {
+            w0 = atomicAdd(&W.counters[0], (u64)g.size());
+            o0 = atomicAdd(&W.counters[1], (u64)(pre + need));
+            atomicMax(&W.counters[2], (u64)lmax);
+        }
+        const u64 w = g.shfl(w0, g.size() - 1) + g.thread_rank();
+        const u64 o = SYM_PAD + g.shfl(o0, g.size() - 1) + pre + 1;
         WordMeta wm; wm.off = (u32)o; wm.len = l; wm.cnt = (i64)c;
         W.meta[w] = wm;
         for (u32 j = 0; j < l; j++) W.sym[o + j] = src[j];                 // (the array was filled with SYM_SEP)
