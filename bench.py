@@ -340,9 +340,18 @@ def run_b200(args):
         ach_merge = alg_merge / 1e9 / (merge_ms / 1e3) if merge_ms > 0 else 0.0
         local_bytes = meta["own_end"] - meta["own_begin"]
         pretok_ms, count_ms = avg("ms_pretok"), avg("ms_count")
+        # DRAM traffic of that kernel from the committed ncu capture of this exact configuration (null otherwise)
+        traffic, traffic_src = None, None
+        try:
+            tj = json.loads((ROOT / "profiles" / "r1_f_merge_loop_11GB.json").read_text())
+            if world == 1 and all(tj["config"][k] == v for k, v in (("corpus_bytes", nbytes), ("vocab_size", vocab_size), ("shape", shape), ("seed", seed))):
+                traffic, traffic_src = tj["traffic_bytes_per_launch"], tj["source"]
+        except Exception:
+            pass
         roofline = {
             "bound": "hbm", "kernel": "k_merge_loop (one persistent cooperative launch, %d merges)" % len(merges),
-            "achieved": round(ach_merge, 1), "peak": peak, "unit": "GB/s", "frac": round(ach_merge / peak, 4), "traffic": None,
+            "achieved": round(ach_merge, 1), "peak": peak, "unit": "GB/s", "frac": round(ach_merge / peak, 4), "traffic": traffic,
+            "traffic_source": traffic_src,
             "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_merge,
             "algorithmic_bytes_definition": "16 B x sum over merges of live pair-table keys (%d) + 8 B x index records (%d)" % (st["sum_live_pairs"], st["log_records"]),
             "share_of_step": round(merge_ms / ms_dev, 4) if ms_dev else None,
