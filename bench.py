@@ -496,6 +496,11 @@ def run_b200(args):
                           "d2h_bytes_per_step": int(2 * tokens_local), "ms_per_step": round(ems2, 3),
                           "api": "bpe_encode (C ABI) with pinned host text in, pinned host uint16 ids out; wall clock"}
             hbuf.free(); hout.free()
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            n_s, dt, n_ids = cpu_encode_sample(train_res[0], train_res[1], "owt", 4322, args.ref_sample_bytes if not is_train and args.ref_sample_bytes else 32e6)
+            enc["cpu_baseline"] = {"value": round(n_s / 1e6 / dt, 4), "unit": "MB/s", "cores": 1, "kind": "port",
+                                   "sample": "oracle/bpe_oracle.c Tokenizer.encode port (1 thread like the reference) on the first %.1f MB of the same text "
+                                             "with the same vocab: %.1f s, %d ids" % (n_s / 1e6, dt, n_ids), "host_cores_available": os.cpu_count()}
         if is_train:
             line["encode"] = enc
         else:
@@ -515,11 +520,8 @@ def run_b200(args):
                                     "sample": "oracle/bpe_oracle.c (C port of the reference's train_bpe, 1 thread like the reference) on the first "
                                               "%.2f MB of the same corpus with the full vocab %d (%d merges): %.1f s" % (n_s / 1e6, vocab_size, len(mm), dt),
                                     "host_cores_available": os.cpu_count()}
-        else:
-            n_s, dt, n_ids = cpu_encode_sample(train_res[0], train_res[1], "owt", 4322, args.ref_sample_bytes or 32e6)
-            line["cpu_baseline"] = {"value": round(n_s / 1e6 / dt, 4), "unit": "MB/s", "cores": 1, "kind": "port",
-                                    "sample": "oracle/bpe_oracle.c Tokenizer.encode port (1 thread) on the first %.1f MB of the same text with the same "
-                                              "vocab: %.1f s, %d ids" % (n_s / 1e6, dt, n_ids), "host_cores_available": os.cpu_count()}
+        elif "cpu_baseline" in enc:
+            line["cpu_baseline"] = enc["cpu_baseline"]
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

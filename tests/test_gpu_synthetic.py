@@ -1,0 +1,64 @@
+"""Parity on the bench's own input distributions: synthetic TinyStories- and OWT-shaped text (Unicode
+whitespace, CJK, emoji, URLs, contractions, documents separated by <|endoftext|>) against the CPU oracle at sizes it
+finishes in seconds, and size-independent properties at larger sizes (encode -> decode round trip, token-count additivity)."""
+import numpy as np
+import pytest
+
+import _bootstrap  # noqa: F401
+from oracle import oracle
+from tests.adapters import get_tokenizer
+from transformer_lm_b200.synth import synth_host
+
+pytestmark = pytest.mark.gpu
+EOT = "<|endoftext|>"
+
+
+def _train(data, vocab_size, specials, **kw):
+    from models.tokenizer.train import train_bpe_on_bytes
+    return train_bpe_on_bytes(data, vocab_size, specials, **kw)
+
+
+@pytest.mark.parametrize("shape,seed,mb,vocab", [("tinystories", 1234, 24, 700), ("owt", 4321, 12, 600)])
+def test_train_on_synthetic_shapes_matches_oracle(shape, seed, mb, vocab):
+    data = synth_host(shape, seed, mb << 20).tobytes()
+    want = oracle.train_bpe_on_bytes(data, vocab, [EOT])
+    got = _train(data, vocab, [EOT])
+    assert got[1] == want[1] and got[0] == want[0]
+
+
+@pytest.fixture(scope="module")
+def owt_tokenizer():
+    data = synth_host("owt", 4321, 64 << 20)
+    vocab, merges = _train(data, 8000, [EOT])
+    return vocab, merges
+
+
+def test_encode_synthetic_owt_matches_oracle(owt_tokenizer):
+    vocab, merges = owt_tokenizer
+    tok = get_tokenizer(dict(vocab), list(merges), [EOT])
+    otok = oracle.OracleTokenizer(dict(vocab), list(merges), [EOT])
+    data = synth_host("owt", 4322, 6 << 20).tobytes()
+    got = tok.encode_to_numpy(data, np.int32)
+    want = otok.encode_bytes(data)
+    assert got.shape == want.shape and np.array_equal(got, want)
+
+
+def test_roundtrip_and_additivity_at_scale(owt_tokenizer):
+    """256 MB: decode(encode(x)) == x byte for byte, and the token count of a text equals the sum over its documents'
+    halves when it is cut at a special token (the encoder splits there first, tokenizer.py:63-66)."""
+    vocab, merges = owt_tokenizer
+    tok = get_tokenizer(dict(vocab), list(merges), [EOT])
+    n = 256 << 20
+    host = synth_host("owt", 4322, n)
+    ids = tok.encode_to_numpy(host, np.uint16)
+    assert ids.max() < len(vocab)
+    back = tok.decode_bytes(ids[: 40_000_000].astype(np.int64))
+    assert back == host[: len(back)].tobytes()
+    raw = host.tobytes()
+    cut = raw.find(EOT.encode(), n // 2)
+    a = tok.encode_to_numpy(host[:cut], np.uint16)
+    b = tok.encode_to_numpy(host[cut:], np.uint16)
+    assert a.size + b.size == ids.size
+    assert np.array_equal(ids[: a.size], a) and np.array_equal(ids[a.size:], b)
+    # uint16 ids reinterpret as the raw little-endian .bin the reference's trainer memory-maps
+    assert ids.dtype == np.uint16 and ids.tobytes()[:2] == int(ids[0]).to_bytes(2, "little")
