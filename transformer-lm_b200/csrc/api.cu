@@ -49,7 +49,13 @@ void bpe_pool_trim(bpe_ctx *ctx) {
 
 void bpe_buf_free(bpe_ctx *ctx, DevBuf &b) {
     if (!b.p) { b.cap = 0; return; }
-    if (ctx) ctx->pool.push_back(b); else cudaFree(b.p);
+    if (ctx) {
+        ctx->pool.push_back(b);
+        if (ctx->pool.size() > 64) {             // bound the cache: drop the buffer that has waited longest
+            cudaFree(ctx->pool.front().p);       // (cudaFree synchronises the device: nothing can still be using it)
+            ctx->pool.erase(ctx->pool.begin());
+        }
+    } else cudaFree(b.p);
     b.p = nullptr; b.cap = 0;
 }
 
