@@ -760,7 +760,7 @@ static int run_merges(bpe_ctx *ctx, const uint8_t *sp_blob, const u32 *sp_offs, 
     // persistent kernel is simply relaunched after the rehash).
     u64 n_pairs0 = 0;
     for (u64 v : dense) n_pairs0 += v != 0;
-    u64 pcap = next_pow2(std::max<u64>(1 << 12, std::max<u64>(8 * n_pairs0, n_syms / 4)));
+    u64 pcap = next_pow2(std::max<u64>(1 << 12, std::max<u64>(8 * n_pairs0, n_syms / 8)));
     MergeState M;
     memset(&M, 0, sizeof(M));
     M.W = W; M.n_words = (u32)n_words;
