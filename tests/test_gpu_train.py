@@ -223,3 +223,27 @@ def test_pipelined_host_training_equals_one_piece():
         host3.tobytes().decode("utf-8")
     except UnicodeDecodeError as e:
         assert ei.value.start == e.start
+
+
+def test_streamed_file_ingest_equals_in_memory(tmp_path, monkeypatch):
+    """train_bpe(path) on a big file reads it in chunks on a few threads while the GPU counts the previous chunk."""
+    import transformer_lm_b200.train as T
+    from transformer_lm_b200.synth import synth_host
+    monkeypatch.setattr(T, "_STREAM_MIN", 64 << 20)
+    monkeypatch.setattr(T, "_STREAM_CHUNK", 48 << 20)
+    n = 200 << 20
+    host = synth_host("owt", 4321, n)
+    path = tmp_path / "corpus.txt"
+    host.tofile(path)
+    got = run_train_bpe(path, 1200, ["<|endoftext|>"])
+    want = _train_bytes(host, 1200, ["<|endoftext|>"])
+    assert got[1] == want[1] and got[0] == want[0]
+    # carriage return -> one-piece path; invalid UTF-8 -> UnicodeDecodeError
+    host2 = host[: 100 << 20].copy()
+    host2[(70 << 20) + 5] = 0x0D
+    host2.tofile(path)
+    assert run_train_bpe(path, 500, []) == _train_bytes(host2, 500, [])
+    host2[(70 << 20) + 5] = 0xFF
+    host2.tofile(path)
+    with pytest.raises(UnicodeDecodeError):
+        run_train_bpe(path, 500, [])

@@ -81,6 +81,81 @@ def train_bpe_on_bytes(data, vocab_size: int, special_tokens: List[str] = [], *,
     return out + (stats.as_dict(),) if return_stats else out
 
 
+_STREAM_MIN = 512 << 20          # files at least this big are streamed: read, upload and counting overlap
+_STREAM_CHUNK = 256 << 20
+_STREAM_HALO_LEFT = 64
+_STREAM_HALO_RIGHT = 64 << 10
+_READ_THREADS = 4
+
+
+def _pread_into(fd: int, view: memoryview, offset: int) -> None:
+    got = 0
+    while got < len(view):
+        k = os.preadv(fd, [view[got:]], offset + got)
+        if k <= 0:
+            raise OSError("short read at offset %d" % (offset + got))
+        got += k
+
+
+def _train_bpe_streamed(input_path, size: int, vocab_size: int, special_tokens: List[str], ctx=None, return_stats: bool = False):
+    """Ingest path for big files: the file is read in 256 MB chunks, each with a small halo, by a few
+    threads into page-locked buffers while the GPU pretokenises and counts the previous chunk (bpe_count_add_shard --
+    the same shard contract as the multi-GPU path); then the merge loop runs on the counts.  Returns None when the file
+    needs the one-piece path (a carriage return: universal newlines shift offsets; or a pretoken longer than the halo)."""
+    import concurrent.futures as cf
+    from .sharded import DeviceCounter, align_cut, _raise_decode_error
+    fd = os.open(os.fspath(input_path), os.O_RDONLY)
+    bufs = []
+    try:
+        def peek(lo, hi):
+            return os.pread(fd, hi - lo, lo)
+        cuts = [0]
+        p = _STREAM_CHUNK
+        while p + _STREAM_CHUNK // 2 < size:
+            cuts.append(align_cut(peek, p, size))
+            p += _STREAM_CHUNK
+        cuts.append(size)
+        ranges = []
+        for k in range(len(cuts) - 1):
+            lo, hi = cuts[k], cuts[k + 1]
+            rlo = align_cut(peek, max(0, lo - _STREAM_HALO_LEFT), size)
+            rhi = align_cut(peek, min(size, hi + _STREAM_HALO_RIGHT), size)
+            ranges.append((lo, hi, rlo, rhi))
+        cap = max(r[3] - r[2] for r in ranges)
+        bufs = [_lib.PinnedBuffer(cap) for _ in range(min(3, len(ranges)))]
+        pool = cf.ThreadPoolExecutor(max_workers=_READ_THREADS)
+
+        def submit(k):
+            lo, hi, rlo, rhi = ranges[k]
+            mv = memoryview(bufs[k % len(bufs)].array)[: rhi - rlo]
+            step = -(-(rhi - rlo) // _READ_THREADS)
+            return [pool.submit(_pread_into, fd, mv[o: min(o + step, rhi - rlo)], rlo + o) for o in range(0, rhi - rlo, step)]
+
+        counter = DeviceCounter(ctx)
+        pending = {k: submit(k) for k in range(min(len(bufs) - 1, len(ranges)))}
+        for k, (lo, hi, rlo, rhi) in enumerate(ranges):
+            nxt = k + len(bufs) - 1
+            if nxt < len(ranges) and nxt not in pending:
+                pending[nxt] = submit(nxt)       # its buffer was consumed by chunk nxt - len(bufs), already counted
+            for fut in pending.pop(k):
+                fut.result()
+            status = counter.add(bufs[k % len(bufs)].array[: rhi - rlo], lo - rlo, hi - rlo, rlo == 0, rhi == size)
+            if status is not None:
+                for futs in pending.values():
+                    for fut in futs:
+                        fut.result()
+                pool.shutdown()
+                if status[0] == "utf8":
+                    _raise_decode_error(peek, size, rlo + status[1])      # what open(path, encoding="utf-8").read() raises
+                return None
+        pool.shutdown()
+        return counter.finish(vocab_size, special_tokens, return_stats=return_stats)
+    finally:
+        for b in bufs:
+            b.free()
+        os.close(fd)
+
+
 def train_bpe(input_path, vocab_size: int, special_tokens: List[str] = [], *, distributed: bool = False, **kwargs):
     """Drop-in for models/tokenizer/train.py:142 train_bpe.  Extra keyword arguments are ours (the reference's
     adapter never passes any): ctx=, return_stats=, and distributed=True to shard the file over the ranks of the
@@ -90,6 +165,12 @@ def train_bpe(input_path, vocab_size: int, special_tokens: List[str] = [], *, di
         return train_bpe_sharded(input_path, vocab_size, special_tokens, **kwargs)
     t0 = time.time()
     logger.info("Extracting subword frequencies")
+    size = os.path.getsize(input_path)           # FileNotFoundError like open() in the reference
+    if size >= _STREAM_MIN:
+        res = _train_bpe_streamed(input_path, size, vocab_size, special_tokens, **kwargs)
+        if res is not None:
+            logger.info("Took %s seconds to read, pretokenize, count and merge %d bytes (streamed)", round(time.time() - t0, 2), size)
+            return res
     arr, _keep = _read_file(input_path)
     logger.info("Took %s seconds to read %d bytes", round(time.time() - t0, 2), arr.size)
     t1 = time.time()
