@@ -124,7 +124,8 @@ __global__ void __launch_bounds__(256) k_count_pretokens(CountTables t, const u3
         const uint8_t *p = t.text + pos;
         if (len <= SHORT_MAX) {
             const u64 key = short_key(p, (u32)len);
-            u32 slot = (u32)mix64(key) & (CNT_SMEM_SLOTS - 1);
+            u32 slot = (((u32)key ^ (u32)(key >> 32)) * 0x9E3779B1u) >> (32 - 11);   // cheap hash for the shared-memory table
+            static_assert(CNT_SMEM_SLOTS == 1u << 11, "slot hash assumes 2048 slots");
             bool done = false;
             for (u32 pr = 0; pr < CNT_SMEM_PROBES && !done; pr++) {
                 u64 k = s_key[slot];
