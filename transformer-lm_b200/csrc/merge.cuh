@@ -29,6 +29,20 @@
 
 namespace cg = cooperative_groups;
 
+// Compile-time experiment switches of k_merge_loop (defaults = the fastest measured combination on B200):
+//   1 = LL-style gather (tag in every word) instead of flag-then-data      2 = new keys are claimed by a CAS-first probe
+//   4 = the four symbols around a site are loaded together                  8 = relaxed polls + fence in the flag gather
+//  16 = release / acquire flag barrier instead of fence + relaxed
+#ifndef MG_OPT
+#define MG_OPT 22u
+#endif
+// slot hash of the pair table: 32-bit multiplies only (the apply path computes four of these per site)
+__device__ __forceinline__ u32 pair_hash(u64 key) {
+    u32 h = ((u32)(key >> 32) * 0x9E3779B1u) ^ ((u32)key * 0x85EBCA77u);
+    h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15;
+    return h;
+}
+
 #define PAIR_EMPTY 0xFFFFFFFFFFFFFFFFull
 #define CNT_DEAD ((i64)0x8000000000000000ll)     // key was popped from the dict (train.py:226)
 #define CNT_DEAD_LIMIT ((i64)0xC000000000000000ll) // counts below this are "popped (+ later deltas)"
@@ -93,7 +107,8 @@ struct MergeState {
     // bk_lg[step] = log2(buckets) (0 = slice left unsorted), bk_start[step] = first of its buckets+1 offsets in bk_off
     Rec *log2; u32 *bk_lg; u64 *bk_start; u32 *bk_off; u64 bk_off_cap; u32 *bk_scratch;   // bk_scratch: 2 x (hist, cursor) x SORT_MAX_BK
     u32 *tok_off; u32 *tok_len; u64 *tok_key; uint8_t *tok_bytes; u64 tok_bytes_cap;
-    Best *cta_best;
+    Best *cta_best;                               // (unused by the flag barrier; kept for the tail kernel's host code)
+    struct BarSlot *bar; u32 *bar_flags;          // gather slots / barrier epochs of k_merge_loop, zeroed before every launch
     // tail kernel (one thread-block cluster): per 64-block superblock a 64-bit mask of dirty blocks
     u64 *sdirty_mask; u32 n_super; int tail_mode;
     int stop_at;                                 // this launch runs steps [ctr[1], stop_at)
@@ -106,6 +121,8 @@ struct MergeState {
     // profile (ns / counts): [0]=phase1 [1]=sync1 [2]=apply [3]=sync2 on CTA 0; [4]=token CTA work; [5]=index records scanned;
     // [6]=words rewritten; [7]=steps; [9]=dirty blocks rescanned
     u64 *prof;
+    u32 opt;          // experiment switches (BPE_MERGE_OPT): 1 = LL gather, 2 = CAS-first new keys, 8 = relaxed polls in the flag gather
+    u64 *cta_prof;    // optional (profile builds): per step and CTA {start, arrive1, exit1, arrive2}
     u32 *step_prof;   // optional per-step trace: 4 x u32 per step (phase1+sync1 ns, apply+sync2 ns, records scanned, words rewritten so far)
 };
 
@@ -217,27 +234,28 @@ __device__ __forceinline__ void mark_dirty(u64 slot) {
 // frequencies[key] += delta with defaultdict semantics (train.py:36,65-78): a missing key is created.
 // The count update is a fire-and-forget reduction; a popped key that is touched again is repaired by
 // the next rescan of its block (see rescan_block).  (s, k) = first probe slot and the key read there.
-__device__ __noinline__ void pair_add_from(u64 key, i64 delta, u64 s, u64 k) {
+// kClaimed: the probe at slot s was the claiming CAS itself and k is what that CAS returned (only for keys that cannot
+// have been in the table before this step); otherwise k is the key read at s.
+template <bool kClaimed>
+__device__ __forceinline__ void pair_add_probe(u64 key, i64 delta, u64 s, u64 k) {
     const u64 mask = cM.pcap - 1;
     for (u64 probes = 0; probes < cM.pcap; probes++) {
-        if (k == PAIR_EMPTY) {
-            u64 old = atomicCAS(&cM.pkey[s], PAIR_EMPTY, key);
-            if (old == PAIR_EMPTY) { atomicAdd(&cM.ctr[2], 1ull); k = key; }
-            else k = old;
-        }
+        if (!kClaimed && k == PAIR_EMPTY) k = atomicCAS(&cM.pkey[s], PAIR_EMPTY, key);
+        if (k == PAIR_EMPTY) { atomicAdd(&cM.ctr[2], 1ull); k = key; }       // our CAS claimed the slot
         if (k == key) {
             atomicAdd((u64 *)&cM.pcnt[s], (u64)delta);
             mark_dirty(s);
             return;
         }
         s = (s + 1) & mask;
-        k = cM.pkey[s];
+        k = kClaimed ? atomicCAS(&cM.pkey[s], PAIR_EMPTY, key) : cM.pkey[s];
     }
     cM.ctr[3] = 1;                                // table full
 }
+__device__ __noinline__ void pair_add_from(u64 key, i64 delta, u64 s, u64 k) { pair_add_probe<false>(key, delta, s, k); }
 __device__ __forceinline__ void pair_add(u32 a, u32 b, i64 delta) {
     u64 key = ((u64)a << 32) | b;
-    u64 s = mix64(key) & (cM.pcap - 1);
+    u64 s = pair_hash(key) & (cM.pcap - 1);
     pair_add_from(key, delta, s, cM.pkey[s]);
 }
 
@@ -260,80 +278,91 @@ __device__ __noinline__ void apply_site(u32 p, i64 c, u32 a, u32 b, u32 nw, int 
     const int32_t ia = (int32_t)a, ib = (int32_t)b, inw = (int32_t)nw;
 #define ORIG(e) ((e) == inw ? ia : ((e) == dead_now ? ib : (e)))            /* value at the start of the step */
 #define WAS_LIVE(e) ((e) >= 0 || (e) == dead_now)                          /* live at the start of the step */
-#define SKIP_OLD_LEFT(q) while (s[q] < SYM_SEP && s[q] != dead_now) (q)--   /* tombstones of earlier steps */
-#define SKIP_OLD_RIGHT(q) while (s[q] < SYM_SEP && s[q] != dead_now) (q)++
+#define OLD_TOMB(e) ((e) < SYM_SEP && (e) != dead_now)                     /* tombstone of an earlier step */
+    // the four symbols around p are loaded together (one round trip in the common case of no old tombstones)
+    const bool upfront = (MG_OPT & 4u) != 0;
+    int32_t vl = 0, vb = 0, vr = 0;
     const int32_t e0 = s[p];
+    if (upfront) { vl = s[p - 1]; vb = s[p + 1]; vr = s[p + 2]; }
     if (!WAS_LIVE(e0) || ORIG(e0) != ia) return;                           // stale record
     u32 pb = p + 1;
-    SKIP_OLD_RIGHT(pb);
-    { const int32_t e = s[pb]; if (!WAS_LIVE(e) || ORIG(e) != ib) return; } // stale record
+    if (!upfront) vb = s[pb];
+    while (OLD_TOMB(vb)) { pb++; vb = s[pb]; }
+    if (!WAS_LIVE(vb) || ORIG(vb) != ib) return;                           // stale record
     // ---- left context ----
     bool has_l = false; u32 left = 0, pos_l = 0;
     u32 q = p - 1;
-    SKIP_OLD_LEFT(q);
+    if (!upfront) vl = s[q];
+    while (OLD_TOMB(vl)) { q--; vl = s[q]; }
     if (a == b) {
         // run of a's ending just before p: its length decides whether p starts a site
-        u32 n_left = 0, first = p, second = p;                             // positions of the two nearest a's on the left
-        while (WAS_LIVE(s[q]) && ORIG(s[q]) == ia) {
+        u32 n_left = 0, second = p;                                        // position of the second nearest a on the left
+        while (WAS_LIVE(vl) && ORIG(vl) == ia) {
             n_left++;
-            if (n_left == 1) first = q; else if (n_left == 2) second = q;
-            q--;
-            SKIP_OLD_LEFT(q);
+            if (n_left == 2) second = q;
+            q--; vl = s[q];
+            while (OLD_TOMB(vl)) { q--; vl = s[q]; }
         }
         if (n_left & 1u) return;                                           // the a at p is the right half of the previous site
-        if (n_left) { has_l = true; left = nw; pos_l = second; (void)first; }
-        else if (s[q] != SYM_SEP) { has_l = true; left = (u32)ORIG(s[q]); pos_l = q; }
-    } else if (s[q] != SYM_SEP) {
-        const int32_t o1 = ORIG(s[q]);
+        if (n_left) { has_l = true; left = nw; pos_l = second; }
+        else if (vl != SYM_SEP) { has_l = true; left = (u32)ORIG(vl); pos_l = q; }
+    } else if (vl != SYM_SEP) {
+        const int32_t o1 = ORIG(vl);
         has_l = true; left = (u32)o1; pos_l = q;
         if (o1 == ib) {                                                    // (.., a, b, [a, b]): the left occurrence is a site too
             u32 q2 = q - 1;
-            SKIP_OLD_LEFT(q2);
-            if (WAS_LIVE(s[q2]) && ORIG(s[q2]) == ia) { left = nw; pos_l = q2; }
+            int32_t v2 = s[q2];
+            while (OLD_TOMB(v2)) { q2--; v2 = s[q2]; }
+            if (WAS_LIVE(v2) && ORIG(v2) == ia) { left = nw; pos_l = q2; }
         }
     }
     // ---- right context: the symbol as it was (it is merged later, if at all) ----
     u32 qr = pb + 1;
-    SKIP_OLD_RIGHT(qr);
-    const bool has_r = s[qr] != SYM_SEP;
-    const u32 right = has_r ? (u32)ORIG(s[qr]) : 0;
-    // ---- the four dict updates of update_frequencies_after_merge: first probes issued together ----
+    if (!upfront || pb != p + 1) vr = s[qr];
+    while (OLD_TOMB(vr)) { qr++; vr = s[qr]; }
+    const bool has_r = vr != SYM_SEP;
+    const u32 right = has_r ? (u32)ORIG(vr) : 0;
+    // ---- the four dict updates of update_frequencies_after_merge.  (left, nw) and (nw, right) contain the token made in
+    // this step, so they are not in the table unless another site of this step put them there: their first probe is the
+    // claiming CAS itself, issued together with the read probes of the two old keys and the log allocation ----
     const u64 mask = cM.pcap - 1;
     const u64 k0 = ((u64)left << 32) | a, k1 = ((u64)left << 32) | nw, k2 = ((u64)b << 32) | right, k3 = ((u64)nw << 32) | right;
-    const u64 s0 = mix64(k0) & mask, s1 = mix64(k1) & mask, s2 = mix64(k2) & mask, s3 = mix64(k3) & mask;
+    const u64 s0 = pair_hash(k0) & mask, s1 = pair_hash(k1) & mask, s2 = pair_hash(k2) & mask, s3 = pair_hash(k3) & mask;
     u64 v0 = 0, v1 = 0, v2 = 0, v3 = 0;
-    if (has_l) { v0 = cM.pkey[s0]; v1 = cM.pkey[s1]; }
-    if (has_r) { v2 = cM.pkey[s2]; v3 = cM.pkey[s3]; }
+    const bool cas_first = (MG_OPT & 2u) != 0;
+    if (has_l) { v0 = cM.pkey[s0]; v1 = cas_first ? atomicCAS(&cM.pkey[s1], PAIR_EMPTY, k1) : cM.pkey[s1]; }
+    if (has_r) { v2 = cM.pkey[s2]; v3 = cas_first ? atomicCAS(&cM.pkey[s3], PAIR_EMPTY, k3) : cM.pkey[s3]; }
     // index records of the two new pairs: one atomic per group of threads that arrive here together
     const u32 n_rec = (u32)has_l + (u32)has_r;
     u64 li = 0;
-    if (n_rec) {
-        cg::coalesced_group cgp = cg::coalesced_threads();
-        u32 pre = cg::exclusive_scan(cgp, n_rec);
+    {
+        const u32 act = __activemask();
+        const u32 ml = __ballot_sync(act, has_l), mr = __ballot_sync(act, has_r);
+        const u32 lt = (1u << lane_id()) - 1u;
+        const u32 pre = __popc(ml & lt) + __popc(mr & lt), tot = __popc(ml) + __popc(mr);
+        const int leader = __ffs(act) - 1;
         u64 base = 0;
-        if (cgp.thread_rank() == cgp.size() - 1) base = atomicAdd(&cM.ctr[0], (u64)(pre + n_rec));
-        li = cgp.shfl(base, cgp.size() - 1) + pre;
+        if ((int)lane_id() == leader && tot) base = atomicAdd(&cM.ctr[0], (u64)tot);
+        li = __shfl_sync(act, base, leader) + pre;
     }
     const bool log_ok = li + n_rec <= cM.log_cap;
     if (!log_ok) cM.ctr[3] = 2;
     s[p] = inw; s[pb] = dead_now;                                          // merge_subwords: positions never move
     if (has_l) {
-        pair_add_from(k0, -c, s0, v0);
-        pair_add_from(k1, c, s1, v1);
+        pair_add_probe<false>(k0, -c, s0, v0);
+        if (cas_first) pair_add_probe<true>(k1, c, s1, v1); else pair_add_probe<false>(k1, c, s1, v1);
         if (log_ok) store_rec(&cM.log[li], left, pos_l, c);                 // (left, nw) at the position of `left`
         li++;
     }
     if (has_r) {
-        pair_add_from(k2, -c, s2, v2);
-        pair_add_from(k3, c, s3, v3);
+        pair_add_probe<false>(k2, -c, s2, v2);
+        if (cas_first) pair_add_probe<true>(k3, c, s3, v3); else pair_add_probe<false>(k3, c, s3, v3);
         if (log_ok) store_rec(&cM.log[li], 0x80000000u | right, p, c);      // (nw, right) at p
     }
-    atomicAdd(&cM.ctr[8], 1ull);
     PROF_ADD(6, 1);
 #undef ORIG
 #undef WAS_LIVE
-#undef SKIP_OLD_LEFT
-#undef SKIP_OLD_RIGHT
+#undef OLD_TOMB
 }
 
 // Rescan the PB slots of one block with a full warp.  Pops `prev_key` when it meets it and repairs
@@ -393,7 +422,7 @@ __device__ __forceinline__ void token_bookkeeping(int step, const Best &win, u32
     }
     // make sure the winner's block is rescanned so the key gets popped
     if (tid == 32) {
-        u64 mask = cM.pcap - 1, s = mix64(win.key) & mask;
+        u64 mask = cM.pcap - 1, s = pair_hash(win.key) & mask;
         while (cM.pkey[s] != win.key) s = (s + 1) & mask;
         mark_dirty(s);
     }
@@ -494,16 +523,170 @@ __device__ __forceinline__ void apply_winner(int step, u32 a, u32 b, u32 nw, u64
     }
 }
 
+// ---- grid-wide synchronisation of k_merge_loop (all CTAs are co-resident: cooperative launch) ------------------------
+// Two primitives, both without a hot counter: every CTA owns a slot, warp 0 of every CTA polls all slots.
+//  * grid_barrier: a dense array of 32-bit epochs (148 x 4 B = five sectors per poll).
+//  * grid_gather:  barrier + all-gather of the per-CTA arg-max candidates in one step.  A slot is eight 64-bit words
+//    {32 payload bits, 32-bit epoch tag} (the layout of NCCL's LL protocol): a word whose tag equals the epoch carries
+//    valid payload, so the poll that sees the last CTA arrive already holds its candidate -- no flag-then-data round trip.
+// Ordering: the publisher fences before its relaxed stores, the pollers fence after the poll (fence-fence synchronisation
+// at gpu scope); the CTA barriers on both sides extend it to the other warps.
+struct __align__(64) BarSlot { u64 w[8]; };
+__device__ __forceinline__ void st_relaxed_v2(u64 *p, u64 a, u64 b) { asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory"); }
+__device__ __forceinline__ void ld_relaxed_v2(const u64 *p, u64 &a, u64 &b) { asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory"); }
+__device__ __forceinline__ void st_relaxed_u32(u32 *p, u32 v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ u32 ld_relaxed_u32(const u32 *p) { u32 v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_release_u32(u32 *p, u32 v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ u32 ld_acquire_u32(const u32 *p) { u32 v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+#define MG_MAX_CTAS 160u
+// Called by all threads of the CTA.
+__device__ __forceinline__ void grid_barrier(u32 *flags, u32 G, u32 epoch, u64 *tp = nullptr) {
+    __syncthreads();
+#ifdef BPE_MERGE_PROFILE
+    if (tp && threadIdx.x == 0) tp[0] = gtime_ns();
+#endif
+    if (threadIdx.x < 32) {
+        const u32 lane = threadIdx.x;
+        const bool acq = (MG_OPT & 16u) != 0;
+        if (lane == 0) { if (acq) st_release_u32(&flags[blockIdx.x], epoch); else { __threadfence(); st_relaxed_u32(&flags[blockIdx.x], epoch); } }
+        bool done;
+        do {
+            done = true;
+#pragma unroll
+            for (u32 k = 0; k < MG_MAX_CTAS / 32; k++) {                  // (a fast CTA may already be at the next barrier)
+                const u32 i = lane + 32 * k;
+                if (i < G && (int)((acq ? ld_acquire_u32(&flags[i]) : ld_relaxed_u32(&flags[i])) - epoch) < 0) done = false;
+            }
+        } while (!__all_sync(0xffffffffu, done));
+        if (!acq) __threadfence();
+    }
+    __syncthreads();
+}
+// Called by all threads of the CTA; `mine` is read from warp 0 (uniform).  Returns the maximum of all CTAs' candidates in
+// every lane of warp 0 (other warps: BEST_NONE).  Two gathers are always separated by a grid_barrier, so a slot never
+// holds a newer epoch than the one polled for.
+__device__ __forceinline__ Best grid_gather(BarSlot *slots, u32 G, u32 epoch, const Best &mine, u64 *tp = nullptr) {
+    __syncthreads();
+#ifdef BPE_MERGE_PROFILE
+    if (tp && threadIdx.x == 0) tp[0] = gtime_ns();
+#endif
+    Best c = BEST_NONE;
+    if (threadIdx.x < 32) {
+        const u32 lane = threadIdx.x;
+        if (lane == 0) {
+            const u64 tag = (u64)epoch << 32;
+            u64 *w = slots[blockIdx.x].w;
+            __threadfence();
+            st_relaxed_v2(w + 0, tag | (u32)mine.cnt, tag | (u32)((u64)mine.cnt >> 32));
+            st_relaxed_v2(w + 2, tag | (u32)mine.key, tag | (u32)(mine.key >> 32));
+            st_relaxed_v2(w + 4, tag | (u32)mine.ka, tag | (u32)(mine.ka >> 32));
+            st_relaxed_v2(w + 6, tag | (u32)mine.kb, tag | (u32)(mine.kb >> 32));
+        }
+        u32 pending = 0;                         // bit k: slot lane + 32 k not seen yet
+#pragma unroll
+        for (u32 k = 0; k < MG_MAX_CTAS / 32; k++) if (lane + 32 * k < G) pending |= 1u << k;
+        while (__any_sync(0xffffffffu, pending != 0)) {
+#pragma unroll
+            for (u32 k = 0; k < MG_MAX_CTAS / 32; k++) {
+                if (!((pending >> k) & 1u)) continue;
+                const u64 *w = slots[lane + 32 * k].w;
+                u64 x[8];
+                ld_relaxed_v2(w + 0, x[0], x[1]); ld_relaxed_v2(w + 2, x[2], x[3]);
+                ld_relaxed_v2(w + 4, x[4], x[5]); ld_relaxed_v2(w + 6, x[6], x[7]);
+                bool ok = true;
+#pragma unroll
+                for (u32 j = 0; j < 8; j++) ok = ok && (u32)(x[j] >> 32) == epoch;
+                if (!ok) continue;
+                pending &= ~(1u << k);
+                Best o;
+                o.cnt = (i64)((x[0] & 0xffffffffull) | (x[1] << 32)); o.key = (x[2] & 0xffffffffull) | (x[3] << 32);
+                o.ka = (x[4] & 0xffffffffull) | (x[5] << 32); o.kb = (x[6] & 0xffffffffull) | (x[7] << 32);
+                if (o.cnt != CNT_DEAD && best_greater(o, c)) c = o;
+            }
+        }
+        __threadfence();
+        c = warp_best(c);
+    }
+    __syncthreads();
+#ifdef BPE_MERGE_PROFILE
+    if (tp && threadIdx.x == 0) tp[1] = gtime_ns();
+#endif
+    return c;
+}
+
+// Flag-then-data variant: slot = {candidate (w[0..3]), epoch (w[4])}.
+__device__ __forceinline__ Best grid_gather_flag(BarSlot *slots, u32 G, u32 epoch, const Best &mine, bool relaxed, u64 *tp = nullptr) {
+    __syncthreads();
+#ifdef BPE_MERGE_PROFILE
+    if (tp && threadIdx.x == 0) tp[0] = gtime_ns();
+#endif
+    Best c = BEST_NONE;
+    if (threadIdx.x < 32) {
+        const u32 lane = threadIdx.x;
+        if (lane == 0) {
+            store_best(reinterpret_cast<Best *>(slots[blockIdx.x].w), mine);
+            st_release_u32(reinterpret_cast<u32 *>(&slots[blockIdx.x].w[4]), epoch);
+        }
+        bool done;
+        do {
+            done = true;
+#pragma unroll
+            for (u32 k = 0; k < MG_MAX_CTAS / 32; k++) {
+                const u32 i = lane + 32 * k;
+                if (i < G) {
+                    const u32 *f = reinterpret_cast<const u32 *>(&slots[i].w[4]);
+                    const u32 e = relaxed ? ld_relaxed_u32(f) : ld_acquire_u32(f);
+                    if (e != epoch) done = false;
+                }
+            }
+        } while (!__all_sync(0xffffffffu, done));
+        if (relaxed) __threadfence();
+        Best o5[MG_MAX_CTAS / 32];
+#pragma unroll
+        for (u32 k = 0; k < MG_MAX_CTAS / 32; k++) { const u32 i = lane + 32 * k; o5[k] = i < G ? load_best(reinterpret_cast<const Best *>(slots[i].w)) : BEST_NONE; }
+#pragma unroll
+        for (u32 k = 0; k < MG_MAX_CTAS / 32; k++) if (o5[k].cnt != CNT_DEAD && best_greater(o5[k], c)) c = o5[k];
+        c = warp_best(c);
+    }
+    __syncthreads();
+#ifdef BPE_MERGE_PROFILE
+    if (tp && threadIdx.x == 0) tp[1] = gtime_ns();
+#endif
+    return c;
+}
+
+// ---- shared-memory copy of the cached block maxima a CTA owns (structure of arrays: conflict-free 8-byte accesses) ----
+#define MG_CACHE_ITERS 5u                        // chunks (of 64 blocks) per warp kept in shared memory; more are read from bmax
+#define MG_CACHE_N (MG_CACHE_ITERS * (MG_NT / 32) * 64u)
+#define MG_LIST_CAP 4096u                        // dirty blocks a CTA lists per step; the overflow is rescanned by the owning warp
+#define MG_DYN_SMEM ((size_t)MG_CACHE_N * 32 + (size_t)MG_LIST_CAP * 4)
+struct BmaxCache { i64 *cnt; u64 *key, *ka, *kb; };
+__device__ __forceinline__ BmaxCache bmax_cache(unsigned char *base) {
+    BmaxCache c;
+    c.cnt = reinterpret_cast<i64 *>(base); c.key = reinterpret_cast<u64 *>(base) + MG_CACHE_N;
+    c.ka = c.key + MG_CACHE_N; c.kb = c.ka + MG_CACHE_N;
+    return c;
+}
+__device__ __forceinline__ void cache_store(const BmaxCache &c, u32 i, const Best &b) { c.cnt[i] = b.cnt; c.key[i] = b.key; c.ka[i] = b.ka; c.kb[i] = b.kb; }
+__device__ __forceinline__ void cache_consider(const BmaxCache &c, u32 i, Best &mine) {
+    const i64 n = c.cnt[i];
+    if (n == CNT_DEAD || n < mine.cnt) return;
+    Best o; o.cnt = n; o.key = c.key[i]; o.ka = c.ka[i]; o.kb = c.kb[i];
+    if (best_greater(o, mine)) mine = o;
+}
+
 __global__ void __launch_bounds__(MG_NT) k_merge_loop() {
-    cg::grid_group grid = cg::this_grid();
     __shared__ Best s_best[MG_NT / 32];
     __shared__ Best s_win;
     __shared__ u64 s_status[2];
     __shared__ u64 s_range[4];
     __shared__ u32 s_scan[SORT_MAX_BK];
+    __shared__ u32 s_nd;                         // dirty blocks listed in this step
+    extern __shared__ __align__(16) unsigned char mg_smem[];
     const u32 tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
     const u32 G = gridDim.x;
     u32 n_sorts = 0;
+    u32 epoch = 0, gepoch = 0;                   // barriers / gathers passed in this launch (the slots start at 0)
     const u32 warps_per_cta = MG_NT / 32;
     const u32 gwarp = blockIdx.x * warps_per_cta + warp, total_warps = G * warps_per_cta;
     const bool token_cta = blockIdx.x == G - 1;
@@ -511,17 +694,24 @@ __global__ void __launch_bounds__(MG_NT) k_merge_loop() {
     u64 prev_key = cM.ctr[6];                     // winner of the previous step: popped lazily during the rescan
     const int first_step = (int)cM.ctr[1];
     u32 n_tok = 256 + (u32)first_step;
+    // The cached block maxima of the chunks this CTA owns stay in shared memory for the whole launch (chunk (it, warp) =
+    // 64 blocks starting at (it * total_warps + gwarp) * 64); bmax in global memory is written through for the next launch.
+    const BmaxCache sc = bmax_cache(mg_smem);
+    if (tid == 0) s_nd = 0;
+    u32 *s_list = reinterpret_cast<u32 *>(mg_smem + (size_t)MG_CACHE_N * 32);
+    const u32 n_iter = (cM.n_blocks + total_warps * 64 - 1) / (total_warps * 64);
+    for (u32 it = 0; it < n_iter && it < MG_CACHE_ITERS; it++) {
+        const u32 base = (it * total_warps + gwarp) * 64, i0 = (it * warps_per_cta + warp) * 64 + lane;
+        cache_store(sc, i0, base + lane < cM.n_blocks ? load_best(&cM.bmax[base + lane]) : BEST_NONE);
+        cache_store(sc, i0 + 32, base + 32 + lane < cM.n_blocks ? load_best(&cM.bmax[base + 32 + lane]) : BEST_NONE);
+    }
+    __syncthreads();
 
     for (int step = first_step; step < cM.stop_at; step++) {
-        // status flags are written before the grid.sync that ends a step and read here: uniform across the grid
-        if (tid == 0) { s_status[0] = *((volatile u64 *)&cM.ctr[3]); s_status[1] = *((volatile u64 *)&cM.ctr[2]); }
-        __syncthreads();
-        if (s_status[0]) break;
-        if (s_status[1] * 2 > cM.pcap) {         // table over half full: hand back to the host to grow it
-            grid.sync();
-            if (blockIdx.x == 0 && tid == 0) { cM.ctr[6] = prev_key; cM.ctr[3] = MG_NEED_GROW; }
-            return;
-        }
+        // status flags are written before the barrier that ends a step and read here (uniform across the grid); the loads
+        // overlap with the dirty-flag loads of phase 1A and are checked behind its CTA barrier
+        u64 st_err = 0, st_keys = 0;
+        if (tid == 0) { st_err = *((volatile u64 *)&cM.ctr[3]); st_keys = *((volatile u64 *)&cM.ctr[2]); }
         // ---- phase 1: rescan dirty blocks, reduce cached block maxima to one candidate per CTA ----
         if (blockIdx.x == 0 && tid == 0) cM.log_begin[step] = cM.ctr[0];
 #ifdef BPE_MERGE_PROFILE
@@ -530,55 +720,93 @@ __global__ void __launch_bounds__(MG_NT) k_merge_loop() {
         const bool prof_thread = false;
 #endif
         u64 t0 = prof_thread ? gtime_ns() : 0;
+#ifdef BPE_MERGE_PROFILE
+        u64 *ctp = cM.cta_prof ? cM.cta_prof + ((size_t)step * G + blockIdx.x) * 4 : nullptr;
+        if (ctp && tid == 0) ctp[0] = gtime_ns();
+#else
+        u64 *ctp = nullptr;
+#endif
         Best mine = BEST_NONE;
-        for (u32 base = gwarp * 64; base < cM.n_blocks; base += total_warps * 64) {
-            // 64 consecutive blocks per warp iteration: flags and cached maxima are loaded unconditionally
-            u32 b0 = base + lane, b1 = base + 32 + lane;
-            bool d0 = b0 < cM.n_blocks && cM.dirty[b0], d1 = b1 < cM.n_blocks && cM.dirty[b1];
-            Best m0 = BEST_NONE, m1 = BEST_NONE;
-            if (b0 < cM.n_blocks) m0 = load_best(&cM.bmax[b0]);
-            if (b1 < cM.n_blocks) m1 = load_best(&cM.bmax[b1]);
-            u64 dm = (u64)__ballot_sync(0xffffffffu, d0) | ((u64)__ballot_sync(0xffffffffu, d1) << 32);
-            while (dm) {                         // warp-cooperative rescan of every dirty block (single inlined copy)
-                u32 l2 = __ffsll((long long)dm) - 1; dm &= dm - 1;
-                Best bst = rescan_block(base + l2, prev_key);
-                if (lane == (l2 & 31)) {
-                    if (l2 < 32) m0 = bst; else m1 = bst;
-                    store_best(&cM.bmax[base + l2], bst); cM.dirty[base + l2] = 0; PROF_ADD(9, 1);
+        // A: collect the dirty blocks of this CTA's chunks in a shared list (any warp of the CTA may rescan them)
+        for (u32 it = 0; it < n_iter; it++) {
+            const u32 base = (it * total_warps + gwarp) * 64;
+            const u32 b0 = base + lane, b1 = base + 32 + lane;
+            const bool d0 = b0 < cM.n_blocks && cM.dirty[b0], d1 = b1 < cM.n_blocks && cM.dirty[b1];
+            const u32 dlo = __ballot_sync(0xffffffffu, d0), dhi = __ballot_sync(0xffffffffu, d1);
+            if (dlo | dhi) {
+                const u32 nlo = __popc(dlo), n = nlo + __popc(dhi);
+                u32 pos = 0;
+                if (lane == 0) pos = atomicAdd(&s_nd, n);
+                pos = __shfl_sync(0xffffffffu, pos, 0);
+                const u32 lt = (1u << lane) - 1u;
+                const u32 e0 = pos + __popc(dlo & lt), e1 = pos + nlo + __popc(dhi & lt);
+                if (d0 && e0 < MG_LIST_CAP) s_list[e0] = b0;
+                if (d1 && e1 < MG_LIST_CAP) s_list[e1] = b1;
+                if (pos + n > MG_LIST_CAP) {     // list full (huge tables, first step): this warp rescans the rest itself
+                    u64 dm = (u64)__ballot_sync(0xffffffffu, d0 && e0 >= MG_LIST_CAP) | ((u64)__ballot_sync(0xffffffffu, d1 && e1 >= MG_LIST_CAP) << 32);
+                    while (dm) {
+                        const u32 l2 = __ffsll((long long)dm) - 1; dm &= dm - 1;
+                        const Best bst = rescan_block(base + l2, prev_key);
+                        if (lane == 0) { store_best(&cM.bmax[base + l2], bst); cM.dirty[base + l2] = 0; if (it < MG_CACHE_ITERS) cache_store(sc, (it * warps_per_cta + warp) * 64 + l2, bst); }
+                    }
                 }
             }
-            if (m0.cnt != CNT_DEAD && best_greater(m0, mine)) mine = m0;
-            if (m1.cnt != CNT_DEAD && best_greater(m1, mine)) mine = m1;
+        }
+        if (tid == 0) { s_status[0] = st_err; s_status[1] = st_keys; }
+        __syncthreads();
+        if (s_status[0]) break;
+        if (s_status[1] * 2 > cM.pcap) {         // table over half full: hand back to the host to grow it
+            grid_barrier(cM.bar_flags, G, ++epoch);
+            if (blockIdx.x == 0 && tid == 0) { cM.ctr[6] = prev_key; cM.ctr[3] = MG_NEED_GROW; }
+            return;
+        }
+        // B: the CTA's warps share the rescans evenly
+        {
+            const u32 nd = s_nd < MG_LIST_CAP ? s_nd : MG_LIST_CAP;
+            for (u32 e = warp; e < nd; e += warps_per_cta) {
+                const u32 blk = s_list[e];
+                const Best bst = rescan_block(blk, prev_key);
+                if (lane == 0) {
+                    store_best(&cM.bmax[blk], bst); cM.dirty[blk] = 0; PROF_ADD(9, 1);
+                    const u32 chunk = blk >> 6, it = chunk / total_warps, w = chunk - it * total_warps - blockIdx.x * warps_per_cta;
+                    if (it < MG_CACHE_ITERS) cache_store(sc, (it * warps_per_cta + w) * 64 + (blk & 63u), bst);
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) s_nd = 0;                  // (next written in phase A of the next step)
+        // C: maximum of the cached block maxima this warp owns (shared memory; global for chunks beyond the cache)
+        for (u32 it = 0; it < n_iter; it++) {
+            if (it < MG_CACHE_ITERS) {
+                const u32 i0 = (it * warps_per_cta + warp) * 64 + lane;
+                cache_consider(sc, i0, mine);
+                cache_consider(sc, i0 + 32, mine);
+            } else {
+                const u32 base = (it * total_warps + gwarp) * 64;
+                const u32 b0 = base + lane, b1 = base + 32 + lane;
+                Best m0 = BEST_NONE, m1 = BEST_NONE;
+                if (b0 < cM.n_blocks) m0 = load_best(&cM.bmax[b0]);
+                if (b1 < cM.n_blocks) m1 = load_best(&cM.bmax[b1]);
+                if (m0.cnt != CNT_DEAD && best_greater(m0, mine)) mine = m0;
+                if (m1.cnt != CNT_DEAD && best_greater(m1, mine)) mine = m1;
+            }
         }
         mine = warp_best(mine);
         if (lane == 0) s_best[warp] = mine;
         __syncthreads();
+        Best cta_cand = BEST_NONE;
         if (warp == 0) {
             Best c = lane < warps_per_cta ? s_best[lane] : BEST_NONE;
-            c = warp_best(c);
-            if (lane == 0) store_best(&cM.cta_best[blockIdx.x * CTA_BEST_STRIDE], c);
+            cta_cand = warp_best(c);
         }
         u64 t1 = prof_thread ? gtime_ns() : 0;
-        grid.sync();
+        // ---- barrier + all-gather of the CTA candidates: every CTA derives the same winner ----
+        Best gw = (MG_OPT & 1u) ? grid_gather(cM.bar, G, ++gepoch, cta_cand, ctp ? ctp + 1 : nullptr)
+                              : grid_gather_flag(cM.bar, G, ++gepoch, cta_cand, (MG_OPT & 8u) != 0, ctp ? ctp + 1 : nullptr);
         u64 t2 = prof_thread ? gtime_ns() : 0;
-        // ---- phase 2: every CTA derives the same winner ----------------------------------------
-        if (warp == 0) {
-            Best c = BEST_NONE;
-            Best o5[5];                          // G <= 160: every lane issues its (up to) 5 loads before using any
-#pragma unroll
-            for (u32 k = 0; k < 5; k++) { u32 i = lane + 32 * k; o5[k] = i < G ? load_best(&cM.cta_best[i * CTA_BEST_STRIDE]) : BEST_NONE; }
-            u64 tl0 = 0, tl1 = 0, tl2 = 0;
-            if (prof_thread) { u64 d = 0; for (u32 k = 0; k < 5; k++) d ^= (u64)o5[k].cnt ^ o5[k].key ^ o5[k].ka ^ o5[k].kb; tl0 = gtime_after(d); }
-#pragma unroll
-            for (u32 k = 0; k < 5; k++) if (o5[k].cnt != CNT_DEAD && best_greater(o5[k], c)) c = o5[k];
-            if (prof_thread && blockIdx.x == 0) cM.prof[25] += gtime_after((u64)c.cnt ^ c.key ^ c.ka ^ c.kb) - tl0;
-            c = warp_best(c);
-            if (prof_thread) tl1 = gtime_after((u64)c.cnt ^ c.key ^ c.ka ^ c.kb);
-            if (lane == 0) {
-                s_win = c;
-                if (c.cnt != CNT_DEAD) winner_range(c.key, s_range);   // index range of the winner, read once per CTA
-            }
-            if (prof_thread && blockIdx.x == 0) { tl2 = gtime_after(s_range[0] ^ s_range[1]); cM.prof[13] += tl0 - t2; cM.prof[14] += tl1 - tl0; cM.prof[15] += tl2 - tl1; }
+        if (warp == 0 && lane == 0) {
+            s_win = gw;
+            if (gw.cnt != CNT_DEAD) winner_range(gw.key, s_range);     // index range of the winner, read once per CTA
         }
         __syncthreads();
         const Best win = s_win;
@@ -592,13 +820,15 @@ __global__ void __launch_bounds__(MG_NT) k_merge_loop() {
         prev_key = win.key;
         n_tok++;
         u64 t3 = prof_thread ? gtime_ns() : 0;
-        grid.sync();
+        u64 tp2[2];
+        grid_barrier(cM.bar_flags, G, ++epoch, ctp ? tp2 : nullptr);
+        if (ctp && tid == 0) ctp[3] = tp2[0];
         if ((r_hi - r_lo) * 2 >= SORT_MIN) {     // heuristic: about two records per index entry visited
             const u64 lb = *((volatile u64 *)&cM.log_begin[step]), cur = *((volatile u64 *)&cM.ctr[0]);
             const u64 pool = *((volatile u64 *)&cM.ctr[9]);
             if (cur - lb >= SORT_MIN && cur <= cM.log_cap && pool + SORT_MAX_BK + 1 <= cM.bk_off_cap) {
                 sort_slice(step, lb, (u32)(cur - lb), n_sorts & 1u, blockIdx.x == 0, (u64)blockIdx.x * MG_NT + tid, (u64)G * MG_NT, s_scan,
-                           [&]() { grid.sync(); });
+                           [&]() { grid_barrier(cM.bar_flags, G, ++epoch); });
                 n_sorts++;
             }
         }
@@ -862,7 +1092,7 @@ __global__ void __launch_bounds__(256) k_pairs_rehash(const u64 *__restrict__ ok
         i64 c = ocnt[i];
         if (c == CNT_DEAD) continue;
         if (c < CNT_DEAD_LIMIT) c = (i64)((u64)c - (u64)CNT_DEAD);     // popped, then touched again
-        u64 mask = cM.pcap - 1, s = mix64(k) & mask;
+        u64 mask = cM.pcap - 1, s = pair_hash(k) & mask;
         for (;;) {
             if (cM.pkey[s] == PAIR_EMPTY && atomicCAS(&cM.pkey[s], PAIR_EMPTY, k) == PAIR_EMPTY) { cM.pcnt[s] = c; break; }
             s = (s + 1) & mask;

@@ -358,10 +358,10 @@ BPE_API void bpe_debug_merge_profile(unsigned long long out[32]) { for (int i = 
 struct TrainBufs {
     DevBuf sym, wmeta, wctr;
     DevBuf dense, hist, csr_off, csr_rec;
-    DevBuf pkey, pcnt, bmax, dirty, sdirty, tok_key, prof, step_prof, merge_cnt, log, log2, bk_lg, bk_start, bk_off, bk_scratch, log_begin, tok_off, tok_len, tok_bytes, cta_best, merges, ctr;
+    DevBuf pkey, pcnt, bmax, dirty, sdirty, tok_key, prof, step_prof, merge_cnt, log, log2, bk_lg, bk_start, bk_off, bk_scratch, log_begin, tok_off, tok_len, tok_bytes, cta_best, bar, cta_prof, merges, ctr;
     void free_all(bpe_ctx *ctx) {
         for (DevBuf *b : {&sym, &wmeta, &wctr, &dense, &hist, &csr_off, &csr_rec, &pkey, &pcnt, &bmax,
-                          &dirty, &sdirty, &tok_key, &prof, &step_prof, &merge_cnt, &log, &log2, &bk_lg, &bk_start, &bk_off, &bk_scratch, &log_begin, &tok_off, &tok_len, &tok_bytes, &cta_best, &merges, &ctr})
+                          &dirty, &sdirty, &tok_key, &prof, &step_prof, &merge_cnt, &log, &log2, &bk_lg, &bk_start, &bk_off, &bk_scratch, &log_begin, &tok_off, &tok_len, &tok_bytes, &cta_best, &bar, &cta_prof, &merges, &ctr})
             bpe_buf_free(ctx, *b);
     }
 };
@@ -817,6 +817,9 @@ static int run_merges(bpe_ctx *ctx, const uint8_t *sp_blob, const u32 *sp_offs, 
     M.tok_bytes_cap = tok_bytes_cap; M.merge_cnt_out = (i64 *)B.merge_cnt.p;
     M.merges_out = (int32_t *)B.merges.p; M.n_merges = n_merges; M.ctr = (u64 *)B.ctr.p; M.prof = (u64 *)B.prof.p;
     M.step_prof = nullptr;
+    M.opt = 0;
+    if (const char *e = getenv("BPE_MERGE_OPT")) M.opt = (u32)atoi(e);
+    if (getenv("BPE_CTA_PROFILE")) { BPE_TRY(alloc_exact(ctx, B.cta_prof, (u64)n_merges * 160 * 32)); CUDA_TRY(ctx, cudaMemsetAsync(B.cta_prof.p, 0, (u64)n_merges * 160 * 32, st)); M.cta_prof = (u64 *)B.cta_prof.p; }
     if (getenv("BPE_STEP_PROFILE")) { BPE_TRY(alloc_exact(ctx, B.step_prof, ((u64)n_merges + 1) * 16)); CUDA_TRY(ctx, cudaMemsetAsync(B.step_prof.p, 0, ((u64)n_merges + 1) * 16, st)); M.step_prof = (u32 *)B.step_prof.p; }
 
     // initial pair table from the dense 256x256 counts (same device-side insert as the merge loop uses)
@@ -827,11 +830,15 @@ static int run_merges(bpe_ctx *ctx, const uint8_t *sp_blob, const u32 *sp_offs, 
 
     {
         int per_sm = 0;
-        CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_merge_loop, MG_NT, 0));
+        CUDA_TRY(ctx, cudaFuncSetAttribute((void *)k_merge_loop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MG_DYN_SMEM));
+        CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_merge_loop, MG_NT, MG_DYN_SMEM));
         if (per_sm < 1) return bpe_set_error(ctx, BPE_ERR_CUDA, "merge kernel does not fit on an SM");
     }
     BPE_TRY(alloc_exact(ctx, B.cta_best, (u64)ctx->sm_count * CTA_BEST_STRIDE * sizeof(Best)));
     M.cta_best = (Best *)B.cta_best.p;
+    const u64 bar_bytes = (u64)MG_MAX_CTAS * sizeof(BarSlot) + (u64)MG_MAX_CTAS * 4;
+    BPE_TRY(alloc_exact(ctx, B.bar, bar_bytes));
+    M.bar = (BarSlot *)B.bar.p; M.bar_flags = (u32 *)(M.bar + MG_MAX_CTAS);
     u64 ctr[8] = {0};
     u64 keys_created = 0;
     // Two kernels run the same loop: k_merge_loop (grid-wide, cooperative) and k_merge_tail (one thread-block cluster:
@@ -879,11 +886,12 @@ static int run_merges(bpe_ctx *ctx, const uint8_t *sp_blob, const u32 *sp_offs, 
             g_bpe_launches++;
             CUDA_TRY(ctx, cudaLaunchKernelExC(&cfg, (void *)k_merge_tail, nullptr));
         } else {
+            CUDA_TRY(ctx, cudaMemsetAsync(B.bar.p, 0, bar_bytes, st));   // epochs restart at 0
             // grid: one CTA per SM for big tables, fewer for small ones (cheaper grid syncs)
             int G = std::max(2, (int)std::min<u64>((u64)std::min(ctx->sm_count, 160), (u64)M.n_blocks / 256 + 1 + (n_words + 4095) / 4096));
             if (const char *e = getenv("BPE_MERGE_G")) G = std::max(2, std::min(atoi(e), std::min(ctx->sm_count, 160)));
             g_bpe_launches++;
-            CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_merge_loop, dim3(G), dim3(MG_NT), nullptr, 0, st));
+            CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_merge_loop, dim3(G), dim3(MG_NT), nullptr, MG_DYN_SMEM, st));
         }
         CUDA_TRY(ctx, cudaMemcpyAsync(host, B.ctr.p, 64, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(ctx, cudaStreamSynchronize(st));
@@ -917,6 +925,12 @@ static int run_merges(bpe_ctx *ctx, const uint8_t *sp_blob, const u32 *sp_offs, 
     ctr[2] = keys_created;
     int ev_merge1 = tm.mark();
     CUDA_TRY(ctx, cudaMemcpyAsync(g_merge_prof, B.prof.p, 256, cudaMemcpyDeviceToHost, st));
+    if (M.cta_prof) {
+        std::vector<u64> cp((size_t)n_merges * 160 * 4);
+        CUDA_TRY(ctx, cudaMemcpyAsync(cp.data(), B.cta_prof.p, cp.size() * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        if (FILE *f = fopen(getenv("BPE_CTA_PROFILE"), "wb")) { fwrite(cp.data(), 8, cp.size(), f); fclose(f); }
+    }
     if (M.step_prof) {
         std::vector<u32> sp((size_t)n_merges * 4);
         CUDA_TRY(ctx, cudaMemcpyAsync(sp.data(), B.step_prof.p, sp.size() * 4, cudaMemcpyDeviceToHost, st));
