@@ -6,6 +6,7 @@ CPU fallback.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import threading
 
 import numpy as np
@@ -61,7 +62,7 @@ def lib():
     global _lib
     with _lock:
         if _lib is None:
-            path = _build.build()
+            path = os.environ.get("BPE_LIB_PATH") or _build.build()   # (BPE_LIB_PATH: A/B runs of two builds in one process tree)
             L = C.CDLL(str(path))
             vp, u64p = C.c_void_p, C.POINTER(C.c_uint64)
             L.bpe_version.restype = C.c_int

@@ -115,30 +115,51 @@ __global__ void __launch_bounds__(256) k_count_pretokens(CountTables t, const u3
     for (u32 i = threadIdx.x; i < CNT_SMEM_SLOTS; i += blockDim.x) { s_key[i] = 0; s_cnt[i] = 0; }
     __syncthreads();
     u64 n_tok = 0;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += (u64)gridDim.x * blockDim.x) {
-        const u64 pos = base + offs[i], end = base + offs[i + 1];
-        if (pos < own_begin || pos >= own_end) continue;
-        const u64 len = end - pos;
-        if (end > trust_end) t.counters[6] = 1;
-        n_tok++;
-        const uint8_t *p = t.text + pos;
-        if (len <= SHORT_MAX) {
-            const u64 key = short_key(p, (u32)len);
-            u32 slot = (((u32)key ^ (u32)(key >> 32)) * 0x9E3779B1u) >> (32 - 11);   // cheap hash for the shared-memory table
-            static_assert(CNT_SMEM_SLOTS == 1u << 11, "slot hash assumes 2048 slots");
-            bool done = false;
-            for (u32 pr = 0; pr < CNT_SMEM_PROBES && !done; pr++) {
-                u64 k = s_key[slot];
-                if (k == 0) { u64 old = atomicCAS(&s_key[slot], 0ull, key); k = old ? old : key; }
-                if (k == key) { atomicAdd(&s_cnt[slot], 1u); done = true; }
-                slot = (slot + 1) & (CNT_SMEM_SLOTS - 1);
+    // Software pipeline over the grid-stride loop: while item i is hashed and counted, the first 16 bytes of item
+    // i + stride and the offsets of item i + 2 stride are in flight (the chain offsets -> text -> table was the latency
+    // that bounded this kernel: one item per thread at a time).
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    bool h0 = i < n_items, h1 = i + stride < n_items;
+    u32 a0 = 0, b0 = 0, a1 = 0, b1 = 0;
+    if (h0) { a0 = offs[i]; b0 = offs[i + 1]; }
+    if (h1) { a1 = offs[i + stride]; b1 = offs[i + stride + 1]; }
+    u64 lo0 = 0, hi0 = 0;
+    if (h0) { const u64 *q = reinterpret_cast<const u64 *>(reinterpret_cast<uintptr_t>(t.text + base + a0) & ~(uintptr_t)7); lo0 = q[0]; hi0 = q[1]; }
+    for (; h0; i += stride) {
+        const bool h2 = i + 2 * stride < n_items;
+        u32 a2 = 0, b2 = 0;
+        if (h2) { a2 = offs[i + 2 * stride]; b2 = offs[i + 2 * stride + 1]; }
+        u64 lo1 = 0, hi1 = 0;
+        if (h1) { const u64 *q = reinterpret_cast<const u64 *>(reinterpret_cast<uintptr_t>(t.text + base + a1) & ~(uintptr_t)7); lo1 = q[0]; hi1 = q[1]; }
+        const u64 pos = base + a0, end = base + b0;
+        if (pos >= own_begin && pos < own_end) {
+            const u64 len = end - pos;
+            if (end > trust_end) t.counters[6] = 1;
+            n_tok++;
+            const uint8_t *p = t.text + pos;
+            if (len <= SHORT_MAX) {
+                const u32 sh = (u32)(reinterpret_cast<uintptr_t>(p) & 7u) * 8u;
+                const u64 first8 = sh ? (lo0 >> sh) | (hi0 << (64u - sh)) : lo0;
+                const u64 key = (first8 & low_bytes_mask((u32)len)) | ((u64)len << 56);   // = short_key(p, len)
+                u32 slot = (((u32)key ^ (u32)(key >> 32)) * 0x9E3779B1u) >> (32 - 11);   // cheap hash for the shared-memory table
+                static_assert(CNT_SMEM_SLOTS == 1u << 11, "slot hash assumes 2048 slots");
+                bool done = false;
+                for (u32 pr = 0; pr < CNT_SMEM_PROBES && !done; pr++) {
+                    u64 k = s_key[slot];
+                    if (k == 0) { u64 old = atomicCAS(&s_key[slot], 0ull, key); k = old ? old : key; }
+                    if (k == key) { atomicAdd(&s_cnt[slot], 1u); done = true; }
+                    slot = (slot + 1) & (CNT_SMEM_SLOTS - 1);
+                }
+                if (!done) short_add(t, key, 1);
+            } else if (len <= MAX_TOKEN_LEN) {
+                long_add(t, p, (u32)len, pos, 1);
+            } else {
+                t.counters[5] = 1;
             }
-            if (!done) short_add(t, key, 1);
-        } else if (len <= MAX_TOKEN_LEN) {
-            long_add(t, p, (u32)len, pos, 1);
-        } else {
-            t.counters[5] = 1;
         }
+        a0 = a1; b0 = b1; lo0 = lo1; hi0 = hi1; h0 = h1;
+        a1 = a2; b1 = b2; h1 = h2;
     }
     // one atomic per warp for the occurrence counter
     for (int d = 16; d; d >>= 1) n_tok += __shfl_down_sync(0xffffffffu, n_tok, d);
