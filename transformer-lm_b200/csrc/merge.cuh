@@ -32,9 +32,10 @@ namespace cg = cooperative_groups;
 // Compile-time experiment switches of k_merge_loop (defaults = the fastest measured combination on B200):
 //   1 = LL-style gather (tag in every word) instead of flag-then-data      2 = new keys are claimed by a CAS-first probe
 //   4 = the four symbols around a site are loaded together                  8 = relaxed polls + fence in the flag gather
-//  16 = release / acquire flag barrier instead of fence + relaxed
+//  16 = release / acquire flag barrier instead of fence + relaxed         32 = the four table probes of a site advance in one loop
+//  64 = counter barrier (one red.release per CTA, one polling lane) instead of per-CTA flags polled by a warp
 #ifndef MG_OPT
-#define MG_OPT 22u
+#define MG_OPT 118u
 #endif
 // slot hash of the pair table: 32-bit multiplies only (the apply path computes four of these per site)
 __device__ __forceinline__ u32 pair_hash(u64 key) {
@@ -348,6 +349,46 @@ __device__ __noinline__ void apply_site(u32 p, i64 c, u32 a, u32 b, u32 nw, int 
     const bool log_ok = li + n_rec <= cM.log_cap;
     if (!log_ok) cM.ctr[3] = 2;
     s[p] = inw; s[pb] = dead_now;                                          // merge_subwords: positions never move
+#if MG_OPT & 32u
+    if (log_ok) {
+        if (has_l) { store_rec(&cM.log[li], left, pos_l, c); li++; }        // (left, nw) at the position of `left`
+        if (has_r) store_rec(&cM.log[li], 0x80000000u | right, p, c);       // (nw, right) at p
+    }
+    // The four probe sequences advance together: one loop whose trip count is the longest of the four (in the warp), with
+    // the loads / CASes of an iteration in flight at the same time -- not four loops one after the other.
+    // vj = what the probe of key j at slot sj returned; casj: that probe was a claiming CAS (PAIR_EMPTY = claimed by us).
+    {
+        u64 kk[4] = {k0, k1, k2, k3}, ss[4] = {s0, s1, s2, s3}, vv[4] = {v0, v1, v2, v3};
+        const i64 dd[4] = {-c, c, -c, c};
+        u32 cas = cas_first ? 0xAu : 0u;
+        u32 pend = (has_l ? 3u : 0u) | (has_r ? 12u : 0u);
+        for (u64 probes = 0; pend && probes <= cM.pcap; probes++) {
+#pragma unroll
+            for (u32 j = 0; j < 4; j++) {
+                if (!((pend >> j) & 1u)) continue;
+                u64 k = vv[j];
+                if (k == PAIR_EMPTY) {
+                    if (!((cas >> j) & 1u)) {                              // empty slot seen by a read probe: claim it
+                        vv[j] = atomicCAS(&cM.pkey[ss[j]], PAIR_EMPTY, kk[j]);
+                        cas |= 1u << j;
+                        continue;
+                    }
+                    atomicAdd(&cM.ctr[2], 1ull);                           // our CAS claimed the slot
+                    k = kk[j];
+                }
+                if (k == kk[j]) {
+                    atomicAdd((u64 *)&cM.pcnt[ss[j]], (u64)dd[j]);
+                    mark_dirty(ss[j]);
+                    pend &= ~(1u << j);
+                    continue;
+                }
+                ss[j] = (ss[j] + 1) & mask;
+                vv[j] = ((cas >> j) & 1u) ? atomicCAS(&cM.pkey[ss[j]], PAIR_EMPTY, kk[j]) : cM.pkey[ss[j]];
+            }
+        }
+        if (pend) cM.ctr[3] = 1;                                           // table full
+    }
+#else
     if (has_l) {
         pair_add_probe<false>(k0, -c, s0, v0);
         if (cas_first) pair_add_probe<true>(k1, c, s1, v1); else pair_add_probe<false>(k1, c, s1, v1);
@@ -359,6 +400,7 @@ __device__ __noinline__ void apply_site(u32 p, i64 c, u32 a, u32 b, u32 nw, int 
         if (cas_first) pair_add_probe<true>(k3, c, s3, v3); else pair_add_probe<false>(k3, c, s3, v3);
         if (log_ok) store_rec(&cM.log[li], 0x80000000u | right, p, c);      // (nw, right) at p
     }
+#endif
     PROF_ADD(6, 1);
 #undef ORIG
 #undef WAS_LIVE
@@ -539,13 +581,24 @@ __device__ __forceinline__ u32 ld_relaxed_u32(const u32 *p) { u32 v; asm volatil
 __device__ __forceinline__ void st_release_u32(u32 *p, u32 v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ u32 ld_acquire_u32(const u32 *p) { u32 v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 #define MG_MAX_CTAS 160u
+__device__ __forceinline__ void red_release_add_u32(u32 *p, u32 v) { asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+// counter barrier (MG_OPT & 64): every CTA adds 1 with release semantics, lane 0 polls the one word with acquire loads
+__device__ __forceinline__ void counter_arrive_wait(u32 *counter, u32 target) {
+    if (threadIdx.x == 0) {
+        red_release_add_u32(counter, 1u);
+        while ((int)(ld_acquire_u32(counter) - target) < 0) { }
+    }
+    __syncwarp();
+}
 // Called by all threads of the CTA.
 __device__ __forceinline__ void grid_barrier(u32 *flags, u32 G, u32 epoch, u64 *tp = nullptr) {
     __syncthreads();
 #ifdef BPE_MERGE_PROFILE
     if (tp && threadIdx.x == 0) tp[0] = gtime_ns();
 #endif
-    if (threadIdx.x < 32) {
+    if (MG_OPT & 64u) {
+        if (threadIdx.x < 32) counter_arrive_wait(flags + MG_MAX_CTAS, epoch * G);
+    } else if (threadIdx.x < 32) {
         const u32 lane = threadIdx.x;
         const bool acq = (MG_OPT & 16u) != 0;
         if (lane == 0) { if (acq) st_release_u32(&flags[blockIdx.x], epoch); else { __threadfence(); st_relaxed_u32(&flags[blockIdx.x], epoch); } }
@@ -615,7 +668,7 @@ __device__ __forceinline__ Best grid_gather(BarSlot *slots, u32 G, u32 epoch, co
 }
 
 // Flag-then-data variant: slot = {candidate (w[0..3]), epoch (w[4])}.
-__device__ __forceinline__ Best grid_gather_flag(BarSlot *slots, u32 G, u32 epoch, const Best &mine, bool relaxed, u64 *tp = nullptr) {
+__device__ __forceinline__ Best grid_gather_flag(BarSlot *slots, u32 *gcounter, u32 G, u32 epoch, const Best &mine, bool relaxed, u64 *tp = nullptr) {
     __syncthreads();
 #ifdef BPE_MERGE_PROFILE
     if (tp && threadIdx.x == 0) tp[0] = gtime_ns();
@@ -625,10 +678,11 @@ __device__ __forceinline__ Best grid_gather_flag(BarSlot *slots, u32 G, u32 epoc
         const u32 lane = threadIdx.x;
         if (lane == 0) {
             store_best(reinterpret_cast<Best *>(slots[blockIdx.x].w), mine);
-            st_release_u32(reinterpret_cast<u32 *>(&slots[blockIdx.x].w[4]), epoch);
+            if (!(MG_OPT & 64u)) st_release_u32(reinterpret_cast<u32 *>(&slots[blockIdx.x].w[4]), epoch);
         }
+        if (MG_OPT & 64u) counter_arrive_wait(gcounter, epoch * G);
         bool done;
-        do {
+        if (!(MG_OPT & 64u)) do {
             done = true;
 #pragma unroll
             for (u32 k = 0; k < MG_MAX_CTAS / 32; k++) {
@@ -802,7 +856,7 @@ __global__ void __launch_bounds__(MG_NT) k_merge_loop() {
         u64 t1 = prof_thread ? gtime_ns() : 0;
         // ---- barrier + all-gather of the CTA candidates: every CTA derives the same winner ----
         Best gw = (MG_OPT & 1u) ? grid_gather(cM.bar, G, ++gepoch, cta_cand, ctp ? ctp + 1 : nullptr)
-                              : grid_gather_flag(cM.bar, G, ++gepoch, cta_cand, (MG_OPT & 8u) != 0, ctp ? ctp + 1 : nullptr);
+                              : grid_gather_flag(cM.bar, cM.bar_flags + MG_MAX_CTAS + 32, G, ++gepoch, cta_cand, (MG_OPT & 8u) != 0, ctp ? ctp + 1 : nullptr);
         u64 t2 = prof_thread ? gtime_ns() : 0;
         if (warp == 0 && lane == 0) {
             s_win = gw;
