@@ -908,11 +908,10 @@ static int run_merges(bpe_ctx *ctx, const uint8_t *sp_blob, const u32 *sp_offs, 
             CUDA_TRY(ctx, cudaLaunchKernelExC(&cfg, (void *)k_merge_tail, nullptr));
         } else {
             CUDA_TRY(ctx, cudaMemsetAsync(B.bar.p, 0, bar_bytes, st));   // epochs restart at 0
-            // grid: at most 64 CTAs (fewer for small tables).  A step is two grid-wide barriers plus a few dependent round
-            // trips; with the block maxima cached in shared memory the work per step no longer needs every SM, and polling
-            // 64 barrier slots instead of 148 is worth more than the extra apply threads (measured at 11 GB, same box:
-            // G = 148: 536 ms, 96: 575*, 72: 528, 64: 518, 56: 575*, 32: 635* -- * on a slower box where 148 gave 608).
-            int G = std::max(2, (int)std::min<u64>((u64)std::min(ctx->sm_count, 64), (u64)M.n_blocks / 256 + 1 + (n_words + 4095) / 4096));
+            // grid: one CTA per SM for big tables, fewer for small ones (cheaper barriers).  Measured at 11 GB with the counter
+            // barrier, same box: G = 148: 449 ms, 112: 464, 96: 463, 80: 481, 64: 485, 48: 535.  (With the per-CTA flag barrier
+            // that this replaced, 64 CTAs were the optimum: polling 148 slots cost more than the extra apply threads gave.)
+            int G = std::max(2, (int)std::min<u64>((u64)std::min(ctx->sm_count, (int)MG_MAX_CTAS), (u64)M.n_blocks / 256 + 1 + (n_words + 4095) / 4096));
             if (const char *e = getenv("BPE_MERGE_G")) G = std::max(2, std::min(atoi(e), std::min(ctx->sm_count, (int)MG_MAX_CTAS)));
             g_bpe_launches++;
             CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_merge_loop, dim3(G), dim3(MG_NT), nullptr, MG_DYN_SMEM, st));
