@@ -35,7 +35,7 @@ namespace cg = cooperative_groups;
 //  16 = release / acquire flag barrier instead of fence + relaxed         32 = the four table probes of a site advance in one loop
 //  64 = counter barrier (one red.release per CTA, one polling lane) instead of per-CTA flags polled by a warp
 #ifndef MG_OPT
-#define MG_OPT 118u
+#define MG_OPT 246u
 #endif
 // slot hash of the pair table: 32-bit multiplies only (the apply path computes four of these per site)
 __device__ __forceinline__ u32 pair_hash(u64 key) {
@@ -122,7 +122,7 @@ struct MergeState {
     // profile (ns / counts): [0]=phase1 [1]=sync1 [2]=apply [3]=sync2 on CTA 0; [4]=token CTA work; [5]=index records scanned;
     // [6]=words rewritten; [7]=steps; [9]=dirty blocks rescanned
     u64 *prof;
-    u32 opt;          // experiment switches (BPE_MERGE_OPT): 1 = LL gather, 2 = CAS-first new keys, 8 = relaxed polls in the flag gather
+    u32 opt;          // smallest number of records dealt to a warp per pass of the apply phase (BPE_MERGE_MINREC)
     u64 *cta_prof;    // optional (profile builds): per step and CTA {start, arrive1, exit1, arrive2}
     u32 *step_prof;   // optional per-step trace: 4 x u32 per step (phase1+sync1 ns, apply+sync2 ns, records scanned, words rewritten so far)
 };
@@ -870,7 +870,15 @@ __global__ void __launch_bounds__(MG_NT) k_merge_loop() {
         const u64 r_lo = s_range[0], r_hi = s_range[1];
 
         if (token_cta) token_bookkeeping(step, win, a, b, nw, prof_thread, t2);
-        else apply_winner(step, a, b, nw, r_lo, r_hi, T_SRC(s_range[2]), (u64)blockIdx.x * MG_NT + tid, (u64)apply_ctas * MG_NT);
+        // Records are dealt to the warps of all apply CTAs R at a time, R as small as one pass over the slice allows (but not
+        // below cM.opt): a step with a few hundred occurrences runs a few lanes on every SM instead of sixteen full warps on
+        // one SM, with less divergence between the sites that share a warp.
+        else if (MG_OPT & 128u) {
+            const u64 n_rec = r_hi - r_lo, aw = (u64)apply_ctas * warps_per_cta;
+            u32 R = 32;
+            while (R > cM.opt && n_rec <= aw * (R >> 1)) R >>= 1;
+            if (lane < R) apply_winner(step, a, b, nw, r_lo, r_hi, T_SRC(s_range[2]), ((u64)warp * apply_ctas + blockIdx.x) * R + lane, aw * R);
+        } else apply_winner(step, a, b, nw, r_lo, r_hi, T_SRC(s_range[2]), (u64)blockIdx.x * MG_NT + tid, (u64)apply_ctas * MG_NT);
         prev_key = win.key;
         n_tok++;
         u64 t3 = prof_thread ? gtime_ns() : 0;
