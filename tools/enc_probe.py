@@ -31,6 +31,7 @@ out = torch.empty(enc_bytes, dtype=torch.uint16, device="cuda")
 for it in range(3):
     n_out = C.c_uint64(0)
     stats = _lib.EncodeStats()
+    L.bpe_tok_cache_reset(h)                     # like bench.py: no step reuses cached BPE results
     t0 = time.time()
     rc = L.bpe_encode_dev(h, C.c_void_p(x.data_ptr()), enc_bytes, 0, C.c_void_p(out.data_ptr()), enc_bytes, C.byref(n_out), C.byref(stats))
     ctx.check(rc)
