@@ -115,6 +115,43 @@ def test_encode_iterable_is_lazy_and_chunked(gpt2):
     assert got != gpt2.encode("".join(lines))  # "...\n" | "\n\nFoo" splits differently from the concatenation
 
 
+def test_encode_iterable_look_ahead_keeps_order_and_errors(gpt2):
+    # chunk k + 1 is encoded on a worker thread while the caller consumes chunk k.  Same ids, same chunk
+    # cuts as the sequential loop over several chunks; the iterable is read at most one chunk ahead of the ids consumed.
+    rng = random.Random(5)
+    words = ["alpha", " beta", "\n", " 12", "gamma!", " δ", "  ", "\n\n", EOT]
+    lines = ["".join(rng.choice(words) for _ in range(rng.randint(50, 400))) + "\n" for _ in range(9000)]
+    assert sum(map(len, lines)) > 3 * 2 * 1024 * 1024                       # at least four chunks
+    otok = oracle.OracleTokenizer(*load_gpt2_fixture(), [EOT])
+    want = list(otok.encode_iterable(iter(lines)))
+    pulled = [0]
+
+    def counting():
+        for line in lines:
+            pulled[0] += 1
+            yield line
+    gen = gpt2.encode_iterable(counting())
+    got = [next(gen)]
+    first_chunk_items = pulled[0]
+    assert first_chunk_items < len(lines) // 2                               # nothing read ahead before the first id
+    got.append(next(gen))
+    assert first_chunk_items < pulled[0] <= 2 * first_chunk_items + 1        # exactly one chunk ahead afterwards
+    mid = gpt2.encode("interleaved call on the same context")               # the caller may use the tokenizer meanwhile
+    assert mid == otok.encode("interleaved call on the same context")
+    got.extend(gen)
+    assert got == want
+    # an error of a later chunk surfaces after every id of the earlier chunks, like in the sequential loop
+    vocab = {i: bytes([i]) for i in range(256)}
+    tok = get_tokenizer(vocab, [(b"a", b"b")], [])                           # b"ab" is not in the vocab
+    good = ["x" * 1023 + "\n"] * 2048
+    seen = []
+    with pytest.raises(KeyError) as ei:
+        for t in tok.encode_iterable(iter(good + ["ab\n"])):
+            seen.append(t)
+    assert ei.value.args == (b"ab",)
+    assert len(seen) == 2048 * 1024
+
+
 # ---- golden vectors produced by the unmodified reference -------------------------------------------------
 @pytest.mark.parametrize("name", sorted(load_golden("encode_golden.json").keys()))
 def test_encode_golden(name):

@@ -157,6 +157,9 @@ class Context:
         if rc != BPE_OK:
             raise BpeError(rc, "bpe_ctx_create failed")
         self.device = device
+        # the C ABI allows one in-flight call per context (include/bpe_sm100.h): host code that may call from two
+        # threads (Tokenizer.encode_iterable's look-ahead worker) serialises on this lock
+        self.lock = threading.RLock()
 
     @property
     def handle(self):

@@ -96,11 +96,15 @@ class Tokenizer:
         return pairs, result, sym_bytes, sym_to_id
 
     def _device_tok(self):
+        ctx = self._ctx or _lib.default_context()
+        with ctx.lock:
+            return self._device_tok_locked(ctx)
+
+    def _device_tok_locked(self, ctx):
         sig = self._signature()
         if self._tok is not None and sig == self._sig:
             return self._tok
         self.close()
-        ctx = self._ctx or _lib.default_context()
         L = _lib.lib()
         pairs, result, sym_bytes, sym_to_id = self._tables()
         if sym_to_id.size and (sym_to_id.max() >= 2**31 or sym_to_id.min() < -1):
@@ -157,9 +161,10 @@ class Tokenizer:
         out = np.empty(max(arr.size, 1), dtype=dtype)             # a token covers at least one byte
         n_out = C.c_uint64(0)
         stats = _lib.EncodeStats()
-        rc = L.bpe_encode(tok, _lib.ptr(arr) if arr.size else None, arr.size, code, _lib.ptr(out), out.size, C.byref(n_out), C.byref(stats))
-        if rc != _lib.BPE_OK:
-            self._raise(ctx, rc, arr)
+        with ctx.lock:
+            rc = L.bpe_encode(tok, _lib.ptr(arr) if arr.size else None, arr.size, code, _lib.ptr(out), out.size, C.byref(n_out), C.byref(stats))
+            if rc != _lib.BPE_OK:
+                self._raise(ctx, rc, arr)
         self.last_stats = stats.as_dict()
         return out[: n_out.value]
 
@@ -169,16 +174,49 @@ class Tokenizer:
     def encode_iterable(self, iterable: Iterable[str]) -> Iterator[int]:
         # Chunk rule of tokenizer.py:140-153: concatenate items until the buffer holds >= 2 Mi CHARACTERS,
         # encode the buffer on its own, repeat until the iterable yields nothing (SURVEY A-13/A-14).
-        while True:
+        #
+        # Double-buffered: once the first id of chunk k has been handed out, chunk k + 1 is read from
+        # the iterable (in the caller's thread: the iterable is never touched from another one) and its encode runs on a
+        # worker thread -- ctypes releases the GIL for the C call -- while the caller consumes the ids of chunk k.  The
+        # ids, their order and the chunk boundaries are those of the sequential loop; the only observable difference is
+        # that the iterable is read one chunk ahead of the ids being consumed (never before the first id is out).
+        def read_chunk():
             parts, chars = [], 0
             for line in iterable:
                 parts.append(line)
                 chars += len(line)
                 if chars >= _CHUNK_CHARS:
                     break
-            if chars == 0:
-                break
-            yield from self.encode("".join(parts))
+            return "".join(parts) if chars else None
+
+        def encode_list(text):
+            return self.encode_to_numpy(text.encode("utf-8"), np.int32).tolist()
+
+        text = read_chunk()
+        if text is None:
+            return
+        ids = encode_list(text)
+        pool = None
+        try:
+            while True:
+                it = iter(ids)
+                for first in it:
+                    yield first
+                    break
+                nxt = read_chunk()
+                fut = None
+                if nxt is not None:
+                    if pool is None:
+                        from concurrent.futures import ThreadPoolExecutor
+                        pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="bpe-encode-ahead")
+                    fut = pool.submit(encode_list, nxt)
+                yield from it
+                if fut is None:
+                    break
+                ids = fut.result()                # re-raises KeyError / UnicodeDecodeError of that chunk here, in order
+        finally:
+            if pool is not None:
+                pool.shutdown(wait=True)
 
     # ---- decode (tokenizer.py:155-157) -------------------------------------------------------------
     def decode_bytes(self, ids) -> bytes:
@@ -192,13 +230,14 @@ class Tokenizer:
         if arr.size == 0:
             return b""
         n_out = C.c_uint64(0)
-        rc = L.bpe_decode(tok, _lib.ptr(arr), arr.size, None, 0, C.byref(n_out))
-        if rc == _lib.ERR_KEY:
-            raise KeyError(int(arr[L.bpe_last_error_detail(ctx.handle)]))
-        ctx.check(rc)
-        out = np.empty(max(n_out.value, 1), dtype=np.uint8)
-        rc = L.bpe_decode(tok, _lib.ptr(arr), arr.size, _lib.ptr(out), out.size, C.byref(n_out))
-        ctx.check(rc)
+        with ctx.lock:
+            rc = L.bpe_decode(tok, _lib.ptr(arr), arr.size, None, 0, C.byref(n_out))
+            if rc == _lib.ERR_KEY:
+                raise KeyError(int(arr[L.bpe_last_error_detail(ctx.handle)]))
+            ctx.check(rc)
+            out = np.empty(max(n_out.value, 1), dtype=np.uint8)
+            rc = L.bpe_decode(tok, _lib.ptr(arr), arr.size, _lib.ptr(out), out.size, C.byref(n_out))
+            ctx.check(rc)
         return out[: n_out.value].tobytes()
 
     def decode(self, ids: List[int]) -> str:
