@@ -192,6 +192,23 @@ int bpe_tok_cache_reset(bpe_tok *tok);
  * models/tokenizer/tokenizer.py:155-157 (the host applies .decode("utf-8", errors="replace")).
  * BPE_ERR_KEY (detail = index into ids) when an id is not in the vocab. */
 int bpe_decode(bpe_tok *tok, const int64_t *ids_host, uint64_t n, uint8_t *out, uint64_t cap, uint64_t *n_out);
+/* Batched form for samplers that decode many sequences at once (models/transformer/decode.py:51 calls
+ * tokenizer.decode once per generated sequence): ids_host holds n_seq sequences back to back, sequence j =
+ * ids[seq_offs[j] .. seq_offs[j+1]) (seq_offs[0] = 0, seq_offs[n_seq] = n).  One decode of the concatenation;
+ * byte_offs_host[j] (n_seq + 1 entries) = where sequence j starts in `out`.  Same size-query idiom and errors. */
+int bpe_decode_batch(bpe_tok *tok, const int64_t *ids_host, uint64_t n, const uint64_t *seq_offs_host, uint64_t n_seq,
+                     uint8_t *out, uint64_t cap, uint64_t *n_out, uint64_t *byte_offs_host);
+
+/* ---- training-batch feeder --------------------------------------------------
+ * Replaces the per-row loop of load_batch, models/util.py:37-57: for r < batch and c < context
+ *   x[r][c] = tokens[starts[r] + c],  y[r][c] = tokens[starts[r] + c + 1]      (int64, row-major)
+ * tokens_dev: the encoder's uint16 / int32 id array resident in HBM (BPE_DTYPE_*), n_tokens entries;
+ * starts_host: the `batch` start indices (the reference draws them with torch.randint(len - context) on
+ * the host; the caller keeps doing that, so a given generator yields the same batches);
+ * x_dev, y_dev: device buffers of batch * context int64.  BPE_ERR_ARG (detail = row) when a window leaves
+ * the array. */
+int bpe_batch_windows_dev(bpe_ctx *ctx, const void *tokens_dev, int dtype, uint64_t n_tokens, const int64_t *starts_host,
+                          uint32_t batch, uint32_t context, int64_t *x_dev, int64_t *y_dev);
 
 /* ---- synthetic corpora (bench/test infrastructure) -------------------------------- */
 #define BPE_SYNTH_TINYSTORIES 0

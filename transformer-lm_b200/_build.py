@@ -10,7 +10,7 @@ import subprocess
 HERE = pathlib.Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libbpe_sm100.so"
-SOURCES = ["api.cu", "pretok.cu", "train.cu", "encode.cu", "synth.cu"]
+SOURCES = ["api.cu", "pretok.cu", "train.cu", "encode.cu", "synth.cu", "batch.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden,-O2", "--use_fast_math", "-Xptxas", "-v",

@@ -1033,7 +1033,14 @@ BPE_API int bpe_encode_dev(bpe_tok *tok, const uint8_t *text_dev, uint64_t n, in
     return BPE_OK;
 }
 
-BPE_API int bpe_decode(bpe_tok *tok, const int64_t *ids_host, uint64_t n, uint8_t *out, uint64_t cap, uint64_t *n_out) {
+// byte offset of the first token of every sequence: boff[j] = off[seq[j]] (seq[n_seq] = n gives the total)
+__global__ void __launch_bounds__(256) k_dec_seq_offsets(const u64 *__restrict__ off, const u64 *__restrict__ seq, u64 n_seq1, u64 *__restrict__ boff) {
+    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n_seq1) boff[j] = off[seq[j]];
+}
+
+static int decode_core(bpe_tok *tok, const int64_t *ids_host, uint64_t n, uint8_t *out, uint64_t cap, uint64_t *n_out,
+                       const uint64_t *seq_offs_host, uint64_t n_seq, uint64_t *byte_offs_host) {
     if (!tok || (!ids_host && n) || !n_out) return BPE_ERR_ARG;
     bpe_ctx *ctx = tok->ctx;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -1065,6 +1072,15 @@ BPE_API int bpe_decode(bpe_tok *tok, const int64_t *ids_host, uint64_t n, uint8_
     }
     u64 total = host[1];
     *n_out = total;
+    if (n_seq && byte_offs_host) {               // byte offsets of the sequences (bpe_decode_batch)
+        BPE_TRY(bpe_buf_reserve(ctx, ctx->tmp2, round_up((n_seq + 1) * 16, 256)));
+        u64 *seq = (u64 *)ctx->tmp2.p, *boff = seq + (n_seq + 1);
+        CUDA_TRY(ctx, cudaMemcpyAsync(seq, seq_offs_host, (n_seq + 1) * 8, cudaMemcpyHostToDevice, st));
+        KLAUNCH(k_dec_seq_offsets, (unsigned)((n_seq + 1 + 255) / 256), 256, 0, st, off, seq, n_seq + 1, boff);
+        CUDA_TRY(ctx, cudaGetLastError());
+        CUDA_TRY(ctx, cudaMemcpyAsync(byte_offs_host, boff, (n_seq + 1) * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    }
     if (!out) return BPE_OK;
     u64 m = std::min<u64>(total, cap);
     if (m) {
@@ -1075,4 +1091,23 @@ BPE_API int bpe_decode(bpe_tok *tok, const int64_t *ids_host, uint64_t n, uint8_
         CUDA_TRY(ctx, cudaStreamSynchronize(st));
     }
     return total > cap ? bpe_set_error(ctx, BPE_ERR_TOO_SMALL, "need room for %llu bytes", (unsigned long long)total) : BPE_OK;
+}
+
+BPE_API int bpe_decode(bpe_tok *tok, const int64_t *ids_host, uint64_t n, uint8_t *out, uint64_t cap, uint64_t *n_out) {
+    return decode_core(tok, ids_host, n, out, cap, n_out, nullptr, 0, nullptr);
+}
+
+BPE_API int bpe_decode_batch(bpe_tok *tok, const int64_t *ids_host, uint64_t n, const uint64_t *seq_offs_host, uint64_t n_seq,
+                             uint8_t *out, uint64_t cap, uint64_t *n_out, uint64_t *byte_offs_host) {
+    if (!tok || !n_out || (n_seq && (!seq_offs_host || !byte_offs_host))) return BPE_ERR_ARG;
+    bpe_ctx *ctx = tok->ctx;
+    for (uint64_t j = 0; j < n_seq; j++)
+        if (seq_offs_host[j] > seq_offs_host[j + 1]) return bpe_set_error(ctx, BPE_ERR_ARG, "bpe_decode_batch: sequence offsets must not decrease");
+    if (n_seq && (seq_offs_host[0] != 0 || seq_offs_host[n_seq] != n)) return bpe_set_error(ctx, BPE_ERR_ARG, "bpe_decode_batch: sequence offsets must run from 0 to n");
+    if (n == 0) {
+        *n_out = 0;
+        for (uint64_t j = 0; j <= n_seq && n_seq; j++) byte_offs_host[j] = 0;
+        return BPE_OK;
+    }
+    return decode_core(tok, ids_host, n, out, cap, n_out, seq_offs_host, n_seq, byte_offs_host);
 }

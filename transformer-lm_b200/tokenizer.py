@@ -243,6 +243,33 @@ class Tokenizer:
     def decode(self, ids: List[int]) -> str:
         return self.decode_bytes(ids).decode("utf-8", errors="replace")
 
+    def decode_batch(self, sequences) -> List[str]:
+        """[self.decode(s) for s in sequences] with one device decode of the concatenation (bpe_decode_batch): what a
+        sampler that generates many sequences needs (models/transformer/decode.py:51 decodes one at a time)."""
+        seqs = [np.asarray(s, dtype=np.int64).reshape(-1) for s in sequences]
+        if not seqs:
+            return []
+        tok = self._device_tok()
+        ctx = self._tok_ctx
+        L = _lib.lib()
+        seq_offs = np.zeros(len(seqs) + 1, dtype=np.uint64)
+        np.cumsum([s.size for s in seqs], out=seq_offs[1:])
+        ids = np.ascontiguousarray(np.concatenate(seqs)) if int(seq_offs[-1]) else np.zeros(0, dtype=np.int64)
+        byte_offs = np.zeros(len(seqs) + 1, dtype=np.uint64)
+        n_out = C.c_uint64(0)
+        with ctx.lock:
+            args = (tok, _lib.ptr(ids) if ids.size else None, ids.size, _lib.ptr(seq_offs), len(seqs))
+            rc = L.bpe_decode_batch(*args, None, 0, C.byref(n_out), _lib.ptr(byte_offs))
+            if rc == _lib.ERR_KEY:
+                raise KeyError(int(ids[L.bpe_last_error_detail(ctx.handle)]))
+            ctx.check(rc)
+            out = np.empty(max(n_out.value, 1), dtype=np.uint8)
+            if n_out.value:
+                ctx.check(L.bpe_decode_batch(*args, _lib.ptr(out), out.size, C.byref(n_out), _lib.ptr(byte_offs)))
+        blob = out[: n_out.value].tobytes()
+        bo = byte_offs.astype(np.int64)
+        return [blob[bo[j]: bo[j + 1]].decode("utf-8", errors="replace") for j in range(len(seqs))]
+
     # ---- the reference's public helper methods (tokenizer.py:63-109), kept for callers that use them ----
     def segment(self, text: str) -> List[str]:
         """re.split on the specials with a capturing group: [text, special, text, ...] (tokenizer.py:63-66)."""
