@@ -307,6 +307,8 @@ def run_b200(args):
             t_b = time.perf_counter()
             v, m, st = counter.finish(vocab_size, SPECIALS, return_stats=True)
             st["ms_count_exchange_wall"] = (t_b - t_a) * 1e3
+            if sharded.LAST_TIMES:
+                st["exchange_profile_ms"] = {k: round(v, 2) for k, v in sharded.LAST_TIMES.items()}
             return v, m, st
 
         for _ in range(args.warmup):
@@ -332,6 +334,8 @@ def run_b200(args):
         st = stats[-1]
         stages = {k: round(avg(k), 3) for k in ("ms_h2d", "ms_pretok", "ms_count", "ms_build", "ms_merge", "ms_total", "ms_count_exchange_wall")
                   if any(k in s for s in stats)}
+        if "exchange_profile_ms" in st:
+            stages["exchange_profile_ms"] = st["exchange_profile_ms"]
         value = nbytes / 1e6 / (ms_dev / 1e3)
         # roofline of the dominant kernel, the persistent merge loop.  Algorithmic bytes: the reference's
         # max() reads every live pair-table entry (16 B: packed pair + count) at every step, plus the rewritten symbols.

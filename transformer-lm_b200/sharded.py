@@ -154,13 +154,31 @@ def _all_reduce_scalar(value: int, op: str, device, group=None) -> int:
     return int(t.item())
 
 
+LAST_TIMES: dict = {}                           # BPE_SHARD_PROFILE=1: wall ms of the phases of the last sharded_count (synchronising)
+
+
+def _tick(name, t0):
+    import os
+    import time
+    if os.environ.get("BPE_SHARD_PROFILE") != "1":
+        return t0
+    import torch
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    LAST_TIMES[name] = LAST_TIMES.get(name, 0.0) + (t1 - t0) * 1e3
+    return t1
+
+
 def exchange_tables(counter, group=None):
     """All-gather every rank's (blob, offs, counts) table and import the other ranks' into `counter`.
     Returns the number of bytes this rank received."""
     import torch
     dist = _dist()
     world, rank = dist.get_world_size(group), dist.get_rank(group)
+    import time
+    t0 = time.perf_counter()
     blob, offs, counts = counter.export()
+    t0 = _tick("export", t0)
     dev = counter.device
     meta = torch.tensor([counts.numel(), blob.numel()], dtype=torch.int64, device=dev)
     metas = torch.empty(world * 2, dtype=torch.int64, device=dev)
@@ -176,6 +194,7 @@ def exchange_tables(counter, group=None):
     dist.all_gather_into_tensor(gb, pb, group=group)
     dist.all_gather_into_tensor(go, po, group=group)
     dist.all_gather_into_tensor(gc, pc, group=group)
+    t0 = _tick("all_gather", t0)
     received = 0
     for r in range(world):
         if r == rank:
@@ -186,6 +205,7 @@ def exchange_tables(counter, group=None):
         counter.import_(gb[r * pb.numel(): r * pb.numel() + nb], go[r * po.numel(): r * po.numel() + nw + 1],
                         gc[r * pc.numel(): r * pc.numel() + nw])
         received += nb + 16 * nw
+    _tick("import", t0)
     return received
 
 
@@ -221,6 +241,9 @@ def sharded_count(counter, shards, special_tokens: List[str], group=None, verify
     then takes the unsharded path: universal-newline translation shifts byte offsets)."""
     dist = _dist()
     world, rank = dist.get_world_size(group), dist.get_rank(group)
+    import time
+    LAST_TIMES.clear()
+    t0 = time.perf_counter()
     halo = HALO_RIGHT
     while True:
         sh = shards.load(rank, world, halo)
@@ -242,14 +265,18 @@ def sharded_count(counter, shards, special_tokens: List[str], group=None, verify
         return "newline"
     if status is not None:
         raise _lib.BpeError(_lib.ERR_HALO, "a pretoken runs past the end of the corpus")
+    t0 = _tick("count", t0)
     local_pairs = counter.pair_table(special_tokens) if verify else None
+    t0 = _tick("pair_table_local", t0)
     exchange_tables(counter, group)
+    t0 = time.perf_counter()
     if verify:
         # linearity check: the per-rank byte-pair tables must sum to the table of the merged counts
         dist.all_reduce(local_pairs, op=dist.ReduceOp.SUM, group=group)
         merged = counter.pair_table(special_tokens)
         if not bool((local_pairs == merged).all()):
             raise RuntimeError("pair-count all-reduce does not match the merged word table")
+        _tick("verify", t0)
     return "ok"
 
 
