@@ -34,8 +34,9 @@ namespace cg = cooperative_groups;
 //   4 = the four symbols around a site are loaded together                  8 = relaxed polls + fence in the flag gather
 //  16 = release / acquire flag barrier instead of fence + relaxed         32 = the four table probes of a site advance in one loop
 //  64 = counter barrier (one red.release per CTA, one polling lane) instead of per-CTA flags polled by a warp
+// 128 = (always on) records dealt thinly to warps      256 = warp 1 publishes the range of the CTA's candidate during the gather
 #ifndef MG_OPT
-#define MG_OPT 246u
+#define MG_OPT 502u
 #endif
 // slot hash of the pair table: 32-bit multiplies only (the apply path computes four of these per site)
 __device__ __forceinline__ u32 pair_hash(u64 key) {
@@ -668,8 +669,40 @@ __device__ __forceinline__ Best grid_gather(BarSlot *slots, u32 G, u32 epoch, co
 }
 
 // Flag-then-data variant: slot = {candidate (w[0..3]), epoch (w[4])}.
-__device__ __forceinline__ Best grid_gather_flag(BarSlot *slots, u32 *gcounter, u32 G, u32 epoch, const Best &mine, bool relaxed, u64 *tp = nullptr) {
+// While warp 0 waits in the gather, warp 1 looks up the index range of this CTA's OWN candidate and publishes it in the
+// spare words of its slot, tagged with the epoch (each 64-bit word carries a tag, so a torn or stale read is detected and
+// the reader falls back to winner_range); it also pulls the first records of that range and the symbols they point at
+// into L2.  Whichever candidate wins, the apply phase then starts one to three dependent round trips later in the chain.
+#define RANGE_TAG0(e) ((u64)((e) & 0xFFFFFFu) << 40)
+#define RANGE_TAG1(e) ((u64)((e) & 0x3FFFFFu) << 42)
+__device__ __forceinline__ void gather_side_work(BarSlot *slots, u32 epoch, const Best &cand, int step) {
+    if (cand.cnt == CNT_DEAD) return;
+    const u32 lane = lane_id();
+    const u32 a = (u32)(cand.key >> 32), b = (u32)cand.key, T = a > b ? a : b;
+    if (T >= 256 && (int)(T - 256) + 1 >= step) return;      // log_begin[step] is being written by CTA 0 right now: not visible yet
+    u64 r[3] = {0, 0, 0};
+    if (lane == 0) {
+        winner_range(cand.key, r);
+        if (threadIdx.x == 32 && r[0] < (1ull << 40) && r[1] < (1ull << 40))
+            st_relaxed_v2(&slots[blockIdx.x].w[6], r[0] | RANGE_TAG0(epoch), r[1] | (r[2] << 40) | RANGE_TAG1(epoch));
+    }
+    const u64 lo = __shfl_sync(0xffffffffu, r[0], 0), hi = __shfl_sync(0xffffffffu, r[1], 0);
+    const u32 code = (u32)__shfl_sync(0xffffffffu, r[2], 0);
+    const Rec *src = T_SRC(code);
+    const bool filter = T >= 256;
+    const u32 want = b >= a ? a : (0x80000000u | b);
+    const u64 i = lo + (threadIdx.x - 32);        // warps 1.. take 32 records each
+    if (i < hi) {
+        const Rec rec = load_rec(&src[i]);
+        if (!filter || rec.x == want) asm volatile("prefetch.global.L2 [%0];" ::"l"(&cM.W.sym[rec.pos]));
+    }
+}
+
+// `sup` (lanes of warp 0): index of the CTA whose candidate won.
+__device__ __forceinline__ Best grid_gather_flag(BarSlot *slots, u32 *gcounter, u32 G, u32 epoch, const Best &mine, bool relaxed, u32 &sup,
+                                                 const Best *s_cand, int step, u64 *tp = nullptr) {
     __syncthreads();
+    if ((MG_OPT & 256u) && threadIdx.x >= 32 && threadIdx.x < ((MG_OPT & 512u) ? 160 : 64)) gather_side_work(slots, epoch, *s_cand, step);
 #ifdef BPE_MERGE_PROFILE
     if (tp && threadIdx.x == 0) tp[0] = gtime_ns();
 #endif
@@ -701,6 +734,11 @@ __device__ __forceinline__ Best grid_gather_flag(BarSlot *slots, u32 *gcounter, 
 #pragma unroll
         for (u32 k = 0; k < MG_MAX_CTAS / 32; k++) if (o5[k].cnt != CNT_DEAD && best_greater(o5[k], c)) c = o5[k];
         c = warp_best(c);
+        u32 who = 0xFFFFFFFFu;                   // a key lives in one block, so exactly one CTA supplied the winner
+#pragma unroll
+        for (u32 k = 0; k < MG_MAX_CTAS / 32; k++) if (lane + 32 * k < G && o5[k].cnt != CNT_DEAD && o5[k].key == c.key) who = lane + 32 * k;
+        const u32 m = __ballot_sync(0xffffffffu, who != 0xFFFFFFFFu);
+        sup = m ? __shfl_sync(0xffffffffu, who, __ffs(m) - 1) : 0xFFFFFFFFu;
     }
     __syncthreads();
 #ifdef BPE_MERGE_PROFILE
@@ -731,7 +769,7 @@ __device__ __forceinline__ void cache_consider(const BmaxCache &c, u32 i, Best &
 
 __global__ void __launch_bounds__(MG_NT) k_merge_loop() {
     __shared__ Best s_best[MG_NT / 32];
-    __shared__ Best s_win;
+    __shared__ Best s_win, s_cand;
     __shared__ u64 s_status[2];
     __shared__ u64 s_range[4];
     __shared__ u32 s_scan[SORT_MAX_BK];
@@ -855,12 +893,26 @@ __global__ void __launch_bounds__(MG_NT) k_merge_loop() {
         }
         u64 t1 = prof_thread ? gtime_ns() : 0;
         // ---- barrier + all-gather of the CTA candidates: every CTA derives the same winner ----
-        Best gw = (MG_OPT & 1u) ? grid_gather(cM.bar, G, ++gepoch, cta_cand, ctp ? ctp + 1 : nullptr)
-                              : grid_gather_flag(cM.bar, cM.bar_flags + MG_MAX_CTAS + 32, G, ++gepoch, cta_cand, (MG_OPT & 8u) != 0, ctp ? ctp + 1 : nullptr);
+        u32 sup = 0xFFFFFFFFu;
+        if (warp == 0 && lane == 0) s_cand = cta_cand;
+        ++gepoch;
+        Best gw = (MG_OPT & 1u) ? grid_gather(cM.bar, G, gepoch, cta_cand, ctp ? ctp + 1 : nullptr)
+                              : grid_gather_flag(cM.bar, cM.bar_flags + MG_MAX_CTAS + 32, G, gepoch, cta_cand, (MG_OPT & 8u) != 0, sup, &s_cand, step, ctp ? ctp + 1 : nullptr);
         u64 t2 = prof_thread ? gtime_ns() : 0;
         if (warp == 0 && lane == 0) {
             s_win = gw;
-            if (gw.cnt != CNT_DEAD) winner_range(gw.key, s_range);     // index range of the winner, read once per CTA
+            if (gw.cnt != CNT_DEAD) {            // index range of the winner, read once per CTA: published by its supplier, or looked up
+                bool have = false;
+                if ((MG_OPT & 256u) && sup != 0xFFFFFFFFu) {
+                    u64 w6, w7;
+                    ld_relaxed_v2(&cM.bar[sup].w[6], w6, w7);
+                    if ((w6 & (0xFFFFFFull << 40)) == RANGE_TAG0(gepoch) && (w7 & (0x3FFFFFull << 42)) == RANGE_TAG1(gepoch)) {
+                        s_range[0] = w6 & ((1ull << 40) - 1); s_range[1] = w7 & ((1ull << 40) - 1); s_range[2] = (w7 >> 40) & 3u;
+                        have = true;
+                    }
+                }
+                if (!have) winner_range(gw.key, s_range);
+            }
         }
         __syncthreads();
         const Best win = s_win;
