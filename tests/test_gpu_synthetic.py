@@ -26,6 +26,23 @@ def test_train_on_synthetic_shapes_matches_oracle(shape, seed, mb, vocab):
     assert got[1] == want[1] and got[0] == want[0]
 
 
+@pytest.mark.parametrize("grid", ["2", "3", "17"])
+def test_merge_loop_result_does_not_depend_on_the_grid(monkeypatch, grid):
+    # Small grids put many 64-block chunks on every warp: more than the shared-memory cache of block maxima holds
+    # (MG_CACHE_ITERS) and, in the first step, more dirty blocks than a CTA's list holds (MG_LIST_CAP) -- the overflow
+    # paths of k_merge_loop.  The result must equal the default grid's (which the oracle pins at smaller sizes) and, on
+    # a slice the oracle finishes, the oracle's.
+    data = synth_host("owt", 4321, 64 << 20)
+    want = _train(data, 2500, [EOT])
+    small = synth_host("owt", 4321, 12 << 20).tobytes()
+    want_small = oracle.train_bpe_on_bytes(small, 600, [EOT])
+    monkeypatch.setenv("BPE_MERGE_G", grid)
+    got = _train(data, 2500, [EOT])
+    assert got[1] == want[1] and got[0] == want[0]
+    got_small = _train(small, 600, [EOT])
+    assert got_small[1] == want_small[1] and got_small[0] == want_small[0]
+
+
 @pytest.fixture(scope="module")
 def owt_tokenizer():
     data = synth_host("owt", 4321, 64 << 20)
