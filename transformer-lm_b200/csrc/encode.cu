@@ -127,7 +127,10 @@ __device__ __forceinline__ u64 enc_long_get(const EncTables &t, const uint8_t *p
     u64 s = h & mask;
     u64 mine = (off_meta << META_LEN_BITS) | len;
     for (u64 probes = 0; probes < t.lcap; probes++) {
+        // the whole 32-byte slot in one round trip (a value read early can only be "not computed yet", which yields a forward
+        // reference that is resolved after the BPE kernel: correct either way)
         const ulonglong2 mh = *reinterpret_cast<const ulonglong2 *>(&t.ltab[s]);
+        const ulonglong2 vp = *(reinterpret_cast<const ulonglong2 *>(&t.ltab[s]) + 1);
         u64 m = mh.x, hh = mh.y;
         if (m == META_EMPTY) {
             u64 old = atomicCAS(&t.ltab[s].meta, META_EMPTY, mine);
@@ -142,7 +145,7 @@ __device__ __forceinline__ u64 enc_long_get(const EncTables &t, const uint8_t *p
             hh = *((volatile u64 *)&t.ltab[s].hash);
         }
         if ((m & META_LEN_MASK) == len && (hh == 0 || hh == h) && bytes_equal(enc_rep_ptr(t, m), p, len)) {
-            const u64 v = *((volatile u64 *)&t.ltab[s].val);
+            const u64 v = vp.x;
             return v != VAL_NONE ? v : ((VAL_FWD << 60) | (u32)s | REF_LONG);
         }
         s = (s + 1) & mask;
@@ -153,8 +156,43 @@ __device__ __forceinline__ u64 enc_long_get(const EncTables &t, const uint8_t *p
 
 // One thread per pretoken occurrence i of the batch (bytes [base + offs[i], base + offs[i+1])): vals[i] = its cached
 // value when the cache has it, else a forward reference to its slot (resolved after the BPE kernel).
+#ifndef ENC_LOOKUP_PIPELINE
+#define ENC_LOOKUP_PIPELINE 1
+#endif
 __global__ void __launch_bounds__(256) k_enc_lookup(EncTables t, const u32 *__restrict__ offs, u64 n_items, u64 base,
                                                    u64 *__restrict__ vals) {
+#if ENC_LOOKUP_PIPELINE
+    // software pipeline over the grid-stride loop (as in k_count_pretokens): the first 16 bytes of item i + stride and the
+    // offsets of item i + 2 stride are in flight while item i is looked up
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    bool h0 = i < n_items, h1 = i + stride < n_items;
+    u32 a0 = 0, b0 = 0, a1 = 0, b1 = 0;
+    if (h0) { a0 = offs[i]; b0 = offs[i + 1]; }
+    if (h1) { a1 = offs[i + stride]; b1 = offs[i + stride + 1]; }
+    u64 lo0 = 0, hi0 = 0;
+    if (h0) { const u64 *q = reinterpret_cast<const u64 *>(reinterpret_cast<uintptr_t>(t.text + base + a0) & ~(uintptr_t)7); lo0 = q[0]; hi0 = q[1]; }
+    for (; h0; i += stride) {
+        const bool h2 = i + 2 * stride < n_items;
+        u32 a2 = 0, b2 = 0;
+        if (h2) { a2 = offs[i + 2 * stride]; b2 = offs[i + 2 * stride + 1]; }
+        u64 lo1 = 0, hi1 = 0;
+        if (h1) { const u64 *q = reinterpret_cast<const u64 *>(reinterpret_cast<uintptr_t>(t.text + base + a1) & ~(uintptr_t)7); lo1 = q[0]; hi1 = q[1]; }
+        const u64 pos = base + a0;
+        const u64 len = base + b0 - pos;
+        const uint8_t *p = t.text + pos;
+        u64 v = 0;
+        if (len <= SHORT_MAX) {
+            const u32 sh = (u32)(reinterpret_cast<uintptr_t>(p) & 7u) * 8u;
+            const u64 first8 = sh ? (lo0 >> sh) | (hi0 << (64u - sh)) : lo0;
+            v = enc_short_get(t, (first8 & low_bytes_mask((u32)len)) | ((u64)len << 56));   // = short_key(p, len)
+        } else if (len <= MAX_TOKEN_LEN) v = enc_long_get(t, p, (u32)len, pos);
+        else t.ctr[6] = 1;
+        vals[i] = v;
+        a0 = a1; b0 = b1; lo0 = lo1; hi0 = hi1; h0 = h1;
+        a1 = a2; b1 = b2; h1 = h2;
+    }
+#else
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += (u64)gridDim.x * blockDim.x) {
         const u64 pos = base + offs[i];
         const u64 len = base + offs[i + 1] - pos;
@@ -165,6 +203,7 @@ __global__ void __launch_bounds__(256) k_enc_lookup(EncTables t, const u32 *__re
         else t.ctr[6] = 1;
         vals[i] = v;
     }
+#endif
 }
 
 // ---- BPE of the queued pretokens: one warp each ----------------------------------------------------------
@@ -817,7 +856,9 @@ static int encode_core(bpe_tok *tok, u64 n, int out_dtype, void *out_dev, u64 de
         const unsigned grid = (unsigned)std::max<u64>(1, std::min<u64>((u64)ctx->sm_count * 8, (bound + 255) / 256));
         CUDA_TRY(ctx, cudaEventRecord(evs[0], st));
         launch_starts_to_offsets((const u32 *)ctx->flags.p, b_lo, b_hi, n, pre + b_lo, base, offs, bound, ctx->sm_count, st);
-        if (bound) KLAUNCH(k_enc_lookup, grid, 256, 0, st, t, offs, bound, base, vals);
+        static const int lk_ctas_per_sm = getenv("BPE_LOOKUP_CTAS") ? std::max(1, atoi(getenv("BPE_LOOKUP_CTAS"))) : 64;
+        const unsigned lgrid = (unsigned)std::max<u64>(1, std::min<u64>((u64)ctx->sm_count * lk_ctas_per_sm, (bound + 255) / 256));
+        if (bound) KLAUNCH(k_enc_lookup, lgrid, 256, 0, st, t, offs, bound, base, vals);
         CUDA_TRY(ctx, cudaGetLastError());
         CUDA_TRY(ctx, cudaEventRecord(evs[1], st));
         BPE_TRY(cache_read_ctr(tok, c, 8));

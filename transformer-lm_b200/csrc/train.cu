@@ -81,7 +81,8 @@ __device__ __forceinline__ void long_add(const CountTables &t, const uint8_t *p,
     u64 s = h & mask;
     u64 mine = (off_meta << META_LEN_BITS) | len;
     for (u64 probes = 0; probes < t.lcap; probes++) {
-        u64 m = LMETA(t, s);
+        const ulonglong2 mh = *reinterpret_cast<const ulonglong2 *>(&LMETA(t, s));   // meta and hash: one 16-byte load, one round trip
+        u64 m = mh.x, hh = mh.y;
         if (m == META_EMPTY) {
             u64 old = atomicCAS(&LMETA(t, s), META_EMPTY, mine);
             if (old == META_EMPTY) {
@@ -92,11 +93,9 @@ __device__ __forceinline__ void long_add(const CountTables &t, const uint8_t *p,
                 return;
             }
             m = old;
+            hh = *((volatile u64 *)&LHASH(t, s));
         }
-        if ((m & META_LEN_MASK) == len) {
-            u64 hh = *((volatile u64 *)&LHASH(t, s));
-            if ((hh == 0 || hh == h) && bytes_equal(rep_ptr(t, m), p, len)) { atomicAdd(&LCNT(t, s), delta); return; }
-        }
+        if ((m & META_LEN_MASK) == len && (hh == 0 || hh == h) && bytes_equal(rep_ptr(t, m), p, len)) { atomicAdd(&LCNT(t, s), delta); return; }
         s = (s + 1) & mask;
     }
     t.counters[3] = 1;
@@ -506,7 +505,8 @@ static int count_current_text(bpe_ctx *ctx, u64 n, u64 own_begin, u64 own_end, u
         launch_starts_to_offsets(fl, b_lo, b_hi, n, pre, base, offs, bound[bi], ctx->sm_count, st);
         CountTables t = count_tables(ctx);
         if (bound[bi]) {
-            unsigned g2 = (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (bound[bi] + 255) / 256);
+            static const int cnt_ctas_per_sm = getenv("BPE_COUNT_CTAS") ? std::max(1, atoi(getenv("BPE_COUNT_CTAS"))) : 192;
+            unsigned g2 = (unsigned)std::min<u64>((u64)ctx->sm_count * cnt_ctas_per_sm, (bound[bi] + 255) / 256);
             KLAUNCH(k_count_pretokens, g2, 256, 0, st, t, offs, bound[bi], base, own_begin, own_end, trust_end);
         }
         CUDA_TRY(ctx, cudaGetLastError());
