@@ -43,7 +43,7 @@ BPE_API int bpe_batch_windows_dev(bpe_ctx *ctx, const void *tokens_dev, int dtyp
     // (pageable source: cudaMemcpyAsync stages it before returning, the caller's array may be reused at once)
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->tmp0.p, starts_host, (size_t)batch * 8, cudaMemcpyHostToDevice, st));
     const u64 total = (u64)batch * context;
-    const unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (total + 255) / 256);
+    const unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (total + 255) / 256);
     if (dtype == BPE_DTYPE_U16)
         KLAUNCH(k_batch_windows<uint16_t>, grid, 256, 0, st, (const uint16_t *)tokens_dev, (const long long *)ctx->tmp0.p, batch, context, (long long *)x_dev, (long long *)y_dev);
     else

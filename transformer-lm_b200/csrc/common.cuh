@@ -1,5 +1,6 @@
 // common.cuh -- context, error plumbing and small device helpers shared by all kernels.
 #pragma once
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -75,6 +76,8 @@ void bpe_pool_trim(bpe_ctx *ctx);                                 // cudaFree ev
     } while (0)
 
 static inline size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+// CTAs per SM of the grid-stride kernels (BPE_GRID_MULT overrides; measured per kernel)
+static inline int bpe_grid_mult(int dflt) { static const int env = getenv("BPE_GRID_MULT") ? atoi(getenv("BPE_GRID_MULT")) : 0; return env > 0 ? env : dflt; }
 static inline uint64_t next_pow2(uint64_t x) { uint64_t p = 1; while (p < x) p <<= 1; return p; }
 
 // every kernel launch of the library goes through KLAUNCH so that launches can be counted (bench.py: gpu_launches)

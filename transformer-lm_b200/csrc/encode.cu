@@ -611,7 +611,7 @@ static int cache_tables_alloc(bpe_tok *tok, u64 scap, u64 lcap) {
     BPE_TRY(alloc_exact_e(ctx, tok->ltab, lcap * sizeof(LSlot)));
     tok->scap = scap; tok->lcap = lcap;
     EncTables t = enc_tables(tok);
-    KLAUNCH(k_enc_clear_tables, (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (std::max(scap, lcap) + 255) / 256), 256, 0, ctx->stream, t);
+    KLAUNCH(k_enc_clear_tables, (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (std::max(scap, lcap) + 255) / 256), 256, 0, ctx->stream, t);
     CUDA_TRY(ctx, cudaGetLastError());
     return BPE_OK;
 }
@@ -662,9 +662,9 @@ static int cache_ensure_capacity(bpe_tok *tok, u64 n_short, u64 n_long, u64 new_
     int rc = cache_tables_alloc(tok, need_s, need_l);
     if (rc == BPE_OK) {
         EncTables t = enc_tables(tok);
-        unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (oscap + 255) / 256);
+        unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (oscap + 255) / 256);
         KLAUNCH(k_enc_rehash_short, grid, 256, 0, ctx->stream, (const SSlot *)ostab.p, oscap, t);
-        grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (olcap + 255) / 256);
+        grid = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (olcap + 255) / 256);
         KLAUNCH(k_enc_rehash_long, grid, 256, 0, ctx->stream, (const LSlot *)oltab.p, olcap, t);
         cudaError_t e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -853,7 +853,7 @@ static int encode_core(bpe_tok *tok, u64 n, int out_dtype, void *out_dev, u64 de
         CUDA_TRY(ctx, cudaMemsetAsync((u64 *)tok->ctr.p + 2, 0, 8, st));
         EncTables t = enc_tables(tok);
         const u64 base = b_lo * 32;
-        const unsigned grid = (unsigned)std::max<u64>(1, std::min<u64>((u64)ctx->sm_count * 8, (bound + 255) / 256));
+        const unsigned grid = (unsigned)std::max<u64>(1, std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (bound + 255) / 256));
         CUDA_TRY(ctx, cudaEventRecord(evs[0], st));
         launch_starts_to_offsets((const u32 *)ctx->flags.p, b_lo, b_hi, n, pre + b_lo, base, offs, bound, ctx->sm_count, st);
         static const int lk_ctas_per_sm = getenv("BPE_LOOKUP_CTAS") ? std::max(1, atoi(getenv("BPE_LOOKUP_CTAS"))) : 64;
@@ -867,8 +867,8 @@ static int encode_core(bpe_tok *tok, u64 n, int out_dtype, void *out_dev, u64 de
         const u64 n_todo = c[2];
         new_unique += n_todo;
         if (n_todo) {
-            unsigned g2 = (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (n_todo + 7) / 8);
-            unsigned g1 = (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (n_todo + BPT_NT - 1) / BPT_NT);
+            unsigned g2 = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (n_todo + 7) / 8);
+            unsigned g1 = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (n_todo + BPT_NT - 1) / BPT_NT);
             KLAUNCH(k_enc_bpe_short, g1, BPT_NT, 0, st, t, n_todo);
             KLAUNCH(k_enc_bpe, g2, 256, 0, st, t, n_todo);
             CUDA_TRY(ctx, cudaGetLastError());
@@ -1099,7 +1099,7 @@ static int decode_core(bpe_tok *tok, const int64_t *ids_host, uint64_t n, uint8_
     host[0] = ~0ull;
     CUDA_TRY(ctx, cudaMemcpyAsync(scr, host, 8, cudaMemcpyHostToDevice, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(ids, ids_host, n * 8, cudaMemcpyHostToDevice, st));
-    unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (n + 255) / 256);
+    unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (n + 255) / 256);
     KLAUNCH(k_dec_lens, grid, 256, 0, st, ids, n, (const u32 *)tok->vlen.p, tok->n_dense, lens, scr);
     launch_scan_u32(lens, n, off, tmp, st);
     CUDA_TRY(ctx, cudaGetLastError());

@@ -76,7 +76,7 @@ void launch_pretok_flags(const uint8_t *text, u64 n, const u32 *spmask, const u3
                          u64 err_lo, u64 err_hi, int sm_count, cudaStream_t st) {
     u64 n_tiles = (n + PT_TILE - 1) / PT_TILE;
     if (n_tiles == 0) return;
-    u64 grid = (u64)sm_count * 8;
+    u64 grid = (u64)sm_count * bpe_grid_mult(64);
     if (grid > n_tiles) grid = n_tiles;
     if (spmask)
         KLAUNCH(k_pretok_flags<true>, (unsigned)grid, PT_NT, 0, st, text, n, n_tiles, spmask, spstart, flags, err, err_lo, err_hi);
@@ -266,7 +266,7 @@ void launch_special_split(const uint8_t *text, u64 n, const uint8_t *sp_blob_dev
                           u32 max_len, u32 *cand, u32 *spstart, u32 *spmask, u64 n_words, int sm_count, cudaStream_t st) {
     SpecialsDev sp{sp_blob_dev, sp_offs_dev, n_sp, max_len};
     u64 grid = (n_words + 255) / 256;
-    u64 cap = (u64)sm_count * 8;
+    u64 cap = (u64)sm_count * bpe_grid_mult(64);
     if (grid > cap) grid = cap;
     if (grid == 0) return;
     KLAUNCH(k_special_candidates, (unsigned)grid, 256, 0, st, text, n, sp, cand, n_words);
@@ -293,12 +293,12 @@ __global__ void __launch_bounds__(256) k_flags_to_offsets(const u32 *__restrict_
     }
 }
 void launch_popc_words(const u32 *flags, u64 n_words, u32 *cnt, int sm_count, cudaStream_t st) {
-    u64 grid = (n_words + 255) / 256, capg = (u64)sm_count * 8;
+    u64 grid = (n_words + 255) / 256, capg = (u64)sm_count * bpe_grid_mult(64);
     if (grid > capg) grid = capg;
     if (grid) KLAUNCH(k_popc_words, (unsigned)grid, 256, 0, st, flags, n_words, cnt);
 }
 void launch_flags_to_offsets(const u32 *flags, u64 n_words, const u64 *pre, u64 *out, u64 cap, int sm_count, cudaStream_t st) {
-    u64 grid = (n_words + 255) / 256, capg = (u64)sm_count * 8;
+    u64 grid = (n_words + 255) / 256, capg = (u64)sm_count * bpe_grid_mult(64);
     if (grid > capg) grid = capg;
     if (grid) KLAUNCH(k_flags_to_offsets, (unsigned)grid, 256, 0, st, flags, n_words, pre, out, cap);
 }
@@ -337,7 +337,7 @@ void launch_starts_to_offsets(const u32 *flags, u64 word_begin, u64 word_end, u6
                               int sm_count, cudaStream_t st) {
     u64 bw = word_end - word_begin;
     if (bw) {
-        unsigned grid = (unsigned)((bw + 255) / 256 < (u64)sm_count * 8 ? (bw + 255) / 256 : (u64)sm_count * 8);
+        unsigned grid = (unsigned)((bw + 255) / 256 < (u64)sm_count * bpe_grid_mult(64) ? (bw + 255) / 256 : (u64)sm_count * bpe_grid_mult(64));
         KLAUNCH(k_starts_to_offsets, grid, 256, 0, st, flags, word_begin, word_end, pre, base, offs);
     }
     KLAUNCH(k_next_start_after, 1, 32, 0, st, flags, word_end * 32, n, base, offs + n_items);

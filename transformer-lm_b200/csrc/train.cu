@@ -451,9 +451,9 @@ static int count_ensure_capacity(bpe_ctx *ctx, u64 n_short, u64 n_long, u64 new_
     // the short rehash re-counts its uniques through short_add: reset [0]; [1],[2] (long) are untouched
     CUDA_TRY(ctx, cudaMemsetAsync(cs->counters.p, 0, sizeof(u64), ctx->stream));
     CountTables t = count_tables(ctx);
-    unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (old_view.scap + 255) / 256);
+    unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (old_view.scap + 255) / 256);
     KLAUNCH(k_rehash_short, grid, 256, 0, ctx->stream, (const u64 *)old_view.stab.p, old_view.scap, t);
-    grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (old_view.lcap + 255) / 256);
+    grid = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (old_view.lcap + 255) / 256);
     KLAUNCH(k_rehash_long, grid, 256, 0, ctx->stream, (const u64 *)old_view.ltab.p, old_view.lcap, t);
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -527,7 +527,7 @@ static int count_rehome(bpe_ctx *ctx) {
     CountTables t = count_tables(ctx);
     u64 *scr = (u64 *)ctx->scratch.p + 8;
     CUDA_TRY(ctx, cudaMemsetAsync(scr, 0, 16, st));
-    unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (cs->lcap + 255) / 256);
+    unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (cs->lcap + 255) / 256);
     KLAUNCH(k_rehome_sizes, grid, 256, 0, st, t, scr);
     u64 *host = (u64 *)ctx->pinned;
     CUDA_TRY(ctx, cudaMemcpyAsync(host, scr, 8, cudaMemcpyDeviceToHost, st));
@@ -589,7 +589,7 @@ BPE_API int bpe_count_export_size(bpe_ctx *ctx, uint64_t *n_words, uint64_t *blo
     u32 *lens = (u32 *)ctx->tmp1.p; u32 *pres = (u32 *)((uint8_t *)lens + lens_b);
     u64 *boff = (u64 *)((uint8_t *)pres + pres_b); u64 *widx = (u64 *)((uint8_t *)boff + boff_b);
     u64 *tmp = (u64 *)((uint8_t *)widx + widx_b);
-    unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (total + 255) / 256);
+    unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (total + 255) / 256);
     KLAUNCH(k_export_lens, grid, 256, 0, st, t, lens);
     KLAUNCH(k_export_flags, grid, 256, 0, st, lens, total, pres);
     launch_scan_u32(lens, total, boff, tmp, st);
@@ -621,7 +621,7 @@ static int count_export(bpe_ctx *ctx, uint8_t *blob, uint64_t *offs, int64_t *co
         dblob = (uint8_t *)ctx->tmp0.p; doffs = (u64 *)(dblob + ob); dcnt = (i64 *)(dblob + ob + oo);
     }
     if ((nb && !dblob) || (nw && !dcnt)) return BPE_ERR_ARG;
-    unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (total + 255) / 256);
+    unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (total + 255) / 256);
     KLAUNCH(k_export_write, grid, 256, 0, st, t, lens, boff, widx, dblob, doffs, dcnt);
     CUDA_TRY(ctx, cudaGetLastError());
     if (to_device) {
@@ -676,7 +676,7 @@ static int count_import(bpe_ctx *ctx, const uint8_t *blob, const uint64_t *offs,
     BPE_TRY(read_counters(ctx, c, 8));
     BPE_TRY(count_ensure_capacity(ctx, c[0], c[1], n_words, n_words));
     CountTables t = count_tables(ctx);
-    unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (n_words + 255) / 256);
+    unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (n_words + 255) / 256);
     KLAUNCH(k_import_words, grid, 256, 0, st, t, (const uint8_t *)cs->pool.p + base, base, doffs, dcnt, n_words);
     CUDA_TRY(ctx, cudaGetLastError());
     BPE_TRY(read_counters(ctx, c, 8));
@@ -717,13 +717,13 @@ BPE_API int bpe_count_pair_table(bpe_ctx *ctx, const uint8_t *specials_blob, con
     Words W{(int32_t *)sym.p, (WordMeta *)wmeta.p, (u64 *)wctr.p};
     CountTables t = count_tables(ctx);
     u64 total = cs->scap + cs->lcap;
-    unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (total + 255) / 256);
+    unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (total + 255) / 256);
     KLAUNCH(k_build_words, grid, 256, 0, st, t, W, spb, spo, n_specials);
     u64 *host = (u64 *)ctx->pinned;
     CUDA_TRY(ctx, cudaMemcpyAsync(host, wctr.p, 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     u64 n_words = host[0];
-    unsigned wgrid = (unsigned)std::max<u64>(1, std::min<u64>((u64)ctx->sm_count * 8, (n_words + 255) / 256));
+    unsigned wgrid = (unsigned)std::max<u64>(1, std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (n_words + 255) / 256));
     KLAUNCH(k_init_pair_counts, wgrid, 256, 0, st, W, n_words, (u64 *)dense.p, (u32 *)hist.p);
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaMemcpyAsync(dense_out, dense.p, 65536 * 8, cudaMemcpyDeviceToHost, st));
@@ -756,7 +756,7 @@ static int run_merges(bpe_ctx *ctx, const uint8_t *sp_blob, const u32 *sp_offs, 
     CountTables t = count_tables(ctx);
     {
         u64 total = cs->scap + cs->lcap;
-        unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (total + 255) / 256);
+        unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (total + 255) / 256);
         KLAUNCH(k_build_words, grid, 256, 0, st, t, W, spb, spo, n_sp);
         CUDA_TRY(ctx, cudaGetLastError());
     }
@@ -768,7 +768,7 @@ static int run_merges(bpe_ctx *ctx, const uint8_t *sp_blob, const u32 *sp_offs, 
     BPE_TRY(alloc_exact(ctx, B.dense, 65536 * 8)); BPE_TRY(alloc_exact(ctx, B.hist, 65536 * 4));
     BPE_TRY(alloc_exact(ctx, B.csr_off, 65537 * 4)); BPE_TRY(alloc_exact(ctx, B.csr_rec, (n_syms + 1) * sizeof(Rec)));
     CUDA_TRY(ctx, cudaMemsetAsync(B.dense.p, 0, 65536 * 8, st)); CUDA_TRY(ctx, cudaMemsetAsync(B.hist.p, 0, 65536 * 4, st));
-    unsigned wgrid = (unsigned)std::max<u64>(1, std::min<u64>((u64)ctx->sm_count * 8, (n_words + 255) / 256));
+    unsigned wgrid = (unsigned)std::max<u64>(1, std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (n_words + 255) / 256));
     KLAUNCH(k_init_pair_counts, wgrid, 256, 0, st, W, n_words, (u64 *)B.dense.p, (u32 *)B.hist.p);
     KLAUNCH(k_csr_scan, 1, 1024, 0, st, (u32 *)B.hist.p, (u32 *)B.csr_off.p);
     KLAUNCH(k_csr_fill, wgrid, 256, 0, st, W, n_words, (const u32 *)B.csr_off.p, (u32 *)B.hist.p, (Rec *)B.csr_rec.p);
@@ -937,7 +937,7 @@ static int run_merges(bpe_ctx *ctx, const uint8_t *sp_blob, const u32 *sp_offs, 
         CUDA_TRY(ctx, cudaMemcpyAsync((u64 *)B.ctr.p + 5, host + 5, 8, cudaMemcpyHostToDevice, st));
         CUDA_TRY(ctx, cudaMemcpyAsync((u64 *)B.ctr.p + 6, host + 6, 8, cudaMemcpyHostToDevice, st));
         ctr[3] = 0;
-        unsigned rg = (unsigned)std::min<u64>((u64)ctx->sm_count * 8, (ocap + 255) / 256);
+        unsigned rg = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (ocap + 255) / 256);
         CUDA_TRY(ctx, cudaMemcpyToSymbolAsync(cM, &M, sizeof(M), 0, cudaMemcpyHostToDevice, st));
         KLAUNCH(k_pairs_rehash, rg, 256, 0, st, (const u64 *)okey.p, (const i64 *)ocnt.p, ocap, pending);
         CUDA_TRY(ctx, cudaGetLastError());
