@@ -11,14 +11,15 @@
 //   3. k_enc_bpe      one warp per queued (new unique) pretoken applies the merges in rank order
 //                     through the pair -> rank table: repeatedly take the lowest-ranked adjacent
 //                     pair and replace all its non-overlapping occurrences left to right
-//   4. k_enc_count    tokens per 32-byte text word -> exclusive scan = output offsets
-//   5. k_enc_emit     token ids scattered to the uint16 / int32 output
+//   4. k_enc_scan_emit  tokens per pretoken -> exclusive offsets -> ids scattered to the uint16 / int32 output, in one
+//                     pass (single-pass scan with decoupled look-back)
 // The reference re-runs BPE for every occurrence (no memoisation, tokenizer.py:118-136); the result per
 // pretoken is a pure function of its bytes, so caching by exact bytes cannot change the output.
 #include <algorithm>
 #include "kernels.h"
 #include "ctx.h"
 #include "hashtab.cuh"
+#include "scan.cuh"
 
 #define SHORT_MAX 7u
 #define META_EMPTY 0xFFFFFFFFFFFFFFFFull
@@ -428,32 +429,85 @@ __device__ __forceinline__ u32 value_count(u64 v) {
     return tag <= 3 ? tag : (tag == VAL_EXT ? (u32)(v & 0xFFFFFFu) : 0);
 }
 
-// tokens per pretoken occurrence; forward references are resolved now that the BPE kernel has run (a KeyError value
-// records the smallest text offset it occurs at)
-__global__ void __launch_bounds__(256) k_enc_ntok(EncTables t, u64 *__restrict__ vals, const u32 *__restrict__ offs, u64 n_items,
-                                                 u64 base, u32 *__restrict__ ntok) {
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += (u64)gridDim.x * blockDim.x) {
-        u64 v = vals[i];
-        if (VAL_TAG(v) == VAL_FWD) { v = enc_value(t, (u32)v); vals[i] = v; }
-        if (VAL_TAG(v) == VAL_ERR) atomicMin(&t.ctr[7], base + offs[i]);
-        ntok[i] = value_count(v);
-    }
+// ---- fused: tokens per pretoken -> exclusive offsets -> ids, in ONE pass (single-pass scan with decoupled look-back) -------
+// The three kernels above read the per-occurrence values twice and round-trip a count and an offset array through HBM
+// (~45 B per pretoken); this one reads each value once and writes only the ids (8 B + 2 B per token).  A CTA takes the next
+// tile from a ticket counter (tiles start in order, so the look-back cannot wait on a tile that has not been scheduled),
+// counts its tokens, publishes {status, sum} in one 64-bit word, adds up its predecessors' words until it meets an
+// inclusive prefix, and emits its ids at that offset.
+#define SE_NT 256
+#define SE_ITEMS 8
+#define SE_TILE (SE_NT * SE_ITEMS)
+#define SE_AGG (1ull << 62)
+#define SE_INCL (2ull << 62)
+#define SE_VAL(x) ((x) & ((1ull << 62) - 1))
+__device__ __forceinline__ u64 warp_sum_u64(u64 v) {
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
 }
-
-// ids of pretoken i go to out[out_base + tokoff[i] ...]: neighbouring threads write neighbouring ids
-template <typename OutT>
-__global__ void __launch_bounds__(256) k_enc_emit(EncTables t, const u64 *__restrict__ vals, u64 n_items, const u64 *__restrict__ tokoff,
-                                                 OutT *__restrict__ out, u64 out_base, u64 cap) {
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += (u64)gridDim.x * blockDim.x) {
-        const u64 v = vals[i];
-        u64 dst = out_base + tokoff[i];
-        const u32 tag = VAL_TAG(v);
+template <typename OutT, bool kEmit>
+__global__ void __launch_bounds__(SE_NT) k_enc_scan_emit(EncTables t, u64 *__restrict__ vals, const u32 *__restrict__ offs, u64 n_items, u64 base,
+                                                        u64 *tile_state, u32 *ticket, OutT *__restrict__ out, u64 out_base, u64 cap,
+                                                        u64 *__restrict__ total_out) {
+    __shared__ u32 s_tile;
+    __shared__ u32 s_warp[33];
+    __shared__ u64 s_prefix;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const u32 tile = s_tile;
+    const u64 first = (u64)tile * SE_TILE + (u64)threadIdx.x * SE_ITEMS;
+    u64 v[SE_ITEMS];
+    u32 sum = 0;
+#pragma unroll
+    for (u32 k = 0; k < SE_ITEMS; k++) v[k] = first + k < n_items ? vals[first + k] : 0;
+#pragma unroll
+    for (u32 k = 0; k < SE_ITEMS; k++) {
+        if (first + k >= n_items) continue;
+        if (VAL_TAG(v[k]) == VAL_FWD) { v[k] = enc_value(t, (u32)v[k]); vals[first + k] = v[k]; }   // computed by the BPE kernels meanwhile
+        if (VAL_TAG(v[k]) == VAL_ERR) atomicMin(&t.ctr[7], base + offs[first + k]);               // KeyError: smallest text offset
+        sum += value_count(v[k]);
+    }
+    u32 tot;
+    const u32 ex = block_excl_scan_u32(sum, &tot, s_warp);
+    if (threadIdx.x < 32) {
+        const u32 lane = threadIdx.x;
+        u64 run = 0;
+        if (tile > 0) {
+            if (lane == 0) *((volatile u64 *)&tile_state[tile]) = SE_AGG | (u64)tot;
+            long long j = (long long)tile - 1;
+            for (;;) {
+                const long long idx = j - lane;
+                u64 w = idx >= 0 ? *((volatile u64 *)&tile_state[idx]) : SE_INCL;
+                while (__any_sync(0xffffffffu, (w >> 62) == 0)) { if (idx >= 0 && (w >> 62) == 0) w = *((volatile u64 *)&tile_state[idx]); }
+                const u32 m = __ballot_sync(0xffffffffu, (w >> 62) == 2);
+                if (m) {
+                    const u32 stop = __ffs(m) - 1;                       // nearest tile with an inclusive prefix
+                    run += warp_sum_u64(lane <= stop ? SE_VAL(w) : 0);
+                    break;
+                }
+                run += warp_sum_u64(SE_VAL(w));
+                j -= 32;
+            }
+        }
+        if (lane == 0) {
+            *((volatile u64 *)&tile_state[tile]) = SE_INCL | (run + tot);
+            s_prefix = run;
+            if ((u64)(tile + 1) * SE_TILE >= n_items) *total_out = run + tot;
+        }
+    }
+    __syncthreads();
+    if (!kEmit) return;
+    u64 dst = out_base + s_prefix + ex;
+#pragma unroll
+    for (u32 k = 0; k < SE_ITEMS; k++) {
+        const u32 tag = VAL_TAG(v[k]);
         if (tag <= 3) {
-            for (u32 k = 0; k < tag; k++) { if (dst < cap) out[dst] = (OutT)((v >> (20 * k)) & 0xFFFFFu); dst++; }
+            for (u32 q = 0; q < tag; q++) { if (dst < cap) out[dst] = (OutT)((v[k] >> (20 * q)) & 0xFFFFFu); dst++; }
         } else if (tag == VAL_EXT) {
-            const u32 *src = t.ipool + ((v >> 24) & 0xFFFFFFFFFull);
-            const u32 c = (u32)(v & 0xFFFFFFu);
-            for (u32 k = 0; k < c; k++) { if (dst < cap) out[dst] = (OutT)src[k]; dst++; }
+            const u32 *src = t.ipool + ((v[k] >> 24) & 0xFFFFFFFFFull);
+            const u32 c = (u32)(v[k] & 0xFFFFFFu);
+            for (u32 q = 0; q < c; q++) { if (dst < cap) out[dst] = (OutT)src[q]; dst++; }
         }
     }
 }
@@ -842,13 +896,12 @@ static int encode_core(bpe_tok *tok, u64 n, int out_dtype, void *out_dev, u64 de
         BPE_TRY(bpe_buf_reserve(ctx, tok->todo, std::max<size_t>(bound * 4, 16)));
         // per-pretoken arrays of the batch: offsets, cache slots, token counts, token offsets
         const u64 bw = b_hi - b_lo;
-        size_t off_b = round_up((bound + 2) * 4, 256), slot_b = round_up((bound + 1) * 8, 256), nt_b = round_up((bound + 1) * 4, 256);
-        size_t to_b = round_up((bound + 2) * 8, 256), st_b = round_up(scan_tmp_elems_host(bound) * 8, 256);
+        const u64 n_tiles = (bound + SE_TILE - 1) / SE_TILE;
+        size_t off_b = round_up((bound + 2) * 4, 256), slot_b = round_up((bound + 1) * 8, 256), nt_b = 0;
+        size_t to_b = 0, st_b = round_up((n_tiles + 4) * 8, 256);          // tile states, ticket, batch total
         BPE_TRY(bpe_buf_reserve(ctx, ctx->tmp1, off_b + slot_b + nt_b + to_b + st_b));
         u32 *offs = (u32 *)ctx->tmp1.p;
         u64 *vals = (u64 *)((uint8_t *)ctx->tmp1.p + off_b);
-        u32 *ntok = (u32 *)((uint8_t *)ctx->tmp1.p + off_b + slot_b);
-        u64 *tokoff = (u64 *)((uint8_t *)ctx->tmp1.p + off_b + slot_b + nt_b);
         u64 *stmp = (u64 *)((uint8_t *)ctx->tmp1.p + off_b + slot_b + nt_b + to_b);
         CUDA_TRY(ctx, cudaMemsetAsync((u64 *)tok->ctr.p + 2, 0, 8, st));
         EncTables t = enc_tables(tok);
@@ -874,12 +927,21 @@ static int encode_core(bpe_tok *tok, u64 n, int out_dtype, void *out_dev, u64 de
             CUDA_TRY(ctx, cudaGetLastError());
         }
         CUDA_TRY(ctx, cudaEventRecord(evs[2], st));
-        // tokens per pretoken -> offsets
-        if (bound) KLAUNCH(k_enc_ntok, grid, 256, 0, st, t, vals, offs, bound, base, ntok);
-        launch_scan_u32(ntok, bound, tokoff, stmp, st);
-        CUDA_TRY(ctx, cudaGetLastError());
+        // tokens per pretoken -> offsets -> ids, one pass
         u64 *host = (u64 *)ctx->pinned;
-        CUDA_TRY(ctx, cudaMemcpyAsync(host, tokoff + bound, 8, cudaMemcpyDeviceToHost, st));
+        {
+            u64 *tile_state = stmp, *total_dev = stmp + n_tiles + 2;
+            u32 *ticket = (u32 *)(stmp + n_tiles + 1);
+            CUDA_TRY(ctx, cudaMemsetAsync(stmp, 0, (n_tiles + 4) * 8, st));
+            const bool emit = out_dev && total_tokens < dev_cap;
+            if (bound) {
+                if (!emit) KLAUNCH((k_enc_scan_emit<uint16_t, false>), (unsigned)n_tiles, SE_NT, 0, st, t, vals, offs, bound, base, tile_state, ticket, (uint16_t *)nullptr, total_tokens, dev_cap, total_dev);
+                else if (out_dtype == BPE_DTYPE_U16) KLAUNCH((k_enc_scan_emit<uint16_t, true>), (unsigned)n_tiles, SE_NT, 0, st, t, vals, offs, bound, base, tile_state, ticket, (uint16_t *)out_dev, total_tokens, dev_cap, total_dev);
+                else KLAUNCH((k_enc_scan_emit<int32_t, true>), (unsigned)n_tiles, SE_NT, 0, st, t, vals, offs, bound, base, tile_state, ticket, (int32_t *)out_dev, total_tokens, dev_cap, total_dev);
+            }
+            CUDA_TRY(ctx, cudaGetLastError());
+            CUDA_TRY(ctx, cudaMemcpyAsync(host, total_dev, 8, cudaMemcpyDeviceToHost, st));
+        }
         CUDA_TRY(ctx, cudaMemcpyAsync(host + 1, (u64 *)tok->ctr.p + 7, 8, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(ctx, cudaStreamSynchronize(st));
         (void)bw;
@@ -893,7 +955,7 @@ static int encode_core(bpe_tok *tok, u64 n, int out_dtype, void *out_dev, u64 de
             CUDA_TRY(ctx, cudaMemcpy(&hpre, pre + w, 8, cudaMemcpyDeviceToHost));
             CUDA_TRY(ctx, cudaMemcpy(&hflags, (const u32 *)ctx->flags.p + w, 4, cudaMemcpyDeviceToHost));
             u64 o = hpre - ord[b] + __builtin_popcount(hflags & ((1u << (err_pos & 31)) - 1u));
-            CUDA_TRY(ctx, cudaMemcpy(&hv[0], vals + o, 8, cudaMemcpyDeviceToHost));   // (forward references were resolved by k_enc_ntok)
+            CUDA_TRY(ctx, cudaMemcpy(&hv[0], vals + o, 8, cudaMemcpyDeviceToHost));   // (forward references were resolved by k_enc_scan_emit)
             u32 sym = (u32)hv[0];
             tok->key_error.clear();
             if (sym & 0x80000000u) {
@@ -906,13 +968,6 @@ static int encode_core(bpe_tok *tok, u64 n, int out_dtype, void *out_dev, u64 de
             CUDA_TRY(ctx, cudaMemcpy((u64 *)tok->ctr.p + 7, &reset7, 8, cudaMemcpyHostToDevice));
             ctx->err_detail = (int64_t)err_pos;
             return bpe_set_error(ctx, BPE_ERR_KEY, "KeyError: a token of the pretoken at byte %llu is not in the vocabulary", (unsigned long long)err_pos);
-        }
-        if (out_dev && total_tokens < dev_cap && bound) {
-            if (out_dtype == BPE_DTYPE_U16)
-                KLAUNCH(k_enc_emit<uint16_t>, grid, 256, 0, st, t, vals, bound, tokoff, (uint16_t *)out_dev, total_tokens, dev_cap);
-            else
-                KLAUNCH(k_enc_emit<int32_t>, grid, 256, 0, st, t, vals, bound, tokoff, (int32_t *)out_dev, total_tokens, dev_cap);
-            CUDA_TRY(ctx, cudaGetLastError());
         }
         CUDA_TRY(ctx, cudaEventRecord(evs[3], st));
         CUDA_TRY(ctx, cudaEventSynchronize(evs[3]));
