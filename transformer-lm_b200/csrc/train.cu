@@ -105,7 +105,16 @@ __device__ __forceinline__ void long_add(const CountTables &t, const uint8_t *p,
 // Short pretokens are first counted in a per-CTA shared-memory table and flushed to the HBM table when the CTA is
 // done: natural-language text is Zipfian, and without this the few hottest words serialise hundreds of millions of
 // same-address L2 atomics.
-#define CNT_SMEM_SLOTS 2048u
+#ifndef CNT_DYNAMIC
+#define CNT_DYNAMIC 1
+#endif
+#ifndef CNT_TILE
+#define CNT_TILE 4096ull
+#endif
+#ifndef CNT_SMEM_LG
+#define CNT_SMEM_LG 11
+#endif
+#define CNT_SMEM_SLOTS (1u << CNT_SMEM_LG)
 #define CNT_SMEM_PROBES 4u
 __global__ void __launch_bounds__(256) k_count_pretokens(CountTables t, const u32 *__restrict__ offs, u64 n_items, u64 base,
                                                         u64 own_begin, u64 own_end, u64 trust_end) {
@@ -117,8 +126,24 @@ __global__ void __launch_bounds__(256) k_count_pretokens(CountTables t, const u3
     // Software pipeline over the grid-stride loop: while item i is hashed and counted, the first 16 bytes of item
     // i + stride and the offsets of item i + 2 stride are in flight (the chain offsets -> text -> table was the latency
     // that bounded this kernel: one item per thread at a time).
+#if CNT_DYNAMIC
+    // tiles of CNT_TILE items are handed out by a ticket counter: every CTA is busy until the batch is done, however uneven
+    // the cost of its items (hash-table misses, long pretokens) was
+    __shared__ u64 s_tile;
+    const u64 n_items_all = n_items;
+    for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_tile = atomicAdd(&t.counters[16], 1ull);
+    __syncthreads();
+    const u64 tile_lo = s_tile * CNT_TILE;
+    if (tile_lo >= n_items_all) break;
+    n_items = tile_lo + CNT_TILE < n_items_all ? tile_lo + CNT_TILE : n_items_all;
+    const u64 stride = blockDim.x;
+    u64 i = tile_lo + threadIdx.x;
+#else
     const u64 stride = (u64)gridDim.x * blockDim.x;
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+#endif
     bool h0 = i < n_items, h1 = i + stride < n_items;
     u32 a0 = 0, b0 = 0, a1 = 0, b1 = 0;
     if (h0) { a0 = offs[i]; b0 = offs[i + 1]; }
@@ -141,8 +166,7 @@ __global__ void __launch_bounds__(256) k_count_pretokens(CountTables t, const u3
                 const u32 sh = (u32)(reinterpret_cast<uintptr_t>(p) & 7u) * 8u;
                 const u64 first8 = sh ? (lo0 >> sh) | (hi0 << (64u - sh)) : lo0;
                 const u64 key = (first8 & low_bytes_mask((u32)len)) | ((u64)len << 56);   // = short_key(p, len)
-                u32 slot = (((u32)key ^ (u32)(key >> 32)) * 0x9E3779B1u) >> (32 - 11);   // cheap hash for the shared-memory table
-                static_assert(CNT_SMEM_SLOTS == 1u << 11, "slot hash assumes 2048 slots");
+                u32 slot = (((u32)key ^ (u32)(key >> 32)) * 0x9E3779B1u) >> (32 - CNT_SMEM_LG);   // cheap hash for the shared-memory table
                 bool done = false;
                 for (u32 pr = 0; pr < CNT_SMEM_PROBES && !done; pr++) {
                     u64 k = s_key[slot];
@@ -160,6 +184,9 @@ __global__ void __launch_bounds__(256) k_count_pretokens(CountTables t, const u3
         a0 = a1; b0 = b1; lo0 = lo1; hi0 = hi1; h0 = h1;
         a1 = a2; b1 = b2; h1 = h2;
     }
+#if CNT_DYNAMIC
+    }
+#endif
     // one atomic per warp for the occurrence counter
     for (int d = 16; d; d >>= 1) n_tok += __shfl_down_sync(0xffffffffu, n_tok, d);
     if (lane_id() == 0 && n_tok) atomicAdd(&t.counters[4], n_tok);
@@ -505,8 +532,9 @@ static int count_current_text(bpe_ctx *ctx, u64 n, u64 own_begin, u64 own_end, u
         launch_starts_to_offsets(fl, b_lo, b_hi, n, pre, base, offs, bound[bi], ctx->sm_count, st);
         CountTables t = count_tables(ctx);
         if (bound[bi]) {
-            static const int cnt_ctas_per_sm = getenv("BPE_COUNT_CTAS") ? std::max(1, atoi(getenv("BPE_COUNT_CTAS"))) : 192;
+            static const int cnt_ctas_per_sm = getenv("BPE_COUNT_CTAS") ? std::max(1, atoi(getenv("BPE_COUNT_CTAS"))) : (CNT_DYNAMIC ? 4 : 192);
             unsigned g2 = (unsigned)std::min<u64>((u64)ctx->sm_count * cnt_ctas_per_sm, (bound[bi] + 255) / 256);
+            if (CNT_DYNAMIC) CUDA_TRY(ctx, cudaMemsetAsync(t.counters + 16, 0, 8, st));
             KLAUNCH(k_count_pretokens, g2, 256, 0, st, t, offs, bound[bi], base, own_begin, own_end, trust_end);
         }
         CUDA_TRY(ctx, cudaGetLastError());
