@@ -347,7 +347,7 @@ def run_b200(args):
         # DRAM traffic of that kernel from the committed ncu capture of this exact configuration (null otherwise)
         traffic, traffic_src = None, None
         try:
-            tj = json.loads((ROOT / "profiles" / "r1_h_merge_loop_11GB.json").read_text())
+            tj = json.loads((ROOT / "profiles" / "r1_k_merge_loop_11GB.json").read_text())
             if world == 1 and all(tj["config"][k] == v for k, v in (("corpus_bytes", nbytes), ("vocab_size", vocab_size), ("shape", shape), ("seed", seed))):
                 traffic, traffic_src = tj["traffic_bytes_per_launch"], tj["source"]
         except Exception:
