@@ -9,8 +9,8 @@
 //   pair table   open addressing, key = a<<32|b, 64-bit count.  A key lives from its first touch
 //                (defaultdict semantics: counts may be 0) until it is merged (count = CNT_DEAD).
 //   argmax       every PB slots form a block with a cached maximum; an update marks its block dirty,
-//                so a step rescans only the blocks that changed and otherwise streams the (small)
-//                array of cached maxima.
+//                so a step rescans only the blocks that changed.  The cached maxima of the blocks a CTA owns
+//                live in its shared memory for the whole launch (written through to bmax for the next one).
 //   tie-break    (count, (bytes_a, bytes_b)) with python's bytes ordering.  Each token keeps its
 //                first 8 bytes as a big-endian integer (tok_key): comparing the integers decides
 //                almost every tie; equal prefixes fall back to lengths / a byte loop.
@@ -20,8 +20,8 @@
 //                CSR built once; any other pair (p,q): every occurrence is created in the step that created the
 //                younger of p,q, so it is found in that step's slice of an append-only log (bucket-sorted by
 //                neighbour when large).  Stale records are harmless (the symbols are re-checked, like the
-//                reference re-checks its stale index entries, train.py:196-200).  One thread per occurrence:
-//                no per-word serialisation, three dependent memory round trips per merge site.
+//                reference re-checks its stale index entries, train.py:196-200).  One warp per occurrence in most
+//                steps: no per-word serialisation, no divergence between sites.
 #pragma once
 #include <cooperative_groups.h>
 #include <cooperative_groups/scan.h>
@@ -29,15 +29,6 @@
 
 namespace cg = cooperative_groups;
 
-// Compile-time experiment switches of k_merge_loop (defaults = the fastest measured combination on B200):
-//   1 = LL-style gather (tag in every word) instead of flag-then-data      2 = new keys are claimed by a CAS-first probe
-//   4 = the four symbols around a site are loaded together                  8 = relaxed polls + fence in the flag gather
-//  16 = release / acquire flag barrier instead of fence + relaxed         32 = the four table probes of a site advance in one loop
-//  64 = counter barrier (one red.release per CTA, one polling lane) instead of per-CTA flags polled by a warp
-// 128 = (always on) records dealt thinly to warps      256 = warp 1 publishes the range of the CTA's candidate during the gather
-#ifndef MG_OPT
-#define MG_OPT 502u
-#endif
 // slot hash of the pair table: 32-bit multiplies only (the apply path computes four of these per site)
 __device__ __forceinline__ u32 pair_hash(u64 key) {
     u32 h = ((u32)(key >> 32) * 0x9E3779B1u) ^ ((u32)key * 0x85EBCA77u);
@@ -50,9 +41,7 @@ __device__ __forceinline__ u32 pair_hash(u64 key) {
 #define CNT_DEAD_LIMIT ((i64)0xC000000000000000ll) // counts below this are "popped (+ later deltas)"
 #define PB 64u                                   // pair-table slots per block (one rescan = two slots per lane)
 #define MG_NT 512
-#define MG_NEED_GROW 8ull
-#define CTA_BEST_STRIDE 1u                       // Best entries (1 KiB) between per-CTA candidates: spreads the all-read-all
-                                                 // exchange over many L2 slices instead of hammering a handful of lines                        // ctr[3] code: pair table more than half full, host must grow it
+#define MG_NEED_GROW 8ull                        // ctr[3] code: pair table more than half full, host must grow it
 
 struct __align__(16) WordMeta {
     u32 off, len;        // word w occupies sym[off, off+len) at build time
@@ -109,8 +98,7 @@ struct MergeState {
     // bk_lg[step] = log2(buckets) (0 = slice left unsorted), bk_start[step] = first of its buckets+1 offsets in bk_off
     Rec *log2; u32 *bk_lg; u64 *bk_start; u32 *bk_off; u64 bk_off_cap; u32 *bk_scratch;   // bk_scratch: 2 x (hist, cursor) x SORT_MAX_BK
     u32 *tok_off; u32 *tok_len; u64 *tok_key; uint8_t *tok_bytes; u64 tok_bytes_cap;
-    Best *cta_best;                               // (unused by the flag barrier; kept for the tail kernel's host code)
-    struct BarSlot *bar; u32 *bar_flags;          // gather slots / barrier epochs of k_merge_loop, zeroed before every launch
+    struct BarSlot *bar; u32 *bar_ctr;            // gather slots / the two barrier counters (128 B apart) of k_merge_loop, zeroed before every launch
     // tail kernel (one thread-block cluster): per 64-block superblock a 64-bit mask of dirty blocks
     u64 *sdirty_mask; u32 n_super; int tail_mode;
     int stop_at;                                 // this launch runs steps [ctr[1], stop_at)
@@ -282,19 +270,16 @@ __device__ __noinline__ void apply_site(u32 p, i64 c, u32 a, u32 b, u32 nw, int 
 #define WAS_LIVE(e) ((e) >= 0 || (e) == dead_now)                          /* live at the start of the step */
 #define OLD_TOMB(e) ((e) < SYM_SEP && (e) != dead_now)                     /* tombstone of an earlier step */
     // the four symbols around p are loaded together (one round trip in the common case of no old tombstones)
-    const bool upfront = (MG_OPT & 4u) != 0;
-    int32_t vl = 0, vb = 0, vr = 0;
+    int32_t vl = s[p - 1];
     const int32_t e0 = s[p];
-    if (upfront) { vl = s[p - 1]; vb = s[p + 1]; vr = s[p + 2]; }
+    int32_t vb = s[p + 1], vr = s[p + 2];
     if (!WAS_LIVE(e0) || ORIG(e0) != ia) return;                           // stale record
     u32 pb = p + 1;
-    if (!upfront) vb = s[pb];
     while (OLD_TOMB(vb)) { pb++; vb = s[pb]; }
     if (!WAS_LIVE(vb) || ORIG(vb) != ib) return;                           // stale record
     // ---- left context ----
     bool has_l = false; u32 left = 0, pos_l = 0;
     u32 q = p - 1;
-    if (!upfront) vl = s[q];
     while (OLD_TOMB(vl)) { q--; vl = s[q]; }
     if (a == b) {
         // run of a's ending just before p: its length decides whether p starts a site
@@ -320,7 +305,7 @@ __device__ __noinline__ void apply_site(u32 p, i64 c, u32 a, u32 b, u32 nw, int 
     }
     // ---- right context: the symbol as it was (it is merged later, if at all) ----
     u32 qr = pb + 1;
-    if (!upfront || pb != p + 1) vr = s[qr];
+    if (pb != p + 1) vr = s[qr];
     while (OLD_TOMB(vr)) { qr++; vr = s[qr]; }
     const bool has_r = vr != SYM_SEP;
     const u32 right = has_r ? (u32)ORIG(vr) : 0;
@@ -331,9 +316,8 @@ __device__ __noinline__ void apply_site(u32 p, i64 c, u32 a, u32 b, u32 nw, int 
     const u64 k0 = ((u64)left << 32) | a, k1 = ((u64)left << 32) | nw, k2 = ((u64)b << 32) | right, k3 = ((u64)nw << 32) | right;
     const u64 s0 = pair_hash(k0) & mask, s1 = pair_hash(k1) & mask, s2 = pair_hash(k2) & mask, s3 = pair_hash(k3) & mask;
     u64 v0 = 0, v1 = 0, v2 = 0, v3 = 0;
-    const bool cas_first = (MG_OPT & 2u) != 0;
-    if (has_l) { v0 = cM.pkey[s0]; v1 = cas_first ? atomicCAS(&cM.pkey[s1], PAIR_EMPTY, k1) : cM.pkey[s1]; }
-    if (has_r) { v2 = cM.pkey[s2]; v3 = cas_first ? atomicCAS(&cM.pkey[s3], PAIR_EMPTY, k3) : cM.pkey[s3]; }
+    if (has_l) { v0 = cM.pkey[s0]; v1 = atomicCAS(&cM.pkey[s1], PAIR_EMPTY, k1); }
+    if (has_r) { v2 = cM.pkey[s2]; v3 = atomicCAS(&cM.pkey[s3], PAIR_EMPTY, k3); }
     // index records of the two new pairs: one atomic per group of threads that arrive here together
     const u32 n_rec = (u32)has_l + (u32)has_r;
     u64 li = 0;
@@ -350,7 +334,6 @@ __device__ __noinline__ void apply_site(u32 p, i64 c, u32 a, u32 b, u32 nw, int 
     const bool log_ok = li + n_rec <= cM.log_cap;
     if (!log_ok) cM.ctr[3] = 2;
     s[p] = inw; s[pb] = dead_now;                                          // merge_subwords: positions never move
-#if MG_OPT & 32u
     if (log_ok) {
         if (has_l) { store_rec(&cM.log[li], left, pos_l, c); li++; }        // (left, nw) at the position of `left`
         if (has_r) store_rec(&cM.log[li], 0x80000000u | right, p, c);       // (nw, right) at p
@@ -361,7 +344,7 @@ __device__ __noinline__ void apply_site(u32 p, i64 c, u32 a, u32 b, u32 nw, int 
     {
         u64 kk[4] = {k0, k1, k2, k3}, ss[4] = {s0, s1, s2, s3}, vv[4] = {v0, v1, v2, v3};
         const i64 dd[4] = {-c, c, -c, c};
-        u32 cas = cas_first ? 0xAu : 0u;
+        u32 cas = 0xAu;                                                    // keys 1 and 3 start with a claiming CAS
         u32 pend = (has_l ? 3u : 0u) | (has_r ? 12u : 0u);
         for (u64 probes = 0; pend && probes <= cM.pcap; probes++) {
 #pragma unroll
@@ -389,19 +372,6 @@ __device__ __noinline__ void apply_site(u32 p, i64 c, u32 a, u32 b, u32 nw, int 
         }
         if (pend) cM.ctr[3] = 1;                                           // table full
     }
-#else
-    if (has_l) {
-        pair_add_probe<false>(k0, -c, s0, v0);
-        if (cas_first) pair_add_probe<true>(k1, c, s1, v1); else pair_add_probe<false>(k1, c, s1, v1);
-        if (log_ok) store_rec(&cM.log[li], left, pos_l, c);                 // (left, nw) at the position of `left`
-        li++;
-    }
-    if (has_r) {
-        pair_add_probe<false>(k2, -c, s2, v2);
-        if (cas_first) pair_add_probe<true>(k3, c, s3, v3); else pair_add_probe<false>(k3, c, s3, v3);
-        if (log_ok) store_rec(&cM.log[li], 0x80000000u | right, p, c);      // (nw, right) at p
-    }
-#endif
     PROF_ADD(6, 1);
 #undef ORIG
 #undef WAS_LIVE
@@ -567,23 +537,22 @@ __device__ __forceinline__ void apply_winner(int step, u32 a, u32 b, u32 nw, u64
 }
 
 // ---- grid-wide synchronisation of k_merge_loop (all CTAs are co-resident: cooperative launch) ------------------------
-// Two primitives, both without a hot counter: every CTA owns a slot, warp 0 of every CTA polls all slots.
-//  * grid_barrier: a dense array of 32-bit epochs (148 x 4 B = five sectors per poll).
-//  * grid_gather:  barrier + all-gather of the per-CTA arg-max candidates in one step.  A slot is eight 64-bit words
-//    {32 payload bits, 32-bit epoch tag} (the layout of NCCL's LL protocol): a word whose tag equals the epoch carries
-//    valid payload, so the poll that sees the last CTA arrive already holds its candidate -- no flag-then-data round trip.
-// Ordering: the publisher fences before its relaxed stores, the pollers fence after the poll (fence-fence synchronisation
-// at gpu scope); the CTA barriers on both sides extend it to the other warps.
+// Counter barrier: every CTA adds 1 to one global counter with release semantics and ONE lane polls that word with acquire
+// loads until it reaches (barriers so far) x (CTAs).  Measured against the alternatives at 11 GB (same box): per-CTA flags
+// polled by a warp 514 ms (five acquire loads per lane per poll, 148 pollers), cooperative_groups::grid.sync 581 ms,
+// fence + relaxed stores / polls 580 ms, this 481 ms.
+//  * grid_barrier: the barrier alone.
+//  * grid_gather:  barrier + all-gather of the per-CTA arg-max candidates: a CTA stores its candidate in its slot before it
+//    arrives; after the barrier warp 0 loads all slots and reduces them, so every CTA derives the same winner.  (An LL-style
+//    slot -- every 64-bit word tagged with the epoch, no barrier-then-data round trip -- was slower: 649 against 541 ms.)
+// Slot of a CTA: w[0..3] candidate, w[6..7] index range of that candidate (epoch-tagged words, written during the gather).
 struct __align__(64) BarSlot { u64 w[8]; };
+#define MG_MAX_CTAS 160u
 __device__ __forceinline__ void st_relaxed_v2(u64 *p, u64 a, u64 b) { asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory"); }
 __device__ __forceinline__ void ld_relaxed_v2(const u64 *p, u64 &a, u64 &b) { asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory"); }
-__device__ __forceinline__ void st_relaxed_u32(u32 *p, u32 v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ u32 ld_relaxed_u32(const u32 *p) { u32 v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
-__device__ __forceinline__ void st_release_u32(u32 *p, u32 v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ u32 ld_acquire_u32(const u32 *p) { u32 v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
-#define MG_MAX_CTAS 160u
 __device__ __forceinline__ void red_release_add_u32(u32 *p, u32 v) { asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-// counter barrier (MG_OPT & 64): every CTA adds 1 with release semantics, lane 0 polls the one word with acquire loads
+// warp 0 only; the CTA barriers around it extend the ordering to the other warps
 __device__ __forceinline__ void counter_arrive_wait(u32 *counter, u32 target) {
     if (threadIdx.x == 0) {
         red_release_add_u32(counter, 1u);
@@ -592,83 +561,15 @@ __device__ __forceinline__ void counter_arrive_wait(u32 *counter, u32 target) {
     __syncwarp();
 }
 // Called by all threads of the CTA.
-__device__ __forceinline__ void grid_barrier(u32 *flags, u32 G, u32 epoch, u64 *tp = nullptr) {
+__device__ __forceinline__ void grid_barrier(u32 *counter, u32 G, u32 epoch, u64 *tp = nullptr) {
     __syncthreads();
 #ifdef BPE_MERGE_PROFILE
     if (tp && threadIdx.x == 0) tp[0] = gtime_ns();
 #endif
-    if (MG_OPT & 64u) {
-        if (threadIdx.x < 32) counter_arrive_wait(flags + MG_MAX_CTAS, epoch * G);
-    } else if (threadIdx.x < 32) {
-        const u32 lane = threadIdx.x;
-        const bool acq = (MG_OPT & 16u) != 0;
-        if (lane == 0) { if (acq) st_release_u32(&flags[blockIdx.x], epoch); else { __threadfence(); st_relaxed_u32(&flags[blockIdx.x], epoch); } }
-        bool done;
-        do {
-            done = true;
-#pragma unroll
-            for (u32 k = 0; k < MG_MAX_CTAS / 32; k++) {                  // (a fast CTA may already be at the next barrier)
-                const u32 i = lane + 32 * k;
-                if (i < G && (int)((acq ? ld_acquire_u32(&flags[i]) : ld_relaxed_u32(&flags[i])) - epoch) < 0) done = false;
-            }
-        } while (!__all_sync(0xffffffffu, done));
-        if (!acq) __threadfence();
-    }
+    if (threadIdx.x < 32) counter_arrive_wait(counter, epoch * G);
     __syncthreads();
-}
-// Called by all threads of the CTA; `mine` is read from warp 0 (uniform).  Returns the maximum of all CTAs' candidates in
-// every lane of warp 0 (other warps: BEST_NONE).  Two gathers are always separated by a grid_barrier, so a slot never
-// holds a newer epoch than the one polled for.
-__device__ __forceinline__ Best grid_gather(BarSlot *slots, u32 G, u32 epoch, const Best &mine, u64 *tp = nullptr) {
-    __syncthreads();
-#ifdef BPE_MERGE_PROFILE
-    if (tp && threadIdx.x == 0) tp[0] = gtime_ns();
-#endif
-    Best c = BEST_NONE;
-    if (threadIdx.x < 32) {
-        const u32 lane = threadIdx.x;
-        if (lane == 0) {
-            const u64 tag = (u64)epoch << 32;
-            u64 *w = slots[blockIdx.x].w;
-            __threadfence();
-            st_relaxed_v2(w + 0, tag | (u32)mine.cnt, tag | (u32)((u64)mine.cnt >> 32));
-            st_relaxed_v2(w + 2, tag | (u32)mine.key, tag | (u32)(mine.key >> 32));
-            st_relaxed_v2(w + 4, tag | (u32)mine.ka, tag | (u32)(mine.ka >> 32));
-            st_relaxed_v2(w + 6, tag | (u32)mine.kb, tag | (u32)(mine.kb >> 32));
-        }
-        u32 pending = 0;                         // bit k: slot lane + 32 k not seen yet
-#pragma unroll
-        for (u32 k = 0; k < MG_MAX_CTAS / 32; k++) if (lane + 32 * k < G) pending |= 1u << k;
-        while (__any_sync(0xffffffffu, pending != 0)) {
-#pragma unroll
-            for (u32 k = 0; k < MG_MAX_CTAS / 32; k++) {
-                if (!((pending >> k) & 1u)) continue;
-                const u64 *w = slots[lane + 32 * k].w;
-                u64 x[8];
-                ld_relaxed_v2(w + 0, x[0], x[1]); ld_relaxed_v2(w + 2, x[2], x[3]);
-                ld_relaxed_v2(w + 4, x[4], x[5]); ld_relaxed_v2(w + 6, x[6], x[7]);
-                bool ok = true;
-#pragma unroll
-                for (u32 j = 0; j < 8; j++) ok = ok && (u32)(x[j] >> 32) == epoch;
-                if (!ok) continue;
-                pending &= ~(1u << k);
-                Best o;
-                o.cnt = (i64)((x[0] & 0xffffffffull) | (x[1] << 32)); o.key = (x[2] & 0xffffffffull) | (x[3] << 32);
-                o.ka = (x[4] & 0xffffffffull) | (x[5] << 32); o.kb = (x[6] & 0xffffffffull) | (x[7] << 32);
-                if (o.cnt != CNT_DEAD && best_greater(o, c)) c = o;
-            }
-        }
-        __threadfence();
-        c = warp_best(c);
-    }
-    __syncthreads();
-#ifdef BPE_MERGE_PROFILE
-    if (tp && threadIdx.x == 0) tp[1] = gtime_ns();
-#endif
-    return c;
 }
 
-// Flag-then-data variant: slot = {candidate (w[0..3]), epoch (w[4])}.
 // While warp 0 waits in the gather, warp 1 looks up the index range of this CTA's OWN candidate and publishes it in the
 // spare words of its slot, tagged with the epoch (each 64-bit word carries a tag, so a torn or stale read is detected and
 // the reader falls back to winner_range); it also pulls the first records of that range and the symbols they point at
@@ -683,7 +584,7 @@ __device__ __forceinline__ void gather_side_work(BarSlot *slots, u32 epoch, cons
     u64 r[3] = {0, 0, 0};
     if (lane == 0) {
         winner_range(cand.key, r);
-        if (threadIdx.x == 32 && r[0] < (1ull << 40) && r[1] < (1ull << 40))
+        if (r[0] < (1ull << 40) && r[1] < (1ull << 40))
             st_relaxed_v2(&slots[blockIdx.x].w[6], r[0] | RANGE_TAG0(epoch), r[1] | (r[2] << 40) | RANGE_TAG1(epoch));
     }
     const u64 lo = __shfl_sync(0xffffffffu, r[0], 0), hi = __shfl_sync(0xffffffffu, r[1], 0);
@@ -691,43 +592,28 @@ __device__ __forceinline__ void gather_side_work(BarSlot *slots, u32 epoch, cons
     const Rec *src = T_SRC(code);
     const bool filter = T >= 256;
     const u32 want = b >= a ? a : (0x80000000u | b);
-    const u64 i = lo + (threadIdx.x - 32);        // warps 1.. take 32 records each
+    const u64 i = lo + lane;
     if (i < hi) {
         const Rec rec = load_rec(&src[i]);
         if (!filter || rec.x == want) asm volatile("prefetch.global.L2 [%0];" ::"l"(&cM.W.sym[rec.pos]));
     }
 }
 
-// `sup` (lanes of warp 0): index of the CTA whose candidate won.
-__device__ __forceinline__ Best grid_gather_flag(BarSlot *slots, u32 *gcounter, u32 G, u32 epoch, const Best &mine, bool relaxed, u32 &sup,
-                                                 const Best *s_cand, int step, u64 *tp = nullptr) {
+// Called by all threads of the CTA; `mine` is read from lane 0 of warp 0, *s_cand is the same candidate in shared memory
+// (for warp 1).  Returns the maximum of all CTAs' candidates in every lane of warp 0 (other warps: BEST_NONE) and, in `sup`,
+// the index of the CTA that supplied it.
+__device__ __forceinline__ Best grid_gather(BarSlot *slots, u32 *counter, u32 G, u32 epoch, const Best &mine, u32 &sup,
+                                            const Best *s_cand, int step, u64 *tp = nullptr) {
     __syncthreads();
-    if ((MG_OPT & 256u) && threadIdx.x >= 32 && threadIdx.x < ((MG_OPT & 512u) ? 160 : 64)) gather_side_work(slots, epoch, *s_cand, step);
+    if (threadIdx.x >= 32 && threadIdx.x < 64) gather_side_work(slots, epoch, *s_cand, step);
 #ifdef BPE_MERGE_PROFILE
     if (tp && threadIdx.x == 0) tp[0] = gtime_ns();
 #endif
     Best c = BEST_NONE;
     if (threadIdx.x < 32) {
         const u32 lane = threadIdx.x;
-        if (lane == 0) {
-            store_best(reinterpret_cast<Best *>(slots[blockIdx.x].w), mine);
-            if (!(MG_OPT & 64u)) st_release_u32(reinterpret_cast<u32 *>(&slots[blockIdx.x].w[4]), epoch);
-        }
-        if (MG_OPT & 64u) counter_arrive_wait(gcounter, epoch * G);
-        bool done;
-        if (!(MG_OPT & 64u)) do {
-            done = true;
-#pragma unroll
-            for (u32 k = 0; k < MG_MAX_CTAS / 32; k++) {
-                const u32 i = lane + 32 * k;
-                if (i < G) {
-                    const u32 *f = reinterpret_cast<const u32 *>(&slots[i].w[4]);
-                    const u32 e = relaxed ? ld_relaxed_u32(f) : ld_acquire_u32(f);
-                    if (e != epoch) done = false;
-                }
-            }
-        } while (!__all_sync(0xffffffffu, done));
-        if (relaxed) __threadfence();
+        if (lane == 0) store_best(reinterpret_cast<Best *>(slots[blockIdx.x].w), mine);
+        counter_arrive_wait(counter, epoch * G);
         Best o5[MG_MAX_CTAS / 32];
 #pragma unroll
         for (u32 k = 0; k < MG_MAX_CTAS / 32; k++) { const u32 i = lane + 32 * k; o5[k] = i < G ? load_best(reinterpret_cast<const Best *>(slots[i].w)) : BEST_NONE; }
@@ -848,7 +734,7 @@ __global__ void __launch_bounds__(MG_NT) k_merge_loop() {
         __syncthreads();
         if (s_status[0]) break;
         if (s_status[1] * 2 > cM.pcap) {         // table over half full: hand back to the host to grow it
-            grid_barrier(cM.bar_flags, G, ++epoch);
+            grid_barrier(cM.bar_ctr, G, ++epoch);
             if (blockIdx.x == 0 && tid == 0) { cM.ctr[6] = prev_key; cM.ctr[3] = MG_NEED_GROW; }
             return;
         }
@@ -896,14 +782,13 @@ __global__ void __launch_bounds__(MG_NT) k_merge_loop() {
         u32 sup = 0xFFFFFFFFu;
         if (warp == 0 && lane == 0) s_cand = cta_cand;
         ++gepoch;
-        Best gw = (MG_OPT & 1u) ? grid_gather(cM.bar, G, gepoch, cta_cand, ctp ? ctp + 1 : nullptr)
-                              : grid_gather_flag(cM.bar, cM.bar_flags + MG_MAX_CTAS + 32, G, gepoch, cta_cand, (MG_OPT & 8u) != 0, sup, &s_cand, step, ctp ? ctp + 1 : nullptr);
+        Best gw = grid_gather(cM.bar, cM.bar_ctr + 32, G, gepoch, cta_cand, sup, &s_cand, step, ctp ? ctp + 1 : nullptr);
         u64 t2 = prof_thread ? gtime_ns() : 0;
         if (warp == 0 && lane == 0) {
             s_win = gw;
             if (gw.cnt != CNT_DEAD) {            // index range of the winner, read once per CTA: published by its supplier, or looked up
                 bool have = false;
-                if ((MG_OPT & 256u) && sup != 0xFFFFFFFFu) {
+                if (sup != 0xFFFFFFFFu) {
                     u64 w6, w7;
                     ld_relaxed_v2(&cM.bar[sup].w[6], w6, w7);
                     if ((w6 & (0xFFFFFFull << 40)) == RANGE_TAG0(gepoch) && (w7 & (0x3FFFFFull << 42)) == RANGE_TAG1(gepoch)) {
@@ -925,24 +810,24 @@ __global__ void __launch_bounds__(MG_NT) k_merge_loop() {
         // Records are dealt to the warps of all apply CTAs R at a time, R as small as one pass over the slice allows (but not
         // below cM.opt): a step with a few hundred occurrences runs a few lanes on every SM instead of sixteen full warps on
         // one SM, with less divergence between the sites that share a warp.
-        else if (MG_OPT & 128u) {
+        else {
             const u64 n_rec = r_hi - r_lo, aw = (u64)apply_ctas * warps_per_cta;
             u32 R = 32;
             while (R > cM.opt && n_rec <= aw * (R >> 1)) R >>= 1;
             if (lane < R) apply_winner(step, a, b, nw, r_lo, r_hi, T_SRC(s_range[2]), ((u64)warp * apply_ctas + blockIdx.x) * R + lane, aw * R);
-        } else apply_winner(step, a, b, nw, r_lo, r_hi, T_SRC(s_range[2]), (u64)blockIdx.x * MG_NT + tid, (u64)apply_ctas * MG_NT);
+        }
         prev_key = win.key;
         n_tok++;
         u64 t3 = prof_thread ? gtime_ns() : 0;
         u64 tp2[2];
-        grid_barrier(cM.bar_flags, G, ++epoch, ctp ? tp2 : nullptr);
+        grid_barrier(cM.bar_ctr, G, ++epoch, ctp ? tp2 : nullptr);
         if (ctp && tid == 0) ctp[3] = tp2[0];
         if ((r_hi - r_lo) * 2 >= SORT_MIN) {     // heuristic: about two records per index entry visited
             const u64 lb = *((volatile u64 *)&cM.log_begin[step]), cur = *((volatile u64 *)&cM.ctr[0]);
             const u64 pool = *((volatile u64 *)&cM.ctr[9]);
             if (cur - lb >= SORT_MIN && cur <= cM.log_cap && pool + SORT_MAX_BK + 1 <= cM.bk_off_cap) {
                 sort_slice(step, lb, (u32)(cur - lb), n_sorts & 1u, blockIdx.x == 0, (u64)blockIdx.x * MG_NT + tid, (u64)G * MG_NT, s_scan,
-                           [&]() { grid_barrier(cM.bar_flags, G, ++epoch); });
+                           [&]() { grid_barrier(cM.bar_ctr, G, ++epoch); });
                 n_sorts++;
             }
         }

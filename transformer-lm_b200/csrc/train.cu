@@ -405,10 +405,10 @@ BPE_API void bpe_debug_merge_profile(unsigned long long out[32]) { for (int i = 
 struct TrainBufs {
     DevBuf sym, wmeta, wctr;
     DevBuf dense, hist, csr_off, csr_rec;
-    DevBuf pkey, pcnt, bmax, dirty, sdirty, tok_key, prof, step_prof, merge_cnt, log, log2, bk_lg, bk_start, bk_off, bk_scratch, log_begin, tok_off, tok_len, tok_bytes, cta_best, bar, cta_prof, merges, ctr;
+    DevBuf pkey, pcnt, bmax, dirty, sdirty, tok_key, prof, step_prof, merge_cnt, log, log2, bk_lg, bk_start, bk_off, bk_scratch, log_begin, tok_off, tok_len, tok_bytes, bar, cta_prof, merges, ctr;
     void free_all(bpe_ctx *ctx) {
         for (DevBuf *b : {&sym, &wmeta, &wctr, &dense, &hist, &csr_off, &csr_rec, &pkey, &pcnt, &bmax,
-                          &dirty, &sdirty, &tok_key, &prof, &step_prof, &merge_cnt, &log, &log2, &bk_lg, &bk_start, &bk_off, &bk_scratch, &log_begin, &tok_off, &tok_len, &tok_bytes, &cta_best, &bar, &cta_prof, &merges, &ctr})
+                          &dirty, &sdirty, &tok_key, &prof, &step_prof, &merge_cnt, &log, &log2, &bk_lg, &bk_start, &bk_off, &bk_scratch, &log_begin, &tok_off, &tok_len, &tok_bytes, &bar, &cta_prof, &merges, &ctr})
             bpe_buf_free(ctx, *b);
     }
 };
@@ -883,11 +883,9 @@ static int run_merges(bpe_ctx *ctx, const uint8_t *sp_blob, const u32 *sp_offs, 
         CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_merge_loop, MG_NT, MG_DYN_SMEM));
         if (per_sm < 1) return bpe_set_error(ctx, BPE_ERR_CUDA, "merge kernel does not fit on an SM");
     }
-    BPE_TRY(alloc_exact(ctx, B.cta_best, (u64)ctx->sm_count * CTA_BEST_STRIDE * sizeof(Best)));
-    M.cta_best = (Best *)B.cta_best.p;
-    const u64 bar_bytes = (u64)MG_MAX_CTAS * sizeof(BarSlot) + (u64)MG_MAX_CTAS * 4 + 512;   // gather slots, barrier epochs, two counters
+    const u64 bar_bytes = (u64)MG_MAX_CTAS * sizeof(BarSlot) + 512;   // gather slots, two counters
     BPE_TRY(alloc_exact(ctx, B.bar, bar_bytes));
-    M.bar = (BarSlot *)B.bar.p; M.bar_flags = (u32 *)(M.bar + MG_MAX_CTAS);
+    M.bar = (BarSlot *)B.bar.p; M.bar_ctr = (u32 *)(M.bar + MG_MAX_CTAS);
     u64 ctr[8] = {0};
     u64 keys_created = 0;
     // Two kernels run the same loop: k_merge_loop (grid-wide, cooperative) and k_merge_tail (one thread-block cluster:
