@@ -473,7 +473,7 @@ def run_b200(args):
                        "parallelism": "1 GPU" if world == 1 else "%d ranks, shards cut at <|endoftext|>, no data collective" % world},
             "stages_ms": {k: round(eavg(k), 3) for k in ("ms_h2d", "ms_pretok", "ms_lookup", "ms_bpe", "ms_emit", "ms_total")},
             "new_unique_pretokens": int(eavg("cache_new_unique")), "pretokens": int(eavg("n_pretokens")),
-            "roofline": {"bound": "hbm", "kernel": "whole encode pipeline (flags, lookup, bpe, count+scan, emit); slowest stage: " + dom,
+            "roofline": {"bound": "hbm", "kernel": "whole encode pipeline (flags, lookup, bpe, fused scan+emit); slowest stage: " + dom,
                          "achieved": round(alg / 1e9 / (ems_dev / 1e3), 1), "peak": peak, "unit": "GB/s",
                          "frac": round(alg / 1e9 / (ems_dev / 1e3) / peak, 4), "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg, "algorithmic_bytes_definition": "N text bytes read once + 2 B per token written"},

@@ -75,3 +75,15 @@ def test_compute_fails_loudly_without_a_device():
     with pytest.raises(_lib.BpeError):
         from transformer_lm_b200.pretok import pretoken_starts
         pretoken_starts(b"hello world")
+
+
+def test_load_batch_shim_has_the_reference_signature_and_no_cpu_path():
+    # models/util.py:37-43 of the reference: load_batch(dataset, batch_size, context_length, device, generator=None)
+    import inspect
+    import numpy as np
+    from models.util import load_batch
+    from transformer_lm_b200 import _lib
+    params = list(inspect.signature(load_batch).parameters)
+    assert params[:5] == ["dataset", "batch_size", "context_length", "device", "generator"]
+    with pytest.raises(_lib.BpeError):          # the gather runs on a B200 or not at all
+        load_batch(np.arange(100, dtype=np.uint16), 2, 8, "cpu")

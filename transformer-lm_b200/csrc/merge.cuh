@@ -577,7 +577,7 @@ __device__ __forceinline__ void grid_barrier(u32 *counter, u32 G, u32 epoch, u64
 #define RANGE_TAG0(e) ((u64)((e) & 0xFFFFFFu) << 40)
 #define RANGE_TAG1(e) ((u64)((e) & 0x3FFFFFu) << 42)
 __device__ __forceinline__ void gather_side_work(BarSlot *slots, u32 epoch, const Best &cand, int step) {
-    if (cand.cnt == CNT_DEAD) return;
+    if (cand.cnt == CNT_DEAD || epoch >= (1u << 22)) return;   // (the tags are 22 bits: no publishing beyond 4 M steps of one launch)
     const u32 lane = lane_id();
     const u32 a = (u32)(cand.key >> 32), b = (u32)cand.key, T = a > b ? a : b;
     if (T >= 256 && (int)(T - 256) + 1 >= step) return;      // log_begin[step] is being written by CTA 0 right now: not visible yet
@@ -788,7 +788,7 @@ __global__ void __launch_bounds__(MG_NT) k_merge_loop() {
             s_win = gw;
             if (gw.cnt != CNT_DEAD) {            // index range of the winner, read once per CTA: published by its supplier, or looked up
                 bool have = false;
-                if (sup != 0xFFFFFFFFu) {
+                if (sup != 0xFFFFFFFFu && gepoch < (1u << 22)) {
                     u64 w6, w7;
                     ld_relaxed_v2(&cM.bar[sup].w[6], w6, w7);
                     if ((w6 & (0xFFFFFFull << 40)) == RANGE_TAG0(gepoch) && (w7 & (0x3FFFFFull << 42)) == RANGE_TAG1(gepoch)) {
