@@ -356,7 +356,7 @@ def run_b200(args):
             "bound": "hbm", "kernel": "k_merge_loop (one persistent cooperative launch, %d merges)" % len(merges),
             "achieved": round(ach_merge, 1), "peak": peak, "unit": "GB/s", "frac": round(ach_merge / peak, 4), "traffic": traffic,
             "traffic_source": traffic_src,
-            "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_merge,
+            "peak_source": peak_src, "frac_of_nominal_8000_GBps": round(ach_merge / 8000.0, 4), "algorithmic_bytes_per_launch": alg_merge,
             "algorithmic_bytes_definition": "16 B x sum over merges of live pair-table keys (%d) + 8 B x index records (%d)" % (st["sum_live_pairs"], st["log_records"]),
             "share_of_step": round(merge_ms / ms_dev, 4) if ms_dev else None,
             "us_per_merge": round(1e3 * merge_ms / max(len(merges), 1), 3),
