@@ -438,6 +438,7 @@ __device__ __forceinline__ u32 value_count(u64 v) {
 #define SE_NT 256
 #define SE_ITEMS 8
 #define SE_TILE (SE_NT * SE_ITEMS)
+#define SE_STAGE 6144u                           // ids staged per tile (24 KB); OWT-shape text averages ~2 900 per tile
 #define SE_AGG (1ull << 62)
 #define SE_INCL (2ull << 62)
 #define SE_VAL(x) ((x) & ((1ull << 62) - 1))
@@ -498,7 +499,30 @@ __global__ void __launch_bounds__(SE_NT) k_enc_scan_emit(EncTables t, u64 *__res
     }
     __syncthreads();
     if (!kEmit) return;
-    u64 dst = out_base + s_prefix + ex;
+    // A thread owns SE_ITEMS consecutive pretokens, i.e. ~11 consecutive ids: written straight to global memory, the 32 lanes
+    // of a store instruction would hit ~22 different sectors with 2 bytes each.  The ids of the tile are staged in shared
+    // memory instead and copied out with consecutive threads on consecutive ids (tiles with more ids than the stage holds
+    // -- long pool-resident values -- take the direct path).
+    __shared__ u32 s_ids[SE_STAGE];
+    const u64 tile_dst = out_base + s_prefix;
+    if (tot <= SE_STAGE) {
+        u32 o = ex;
+#pragma unroll
+        for (u32 k = 0; k < SE_ITEMS; k++) {
+            const u32 tag = VAL_TAG(v[k]);
+            if (tag <= 3) {
+                for (u32 q = 0; q < tag; q++) s_ids[o++] = (u32)((v[k] >> (20 * q)) & 0xFFFFFu);
+            } else if (tag == VAL_EXT) {
+                const u32 *src = t.ipool + ((v[k] >> 24) & 0xFFFFFFFFFull);
+                const u32 c = (u32)(v[k] & 0xFFFFFFu);
+                for (u32 q = 0; q < c; q++) s_ids[o++] = src[q];
+            }
+        }
+        __syncthreads();
+        for (u32 j = threadIdx.x; j < tot; j += SE_NT) { const u64 d = tile_dst + j; if (d < cap) out[d] = (OutT)s_ids[j]; }
+        return;
+    }
+    u64 dst = tile_dst + ex;
 #pragma unroll
     for (u32 k = 0; k < SE_ITEMS; k++) {
         const u32 tag = VAL_TAG(v[k]);
