@@ -111,7 +111,7 @@ struct MergeState {
     // profile (ns / counts): [0]=phase1 [1]=sync1 [2]=apply [3]=sync2 on CTA 0; [4]=token CTA work; [5]=index records scanned;
     // [6]=words rewritten; [7]=steps; [9]=dirty blocks rescanned
     u64 *prof;
-    u32 opt;          // smallest number of records dealt to a warp per pass of the apply phase (BPE_MERGE_MINREC)
+    u32 min_rec;      // smallest number of records dealt to a warp per pass of the apply phase (BPE_MERGE_MINREC)
     u64 *cta_prof;    // optional (profile builds): per step and CTA {start, arrive1, exit1, arrive2}
     u32 *step_prof;   // optional per-step trace: 4 x u32 per step (phase1+sync1 ns, apply+sync2 ns, records scanned, words rewritten so far)
 };
@@ -808,12 +808,12 @@ __global__ void __launch_bounds__(MG_NT) k_merge_loop() {
 
         if (token_cta) token_bookkeeping(step, win, a, b, nw, prof_thread, t2);
         // Records are dealt to the warps of all apply CTAs R at a time, R as small as one pass over the slice allows (but not
-        // below cM.opt): a step with a few hundred occurrences runs a few lanes on every SM instead of sixteen full warps on
+        // below cM.min_rec): a step with a few hundred occurrences runs a few lanes on every SM instead of sixteen full warps on
         // one SM, with less divergence between the sites that share a warp.
         else {
             const u64 n_rec = r_hi - r_lo, aw = (u64)apply_ctas * warps_per_cta;
             u32 R = 32;
-            while (R > cM.opt && n_rec <= aw * (R >> 1)) R >>= 1;
+            while (R > cM.min_rec && n_rec <= aw * (R >> 1)) R >>= 1;
             if (lane < R) apply_winner(step, a, b, nw, r_lo, r_hi, T_SRC(s_range[2]), ((u64)warp * apply_ctas + blockIdx.x) * R + lane, aw * R);
         }
         prev_key = win.key;
