@@ -142,6 +142,10 @@ int bpe_count_pair_table(bpe_ctx *ctx, const uint8_t *specials_blob, const uint3
 /* Merge loop over whatever has been counted/imported so far. */
 int bpe_train_from_counts(bpe_ctx *ctx, const uint8_t *specials_blob, const uint32_t *special_offs, int n_specials,
                           int n_merges, int32_t *merge_pairs_out, int *n_done, bpe_train_stats *stats);
+/* The dense 256 x 256 byte-pair table (calculate_byte_pair_frequencies over single bytes, train.py:35-49) that the last
+ * bpe_train / bpe_train_dev / bpe_train_from_counts call on this context built before its first merge: the multi-GPU path
+ * checks it against the all-reduced per-rank tables of bpe_count_pair_table without building the table a second time. */
+int bpe_last_pair_table(bpe_ctx *ctx, int64_t *dense_out /* [65536] */);
 
 /* ---- tokenizer ----------------------------------------------------------------------------- */
 /* Replaces Tokenizer.__init__ table building: models/tokenizer/tokenizer.py:12-38 and the per-call

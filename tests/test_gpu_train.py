@@ -247,3 +247,23 @@ def test_streamed_file_ingest_equals_in_memory(tmp_path, monkeypatch):
     host2.tofile(path)
     with pytest.raises(UnicodeDecodeError):
         run_train_bpe(path, 500, [])
+
+
+def test_finish_checks_the_expected_pair_table():
+    # multi-GPU linearity check: the all-reduced per-rank pair tables are compared with the table the merge phase builds
+    import torch
+    from transformer_lm_b200 import sharded
+    data = (FIXTURES_PATH / "corpus.en").read_bytes()
+    c = sharded.DeviceCounter()
+    assert c.add(data, 0, len(data), True, True) is None
+    good = c.pair_table(["<|endoftext|>"])
+    c.expect_pair_table(good)
+    vocab, merges = c.finish(500, ["<|endoftext|>"])
+    assert (vocab, merges) == oracle.train_bpe_on_bytes(data, 500, ["<|endoftext|>"])
+    c = sharded.DeviceCounter()
+    assert c.add(data, 0, len(data), True, True) is None
+    bad = good.clone()
+    bad[ord("t") * 256 + ord("h")] += 1
+    c.expect_pair_table(bad)
+    with pytest.raises(RuntimeError):
+        c.finish(500, ["<|endoftext|>"])

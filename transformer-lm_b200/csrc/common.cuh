@@ -51,6 +51,7 @@ struct bpe_ctx {
     uint64_t mem_limit = 0;
     std::vector<DevBuf> pool;                        // cached free device buffers
     bool saw_cr = false;                             // the last flags pass met a '\r'
+    std::vector<unsigned long long> last_dense;      // initial 256 x 256 byte-pair table of the last training call (bpe_last_pair_table)
 };
 
 int bpe_set_error(bpe_ctx *ctx, int code, const char *fmt, ...);

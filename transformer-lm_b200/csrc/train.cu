@@ -4,6 +4,7 @@
 // Reference being replaced: models/tokenizer/train.py:142-231 (see each kernel for the exact lines).
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <unordered_set>
 #include "kernels.h"
 #include "ctx.h"
@@ -759,6 +760,13 @@ BPE_API int bpe_count_pair_table(bpe_ctx *ctx, const uint8_t *specials_blob, con
     return BPE_OK;
 }
 
+BPE_API int bpe_last_pair_table(bpe_ctx *ctx, int64_t *dense_out) {
+    if (!ctx || !dense_out) return BPE_ERR_ARG;
+    if (ctx->last_dense.size() != 65536) return bpe_set_error(ctx, BPE_ERR_ARG, "bpe_last_pair_table: no training call has built a pair table on this context");
+    memcpy(dense_out, ctx->last_dense.data(), 65536 * 8);
+    return BPE_OK;
+}
+
 // ---- merge phase ---------------------------------------------------------------------------------
 static int run_merges(bpe_ctx *ctx, const uint8_t *sp_blob, const u32 *sp_offs, int n_sp, int n_merges,
                       int32_t *merge_pairs_out, int *n_done, bpe_train_stats *stats, EvTimer &tm, int ev_start) {
@@ -804,6 +812,7 @@ static int run_merges(bpe_ctx *ctx, const uint8_t *sp_blob, const u32 *sp_offs, 
     std::vector<u64> dense(65536);
     CUDA_TRY(ctx, cudaMemcpyAsync(dense.data(), B.dense.p, 65536 * 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    ctx->last_dense.assign(dense.begin(), dense.end());
 
     // pair table: sized for the keys we expect (initial pairs + a fraction of the symbols), grown x4 by
     // the host whenever the kernel reports it more than half full (all loop state lives in HBM, so the

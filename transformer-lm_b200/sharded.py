@@ -68,6 +68,7 @@ class DeviceCounter:
         self.torch = torch
         self.device = torch.device("cuda", self.ctx.device)
         self.ctx.check(self.L.bpe_count_begin(self.ctx.handle))
+        self._expected_pairs = None
 
     # returns None, or ("utf8", offset within data) / ("halo", 0) / ("newline", 0)
     def add(self, data, own_begin: int, own_end: int, at_file_start: bool, at_file_end: bool, device_ptr: int | None = None,
@@ -117,6 +118,10 @@ class DeviceCounter:
         self.ctx.check(self.L.bpe_count_pair_table(self.ctx.handle, _lib.ptr(sp_blob), _lib.ptr(sp_offs), len(special_tokens), _lib.ptr(dense)))
         return self.torch.from_numpy(dense).to(self.device)
 
+    def expect_pair_table(self, dense):
+        """Remember the all-reduced per-rank pair table; finish() compares it with the merged one."""
+        self._expected_pairs = dense
+
     def finish(self, vocab_size: int, special_tokens: List[str], return_stats: bool = False):
         """Merge loop over the merged table (bpe_train_from_counts): train.py:165-228."""
         vocab = Vocab(special_tokens=list(special_tokens))
@@ -129,6 +134,14 @@ class DeviceCounter:
                                                     _lib.ptr(pairs), C.byref(n_done), C.byref(stats)))
         if stats.duplicate_tokens:
             raise NotImplementedError("two merges produced identical token bytes (SURVEY A-6); not supported")
+        if self._expected_pairs is not None:
+            # linearity check of the sharded count: the all-reduced per-rank byte-pair tables must equal the table of the
+            # merged counts, which the merge phase has just built
+            merged = np.zeros(65536, dtype=np.int64)
+            self.ctx.check(self.L.bpe_last_pair_table(self.ctx.handle, _lib.ptr(merged)))
+            expected, self._expected_pairs = self._expected_pairs, None
+            if not np.array_equal(expected.cpu().numpy(), merged):
+                raise RuntimeError("pair-count all-reduce does not match the merged word table")
         sym = [bytes([i]) for i in range(256)]
         merges = []
         for k in range(n_done.value):
@@ -273,9 +286,12 @@ def sharded_count(counter, shards, special_tokens: List[str], group=None, verify
     if verify:
         # linearity check: the per-rank byte-pair tables must sum to the table of the merged counts
         dist.all_reduce(local_pairs, op=dist.ReduceOp.SUM, group=group)
-        merged = counter.pair_table(special_tokens)
-        if not bool((local_pairs == merged).all()):
-            raise RuntimeError("pair-count all-reduce does not match the merged word table")
+        if hasattr(counter, "expect_pair_table"):
+            counter.expect_pair_table(local_pairs)         # compared in finish(), against the table the merge phase builds anyway
+        else:
+            merged = counter.pair_table(special_tokens)
+            if not bool((local_pairs == merged).all()):
+                raise RuntimeError("pair-count all-reduce does not match the merged word table")
         _tick("verify", t0)
     return "ok"
 
