@@ -359,6 +359,31 @@ __global__ void __launch_bounds__(256) k_build_words(CountTables t, Words W, con
     }
 }
 
+// The dense byte-pair table straight from the count tables (what k_build_words + k_init_pair_counts compute, without
+// materialising the words): the per-rank table of the multi-GPU linearity check.
+__global__ void __launch_bounds__(256) k_dense_pairs(CountTables t, const uint8_t *__restrict__ sp_blob, const u32 *__restrict__ sp_offs,
+                                                    int n_sp, u64 *__restrict__ dense /* 65536 */) {
+    u64 total = t.scap + t.lcap;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (u64)gridDim.x * blockDim.x) {
+        u32 l = 0; const uint8_t *src = nullptr; uint8_t tmp[8]; u64 c = 0;
+        if (i < t.scap) {
+            u64 k = SKEY(t, i);
+            if (!k) continue;
+            l = (u32)(k >> 56);
+            for (u32 j = 0; j < l; j++) tmp[j] = (uint8_t)(k >> (8 * j));
+            src = tmp; c = SCNT(t, i);
+        } else {
+            u64 m = LMETA(t, i - t.scap);
+            if (m == META_EMPTY) continue;
+            l = (u32)(m & META_LEN_MASK); src = rep_ptr(t, m); c = LCNT(t, i - t.scap);
+        }
+        if (l < 2 || c == 0) continue;
+        if (n_sp && equals_special(src, l, sp_blob, sp_offs, n_sp)) continue;
+        u32 prev = src[0];
+        for (u32 j = 1; j < l; j++) { const u32 cur = src[j]; atomicAdd(&dense[(prev << 8) | cur], c); prev = cur; }
+    }
+}
+
 __global__ void __launch_bounds__(256) k_init_pair_counts(Words W, u64 n_words, u64 *__restrict__ dense /* 65536 */,
                                                          u32 *__restrict__ hist /* 65536 */) {
     for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += (u64)gridDim.x * blockDim.x) {
@@ -728,32 +753,16 @@ BPE_API int bpe_count_pair_table(bpe_ctx *ctx, const uint8_t *specials_blob, con
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     CountState *cs = ctx->count;
-    u64 c[8];
-    BPE_TRY(read_counters(ctx, c, 8));
-    u64 max_words = c[0] + c[1], max_syms = c[0] * SHORT_MAX + c[2];
-    if (max_syms >= (1ull << 32)) return bpe_set_error(ctx, BPE_ERR_UNSUPPORTED, "more than 2^32 symbols in unique words");
     const uint8_t *spb; const u32 *spo; u32 spmax;
     BPE_TRY(ctx_upload_specials(ctx, specials_blob, special_offs, n_specials, &spb, &spo, &spmax));
-    DevBuf sym, wmeta, wctr, dense, hist;
-    struct G { bpe_ctx *c; DevBuf *b[5]; ~G() { for (auto x : b) bpe_buf_free(c, *x); } } g{ctx, {&sym, &wmeta, &wctr, &dense, &hist}};
-    const u64 sym_slots = max_syms + max_words + 2 * SYM_PAD;
-    if (sym_slots >= (1ull << 32)) return bpe_set_error(ctx, BPE_ERR_UNSUPPORTED, "more than 2^32 symbols in unique words");
-    BPE_TRY(bpe_buf_reserve(ctx, sym, sym_slots * 4)); BPE_TRY(bpe_buf_reserve(ctx, wmeta, (max_words + 1) * sizeof(WordMeta)));
-    BPE_TRY(bpe_buf_reserve(ctx, wctr, 64)); BPE_TRY(bpe_buf_reserve(ctx, dense, 65536 * 8)); BPE_TRY(bpe_buf_reserve(ctx, hist, 65536 * 4));
-    CUDA_TRY(ctx, cudaMemsetAsync(sym.p, 0xFF, sym_slots * 4, st));
-    CUDA_TRY(ctx, cudaMemsetAsync(wctr.p, 0, 64, st)); CUDA_TRY(ctx, cudaMemsetAsync(dense.p, 0, 65536 * 8, st));
-    CUDA_TRY(ctx, cudaMemsetAsync(hist.p, 0, 65536 * 4, st));
-    Words W{(int32_t *)sym.p, (WordMeta *)wmeta.p, (u64 *)wctr.p};
+    DevBuf dense;
+    struct G { bpe_ctx *c; DevBuf *b; ~G() { bpe_buf_free(c, *b); } } g{ctx, &dense};
+    BPE_TRY(bpe_buf_reserve(ctx, dense, 65536 * 8));
+    CUDA_TRY(ctx, cudaMemsetAsync(dense.p, 0, 65536 * 8, st));
     CountTables t = count_tables(ctx);
     u64 total = cs->scap + cs->lcap;
     unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (total + 255) / 256);
-    KLAUNCH(k_build_words, grid, 256, 0, st, t, W, spb, spo, n_specials);
-    u64 *host = (u64 *)ctx->pinned;
-    CUDA_TRY(ctx, cudaMemcpyAsync(host, wctr.p, 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(ctx, cudaStreamSynchronize(st));
-    u64 n_words = host[0];
-    unsigned wgrid = (unsigned)std::max<u64>(1, std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (n_words + 255) / 256));
-    KLAUNCH(k_init_pair_counts, wgrid, 256, 0, st, W, n_words, (u64 *)dense.p, (u32 *)hist.p);
+    KLAUNCH(k_dense_pairs, grid, 256, 0, st, t, spb, spo, n_specials, (u64 *)dense.p);
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaMemcpyAsync(dense_out, dense.p, 65536 * 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
