@@ -17,3 +17,10 @@ def run_train_bpe(input_path: str | os.PathLike, vocab_size: int, special_tokens
 
     vocab, merges = train_bpe(input_path, vocab_size, special_tokens)
     return vocab, merges
+
+
+def run_get_batch(dataset, batch_size: int, context_length: int, device: str):
+    """tests/adapters.py:398-424 of the reference."""
+    from models.util import load_batch
+
+    return load_batch(dataset, batch_size, context_length, device)

@@ -94,3 +94,25 @@ def test_decode_batch_matches_decode():
     with pytest.raises(KeyError) as ei:
         tok.decode_batch([[1, 2], [3, 999999]])
     assert ei.value.args == (999999,)
+
+
+def test_get_batch_like_the_reference_test():
+    # tests/test_data.py:11-60 of the reference, on the GPU: shapes, y = x + 1 on an arange dataset, start indices cover
+    # [0, len - context) uniformly (mean +/- 5 sigma)
+    import math
+    from collections import Counter
+    from tests.adapters import run_get_batch
+    dataset = np.arange(0, 100)
+    context_length, batch_size, num_iters = 7, 32, 1000
+    starting_indices = Counter()
+    for _ in range(num_iters):
+        x, y = run_get_batch(dataset=dataset, batch_size=batch_size, context_length=context_length, device="cuda:0")
+        assert x.shape == (batch_size, context_length) and y.shape == (batch_size, context_length)
+        assert torch.equal(x + 1, y)
+        starting_indices.update(x[:, 0].tolist())
+    n_starts = len(dataset) - context_length
+    assert max(starting_indices) == n_starts - 1 and min(starting_indices) == 0
+    expected = (num_iters * batch_size) / n_starts
+    sigma = math.sqrt((num_iters * batch_size) * (1 / n_starts) * (1 - (1 / n_starts)))
+    for count in starting_indices.values():
+        assert expected - 5 * sigma < count < expected + 5 * sigma
