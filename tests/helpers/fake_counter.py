@@ -67,3 +67,15 @@ class OracleCounter:
             for a, b in zip(w, w[1:]):
                 dense[a * 256 + b] += c
         return torch.from_numpy(dense)
+
+
+class DeferredCheckCounter(OracleCounter):
+    """Like DeviceCounter: takes the all-reduced pair table and checks it later (DeviceCounter.finish does that against the
+    table the merge phase builds)."""
+
+    def __init__(self):
+        super().__init__()
+        self.expected = None
+
+    def expect_pair_table(self, dense):
+        self.expected = dense

@@ -30,12 +30,14 @@ def _worker(rank, world, port, scenarios, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from tests.helpers.fake_counter import OracleCounter
+        from tests.helpers.fake_counter import DeferredCheckCounter, OracleCounter
         for name, data, specials, halo in scenarios:
             sharded.HALO_RIGHT = halo
-            counter = OracleCounter()
+            counter = DeferredCheckCounter() if name.startswith("deferred") else OracleCounter()
             try:
                 out = sharded.sharded_count(counter, sharded.FileShards(lambda lo, hi: data[lo:hi], len(data)), specials, None, True)
+                if name.startswith("deferred"):    # the all-reduced per-rank tables were handed over instead of compared at once
+                    assert counter.expected is not None and bool((counter.expected == counter.pair_table(specials)).all())
                 q.put((name, rank, out, dict(counter.table), counter.adds))
             except UnicodeDecodeError as e:
                 q.put((name, rank, "utf8", (e.start, e.reason), 0))
@@ -159,3 +161,11 @@ def test_merges_digest_is_order_sensitive():
     a = [(b"a", b"b"), (b"ab", b"c")]
     assert sharded.merges_digest(a) != sharded.merges_digest(a[::-1])
     assert sharded.merges_digest(a) == sharded.merges_digest(list(a))
+
+
+def test_deferred_linearity_check_receives_the_all_reduced_table():
+    data = _corpus()
+    res = _run_many(2, [("deferred", data, ["<|endoftext|>"], 64 << 10)])["deferred"]
+    want = _want(data)
+    for rank, out, table, adds in res:
+        assert out == "ok" and table == want
