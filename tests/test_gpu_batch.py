@@ -7,6 +7,7 @@ import torch
 
 import _bootstrap  # noqa: F401
 from models.util import load_batch
+from oracle import oracle
 from tests.adapters import get_tokenizer
 from tests.common import load_gpt2_fixture
 from transformer_lm_b200 import _lib
@@ -88,6 +89,8 @@ def test_decode_batch_matches_decode():
     seqs = [tok.encode(t) for t in texts]
     seqs.append([8582, 247])                   # a split emoji: U+FFFD replacement per sequence (SURVEY A-17)
     seqs.append([])
+    otok = oracle.OracleTokenizer(dict(vocab), list(merges), ["<|endoftext|>"])
+    assert tok.decode_batch(seqs) == [otok.decode(s) for s in seqs]      # the oracle's b"".join(...).decode("utf-8", "replace")
     assert tok.decode_batch(seqs) == [tok.decode(s) for s in seqs]
     assert tok.decode_batch([]) == []
     assert tok.decode_batch([[], []]) == ["", ""]

@@ -117,3 +117,20 @@ def test_utf8_validation_matches_cpython():
         bytes(big).decode("utf-8")
     except UnicodeDecodeError as e:
         assert utf8_validate(bytes(big)) == e.start
+
+
+def test_every_code_point_goes_through_the_device_class_table():
+    """Every scalar value U+0000..U+10FFFF (surrogates excluded) between an ASCII letter and a digit: the device's
+    two-level class table in shared memory (pretok.cuh cp_class_smem) against the oracle's table walk, so all 684 L
+    ranges / 146 N ranges / 25 whitespace code points are pinned on the GPU too, in all four UTF-8 lengths."""
+    cps = [cp for cp in range(0x110000) if not 0xD800 <= cp <= 0xDFFF]
+    for lo in range(0, len(cps), 1 << 18):
+        text = "".join("a" + chr(cp) + "1 " for cp in cps[lo: lo + (1 << 18)])
+        data = text.encode("utf-8")
+        got = np.asarray(_starts(data), dtype=np.int64)
+        want = np.asarray(oracle.pretokenize(data), dtype=np.int64)
+        assert got.shape == want.shape and np.array_equal(got, want), "code points %#x.." % cps[lo]
+    # and back to back without separators (class transitions between neighbouring code points)
+    text = "".join(chr(cp) for cp in cps[:: 7])
+    data = text.encode("utf-8")
+    assert _starts(data) == oracle.pretokenize(data)

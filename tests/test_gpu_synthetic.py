@@ -26,6 +26,16 @@ def test_train_on_synthetic_shapes_matches_oracle(shape, seed, mb, vocab):
     assert got[1] == want[1] and got[0] == want[0]
 
 
+@pytest.mark.parametrize("shape,seed", [("owt", 4321), ("tinystories", 1234)])
+def test_train_64MB_slice_vocab_1000_matches_oracle(shape, seed):
+    """the 64 MB prefix of each bench corpus (same generator and seed) at vocab 1000, exact vocab and merges
+    against the oracle (about 10 s of oracle time per shape)."""
+    data = synth_host(shape, seed, 64 << 20).tobytes()
+    want = oracle.train_bpe_on_bytes(data, 1000, [EOT])
+    got = _train(data, 1000, [EOT])
+    assert got[1] == want[1] and got[0] == want[0]
+
+
 @pytest.mark.parametrize("grid", ["2", "3", "17"])
 def test_merge_loop_result_does_not_depend_on_the_grid(monkeypatch, grid):
     # Small grids put many 64-block chunks on every warp: more than the shared-memory cache of block maxima holds
@@ -58,6 +68,28 @@ def test_encode_synthetic_owt_matches_oracle(owt_tokenizer):
     got = tok.encode_to_numpy(data, np.int32)
     want = otok.encode_bytes(data)
     assert got.shape == want.shape and np.array_equal(got, want)
+
+
+def test_encode_16MB_with_the_32k_vocab_matches_oracle():
+    """a 16 MB slice of the bench's encode text with a 32 000-entry vocab trained on the GPU on 1 GB of the
+    bench's train corpus (text generated in HBM), ids bit-exact against the oracle's Tokenizer.encode."""
+    import torch
+    from transformer_lm_b200 import _lib
+    from transformer_lm_b200.synth import synth_device
+    ctx = _lib.default_context()
+    n = (1 << 30) // 4096 * 4096
+    t = torch.empty(n, dtype=torch.uint8, device="cuda")
+    synth_device("owt", 4321, n, t.data_ptr(), ctx=ctx)
+    vocab, merges = _train(None, 32000, [EOT], device_ptr=t.data_ptr(), n_bytes=n)
+    del t
+    assert len(merges) == 32000 - 257
+    tok = get_tokenizer(dict(vocab), list(merges), [EOT])
+    otok = oracle.OracleTokenizer(dict(vocab), list(merges), [EOT])
+    data = synth_host("owt", 4322, 16 << 20).tobytes()
+    got = tok.encode_to_numpy(data, np.uint16)
+    want = otok.encode_bytes(data)
+    assert got.shape == want.shape and np.array_equal(got.astype(np.int64), want)
+    assert tok.decode_bytes(got.astype(np.int64)) == data
 
 
 def test_roundtrip_and_additivity_at_scale(owt_tokenizer):

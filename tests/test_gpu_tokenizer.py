@@ -351,7 +351,8 @@ def test_bulk_encode_driver_streams_a_file(tmp_path):
     src.write_bytes(raw)
     with open(src, "r", encoding="utf-8") as f:
         text = f.read()                                   # what the reference's text-mode read sees
-    want = tok.encode(text)
+    want = oracle.OracleTokenizer(dict(vocab), list(merges), [EOT]).encode(text)   # the oracle, not the GPU's own encode
+    assert tok.encode(text) == want
     for piece in (1 << 30, 70000, 9000):                  # one piece, several, many (forces carries and "\r" holds)
         dst = tmp_path / ("out_%d.bin" % piece)
         n = encode_file(tok, src, dst, np.uint16, piece_bytes=piece)
@@ -362,4 +363,4 @@ def test_bulk_encode_driver_streams_a_file(tmp_path):
     tok2 = get_tokenizer(dict(vocab), list(merges), [])
     dst = tmp_path / "out_nosp.bin"
     encode_file(tok2, src, dst, np.int32, piece_bytes=5000)
-    assert np.fromfile(dst, dtype="<i4").tolist() == tok2.encode(text)
+    assert np.fromfile(dst, dtype="<i4").tolist() == oracle.OracleTokenizer(dict(vocab), list(merges), []).encode(text)

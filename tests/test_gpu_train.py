@@ -173,23 +173,59 @@ def test_shard_reports_only_owned_utf8_errors_and_refuses_cr():
     assert c.add(long_tail, 0, 400, True, True) is None
 
 
-# ---- the two merge-loop kernels (grid-wide k_merge_loop, single-cluster k_merge_tail) must agree ---------------
-@pytest.mark.parametrize("tail_after", ["0", "1", "37", "1000000"])
-def test_merge_kernels_agree_at_any_switch_point(monkeypatch, tail_after):
-    monkeypatch.setenv("BPE_TAIL_AFTER", tail_after)
-    data = (FIXTURES_PATH / "corpus.en").read_bytes()
-    want = oracle.train_bpe_on_bytes(data, 1500, ["<|endoftext|>"])
-    got = _train_bytes(data, 1500, ["<|endoftext|>"])
-    assert got[1] == want[1] and got[0] == want[0]
-    # exhaustion phase (zero-count pairs, early stop) inside the tail kernel
+# ---- several merges per grid step (csrc/merge.cuh): the batches must be exactly the reference's sequence ----------------
+def _adjacency_corpus(seed, n_words=400, n_pairs=10):
+    """Words glued from letter pairs with distinct, well separated frequencies: the top pairs share no token, so a step
+    takes several of them, and their occurrences sit next to each other in every order (abcd, cdab, ababcd, ...)."""
+    rnd = random.Random(seed)
+    letters = "abcdefghijklmnopqrstuvwxyz"[: 2 * n_pairs]
+    pairs = [letters[2 * i: 2 * i + 2] for i in range(n_pairs)]
+    weights = [2.0 ** -(i / 2) for i in range(n_pairs)]
+    out = []
+    for _ in range(n_words):
+        pieces = []
+        for _ in range(rnd.randint(1, 6)):
+            pieces.append(rnd.choices(pairs, weights)[0] if rnd.random() < 0.85 else rnd.choice(letters))
+        out.extend(["".join(pieces)] * rnd.randint(1, 40))
+    rnd.shuffle(out)
+    return " ".join(out).encode()
+
+
+@pytest.mark.parametrize("grid", [None, "3", "17", "148"])
+def test_multi_merge_steps_match_oracle_on_adjacent_sites(monkeypatch, grid):
+    if grid:
+        monkeypatch.setenv("BPE_MERGE_G", grid)
+    batched = 0
+    for seed in range(12):
+        data = _adjacency_corpus(seed, n_pairs=6 + seed % 7)
+        want = oracle.train_bpe_on_bytes(data, 256 + 60, [])
+        vocab, merges, st = _train_bytes(data, 256 + 60, [], return_stats=True)
+        assert merges == want[1] and vocab == want[0], seed
+        batched += st["merge_steps"] < len(merges)
+    assert batched >= 6                                   # the multi-merge path really ran
+
+
+@pytest.mark.parametrize("batch", ["1", "2", "5"])
+def test_merges_do_not_depend_on_the_batch_limit(monkeypatch, batch):
+    from transformer_lm_b200.synth import synth_host
+    data = synth_host("owt", 4321, 48 << 20)
+    vocab, merges, st = _train_bytes(data, 3000, ["<|endoftext|>"], return_stats=True)
+    assert st["merge_steps"] < len(merges) // 2           # default: up to 8 merges per step
+    monkeypatch.setenv("BPE_MERGE_BATCH", batch)
+    v2, m2, st2 = _train_bytes(data, 3000, ["<|endoftext|>"], return_stats=True)
+    assert m2 == merges and v2 == vocab
+    if batch == "1":
+        assert st2["merge_steps"] == len(merges)
+    # deep into the tie-heavy tail and the zero-count exhaustion phase, against the oracle
+    small = (FIXTURES_PATH / "corpus.en").read_bytes()
+    assert _train_bytes(small, 1500, ["<|endoftext|>"]) == oracle.train_bpe_on_bytes(small, 1500, ["<|endoftext|>"])
     tiny = b"aaaa abab aaaa"
     assert _train_bytes(tiny, 300, []) == oracle.train_bpe_on_bytes(tiny, 300, [])
     fz = _fuzz_corpus(31, 3000, WORDS)
     assert _train_bytes(fz, 5000, []) == oracle.train_bpe_on_bytes(fz, 5000, [])
 
 
-def test_tail_kernel_survives_table_growth(monkeypatch):
-    monkeypatch.setenv("BPE_TAIL_AFTER", "5")
+def test_merge_loop_survives_table_growth():
     rnd = random.Random(77)
     words = ["".join(rnd.choice("abcdefghijklmnopqrstuvwxyz") for _ in range(rnd.randint(2, 9))) for _ in range(6000)]
     data = " ".join(rnd.choice(words) for _ in range(40000)).encode()
@@ -237,6 +273,14 @@ def test_streamed_file_ingest_equals_in_memory(tmp_path, monkeypatch):
     host.tofile(path)
     got = run_train_bpe(path, 1200, ["<|endoftext|>"])
     want = _train_bytes(host, 1200, ["<|endoftext|>"])
+    assert got[1] == want[1] and got[0] == want[0]
+    # the same path (four chunks with halos, reader threads, pinned staging) against the ORACLE on a file it finishes
+    monkeypatch.setattr(T, "_STREAM_MIN", 16 << 20)
+    monkeypatch.setattr(T, "_STREAM_CHUNK", 12 << 20)
+    small = synth_host("owt", 4321, 44 << 20)
+    small.tofile(path)
+    got = run_train_bpe(path, 800, ["<|endoftext|>"])
+    want = oracle.train_bpe_on_bytes(small.tobytes(), 800, ["<|endoftext|>"])
     assert got[1] == want[1] and got[0] == want[0]
     # carriage return -> one-piece path; invalid UTF-8 -> UnicodeDecodeError
     host2 = host[: 100 << 20].copy()

@@ -29,7 +29,7 @@ class BpeError(RuntimeError):
 
 class TrainStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("n_bytes", "n_pretokens", "n_unique", "n_symbols", "n_pairs_initial",
-                                          "n_pairs_final", "log_records", "duplicate_tokens", "sum_live_pairs")] + \
+                                          "n_pairs_final", "log_records", "duplicate_tokens", "sum_live_pairs", "merge_steps")] + \
                [(n, C.c_float) for n in ("ms_h2d", "ms_validate", "ms_pretok", "ms_count", "ms_build", "ms_merge", "ms_total")]
 
     def as_dict(self):

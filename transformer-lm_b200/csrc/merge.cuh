@@ -1,4 +1,4 @@
-// merge.cuh -- the BPE merge loop as one persistent cooperative kernel.
+// merge.cuh -- the BPE merge loop as one persistent cooperative kernel that applies SEVERAL merges per grid step.
 //
 // Reference: the loop at models/tokenizer/train.py:183-228:
 //     best = max(byte_pair_frequencies, key=lambda x: (byte_pair_frequencies[x], x))        187-189
@@ -8,9 +8,9 @@
 // Device data structures
 //   pair table   open addressing, key = a<<32|b, 64-bit count.  A key lives from its first touch
 //                (defaultdict semantics: counts may be 0) until it is merged (count = CNT_DEAD).
-//   argmax       every PB slots form a block with a cached maximum; an update marks its block dirty,
-//                so a step rescans only the blocks that changed.  The cached maxima of the blocks a CTA owns
-//                live in its shared memory for the whole launch (written through to bmax for the next one).
+//   argmax       every PB slots form a block with a cached maximum and an upper bound of its second-largest count; an
+//                update marks its block dirty, so a step rescans only the blocks that changed.  The cached values of the
+//                blocks a CTA owns live in its shared memory for the whole launch (written through for the next one).
 //   tie-break    (count, (bytes_a, bytes_b)) with python's bytes ordering.  Each token keeps its
 //                first 8 bytes as a big-endian integer (tok_key): comparing the integers decides
 //                almost every tie; equal prefixes fall back to lengths / a byte loop.
@@ -22,6 +22,19 @@
 //                neighbour when large).  Stale records are harmless (the symbols are re-checked, like the
 //                reference re-checks its stale index entries, train.py:196-200).  One warp per occurrence in most
 //                steps: no per-word serialisation, no divergence between sites.
+//
+// Several merges per step (the loop is latency-bound: two grid barriers and ~10 dependent memory round trips per step, whatever
+// the step does).  Every CTA reports its best TWO pairs and a bound H on the count of everything else it owns; every CTA then
+// derives the same sorted candidate list d1 >= d2 >= ... and applies the longest prefix d1..dr (r <= MG_BATCH) with
+//   (1) all 2r tokens distinct, no a == b unless r == 1,
+//   (2) count(dr) > count(d(r+1)) and count(dr) > H.
+// Why this is exactly the reference's next r merges: merge i only decrements pairs (x, a_i) and (b_i, y) and creates pairs that
+// contain its new token.  By (1) no dj is decremented by another merge of the step, and the occurrences of dj are untouched.  A new
+// pair (x, new_i) is counted at most count(x, a_i) times, and (x, a_i) is neither a d1..dr (distinct tokens) nor, by (2), a pair
+// with a count >= count(dr): so every pair created or changed during the step stays strictly below count(dr), the reference's
+// max() picks d1, .., dr in this order, and the pair it picks next is again the maximum of the table after the step.
+// Adjacent sites of different merges of a step are resolved as the reference's sequence would: a site of merge j sees the
+// occurrences of merges i < j already merged and those of merges i > j untouched (apply_site).
 #pragma once
 #include <cooperative_groups.h>
 #include <cooperative_groups/scan.h>
@@ -42,6 +55,9 @@ __device__ __forceinline__ u32 pair_hash(u64 key) {
 #define PB 64u                                   // pair-table slots per block (one rescan = two slots per lane)
 #define MG_NT 512
 #define MG_NEED_GROW 8ull                        // ctr[3] code: pair table more than half full, host must grow it
+#ifndef MG_BATCH
+#define MG_BATCH 12u                             // merges per step, at most (2 (MG_BATCH + 1) <= 32: select_batch ranks the survivors in one warp; measured at 11 GB: 8 -> 197 ms, 12 -> 183, 15 -> 183)
+#endif
 
 struct __align__(16) WordMeta {
     u32 off, len;        // word w occupies sym[off, off+len) at build time
@@ -87,34 +103,44 @@ __device__ __forceinline__ void store_best(Best *p, const Best &b) {
     q[0] = make_uint4((u32)b.cnt, (u32)((u64)b.cnt >> 32), (u32)b.key, (u32)(b.key >> 32));
     q[1] = make_uint4((u32)b.ka, (u32)(b.ka >> 32), (u32)b.kb, (u32)(b.kb >> 32));
 }
+// Upper bound of the second-largest count of a block as 32 bits: 0 = "no second key" (a real bound of 0 means the same to
+// the batching rule, which needs count > bound), saturated = "unknown, assume huge".
+#define SEC_SAT 0xFFFFFFFFu
+__device__ __forceinline__ u32 sec_pack(i64 c) { return c <= 0 ? 0u : (c >= (i64)SEC_SAT ? SEC_SAT : (u32)c); }
+__device__ __forceinline__ i64 sec_unpack(u32 s) { return s == SEC_SAT ? (i64)0x7FFFFFFFFFFFFFFFll : (i64)s; }
 
 struct MergeState {
     Words W; u32 n_words;
     u64 *pkey; i64 *pcnt; u64 pcap;
-    Best *bmax; uint8_t *dirty; u32 n_blocks;
+    Best *bmax; u32 *bsec; uint8_t *dirty; u32 n_blocks;
     const u32 *csr_off; const Rec *csr_rec;
-    Rec *log; u64 *log_begin; u64 log_cap;
+    // log_rng[2t], [2t+1] = slice of the log written by the STEP that contained merge t (all merges of a step share it)
+    Rec *log; u64 *log_rng; u64 log_cap;
     // big log slices are bucket-sorted by hash(neighbour) into log2 right after the step that wrote them:
-    // bk_lg[step] = log2(buckets) (0 = slice left unsorted), bk_start[step] = first of its buckets+1 offsets in bk_off
+    // bk_lg[t] = log2(buckets) (0 = slice left unsorted), bk_start[t] = first of its buckets+1 offsets in bk_off
     Rec *log2; u32 *bk_lg; u64 *bk_start; u32 *bk_off; u64 bk_off_cap; u32 *bk_scratch;   // bk_scratch: 2 x (hist, cursor) x SORT_MAX_BK
     u32 *tok_off; u32 *tok_len; u64 *tok_key; uint8_t *tok_bytes; u64 tok_bytes_cap;
     struct BarSlot *bar; u32 *bar_ctr;            // gather slots / the two barrier counters (128 B apart) of k_merge_loop, zeroed before every launch
-    // tail kernel (one thread-block cluster): per 64-block superblock a 64-bit mask of dirty blocks
-    u64 *sdirty_mask; u32 n_super; int tail_mode;
-    int stop_at;                                 // this launch runs steps [ctr[1], stop_at)
+    int stop_at;                                 // this launch runs merges [ctr[1], stop_at)
+    u32 max_batch;                               // merges per step, <= MG_BATCH (BPE_MERGE_BATCH)
     int32_t *merges_out; i64 *merge_cnt_out; int n_merges;
-    // [0]=log cursor [1]=n_done (next step) [2]=pair keys created [3]=status flags [4]=tok bytes cursor
-    // [5]=keys popped since the table was last rebuilt [6]=previous winner key still to be popped (PAIR_EMPTY if none)
+    // [0]=log cursor [1]=n_done (next merge) [2]=pair keys created [3]=status flags [4]=tok bytes cursor
+    // [5]=keys popped since the table was last rebuilt [6]=number of keys still to be popped (the last step's winners, in [16..16+MG_BATCH))
+    // [7]=sum over merges of the live pair-table keys (the reference's max() scans that many dict entries, train.py:187-189;
+    //     merges of one step are all charged the table size at the start of the step)
     // [8]=words rewritten (all steps) [9]=bk_off pool cursor [10]=slices sorted
-    // [7]=sum over steps of the live pair-table keys (the reference's max() scans that many dict entries, train.py:187-189)
+    // [12]=grid steps taken
     u64 *ctr;
     // profile (ns / counts): [0]=phase1 [1]=sync1 [2]=apply [3]=sync2 on CTA 0; [4]=token CTA work; [5]=index records scanned;
     // [6]=words rewritten; [7]=steps; [9]=dirty blocks rescanned
     u64 *prof;
+    u32 sort_min;     // log slices with fewer records are left unsorted and scanned whole (BPE_MERGE_SORTMIN)
     u32 min_rec;      // smallest number of records dealt to a warp per pass of the apply phase (BPE_MERGE_MINREC)
     u64 *cta_prof;    // optional (profile builds): per step and CTA {start, arrive1, exit1, arrive2}
     u32 *step_prof;   // optional per-step trace: 4 x u32 per step (phase1+sync1 ns, apply+sync2 ns, records scanned, words rewritten so far)
 };
+#define MG_CTR_WORDS 32
+#define MG_CTR_PENDING 16
 
 // The loop state lives in constant memory: helpers are real (non-inlined) functions so that the persistent
 // kernel stays small enough for the instruction caches -- every step runs each code path only once, so a
@@ -123,12 +149,9 @@ __constant__ MergeState cM;
 
 #ifdef BPE_MERGE_PROFILE
 __device__ __forceinline__ u64 gtime_ns() { u64 t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
-// timer read that cannot be scheduled before `dep` is available
-__device__ __forceinline__ u64 gtime_after(u64 dep) { u64 t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t) : "l"(dep) : "memory"); return t; }
 #define PROF_ADD(i, v) atomicAdd(&cM.prof[i], (u64)(v))
 #else
 __device__ __forceinline__ u64 gtime_ns() { return 0; }
-__device__ __forceinline__ u64 gtime_after(u64) { return 0; }
 #define PROF_ADD(i, v) do { } while (0)
 #endif
 
@@ -144,8 +167,7 @@ __device__ __noinline__ bool tok_greater_slow(u32 p, u32 q) {
     if (lp <= 8 && lq <= 8) return lp > lq;      // equal zero-padded prefixes: the shorter one is a prefix of the longer
     return bytes_cmp_dev(cM.tok_bytes + cM.tok_off[p], lp, cM.tok_bytes + cM.tok_off[q], lq) > 0;
 }
-// Tie-break of two candidates with equal counts: python's ((bytes_a, bytes_b)) tuple order.  A real function
-// (not inlined): the persistent kernel must stay small, see the note at cM.
+// Tie-break of two candidates with equal counts: python's ((bytes_a, bytes_b)) tuple order.
 __device__ __forceinline__ bool best_tie_greater(u64 xkey, u64 xka, u64 xkb, u64 ykey, u64 yka, u64 ykb) {
     u32 xa = (u32)(xkey >> 32), ya = (u32)(ykey >> 32);
     if (xa != ya) return xka != yka ? xka > yka : tok_greater_slow(xa, ya);
@@ -154,10 +176,13 @@ __device__ __forceinline__ bool best_tie_greater(u64 xkey, u64 xka, u64 xkb, u64
     return xkb != ykb ? xkb > ykb : tok_greater_slow(xb, yb);
 }
 // (count, (bytes_a, bytes_b)) ordering of train.py:187-189
+// (a real function: the persistent kernel is instruction-fetch bound -- every step walks through most of its code once, far more
+// than the 32 KB instruction cache of an SM holds -- so the comparison exists once, not once per call site)
+__device__ __noinline__ bool best_tie_greater_ni(u64 xkey, u64 xka, u64 xkb, u64 ykey, u64 yka, u64 ykb) { return best_tie_greater(xkey, xka, xkb, ykey, yka, ykb); }
 __device__ __forceinline__ bool best_greater(const Best &x, const Best &y) {
     if (x.cnt != y.cnt) return x.cnt > y.cnt;
     if (x.cnt == CNT_DEAD) return false;
-    return best_tie_greater(x.key, x.ka, x.kb, y.key, y.ka, y.kb);
+    return best_tie_greater_ni(x.key, x.ka, x.kb, y.key, y.ka, y.kb);
 }
 // butterfly reduction with the full comparison (handles every tie): the slow path of warp_best
 __device__ __noinline__ Best warp_best_butterfly(Best b) {
@@ -180,10 +205,12 @@ __device__ __forceinline__ u64 warp_max_u64(u64 v, bool active) {
     const u32 ml = __reduce_max_sync(0xffffffffu, lo);
     return ((u64)mh << 32) | ml;
 }
+// warp-wide maximum of signed counts (CNT_DEAD = "nothing")
+__device__ __forceinline__ i64 warp_max_cnt(i64 c) { return (i64)(warp_max_u64((u64)c ^ 0x8000000000000000ull, true) ^ 0x8000000000000000ull); }
 // Warp arg-max under the (count, (bytes_a, bytes_b)) order; every lane returns the winner.  The common cases -- a
 // unique maximal count, or ties decided by the 8-byte prefix keys -- take a few redux / ballot steps instead of a
 // five-round butterfly of 256-bit shuffles; anything subtler (equal prefixes of different tokens) falls back to it.
-__device__ __forceinline__ Best warp_best(Best b) {
+__device__ __noinline__ Best warp_best(Best b) {
     // counts: CNT_DEAD (most negative) marks "no candidate"; bias to unsigned order
     const u64 bc = (u64)b.cnt ^ 0x8000000000000000ull;
     const u64 mc = warp_max_u64(bc, true);
@@ -214,23 +241,49 @@ __device__ __forceinline__ Best warp_best(Best b) {
     return r;
 }
 
-// A pair-table slot changed: its block must be rescanned before the next arg-max.
-__device__ __forceinline__ void mark_dirty(u64 slot) {
-    const u32 blk = (u32)(slot / PB);
-    if (cM.tail_mode) atomicOr(&cM.sdirty_mask[blk >> 6], 1ull << (blk & 63u));   // fire-and-forget reduction
-    else cM.dirty[blk] = 1;
+// The two largest candidates a thread / warp / CTA has seen, and an upper bound h of the counts of everything else it has seen.
+struct Top2 { Best m1, m2; i64 h; };
+__device__ __forceinline__ Top2 top2_none() { Top2 t; t.m1 = BEST_NONE; t.m2 = BEST_NONE; t.h = CNT_DEAD; return t; }
+__device__ __forceinline__ void top2_add(Top2 &t, const Best &e) {
+    if (e.cnt == CNT_DEAD) return;
+    if (e.cnt < t.m2.cnt) { if (e.cnt > t.h) t.h = e.cnt; return; }
+    if (best_greater(e, t.m1)) { if (t.m2.cnt > t.h) t.h = t.m2.cnt; t.m2 = t.m1; t.m1 = e; }
+    else if (best_greater(e, t.m2)) { if (t.m2.cnt > t.h) t.h = t.m2.cnt; t.m2 = e; }
+    else if (e.cnt > t.h) t.h = e.cnt;
 }
+// Reduce the lanes' Top2 to the warp's (returned in every lane).
+__device__ __forceinline__ Top2 warp_top2(Top2 t) {
+    Top2 r;
+    r.m1 = warp_best(t.m1);
+    if (r.m1.cnt != CNT_DEAD && t.m1.key == r.m1.key) { t.m1 = t.m2; t.m2 = BEST_NONE; }
+    r.m2 = warp_best(t.m1);
+    if (r.m2.cnt != CNT_DEAD && t.m1.key == r.m2.key) { t.m1 = t.m2; t.m2 = BEST_NONE; }
+    i64 h = t.h;
+    if (t.m1.cnt > h) h = t.m1.cnt;              // (m2 <= m1 in every lane, and CNT_DEAD is the smallest value)
+    r.h = warp_max_cnt(h);
+    return r;
+}
+
+// The merges of the current step, identical in every CTA (shared memory).
+struct __align__(16) Batch {
+    u64 key[MG_BATCH]; i64 cnt[MG_BATCH];
+    u64 lo[MG_BATCH], pre[MG_BATCH + 1];         // index range of merge j: src[j][lo[j] .. lo[j] + pre[j+1] - pre[j])
+    const Rec *src[MG_BATCH];
+    u32 a[MG_BATCH], b[MG_BATCH], want[MG_BATCH]; // want: neighbour the records are filtered by (0xFFFFFFFF: no filter, CSR slice)
+    u32 r;
+};
+#define WANT_ANY 0xFFFFFFFFu
+
+// A pair-table slot changed: its block must be rescanned before the next arg-max.
+__device__ __forceinline__ void mark_dirty(u64 slot) { cM.dirty[(u32)(slot / PB)] = 1; }
 
 // frequencies[key] += delta with defaultdict semantics (train.py:36,65-78): a missing key is created.
 // The count update is a fire-and-forget reduction; a popped key that is touched again is repaired by
 // the next rescan of its block (see rescan_block).  (s, k) = first probe slot and the key read there.
-// kClaimed: the probe at slot s was the claiming CAS itself and k is what that CAS returned (only for keys that cannot
-// have been in the table before this step); otherwise k is the key read at s.
-template <bool kClaimed>
-__device__ __forceinline__ void pair_add_probe(u64 key, i64 delta, u64 s, u64 k) {
+__device__ __noinline__ void pair_add_from(u64 key, i64 delta, u64 s, u64 k) {
     const u64 mask = cM.pcap - 1;
     for (u64 probes = 0; probes < cM.pcap; probes++) {
-        if (!kClaimed && k == PAIR_EMPTY) k = atomicCAS(&cM.pkey[s], PAIR_EMPTY, key);
+        if (k == PAIR_EMPTY) k = atomicCAS(&cM.pkey[s], PAIR_EMPTY, key);
         if (k == PAIR_EMPTY) { atomicAdd(&cM.ctr[2], 1ull); k = key; }       // our CAS claimed the slot
         if (k == key) {
             atomicAdd((u64 *)&cM.pcnt[s], (u64)delta);
@@ -238,37 +291,39 @@ __device__ __forceinline__ void pair_add_probe(u64 key, i64 delta, u64 s, u64 k)
             return;
         }
         s = (s + 1) & mask;
-        k = kClaimed ? atomicCAS(&cM.pkey[s], PAIR_EMPTY, key) : cM.pkey[s];
+        k = cM.pkey[s];
     }
     cM.ctr[3] = 1;                                // table full
 }
-__device__ __noinline__ void pair_add_from(u64 key, i64 delta, u64 s, u64 k) { pair_add_probe<false>(key, delta, s, k); }
 __device__ __forceinline__ void pair_add(u32 a, u32 b, i64 delta) {
     u64 key = ((u64)a << 32) | b;
     u64 s = pair_hash(key) & (cM.pcap - 1);
     pair_add_from(key, delta, s, cM.pkey[s]);
 }
 
-// Apply merge (a,b)->nw at the occurrence whose left symbol sits at position p (word frequency c): one merge site of the
-// left-to-right scan of train.py:196-224 with update_frequencies_after_merge (52-78), merge_subwords (132-139) and
-// create_new_token_indices (107-129).
+// Apply merge j of the step, (a,b) -> nw = nw0 + j, at the occurrence whose left symbol sits at position p (word frequency c):
+// one merge site of the left-to-right scan of train.py:196-224 with update_frequencies_after_merge (52-78), merge_subwords
+// (132-139) and create_new_token_indices (107-129).
 //
-// All sites of a step run concurrently, so every thread reasons about the state AT THE START OF THE STEP, which it can
-// always reconstruct: a symbol equal to nw was `a`, a tombstone of this step was `b`.  The reference's sequential
+// All sites of a step run concurrently, so every thread reasons about the state AT THE START OF THE STEP, which it can always
+// reconstruct: a symbol equal to nw0 + i was a_i, the tombstone of merge i of this step was b_i.  The reference's sequential
 // semantics in those terms:
-//   * a record is a site iff its symbols are (a,b) and -- for a == b, inside a run of a's -- it sits at an even offset
-//     from the start of the run (non-overlapping, left to right: aaaa -> [aa, aa], aaa -> [aa, a]);
-//   * the left neighbour is the already merged token when the occurrence directly to the left is a site as well
-//     (abab: the second site sees (nw, a), decrements it and creates (nw, nw)); the right neighbour is always the
-//     unmerged symbol (the scan has not reached it yet);
+//   * a record is a site iff its symbols are (a,b) and -- for a == b (only in steps of one merge), inside a run of a's -- it
+//     sits at an even offset from the start of the run (non-overlapping, left to right: aaaa -> [aa, aa], aaa -> [aa, a]);
+//   * the left neighbour is the already merged token when the occurrence directly to the left is a site of merge i <= j
+//     (abab: the second site sees (nw, a), decrements it and creates (nw, nw)); when it is a site of a merge i > j, or no site,
+//     it is the plain symbol;
+//   * the right neighbour is the merged token when the occurrence directly to the right is a site of a merge i < j, and the
+//     unmerged symbol otherwise (the same merge's scan has not reached it yet, a later merge has not happened yet);
 //   * both new pairs are indexed, even if the right one is merged away later in the same step (stale, harmless).
-__device__ __noinline__ void apply_site(u32 p, i64 c, u32 a, u32 b, u32 nw, int step) {
+__device__ __noinline__ void apply_site(u32 p, i64 c, u32 j, int step0, u32 nw0, const Batch *B) {
     int32_t *s = cM.W.sym;
-    const int32_t dead_now = -(step + 2);
-    const int32_t ia = (int32_t)a, ib = (int32_t)b, inw = (int32_t)nw;
-#define ORIG(e) ((e) == inw ? ia : ((e) == dead_now ? ib : (e)))            /* value at the start of the step */
-#define WAS_LIVE(e) ((e) >= 0 || (e) == dead_now)                          /* live at the start of the step */
-#define OLD_TOMB(e) ((e) < SYM_SEP && (e) != dead_now)                     /* tombstone of an earlier step */
+    const int32_t ia = (int32_t)B->a[j], ib = (int32_t)B->b[j], inw = (int32_t)(nw0 + j);
+    const int32_t tomb_hi = -(step0 + 2);                                     // tombstones of this step: tomb_hi - i for merge i
+    const int32_t dead_now = tomb_hi - (int32_t)j;
+#define ORIG(e) ((e) >= (int32_t)nw0 ? (int32_t)B->a[(e) - (int32_t)nw0] : ((e) <= tomb_hi ? (int32_t)B->b[tomb_hi - (e)] : (e)))   /* value at the start of the step */
+#define WAS_LIVE(e) ((e) >= 0 || (e) <= tomb_hi)                            /* live at the start of the step */
+#define OLD_TOMB(e) ((e) < SYM_SEP && (e) > tomb_hi)                         /* tombstone of an earlier step */
     // the four symbols around p are loaded together (one round trip in the common case of no old tombstones)
     int32_t vl = s[p - 1];
     const int32_t e0 = s[p];
@@ -281,7 +336,7 @@ __device__ __noinline__ void apply_site(u32 p, i64 c, u32 a, u32 b, u32 nw, int 
     bool has_l = false; u32 left = 0, pos_l = 0;
     u32 q = p - 1;
     while (OLD_TOMB(vl)) { q--; vl = s[q]; }
-    if (a == b) {
+    if (ia == ib) {
         // run of a's ending just before p: its length decides whether p starts a site
         u32 n_left = 0, second = p;                                        // position of the second nearest a on the left
         while (WAS_LIVE(vl) && ORIG(vl) == ia) {
@@ -291,24 +346,38 @@ __device__ __noinline__ void apply_site(u32 p, i64 c, u32 a, u32 b, u32 nw, int 
             while (OLD_TOMB(vl)) { q--; vl = s[q]; }
         }
         if (n_left & 1u) return;                                           // the a at p is the right half of the previous site
-        if (n_left) { has_l = true; left = nw; pos_l = second; }
+        if (n_left) { has_l = true; left = (u32)inw; pos_l = second; }
         else if (vl != SYM_SEP) { has_l = true; left = (u32)ORIG(vl); pos_l = q; }
     } else if (vl != SYM_SEP) {
         const int32_t o1 = ORIG(vl);
         has_l = true; left = (u32)o1; pos_l = q;
-        if (o1 == ib) {                                                    // (.., a, b, [a, b]): the left occurrence is a site too
+        for (u32 i = 0; i <= j; i++) {
+            if ((int32_t)B->b[i] != o1) continue;
+            // (.., a_i, b_i, [a, b]): the occurrence on the left is a site of merge i <= j: it is merged before this one
             u32 q2 = q - 1;
             int32_t v2 = s[q2];
             while (OLD_TOMB(v2)) { q2--; v2 = s[q2]; }
-            if (WAS_LIVE(v2) && ORIG(v2) == ia) { left = nw; pos_l = q2; }
+            if (WAS_LIVE(v2) && ORIG(v2) == (int32_t)B->a[i]) { left = nw0 + i; pos_l = q2; }
+            break;
         }
     }
-    // ---- right context: the symbol as it was (it is merged later, if at all) ----
+    // ---- right context: the symbol as it was, unless it starts a site of an EARLIER merge of this step ----
     u32 qr = pb + 1;
     if (pb != p + 1) vr = s[qr];
     while (OLD_TOMB(vr)) { qr++; vr = s[qr]; }
     const bool has_r = vr != SYM_SEP;
-    const u32 right = has_r ? (u32)ORIG(vr) : 0;
+    u32 right = has_r ? (u32)ORIG(vr) : 0;
+    if (has_r) {
+        for (u32 i = 0; i < j; i++) {
+            if (B->a[i] != right) continue;
+            u32 q3 = qr + 1;
+            int32_t v3 = s[q3];
+            while (OLD_TOMB(v3)) { q3++; v3 = s[q3]; }
+            if (WAS_LIVE(v3) && ORIG(v3) == (int32_t)B->b[i]) right = nw0 + i;
+            break;
+        }
+    }
+    const u32 a = (u32)ia, b = (u32)ib, nw = (u32)inw;
     // ---- the four dict updates of update_frequencies_after_merge.  (left, nw) and (nw, right) contain the token made in
     // this step, so they are not in the table unless another site of this step put them there: their first probe is the
     // claiming CAS itself, issued together with the read probes of the two old keys and the log allocation ----
@@ -348,26 +417,26 @@ __device__ __noinline__ void apply_site(u32 p, i64 c, u32 a, u32 b, u32 nw, int 
         u32 pend = (has_l ? 3u : 0u) | (has_r ? 12u : 0u);
         for (u64 probes = 0; pend && probes <= cM.pcap; probes++) {
 #pragma unroll
-            for (u32 j = 0; j < 4; j++) {
-                if (!((pend >> j) & 1u)) continue;
-                u64 k = vv[j];
+            for (u32 t = 0; t < 4; t++) {
+                if (!((pend >> t) & 1u)) continue;
+                u64 k = vv[t];
                 if (k == PAIR_EMPTY) {
-                    if (!((cas >> j) & 1u)) {                              // empty slot seen by a read probe: claim it
-                        vv[j] = atomicCAS(&cM.pkey[ss[j]], PAIR_EMPTY, kk[j]);
-                        cas |= 1u << j;
+                    if (!((cas >> t) & 1u)) {                              // empty slot seen by a read probe: claim it
+                        vv[t] = atomicCAS(&cM.pkey[ss[t]], PAIR_EMPTY, kk[t]);
+                        cas |= 1u << t;
                         continue;
                     }
                     atomicAdd(&cM.ctr[2], 1ull);                           // our CAS claimed the slot
-                    k = kk[j];
+                    k = kk[t];
                 }
-                if (k == kk[j]) {
-                    atomicAdd((u64 *)&cM.pcnt[ss[j]], (u64)dd[j]);
-                    mark_dirty(ss[j]);
-                    pend &= ~(1u << j);
+                if (k == kk[t]) {
+                    atomicAdd((u64 *)&cM.pcnt[ss[t]], (u64)dd[t]);
+                    mark_dirty(ss[t]);
+                    pend &= ~(1u << t);
                     continue;
                 }
-                ss[j] = (ss[j] + 1) & mask;
-                vv[j] = ((cas >> j) & 1u) ? atomicCAS(&cM.pkey[ss[j]], PAIR_EMPTY, kk[j]) : cM.pkey[ss[j]];
+                ss[t] = (ss[t] + 1) & mask;
+                vv[t] = ((cas >> t) & 1u) ? atomicCAS(&cM.pkey[ss[t]], PAIR_EMPTY, kk[t]) : cM.pkey[ss[t]];
             }
         }
         if (pend) cM.ctr[3] = 1;                                           // table full
@@ -378,10 +447,12 @@ __device__ __noinline__ void apply_site(u32 p, i64 c, u32 a, u32 b, u32 nw, int 
 #undef OLD_TOMB
 }
 
-// Rescan the PB slots of one block with a full warp.  Pops `prev_key` when it meets it and repairs
-// popped keys that were touched again (count = CNT_DEAD + deltas  ->  deltas).
-__device__ __forceinline__ Best rescan_block(u32 blk, u64 prev_key) {
+// Rescan the PB slots of one block with a full warp.  Pops the winners of the previous step (prev[0..n_prev)) when it meets
+// them and repairs popped keys that were touched again (count = CNT_DEAD + deltas  ->  deltas).  Returns the block's maximum
+// and, in sec, the bound of its second-largest count.
+__device__ __noinline__ Best rescan_block(u32 blk, const u64 *prev, u32 n_prev, u32 &sec) {
     Best bst = BEST_NONE;
+    i64 other = CNT_DEAD;                         // largest count this lane saw apart from bst
     const u64 sbase = (u64)blk * PB;
     u64 keys[PB / 32]; i64 cnts[PB / 32]; u64 kas[PB / 32], kbs[PB / 32];
 #pragma unroll
@@ -397,64 +468,33 @@ __device__ __forceinline__ Best rescan_block(u32 blk, u64 prev_key) {
         Best c;
         c.key = keys[k]; c.cnt = cnts[k]; c.ka = kas[k]; c.kb = kbs[k];
         if (c.key == PAIR_EMPTY) continue;
-        if (c.key == prev_key) { cM.pcnt[sbase + k * 32 + lane_id()] = CNT_DEAD; continue; }
+        bool popped = false;
+        for (u32 i = 0; i < n_prev; i++) popped |= c.key == prev[i];
+        if (popped) { cM.pcnt[sbase + k * 32 + lane_id()] = CNT_DEAD; continue; }
         if (c.cnt == CNT_DEAD) continue;
         if (c.cnt < CNT_DEAD_LIMIT) { c.cnt = (i64)((u64)c.cnt - (u64)CNT_DEAD); cM.pcnt[sbase + k * 32 + lane_id()] = c.cnt; }
-        if (best_greater(c, bst)) bst = c;
+        if (best_greater(c, bst)) { other = bst.cnt; bst = c; }
+        else other = c.cnt > other ? c.cnt : other;
     }
-    return warp_best(bst);
-}
-
-
-// ---- token bookkeeping: bytes and prefix key of the new token, outputs (one CTA, all its threads) -------------
-__device__ __forceinline__ void token_bookkeeping(int step, const Best &win, u32 a, u32 b, u32 nw, bool prof_thread, u64 t2) {
-    const u32 tid = threadIdx.x;
-    u64 tA = prof_thread ? gtime_ns() : 0;
-    const u32 la = cM.tok_len[a], lb = cM.tok_len[b], ln = la + lb;
-    const u32 oa = cM.tok_off[a], ob = cM.tok_off[b];
-    const u64 cur = cM.ctr[4];
-    const u64 live = cM.ctr[2];
-    __syncthreads();
-    u64 tB = prof_thread ? gtime_ns() : 0;
-    if (cur + ln > cM.tok_bytes_cap) { if (tid == 0) cM.ctr[3] = 4; }
-    else {
-        uint8_t *dst = cM.tok_bytes + cur;
-        const uint8_t *pa = cM.tok_bytes + oa, *pb = cM.tok_bytes + ob;
-        for (u32 i = tid; i < ln; i += MG_NT) dst[i] = i < la ? pa[i] : pb[i - la];
-        if (tid == 0) {
-            // first 8 bytes of a+b from the operands' zero-padded big-endian prefix keys
-            u64 nkey = cM.tok_key[a];
-            if (la < 8) nkey |= cM.tok_key[b] >> (8 * la);
-            cM.tok_off[nw] = (u32)cur; cM.tok_len[nw] = ln; cM.tok_key[nw] = nkey; cM.ctr[4] = cur + ln;
-            cM.merges_out[2 * step] = (int32_t)a; cM.merges_out[2 * step + 1] = (int32_t)b;
-            cM.merge_cnt_out[step] = win.cnt;
-            cM.ctr[1] = (u64)(step + 1);
-            cM.ctr[7] += live - cM.ctr[5]; cM.ctr[5] += 1;
-            if (prof_thread) { cM.prof[10] += tA - t2; cM.prof[11] += tB - tA; cM.prof[12] += gtime_ns() - tB; }
-        }
-    }
-    // make sure the winner's block is rescanned so the key gets popped
-    if (tid == 32) {
-        u64 mask = cM.pcap - 1, s = pair_hash(win.key) & mask;
-        while (cM.pkey[s] != win.key) s = (s + 1) & mask;
-        mark_dirty(s);
-    }
+    const Best w = warp_best(bst);
+    const i64 rest = (w.cnt != CNT_DEAD && bst.key == w.key) ? other : (bst.cnt > other ? bst.cnt : other);
+    sec = sec_pack(warp_max_cnt(rest));
+    return w;
 }
 
 // source array of an index range: 0 = log, 1 = bucket-sorted copy, 2 = CSR of the initial byte pairs
 #define T_SRC(code) ((code) == 2 ? cM.csr_rec : ((code) == 1 ? (const Rec *)cM.log2 : (const Rec *)cM.log))
-#define SORT_MIN 2048u                           // slices with fewer records are scanned whole
 #define SORT_MAX_LG 12u                          // at most 4096 buckets
 #define SORT_MAX_BK (1u << SORT_MAX_LG)
 __device__ __forceinline__ u32 bucket_of(u32 x, u32 lg) { return (x * 0x9E3779B1u) >> (32u - lg); }
 
-// Index range of the winner (a,b): token_indices[best_pair] of train.py:192.  out[0..1] = record range, out[2] = 1 when
-// the range lies in the bucket-sorted copy (log2).  One thread per CTA.
+// Index range of the pair (a,b): token_indices[best_pair] of train.py:192.  out[0..1] = record range, out[2] = source code.
 __device__ __forceinline__ void winner_range(u64 key, u64 *out) {
     const u32 wa = (u32)(key >> 32), wb = (u32)key, wT = wa > wb ? wa : wb;
     if (wT < 256) { u32 pp = (wa << 8) | wb; out[0] = cM.csr_off[pp]; out[1] = cM.csr_off[pp + 1]; out[2] = 2; return; }
     const u32 t = wT - 256;
-    const u64 lo = cM.log_begin[t], hi = cM.log_begin[t + 1];
+    const ulonglong2 rg = *reinterpret_cast<const ulonglong2 *>(&cM.log_rng[2 * (u64)t]);
+    const u64 lo = rg.x, hi = rg.y;
     const u32 lg = cM.bk_lg[t];
     const u64 st0 = cM.bk_start[t];              // (garbage when the slice is unsorted; loaded alongside, not after)
     if (!lg) { out[0] = lo; out[1] = hi; out[2] = 0; return; }
@@ -464,11 +504,12 @@ __device__ __forceinline__ void winner_range(u64 key, u64 *out) {
 }
 
 // Bucket-sort the slice [lo, lo + n) of the log by hash(record.x) into log2 (same offsets) and publish the bucket
-// offsets.  Called by every thread of every CTA between two steps; `sync` is the grid / cluster barrier.
-// s_scan: SORT_MAX_BK u32 of shared memory.  parity alternates so that the scratch of the previous sort can be cleared here.
+// offsets for the r merges [step0, step0 + r) that wrote it.  Called by every thread of every CTA between two steps; `sync` is
+// the grid barrier.  s_scan: SORT_MAX_BK u32 of shared memory.  parity alternates so that the scratch of the previous sort can
+// be cleared here.
 template <typename SyncFn>
-__device__ __forceinline__ void sort_slice(int step, u64 lo, u32 n, u32 parity, bool leader_cta, u64 gthread, u64 gstride,
-                                           u32 *s_scan, SyncFn sync) {
+__device__ __forceinline__ void sort_slice(int step0, u32 r, u64 lo, u32 n, u32 parity, bool leader_cta, u64 gthread, u64 gstride,
+                                           u32 *s_scan, u32 *s_wsum, SyncFn sync) {
     u32 lg = 4;
     while ((64u << lg) < n && lg < SORT_MAX_LG) lg++;
     const u32 nbk = 1u << lg;
@@ -483,7 +524,6 @@ __device__ __forceinline__ void sort_slice(int step, u64 lo, u32 n, u32 parity, 
     u32 v[8], sum = 0;
 #pragma unroll
     for (u32 k = 0; k < 8; k++) { u32 i = tid * per + k; v[k] = (k < per && i < nbk) ? hist[i] : 0; sum += v[k]; }
-    __shared__ u32 s_wsum[MG_NT / 32 + 1];
     u32 inc = sum;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { u32 t = __shfl_up_sync(0xffffffffu, inc, d); if (lane_id() >= (u32)d) inc += t; }
@@ -505,34 +545,36 @@ __device__ __forceinline__ void sort_slice(int step, u64 lo, u32 n, u32 parity, 
         if (k < per && i < nbk) { s_scan[i] = base; if (leader_cta) cM.bk_off[pool + i] = base; base += v[k]; }
     }
     if (leader_cta && tid == 0) {
-        cM.bk_off[pool + nbk] = n; cM.bk_start[step] = pool; cM.bk_lg[step] = lg; cM.ctr[9] = pool + nbk + 1; cM.ctr[10] += 1;
+        cM.bk_off[pool + nbk] = n; cM.ctr[9] = pool + nbk + 1; cM.ctr[10] += 1;
+        for (u32 j = 0; j < r; j++) { cM.bk_start[step0 + j] = pool; cM.bk_lg[step0 + j] = lg; }
     }
     __syncthreads();
     for (u64 i = gthread; i < n; i += gstride) {
-        const uint4 r = *reinterpret_cast<const uint4 *>(&cM.log[lo + i]);
-        const u32 bk = bucket_of(r.x, lg);
-        *reinterpret_cast<uint4 *>(&cM.log2[lo + s_scan[bk] + atomicAdd(&cur[bk], 1u)]) = r;
+        const uint4 rec = *reinterpret_cast<const uint4 *>(&cM.log[lo + i]);
+        const u32 bk = bucket_of(rec.x, lg);
+        *reinterpret_cast<uint4 *>(&cM.log2[lo + s_scan[bk] + atomicAdd(&cur[bk], 1u)]) = rec;
     }
     sync();
 }
 
-// ---- apply the merge at every occurrence indexed under (a,b): index slice [lo, hi) spread over `gstride` threads ----
-__device__ __forceinline__ void apply_winner(int step, u32 a, u32 b, u32 nw, u64 lo, u64 hi, const Rec *__restrict__ src, u64 gthread, u64 gstride) {
-    const u32 T = a > b ? a : b;
-    if (gthread == 0) PROF_ADD(5, hi - lo);
-    // pairs of two initial bytes: the CSR slice holds exactly the occurrences of (a,b); otherwise filter by neighbour
-    const bool filter = T >= 256;
-    const u32 want = b >= a ? a : (0x80000000u | b);
-    for (u64 i = lo + gthread; i < hi; i += 4 * gstride) {               // 4 records in flight per thread
-        Rec r0 = load_rec(&src[i]), r1, r2, r3;
-        const bool h1 = i + gstride < hi, h2 = i + 2 * gstride < hi, h3 = i + 3 * gstride < hi;
-        if (h1) r1 = load_rec(&src[i + gstride]);
-        if (h2) r2 = load_rec(&src[i + 2 * gstride]);
-        if (h3) r3 = load_rec(&src[i + 3 * gstride]);
-        if (!filter || r0.x == want) apply_site(r0.pos, r0.cnt, a, b, nw, step);
-        if (h1 && (!filter || r1.x == want)) apply_site(r1.pos, r1.cnt, a, b, nw, step);
-        if (h2 && (!filter || r2.x == want)) apply_site(r2.pos, r2.cnt, a, b, nw, step);
-        if (h3 && (!filter || r3.x == want)) apply_site(r3.pos, r3.cnt, a, b, nw, step);
+// ---- apply the merges of the step at every occurrence indexed under their pairs: the r index slices form one list of
+// B->pre[r] records, spread over `gstride` threads ----
+__device__ __forceinline__ bool fetch_rec(const Batch *B, u64 g, Rec &rec, u32 &j) {
+    j = 0;
+    while (g >= B->pre[j + 1]) j++;
+    rec = load_rec(&B->src[j][B->lo[j] + (g - B->pre[j])]);
+    return B->want[j] == WANT_ANY || rec.x == B->want[j];
+}
+__device__ __forceinline__ void apply_batch(int step0, u32 nw0, const Batch *B, u64 gthread, u64 gstride) {
+    const u64 total = B->pre[B->r];
+    if (gthread == 0) PROF_ADD(5, total);
+    for (u64 g = gthread; g < total; g += 2 * gstride) {                  // 2 records in flight per thread
+        Rec r0, r1; u32 j0, j1 = 0;
+        const bool ok0 = fetch_rec(B, g, r0, j0);
+        const bool h1 = g + gstride < total;
+        const bool ok1 = h1 && fetch_rec(B, g + gstride, r1, j1);
+        if (ok0) apply_site(r0.pos, r0.cnt, j0, step0, nw0, B);
+        if (ok1) apply_site(r1.pos, r1.cnt, j1, step0, nw0, B);
     }
 }
 
@@ -542,14 +584,11 @@ __device__ __forceinline__ void apply_winner(int step, u32 a, u32 b, u32 nw, u64
 // polled by a warp 514 ms (five acquire loads per lane per poll, 148 pollers), cooperative_groups::grid.sync 581 ms,
 // fence + relaxed stores / polls 580 ms, this 481 ms.
 //  * grid_barrier: the barrier alone.
-//  * grid_gather:  barrier + all-gather of the per-CTA arg-max candidates: a CTA stores its candidate in its slot before it
-//    arrives; after the barrier warp 0 loads all slots and reduces them, so every CTA derives the same winner.  (An LL-style
-//    slot -- every 64-bit word tagged with the epoch, no barrier-then-data round trip -- was slower: 649 against 541 ms.)
-// Slot of a CTA: w[0..3] candidate, w[6..7] index range of that candidate (epoch-tagged words, written during the gather).
-struct __align__(64) BarSlot { u64 w[8]; };
+//  * grid_gather:  barrier + all-gather of the per-CTA candidates: a CTA stores its two best pairs and its bound H in its slot
+//    before it arrives; after the barrier warp 0 of every CTA loads all slots and derives the same batch of merges.
+// Slot of a CTA: w[0..3] best pair, w[4..7] second best, w[8] bound of everything else.
+struct __align__(128) BarSlot { u64 w[16]; };
 #define MG_MAX_CTAS 160u
-__device__ __forceinline__ void st_relaxed_v2(u64 *p, u64 a, u64 b) { asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory"); }
-__device__ __forceinline__ void ld_relaxed_v2(const u64 *p, u64 &a, u64 &b) { asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory"); }
 __device__ __forceinline__ u32 ld_acquire_u32(const u32 *p) { u32 v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ void red_release_add_u32(u32 *p, u32 v) { asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 // warp 0 only; the CTA barriers around it extend the ordering to the other warps
@@ -570,95 +609,228 @@ __device__ __forceinline__ void grid_barrier(u32 *counter, u32 G, u32 epoch, u64
     __syncthreads();
 }
 
-// While warp 0 waits in the gather, warp 1 looks up the index range of this CTA's OWN candidate and publishes it in the
-// spare words of its slot, tagged with the epoch (each 64-bit word carries a tag, so a torn or stale read is detected and
-// the reader falls back to winner_range); it also pulls the first records of that range and the symbols they point at
-// into L2.  Whichever candidate wins, the apply phase then starts one to three dependent round trips later in the chain.
-#define RANGE_TAG0(e) ((u64)((e) & 0xFFFFFFu) << 40)
-#define RANGE_TAG1(e) ((u64)((e) & 0x3FFFFFu) << 42)
-__device__ __forceinline__ void gather_side_work(BarSlot *slots, u32 epoch, const Best &cand, int step) {
-    if (cand.cnt == CNT_DEAD || epoch >= (1u << 22)) return;   // (the tags are 22 bits: no publishing beyond 4 M steps of one launch)
-    const u32 lane = lane_id();
-    const u32 a = (u32)(cand.key >> 32), b = (u32)cand.key, T = a > b ? a : b;
-    if (T >= 256 && (int)(T - 256) + 1 >= step) return;      // log_begin[step] is being written by CTA 0 right now: not visible yet
-    u64 r[3] = {0, 0, 0};
-    if (lane == 0) {
-        winner_range(cand.key, r);
-        if (r[0] < (1ull << 40) && r[1] < (1ull << 40))
-            st_relaxed_v2(&slots[blockIdx.x].w[6], r[0] | RANGE_TAG0(epoch), r[1] | (r[2] << 40) | RANGE_TAG1(epoch));
+// After the gather barrier: all CTAs' candidates (s_c[0 .. 2G): entry 2i is CTA i's best pair, 2i + 1 its second best) -> the
+// merges of this step in *B (see the header of this file for the rule).  Two stages, both exact under the full
+// (count, (bytes, bytes)) order:
+//   rank_bests    (threads 0 .. 2G) the rank of every CTA's best pair among all CTAs' best pairs.  One of the MG_BATCH + 1
+//                 greatest candidates overall is either a best pair of rank <= MG_BATCH or the second best of such a CTA, so
+//                 those CTAs' pairs are copied to s_surv[2 * rank + {0, 1}] and nothing else matters.
+//   select_batch  (warp 0) ranks the <= 2 (MG_BATCH + 1) survivors against each other, which yields d1 >= d2 >= ..., and applies
+//                 the rule with one lane per candidate.
+#define MG_SURV (2u * (MG_BATCH + 1u))
+__device__ __noinline__ bool best_greater_ni(const Best *x, const Best *y) { return best_greater(*x, *y); }
+__device__ __forceinline__ void rank_bests(const Best *s_c, const i64 *s_cnt, Best *s_surv, u32 G) {
+    const u32 t = threadIdx.x;                    // all threads of the CTA call this; threads 2i and 2i + 1 share CTA i's best pair
+    const u32 i = t >> 1, half = (G + 1) / 2;
+    const bool act = i < G;
+    const u32 j0 = (t & 1u) ? half : 0u, j1 = act ? ((t & 1u) ? G : half) : 0u;
+    const i64 ci = act ? s_cnt[2 * i] : CNT_DEAD;
+    // counts first: most pairs are out after this pass, and only pairs that can still be among the first MG_BATCH + 1 pay for
+    // the (bytes, bytes) comparisons with the pairs of equal count
+    u32 gt = 0, ties = 0;                         // (ties counts the pair itself)
+#pragma unroll 4
+    for (u32 j = j0; j < j1; j++) { const i64 cj = s_cnt[2 * j]; gt += cj > ci; ties += cj == ci; }
+    gt += __shfl_xor_sync(0xffffffffu, gt, 1);
+    ties += __shfl_xor_sync(0xffffffffu, ties, 1);
+    u32 extra = 0;
+    if (act && ci != CNT_DEAD && gt <= MG_BATCH && ties > 1) {
+#pragma unroll 1
+        for (u32 j = j0; j < j1; j++) if (s_cnt[2 * j] == ci && j != i && best_greater_ni(&s_c[2 * j], &s_c[2 * i])) extra++;
     }
-    const u64 lo = __shfl_sync(0xffffffffu, r[0], 0), hi = __shfl_sync(0xffffffffu, r[1], 0);
-    const u32 code = (u32)__shfl_sync(0xffffffffu, r[2], 0);
-    const Rec *src = T_SRC(code);
-    const bool filter = T >= 256;
-    const u32 want = b >= a ? a : (0x80000000u | b);
-    const u64 i = lo + lane;
-    if (i < hi) {
-        const Rec rec = load_rec(&src[i]);
-        if (!filter || rec.x == want) asm volatile("prefetch.global.L2 [%0];" ::"l"(&cM.W.sym[rec.pos]));
+    extra += __shfl_xor_sync(0xffffffffu, extra, 1);
+    const u32 rank = gt + extra;
+    if (act && !(t & 1u) && ci != CNT_DEAD && rank <= MG_BATCH) { s_surv[2 * rank] = s_c[2 * i]; s_surv[2 * rank + 1] = s_c[2 * i + 1]; }
+}
+// warp 0; H: bound of every pair that is not a candidate; max_r: upper limit of merges for this step
+__device__ __noinline__ void select_batch(const Best *s_surv, Best *s_sorted, i64 H, Batch *B, u32 max_r) {
+    const u32 lane = threadIdx.x;
+    const Best e = lane < MG_SURV ? s_surv[lane] : BEST_NONE;
+    u32 rank = 0;
+#pragma unroll 1
+    for (u32 m = 0; m < MG_SURV; m++) { const Best o = s_surv[m]; if (o.cnt != CNT_DEAD && m != lane && best_greater(o, e)) rank++; }
+    if (lane <= MG_BATCH) s_sorted[lane] = BEST_NONE;
+    __syncwarp();
+    if (e.cnt != CNT_DEAD && rank <= MG_BATCH) s_sorted[rank] = e;
+    __syncwarp();
+    const Best d = lane <= MG_BATCH ? s_sorted[lane] : BEST_NONE;           // lane t holds d(t+1)
+    const u32 a = (u32)(d.key >> 32), b = (u32)d.key;
+    const bool sq0 = __shfl_sync(0xffffffffu, a == b, 0);
+    bool bad = d.cnt == CNT_DEAD || (lane > 0 && (a == b || sq0));          // a == b goes alone
+#pragma unroll
+    for (u32 i = 0; i < MG_BATCH; i++) {
+        const u32 ai = __shfl_sync(0xffffffffu, a, i), bi = __shfl_sync(0xffffffffu, b, i);
+        if (i < lane) bad |= ai == a || ai == b || bi == a || bi == b;
     }
+    const u32 first_bad = __ffs(__ballot_sync(0xffffffffu, bad || lane >= max_r)) - 1;   // d1 .. d(first_bad) share no token
+    const i64 next = __shfl_down_sync(0xffffffffu, d.cnt, 1);
+    const bool strict = d.cnt != CNT_DEAD && d.cnt > H && (next == CNT_DEAD || d.cnt > next);   // d1 .. d(lane+1) may go together
+    const u32 ends = __ballot_sync(0xffffffffu, lane < first_bad && strict);
+    u32 good = ends ? 32u - __clz(ends) : 0u;
+    const bool any = __shfl_sync(0xffffffffu, d.cnt != CNT_DEAD, 0);
+    if (good == 0 && any && max_r > 0) good = 1;  // the maximum alone is always the reference's next merge
+    // index ranges of the merges, one lane each
+    u64 n = 0;
+    if (lane < good) {
+        u64 rg[3];
+        winner_range(d.key, rg);
+        B->a[lane] = a; B->b[lane] = b; B->key[lane] = d.key; B->cnt[lane] = d.cnt;
+        B->lo[lane] = rg[0]; B->src[lane] = T_SRC(rg[2]);
+        B->want[lane] = (a > b ? a : b) < 256 ? WANT_ANY : (b >= a ? a : (0x80000000u | b));
+        n = rg[1] - rg[0];
+    }
+    u64 inc = n;
+#pragma unroll
+    for (int k = 1; k < (int)MG_BATCH; k <<= 1) { const u64 t = __shfl_up_sync(0xffffffffu, inc, k); if (lane >= (u32)k) inc += t; }
+    if (lane < good) B->pre[lane + 1] = inc;
+    if (lane == 0) { B->pre[0] = 0; B->r = good; }
 }
 
-// Called by all threads of the CTA; `mine` is read from lane 0 of warp 0, *s_cand is the same candidate in shared memory
-// (for warp 1).  Returns the maximum of all CTAs' candidates in every lane of warp 0 (other warps: BEST_NONE) and, in `sup`,
-// the index of the CTA that supplied it.
-__device__ __forceinline__ Best grid_gather(BarSlot *slots, u32 *counter, u32 G, u32 epoch, const Best &mine, u32 &sup,
-                                            const Best *s_cand, int step, u64 *tp = nullptr) {
+__device__ __forceinline__ uint4 ldcg_v4(const void *p) { return __ldcg(reinterpret_cast<const uint4 *>(p)); }
+// Called by all threads of the CTA; `mine` (the CTA's two best pairs and its bound) is read from lane 0 of warp 0.
+// s_c / s_cnt: 2 * MG_MAX_CTAS candidates, s_h: MG_NT / 32 words, s_surv: MG_SURV + MG_BATCH + 1 candidates.
+__device__ __forceinline__ void grid_gather(BarSlot *slots, u32 *counter, u32 G, u32 epoch, const Top2 &mine, Best *s_c, i64 *s_cnt, i64 *s_h,
+                                            Best *s_surv, Batch *B, u32 max_r, u64 *tp = nullptr) {
     __syncthreads();
-    if (threadIdx.x >= 32 && threadIdx.x < 64) gather_side_work(slots, epoch, *s_cand, step);
 #ifdef BPE_MERGE_PROFILE
     if (tp && threadIdx.x == 0) tp[0] = gtime_ns();
 #endif
-    Best c = BEST_NONE;
     if (threadIdx.x < 32) {
-        const u32 lane = threadIdx.x;
-        if (lane == 0) store_best(reinterpret_cast<Best *>(slots[blockIdx.x].w), mine);
+        if (threadIdx.x == 0) {
+            u64 *w = slots[blockIdx.x].w;
+            store_best(reinterpret_cast<Best *>(w), mine.m1);
+            store_best(reinterpret_cast<Best *>(w + 4), mine.m2);
+            w[8] = (u64)mine.h;
+        }
         counter_arrive_wait(counter, epoch * G);
-        Best o5[MG_MAX_CTAS / 32];
-#pragma unroll
-        for (u32 k = 0; k < MG_MAX_CTAS / 32; k++) { const u32 i = lane + 32 * k; o5[k] = i < G ? load_best(reinterpret_cast<const Best *>(slots[i].w)) : BEST_NONE; }
-#pragma unroll
-        for (u32 k = 0; k < MG_MAX_CTAS / 32; k++) if (o5[k].cnt != CNT_DEAD && best_greater(o5[k], c)) c = o5[k];
-        c = warp_best(c);
-        u32 who = 0xFFFFFFFFu;                   // a key lives in one block, so exactly one CTA supplied the winner
-#pragma unroll
-        for (u32 k = 0; k < MG_MAX_CTAS / 32; k++) if (lane + 32 * k < G && o5[k].cnt != CNT_DEAD && o5[k].key == c.key) who = lane + 32 * k;
-        const u32 m = __ballot_sync(0xffffffffu, who != 0xFFFFFFFFu);
-        sup = m ? __shfl_sync(0xffffffffu, who, __ffs(m) - 1) : 0xFFFFFFFFu;
+    }
+    __syncthreads();
+#ifdef BPE_MERGE_PROFILE
+    const bool pt = tp && threadIdx.x == 0 && blockIdx.x == 0;
+    u64 q0 = pt ? gtime_ns() : 0;
+#endif
+    // one candidate per thread: a single round trip for the whole gather
+    const u32 tid = threadIdx.x;
+    i64 h = CNT_DEAD;
+    if (tid < 2 * G) {
+        const u64 *w = slots[tid >> 1].w + 4 * (tid & 1u);
+        const uint4 lo = ldcg_v4(w), hi = ldcg_v4(w + 2);
+        if (!(tid & 1u)) h = (i64)__ldcg(slots[tid >> 1].w + 8);
+        Best b;
+        b.cnt = (i64)(((u64)lo.y << 32) | lo.x); b.key = ((u64)lo.w << 32) | lo.z;
+        b.ka = ((u64)hi.y << 32) | hi.x; b.kb = ((u64)hi.w << 32) | hi.z;
+        s_c[tid] = b; s_cnt[tid] = b.cnt;
+    }
+    if (tid >= MG_NT - MG_SURV) s_surv[tid - (MG_NT - MG_SURV)] = BEST_NONE;
+    h = warp_max_cnt(h);
+    if (lane_id() == 0) s_h[tid >> 5] = h;
+    __syncthreads();
+#ifdef BPE_MERGE_PROFILE
+    u64 q1 = pt ? gtime_ns() : 0;
+#endif
+    rank_bests(s_c, s_cnt, s_surv, G);
+    __syncthreads();
+#ifdef BPE_MERGE_PROFILE
+    u64 q2 = pt ? gtime_ns() : 0;
+#endif
+    if (tid < 32) {
+        i64 hh = tid < MG_NT / 32 ? s_h[tid] : CNT_DEAD;
+        hh = warp_max_cnt(hh);
+        select_batch(s_surv, s_surv + MG_SURV, hh, B, max_r);
     }
     __syncthreads();
 #ifdef BPE_MERGE_PROFILE
     if (tp && threadIdx.x == 0) tp[1] = gtime_ns();
+    if (pt) { u64 q3 = gtime_ns(); cM.prof[10] += q0 - tp[0]; cM.prof[11] += q1 - q0; cM.prof[12] += q2 - q1; cM.prof[13] += q3 - q2; }
 #endif
-    return c;
+}
+
+// ---- token bookkeeping: bytes and prefix keys of the new tokens, outputs (one CTA, all its threads; warp j = merge j) ------
+__device__ __forceinline__ void token_bookkeeping(int step0, u32 nw0, const Batch *B, u32 *s_off) {
+    const u32 tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+    const u32 r = B->r;
+    if (warp == 0) {
+        u32 ln = 0;
+        if (lane < r) ln = cM.tok_len[B->a[lane]] + cM.tok_len[B->b[lane]];
+        u32 inc = ln;
+#pragma unroll
+        for (int d = 1; d < (int)MG_BATCH; d <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (u32)d) inc += t; }
+        if (lane < r) s_off[lane] = inc - ln;
+        if (lane == r - 1) s_off[MG_BATCH] = inc;
+    }
+    const u64 cur = cM.ctr[4];
+    const u64 live = cM.ctr[2];
+    __syncthreads();
+    const u64 total = s_off[MG_BATCH];
+    if (cur + total > cM.tok_bytes_cap) { if (tid == 0) cM.ctr[3] = 4; }
+    else {
+        if (warp < r) {
+            const u32 a = B->a[warp], b = B->b[warp], nw = nw0 + warp;
+            const u32 la = cM.tok_len[a], lb = cM.tok_len[b], ln = la + lb;
+            const u64 at = cur + s_off[warp];
+            uint8_t *dst = cM.tok_bytes + at;
+            const uint8_t *pa = cM.tok_bytes + cM.tok_off[a], *pb = cM.tok_bytes + cM.tok_off[b];
+            for (u32 i = lane; i < ln; i += 32) dst[i] = i < la ? pa[i] : pb[i - la];
+            if (lane == 0) {
+                // first 8 bytes of a+b from the operands' zero-padded big-endian prefix keys
+                u64 nkey = cM.tok_key[a];
+                if (la < 8) nkey |= cM.tok_key[b] >> (8 * la);
+                cM.tok_off[nw] = (u32)at; cM.tok_len[nw] = ln; cM.tok_key[nw] = nkey;
+                const int step = step0 + (int)warp;
+                cM.merges_out[2 * step] = (int32_t)a; cM.merges_out[2 * step + 1] = (int32_t)b;
+                cM.merge_cnt_out[step] = B->cnt[warp];
+            }
+            // make sure the winner's block is rescanned so the key gets popped
+            if (lane == 1) {
+                const u64 key = B->key[warp], mask = cM.pcap - 1;
+                u64 s = pair_hash(key) & mask;
+                while (cM.pkey[s] != key) s = (s + 1) & mask;
+                mark_dirty(s);
+            }
+        }
+        if (tid == 0) {
+            cM.ctr[4] = cur + total;
+            cM.ctr[1] = (u64)(step0 + (int)r);
+            const u64 popped = cM.ctr[5];
+            cM.ctr[7] += (u64)r * (live - popped) - (u64)r * (r - 1) / 2; cM.ctr[5] = popped + r;
+            cM.ctr[12] += 1;
+        }
+    }
 }
 
 // ---- shared-memory copy of the cached block maxima a CTA owns (structure of arrays: conflict-free 8-byte accesses) ----
-#define MG_CACHE_ITERS 5u                        // chunks (of 64 blocks) per warp kept in shared memory; more are read from bmax
+#define MG_CACHE_ITERS 4u                        // chunks (of 64 blocks) per warp kept in shared memory; more are read from bmax
 #define MG_CACHE_N (MG_CACHE_ITERS * (MG_NT / 32) * 64u)
-#define MG_LIST_CAP 4096u                        // dirty blocks a CTA lists per step; the overflow is rescanned by the owning warp
-#define MG_DYN_SMEM ((size_t)MG_CACHE_N * 32 + (size_t)MG_LIST_CAP * 4)
-struct BmaxCache { i64 *cnt; u64 *key, *ka, *kb; };
+#define MG_LIST_CAP 2048u                        // dirty blocks a CTA lists per step; the overflow is rescanned by the owning warp
+#define MG_DYN_SMEM ((size_t)MG_CACHE_N * 36 + (size_t)MG_LIST_CAP * 4)
+struct BmaxCache { i64 *cnt; u64 *key, *ka, *kb; u32 *sec; };
 __device__ __forceinline__ BmaxCache bmax_cache(unsigned char *base) {
     BmaxCache c;
     c.cnt = reinterpret_cast<i64 *>(base); c.key = reinterpret_cast<u64 *>(base) + MG_CACHE_N;
-    c.ka = c.key + MG_CACHE_N; c.kb = c.ka + MG_CACHE_N;
+    c.ka = c.key + MG_CACHE_N; c.kb = c.ka + MG_CACHE_N; c.sec = reinterpret_cast<u32 *>(c.kb + MG_CACHE_N);
     return c;
 }
-__device__ __forceinline__ void cache_store(const BmaxCache &c, u32 i, const Best &b) { c.cnt[i] = b.cnt; c.key[i] = b.key; c.ka[i] = b.ka; c.kb[i] = b.kb; }
-__device__ __forceinline__ void cache_consider(const BmaxCache &c, u32 i, Best &mine) {
+__device__ __forceinline__ void cache_store(const BmaxCache &c, u32 i, const Best &b, u32 sec) { c.cnt[i] = b.cnt; c.key[i] = b.key; c.ka[i] = b.ka; c.kb[i] = b.kb; c.sec[i] = sec; }
+__device__ __forceinline__ void cache_consider(const BmaxCache &c, u32 i, Top2 &mine) {
+    const i64 s2 = sec_unpack(c.sec[i]);
+    if (s2 > mine.h) mine.h = s2;
     const i64 n = c.cnt[i];
-    if (n == CNT_DEAD || n < mine.cnt) return;
+    if (n == CNT_DEAD) return;
+    if (n < mine.m2.cnt) { if (n > mine.h) mine.h = n; return; }
     Best o; o.cnt = n; o.key = c.key[i]; o.ka = c.ka[i]; o.kb = c.kb[i];
-    if (best_greater(o, mine)) mine = o;
+    top2_add(mine, o);
 }
 
 __global__ void __launch_bounds__(MG_NT) k_merge_loop() {
-    __shared__ Best s_best[MG_NT / 32];
-    __shared__ Best s_win, s_cand;
+    __shared__ Best s_w1[MG_NT / 32], s_w2[MG_NT / 32];
+    __shared__ i64 s_wh[MG_NT / 32];
+    __shared__ Best s_c[2 * MG_MAX_CTAS];
+    __shared__ i64 s_cnt[2 * MG_MAX_CTAS], s_h[MG_NT / 32];
+    __shared__ Best s_surv[MG_SURV + MG_BATCH + 1];
+    __shared__ Batch s_B;
     __shared__ u64 s_status[2];
-    __shared__ u64 s_range[4];
     __shared__ u32 s_scan[SORT_MAX_BK];
+    __shared__ u32 s_wsum[32];                   // (sort_slice writes all 32 entries)
+    __shared__ u32 s_off[MG_BATCH + 1];
     __shared__ u32 s_nd;                         // dirty blocks listed in this step
     extern __shared__ __align__(16) unsigned char mg_smem[];
     const u32 tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
@@ -669,42 +841,49 @@ __global__ void __launch_bounds__(MG_NT) k_merge_loop() {
     const u32 gwarp = blockIdx.x * warps_per_cta + warp, total_warps = G * warps_per_cta;
     const bool token_cta = blockIdx.x == G - 1;
     const u32 apply_ctas = G - 1;
-    u64 prev_key = cM.ctr[6];                     // winner of the previous step: popped lazily during the rescan
     const int first_step = (int)cM.ctr[1];
-    u32 n_tok = 256 + (u32)first_step;
+    // winners of the previous step: popped lazily during the rescans of this step (they stay in s_B until the next gather)
+    if (tid == 0) {
+        const u32 np = (u32)cM.ctr[6];
+        s_B.r = np <= MG_BATCH ? np : 0;
+        for (u32 i = 0; i < s_B.r; i++) s_B.key[i] = cM.ctr[MG_CTR_PENDING + i];
+        s_nd = 0;
+    }
+    if (tid < 2 * MG_MAX_CTAS) { s_c[tid] = BEST_NONE; s_cnt[tid] = CNT_DEAD; }
     // The cached block maxima of the chunks this CTA owns stay in shared memory for the whole launch (chunk (it, warp) =
-    // 64 blocks starting at (it * total_warps + gwarp) * 64); bmax in global memory is written through for the next launch.
+    // 64 blocks starting at (it * total_warps + gwarp) * 64); bmax / bsec in global memory are written through for the next launch.
     const BmaxCache sc = bmax_cache(mg_smem);
-    if (tid == 0) s_nd = 0;
-    u32 *s_list = reinterpret_cast<u32 *>(mg_smem + (size_t)MG_CACHE_N * 32);
+    u32 *s_list = reinterpret_cast<u32 *>(mg_smem + (size_t)MG_CACHE_N * 36);
     const u32 n_iter = (cM.n_blocks + total_warps * 64 - 1) / (total_warps * 64);
     for (u32 it = 0; it < n_iter && it < MG_CACHE_ITERS; it++) {
         const u32 base = (it * total_warps + gwarp) * 64, i0 = (it * warps_per_cta + warp) * 64 + lane;
-        cache_store(sc, i0, base + lane < cM.n_blocks ? load_best(&cM.bmax[base + lane]) : BEST_NONE);
-        cache_store(sc, i0 + 32, base + 32 + lane < cM.n_blocks ? load_best(&cM.bmax[base + 32 + lane]) : BEST_NONE);
+        const bool in0 = base + lane < cM.n_blocks, in1 = base + 32 + lane < cM.n_blocks;
+        cache_store(sc, i0, in0 ? load_best(&cM.bmax[base + lane]) : BEST_NONE, in0 ? cM.bsec[base + lane] : 0u);
+        cache_store(sc, i0 + 32, in1 ? load_best(&cM.bmax[base + 32 + lane]) : BEST_NONE, in1 ? cM.bsec[base + 32 + lane] : 0u);
     }
     __syncthreads();
 
-    for (int step = first_step; step < cM.stop_at; step++) {
+    int step = first_step;
+    while (step < cM.stop_at) {
         // status flags are written before the barrier that ends a step and read here (uniform across the grid); the loads
         // overlap with the dirty-flag loads of phase 1A and are checked behind its CTA barrier
         u64 st_err = 0, st_keys = 0;
         if (tid == 0) { st_err = *((volatile u64 *)&cM.ctr[3]); st_keys = *((volatile u64 *)&cM.ctr[2]); }
-        // ---- phase 1: rescan dirty blocks, reduce cached block maxima to one candidate per CTA ----
-        if (blockIdx.x == 0 && tid == 0) cM.log_begin[step] = cM.ctr[0];
+        // ---- phase 1: rescan dirty blocks, reduce cached block maxima to two candidates per CTA ----
+        // log cursor at the start of the step (a slot of its own per step: a fast CTA 0 must not overwrite the value the
+        // others still have to read after the barrier that ends the previous step)
+        if (blockIdx.x == 0 && tid == 0) cM.log_rng[2 * (u64)step] = *((volatile u64 *)&cM.ctr[0]);
 #ifdef BPE_MERGE_PROFILE
         const bool prof_thread = tid == 0 && (blockIdx.x == 0 || token_cta);
-#else
-        const bool prof_thread = false;
-#endif
-        u64 t0 = prof_thread ? gtime_ns() : 0;
-#ifdef BPE_MERGE_PROFILE
         u64 *ctp = cM.cta_prof ? cM.cta_prof + ((size_t)step * G + blockIdx.x) * 4 : nullptr;
         if (ctp && tid == 0) ctp[0] = gtime_ns();
 #else
+        const bool prof_thread = false;
         u64 *ctp = nullptr;
 #endif
-        Best mine = BEST_NONE;
+        u64 t0 = prof_thread ? gtime_ns() : 0;
+        const u32 n_prev = s_B.r;
+        const u64 *prev = s_B.key;
         // A: collect the dirty blocks of this CTA's chunks in a shared list (any warp of the CTA may rescan them)
         for (u32 it = 0; it < n_iter; it++) {
             const u32 base = (it * total_warps + gwarp) * 64;
@@ -724,8 +903,12 @@ __global__ void __launch_bounds__(MG_NT) k_merge_loop() {
                     u64 dm = (u64)__ballot_sync(0xffffffffu, d0 && e0 >= MG_LIST_CAP) | ((u64)__ballot_sync(0xffffffffu, d1 && e1 >= MG_LIST_CAP) << 32);
                     while (dm) {
                         const u32 l2 = __ffsll((long long)dm) - 1; dm &= dm - 1;
-                        const Best bst = rescan_block(base + l2, prev_key);
-                        if (lane == 0) { store_best(&cM.bmax[base + l2], bst); cM.dirty[base + l2] = 0; if (it < MG_CACHE_ITERS) cache_store(sc, (it * warps_per_cta + warp) * 64 + l2, bst); }
+                        u32 sec;
+                        const Best bst = rescan_block(base + l2, prev, n_prev, sec);
+                        if (lane == 0) {
+                            store_best(&cM.bmax[base + l2], bst); cM.bsec[base + l2] = sec; cM.dirty[base + l2] = 0;
+                            if (it < MG_CACHE_ITERS) cache_store(sc, (it * warps_per_cta + warp) * 64 + l2, bst, sec);
+                        }
                     }
                 }
             }
@@ -735,25 +918,27 @@ __global__ void __launch_bounds__(MG_NT) k_merge_loop() {
         if (s_status[0]) break;
         if (s_status[1] * 2 > cM.pcap) {         // table over half full: hand back to the host to grow it
             grid_barrier(cM.bar_ctr, G, ++epoch);
-            if (blockIdx.x == 0 && tid == 0) { cM.ctr[6] = prev_key; cM.ctr[3] = MG_NEED_GROW; }
-            return;
+            if (blockIdx.x == 0 && tid == 0) cM.ctr[3] = MG_NEED_GROW;
+            break;
         }
         // B: the CTA's warps share the rescans evenly
         {
             const u32 nd = s_nd < MG_LIST_CAP ? s_nd : MG_LIST_CAP;
             for (u32 e = warp; e < nd; e += warps_per_cta) {
                 const u32 blk = s_list[e];
-                const Best bst = rescan_block(blk, prev_key);
+                u32 sec;
+                const Best bst = rescan_block(blk, prev, n_prev, sec);
                 if (lane == 0) {
-                    store_best(&cM.bmax[blk], bst); cM.dirty[blk] = 0; PROF_ADD(9, 1);
+                    store_best(&cM.bmax[blk], bst); cM.bsec[blk] = sec; cM.dirty[blk] = 0; PROF_ADD(9, 1);
                     const u32 chunk = blk >> 6, it = chunk / total_warps, w = chunk - it * total_warps - blockIdx.x * warps_per_cta;
-                    if (it < MG_CACHE_ITERS) cache_store(sc, (it * warps_per_cta + w) * 64 + (blk & 63u), bst);
+                    if (it < MG_CACHE_ITERS) cache_store(sc, (it * warps_per_cta + w) * 64 + (blk & 63u), bst, sec);
                 }
             }
         }
         __syncthreads();
         if (tid == 0) s_nd = 0;                  // (next written in phase A of the next step)
-        // C: maximum of the cached block maxima this warp owns (shared memory; global for chunks beyond the cache)
+        // C: the two largest of the cached block maxima this warp owns (shared memory; global for chunks beyond the cache)
+        Top2 mine = top2_none();
         for (u32 it = 0; it < n_iter; it++) {
             if (it < MG_CACHE_ITERS) {
                 const u32 i0 = (it * warps_per_cta + warp) * 64 + lane;
@@ -762,71 +947,52 @@ __global__ void __launch_bounds__(MG_NT) k_merge_loop() {
             } else {
                 const u32 base = (it * total_warps + gwarp) * 64;
                 const u32 b0 = base + lane, b1 = base + 32 + lane;
-                Best m0 = BEST_NONE, m1 = BEST_NONE;
-                if (b0 < cM.n_blocks) m0 = load_best(&cM.bmax[b0]);
-                if (b1 < cM.n_blocks) m1 = load_best(&cM.bmax[b1]);
-                if (m0.cnt != CNT_DEAD && best_greater(m0, mine)) mine = m0;
-                if (m1.cnt != CNT_DEAD && best_greater(m1, mine)) mine = m1;
+                if (b0 < cM.n_blocks) { const i64 s2 = sec_unpack(cM.bsec[b0]); if (s2 > mine.h) mine.h = s2; top2_add(mine, load_best(&cM.bmax[b0])); }
+                if (b1 < cM.n_blocks) { const i64 s2 = sec_unpack(cM.bsec[b1]); if (s2 > mine.h) mine.h = s2; top2_add(mine, load_best(&cM.bmax[b1])); }
             }
         }
-        mine = warp_best(mine);
-        if (lane == 0) s_best[warp] = mine;
+        mine = warp_top2(mine);
+        if (lane == 0) { s_w1[warp] = mine.m1; s_w2[warp] = mine.m2; s_wh[warp] = mine.h; }
         __syncthreads();
-        Best cta_cand = BEST_NONE;
+        Top2 cta = top2_none();
         if (warp == 0) {
-            Best c = lane < warps_per_cta ? s_best[lane] : BEST_NONE;
-            cta_cand = warp_best(c);
+            // 32 candidates, one per lane: the best of warp l in lane l, its second best in lane 16 + l
+            Top2 t = top2_none();
+            t.m1 = lane < warps_per_cta ? s_w1[lane] : s_w2[lane - warps_per_cta];
+            t.h = lane < warps_per_cta ? s_wh[lane] : CNT_DEAD;
+            cta = warp_top2(t);
         }
         u64 t1 = prof_thread ? gtime_ns() : 0;
-        // ---- barrier + all-gather of the CTA candidates: every CTA derives the same winner ----
-        u32 sup = 0xFFFFFFFFu;
-        if (warp == 0 && lane == 0) s_cand = cta_cand;
-        ++gepoch;
-        Best gw = grid_gather(cM.bar, cM.bar_ctr + 32, G, gepoch, cta_cand, sup, &s_cand, step, ctp ? ctp + 1 : nullptr);
+        // ---- barrier + all-gather of the CTA candidates: every CTA derives the same merges for this step ----
+        const u32 max_r = min(cM.max_batch, (u32)(cM.stop_at - step));
+        grid_gather(cM.bar, cM.bar_ctr + 32, G, ++gepoch, cta, s_c, s_cnt, s_h, s_surv, &s_B, max_r, ctp ? ctp + 1 : nullptr);
         u64 t2 = prof_thread ? gtime_ns() : 0;
-        if (warp == 0 && lane == 0) {
-            s_win = gw;
-            if (gw.cnt != CNT_DEAD) {            // index range of the winner, read once per CTA: published by its supplier, or looked up
-                bool have = false;
-                if (sup != 0xFFFFFFFFu && gepoch < (1u << 22)) {
-                    u64 w6, w7;
-                    ld_relaxed_v2(&cM.bar[sup].w[6], w6, w7);
-                    if ((w6 & (0xFFFFFFull << 40)) == RANGE_TAG0(gepoch) && (w7 & (0x3FFFFFull << 42)) == RANGE_TAG1(gepoch)) {
-                        s_range[0] = w6 & ((1ull << 40) - 1); s_range[1] = w7 & ((1ull << 40) - 1); s_range[2] = (w7 >> 40) & 3u;
-                        have = true;
-                    }
-                }
-                if (!have) winner_range(gw.key, s_range);
-            }
-        }
-        __syncthreads();
-        const Best win = s_win;
-        if (win.cnt == CNT_DEAD) break;          // len(byte_pair_frequencies) == 0 (train.py:184-185)
-        const u32 a = (u32)(win.key >> 32), b = (u32)win.key;
-        const u32 nw = n_tok;                    // symbol id of new_byte = a + b (train.py:190)
-        const u64 r_lo = s_range[0], r_hi = s_range[1];
+        const u32 r = s_B.r;
+        if (r == 0) break;                       // len(byte_pair_frequencies) == 0 (train.py:184-185)
+        const u32 nw0 = 256 + (u32)step;         // symbol ids of the new tokens: nw0 + j = a_j + b_j (train.py:190)
+        const u64 n_rec = s_B.pre[r];
 
-        if (token_cta) token_bookkeeping(step, win, a, b, nw, prof_thread, t2);
-        // Records are dealt to the warps of all apply CTAs R at a time, R as small as one pass over the slice allows (but not
+        if (token_cta) token_bookkeeping(step, nw0, &s_B, s_off);
+        // Records are dealt to the warps of all apply CTAs R at a time, R as small as one pass over the slices allows (but not
         // below cM.min_rec): a step with a few hundred occurrences runs a few lanes on every SM instead of sixteen full warps on
         // one SM, with less divergence between the sites that share a warp.
         else {
-            const u64 n_rec = r_hi - r_lo, aw = (u64)apply_ctas * warps_per_cta;
+            const u64 aw = (u64)apply_ctas * warps_per_cta;
             u32 R = 32;
             while (R > cM.min_rec && n_rec <= aw * (R >> 1)) R >>= 1;
-            if (lane < R) apply_winner(step, a, b, nw, r_lo, r_hi, T_SRC(s_range[2]), ((u64)warp * apply_ctas + blockIdx.x) * R + lane, aw * R);
+            if (lane < R) apply_batch(step, nw0, &s_B, ((u64)warp * apply_ctas + blockIdx.x) * R + lane, aw * R);
         }
-        prev_key = win.key;
-        n_tok++;
         u64 t3 = prof_thread ? gtime_ns() : 0;
         u64 tp2[2];
         grid_barrier(cM.bar_ctr, G, ++epoch, ctp ? tp2 : nullptr);
         if (ctp && tid == 0) ctp[3] = tp2[0];
-        if ((r_hi - r_lo) * 2 >= SORT_MIN) {     // heuristic: about two records per index entry visited
-            const u64 lb = *((volatile u64 *)&cM.log_begin[step]), cur = *((volatile u64 *)&cM.ctr[0]);
+        // the slice of the log this step wrote belongs to all its merges
+        const u64 lb = *((volatile u64 *)&cM.log_rng[2 * (u64)step]), cur = *((volatile u64 *)&cM.ctr[0]);
+        if (blockIdx.x == 0 && tid < r) { cM.log_rng[2 * (u64)(step + (int)tid)] = lb; cM.log_rng[2 * (u64)(step + (int)tid) + 1] = cur; }
+        if (n_rec * 2 >= cM.sort_min) {          // heuristic: about two records per index entry visited
             const u64 pool = *((volatile u64 *)&cM.ctr[9]);
-            if (cur - lb >= SORT_MIN && cur <= cM.log_cap && pool + SORT_MAX_BK + 1 <= cM.bk_off_cap) {
-                sort_slice(step, lb, (u32)(cur - lb), n_sorts & 1u, blockIdx.x == 0, (u64)blockIdx.x * MG_NT + tid, (u64)G * MG_NT, s_scan,
+            if (cur - lb >= cM.sort_min && cur <= cM.log_cap && pool + SORT_MAX_BK + 1 <= cM.bk_off_cap) {
+                sort_slice(step, r, lb, (u32)(cur - lb), n_sorts & 1u, blockIdx.x == 0, (u64)blockIdx.x * MG_NT + tid, (u64)G * MG_NT, s_scan, s_wsum,
                            [&]() { grid_barrier(cM.bar_ctr, G, ++epoch); });
                 n_sorts++;
             }
@@ -837,245 +1003,19 @@ __global__ void __launch_bounds__(MG_NT) k_merge_loop() {
                 cM.prof[0] += t1 - t0; cM.prof[1] += t2 - t1; cM.prof[2] += t3 - t2; cM.prof[3] += t4 - t3; cM.prof[7] += 1;
                 if (cM.step_prof) {
                     cM.step_prof[4 * step] = (u32)(t2 - t0); cM.step_prof[4 * step + 1] = (u32)(t4 - t2);
-                    cM.step_prof[4 * step + 2] = (u32)cM.prof[5]; cM.step_prof[4 * step + 3] = (u32)cM.prof[6];
+                    cM.step_prof[4 * step + 2] = (u32)cM.prof[5]; cM.step_prof[4 * step + 3] = r;
                 }
             }
             if (token_cta) cM.prof[4] += t3 - t2;
         }
+        step += (int)r;
     }
-    if (blockIdx.x == 0 && tid == 0) cM.ctr[6] = prev_key;
-}
-
-
-// =============================================================================================
-// Tail kernel: the same loop run by ONE thread-block cluster.
-//
-// After the first ~thousand merges a step touches a handful of words, and its cost in k_merge_loop is the latency
-// of two grid-wide barriers plus the L2 round trips of the cross-CTA arg-max.  Inside one cluster the barrier is the
-// hardware cluster barrier (0.27 us for 16 CTAs against 1.2 us for the grid barrier, tools/bench_gridsync.cu), the
-// per-superblock maxima live in shared memory and the per-CTA candidates travel through distributed shared memory.
-//   level 0  pair-table slots
-//   level 1  bmax[block]          global, PB slots per block
-//   level 2  s_smax[superblock]   shared memory of the CTA that owns the superblock (64 blocks), persistent across steps
-// Updates set a bit in sdirty_mask[superblock] (fire-and-forget atomicOr); a step rescans only those blocks.
-// =============================================================================================
-#define TAIL_MAX_CTAS 16u
-#define MG_STOP_ERROR 1u
-#define MG_STOP_GROW 2u
-
-__global__ void __launch_bounds__(256) k_tail_prepare() {
-    // dirty[] bytes of k_merge_loop -> per-superblock bit masks
-    for (u32 sb = blockIdx.x * blockDim.x + threadIdx.x; sb < cM.n_super; sb += gridDim.x * blockDim.x) {
-        u64 m = 0;
-        for (u32 j = 0; j < 64; j++) { u32 b = sb * 64 + j; if (b < cM.n_blocks && cM.dirty[b]) { m |= 1ull << j; cM.dirty[b] = 0; } }
-        cM.sdirty_mask[sb] = m;
-    }
-}
-
-__device__ __forceinline__ Best load_best_cg(const Best *p) {      // from L2: the entry may just have been written by another warp
-    const uint4 *q = reinterpret_cast<const uint4 *>(p);
-    uint4 lo = __ldcg(q), hi = __ldcg(q + 1);
-    Best b;
-    b.cnt = (i64)(((u64)lo.y << 32) | lo.x); b.key = ((u64)lo.w << 32) | lo.z;
-    b.ka = ((u64)hi.y << 32) | hi.x; b.kb = ((u64)hi.w << 32) | hi.z;
-    return b;
-}
-__device__ __forceinline__ u32 nth_set_bit64(u64 m, u32 n) {       // position of the n-th (0-based) set bit
-    for (u32 i = 0; i < n; i++) m &= m - 1;
-    return __ffsll((long long)m) - 1;
-}
-// maximum of superblock sb from its 64 cached block maxima
-__device__ __forceinline__ Best superblock_max(u32 sb, u32 lane) {
-    const u32 b0 = sb * 64 + lane, b1 = b0 + 32;
-    Best c = BEST_NONE;
-    if (b0 < cM.n_blocks) { Best m = load_best_cg(&cM.bmax[b0]); if (m.cnt != CNT_DEAD) c = m; }
-    if (b1 < cM.n_blocks) { Best m = load_best_cg(&cM.bmax[b1]); if (m.cnt != CNT_DEAD && best_greater(m, c)) c = m; }
-    return warp_best(c);
-}
-
-#define TAIL_LIST_MAX 1024u
-
-__global__ void __launch_bounds__(MG_NT) k_merge_tail() {
-    cg::cluster_group cl = cg::this_cluster();
-    extern __shared__ Best s_smax[];             // maxima of the superblocks this CTA owns: entry k * 16 + warp; then u32 s_sblist[]
-    __shared__ Best s_best[MG_NT / 32];
-    __shared__ Best s_cand[TAIL_MAX_CTAS];       // candidate of every CTA of the cluster (written through DSMEM)
-    __shared__ Best s_win;
-    __shared__ u64 s_range[4];
-    __shared__ u32 s_stop, s_nlist, s_nsb;
-    __shared__ u32 s_list[TAIL_LIST_MAX];        // dirty blocks of this CTA's superblocks (work list of the step)
-    __shared__ u32 s_scan[SORT_MAX_BK];
-    const u32 tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
-    const u32 C = cl.num_blocks(), rank = cl.block_rank();
-    const u32 warps_per_cta = MG_NT / 32;
-    const u32 gwarp = rank * warps_per_cta + warp, total_warps = C * warps_per_cta;
-    const u32 KS = (cM.n_super + total_warps - 1) / total_warps;   // superblocks per warp
-    u32 *s_sblist = reinterpret_cast<u32 *>(s_smax + (size_t)KS * warps_per_cta);
-    const bool token_cta = rank == C - 1;
-    const u32 apply_ctas = C - 1;
-    u64 prev_key = cM.ctr[6];
-    const int first_step = (int)cM.ctr[1];
-    u32 n_tok = 256 + (u32)first_step;
-    u32 n_sorts = 0;
-    if (tid == 0) {
-        u64 st = *((volatile u64 *)&cM.ctr[3]), keys = *((volatile u64 *)&cM.ctr[2]);
-        s_stop = st ? MG_STOP_ERROR : (keys * 2 > cM.pcap ? MG_STOP_GROW : 0u);
-        s_nlist = 0; s_nsb = 0;
-    }
+    // the winners of the last step are still to be popped: by the next launch, or dropped by the table rebuild
     __syncthreads();
-    bool first = true;
-
-    for (int step = first_step; step < cM.stop_at; step++) {
-        const u32 stop = s_stop;                 // uniform across the cluster (broadcast before the closing barrier)
-        if (stop == MG_STOP_ERROR) break;
-        if (stop == MG_STOP_GROW) {
-            if (rank == 0 && tid == 0) { cM.ctr[6] = prev_key; cM.ctr[3] = MG_NEED_GROW; }
-            break;
-        }
-        if (rank == 0 && tid == MG_NT - 1) cM.log_begin[step] = *((volatile u64 *)&cM.ctr[0]);
-#ifdef BPE_MERGE_PROFILE
-        const bool prof_thread = tid == 0 && (rank == 0 || token_cta);
-#else
-        const bool prof_thread = false;
-#endif
-        u64 t0 = prof_thread ? gtime_ns() : 0;
-        // ---- phase 1a: collect the dirty blocks of the superblocks this CTA owns into a CTA-wide work list -----
-        for (u32 k0 = 0; k0 < KS; k0 += 32) {
-            const u32 kk = k0 + lane;
-            const u32 sbl = gwarp + kk * total_warps;
-            u64 my = (kk < KS && sbl < cM.n_super) ? cM.sdirty_mask[sbl] : 0;      // one round trip for 32 masks
-            const u32 kend = KS - k0 < 32 ? KS - k0 : 32;
-            for (u32 q = 0; q < kend; q++) {
-                const u32 k = k0 + q, sb = gwarp + k * total_warps;
-                u64 dm = __shfl_sync(0xffffffffu, my, q);
-                if (sb >= cM.n_super) { if (first && lane == 0) s_smax[k * warps_per_cta + warp] = BEST_NONE; continue; }
-                if (!first && dm == 0) continue; // (at kernel start every superblock maximum has to be built)
-                const u32 nb = cM.n_blocks - sb * 64;
-                if (nb < 64) dm &= (1ull << nb) - 1;
-                const u32 cnt = __popcll(dm);
-                u32 base = 0;
-                if (lane == 0 && cnt) base = atomicAdd(&s_nlist, cnt);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (lane == 0 && dm) cM.sdirty_mask[sb] = 0;
-                if (cnt && base + cnt > TAIL_LIST_MAX) {
-                    // work list full (table just rebuilt: everything is dirty): this warp does the superblock on its own
-                    for (u32 r = lane; r < cnt && base + r < TAIL_LIST_MAX; r += 32) s_list[base + r] = 0xFFFFFFFFu;
-                    const u32 b0 = sb * 64 + lane, b1 = b0 + 32;
-                    Best m0 = BEST_NONE, m1 = BEST_NONE;
-                    if (b0 < cM.n_blocks) m0 = load_best(&cM.bmax[b0]);
-                    if (b1 < cM.n_blocks) m1 = load_best(&cM.bmax[b1]);
-                    while (dm) {
-                        u32 j = __ffsll((long long)dm) - 1; dm &= dm - 1;
-                        Best bst = rescan_block(sb * 64 + j, prev_key);
-                        if (lane == (j & 31)) { if (j < 32) m0 = bst; else m1 = bst; store_best(&cM.bmax[sb * 64 + j], bst); }
-                    }
-                    Best c = BEST_NONE;
-                    if (m0.cnt != CNT_DEAD) c = m0;
-                    if (m1.cnt != CNT_DEAD && best_greater(m1, c)) c = m1;
-                    c = warp_best(c);
-                    if (lane == 0) s_smax[k * warps_per_cta + warp] = c;
-                    continue;
-                }
-                for (u32 r = lane; r < cnt; r += 32) s_list[base + r] = sb * 64 + nth_set_bit64(dm, r);
-                if (lane == 0) s_sblist[atomicAdd(&s_nsb, 1u)] = k * warps_per_cta + warp;
-            }
-        }
-        first = false;
-        __syncthreads();
-        u64 ta = prof_thread ? gtime_ns() : 0;
-        if (prof_thread && rank == 0) { cM.prof[20] += s_nlist; cM.prof[21] += s_nsb; }
-        // ---- phase 1b: rescan the listed blocks, spread evenly over the warps ---------------------------------
-        {
-            const u32 nl = s_nlist < TAIL_LIST_MAX ? s_nlist : TAIL_LIST_MAX;
-            for (u32 i = warp; i < nl; i += warps_per_cta) {
-                const u32 blk = s_list[i];
-                if (blk == 0xFFFFFFFFu) continue;
-                Best bst = rescan_block(blk, prev_key);
-                if (lane == 0) { store_best(&cM.bmax[blk], bst); PROF_ADD(9, 1); }
-            }
-        }
-        __threadfence_block();
-        __syncthreads();
-        u64 tb = prof_thread ? gtime_ns() : 0;
-        // ---- phase 1c: maxima of the superblocks that had dirty blocks ------------------------------------------
-        {
-            const u32 ns = s_nsb;
-            for (u32 i = warp; i < ns; i += warps_per_cta) {
-                const u32 local = s_sblist[i];
-                const u32 sb = rank * warps_per_cta + (local % warps_per_cta) + (local / warps_per_cta) * total_warps;
-                Best c = superblock_max(sb, lane);
-                if (lane == 0) s_smax[local] = c;
-            }
-        }
-        __syncthreads();
-        u64 tc = prof_thread ? gtime_ns() : 0;
-        if (tid == 0) { s_nlist = 0; s_nsb = 0; }
-        // ---- phase 2: CTA candidate from its superblock maxima, exchanged through distributed shared memory ----
-        {
-            Best mine = BEST_NONE;
-            for (u32 i = tid; i < KS * warps_per_cta; i += MG_NT) { Best e = s_smax[i]; if (e.cnt != CNT_DEAD && best_greater(e, mine)) mine = e; }
-            mine = warp_best(mine);
-            if (lane == 0) s_best[warp] = mine;
-            __syncthreads();
-            if (warp == 0) {
-                Best c = lane < warps_per_cta ? s_best[lane] : BEST_NONE;
-                c = warp_best(c);
-                if (lane < C) store_best(cl.map_shared_rank(&s_cand[rank], lane), c);
-            }
-        }
-        u64 t1 = prof_thread ? gtime_ns() : 0;
-        cl.sync();
-        u64 t2 = prof_thread ? gtime_ns() : 0;
-        if (warp == 0) {
-            Best c = lane < C ? load_best(&s_cand[lane]) : BEST_NONE;
-            c = warp_best(c);
-            if (lane == 0) {
-                s_win = c;
-                if (c.cnt != CNT_DEAD) winner_range(c.key, s_range);   // index range of the winner, read once per CTA
-            }
-        }
-        __syncthreads();
-        const Best win = s_win;
-        if (win.cnt == CNT_DEAD) break;          // len(byte_pair_frequencies) == 0 (train.py:184-185): uniform across the cluster
-        const u32 a = (u32)(win.key >> 32), b = (u32)win.key;
-        const u32 nw = n_tok;
-        const u64 r_lo = s_range[0], r_hi = s_range[1];
-        if (token_cta) {
-            token_bookkeeping(step, win, a, b, nw, prof_thread, t2);
-            if (tid == 0) {                      // stop code for the next step, broadcast to every CTA
-                u64 st = *((volatile u64 *)&cM.ctr[3]), keys = *((volatile u64 *)&cM.ctr[2]);
-                u32 code = st ? MG_STOP_ERROR : (keys * 2 > cM.pcap ? MG_STOP_GROW : 0u);
-                for (u32 r = 0; r < C; r++) *cl.map_shared_rank(&s_stop, r) = code;
-            }
-        } else {
-            apply_winner(step, a, b, nw, r_lo, r_hi, T_SRC(s_range[2]), (u64)rank * MG_NT + tid, (u64)apply_ctas * MG_NT);
-        }
-        prev_key = win.key;
-        n_tok++;
-        u64 t3 = prof_thread ? gtime_ns() : 0;
-        cl.sync();
-        if (prof_thread) {
-            u64 t4 = gtime_ns();
-            if (rank == 0) {
-                cM.prof[0] += t1 - t0; cM.prof[1] += t2 - t1; cM.prof[2] += t3 - t2; cM.prof[3] += t4 - t3; cM.prof[7] += 1;
-                cM.prof[16] += ta - t0; cM.prof[17] += tb - ta; cM.prof[18] += tc - tb; cM.prof[19] += t1 - tc; cM.prof[22] += r_hi - r_lo;
-            }
-            if (token_cta) cM.prof[4] += t3 - t2;
-        }
-        if ((r_hi - r_lo) * 2 >= SORT_MIN) {     // heuristic: about two records per index entry visited
-            u64 ts = prof_thread ? gtime_ns() : 0;
-            const u64 lb = *((volatile u64 *)&cM.log_begin[step]), cur = *((volatile u64 *)&cM.ctr[0]);
-            const u64 pool = *((volatile u64 *)&cM.ctr[9]);
-            if (cur - lb >= SORT_MIN && cur <= cM.log_cap && pool + SORT_MAX_BK + 1 <= cM.bk_off_cap) {
-                sort_slice(step, lb, (u32)(cur - lb), n_sorts & 1u, rank == 0, (u64)rank * MG_NT + tid, (u64)C * MG_NT, s_scan,
-                           [&]() { cl.sync(); });
-                n_sorts++;
-            }
-            if (prof_thread && rank == 0) { cM.prof[23] += gtime_ns() - ts; cM.prof[24] += 1; }
-        }
+    if (blockIdx.x == 0 && tid == 0) {
+        cM.ctr[6] = s_B.r;
+        for (u32 i = 0; i < s_B.r; i++) cM.ctr[MG_CTR_PENDING + i] = s_B.key[i];
     }
-    if (rank == 0 && tid == 0) cM.ctr[6] = prev_key;
-    cl.sync();                                   // nobody leaves while a peer may still touch its shared memory
 }
 
 __global__ void __launch_bounds__(256) k_insert_initial_pairs(const u64 *__restrict__ dense) {
@@ -1083,11 +1023,15 @@ __global__ void __launch_bounds__(256) k_insert_initial_pairs(const u64 *__restr
     if (p < 65536 && dense[p]) pair_add(p >> 8, p & 255u, (i64)dense[p]);
 }
 
-// Table growth: re-insert every live key of the old table (popped keys and the pending pop are dropped).
-__global__ void __launch_bounds__(256) k_pairs_rehash(const u64 *__restrict__ okey, const i64 *__restrict__ ocnt, u64 ocap, u64 pending_pop) {
+// Table growth: re-insert every live key of the old table (popped keys and the pending pops are dropped).
+struct PendingPops { u64 key[MG_BATCH]; u32 n; };
+__global__ void __launch_bounds__(256) k_pairs_rehash(const u64 *__restrict__ okey, const i64 *__restrict__ ocnt, u64 ocap, PendingPops pending) {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < ocap; i += (u64)gridDim.x * blockDim.x) {
         u64 k = okey[i];
-        if (k == PAIR_EMPTY || k == pending_pop) continue;
+        if (k == PAIR_EMPTY) continue;
+        bool popped = false;
+        for (u32 j = 0; j < pending.n; j++) popped |= k == pending.key[j];
+        if (popped) continue;
         i64 c = ocnt[i];
         if (c == CNT_DEAD) continue;
         if (c < CNT_DEAD_LIMIT) c = (i64)((u64)c - (u64)CNT_DEAD);     // popped, then touched again

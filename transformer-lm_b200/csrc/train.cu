@@ -431,10 +431,10 @@ BPE_API void bpe_debug_merge_profile(unsigned long long out[32]) { for (int i = 
 struct TrainBufs {
     DevBuf sym, wmeta, wctr;
     DevBuf dense, hist, csr_off, csr_rec;
-    DevBuf pkey, pcnt, bmax, dirty, sdirty, tok_key, prof, step_prof, merge_cnt, log, log2, bk_lg, bk_start, bk_off, bk_scratch, log_begin, tok_off, tok_len, tok_bytes, bar, cta_prof, merges, ctr;
+    DevBuf pkey, pcnt, bmax, bsec, dirty, tok_key, prof, step_prof, merge_cnt, log, log2, bk_lg, bk_start, bk_off, bk_scratch, log_rng, tok_off, tok_len, tok_bytes, bar, cta_prof, merges, ctr;
     void free_all(bpe_ctx *ctx) {
-        for (DevBuf *b : {&sym, &wmeta, &wctr, &dense, &hist, &csr_off, &csr_rec, &pkey, &pcnt, &bmax,
-                          &dirty, &sdirty, &tok_key, &prof, &step_prof, &merge_cnt, &log, &log2, &bk_lg, &bk_start, &bk_off, &bk_scratch, &log_begin, &tok_off, &tok_len, &tok_bytes, &bar, &cta_prof, &merges, &ctr})
+        for (DevBuf *b : {&sym, &wmeta, &wctr, &dense, &hist, &csr_off, &csr_rec, &pkey, &pcnt, &bmax, &bsec,
+                          &dirty, &tok_key, &prof, &step_prof, &merge_cnt, &log, &log2, &bk_lg, &bk_start, &bk_off, &bk_scratch, &log_rng, &tok_off, &tok_len, &tok_bytes, &bar, &cta_prof, &merges, &ctr})
             bpe_buf_free(ctx, *b);
     }
 };
@@ -836,27 +836,25 @@ static int run_merges(bpe_ctx *ctx, const uint8_t *sp_blob, const u32 *sp_offs, 
         M.pcap = cap; M.n_blocks = (u32)(cap / PB);
         BPE_TRY(alloc_exact(ctx, B.pkey, cap * 8)); BPE_TRY(alloc_exact(ctx, B.pcnt, cap * 8));
         BPE_TRY(alloc_exact(ctx, B.bmax, (u64)M.n_blocks * sizeof(Best))); BPE_TRY(alloc_exact(ctx, B.dirty, M.n_blocks));
+        BPE_TRY(alloc_exact(ctx, B.bsec, (u64)M.n_blocks * 4));
         CUDA_TRY(ctx, cudaMemsetAsync(B.pkey.p, 0xFF, cap * 8, st)); CUDA_TRY(ctx, cudaMemsetAsync(B.pcnt.p, 0, cap * 8, st));
-        CUDA_TRY(ctx, cudaMemsetAsync(B.dirty.p, 1, M.n_blocks, st));
-        M.n_super = (M.n_blocks + 63) / 64;
-        BPE_TRY(alloc_exact(ctx, B.sdirty, (u64)M.n_super * 8));
-        CUDA_TRY(ctx, cudaMemsetAsync(B.sdirty.p, 0, (u64)M.n_super * 8, st));
-        M.pkey = (u64 *)B.pkey.p; M.pcnt = (i64 *)B.pcnt.p; M.bmax = (Best *)B.bmax.p; M.dirty = (uint8_t *)B.dirty.p;
-        M.sdirty_mask = (u64 *)B.sdirty.p;
+        CUDA_TRY(ctx, cudaMemsetAsync(B.dirty.p, 1, M.n_blocks, st));          // every block is rescanned in the first step
+        CUDA_TRY(ctx, cudaMemsetAsync(B.bsec.p, 0, (u64)M.n_blocks * 4, st));
+        M.pkey = (u64 *)B.pkey.p; M.pcnt = (i64 *)B.pcnt.p; M.bmax = (Best *)B.bmax.p; M.bsec = (u32 *)B.bsec.p; M.dirty = (uint8_t *)B.dirty.p;
         return BPE_OK;
     };
     BPE_TRY(alloc_pair_table(pcap));
     u64 log_cap = 2 * n_syms + 16;
-    BPE_TRY(alloc_exact(ctx, B.log, log_cap * sizeof(Rec))); BPE_TRY(alloc_exact(ctx, B.log_begin, ((u64)n_merges + 2) * 8));
+    BPE_TRY(alloc_exact(ctx, B.log, log_cap * sizeof(Rec))); BPE_TRY(alloc_exact(ctx, B.log_rng, ((u64)n_merges + 2) * 16));
     u64 n_tok_max = 256 + (u64)n_merges;
     u64 tok_bytes_cap = 256 + (u64)n_merges * 2 * std::max<u64>(max_len, 1);
     if (tok_bytes_cap > (4ull << 30)) tok_bytes_cap = 4ull << 30;
     BPE_TRY(alloc_exact(ctx, B.tok_off, n_tok_max * 4)); BPE_TRY(alloc_exact(ctx, B.tok_len, n_tok_max * 4));
     BPE_TRY(alloc_exact(ctx, B.tok_key, n_tok_max * 8));
     BPE_TRY(alloc_exact(ctx, B.tok_bytes, tok_bytes_cap)); BPE_TRY(alloc_exact(ctx, B.merge_cnt, ((u64)n_merges + 1) * 8));
-    BPE_TRY(alloc_exact(ctx, B.merges, ((u64)n_merges + 1) * 8)); BPE_TRY(alloc_exact(ctx, B.ctr, 128));
+    BPE_TRY(alloc_exact(ctx, B.merges, ((u64)n_merges + 1) * 8)); BPE_TRY(alloc_exact(ctx, B.ctr, MG_CTR_WORDS * 8));
     BPE_TRY(alloc_exact(ctx, B.prof, 256)); CUDA_TRY(ctx, cudaMemsetAsync(B.prof.p, 0, 256, st));
-    CUDA_TRY(ctx, cudaMemsetAsync(B.log_begin.p, 0, ((u64)n_merges + 2) * 8, st));
+    CUDA_TRY(ctx, cudaMemsetAsync(B.log_rng.p, 0, ((u64)n_merges + 2) * 16, st));
     {   // byte tokens: bytes(i) = [i], rank(i) = i; counters
         std::vector<u32> toff(256), tlen(256, 1); std::vector<uint8_t> tb(256); std::vector<u64> tk(256);
         for (int i = 0; i < 256; i++) { toff[i] = i; tb[i] = (uint8_t)i; tk[i] = (u64)i << 56; }
@@ -864,13 +862,13 @@ static int run_merges(bpe_ctx *ctx, const uint8_t *sp_blob, const u32 *sp_offs, 
         CUDA_TRY(ctx, cudaMemcpyAsync(B.tok_len.p, tlen.data(), 1024, cudaMemcpyHostToDevice, st));
         CUDA_TRY(ctx, cudaMemcpyAsync(B.tok_key.p, tk.data(), 2048, cudaMemcpyHostToDevice, st));
         CUDA_TRY(ctx, cudaMemcpyAsync(B.tok_bytes.p, tb.data(), 256, cudaMemcpyHostToDevice, st));
-        for (int i = 0; i < 16; i++) host[i] = 0;
-        host[4] = 256; host[6] = PAIR_EMPTY;
-        CUDA_TRY(ctx, cudaMemcpyAsync(B.ctr.p, host, 128, cudaMemcpyHostToDevice, st));
+        for (int i = 0; i < MG_CTR_WORDS; i++) host[i] = 0;
+        host[4] = 256;
+        CUDA_TRY(ctx, cudaMemcpyAsync(B.ctr.p, host, MG_CTR_WORDS * 8, cudaMemcpyHostToDevice, st));
         CUDA_TRY(ctx, cudaStreamSynchronize(st));
     }
     M.csr_off = (const u32 *)B.csr_off.p; M.csr_rec = (const Rec *)B.csr_rec.p;
-    M.log = (Rec *)B.log.p; M.log_begin = (u64 *)B.log_begin.p; M.log_cap = log_cap;
+    M.log = (Rec *)B.log.p; M.log_rng = (u64 *)B.log_rng.p; M.log_cap = log_cap;
     {
         const u64 bk_cap = log_cap / 32 + (u64)(SORT_MAX_BK + 1) * 64 + 1024;
         BPE_TRY(alloc_exact(ctx, B.log2, log_cap * sizeof(Rec))); BPE_TRY(alloc_exact(ctx, B.bk_lg, ((u64)n_merges + 2) * 4));
@@ -886,6 +884,10 @@ static int run_merges(bpe_ctx *ctx, const uint8_t *sp_blob, const u32 *sp_offs, 
     M.step_prof = nullptr;
     M.min_rec = 1;                                   // measured at 11 GB, same box: 32 -> 433 ms, 8 -> 418, 2 -> 409, 1 -> 406
     if (const char *e = getenv("BPE_MERGE_MINREC")) M.min_rec = (u32)std::max(1, std::min(32, atoi(e)));
+    M.sort_min = 65536;                              // one pass of the apply phase covers 148 x 16 x 32 = 75 776 records
+    if (const char *e = getenv("BPE_MERGE_SORTMIN")) M.sort_min = (u32)std::max(64, atoi(e));
+    M.max_batch = MG_BATCH;                          // merges per grid step, at most (1 = the strictly sequential loop)
+    if (const char *e = getenv("BPE_MERGE_BATCH")) M.max_batch = (u32)std::max(1, std::min((int)MG_BATCH, atoi(e)));
     if (getenv("BPE_CTA_PROFILE")) { BPE_TRY(alloc_exact(ctx, B.cta_prof, (u64)n_merges * 160 * 32)); CUDA_TRY(ctx, cudaMemsetAsync(B.cta_prof.p, 0, (u64)n_merges * 160 * 32, st)); M.cta_prof = (u64 *)B.cta_prof.p; }
     if (getenv("BPE_STEP_PROFILE")) { BPE_TRY(alloc_exact(ctx, B.step_prof, ((u64)n_merges + 1) * 16)); CUDA_TRY(ctx, cudaMemsetAsync(B.step_prof.p, 0, ((u64)n_merges + 1) * 16, st)); M.step_prof = (u32 *)B.step_prof.p; }
 
@@ -904,82 +906,37 @@ static int run_merges(bpe_ctx *ctx, const uint8_t *sp_blob, const u32 *sp_offs, 
     const u64 bar_bytes = (u64)MG_MAX_CTAS * sizeof(BarSlot) + 512;   // gather slots, two counters
     BPE_TRY(alloc_exact(ctx, B.bar, bar_bytes));
     M.bar = (BarSlot *)B.bar.p; M.bar_ctr = (u32 *)(M.bar + MG_MAX_CTAS);
-    u64 ctr[8] = {0};
+    u64 ctr[MG_CTR_WORDS] = {0};
     u64 keys_created = 0;
-    // Two kernels run the same loop: k_merge_loop (grid-wide, cooperative) and k_merge_tail (one thread-block cluster:
-    // hardware cluster barrier, arg-max levels in shared memory / DSMEM).  Measured on B200 (1 GB OWT-shape, 31 743
-    // merges): 20.5 us/merge grid-wide against 27 us in the cluster, whose 16 SMs lose more in the apply phase than the
-    // cheaper barrier wins -- so the cluster kernel is opt-in: BPE_TAIL_AFTER=<step> switches to it from that step on
-    // (the tests run both and require identical merges).
-    int tail_after = 0x7fffffff;
-    if (const char *e = getenv("BPE_TAIL_AFTER")) tail_after = atoi(e);
-    int tail_ctas = 0;
-    if (tail_after < n_merges) {
-        cudaFuncSetAttribute((void *)k_merge_tail, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        for (int cs : {16, 8}) {
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(cs); cfg.blockDim = dim3(MG_NT); cfg.dynamicSmemBytes = 0;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            cfg.attrs = at; cfg.numAttrs = 1;
-            int ncl = 0;
-            if (cudaOccupancyMaxActiveClusters(&ncl, (void *)k_merge_tail, &cfg) == cudaSuccess && ncl >= 1) { tail_ctas = cs; break; }
-            cudaGetLastError();
-        }
-        if (!tail_ctas) tail_after = n_merges;   // no cluster launch possible: stay with the grid-wide kernel
-    }
+    M.stop_at = n_merges;
     for (int round = 0; n_merges > 0 && round < 64; round++) {
-        const int done_so_far = (int)ctr[1];
-        const bool tail = tail_ctas && done_so_far >= tail_after;
-        M.tail_mode = tail ? 1 : 0;
-        M.stop_at = tail ? n_merges : std::min(n_merges, std::max(tail_after, 0));
-        if (!tail_ctas) M.stop_at = n_merges;
         CUDA_TRY(ctx, cudaMemcpyToSymbolAsync(cM, &M, sizeof(M), 0, cudaMemcpyHostToDevice, st));
         CUDA_TRY(ctx, cudaMemsetAsync(B.bk_scratch.p, 0, (u64)4 * SORT_MAX_BK * 4, st));
-        if (tail) {
-            KLAUNCH(k_tail_prepare, (M.n_super + 255) / 256, 256, 0, st);
-            const u32 total_warps = (u32)tail_ctas * (MG_NT / 32);
-            const u32 KS = (M.n_super + total_warps - 1) / total_warps;
-            const size_t smem = (size_t)KS * (MG_NT / 32) * (sizeof(Best) + sizeof(u32));
-            if (smem > 160 * 1024) return bpe_set_error(ctx, BPE_ERR_UNSUPPORTED, "pair table too large for the tail kernel (%zu B of shared memory)", smem);
-            if (smem > 40 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute((void *)k_merge_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(tail_ctas); cfg.blockDim = dim3(MG_NT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = tail_ctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            cfg.attrs = at; cfg.numAttrs = 1;
-            g_bpe_launches++;
-            CUDA_TRY(ctx, cudaLaunchKernelExC(&cfg, (void *)k_merge_tail, nullptr));
-        } else {
-            CUDA_TRY(ctx, cudaMemsetAsync(B.bar.p, 0, bar_bytes, st));   // epochs restart at 0
-            // grid: one CTA per SM for big tables, fewer for small ones (cheaper barriers).  Measured at 11 GB with the counter
-            // barrier, same box: G = 148: 449 ms, 112: 464, 96: 463, 80: 481, 64: 485, 48: 535.  (With the per-CTA flag barrier
-            // that this replaced, 64 CTAs were the optimum: polling 148 slots cost more than the extra apply threads gave.)
-            int G = std::max(2, (int)std::min<u64>((u64)std::min(ctx->sm_count, (int)MG_MAX_CTAS), (u64)M.n_blocks / 256 + 1 + (n_words + 4095) / 4096));
-            if (const char *e = getenv("BPE_MERGE_G")) G = std::max(2, std::min(atoi(e), std::min(ctx->sm_count, (int)MG_MAX_CTAS)));
-            g_bpe_launches++;
-            CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_merge_loop, dim3(G), dim3(MG_NT), nullptr, MG_DYN_SMEM, st));
-        }
-        CUDA_TRY(ctx, cudaMemcpyAsync(host, B.ctr.p, 64, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaMemsetAsync(B.bar.p, 0, bar_bytes, st));   // epochs restart at 0
+        // grid: one CTA per SM for big tables, fewer for small ones (cheaper barriers).  Measured at 11 GB with the counter
+        // barrier, same box: G = 148: 449 ms, 112: 464, 96: 463, 80: 481, 64: 485, 48: 535.  (With the per-CTA flag barrier
+        // that this replaced, 64 CTAs were the optimum: polling 148 slots cost more than the extra apply threads gave.)
+        int G = std::max(2, (int)std::min<u64>((u64)std::min(ctx->sm_count, (int)MG_MAX_CTAS), (u64)M.n_blocks / 256 + 1 + (n_words + 4095) / 4096));
+        if (const char *e = getenv("BPE_MERGE_G")) G = std::max(2, std::min(atoi(e), std::min(ctx->sm_count, (int)MG_MAX_CTAS)));
+        g_bpe_launches++;
+        CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_merge_loop, dim3(G), dim3(MG_NT), nullptr, MG_DYN_SMEM, st));
+        CUDA_TRY(ctx, cudaMemcpyAsync(host, B.ctr.p, MG_CTR_WORDS * 8, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(ctx, cudaStreamSynchronize(st));
-        for (int i = 0; i < 8; i++) ctr[i] = host[i];
-        if (ctr[3] != MG_NEED_GROW) {
-            if (ctr[3] != 0) break;                                   // error
-            if ((int)ctr[1] >= n_merges) break;                       // all merges done
-            if ((int)ctr[1] < M.stop_at) break;                       // pair table ran empty (train.py:184-185)
-            continue;                                                 // reached the switch point: go on in the tail kernel
-        }
-        // grow x4 and re-insert the live keys; the pending pop (ctr[6]) is applied by dropping that key
+        for (int i = 0; i < MG_CTR_WORDS; i++) ctr[i] = host[i];
+        if (ctr[3] != MG_NEED_GROW) break;                            // done, pair table ran empty (train.py:184-185), or error
+        // grow x4 and re-insert the live keys; the pending pops (the last step's winners) are applied by dropping those keys
         keys_created += ctr[2];
         DevBuf okey = B.pkey, ocnt = B.pcnt;
         u64 ocap = M.pcap;
         B.pkey = DevBuf(); B.pcnt = DevBuf();
         int rc = alloc_pair_table(ocap * 4);
         if (rc != BPE_OK) { bpe_buf_free(ctx, okey); bpe_buf_free(ctx, ocnt); return rc; }
-        host[2] = 0; host[3] = 0; u64 pending = ctr[6]; host[6] = PAIR_EMPTY; host[5] = 0;
+        PendingPops pending;
+        pending.n = (u32)std::min<u64>(ctr[6], MG_BATCH);
+        for (u32 i = 0; i < MG_BATCH; i++) pending.key[i] = i < pending.n ? ctr[MG_CTR_PENDING + i] : PAIR_EMPTY;
+        host[2] = 0; host[3] = 0; host[5] = 0; host[6] = 0;
         CUDA_TRY(ctx, cudaMemcpyAsync((u64 *)B.ctr.p + 2, host + 2, 16, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(ctx, cudaMemcpyAsync((u64 *)B.ctr.p + 5, host + 5, 8, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(ctx, cudaMemcpyAsync((u64 *)B.ctr.p + 6, host + 6, 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(ctx, cudaMemcpyAsync((u64 *)B.ctr.p + 5, host + 5, 16, cudaMemcpyHostToDevice, st));
         ctr[3] = 0;
         unsigned rg = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (ocap + 255) / 256);
         CUDA_TRY(ctx, cudaMemcpyToSymbolAsync(cM, &M, sizeof(M), 0, cudaMemcpyHostToDevice, st));
@@ -1017,6 +974,12 @@ static int run_merges(bpe_ctx *ctx, const uint8_t *sp_blob, const u32 *sp_offs, 
         std::vector<i64> mc(done);
         CUDA_TRY(ctx, cudaMemcpyAsync(mc.data(), B.merge_cnt.p, (size_t)done * 8, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        if (const char *dump = getenv("BPE_DUMP_MERGES")) {        // debug aid: (a, b, count) of every merge, for offline analysis
+            if (FILE *f = fopen(dump, "wb")) {
+                for (int k = 0; k < done; k++) { i64 rec[3] = {merge_pairs_out[2 * k], merge_pairs_out[2 * k + 1], mc[k]}; fwrite(rec, 8, 3, f); }
+                fclose(f);
+            }
+        }
         std::vector<std::string> sym(256);
         std::unordered_set<std::string> seen;
         for (int i = 0; i < 256; i++) { sym[i] = std::string(1, (char)i); seen.insert(sym[i]); }
@@ -1030,7 +993,7 @@ static int run_merges(bpe_ctx *ctx, const uint8_t *sp_blob, const u32 *sp_offs, 
     if (stats) {
         stats->n_unique = n_words; stats->n_symbols = n_syms; stats->n_pairs_initial = n_pairs0;
         stats->n_pairs_final = ctr[2]; stats->log_records = ctr[0]; stats->duplicate_tokens = dup_tokens;
-        stats->n_pretokens = cs->n_pretokens; stats->sum_live_pairs = ctr[7];
+        stats->n_pretokens = cs->n_pretokens; stats->sum_live_pairs = ctr[7]; stats->merge_steps = ctr[12];
         stats->ms_build = tm.ms(ev_build0, ev_build1); stats->ms_merge = tm.ms(ev_build1, ev_merge1);
         stats->ms_total = tm.ms(ev_start, ev_end);
     }
