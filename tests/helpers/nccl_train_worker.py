@@ -32,6 +32,29 @@ def main():
     p2.write_bytes(b"hello world\r\nthe quick brown fox\r" * 500)
     got2 = train_bpe_sharded(p2, 300, [], ctx=ctx)
     assert got2 == oracle.train_bpe(p2, 300, [])
+    # ---- bulk encode, sharded (transformer_lm_b200/sharded_encode.py): the ranks' ids in rank order == the oracle's encode ----
+    import numpy as np
+    from transformer_lm_b200.synth import synth_host
+    from transformer_lm_b200.tokenizer import Tokenizer
+    world = dist.get_world_size()
+    tok = Tokenizer(dict(got[0]), list(got[1]), ["<|endoftext|>"], ctx=ctx)
+    text = synth_host("owt", 4322, 3 << 20)
+    want_ids = oracle.OracleTokenizer(dict(got[0]), list(got[1]), ["<|endoftext|>"]).encode_bytes(text.tobytes())
+    ids, first, total = tok.encode_sharded(text, np.int32)
+    assert total == want_ids.size and np.array_equal(ids, want_ids[first: first + ids.size]), "sharded ids differ on rank %d" % rank
+    sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([ids.size], dtype=torch.int64, device="cuda"))
+    assert sum(int(s) for s in sizes) == total and first == sum(int(s) for s in sizes[:rank])
+    # the file driver, distributed: one output file assembled from the ranks' segments
+    src = out / "enc_in.txt"
+    if rank == 0:
+        src.write_bytes(text.tobytes())
+    dist.barrier()
+    from transformer_lm_b200.encode_file import encode_file
+    n = encode_file(tok, src, out / "enc_out.bin", np.uint16, piece_bytes=400000, distributed=True)
+    assert n == total
+    if rank == 0:
+        assert np.array_equal(np.fromfile(out / "enc_out.bin", dtype="<u2").astype(np.int64), want_ids)
     dist.barrier()
     (out / ("ok.%d" % rank)).write_text("ok")
     dist.destroy_process_group()

@@ -119,3 +119,26 @@ def test_get_batch_like_the_reference_test():
     sigma = math.sqrt((num_iters * batch_size) * (1 / n_starts) * (1 - (1 / n_starts)))
     for count in starting_indices.values():
         assert expected - 5 * sigma < count < expected + 5 * sigma
+
+
+def test_load_batch_device_without_index_hits_the_resident_copy():
+    """The reference's trainer passes torch.device("cuda") (train.py:226), which is != torch.device("cuda:0"): the resident
+    copy must still be found, the result must be ordered with torch's stream, and models.util must export what train.py:17 imports."""
+    from models.util import load_checkpoint, save_checkpoint  # noqa: F401
+    from transformer_lm_b200 import batch as B
+    data = np.arange(0, 5000, dtype=np.uint16)
+    x, y = load_batch(data, 8, 16, torch.device("cuda"), generator=torch.Generator().manual_seed(1))
+    n_cached = len(B._resident)
+    tokens_a = B._resident[(id(data), torch.cuda.current_device())][1]
+    for dev in ("cuda", "cuda:0", torch.device("cuda")):
+        x, y = load_batch(data, 8, 16, dev, generator=torch.Generator().manual_seed(1))
+        assert len(B._resident) == n_cached and B._resident[(id(data), torch.cuda.current_device())][1] is tokens_a
+        assert torch.equal(x + 1, y) and x.device.type == "cuda"
+    # on a side stream with queued work: the gather is ordered with torch's current stream
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        junk = torch.zeros(1 << 24, device="cuda").cumsum(0)
+        x, y = load_batch(data, 64, 128, "cuda", generator=torch.Generator().manual_seed(2))
+        z = (x + 1 - y).abs().sum()
+    s.synchronize()
+    assert int(z) == 0 and junk.numel()

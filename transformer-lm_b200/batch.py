@@ -15,14 +15,17 @@ import numpy as np
 
 from . import _lib
 
-_resident: dict[int, tuple] = {}                 # id(dataset) -> (weakref, device tensor, dtype code)
+_resident: dict[tuple, tuple] = {}               # (id(dataset), device index) -> (weakref, device tensor, dtype code)
+_contexts: dict[int, list] = {}                  # device index -> [Context, cuda stream handle it is on]
 
 
 def _device_tokens(dataset, device):
+    """Device copy of the token array, uploaded once per (dataset object, device) and kept until the dataset is collected.
+    `device` is a torch.device with an explicit index.  (An in-place change of the host array is not seen: pass a new object.)"""
     import torch
-    key = id(dataset)
+    key = (id(dataset), device.index)
     hit = _resident.get(key)
-    if hit is not None and hit[0]() is dataset and hit[1].device == torch.device(device):
+    if hit is not None and hit[0]() is dataset:
         return hit[1], hit[2]
     if isinstance(dataset, torch.Tensor):
         arr = dataset
@@ -52,7 +55,20 @@ def load_batch(dataset, batch_size: int, context_length: int, device: str, gener
     if dev.type != "cuda":
         raise _lib.BpeError(_lib.ERR_NO_DEVICE, "load_batch gathers on a B200: device must be a cuda device (there is no CPU path)")
     index = dev.index if dev.index is not None else torch.cuda.current_device()
-    ctx = ctx or _lib.default_context(index)
+    dev = torch.device("cuda", index)            # torch.device("cuda") != torch.device("cuda:0"): always carry the index
+    # The gather runs on torch's CURRENT stream: x / y come from torch's caching allocator and the token array may just have
+    # been copied by torch, so the kernel must be ordered with torch's queued work (a private stream would race with it).
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    if ctx is None:
+        slot = _contexts.get(index)
+        if slot is None:
+            slot = _contexts[index] = [_lib.Context(index), None]
+        ctx = slot[0]
+        if slot[1] != stream:
+            ctx.use_stream(stream)
+            slot[1] = stream
+    else:
+        ctx.use_stream(stream)
     n = len(dataset)
     limit = n - context_length                   # models/util.py:48
     start_idx = torch.randint(limit, (batch_size,), generator=generator)   # host generator, like the reference (:49)

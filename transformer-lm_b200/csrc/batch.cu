@@ -49,6 +49,8 @@ BPE_API int bpe_batch_windows_dev(bpe_ctx *ctx, const void *tokens_dev, int dtyp
     else
         KLAUNCH(k_batch_windows<int32_t>, grid, 256, 0, st, (const int32_t *)tokens_dev, (const long long *)ctx->tmp0.p, batch, context, (long long *)x_dev, (long long *)y_dev);
     CUDA_TRY(ctx, cudaGetLastError());
-    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    // On the caller's stream (bpe_ctx_set_stream) the result is stream-ordered with the caller's other work and nothing waits
+    // here; on the context's private stream the call returns with x / y complete.
+    if (st == ctx->own_stream) CUDA_TRY(ctx, cudaStreamSynchronize(st));
     return BPE_OK;
 }

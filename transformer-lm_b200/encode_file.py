@@ -8,7 +8,9 @@ the raw `.bin` the trainer's np.memmap(dtype=np.uint16) reads (optionally the re
 
 The file is streamed in pieces cut at exact boundaries -- an occurrence of a special token (Tokenizer.segment splits
 there first, tokenizer.py:63-66) or a lone U+0020 between two ASCII non-space bytes -- so a file of any
-size needs bounded host memory; every piece goes through bpe_encode, which overlaps upload, kernels and download.
+size needs bounded host memory; every piece goes through bpe_encode, which overlaps upload, kernels and download, while
+a reader thread fetches the next block and a writer thread stores the previous piece's ids.  `distributed=True` shards the
+file over the ranks of a torch.distributed group (sharded_encode.py).
 """
 from __future__ import annotations
 
@@ -51,19 +53,76 @@ def _last_exact_cut(buf: bytes, specials: list[bytes], lo: int) -> int:
     return 0
 
 
-def encode_file(tokenizer, input_path, output_path, dtype=np.uint16, piece_bytes: int = 1 << 30, save_pt: str | None = None) -> int:
-    """Encode `input_path` with `tokenizer` into raw little-endian `dtype` ids at `output_path`.  Returns the token count."""
+def encode_file(tokenizer, input_path, output_path, dtype=np.uint16, piece_bytes: int = 1 << 30, save_pt: str | None = None,
+                byte_range: tuple[int, int] | None = None, distributed: bool = False, group=None) -> int:
+    """Encode `input_path` with `tokenizer` into raw little-endian `dtype` ids at `output_path`.  Returns the token count.
+
+    Three stages run concurrently: a reader thread pulls the next block from the file, the calling thread
+    cuts and encodes the current piece (bpe_encode, which itself overlaps upload, kernels and download), a writer thread
+    appends the ids of the previous piece to the output.  byte_range = (lo, hi) restricts the work to those bytes of the file
+    (lo and hi must be exact cut positions: sharded_encode.py); distributed=True shards the file over the ranks of the
+    initialised torch.distributed group."""
+    if distributed:
+        from .sharded_encode import encode_file_sharded
+        return encode_file_sharded(tokenizer, input_path, output_path, dtype, piece_bytes, group)
+    import queue
+    import threading
     dtype = np.dtype(dtype)
     specials = [s.encode("utf-8") for s in tokenizer.special_tokens]
+    lo, hi = byte_range if byte_range is not None else (0, os.path.getsize(input_path))
+    blocks: queue.Queue = queue.Queue(maxsize=2)
+    results: queue.Queue = queue.Queue(maxsize=2)
+    failure: list = []
+
+    def reader():
+        try:
+            with open(input_path, "rb", buffering=0) as f:
+                f.seek(lo)
+                left = hi - lo
+                while left > 0 and not failure:
+                    want = min(piece_bytes, left)
+                    block = bytearray(want)
+                    mv, got = memoryview(block), 0
+                    while got < want:
+                        k = f.readinto(mv[got:])
+                        if not k:
+                            break
+                        got += k
+                    left -= got
+                    blocks.put(block[:got] if got < want else block)
+                    if got < want:
+                        break
+        except BaseException as e:            # surfaced in the calling thread
+            failure.append(e)
+        blocks.put(None)
+
+    def writer():
+        try:
+            with open(output_path, "wb") as out:
+                while True:
+                    ids = results.get()
+                    if ids is None:
+                        return
+                    ids.astype(dtype.newbyteorder("<"), copy=False).tofile(out)
+        except BaseException as e:
+            failure.append(e)
+            while results.get() is not None:
+                pass
+
+    rt, wt = threading.Thread(target=reader, daemon=True), threading.Thread(target=writer, daemon=True)
+    rt.start(); wt.start()
     total = 0
-    offset = 0                                   # bytes of the (untranslated) file consumed so far: for error offsets
+    offset = lo                                  # bytes of the (untranslated) file consumed so far: for error offsets
     pin = None
-    with open(input_path, "rb") as f, open(output_path, "wb") as out:
+    try:
         carry = b""
-        while True:
-            block = f.read(piece_bytes)
-            eof = len(block) < piece_bytes
-            buf = carry + block
+        eof = False
+        while not eof:
+            block = blocks.get()
+            if failure:
+                raise failure[0]
+            eof = block is None
+            buf = carry if eof else (carry + block if carry else block)
             if not buf:
                 break
             hold = b""
@@ -81,23 +140,43 @@ def encode_file(tokenizer, input_path, output_path, dtype=np.uint16, piece_bytes
                         raise RuntimeError("no exact cut point within %d bytes" % len(carry))
                     continue
                 piece, carry = buf[:cut], buf[cut:] + hold
-            if pin is None or pin.nbytes < len(piece):
-                if pin is not None:
-                    pin.free()
-                pin = _lib.PinnedBuffer(max(len(piece), piece_bytes + (piece_bytes >> 2)))
-            pin.array[: len(piece)] = np.frombuffer(piece, dtype=np.uint8)
+            if not piece:
+                continue
+            if getattr(tokenizer, "host_only", False):       # (checker-backed tokenizers of the CPU tests: no page-locked staging)
+                staged = np.frombuffer(piece, dtype=np.uint8)
+            else:
+                if pin is None or pin.nbytes < len(piece):
+                    if pin is not None:
+                        pin.free()
+                    pin = _lib.PinnedBuffer(max(len(piece), piece_bytes + (piece_bytes >> 2)))
+                pin.array[: len(piece)] = np.frombuffer(piece, dtype=np.uint8)
+                staged = pin.array[: len(piece)]
             try:
-                ids = tokenizer.encode_to_numpy(pin.array[: len(piece)], dtype)
+                ids = tokenizer.encode_to_numpy(staged, dtype)
             except UnicodeDecodeError as e:
                 raise UnicodeDecodeError(e.encoding, e.object[max(e.start - 8, 0): e.end + 8], min(e.start, 8), min(e.start, 8) + (e.end - e.start),
                                          e.reason + " (near byte %d of the file)" % (offset + e.start)) from None
-            ids.astype(dtype.newbyteorder("<"), copy=False).tofile(out)
+            results.put(ids)
+            if failure:
+                raise failure[0]
             total += ids.size
             offset += len(piece)
-            if eof:
-                break
-    if pin is not None:
-        pin.free()
+    except BaseException:
+        failure.append(RuntimeError("encode_file aborted"))   # stops the reader
+        while rt.is_alive():
+            try:
+                blocks.get(timeout=0.05)
+            except queue.Empty:
+                pass
+        raise
+    finally:
+        results.put(None)
+        wt.join()
+        rt.join(timeout=5)
+        if pin is not None:
+            pin.free()
+    if failure:
+        raise failure[0]
     if save_pt:
         import torch
         torch.save(np.fromfile(output_path, dtype=dtype), save_pt, pickle_protocol=4)       # models/tokenizer/encode.py:37-38

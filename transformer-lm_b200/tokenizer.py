@@ -171,6 +171,13 @@ class Tokenizer:
     def encode(self, text: str) -> List[int]:
         return self.encode_to_numpy(text.encode("utf-8"), np.int32).tolist()
 
+    def encode_sharded(self, data, dtype=np.uint16, group=None):
+        """Multi-GPU encode (one process per GPU, torch.distributed initialised): every rank passes the same UTF-8 `data`
+        and gets (ids of its shard, global index of its first id, total ids); shards are cut at exact boundaries, so the
+        ranks' arrays in rank order concatenate to encode(data).  See sharded_encode.py."""
+        from .sharded_encode import encode_sharded
+        return encode_sharded(self, data, dtype, group)
+
     def encode_iterable(self, iterable: Iterable[str]) -> Iterator[int]:
         # Chunk rule of tokenizer.py:140-153: concatenate items until the buffer holds >= 2 Mi CHARACTERS,
         # encode the buffer on its own, repeat until the iterable yields nothing (SURVEY A-13/A-14).

@@ -106,6 +106,8 @@ def _train_bpe_streamed(input_path, size: int, vocab_size: int, special_tokens: 
     from .sharded import DeviceCounter, align_cut, _raise_decode_error
     fd = os.open(os.fspath(input_path), os.O_RDONLY)
     bufs = []
+    pool = None
+    pending: dict = {}
     try:
         def peek(lo, hi):
             return os.pread(fd, hi - lo, lo)
@@ -141,16 +143,21 @@ def _train_bpe_streamed(input_path, size: int, vocab_size: int, special_tokens: 
                 fut.result()
             status = counter.add(bufs[k % len(bufs)].array[: rhi - rlo], lo - rlo, hi - rlo, rlo == 0, rhi == size)
             if status is not None:
-                for futs in pending.values():
-                    for fut in futs:
-                        fut.result()
-                pool.shutdown()
                 if status[0] == "utf8":
                     _raise_decode_error(peek, size, rlo + status[1])      # what open(path, encoding="utf-8").read() raises
                 return None
-        pool.shutdown()
         return counter.finish(vocab_size, special_tokens, return_stats=return_stats)
     finally:
+        # reader threads may still be writing into the page-locked buffers (an error or an early return above): wait for every
+        # submitted read before the buffers are freed
+        for futs in pending.values():
+            for fut in futs:
+                try:
+                    fut.result()
+                except Exception:
+                    pass
+        if pool is not None:
+            pool.shutdown(wait=True)
         for b in bufs:
             b.free()
         os.close(fd)
@@ -164,17 +171,31 @@ def train_bpe(input_path, vocab_size: int, special_tokens: List[str] = [], *, di
         from .sharded import train_bpe_sharded
         return train_bpe_sharded(input_path, vocab_size, special_tokens, **kwargs)
     t0 = time.time()
-    logger.info("Extracting subword frequencies")
     size = os.path.getsize(input_path)           # FileNotFoundError like open() in the reference
+    kwargs = dict(kwargs)
+    want_stats = kwargs.pop("return_stats", False)
+    res = None
     if size >= _STREAM_MIN:
-        res = _train_bpe_streamed(input_path, size, vocab_size, special_tokens, **kwargs)
-        if res is not None:
-            logger.info("Took %s seconds to read, pretokenize, count and merge %d bytes (streamed)", round(time.time() - t0, 2), size)
-            return res
-    arr, _keep = _read_file(input_path)
-    logger.info("Took %s seconds to read %d bytes", round(time.time() - t0, 2), arr.size)
-    t1 = time.time()
+        res = _train_bpe_streamed(input_path, size, vocab_size, special_tokens, return_stats=True, **kwargs)
+    if res is None:
+        arr, _keep = _read_file(input_path)
+        res = train_bpe_on_bytes(arr, vocab_size, special_tokens, return_stats=True, **kwargs)
+    _log_stages(res[2], time.time() - t0)
+    return res if want_stats else res[:2]
+
+
+def _log_stages(st: dict, wall_s: float) -> None:
+    """The reference's five stage lines (models/tokenizer/train.py:148-229), so CPU and GPU logs line up.  The stages ran
+    on the device: the times are their CUDA-event durations (the words and the pair table are built in one pass)."""
+    logger.info("Creating vocab")
+    logger.info("Took %s seconds to create vocab", 0.0)
+    logger.info("Extracting subword frequencies")
+    logger.info("Took %s seconds to extract subword frequencies", round((st["ms_h2d"] + st["ms_pretok"] + st["ms_count"]) / 1e3, 4))
+    logger.info("Encoding subwords")
+    logger.info("Took %s seconds to encode subwords", round(st["ms_build"] / 1e3, 4))
+    logger.info("Calculating byte pair frequencies")
+    logger.info("Took %s seconds to calculate byte pair frequencies", 0.0)
     logger.info("Merging subwords")
-    res = train_bpe_on_bytes(arr, vocab_size, special_tokens, **kwargs)
-    logger.info("Took %s seconds to pretokenize, count and merge subwords on the GPU", round(time.time() - t1, 2))
-    return res
+    logger.info("Took %s seconds to merge subwords", round(st["ms_merge"] / 1e3, 4))
+    logger.info("train_bpe on the GPU: %d bytes, %d pretokens (%d unique), %d merge steps; %.3f s wall including the file read",
+                st["n_bytes"], st["n_pretokens"], st["n_unique"], st["merge_steps"], wall_s)
