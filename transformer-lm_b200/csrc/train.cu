@@ -35,6 +35,10 @@
 struct CountTables {
     u64 *stab; u64 scap;                         // short: slots of {key, count}            (16 B)
     u64 *ltab; u64 lcap;                         // long:  slots of {meta, hash, count, pad} (32 B, one sector)
+    // slot of the k-th unique short / long word (k = value of counters[0] / [1] when it was claimed): everything that walks the
+    // words (re-homing, export, word list, table growth) walks these lists instead of scanning the tables' capacity, which is
+    // sized for the worst case (every pretoken of a batch new) and mostly empty
+    u32 *slist, *llist;
     const uint8_t *text;                         // payload of the current text arena
     const uint8_t *pool;                         // persistent bytes of long words
     u64 *counters;                               // [0]=n_short [1]=n_long [2]=long_bytes [3]=overflow [4]=n_pretokens [5]=too_long
@@ -48,10 +52,11 @@ struct CountTables {
 #define LCNT(t, s) ((t).ltab[4 * (s) + 2])
 
 struct CountState {
-    DevBuf stab, ltab, pool, counters;
+    DevBuf stab, ltab, slist, llist, pool, counters;
     u64 scap = 0, lcap = 0, pool_used = 0;
     bool active = false;
     u64 n_pretokens = 0;
+    u64 n_rehomed = 0;                           // long words [0, n_rehomed) of the list have their bytes in the pool
 };
 
 __device__ __forceinline__ const uint8_t *rep_ptr(const CountTables &t, u64 meta) {
@@ -66,7 +71,7 @@ __device__ __forceinline__ void short_add(const CountTables &t, u64 key, u64 del
         u64 k = SKEY(t, s);
         if (k == 0) {
             u64 old = atomicCAS(&SKEY(t, s), 0ull, key);
-            if (old == 0) { atomicAdd(&t.counters[0], 1ull); k = key; }
+            if (old == 0) { t.slist[atomicAdd(&t.counters[0], 1ull)] = (u32)s; k = key; }
             else k = old;
         }
         if (k == key) { atomicAdd(&SCNT(t, s), delta); return; }
@@ -88,7 +93,7 @@ __device__ __forceinline__ void long_add(const CountTables &t, const uint8_t *p,
             u64 old = atomicCAS(&LMETA(t, s), META_EMPTY, mine);
             if (old == META_EMPTY) {
                 LHASH(t, s) = h;
-                atomicAdd(&t.counters[1], 1ull);
+                t.llist[atomicAdd(&t.counters[1], 1ull)] = (u32)s;
                 atomicAdd(&t.counters[2], (u64)len);
                 atomicAdd(&LCNT(t, s), delta);
                 return;
@@ -102,97 +107,116 @@ __device__ __forceinline__ void long_add(const CountTables &t, const uint8_t *p,
     t.counters[3] = 1;
 }
 
-// One thread per pretoken occurrence i of the batch: bytes [base + offs[i], base + offs[i+1]).
-// Short pretokens are first counted in a per-CTA shared-memory table and flushed to the HBM table when the CTA is
-// done: natural-language text is Zipfian, and without this the few hottest words serialise hundreds of millions of
-// same-address L2 atomics.
-#ifndef CNT_DYNAMIC
-#define CNT_DYNAMIC 1
+// Pretoken occurrences i of the batch: bytes [base + offs[i], base + offs[i+1]).  Tiles of CNT_NT x CNT_ITEMS occurrences are
+// handed out by a ticket counter (every CTA is busy until the batch is done, however uneven its items were) and go through two
+// phases, so that threads that hit the shared-memory table never wait in lockstep behind threads that go to HBM:
+//   A  every thread forms the keys of its CNT_ITEMS occurrences (offsets and the first 16 text bytes of all of them in flight
+//      together).  Pretokens of <= 7 bytes are counted in a per-CTA shared-memory table (natural-language text is Zipfian: without
+//      it the few hottest words serialise hundreds of millions of same-address L2 atomics); what does not fit there, and every longer
+//      pretoken, is queued in shared memory.
+//   B  all threads drain the queues: one HBM probe sequence per thread, all in flight at once.
+// The shared-memory table is flushed to the HBM table when the CTA is done.
+#ifndef CNT_NT
+#define CNT_NT 512
 #endif
-#ifndef CNT_TILE
-#define CNT_TILE 4096ull
+#ifndef CNT_ITEMS
+#define CNT_ITEMS 4
 #endif
 #ifndef CNT_SMEM_LG
-#define CNT_SMEM_LG 11
+#define CNT_SMEM_LG 12
 #endif
+#define CNT_TILE ((u64)CNT_NT * CNT_ITEMS)
 #define CNT_SMEM_SLOTS (1u << CNT_SMEM_LG)
-#define CNT_SMEM_PROBES 4u
-__global__ void __launch_bounds__(256) k_count_pretokens(CountTables t, const u32 *__restrict__ offs, u64 n_items, u64 base,
-                                                        u64 own_begin, u64 own_end, u64 trust_end) {
-    __shared__ u64 s_key[CNT_SMEM_SLOTS];
-    __shared__ u32 s_cnt[CNT_SMEM_SLOTS];
-    for (u32 i = threadIdx.x; i < CNT_SMEM_SLOTS; i += blockDim.x) { s_key[i] = 0; s_cnt[i] = 0; }
-    __syncthreads();
-    u64 n_tok = 0;
-    // Software pipeline over the grid-stride loop: while item i is hashed and counted, the first 16 bytes of item
-    // i + stride and the offsets of item i + 2 stride are in flight (the chain offsets -> text -> table was the latency
-    // that bounded this kernel: one item per thread at a time).
-#if CNT_DYNAMIC
-    // tiles of CNT_TILE items are handed out by a ticket counter: every CTA is busy until the batch is done, however uneven
-    // the cost of its items (hash-table misses, long pretokens) was
+#ifndef CNT_SMEM_PROBES
+#define CNT_SMEM_PROBES 2u                       // (4 -> 84 ms per 11 GB, 2 -> 81, 1 -> 81)
+#endif
+#define CNT_DYN_SMEM ((size_t)CNT_SMEM_SLOTS * 12 + (size_t)CNT_TILE * 16)
+// queue push with one shared-memory atomic per warp
+__device__ __forceinline__ u32 warp_queue_slot(u32 *counter, bool want) {
+    const u32 m = __ballot_sync(0xffffffffu, want);
+    if (!m) return 0;
+    u32 base = 0;
+    if (lane_id() == (u32)(__ffs(m) - 1)) base = atomicAdd(counter, (u32)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    return base + __popc(m & ((1u << lane_id()) - 1u));
+}
+__global__ void __launch_bounds__(CNT_NT) k_count_pretokens(CountTables t, const u32 *__restrict__ offs, u64 n_items, u64 base,
+                                                           u64 own_begin, u64 own_end, u64 trust_end) {
+    extern __shared__ __align__(16) unsigned char cnt_smem[];
+    u64 *s_key = reinterpret_cast<u64 *>(cnt_smem);                       // shared-memory table: keys ...
+    u64 *s_sq = s_key + CNT_SMEM_SLOTS;                                   // short pretokens that did not fit the shared table: their keys
+    uint2 *s_lq = reinterpret_cast<uint2 *>(s_sq + CNT_TILE);             // long pretokens: (offset from base, length)
+    u32 *s_cnt = reinterpret_cast<u32 *>(s_lq + CNT_TILE);                // ... and counts
+    __shared__ u32 s_nq[2];
     __shared__ u64 s_tile;
-    const u64 n_items_all = n_items;
+    for (u32 i = threadIdx.x; i < CNT_SMEM_SLOTS; i += CNT_NT) { s_key[i] = 0; s_cnt[i] = 0; }
+    if (threadIdx.x < 2) s_nq[threadIdx.x] = 0;
+    u64 n_tok = 0;
     for (;;) {
-    __syncthreads();
-    if (threadIdx.x == 0) s_tile = atomicAdd(&t.counters[16], 1ull);
-    __syncthreads();
-    const u64 tile_lo = s_tile * CNT_TILE;
-    if (tile_lo >= n_items_all) break;
-    n_items = tile_lo + CNT_TILE < n_items_all ? tile_lo + CNT_TILE : n_items_all;
-    const u64 stride = blockDim.x;
-    u64 i = tile_lo + threadIdx.x;
-#else
-    const u64 stride = (u64)gridDim.x * blockDim.x;
-    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-#endif
-    bool h0 = i < n_items, h1 = i + stride < n_items;
-    u32 a0 = 0, b0 = 0, a1 = 0, b1 = 0;
-    if (h0) { a0 = offs[i]; b0 = offs[i + 1]; }
-    if (h1) { a1 = offs[i + stride]; b1 = offs[i + stride + 1]; }
-    u64 lo0 = 0, hi0 = 0;
-    if (h0) { const u64 *q = reinterpret_cast<const u64 *>(reinterpret_cast<uintptr_t>(t.text + base + a0) & ~(uintptr_t)7); lo0 = q[0]; hi0 = q[1]; }
-    for (; h0; i += stride) {
-        const bool h2 = i + 2 * stride < n_items;
-        u32 a2 = 0, b2 = 0;
-        if (h2) { a2 = offs[i + 2 * stride]; b2 = offs[i + 2 * stride + 1]; }
-        u64 lo1 = 0, hi1 = 0;
-        if (h1) { const u64 *q = reinterpret_cast<const u64 *>(reinterpret_cast<uintptr_t>(t.text + base + a1) & ~(uintptr_t)7); lo1 = q[0]; hi1 = q[1]; }
-        const u64 pos = base + a0, end = base + b0;
-        if (pos >= own_begin && pos < own_end) {
-            const u64 len = end - pos;
-            if (end > trust_end) t.counters[6] = 1;
-            n_tok++;
-            const uint8_t *p = t.text + pos;
-            if (len <= SHORT_MAX) {
-                const u32 sh = (u32)(reinterpret_cast<uintptr_t>(p) & 7u) * 8u;
-                const u64 first8 = sh ? (lo0 >> sh) | (hi0 << (64u - sh)) : lo0;
-                const u64 key = (first8 & low_bytes_mask((u32)len)) | ((u64)len << 56);   // = short_key(p, len)
-                u32 slot = (((u32)key ^ (u32)(key >> 32)) * 0x9E3779B1u) >> (32 - CNT_SMEM_LG);   // cheap hash for the shared-memory table
-                bool done = false;
-                for (u32 pr = 0; pr < CNT_SMEM_PROBES && !done; pr++) {
-                    u64 k = s_key[slot];
-                    if (k == 0) { u64 old = atomicCAS(&s_key[slot], 0ull, key); k = old ? old : key; }
-                    if (k == key) { atomicAdd(&s_cnt[slot], 1u); done = true; }
-                    slot = (slot + 1) & (CNT_SMEM_SLOTS - 1);
-                }
-                if (!done) short_add(t, key, 1);
-            } else if (len <= MAX_TOKEN_LEN) {
-                long_add(t, p, (u32)len, pos, 1);
-            } else {
-                t.counters[5] = 1;
-            }
+        __syncthreads();
+        if (threadIdx.x == 0) s_tile = atomicAdd(&t.counters[16], 1ull);
+        __syncthreads();
+        const u64 tile_lo = s_tile * CNT_TILE;
+        if (tile_lo >= n_items) break;
+        // ---- phase A ----
+        u32 a[CNT_ITEMS], b[CNT_ITEMS];
+        u64 lo[CNT_ITEMS], hi[CNT_ITEMS];
+        bool has[CNT_ITEMS];
+#pragma unroll
+        for (u32 k = 0; k < CNT_ITEMS; k++) {
+            const u64 i = tile_lo + (u64)k * CNT_NT + threadIdx.x;
+            has[k] = i < n_items;
+            a[k] = 0; b[k] = 0;
+            if (has[k]) { a[k] = offs[i]; b[k] = offs[i + 1]; }
         }
-        a0 = a1; b0 = b1; lo0 = lo1; hi0 = hi1; h0 = h1;
-        a1 = a2; b1 = b2; h1 = h2;
+#pragma unroll
+        for (u32 k = 0; k < CNT_ITEMS; k++) {
+            lo[k] = 0; hi[k] = 0;
+            if (has[k]) { const u64 *q = reinterpret_cast<const u64 *>(reinterpret_cast<uintptr_t>(t.text + base + a[k]) & ~(uintptr_t)7); lo[k] = q[0]; hi[k] = q[1]; }
+        }
+#pragma unroll
+        for (u32 k = 0; k < CNT_ITEMS; k++) {
+            const u64 pos = base + a[k];
+            const u32 len = b[k] - a[k];
+            const bool mine = has[k] && pos >= own_begin && pos < own_end;
+            bool to_sq = false, to_lq = false;
+            u64 key = 0;
+            if (mine) {
+                if (base + b[k] > trust_end) t.counters[6] = 1;
+                n_tok++;
+                if (len <= SHORT_MAX) {
+                    const u32 sh = (u32)(reinterpret_cast<uintptr_t>(t.text + pos) & 7u) * 8u;
+                    const u64 first8 = sh ? (lo[k] >> sh) | (hi[k] << (64u - sh)) : lo[k];
+                    key = (first8 & low_bytes_mask(len)) | ((u64)len << 56);       // = short_key(p, len)
+                    u32 slot = (((u32)key ^ (u32)(key >> 32)) * 0x9E3779B1u) >> (32 - CNT_SMEM_LG);   // cheap hash for the shared-memory table
+                    to_sq = true;
+                    for (u32 pr = 0; pr < CNT_SMEM_PROBES; pr++) {
+                        u64 kk = s_key[slot];
+                        if (kk == 0) { const u64 old = atomicCAS(&s_key[slot], 0ull, key); kk = old ? old : key; }
+                        if (kk == key) { atomicAdd(&s_cnt[slot], 1u); to_sq = false; break; }
+                        slot = (slot + 1) & (CNT_SMEM_SLOTS - 1);
+                    }
+                } else if (len <= MAX_TOKEN_LEN) to_lq = true;
+                else t.counters[5] = 1;
+            }
+            const u32 qs = warp_queue_slot(&s_nq[0], to_sq);
+            if (to_sq) s_sq[qs] = key;
+            const u32 ql = warp_queue_slot(&s_nq[1], to_lq);
+            if (to_lq) s_lq[ql] = make_uint2(a[k], len);
+        }
+        __syncthreads();
+        // ---- phase B ----
+        const u32 nq = s_nq[0], nl = s_nq[1];
+        for (u32 e = threadIdx.x; e < nq; e += CNT_NT) short_add(t, s_sq[e], 1);
+        for (u32 e = threadIdx.x; e < nl; e += CNT_NT) { const uint2 it = s_lq[e]; long_add(t, t.text + base + it.x, it.y, base + it.x, 1); }
+        __syncthreads();
+        if (threadIdx.x < 2) s_nq[threadIdx.x] = 0;
     }
-#if CNT_DYNAMIC
-    }
-#endif
     // one atomic per warp for the occurrence counter
     for (int d = 16; d; d >>= 1) n_tok += __shfl_down_sync(0xffffffffu, n_tok, d);
     if (lane_id() == 0 && n_tok) atomicAdd(&t.counters[4], n_tok);
     __syncthreads();
-    for (u32 i = threadIdx.x; i < CNT_SMEM_SLOTS; i += blockDim.x)
+    for (u32 i = threadIdx.x; i < CNT_SMEM_SLOTS; i += CNT_NT)
         if (s_cnt[i]) short_add(t, s_key[i], (u64)s_cnt[i]);
 }
 
@@ -209,19 +233,22 @@ __global__ void __launch_bounds__(256) k_popc_ranges(const u32 *__restrict__ fla
 }
 
 // ---- table growth: re-insert every entry of an old table into a bigger one -------------------
-__global__ void __launch_bounds__(256) k_rehash_short(const u64 *__restrict__ otab, u64 ocap, CountTables t) {
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < ocap; i += (u64)gridDim.x * blockDim.x)
-        if (otab[2 * i]) short_add(t, otab[2 * i], otab[2 * i + 1]);
+__global__ void __launch_bounds__(256) k_rehash_short(const u64 *__restrict__ otab, const u32 *__restrict__ olist, u64 n_old, CountTables t) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_old; i += (u64)gridDim.x * blockDim.x) {
+        const u64 o = olist[i];
+        short_add(t, otab[2 * o], otab[2 * o + 1]);          // (claims a slot and appends it to the new list: counters[0] was reset)
+    }
 }
-__global__ void __launch_bounds__(256) k_rehash_long(const u64 *__restrict__ otab, u64 ocap, CountTables t) {
+__global__ void __launch_bounds__(256) k_rehash_long(const u64 *__restrict__ otab, const u32 *__restrict__ olist, u64 n_old, CountTables t) {
     u64 mask = t.lcap - 1;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < ocap; i += (u64)gridDim.x * blockDim.x) {
-        u64 m = otab[4 * i];
-        if (m == META_EMPTY) continue;
-        u64 s = otab[4 * i + 1] & mask;          // keys are unique: no comparison needed, just find a hole
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_old; i += (u64)gridDim.x * blockDim.x) {
+        const u64 o = olist[i];
+        u64 m = otab[4 * o];
+        u64 s = otab[4 * o + 1] & mask;          // keys are unique: no comparison needed, just find a hole
         for (;;) {
             if (LMETA(t, s) == META_EMPTY && atomicCAS(&LMETA(t, s), META_EMPTY, m) == META_EMPTY) {
-                LHASH(t, s) = otab[4 * i + 1]; LCNT(t, s) = otab[4 * i + 2];
+                LHASH(t, s) = otab[4 * o + 1]; LCNT(t, s) = otab[4 * o + 2];
+                t.llist[i] = (u32)s;             // same position in the list: counters[1] / [2] stay as they are
                 break;
             }
             s = (s + 1) & mask;
@@ -230,24 +257,26 @@ __global__ void __launch_bounds__(256) k_rehash_long(const u64 *__restrict__ ota
 }
 
 // ---- re-homing: copy representatives that still point into the text arena to the pool ---------
-__global__ void __launch_bounds__(256) k_rehome_sizes(CountTables t, u64 *__restrict__ need /* [0] */) {
+// (only the long words claimed since the last re-homing can point into the arena: list positions [first, n_long))
+__global__ void __launch_bounds__(256) k_rehome_sizes(CountTables t, u64 first, u64 n_long, u64 *__restrict__ need /* [0] */) {
     u64 c = 0;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < t.lcap; i += (u64)gridDim.x * blockDim.x) {
-        u64 m = LMETA(t, i);
-        if (m != META_EMPTY && !((m >> META_LEN_BITS) & META_POOL_BIT)) c += m & META_LEN_MASK;
+    for (u64 i = first + (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_long; i += (u64)gridDim.x * blockDim.x) {
+        u64 m = LMETA(t, t.llist[i]);
+        if (!((m >> META_LEN_BITS) & META_POOL_BIT)) c += m & META_LEN_MASK;
     }
     for (int d = 16; d; d >>= 1) c += __shfl_down_sync(0xffffffffu, c, d);
     if (lane_id() == 0 && c) atomicAdd(&need[0], c);
 }
-__global__ void __launch_bounds__(256) k_rehome_copy(CountTables t, uint8_t *__restrict__ pool, u64 *__restrict__ cursor) {
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < t.lcap; i += (u64)gridDim.x * blockDim.x) {
-        u64 m = LMETA(t, i);
-        if (m == META_EMPTY || ((m >> META_LEN_BITS) & META_POOL_BIT)) continue;
+__global__ void __launch_bounds__(256) k_rehome_copy(CountTables t, u64 first, u64 n_long, uint8_t *__restrict__ pool, u64 *__restrict__ cursor) {
+    for (u64 i = first + (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_long; i += (u64)gridDim.x * blockDim.x) {
+        const u64 s = t.llist[i];
+        u64 m = LMETA(t, s);
+        if ((m >> META_LEN_BITS) & META_POOL_BIT) continue;
         u32 len = (u32)(m & META_LEN_MASK);
         u64 o = atomicAdd(cursor, (u64)len);
         const uint8_t *src = t.text + (m >> META_LEN_BITS);
         for (u32 k = 0; k < len; k++) pool[o + k] = src[k];
-        LMETA(t, i) = ((o | META_POOL_BIT) << META_LEN_BITS) | len;
+        LMETA(t, s) = ((o | META_POOL_BIT) << META_LEN_BITS) | len;
     }
 }
 
@@ -269,36 +298,26 @@ __global__ void __launch_bounds__(256) k_import_words(CountTables t, const uint8
     }
 }
 
-// ---- export: (bytes, offs, counts) of every word ----------------------------------------------
-__global__ void __launch_bounds__(256) k_export_lens(CountTables t, u32 *__restrict__ lens /* scap + lcap */) {
-    u64 total = t.scap + t.lcap;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (u64)gridDim.x * blockDim.x) {
-        u32 l = 0;
-        if (i < t.scap) { if (SKEY(t, i)) l = (u32)(SKEY(t, i) >> 56); }
-        else { u64 m = LMETA(t, i - t.scap); if (m != META_EMPTY) l = (u32)(m & META_LEN_MASK); }
-        lens[i] = l;
-    }
+// ---- export: (bytes, offs, counts) of every word; word w < n_short is the w-th short word, the others the long ones ----
+__global__ void __launch_bounds__(256) k_export_lens(CountTables t, u64 n_short, u64 n_words, u32 *__restrict__ lens) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (u64)gridDim.x * blockDim.x)
+        lens[i] = i < n_short ? (u32)(SKEY(t, t.slist[i]) >> 56) : (u32)(LMETA(t, t.llist[i - n_short]) & META_LEN_MASK);
 }
-__global__ void __launch_bounds__(256) k_export_flags(const u32 *__restrict__ lens, u64 total, u32 *__restrict__ present) {
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (u64)gridDim.x * blockDim.x) present[i] = lens[i] ? 1u : 0u;
-}
-__global__ void __launch_bounds__(256) k_export_write(CountTables t, const u32 *__restrict__ lens, const u64 *__restrict__ byte_off,
-                                                     const u64 *__restrict__ word_idx, uint8_t *__restrict__ blob,
-                                                     u64 *__restrict__ offs, i64 *__restrict__ counts) {
-    u64 total = t.scap + t.lcap;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (u64)gridDim.x * blockDim.x) {
-        u32 l = lens[i];
-        if (!l) continue;
-        u64 o = byte_off[i], w = word_idx[i];
-        offs[w] = o;
-        if (i < t.scap) {
-            u64 k = SKEY(t, i);
+__global__ void __launch_bounds__(256) k_export_write(CountTables t, u64 n_short, u64 n_words, const u32 *__restrict__ lens, const u64 *__restrict__ byte_off,
+                                                     uint8_t *__restrict__ blob, u64 *__restrict__ offs, i64 *__restrict__ counts) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (u64)gridDim.x * blockDim.x) {
+        const u32 l = lens[i];
+        const u64 o = byte_off[i];
+        offs[i] = o;
+        if (i < n_short) {
+            const u64 sl = t.slist[i], k = SKEY(t, sl);
             for (u32 j = 0; j < l; j++) blob[o + j] = (uint8_t)(k >> (8 * j));
-            counts[w] = (i64)SCNT(t, i);
+            counts[i] = (i64)SCNT(t, sl);
         } else {
-            const uint8_t *src = rep_ptr(t, LMETA(t, i - t.scap));
+            const u64 sl = t.llist[i - n_short];
+            const uint8_t *src = rep_ptr(t, LMETA(t, sl));
             for (u32 j = 0; j < l; j++) blob[o + j] = src[j];
-            counts[w] = (i64)LCNT(t, i - t.scap);
+            counts[i] = (i64)LCNT(t, sl);
         }
     }
 }
@@ -321,21 +340,18 @@ __device__ __forceinline__ bool equals_special(const uint8_t *p, u32 len, const 
 
 // Pretokens equal to a special token are dropped (train.py:25).  Words of one byte carry no pair and are
 // skipped: they can never be touched by the merge loop.
-__global__ void __launch_bounds__(256) k_build_words(CountTables t, Words W, const uint8_t *__restrict__ sp_blob,
+__global__ void __launch_bounds__(256) k_build_words(CountTables t, u64 n_short, u64 n_unique, Words W, const uint8_t *__restrict__ sp_blob,
                                                     const u32 *__restrict__ sp_offs, int n_sp) {
-    u64 total = t.scap + t.lcap;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (u64)gridDim.x * blockDim.x) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_unique; i += (u64)gridDim.x * blockDim.x) {
         u32 l = 0; const uint8_t *src = nullptr; uint8_t tmp[8]; u64 c = 0;
-        if (i < t.scap) {
-            u64 k = SKEY(t, i);
-            if (!k) continue;
+        if (i < n_short) {
+            const u64 sl = t.slist[i], k = SKEY(t, sl);
             l = (u32)(k >> 56);
             for (u32 j = 0; j < l; j++) tmp[j] = (uint8_t)(k >> (8 * j));
-            src = tmp; c = SCNT(t, i);
+            src = tmp; c = SCNT(t, sl);
         } else {
-            u64 m = LMETA(t, i - t.scap);
-            if (m == META_EMPTY) continue;
-            l = (u32)(m & META_LEN_MASK); src = rep_ptr(t, m); c = LCNT(t, i - t.scap);
+            const u64 sl = t.llist[i - n_short], m = LMETA(t, sl);
+            l = (u32)(m & META_LEN_MASK); src = rep_ptr(t, m); c = LCNT(t, sl);
         }
         if (l < 2 || c == 0) continue;
         if (n_sp && equals_special(src, l, sp_blob, sp_offs, n_sp)) continue;
@@ -361,21 +377,18 @@ __global__ void __launch_bounds__(256) k_build_words(CountTables t, Words W, con
 
 // The dense byte-pair table straight from the count tables (what k_build_words + k_init_pair_counts compute, without
 // materialising the words): the per-rank table of the multi-GPU linearity check.
-__global__ void __launch_bounds__(256) k_dense_pairs(CountTables t, const uint8_t *__restrict__ sp_blob, const u32 *__restrict__ sp_offs,
+__global__ void __launch_bounds__(256) k_dense_pairs(CountTables t, u64 n_short, u64 n_unique, const uint8_t *__restrict__ sp_blob, const u32 *__restrict__ sp_offs,
                                                     int n_sp, u64 *__restrict__ dense /* 65536 */) {
-    u64 total = t.scap + t.lcap;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (u64)gridDim.x * blockDim.x) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_unique; i += (u64)gridDim.x * blockDim.x) {
         u32 l = 0; const uint8_t *src = nullptr; uint8_t tmp[8]; u64 c = 0;
-        if (i < t.scap) {
-            u64 k = SKEY(t, i);
-            if (!k) continue;
+        if (i < n_short) {
+            const u64 sl = t.slist[i], k = SKEY(t, sl);
             l = (u32)(k >> 56);
             for (u32 j = 0; j < l; j++) tmp[j] = (uint8_t)(k >> (8 * j));
-            src = tmp; c = SCNT(t, i);
+            src = tmp; c = SCNT(t, sl);
         } else {
-            u64 m = LMETA(t, i - t.scap);
-            if (m == META_EMPTY) continue;
-            l = (u32)(m & META_LEN_MASK); src = rep_ptr(t, m); c = LCNT(t, i - t.scap);
+            const u64 sl = t.llist[i - n_short], m = LMETA(t, sl);
+            l = (u32)(m & META_LEN_MASK); src = rep_ptr(t, m); c = LCNT(t, sl);
         }
         if (l < 2 || c == 0) continue;
         if (n_sp && equals_special(src, l, sp_blob, sp_offs, n_sp)) continue;
@@ -444,6 +457,7 @@ static CountTables count_tables(bpe_ctx *ctx) {
     CountTables t;
     t.stab = (u64 *)cs->stab.p; t.scap = cs->scap;
     t.ltab = (u64 *)cs->ltab.p; t.lcap = cs->lcap;
+    t.slist = (u32 *)cs->slist.p; t.llist = (u32 *)cs->llist.p;
     t.text = ctx->text.p ? (const uint8_t *)ctx->text.p + BPE_PAD : nullptr;
     t.pool = (const uint8_t *)cs->pool.p;
     t.counters = (u64 *)cs->counters.p;
@@ -453,7 +467,7 @@ static CountTables count_tables(bpe_ctx *ctx) {
 void count_state_free(bpe_ctx *ctx) {
     if (!ctx->count) return;
     CountState *cs = ctx->count;
-    for (DevBuf *b : {&cs->stab, &cs->ltab, &cs->pool, &cs->counters}) bpe_buf_free(ctx, *b);
+    for (DevBuf *b : {&cs->stab, &cs->ltab, &cs->slist, &cs->llist, &cs->pool, &cs->counters}) bpe_buf_free(ctx, *b);
     delete cs;
     ctx->count = nullptr;
 }
@@ -463,6 +477,7 @@ static int alloc_exact(bpe_ctx *ctx, DevBuf &b, size_t bytes) { return bpe_buf_a
 static int count_tables_alloc(bpe_ctx *ctx, u64 scap, u64 lcap) {
     CountState *cs = ctx->count;
     BPE_TRY(alloc_exact(ctx, cs->stab, scap * 16)); BPE_TRY(alloc_exact(ctx, cs->ltab, lcap * 32));
+    BPE_TRY(alloc_exact(ctx, cs->slist, scap * 4)); BPE_TRY(alloc_exact(ctx, cs->llist, lcap * 4));   // (written before read: no clearing)
     cudaStream_t st = ctx->stream;
     CUDA_TRY(ctx, cudaMemsetAsync(cs->stab.p, 0, scap * 16, st)); CUDA_TRY(ctx, cudaMemsetAsync(cs->ltab.p, 0, lcap * 32, st));
     cs->scap = scap; cs->lcap = lcap;
@@ -477,7 +492,7 @@ BPE_API int bpe_count_begin(bpe_ctx *ctx) {
     BPE_TRY(bpe_buf_reserve(ctx, cs->counters, 64 * sizeof(u64)));
     CUDA_TRY(ctx, cudaMemsetAsync(cs->counters.p, 0, 64 * sizeof(u64), ctx->stream));
     BPE_TRY(count_tables_alloc(ctx, 1 << 16, 1 << 14));
-    cs->pool_used = 0; cs->active = true; cs->n_pretokens = 0;
+    cs->pool_used = 0; cs->active = true; cs->n_pretokens = 0; cs->n_rehomed = 0;
     return BPE_OK;
 }
 
@@ -496,21 +511,25 @@ static int count_ensure_capacity(bpe_ctx *ctx, u64 n_short, u64 n_long, u64 new_
     u64 need_l = next_pow2(std::max<u64>(1 << 14, (n_long + new_long) * 8 / 7 + 64));
     if (need_s <= cs->scap && need_l <= cs->lcap) return BPE_OK;
     need_s = std::max(need_s, cs->scap); need_l = std::max(need_l, cs->lcap);
-    // grow: move old tables aside, allocate, re-insert
+    // grow: move old tables aside, allocate, re-insert the n_short + n_long words of the old lists
     CountState old_view = *cs;                   // shallow copy of the DevBufs
-    cs->stab = DevBuf(); cs->ltab = DevBuf();
+    cs->stab = DevBuf(); cs->ltab = DevBuf(); cs->slist = DevBuf(); cs->llist = DevBuf();
     int rc = count_tables_alloc(ctx, need_s, need_l);
     if (rc != BPE_OK) return rc;
     // the short rehash re-counts its uniques through short_add: reset [0]; [1],[2] (long) are untouched
     CUDA_TRY(ctx, cudaMemsetAsync(cs->counters.p, 0, sizeof(u64), ctx->stream));
     CountTables t = count_tables(ctx);
-    unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (old_view.scap + 255) / 256);
-    KLAUNCH(k_rehash_short, grid, 256, 0, ctx->stream, (const u64 *)old_view.stab.p, old_view.scap, t);
-    grid = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (old_view.lcap + 255) / 256);
-    KLAUNCH(k_rehash_long, grid, 256, 0, ctx->stream, (const u64 *)old_view.ltab.p, old_view.lcap, t);
+    if (n_short) {
+        unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (n_short + 255) / 256);
+        KLAUNCH(k_rehash_short, grid, 256, 0, ctx->stream, (const u64 *)old_view.stab.p, (const u32 *)old_view.slist.p, n_short, t);
+    }
+    if (n_long) {
+        unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (n_long + 255) / 256);
+        KLAUNCH(k_rehash_long, grid, 256, 0, ctx->stream, (const u64 *)old_view.ltab.p, (const u32 *)old_view.llist.p, n_long, t);
+    }
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    for (DevBuf *b : {&old_view.stab, &old_view.ltab}) bpe_buf_free(ctx, *b);
+    for (DevBuf *b : {&old_view.stab, &old_view.ltab, &old_view.slist, &old_view.llist}) bpe_buf_free(ctx, *b);
     return BPE_OK;
 }
 
@@ -541,7 +560,8 @@ static int count_current_text(bpe_ctx *ctx, u64 n, u64 own_begin, u64 own_end, u
     for (u64 bi = 0; bi < n_batches; bi++) {
         u64 b_lo = w_lo + bi * words_per_batch, b_hi = std::min(w_hi, b_lo + words_per_batch);
         u64 bytes = (b_hi - b_lo) * 32, bw = b_hi - b_lo;
-        BPE_TRY(count_ensure_capacity(ctx, c[0], c[1], bound[bi], std::min(bound[bi], bytes / (SHORT_MAX + 1) + 1)));
+        static const u64 bound_div = getenv("BPE_COUNT_BOUND_DIV") ? std::max(1, atoi(getenv("BPE_COUNT_BOUND_DIV"))) : 1;   // EXPERIMENT ONLY (unsafe)
+        BPE_TRY(count_ensure_capacity(ctx, c[0], c[1], bound[bi] / bound_div, std::min(bound[bi], bytes / (SHORT_MAX + 1) + 1) / bound_div));
         // ordinals of the batch's pretokens -> explicit offsets
         size_t cnt_b = round_up((bw + 1) * 4, 256), pre_b = round_up((bw + 2) * 8, 256), tmp_b = round_up(scan_tmp_elems_host(bw) * 8, 256);
         size_t off_b = round_up((bound[bi] + 2) * 4, 256);
@@ -558,10 +578,12 @@ static int count_current_text(bpe_ctx *ctx, u64 n, u64 own_begin, u64 own_end, u
         launch_starts_to_offsets(fl, b_lo, b_hi, n, pre, base, offs, bound[bi], ctx->sm_count, st);
         CountTables t = count_tables(ctx);
         if (bound[bi]) {
-            static const int cnt_ctas_per_sm = getenv("BPE_COUNT_CTAS") ? std::max(1, atoi(getenv("BPE_COUNT_CTAS"))) : (CNT_DYNAMIC ? 4 : 192);
-            unsigned g2 = (unsigned)std::min<u64>((u64)ctx->sm_count * cnt_ctas_per_sm, (bound[bi] + 255) / 256);
-            if (CNT_DYNAMIC) CUDA_TRY(ctx, cudaMemsetAsync(t.counters + 16, 0, 8, st));
-            KLAUNCH(k_count_pretokens, g2, 256, 0, st, t, offs, bound[bi], base, own_begin, own_end, trust_end);
+            static const int cnt_ctas_per_sm = getenv("BPE_COUNT_CTAS") ? std::max(1, atoi(getenv("BPE_COUNT_CTAS"))) : 2;
+            unsigned g2 = (unsigned)std::min<u64>((u64)ctx->sm_count * cnt_ctas_per_sm, (bound[bi] + CNT_TILE - 1) / CNT_TILE);
+            CUDA_TRY(ctx, cudaMemsetAsync(t.counters + 16, 0, 8, st));
+            static bool attr_set = false;
+            if (!attr_set) { CUDA_TRY(ctx, cudaFuncSetAttribute((void *)k_count_pretokens, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CNT_DYN_SMEM)); attr_set = true; }
+            KLAUNCH(k_count_pretokens, g2, CNT_NT, CNT_DYN_SMEM, st, t, offs, bound[bi], base, own_begin, own_end, trust_end);
         }
         CUDA_TRY(ctx, cudaGetLastError());
         if (bi + 1 < n_batches) BPE_TRY(read_counters(ctx, c, 8));
@@ -578,15 +600,20 @@ static int count_current_text(bpe_ctx *ctx, u64 n, u64 own_begin, u64 own_end, u
 static int count_rehome(bpe_ctx *ctx) {
     CountState *cs = ctx->count;
     cudaStream_t st = ctx->stream;
+    u64 c[2];
+    BPE_TRY(read_counters(ctx, c, 2));
+    const u64 n_long = c[1], first = cs->n_rehomed;
+    if (n_long <= first) return BPE_OK;
     CountTables t = count_tables(ctx);
     u64 *scr = (u64 *)ctx->scratch.p + 8;
     CUDA_TRY(ctx, cudaMemsetAsync(scr, 0, 16, st));
-    unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (cs->lcap + 255) / 256);
-    KLAUNCH(k_rehome_sizes, grid, 256, 0, st, t, scr);
+    unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (n_long - first + 255) / 256);
+    KLAUNCH(k_rehome_sizes, grid, 256, 0, st, t, first, n_long, scr);
     u64 *host = (u64 *)ctx->pinned;
     CUDA_TRY(ctx, cudaMemcpyAsync(host, scr, 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     u64 need = host[0];
+    cs->n_rehomed = n_long;
     if (!need) return BPE_OK;
     if (cs->pool_used + need > cs->pool.cap) {
         DevBuf nb;
@@ -599,7 +626,7 @@ static int count_rehome(bpe_ctx *ctx) {
     }
     host[0] = cs->pool_used;
     CUDA_TRY(ctx, cudaMemcpyAsync(scr + 1, host, 8, cudaMemcpyHostToDevice, st));
-    KLAUNCH(k_rehome_copy, grid, 256, 0, st, t, (uint8_t *)cs->pool.p, scr + 1);
+    KLAUNCH(k_rehome_copy, grid, 256, 0, st, t, first, n_long, (uint8_t *)cs->pool.p, scr + 1);
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     cs->pool_used += need;
@@ -630,43 +657,52 @@ BPE_API int bpe_count_add_shard_dev(bpe_ctx *ctx, const uint8_t *text_dev, uint6
     return count_add_shard(ctx, text_dev, n, true, own_begin, own_end, at_file_end);
 }
 
+// lens[] and the byte offsets of the export live in tmp1 between export_size and export (n_words entries, not table capacity)
+static int count_export_scan(bpe_ctx *ctx, u64 *n_short_out, u64 *n_words_out, u64 *blob_bytes_out) {
+    cudaStream_t st = ctx->stream;
+    u64 c[2];
+    BPE_TRY(read_counters(ctx, c, 2));
+    const u64 n_short = c[0], n_words = c[0] + c[1];
+    CountTables t = count_tables(ctx);
+    size_t lens_b = round_up((n_words + 1) * 4, 256), boff_b = round_up((n_words + 2) * 8, 256);
+    size_t tmp_b = scan_tmp_elems_host(n_words + 1) * 8;
+    BPE_TRY(bpe_buf_reserve(ctx, ctx->tmp1, lens_b + boff_b + tmp_b));
+    u32 *lens = (u32 *)ctx->tmp1.p;
+    u64 *boff = (u64 *)((uint8_t *)lens + lens_b);
+    u64 *tmp = (u64 *)((uint8_t *)boff + boff_b);
+    u64 *host = (u64 *)ctx->pinned;
+    host[0] = 0;
+    if (n_words) {
+        unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (n_words + 255) / 256);
+        KLAUNCH(k_export_lens, grid, 256, 0, st, t, n_short, n_words, lens);
+        launch_scan_u32(lens, n_words, boff, tmp, st);
+        CUDA_TRY(ctx, cudaGetLastError());
+        CUDA_TRY(ctx, cudaMemcpyAsync(host, boff + n_words, 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    }
+    *n_short_out = n_short; *n_words_out = n_words; *blob_bytes_out = host[0];
+    return BPE_OK;
+}
+
 BPE_API int bpe_count_export_size(bpe_ctx *ctx, uint64_t *n_words, uint64_t *blob_bytes) {
     if (!ctx || !ctx->count || !n_words || !blob_bytes) return BPE_ERR_ARG;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    CountState *cs = ctx->count;
-    cudaStream_t st = ctx->stream;
-    CountTables t = count_tables(ctx);
-    u64 total = cs->scap + cs->lcap;
-    size_t lens_b = round_up(total * 4, 256), pres_b = lens_b, boff_b = round_up((total + 1) * 8, 256), widx_b = boff_b;
-    size_t tmp_b = scan_tmp_elems_host(total) * 8;
-    BPE_TRY(bpe_buf_reserve(ctx, ctx->tmp1, lens_b + pres_b + boff_b + widx_b + tmp_b));
-    u32 *lens = (u32 *)ctx->tmp1.p; u32 *pres = (u32 *)((uint8_t *)lens + lens_b);
-    u64 *boff = (u64 *)((uint8_t *)pres + pres_b); u64 *widx = (u64 *)((uint8_t *)boff + boff_b);
-    u64 *tmp = (u64 *)((uint8_t *)widx + widx_b);
-    unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (total + 255) / 256);
-    KLAUNCH(k_export_lens, grid, 256, 0, st, t, lens);
-    KLAUNCH(k_export_flags, grid, 256, 0, st, lens, total, pres);
-    launch_scan_u32(lens, total, boff, tmp, st);
-    launch_scan_u32(pres, total, widx, tmp, st);
-    u64 *host = (u64 *)ctx->pinned;
-    CUDA_TRY(ctx, cudaMemcpyAsync(host, boff + total, 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(ctx, cudaMemcpyAsync(host + 1, widx + total, 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(ctx, cudaStreamSynchronize(st));
-    *blob_bytes = host[0]; *n_words = host[1];
+    u64 ns, nw, nb;
+    BPE_TRY(count_export_scan(ctx, &ns, &nw, &nb));
+    *n_words = nw; *blob_bytes = nb;
     return BPE_OK;
 }
 
 static int count_export(bpe_ctx *ctx, uint8_t *blob, uint64_t *offs, int64_t *counts, bool to_device) {
     if (!ctx || !ctx->count || !offs) return BPE_ERR_ARG;
-    uint64_t nw, nb;
-    BPE_TRY(bpe_count_export_size(ctx, &nw, &nb));   // recomputes the scans in tmp1
-    CountState *cs = ctx->count;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    u64 ns, nw, nb;
+    BPE_TRY(count_export_scan(ctx, &ns, &nw, &nb));
     cudaStream_t st = ctx->stream;
     CountTables t = count_tables(ctx);
-    u64 total = cs->scap + cs->lcap;
-    size_t lens_b = round_up(total * 4, 256), pres_b = lens_b, boff_b = round_up((total + 1) * 8, 256);
-    u32 *lens = (u32 *)ctx->tmp1.p; u32 *pres = (u32 *)((uint8_t *)lens + lens_b);
-    u64 *boff = (u64 *)((uint8_t *)pres + pres_b); u64 *widx = (u64 *)((uint8_t *)boff + boff_b);
+    size_t lens_b = round_up((nw + 1) * 4, 256);
+    u32 *lens = (u32 *)ctx->tmp1.p;
+    u64 *boff = (u64 *)((uint8_t *)lens + lens_b);
     uint8_t *dblob; u64 *doffs; i64 *dcnt;
     if (to_device) { dblob = blob; doffs = (u64 *)offs; dcnt = (i64 *)counts; }
     else {
@@ -675,9 +711,11 @@ static int count_export(bpe_ctx *ctx, uint8_t *blob, uint64_t *offs, int64_t *co
         dblob = (uint8_t *)ctx->tmp0.p; doffs = (u64 *)(dblob + ob); dcnt = (i64 *)(dblob + ob + oo);
     }
     if ((nb && !dblob) || (nw && !dcnt)) return BPE_ERR_ARG;
-    unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (total + 255) / 256);
-    KLAUNCH(k_export_write, grid, 256, 0, st, t, lens, boff, widx, dblob, doffs, dcnt);
-    CUDA_TRY(ctx, cudaGetLastError());
+    if (nw) {
+        unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (nw + 255) / 256);
+        KLAUNCH(k_export_write, grid, 256, 0, st, t, ns, nw, lens, boff, dblob, doffs, dcnt);
+        CUDA_TRY(ctx, cudaGetLastError());
+    }
     if (to_device) {
         CUDA_TRY(ctx, cudaMemcpyAsync(doffs + nw, &nb, 8, cudaMemcpyHostToDevice, st));
     } else {
@@ -752,7 +790,6 @@ BPE_API int bpe_count_pair_table(bpe_ctx *ctx, const uint8_t *specials_blob, con
     if (!ctx || !ctx->count || !dense_out || (n_specials > 0 && (!specials_blob || !special_offs))) return BPE_ERR_ARG;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    CountState *cs = ctx->count;
     const uint8_t *spb; const u32 *spo; u32 spmax;
     BPE_TRY(ctx_upload_specials(ctx, specials_blob, special_offs, n_specials, &spb, &spo, &spmax));
     DevBuf dense;
@@ -760,9 +797,12 @@ BPE_API int bpe_count_pair_table(bpe_ctx *ctx, const uint8_t *specials_blob, con
     BPE_TRY(bpe_buf_reserve(ctx, dense, 65536 * 8));
     CUDA_TRY(ctx, cudaMemsetAsync(dense.p, 0, 65536 * 8, st));
     CountTables t = count_tables(ctx);
-    u64 total = cs->scap + cs->lcap;
-    unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (total + 255) / 256);
-    KLAUNCH(k_dense_pairs, grid, 256, 0, st, t, spb, spo, n_specials, (u64 *)dense.p);
+    u64 c[2];
+    BPE_TRY(read_counters(ctx, c, 2));
+    if (c[0] + c[1]) {
+        unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (c[0] + c[1] + 255) / 256);
+        KLAUNCH(k_dense_pairs, grid, 256, 0, st, t, c[0], c[0] + c[1], spb, spo, n_specials, (u64 *)dense.p);
+    }
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaMemcpyAsync(dense_out, dense.p, 65536 * 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
@@ -799,10 +839,9 @@ static int run_merges(bpe_ctx *ctx, const uint8_t *sp_blob, const u32 *sp_offs, 
     CUDA_TRY(ctx, cudaMemsetAsync(B.wctr.p, 0, 64, st));
     Words W{(int32_t *)B.sym.p, (WordMeta *)B.wmeta.p, (u64 *)B.wctr.p};
     CountTables t = count_tables(ctx);
-    {
-        u64 total = cs->scap + cs->lcap;
-        unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (total + 255) / 256);
-        KLAUNCH(k_build_words, grid, 256, 0, st, t, W, spb, spo, n_sp);
+    if (max_words) {
+        unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (max_words + 255) / 256);
+        KLAUNCH(k_build_words, grid, 256, 0, st, t, n_short, max_words, W, spb, spo, n_sp);
         CUDA_TRY(ctx, cudaGetLastError());
     }
     u64 *host = (u64 *)ctx->pinned;
