@@ -51,7 +51,7 @@ void bpe_buf_free(bpe_ctx *ctx, DevBuf &b) {
     if (!b.p) { b.cap = 0; return; }
     if (ctx) {
         ctx->pool.push_back(b);
-        if (ctx->pool.size() > 64) {             // bound the cache: drop the buffer that has waited longest
+        if (ctx->pool.size() > 256) {            // bound the cache: drop the buffer that has waited longest (a training call alone holds ~40 buffers)
             cudaFree(ctx->pool.front().p);       // (cudaFree synchronises the device: nothing can still be using it)
             ctx->pool.erase(ctx->pool.begin());
         }

@@ -533,6 +533,8 @@ static int count_ensure_capacity(bpe_ctx *ctx, u64 n_short, u64 n_long, u64 new_
     return BPE_OK;
 }
 
+#include <chrono>
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 #define COUNT_BATCH_BYTES (256ull << 20)
 
 // Count the pretokens whose start lies in [own_begin, own_end) of the text currently in the arena
@@ -557,7 +559,9 @@ static int count_current_text(bpe_ctx *ctx, u64 n, u64 own_begin, u64 own_end, u
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     u64 c[8];
     BPE_TRY(read_counters(ctx, c, 8));
+    static const bool prof = getenv("BPE_COUNT_PROFILE") != nullptr;
     for (u64 bi = 0; bi < n_batches; bi++) {
+        const double tb0 = prof ? now_ms() : 0;
         u64 b_lo = w_lo + bi * words_per_batch, b_hi = std::min(w_hi, b_lo + words_per_batch);
         u64 bytes = (b_hi - b_lo) * 32, bw = b_hi - b_lo;
         static const u64 bound_div = getenv("BPE_COUNT_BOUND_DIV") ? std::max(1, atoi(getenv("BPE_COUNT_BOUND_DIV"))) : 1;   // EXPERIMENT ONLY (unsafe)
@@ -587,6 +591,7 @@ static int count_current_text(bpe_ctx *ctx, u64 n, u64 own_begin, u64 own_end, u
         }
         CUDA_TRY(ctx, cudaGetLastError());
         if (bi + 1 < n_batches) BPE_TRY(read_counters(ctx, c, 8));
+        if (prof) { cudaStreamSynchronize(st); fprintf(stderr, "  [batch %llu: %llu pretokens] %.2f ms (tables %llu + %llu slots)\n", (unsigned long long)bi, (unsigned long long)bound[bi], now_ms() - tb0, (unsigned long long)cs->scap, (unsigned long long)cs->lcap); }
     }
     BPE_TRY(read_counters(ctx, c, 8));
     if (c[6]) return bpe_set_error(ctx, BPE_ERR_HALO, "a pretoken that starts in the owned range runs past the right halo");
@@ -636,15 +641,22 @@ static int count_rehome(bpe_ctx *ctx) {
 static int count_add_shard(bpe_ctx *ctx, const uint8_t *text, u64 n, bool on_device, u64 own_begin, u64 own_end, int at_file_end) {
     if (!ctx || !ctx->count || !ctx->count->active || (!text && n) || own_begin > own_end || own_end > n) return BPE_ERR_ARG;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    static const bool prof = getenv("BPE_COUNT_PROFILE") != nullptr;     // debug aid: host-side wall time of the phases (synchronising)
+    double t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+    if (prof) { cudaStreamSynchronize(ctx->stream); t0 = now_ms(); }
     BPE_TRY(ctx_load_text(ctx, text, n, on_device));
     u64 nn = n;
     // only ill-formed sequences that start in the owned range are this shard's to report
     BPE_TRY(ctx_run_flags(ctx, &nn, false, nullptr, nullptr, 0, 0, own_begin, own_end));
     if (ctx->saw_cr) return bpe_set_error(ctx, BPE_ERR_NEWLINE, "the shard contains a carriage return");
+    if (prof) { cudaStreamSynchronize(ctx->stream); t1 = now_ms(); }
     // start bits in the last 16 bytes of a shard that is cut mid-file lack their right context
     u64 trust_end = at_file_end ? n : (n >= 16 ? n - 16 : 0);
     BPE_TRY(count_current_text(ctx, n, own_begin, own_end, trust_end));
-    return count_rehome(ctx);
+    if (prof) { cudaStreamSynchronize(ctx->stream); t2 = now_ms(); }
+    int rc = count_rehome(ctx);
+    if (prof) { cudaStreamSynchronize(ctx->stream); t3 = now_ms(); fprintf(stderr, "[count_add_shard %.2f GB] load+flags %.2f ms, count %.2f ms, rehome %.2f ms\n", n / 1e9, t1 - t0, t2 - t1, t3 - t2); }
+    return rc;
 }
 BPE_API int bpe_count_add_shard(bpe_ctx *ctx, const uint8_t *text_host, uint64_t n, uint64_t own_begin, uint64_t own_end,
                                 int at_file_start, int at_file_end) {
