@@ -205,6 +205,34 @@ def test_multi_merge_steps_match_oracle_on_adjacent_sites(monkeypatch, grid):
     assert batched >= 6                                   # the multi-merge path really ran
 
 
+def _shared_token_corpus(seed, n_words=500):
+    """Words over a small alphabet with skewed letter frequencies: the top pairs SHARE tokens ((a,b), (a,c), (c,b), ...), sit next
+    to each other in every order and overlap (aba, abab, aab): what the relaxed batching rule admits into one step."""
+    rnd = random.Random(seed)
+    alpha = "abcdefg"[: 4 + seed % 4]
+    weights = [1.0 / (k + 1) for k in range(len(alpha))]
+    out = []
+    for _ in range(n_words):
+        w = "".join(rnd.choices(alpha, weights, k=rnd.randint(2, 9)))
+        out.extend([w] * rnd.randint(1, 30 + 13 * (seed % 5)))
+    rnd.shuffle(out)
+    return " ".join(out).encode()
+
+
+@pytest.mark.parametrize("grid", [None, "5", "148"])
+def test_multi_merge_steps_with_shared_tokens_match_oracle(monkeypatch, grid):
+    if grid:
+        monkeypatch.setenv("BPE_MERGE_G", grid)
+    batched = 0
+    for seed in range(24):
+        data = _shared_token_corpus(seed)
+        want = oracle.train_bpe_on_bytes(data, 256 + 80, [])
+        vocab, merges, st = _train_bytes(data, 256 + 80, [], return_stats=True)
+        assert merges == want[1] and vocab == want[0], seed
+        batched += st["merge_steps"] < len(merges)
+    assert batched >= 8
+
+
 @pytest.mark.parametrize("batch", ["1", "2", "5"])
 def test_merges_do_not_depend_on_the_batch_limit(monkeypatch, batch):
     from transformer_lm_b200.synth import synth_host

@@ -26,13 +26,16 @@
 // Several merges per step (the loop is latency-bound: two grid barriers and ~10 dependent memory round trips per step, whatever
 // the step does).  Every CTA reports its best TWO pairs and a bound H on the count of everything else it owns; every CTA then
 // derives the same sorted candidate list d1 >= d2 >= ... and applies the longest prefix d1..dr (r <= MG_BATCH) with
-//   (1) all 2r tokens distinct, no a == b unless r == 1,
+//   (1) for i < j: the second token of dj is not the first token of di, and the first token of dj is not the second token of di
+//       (dj is neither of the form (x, a_i) nor (b_i, y)); no a == b unless r == 1,
 //   (2) count(dr) > count(d(r+1)) and count(dr) > H.
 // Why this is exactly the reference's next r merges: merge i only decrements pairs (x, a_i) and (b_i, y) and creates pairs that
-// contain its new token.  By (1) no dj is decremented by another merge of the step, and the occurrences of dj are untouched.  A new
-// pair (x, new_i) is counted at most count(x, a_i) times, and (x, a_i) is neither a d1..dr (distinct tokens) nor, by (2), a pair
-// with a count >= count(dr): so every pair created or changed during the step stays strictly below count(dr), the reference's
-// max() picks d1, .., dr in this order, and the pair it picks next is again the maximum of the table after the step.
+// contain its new token.  By (1) no dj is decremented by an earlier merge of the step and no occurrence of dj shares a symbol with
+// an occurrence of di (the merges may share tokens otherwise: (a,b) and (a,c) do not interact).  A new pair (x, new_i) is counted
+// at most count(x, a_i) times, and (x, a_i) is not a later dj by (1), cannot occur after an earlier dj = (x, a_i) took all its
+// occurrences, and otherwise has, by (2), a count below count(dr): so every pair created or changed during the step stays strictly
+// below count(dr), the reference's max() picks d1, .., dr in this order, and the pair it picks next is again the maximum of the
+// table after the step.
 // Adjacent sites of different merges of a step are resolved as the reference's sequence would: a site of merge j sees the
 // occurrences of merges i < j already merged and those of merges i > j untouched (apply_site).
 #pragma once
@@ -56,7 +59,7 @@ __device__ __forceinline__ u32 pair_hash(u64 key) {
 #define MG_NT 512
 #define MG_NEED_GROW 8ull                        // ctr[3] code: pair table more than half full, host must grow it
 #ifndef MG_BATCH
-#define MG_BATCH 12u                             // merges per step, at most (2 (MG_BATCH + 1) <= 32: select_batch ranks the survivors in one warp; measured at 11 GB: 8 -> 197 ms, 12 -> 183, 15 -> 183)
+#define MG_BATCH 15u                             // merges per step, at most (2 (MG_BATCH + 1) <= 32: select_batch ranks the survivors in one warp; measured at 11 GB: 8 -> 197 ms, 12 -> 183, 15 -> 183)
 #endif
 
 struct __align__(16) WordMeta {
@@ -351,14 +354,18 @@ __device__ __noinline__ void apply_site(u32 p, i64 c, u32 j, int step0, u32 nw0,
     } else if (vl != SYM_SEP) {
         const int32_t o1 = ORIG(vl);
         has_l = true; left = (u32)o1; pos_l = q;
+        // (.., a_i, b_i, [a, b]): when the occurrence on the left is a site of a merge i <= j it is merged before this one
+        // (several merges of the step may have the same second token: the symbol further left decides which one it is)
+        bool looked = false; u32 q2 = q - 1; int32_t o2 = SYM_SEP;
         for (u32 i = 0; i <= j; i++) {
             if ((int32_t)B->b[i] != o1) continue;
-            // (.., a_i, b_i, [a, b]): the occurrence on the left is a site of merge i <= j: it is merged before this one
-            u32 q2 = q - 1;
-            int32_t v2 = s[q2];
-            while (OLD_TOMB(v2)) { q2--; v2 = s[q2]; }
-            if (WAS_LIVE(v2) && ORIG(v2) == (int32_t)B->a[i]) { left = nw0 + i; pos_l = q2; }
-            break;
+            if (!looked) {
+                int32_t v2 = s[q2];
+                while (OLD_TOMB(v2)) { q2--; v2 = s[q2]; }
+                o2 = WAS_LIVE(v2) ? ORIG(v2) : SYM_SEP;
+                looked = true;
+            }
+            if (o2 == (int32_t)B->a[i]) { left = nw0 + i; pos_l = q2; break; }
         }
     }
     // ---- right context: the symbol as it was, unless it starts a site of an EARLIER merge of this step ----
@@ -368,13 +375,17 @@ __device__ __noinline__ void apply_site(u32 p, i64 c, u32 j, int step0, u32 nw0,
     const bool has_r = vr != SYM_SEP;
     u32 right = has_r ? (u32)ORIG(vr) : 0;
     if (has_r) {
+        bool looked = false; int32_t o3 = SYM_SEP;
         for (u32 i = 0; i < j; i++) {
             if (B->a[i] != right) continue;
-            u32 q3 = qr + 1;
-            int32_t v3 = s[q3];
-            while (OLD_TOMB(v3)) { q3++; v3 = s[q3]; }
-            if (WAS_LIVE(v3) && ORIG(v3) == (int32_t)B->b[i]) right = nw0 + i;
-            break;
+            if (!looked) {
+                u32 q3 = qr + 1;
+                int32_t v3 = s[q3];
+                while (OLD_TOMB(v3)) { q3++; v3 = s[q3]; }
+                o3 = WAS_LIVE(v3) ? ORIG(v3) : SYM_SEP;
+                looked = true;
+            }
+            if (o3 == (int32_t)B->b[i]) { right = nw0 + i; break; }
         }
     }
     const u32 a = (u32)ia, b = (u32)ib, nw = (u32)inw;
@@ -488,21 +499,9 @@ __device__ __noinline__ Best rescan_block(u32 blk, const u64 *prev, u32 n_prev, 
 #define SORT_MAX_BK (1u << SORT_MAX_LG)
 __device__ __forceinline__ u32 bucket_of(u32 x, u32 lg) { return (x * 0x9E3779B1u) >> (32u - lg); }
 
-// Index range of the pair (a,b): token_indices[best_pair] of train.py:192.  out[0..1] = record range, out[2] = source code.
-__device__ __forceinline__ void winner_range(u64 key, u64 *out) {
-    const u32 wa = (u32)(key >> 32), wb = (u32)key, wT = wa > wb ? wa : wb;
-    if (wT < 256) { u32 pp = (wa << 8) | wb; out[0] = cM.csr_off[pp]; out[1] = cM.csr_off[pp + 1]; out[2] = 2; return; }
-    const u32 t = wT - 256;
-    const ulonglong2 rg = *reinterpret_cast<const ulonglong2 *>(&cM.log_rng[2 * (u64)t]);
-    const u64 lo = rg.x, hi = rg.y;
-    const u32 lg = cM.bk_lg[t];
-    const u64 st0 = cM.bk_start[t];              // (garbage when the slice is unsorted; loaded alongside, not after)
-    if (!lg) { out[0] = lo; out[1] = hi; out[2] = 0; return; }
-    const u32 want = wb >= wa ? wa : (0x80000000u | wb);
-    const u64 st = st0 + bucket_of(want, lg);
-    out[0] = lo + cM.bk_off[st]; out[1] = lo + cM.bk_off[st + 1]; out[2] = 1;
-}
-
+// Index range of a pair (a,b) -- token_indices[best_pair] of train.py:192 -- is looked up in select_batch: pairs of two initial
+// bytes in the CSR; any other pair in the log slice of the step that made its younger token, in the bucket of its other token
+// when that slice was sorted.
 // Bucket-sort the slice [lo, lo + n) of the log by hash(record.x) into log2 (same offsets) and publish the bucket
 // offsets for the r merges [step0, step0 + r) that wrote it.  Called by every thread of every CTA between two steps; `sync` is
 // the grid barrier.  s_scan: SORT_MAX_BK u32 of shared memory.  parity alternates so that the scratch of the previous sort can
@@ -619,64 +618,96 @@ __device__ __forceinline__ void grid_barrier(u32 *counter, u32 G, u32 epoch, u64
 //                 the rule with one lane per candidate.
 #define MG_SURV (2u * (MG_BATCH + 1u))
 __device__ __noinline__ bool best_greater_ni(const Best *x, const Best *y) { return best_greater(*x, *y); }
+// All warps of the CTA: warp w ranks the best pairs of CTAs [w * per, (w + 1) * per) against all G best pairs, which its lanes hold
+// in registers (five per lane): a candidate costs five compares per lane and two warp reductions.  Pairs of equal count are
+// compared in full only for candidates that can still be among the first MG_BATCH + 1.
 __device__ __forceinline__ void rank_bests(const Best *s_c, const i64 *s_cnt, Best *s_surv, u32 G) {
-    const u32 t = threadIdx.x;                    // all threads of the CTA call this; threads 2i and 2i + 1 share CTA i's best pair
-    const u32 i = t >> 1, half = (G + 1) / 2;
-    const bool act = i < G;
-    const u32 j0 = (t & 1u) ? half : 0u, j1 = act ? ((t & 1u) ? G : half) : 0u;
-    const i64 ci = act ? s_cnt[2 * i] : CNT_DEAD;
-    // counts first: most pairs are out after this pass, and only pairs that can still be among the first MG_BATCH + 1 pay for
-    // the (bytes, bytes) comparisons with the pairs of equal count
-    u32 gt = 0, ties = 0;                         // (ties counts the pair itself)
-#pragma unroll 4
-    for (u32 j = j0; j < j1; j++) { const i64 cj = s_cnt[2 * j]; gt += cj > ci; ties += cj == ci; }
-    gt += __shfl_xor_sync(0xffffffffu, gt, 1);
-    ties += __shfl_xor_sync(0xffffffffu, ties, 1);
-    u32 extra = 0;
-    if (act && ci != CNT_DEAD && gt <= MG_BATCH && ties > 1) {
+    const u32 lane = lane_id(), warp = threadIdx.x >> 5;
+    const u32 per = (G + MG_NT / 32 - 1) / (MG_NT / 32);
+    i64 cj[MG_MAX_CTAS / 32];
+#pragma unroll
+    for (u32 m = 0; m < MG_MAX_CTAS / 32; m++) { const u32 j = lane + 32 * m; cj[m] = j < G ? s_cnt[2 * j] : CNT_DEAD; }
 #pragma unroll 1
-        for (u32 j = j0; j < j1; j++) if (s_cnt[2 * j] == ci && j != i && best_greater_ni(&s_c[2 * j], &s_c[2 * i])) extra++;
+    for (u32 k = 0; k < per; k++) {
+        const u32 i = warp * per + k;
+        if (i >= G) break;
+        const i64 ci = s_cnt[2 * i];
+        if (ci == CNT_DEAD) continue;
+        u32 gt = 0, eq = 0;
+#pragma unroll
+        for (u32 m = 0; m < MG_MAX_CTAS / 32; m++) { gt += cj[m] > ci; eq += cj[m] == ci; }
+        gt = __reduce_add_sync(0xffffffffu, gt);
+        eq = __reduce_add_sync(0xffffffffu, eq);   // (counts the pair itself)
+        if (gt <= MG_BATCH && eq > 1) {
+            u32 extra = 0;
+#pragma unroll 1
+            for (u32 m = 0; m < MG_MAX_CTAS / 32; m++) {
+                const u32 j = lane + 32 * m;
+                if (j < G && j != i && s_cnt[2 * j] == ci && best_greater_ni(&s_c[2 * j], &s_c[2 * i])) extra++;
+            }
+            gt += __reduce_add_sync(0xffffffffu, extra);
+        }
+        if (lane == 0 && gt <= MG_BATCH) { s_surv[2 * gt] = s_c[2 * i]; s_surv[2 * gt + 1] = s_c[2 * i + 1]; }
     }
-    extra += __shfl_xor_sync(0xffffffffu, extra, 1);
-    const u32 rank = gt + extra;
-    if (act && !(t & 1u) && ci != CNT_DEAD && rank <= MG_BATCH) { s_surv[2 * rank] = s_c[2 * i]; s_surv[2 * rank + 1] = s_c[2 * i + 1]; }
 }
 // warp 0; H: bound of every pair that is not a candidate; max_r: upper limit of merges for this step
 __device__ __noinline__ void select_batch(const Best *s_surv, Best *s_sorted, i64 H, Batch *B, u32 max_r) {
     const u32 lane = threadIdx.x;
     const Best e = lane < MG_SURV ? s_surv[lane] : BEST_NONE;
+    // rank of this lane's survivor among the survivors: one shuffled count per round, the (bytes, bytes) comparison only on ties
     u32 rank = 0;
 #pragma unroll 1
-    for (u32 m = 0; m < MG_SURV; m++) { const Best o = s_surv[m]; if (o.cnt != CNT_DEAD && m != lane && best_greater(o, e)) rank++; }
+    for (u32 m = 0; m < MG_SURV; m++) {
+        const i64 cm = __shfl_sync(0xffffffffu, e.cnt, m);
+        if (cm > e.cnt) rank++;
+        else if (cm == e.cnt && cm != CNT_DEAD && m != lane && best_greater_ni(&s_surv[m], &s_surv[lane])) rank++;
+    }
     if (lane <= MG_BATCH) s_sorted[lane] = BEST_NONE;
     __syncwarp();
     if (e.cnt != CNT_DEAD && rank <= MG_BATCH) s_sorted[rank] = e;
     __syncwarp();
     const Best d = lane <= MG_BATCH ? s_sorted[lane] : BEST_NONE;           // lane t holds d(t+1)
     const u32 a = (u32)(d.key >> 32), b = (u32)d.key;
+    // first half of the index-range lookup of every candidate, in flight while the rule is evaluated (winner_range, split)
+    const u32 wT = a > b ? a : b;
+    const bool have = d.cnt != CNT_DEAD, csr = wT < 256;
+    u64 r_lo = 0, r_hi = 0, st0 = 0; u32 lg = 0;
+    if (have) {
+        if (csr) { const u32 pp = (a << 8) | b; r_lo = cM.csr_off[pp]; r_hi = cM.csr_off[pp + 1]; }
+        else {
+            const u32 t = wT - 256;
+            const ulonglong2 rg = *reinterpret_cast<const ulonglong2 *>(&cM.log_rng[2 * (u64)t]);
+            r_lo = rg.x; r_hi = rg.y; lg = cM.bk_lg[t]; st0 = cM.bk_start[t];
+        }
+    }
     const bool sq0 = __shfl_sync(0xffffffffu, a == b, 0);
-    bool bad = d.cnt == CNT_DEAD || (lane > 0 && (a == b || sq0));          // a == b goes alone
-#pragma unroll
+    bool bad = !have || (lane > 0 && (a == b || sq0));                        // a == b goes alone
+#pragma unroll 1
     for (u32 i = 0; i < MG_BATCH; i++) {
         const u32 ai = __shfl_sync(0xffffffffu, a, i), bi = __shfl_sync(0xffffffffu, b, i);
-        if (i < lane) bad |= ai == a || ai == b || bi == a || bi == b;
+        if (i < lane) bad |= ai == b || bi == a;  // this pair is (x, a_i) or (b_i, y): merge i changes its count
     }
-    const u32 first_bad = __ffs(__ballot_sync(0xffffffffu, bad || lane >= max_r)) - 1;   // d1 .. d(first_bad) share no token
+    const u32 first_bad = __ffs(__ballot_sync(0xffffffffu, bad || lane >= max_r)) - 1;   // d1 .. d(first_bad) do not interact
     const i64 next = __shfl_down_sync(0xffffffffu, d.cnt, 1);
-    const bool strict = d.cnt != CNT_DEAD && d.cnt > H && (next == CNT_DEAD || d.cnt > next);   // d1 .. d(lane+1) may go together
+    const bool strict = have && d.cnt > H && (next == CNT_DEAD || d.cnt > next);   // d1 .. d(lane+1) may go together
     const u32 ends = __ballot_sync(0xffffffffu, lane < first_bad && strict);
     u32 good = ends ? 32u - __clz(ends) : 0u;
-    const bool any = __shfl_sync(0xffffffffu, d.cnt != CNT_DEAD, 0);
+    const bool any = __shfl_sync(0xffffffffu, have, 0);
     if (good == 0 && any && max_r > 0) good = 1;  // the maximum alone is always the reference's next merge
     // index ranges of the merges, one lane each
     u64 n = 0;
     if (lane < good) {
-        u64 rg[3];
-        winner_range(d.key, rg);
+        const u32 want = b >= a ? a : (0x80000000u | b);
+        u32 code = csr ? 2u : 0u;
+        if (!csr && lg) {                         // bucket-sorted slice: the bucket of the neighbour
+            const u64 st = st0 + bucket_of(want, lg);
+            const u64 base = r_lo;
+            r_lo = base + cM.bk_off[st]; r_hi = base + cM.bk_off[st + 1]; code = 1u;
+        }
         B->a[lane] = a; B->b[lane] = b; B->key[lane] = d.key; B->cnt[lane] = d.cnt;
-        B->lo[lane] = rg[0]; B->src[lane] = T_SRC(rg[2]);
-        B->want[lane] = (a > b ? a : b) < 256 ? WANT_ANY : (b >= a ? a : (0x80000000u | b));
-        n = rg[1] - rg[0];
+        B->lo[lane] = r_lo; B->src[lane] = T_SRC(code);
+        B->want[lane] = csr ? WANT_ANY : want;
+        n = r_hi - r_lo;
     }
     u64 inc = n;
 #pragma unroll

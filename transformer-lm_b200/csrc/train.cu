@@ -879,7 +879,12 @@ static int run_merges(bpe_ctx *ctx, const uint8_t *sp_blob, const u32 *sp_offs, 
     // persistent kernel is simply relaunched after the rehash).
     u64 n_pairs0 = 0;
     for (u64 v : dense) n_pairs0 += v != 0;
-    u64 pcap = next_pow2(std::max<u64>(1 << 12, std::max<u64>(8 * n_pairs0, n_syms / 8)));
+    // At least 2^22 slots (64 MB): every 64-slot block reports only its largest pair, so the several-merges-per-step rule needs
+    // the top pairs in different blocks (a small table put the top 16 of a TinyStories-sized run into a few hundred blocks and the
+    // hidden second-largest counts cut the batches short).  The grid is sized from the natural capacity, not from the floor.
+    const u64 pcap_natural = next_pow2(std::max<u64>(1 << 12, std::max<u64>(8 * n_pairs0, n_syms / 8)));
+    static const u64 pcap_floor = getenv("BPE_MERGE_PCAP_MIN") ? std::max<u64>(1 << 12, next_pow2(strtoull(getenv("BPE_MERGE_PCAP_MIN"), nullptr, 10))) : (1ull << 22);
+    u64 pcap = std::max(pcap_natural, pcap_floor);
     MergeState M;
     memset(&M, 0, sizeof(M));
     M.W = W; M.n_words = (u32)n_words;
@@ -967,7 +972,7 @@ static int run_merges(bpe_ctx *ctx, const uint8_t *sp_blob, const u32 *sp_offs, 
         // grid: one CTA per SM for big tables, fewer for small ones (cheaper barriers).  Measured at 11 GB with the counter
         // barrier, same box: G = 148: 449 ms, 112: 464, 96: 463, 80: 481, 64: 485, 48: 535.  (With the per-CTA flag barrier
         // that this replaced, 64 CTAs were the optimum: polling 148 slots cost more than the extra apply threads gave.)
-        int G = std::max(2, (int)std::min<u64>((u64)std::min(ctx->sm_count, (int)MG_MAX_CTAS), (u64)M.n_blocks / 256 + 1 + (n_words + 4095) / 4096));
+        int G = std::max(2, (int)std::min<u64>((u64)std::min(ctx->sm_count, (int)MG_MAX_CTAS), std::max<u64>(pcap_natural, M.pcap / 16) / PB / 256 + 1 + (n_words + 4095) / 4096));
         if (const char *e = getenv("BPE_MERGE_G")) G = std::max(2, std::min(atoi(e), std::min(ctx->sm_count, (int)MG_MAX_CTAS)));
         g_bpe_launches++;
         CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_merge_loop, dim3(G), dim3(MG_NT), nullptr, MG_DYN_SMEM, st));
