@@ -29,6 +29,11 @@ if os.environ.get("BPE_STEP_PROFILE"):
     ph1, ph2, r = a[:, 0] / 1e3, a[:, 1] / 1e3, a[:, 3]
     tot = ph1 + ph2
     print("step time us: sum %.0f ms; percentiles 10/50/90/99: %s" % (tot.sum() / 1e3, np.percentile(tot, [10, 50, 90, 99]).round(1)))
-    for k in range(1, 9):
+    idx = np.nonzero(np.fromfile(os.environ["BPE_STEP_PROFILE"], dtype=np.uint32).reshape(-1, 4)[:, 3] > 0)[0]
+    for lo, hi in [(0, 100), (100, 1000), (1000, 5000), (5000, 15000), (15000, 1 << 30)]:
+        mk = (idx >= lo) & (idx < hi)
+        if mk.any(): print("  merges %5d-%5d: %5d steps, %.1f ms total, %.1f us/step (ph1+gather %.1f, apply+sync %.1f), %.1f merges/step" % (
+            lo, min(hi, idx.max()), mk.sum(), tot[mk].sum() / 1e3, tot[mk].mean(), ph1[mk].mean(), ph2[mk].mean(), r[mk].mean()))
+    for k in range(1, 16):
         mk = r == k
         if mk.any(): print("  batch %d: %6d steps, ph1+gather %.1f us, apply+sync %.1f us" % (k, mk.sum(), ph1[mk].mean(), ph2[mk].mean()))

@@ -59,7 +59,7 @@ __device__ __forceinline__ u32 pair_hash(u64 key) {
 #define MG_NT 512
 #define MG_NEED_GROW 8ull                        // ctr[3] code: pair table more than half full, host must grow it
 #ifndef MG_BATCH
-#define MG_BATCH 15u                             // merges per step, at most (2 (MG_BATCH + 1) <= 32: select_batch ranks the survivors in one warp; measured at 11 GB: 8 -> 197 ms, 12 -> 183, 15 -> 183)
+#define MG_BATCH 15u                             // merges per step, at most (<= 30).  Measured at 11 GB with the relaxed rule: 15 -> 143 ms, 20 -> 150, 24 -> 155, 30 -> 164 (fewer steps, but every extra merge of a step costs ~1.5 us of rescans and apply work)
 #endif
 
 struct __align__(16) WordMeta {
@@ -142,8 +142,8 @@ struct MergeState {
     u64 *cta_prof;    // optional (profile builds): per step and CTA {start, arrive1, exit1, arrive2}
     u32 *step_prof;   // optional per-step trace: 4 x u32 per step (phase1+sync1 ns, apply+sync2 ns, records scanned, words rewritten so far)
 };
-#define MG_CTR_WORDS 32
-#define MG_CTR_PENDING 16
+#define MG_CTR_WORDS 64
+#define MG_CTR_PENDING 16                        // .. 16 + MG_BATCH <= 64
 
 // The loop state lives in constant memory: helpers are real (non-inlined) functions so that the persistent
 // kernel stays small enough for the instruction caches -- every step runs each code path only once, so a
@@ -653,18 +653,25 @@ __device__ __forceinline__ void rank_bests(const Best *s_c, const i64 *s_cnt, Be
 // warp 0; H: bound of every pair that is not a candidate; max_r: upper limit of merges for this step
 __device__ __noinline__ void select_batch(const Best *s_surv, Best *s_sorted, i64 H, Batch *B, u32 max_r) {
     const u32 lane = threadIdx.x;
+    // rank of the survivors among themselves (a lane holds survivors lane and lane + 32): counts first, the (bytes, bytes)
+    // comparison only on ties
     const Best e = lane < MG_SURV ? s_surv[lane] : BEST_NONE;
-    // rank of this lane's survivor among the survivors: one shuffled count per round, the (bytes, bytes) comparison only on ties
-    u32 rank = 0;
+    const Best e2 = lane + 32 < MG_SURV ? s_surv[lane + 32] : BEST_NONE;
+    u32 rank = 0, rank2 = 0;
 #pragma unroll 1
     for (u32 m = 0; m < MG_SURV; m++) {
-        const i64 cm = __shfl_sync(0xffffffffu, e.cnt, m);
+        const i64 cm = s_surv[m].cnt;
         if (cm > e.cnt) rank++;
         else if (cm == e.cnt && cm != CNT_DEAD && m != lane && best_greater_ni(&s_surv[m], &s_surv[lane])) rank++;
+        if (MG_SURV > 32) {
+            if (cm > e2.cnt) rank2++;
+            else if (cm == e2.cnt && cm != CNT_DEAD && m != lane + 32 && best_greater_ni(&s_surv[m], &s_surv[lane + 32])) rank2++;
+        }
     }
     if (lane <= MG_BATCH) s_sorted[lane] = BEST_NONE;
     __syncwarp();
     if (e.cnt != CNT_DEAD && rank <= MG_BATCH) s_sorted[rank] = e;
+    if (MG_SURV > 32 && e2.cnt != CNT_DEAD && rank2 <= MG_BATCH) s_sorted[rank2] = e2;
     __syncwarp();
     const Best d = lane <= MG_BATCH ? s_sorted[lane] : BEST_NONE;           // lane t holds d(t+1)
     const u32 a = (u32)(d.key >> 32), b = (u32)d.key;
@@ -711,7 +718,7 @@ __device__ __noinline__ void select_batch(const Best *s_surv, Best *s_sorted, i6
     }
     u64 inc = n;
 #pragma unroll
-    for (int k = 1; k < (int)MG_BATCH; k <<= 1) { const u64 t = __shfl_up_sync(0xffffffffu, inc, k); if (lane >= (u32)k) inc += t; }
+    for (int k = 1; k < 32; k <<= 1) { const u64 t = __shfl_up_sync(0xffffffffu, inc, k); if (lane >= (u32)k) inc += t; }
     if (lane < good) B->pre[lane + 1] = inc;
     if (lane == 0) { B->pre[0] = 0; B->r = good; }
 }
@@ -784,7 +791,7 @@ __device__ __forceinline__ void token_bookkeeping(int step0, u32 nw0, const Batc
         if (lane < r) ln = cM.tok_len[B->a[lane]] + cM.tok_len[B->b[lane]];
         u32 inc = ln;
 #pragma unroll
-        for (int d = 1; d < (int)MG_BATCH; d <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (u32)d) inc += t; }
+        for (int d = 1; d < 32; d <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (u32)d) inc += t; }
         if (lane < r) s_off[lane] = inc - ln;
         if (lane == r - 1) s_off[MG_BATCH] = inc;
     }
@@ -794,10 +801,10 @@ __device__ __forceinline__ void token_bookkeeping(int step0, u32 nw0, const Batc
     const u64 total = s_off[MG_BATCH];
     if (cur + total > cM.tok_bytes_cap) { if (tid == 0) cM.ctr[3] = 4; }
     else {
-        if (warp < r) {
-            const u32 a = B->a[warp], b = B->b[warp], nw = nw0 + warp;
+        for (u32 j = warp; j < r; j += MG_NT / 32) {
+            const u32 a = B->a[j], b = B->b[j], nw = nw0 + j;
             const u32 la = cM.tok_len[a], lb = cM.tok_len[b], ln = la + lb;
-            const u64 at = cur + s_off[warp];
+            const u64 at = cur + s_off[j];
             uint8_t *dst = cM.tok_bytes + at;
             const uint8_t *pa = cM.tok_bytes + cM.tok_off[a], *pb = cM.tok_bytes + cM.tok_off[b];
             for (u32 i = lane; i < ln; i += 32) dst[i] = i < la ? pa[i] : pb[i - la];
@@ -806,13 +813,13 @@ __device__ __forceinline__ void token_bookkeeping(int step0, u32 nw0, const Batc
                 u64 nkey = cM.tok_key[a];
                 if (la < 8) nkey |= cM.tok_key[b] >> (8 * la);
                 cM.tok_off[nw] = (u32)at; cM.tok_len[nw] = ln; cM.tok_key[nw] = nkey;
-                const int step = step0 + (int)warp;
+                const int step = step0 + (int)j;
                 cM.merges_out[2 * step] = (int32_t)a; cM.merges_out[2 * step + 1] = (int32_t)b;
-                cM.merge_cnt_out[step] = B->cnt[warp];
+                cM.merge_cnt_out[step] = B->cnt[j];
             }
             // make sure the winner's block is rescanned so the key gets popped
             if (lane == 1) {
-                const u64 key = B->key[warp], mask = cM.pcap - 1;
+                const u64 key = B->key[j], mask = cM.pcap - 1;
                 u64 s = pair_hash(key) & mask;
                 while (cM.pkey[s] != key) s = (s + 1) & mask;
                 mark_dirty(s);
