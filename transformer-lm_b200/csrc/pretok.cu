@@ -6,69 +6,125 @@
 #include "hashtab.cuh"
 
 // ---------------------------------------------------------------------------------------------
-// flags kernel: one pass over the text.  Per 16-byte chunk a thread turns its bytes into class masks (ASCII
-// through a shared-memory table, non-ASCII characters decoded, validated and looked up in the Unicode class
-// table in shared memory), then evaluates the start rules on 32-bit windows built with its neighbours' masks.
-// Output: 1 bit per byte (bit set = a pretoken starts on that byte).
-// Algorithmic HBM bytes: n read + n/8 written.
+// flags kernel: one pass over the text, a tile of PT_TILE bytes at a time.
+//   staging   a tile and its two 16-byte neighbour chunks are ONE contiguous global range (the arena is padded on both sides):
+//             one elected thread fetches it with a bulk asynchronous copy (cp.async.bulk, completion on an mbarrier) into one of
+//             two shared-memory stages while the CTA works on the other one -- no LDG / STS instructions, no exposed load latency
+//   phase 1   per 16-byte chunk a thread turns its ASCII bytes into one-hot class bytes through a shared-memory table; chunks
+//             with bytes >= 0x80 are queued
+//   phase 2   the queued chunks are patched densely, one thread each (characters decoded, validated and looked up in the Unicode
+//             class table in shared memory).  Almost every warp holds a few non-ASCII bytes (1-2 % of natural text), so doing this
+//             inline made every warp walk the long decode path with one or two active lanes.
+//   phase 3   class bytes -> bit masks, start rules on 32-bit windows built with the neighbours' masks
+// Output: 1 bit per byte (bit set = a pretoken starts on that byte).  Algorithmic HBM bytes: n read + n/8 written.
 // ---------------------------------------------------------------------------------------------
+#define PT_STAGE_BYTES (PT_TILE + 64u)           // [16 B of 0xFF][chunk before][PT_NT chunks][chunk after][16 B of 0xFF]
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src_gmem, u32 bytes, u64 *bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
+    u32 done = 0;
+    while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
 template <bool HAS_SP>
 __global__ void __launch_bounds__(PT_NT) k_pretok_flags(const uint8_t *__restrict__ text, u64 n, u64 n_tiles,
                                                        const u32 *__restrict__ spmask, const u32 *__restrict__ spstart,
                                                        u32 *__restrict__ flags, u64 *__restrict__ err, u64 err_lo, u64 err_hi) {
     __shared__ PretokTables tb;
-    // text tile, byte-addressable: [16 B of 0xFF][chunk before the tile][PT_NT chunks][chunk after][16 B of 0xFF]
-    __shared__ uint4 s_text[PT_NT + 4];
-    __shared__ uint4 s_mask[PT_NT + 2];          // masks of [chunk before][PT_NT chunks][chunk after]
+    __shared__ __align__(128) uint8_t s_stage[2][PT_STAGE_BYTES];
+    __shared__ uint4 s_info[PT_NT + 2];          // class bytes, then masks, of [chunk before][PT_NT chunks][chunk after]
+    __shared__ u32 s_hi[PT_NT + 2];
+    __shared__ u32 s_q[PT_NT + 2];               // chunks with non-ASCII bytes
+    __shared__ u32 s_nq;
+    __shared__ __align__(8) u64 s_bar[2];
     const u32 tid = threadIdx.x;
     pretok_load_tables(&tb);
-    if (tid == 0) { s_text[0] = make_uint4(~0u, ~0u, ~0u, ~0u); s_text[PT_NT + 3] = make_uint4(~0u, ~0u, ~0u, ~0u); }
+    for (u32 i = tid; i < 2 * 32; i += PT_NT) {  // the 16-byte guards of both stages (never overwritten by the copies)
+        const u32 st = i >> 5, k = i & 31u;
+        s_stage[st][k < 16 ? k : PT_STAGE_BYTES - 32 + k] = 0xFF;
+    }
+    if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); s_nq = 0; asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     __syncthreads();
-    const uint8_t *tx = reinterpret_cast<const uint8_t *>(s_text);
-    for (u64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    u32 k = 0;
+    if (tid == 0 && blockIdx.x < n_tiles) bulk_load(&s_stage[0][16], text + (u64)blockIdx.x * PT_TILE - 16, PT_TILE + 32, &s_bar[0]);
+    for (u64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, k++) {
+        const u32 stg = k & 1u;
         const u64 tbeg = tile * PT_TILE;
-        const uint4 *g = reinterpret_cast<const uint4 *>(text + tbeg);
-        s_text[2 + tid] = ld_stream_v4(g + tid);
-        if (tid == 0) s_text[1] = ld_stream_v4(g - 1);
-        if (tid == 1) s_text[PT_NT + 2] = ld_stream_v4(g + PT_NT);
-        __syncthreads();
-        u32 m16 = 0, s16 = 0;
+        // the other stage was released by the barrier that ended the previous iteration
+        if (tid == 0 && tile + gridDim.x < n_tiles) bulk_load(&s_stage[stg ^ 1u][16], text + (tile + gridDim.x) * PT_TILE - 16, PT_TILE + 32, &s_bar[stg ^ 1u]);
+        mbar_wait(&s_bar[stg], (k >> 1) & 1u);
+        const uint8_t *tx = s_stage[stg];
+        // ---- phase 1: ASCII class bytes, queue of the chunks that need decoding ----
         {
-            u32 e; bool cr;
-            uint4 mk = info_to_masks(chunk_info(&tb, tx, 32u + tid * 16u, &e, &cr));
-            if (HAS_SP) {
-                u64 wi = (tbeg >> 5) + (tid >> 1);
-                u32 sh = (tid & 1u) * 16u;
-                m16 = (spmask[wi] >> sh) & 0xFFFFu;
-                s16 = (spstart[wi] >> sh) & 0xFFFFu;
-                if (m16) mk = masks_apply_boundary(mk, m16);
-            }
-            s_mask[tid + 1] = mk;
-            if (e != 0xFFu) {
-                u64 off = tbeg + (u64)tid * PT_CHUNK + e;
-                if (off < n && off >= err_lo && off < err_hi) atomicMin(reinterpret_cast<u64 *>(&err[0]), off);
-            }
+            u32 hi; bool cr;
+            s_info[tid + 1] = chunk_info_ascii(&tb, tx, 32u + tid * 16u, &hi, &cr);
+            s_hi[tid + 1] = hi;
             if (cr) err[1] = 1;
-            if (tid < 2) {                       // halo chunks (validated by the tile that owns them)
-                const u32 idx = tid == 0 ? 0u : PT_NT + 1u;
-                u32 e2; bool cr2;
-                uint4 hk = info_to_masks(chunk_info(&tb, tx, 16u + idx * 16u, &e2, &cr2));
-                if (HAS_SP) {
-                    // halo chunk = last chunk of the previous tile / first chunk of the next one
-                    u32 hm = 0;
-                    if (idx != 0) hm = spmask[(tbeg >> 5) + (PT_NT >> 1)] & 0xFFFFu;
-                    else if (tile > 0) hm = (spmask[(tbeg >> 5) - 1] >> 16) & 0xFFFFu;
-                    if (hm) hk = masks_apply_boundary(hk, hm);
-                }
-                s_mask[idx] = hk;
+            const u32 m = __ballot_sync(0xffffffffu, hi != 0);
+            if (m) {
+                u32 base = 0;
+                if ((tid & 31u) == (u32)(__ffs(m) - 1)) base = atomicAdd(&s_nq, (u32)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+                if (hi) s_q[base + __popc(m & ((1u << (tid & 31u)) - 1u))] = tid + 1;
+            }
+            if (tid >= PT_NT - 2) {              // halo chunks (validated by the tile that owns them)
+                const u32 idx = tid == PT_NT - 2 ? 0u : PT_NT + 1u;
+                u32 h2; bool cr2;
+                s_info[idx] = chunk_info_ascii(&tb, tx, 16u + idx * 16u, &h2, &cr2);
+                s_hi[idx] = h2;
+                if (h2) s_q[atomicAdd(&s_nq, 1u)] = idx;
             }
         }
         __syncthreads();
-        u32 bits = flags_from_masks(s_mask[tid], s_mask[tid + 1], s_mask[tid + 2], tx, 32u + tid * 16u);
-        if (HAS_SP) bits = (bits & ~m16) | s16;
-        u32 hi = __shfl_down_sync(0xffffffffu, bits, 1);
-        if ((tid & 1u) == 0) flags[(tbeg >> 5) + (tid >> 1)] = bits | (hi << 16);
+        // ---- phase 2: non-ASCII characters, one queued chunk per thread ----
+        {
+            const u32 nq = s_nq;
+            for (u32 e = tid; e < nq; e += PT_NT) {
+                const u32 c = s_q[e];
+                const u32 bad = chunk_patch_non_ascii(&tb, tx, 16u + c * 16u, s_hi[c], &s_info[c]);
+                if (bad != 0xFFu && c >= 1 && c <= PT_NT) {
+                    const u64 off = tbeg + (u64)(c - 1) * PT_CHUNK + bad;
+                    if (off < n && off >= err_lo && off < err_hi) atomicMin(reinterpret_cast<u64 *>(&err[0]), off);
+                }
+            }
+        }
         __syncthreads();
+        // ---- phase 3: masks ----
+        u32 m16 = 0, s16 = 0;
+        uint4 mk = info_to_masks(s_info[tid + 1]);
+        uint4 hk = make_uint4(0, 0, 0, 0);
+        const u32 hidx = tid == PT_NT - 2 ? 0u : PT_NT + 1u;
+        if (tid >= PT_NT - 2) hk = info_to_masks(s_info[hidx]);
+        if (HAS_SP) {
+            const u64 wi = (tbeg >> 5) + (tid >> 1);
+            const u32 sh = (tid & 1u) * 16u;
+            m16 = (spmask[wi] >> sh) & 0xFFFFu;
+            s16 = (spstart[wi] >> sh) & 0xFFFFu;
+            if (m16) mk = masks_apply_boundary(mk, m16);
+            if (tid >= PT_NT - 2) {              // halo chunk = last chunk of the previous tile / first chunk of the next one
+                u32 hm = 0;
+                if (hidx != 0) hm = spmask[(tbeg >> 5) + (PT_NT >> 1)] & 0xFFFFu;
+                else if (tile > 0) hm = (spmask[(tbeg >> 5) - 1] >> 16) & 0xFFFFu;
+                if (hm) hk = masks_apply_boundary(hk, hm);
+            }
+        }
+        __syncthreads();                         // every thread has read its class bytes: the array now takes the masks
+        s_info[tid + 1] = mk;
+        if (tid >= PT_NT - 2) s_info[hidx] = hk;
+        if (tid == 0) s_nq = 0;
+        __syncthreads();
+        u32 bits = flags_from_masks(s_info[tid], s_info[tid + 1], s_info[tid + 2], tx, 32u + tid * 16u);
+        if (HAS_SP) bits = (bits & ~m16) | s16;
+        const u32 hi2 = __shfl_down_sync(0xffffffffu, bits, 1);
+        if ((tid & 1u) == 0) flags[(tbeg >> 5) + (tid >> 1)] = bits | (hi2 << 16);
+        __syncthreads();                         // the stage and the mask array are free for the next tile
     }
 }
 

@@ -99,10 +99,9 @@ __device__ __forceinline__ u32 cp_class_smem(const PretokTables *t, u32 cp) {
 __device__ __forceinline__ u32 movemask4(u32 w, u32 k) { return ((((w >> k) & 0x01010101u) * 0x00204081u) >> 21) & 0xFu; }
 __device__ __forceinline__ bool has_byte(u32 w, u32 b) { u32 x = w ^ (b * 0x01010101u); return ((x - 0x01010101u) & ~x & 0x80808080u) != 0; }
 
-// Info bytes of the 16 bytes of the chunk at byte offset `at` of the shared-memory text tile `tx` (byte-addressable;
-// at least 3 readable bytes before and 4 after the chunk).  err_rel: smallest chunk-relative offset (0..15) of an
-// ill-formed sequence that STARTS in this chunk, or 0xFF; has_cr: the chunk contains '\r'.
-__device__ __forceinline__ uint4 chunk_info(const PretokTables *tb, const uint8_t *tx, u32 at, u32 *err_rel, bool *has_cr) {
+// Info bytes of the ASCII bytes of the 16-byte chunk at byte offset `at` of the shared-memory text tile `tx` (bytes >= 0x80 get
+// 0 and are patched by chunk_patch_non_ascii).  *hi: mask of the chunk's bytes >= 0x80; *has_cr: the chunk contains '\r'.
+__device__ __forceinline__ uint4 chunk_info_ascii(const PretokTables *tb, const uint8_t *tx, u32 at, u32 *hi_out, bool *has_cr) {
     const uint4 c = *reinterpret_cast<const uint4 *>(tx + at);
     const u32 w[4] = {c.x, c.y, c.z, c.w};
     u32 iw[4];
@@ -116,45 +115,50 @@ __device__ __forceinline__ uint4 chunk_info(const PretokTables *tb, const uint8_
         hi |= movemask4(x, 7) << (4 * q);
         cr |= has_byte(x, 0x0Du);
     }
+    *hi_out = hi; *has_cr = cr;
+    return make_uint4(iw[0], iw[1], iw[2], iw[3]);
+}
+// The non-ASCII bytes (mask hi) of that chunk: leads are decoded, validated and classified through the Unicode table in shared
+// memory, continuation bytes inherit the class of their character.  `tx` needs at least 3 readable bytes before and 4 after the
+// chunk.  Returns the smallest chunk-relative offset (0..15) of an ill-formed sequence that STARTS in this chunk, or 0xFF.
+__device__ __forceinline__ u32 chunk_patch_non_ascii(const PretokTables *tb, const uint8_t *tx, u32 at, u32 hi, uint4 *info) {
+    u32 iw[4] = {info->x, info->y, info->z, info->w};
     u32 e = 0xFFu;
-    if (hi) {
-        // one iteration per non-ASCII byte group: leads are decoded and validated, continuation bytes inherit
-        int carry_left = 0; u32 carry_cls = 0, expect = 0;
-        if ((tx[at] & 0xC0u) == 0x80u) {                               // first byte continues a character of the previous chunk?
+    int carry_left = 0; u32 carry_cls = 0, expect = 0;
+    if ((tx[at] & 0xC0u) == 0x80u) {                               // first byte continues a character of the previous chunk?
 #pragma unroll
-            for (int d = 1; d <= 3; d++) {
-                const u32 l0 = tx[at - d];
-                if (carry_left == 0 && l0 >= 0xC0u && l0 < 0xF8u) {
-                    u32 cp; bool ok;
-                    int len = utf8_decode_multi(l0, tx[at - d + 1], tx[at - d + 2], tx[at - d + 3], &cp, &ok);
-                    if (ok && len > d) { carry_left = len - d; carry_cls = cp_class_smem(tb, cp); expect = 0; }
-                }
-            }
-        }
-        u32 m = hi;
-        while (m) {
-            const u32 j = __ffs(m) - 1; m &= m - 1;
-            const u32 b = tx[at + j];
-            u32 inf;
-            if (b >= 0xF8u) {                                          // never occurs in UTF-8: padding / boundary
-                inf = INF_B | INF_LEAD; if (e == 0xFFu) e = j; carry_left = 0;
-            } else if (b >= 0xC0u) {
+        for (int d = 1; d <= 3; d++) {
+            const u32 l0 = tx[at - d];
+            if (carry_left == 0 && l0 >= 0xC0u && l0 < 0xF8u) {
                 u32 cp; bool ok;
-                int len = utf8_decode_multi(b, tx[at + j + 1], tx[at + j + 2], tx[at + j + 3], &cp, &ok);
-                carry_cls = ok ? cp_class_smem(tb, cp) : CLS_P;
-                inf = (1u << carry_cls) | INF_LEAD;
-                carry_left = ok ? len - 1 : 0; expect = j + 1;
-                if (!ok && e == 0xFFu) e = j;
-            } else if (carry_left > 0 && j == expect) {                // continuation byte of the character in progress
-                inf = 1u << carry_cls; carry_left--; expect++;
-            } else {                                                   // orphan continuation byte (or tail of an invalid sequence)
-                inf = INF_P; if (e == 0xFFu) e = j; carry_left = 0;
+                int len = utf8_decode_multi(l0, tx[at - d + 1], tx[at - d + 2], tx[at - d + 3], &cp, &ok);
+                if (ok && len > d) { carry_left = len - d; carry_cls = cp_class_smem(tb, cp); expect = 0; }
             }
-            iw[j >> 2] |= inf << ((j & 3u) * 8u);
         }
     }
-    *err_rel = e; *has_cr = cr;
-    return make_uint4(iw[0], iw[1], iw[2], iw[3]);
+    u32 m = hi;
+    while (m) {
+        const u32 j = __ffs(m) - 1; m &= m - 1;
+        const u32 b = tx[at + j];
+        u32 inf;
+        if (b >= 0xF8u) {                                          // never occurs in UTF-8: padding / boundary
+            inf = INF_B | INF_LEAD; if (e == 0xFFu) e = j; carry_left = 0;
+        } else if (b >= 0xC0u) {
+            u32 cp; bool ok;
+            int len = utf8_decode_multi(b, tx[at + j + 1], tx[at + j + 2], tx[at + j + 3], &cp, &ok);
+            carry_cls = ok ? cp_class_smem(tb, cp) : CLS_P;
+            inf = (1u << carry_cls) | INF_LEAD;
+            carry_left = ok ? len - 1 : 0; expect = j + 1;
+            if (!ok && e == 0xFFu) e = j;
+        } else if (carry_left > 0 && j == expect) {                // continuation byte of the character in progress
+            inf = 1u << carry_cls; carry_left--; expect++;
+        } else {                                                   // orphan continuation byte (or tail of an invalid sequence)
+            inf = INF_P; if (e == 0xFFu) e = j; carry_left = 0;
+        }
+        iw[j >> 2] |= inf << ((j & 3u) * 8u);
+    }
+    *info = make_uint4(iw[0], iw[1], iw[2], iw[3]);
+    return e;
 }
 
 // 16 info bytes -> eight 16-bit masks packed as {S|L<<16, N|P<<16, B|LEAD<<16, SP|AP<<16}
