@@ -781,13 +781,15 @@ def run_b200(args):
             from oracle import synth as osynth                   # (host generator of the CPU arms: identical bytes, tests/test_synth.py)
             data = osynth.synth_host("owt", 4322, n_s)
             stok.encode_to_numpy(data, np.uint16)
-            t0 = time.perf_counter()
-            ids = stok.encode_to_numpy(data, np.uint16)
-            dt = time.perf_counter() - t0
+            dt = 1e9
+            for _ in range(3):                                   # best of three warm calls (the first ones may still grow the cache tables)
+                t0 = time.perf_counter()
+                ids = stok.encode_to_numpy(data, np.uint16)
+                dt = min(dt, time.perf_counter() - t0)
             enc_slices.append({"name": name, "text_bytes": n_s, "gpu_e2e_ms": round(dt * 1e3, 3), "gpu_e2e_MBps": round(n_s / 1e6 / dt, 2), "n_ids": int(ids.size),
                                "ids_sha": hashlib.sha256(ids.astype("<i8").tobytes()).hexdigest()[:16],
                                "tokenizer": "vocab %d trained on the first %d MiB of the train corpus" % (SLICE_VOCAB, SLICE_REF_BYTES >> 20),
-                               "cache": "warm pretoken cache (second call)"})
+                               "cache": "warm pretoken cache (best of three calls after a first one)"})
         line["same_slice_encode"] = enc_slices
 
         # ======================= CPU baseline: the CPU arms on those slices, timed in this run (rank 0, N = 1) =======================

@@ -142,14 +142,8 @@ class DeviceCounter:
             expected, self._expected_pairs = self._expected_pairs, None
             if not np.array_equal(expected.cpu().numpy(), merged):
                 raise RuntimeError("pair-count all-reduce does not match the merged word table")
-        sym = [bytes([i]) for i in range(256)]
-        merges = []
-        for k in range(n_done.value):
-            a, b = sym[pairs[k, 0]], sym[pairs[k, 1]]
-            merges.append((a, b))
-            sym.append(a + b)
-            vocab.add_token(a + b)
-        out = (vocab.get_idx_to_token(), merges)
+        from .train import merges_to_python
+        out = merges_to_python(vocab, pairs, n_done.value)
         return out + (stats.as_dict(),) if return_stats else out
 
 

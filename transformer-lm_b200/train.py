@@ -43,6 +43,23 @@ def _read_file(input_path):
     return np.frombuffer(data, dtype=np.uint8), data
 
 
+def merges_to_python(vocab: Vocab, pairs: np.ndarray, n_done: int):
+    """Symbol-id merge list of the device -> (vocab dict, merges list) of the reference (train.py:190-191, 228): tokens are
+    byte strings, `Vocab.add_token` skips a byte string that is already present (vocab.py:28-34)."""
+    sym = [bytes([i]) for i in range(256)]
+    merges = []
+    idx_to_token, present = vocab.idx_to_token, vocab._present     # (Vocab.add_token inlined: tens of thousands of calls)
+    for ia, ib in pairs[:n_done].tolist():
+        a, b = sym[ia], sym[ib]
+        t = a + b
+        merges.append((a, b))
+        sym.append(t)
+        if t not in present:
+            present.add(t)
+            idx_to_token[len(idx_to_token)] = t
+    return vocab.get_idx_to_token(), merges
+
+
 def train_bpe_on_bytes(data, vocab_size: int, special_tokens: List[str] = [], *, ctx=None, return_stats: bool = False,
                        device_ptr: int | None = None, n_bytes: int | None = None):
     """train_bpe on an in-memory byte buffer (bytes / numpy uint8) or, with device_ptr, on text already in HBM."""
@@ -70,14 +87,7 @@ def train_bpe_on_bytes(data, vocab_size: int, special_tokens: List[str] = [], *,
         # SURVEY A-6: two different merges produced the same byte string while the pair still had a positive
         # count.  The reference would pool the two symbols; this has never been observed and is not implemented.
         raise NotImplementedError("two merges produced identical token bytes (SURVEY A-6); not supported")
-    sym = [bytes([i]) for i in range(256)]
-    merges = []
-    for k in range(n_done.value):
-        a, b = sym[pairs[k, 0]], sym[pairs[k, 1]]
-        merges.append((a, b))
-        sym.append(a + b)
-        vocab.add_token(a + b)                                    # dedupes like vocab.py:28-34
-    out = (vocab.get_idx_to_token(), merges)
+    out = (*merges_to_python(vocab, pairs, n_done.value),)
     return out + (stats.as_dict(),) if return_stats else out
 
 
