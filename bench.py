@@ -137,12 +137,14 @@ def measured_peak_gbs():
 
 
 def ncu_traffic(kernel: str, config: dict):
-    """DRAM bytes per launch of `kernel` from the committed ncu capture of this configuration (profiles/r2_traffic.json), or None."""
+    """DRAM bytes (read + written) `kernel` moves per bench step, from the committed ncu capture of this configuration
+    (profiles/r2_traffic.json: bytes of one launch x the launches a step makes), or None."""
     try:
         tj = json.loads((ROOT / "profiles" / "r2_traffic.json").read_text())
+        kernel = kernel.split("<")[0]
         for e in tj["captures"]:
-            if e["kernel"] == kernel and all(e["config"].get(k) == v for k, v in config.items()):
-                return e["dram_bytes_per_launch"], e["source"]
+            if e["kernel"] == kernel and all(e["config"].get(k) == v for k, v in config.items() if k in e["config"]) and e["config"].get("n_gpus") == config.get("n_gpus"):
+                return e["dram_bytes_per_step"], "%s; %d launch(es) per step" % (e["source"], e["launches_per_step"])
     except Exception:
         pass
     return None, None
