@@ -22,10 +22,15 @@
 //   long table:  pretokens of >= 8 bytes.  meta = (offset:40 | len:24) of a representative occurrence,
 //                claimed by CAS; a 64-bit hash is kept beside it as a filter and every hash hit is
 //                confirmed by comparing the bytes (exact).
+//   medium table: pretokens of 8..15 bytes -- a sixth of all occurrences of English-like text and nearly all of those with more
+//                than 7 bytes.  32-byte slots {bytes 0-7, bytes 8-14 | len << 56, count, -}: the 16-byte key IS the token,
+//                claimed and published by one 128-bit CAS, so an occurrence costs one 32-byte sector like a short one (through
+//                the long table it cost the slot, the bytes of the stored representative and a second look at the text).
 // Counts are 64-bit atomics.  Offsets with bit 39 set address the persistent pool (imported /
 // re-homed words), others the text arena of the current shard.
 // =============================================================================================
 #define SHORT_MAX 7u
+#define MED_MAX 15u
 #define META_EMPTY 0ull                          // a real meta word has len >= 8, never 0: empty tables are all-zero memory
 #define META_LEN_BITS 24
 #define META_LEN_MASK ((1ull << META_LEN_BITS) - 1)
@@ -34,26 +39,31 @@
 
 struct CountTables {
     u64 *stab; u64 scap;                         // short: slots of {key, count}            (16 B)
+    u64 *mtab; u64 mcap;                         // medium: slots of {k0, k1, count, pad}    (32 B, one sector)
     u64 *ltab; u64 lcap;                         // long:  slots of {meta, hash, count, pad} (32 B, one sector)
     // slot of the k-th unique short / long word (k = value of counters[0] / [1] when it was claimed): everything that walks the
     // words (re-homing, export, word list, table growth) walks these lists instead of scanning the tables' capacity, which is
     // sized for the worst case (every pretoken of a batch new) and mostly empty
-    u32 *slist, *llist;
+    u32 *slist, *mlist, *llist;
     const uint8_t *text;                         // payload of the current text arena
     const uint8_t *pool;                         // persistent bytes of long words
     u64 *counters;                               // [0]=n_short [1]=n_long [2]=long_bytes [3]=overflow [4]=n_pretokens [5]=too_long
-                                                 // [6]=an owned pretoken ran past the trusted part of the right halo
+                                                 // [6]=an owned pretoken ran past the trusted part of the right halo [7]=n_medium
 };
+struct WordCounts { u64 n_short, n_medium, n_long; };
 
 #define SKEY(t, s) ((t).stab[2 * (s)])
 #define SCNT(t, s) ((t).stab[2 * (s) + 1])
+#define MK0(t, s) ((t).mtab[4 * (s)])
+#define MK1(t, s) ((t).mtab[4 * (s) + 1])
+#define MCNT(t, s) ((t).mtab[4 * (s) + 2])
 #define LMETA(t, s) ((t).ltab[4 * (s)])
 #define LHASH(t, s) ((t).ltab[4 * (s) + 1])
 #define LCNT(t, s) ((t).ltab[4 * (s) + 2])
 
 struct CountState {
-    DevBuf stab, ltab, slist, llist, pool, counters;
-    u64 scap = 0, lcap = 0, pool_used = 0;
+    DevBuf stab, mtab, ltab, slist, mlist, llist, pool, counters;
+    u64 scap = 0, mcap = 0, lcap = 0, pool_used = 0;
     bool active = false;
     u64 n_pretokens = 0;
     u64 n_rehomed = 0;                           // long words [0, n_rehomed) of the list have their bytes in the pool
@@ -75,6 +85,32 @@ __device__ __forceinline__ void short_add(const CountTables &t, u64 key, u64 del
             else k = old;
         }
         if (k == key) { atomicAdd(&SCNT(t, s), delta); return; }
+        s = (s + 1) & mask;
+    }
+    t.counters[3] = 1;
+}
+
+// 128-bit compare-and-swap on a 16-byte aligned address: returns the old value in (lo, hi)
+__device__ __forceinline__ void cas128(u64 *addr, u64 cmp_lo, u64 cmp_hi, u64 new_lo, u64 new_hi, u64 &lo, u64 &hi) {
+    asm volatile("{\n .reg .b128 c, n, d;\n mov.b128 c, {%3, %4};\n mov.b128 n, {%5, %6};\n atom.global.cas.b128 d, [%2], c, n;\n mov.b128 {%0, %1}, d;\n}"
+                 : "=l"(lo), "=l"(hi) : "l"(addr), "l"(cmp_lo), "l"(cmp_hi), "l"(new_lo), "l"(new_hi) : "memory");
+}
+// key of a pretoken of 8..15 bytes: k0 = bytes 0-7, k1 = bytes 8-14 (little-endian) | len << 56
+__device__ __forceinline__ void medium_key(const uint8_t *p, u32 len, u64 &k0, u64 &k1) {
+    k0 = load8_unaligned(p);
+    k1 = (len > 8 ? load8_unaligned(p + 8) & low_bytes_mask(len - 8) : 0ull) | ((u64)len << 56);
+}
+__device__ __forceinline__ void medium_add(const CountTables &t, u64 k0, u64 k1, u64 delta) {
+    u64 mask = t.mcap - 1;
+    u64 s = mix64(k0 ^ (k1 * 0x9E3779B97F4A7C15ull)) & mask;
+    for (u64 probes = 0; probes < t.mcap; probes++) {
+        const ulonglong2 kv = *reinterpret_cast<const ulonglong2 *>(&MK0(t, s));
+        u64 a = kv.x, b = kv.y;
+        if (a == 0 && b == 0) {                  // (k1 carries the length: a real key is never all zero)
+            cas128(&MK0(t, s), 0, 0, k0, k1, a, b);
+            if (a == 0 && b == 0) { t.mlist[atomicAdd(&t.counters[7], 1ull)] = (u32)s; a = k0; b = k1; }
+        }
+        if (a == k0 && b == k1) { atomicAdd(&MCNT(t, s), delta); return; }
         s = (s + 1) & mask;
     }
     t.counters[3] = 1;
@@ -140,24 +176,28 @@ __device__ __forceinline__ u32 warp_queue_slot(u32 *counter, bool want) {
     base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
     return base + __popc(m & ((1u << lane_id()) - 1u));
 }
+// queue entry (16 bytes): short pretoken that missed the shared table {key, 0}; medium {k0, k1} (k1 != 0: it carries the length);
+// long {offset from base | len << 32, ~0}
+#define CNT_Q_LONG 0xFFFFFFFFFFFFFFFFull
 __global__ void __launch_bounds__(CNT_NT) k_count_pretokens(CountTables t, const u32 *__restrict__ offs, u64 n_items, u64 base,
                                                            u64 own_begin, u64 own_end, u64 trust_end) {
     extern __shared__ __align__(16) unsigned char cnt_smem[];
     u64 *s_key = reinterpret_cast<u64 *>(cnt_smem);                       // shared-memory table: keys ...
-    u64 *s_sq = s_key + CNT_SMEM_SLOTS;                                   // short pretokens that did not fit the shared table: their keys
-    uint2 *s_lq = reinterpret_cast<uint2 *>(s_sq + CNT_TILE);             // long pretokens: (offset from base, length)
-    u32 *s_cnt = reinterpret_cast<u32 *>(s_lq + CNT_TILE);                // ... and counts
-    __shared__ u32 s_nq[2];
-    __shared__ u64 s_tile;
+    ulonglong2 *s_q = reinterpret_cast<ulonglong2 *>(s_key + CNT_SMEM_SLOTS);   // what goes to the HBM tables
+    u32 *s_cnt = reinterpret_cast<u32 *>(s_q + CNT_TILE);                 // ... and counts
+    __shared__ u32 s_nq[2];                      // queue length, alternating between tiles (the other one is cleared meanwhile)
+    __shared__ u64 s_tile[2];
     for (u32 i = threadIdx.x; i < CNT_SMEM_SLOTS; i += CNT_NT) { s_key[i] = 0; s_cnt[i] = 0; }
     if (threadIdx.x < 2) s_nq[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_tile[0] = atomicAdd(&t.counters[16], 1ull);
+    __syncthreads();
     u64 n_tok = 0;
-    for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_tile = atomicAdd(&t.counters[16], 1ull);
-        __syncthreads();
-        const u64 tile_lo = s_tile * CNT_TILE;
+    for (u32 it = 0;; it++) {
+        const u32 par = it & 1u;
+        const u64 tile_lo = s_tile[par] * CNT_TILE;
         if (tile_lo >= n_items) break;
+        // the ticket of the next tile is fetched while this one is worked on (two CTA barriers per tile, not four)
+        if (threadIdx.x == 0) { s_tile[par ^ 1u] = atomicAdd(&t.counters[16], 1ull); s_nq[par ^ 1u] = 0; }
         // ---- phase A ----
         u32 a[CNT_ITEMS], b[CNT_ITEMS];
         u64 lo[CNT_ITEMS], hi[CNT_ITEMS];
@@ -179,38 +219,44 @@ __global__ void __launch_bounds__(CNT_NT) k_count_pretokens(CountTables t, const
             const u64 pos = base + a[k];
             const u32 len = b[k] - a[k];
             const bool mine = has[k] && pos >= own_begin && pos < own_end;
-            bool to_sq = false, to_lq = false;
-            u64 key = 0;
+            bool to_q = false;
+            ulonglong2 ent = make_ulonglong2(0, 0);
             if (mine) {
                 if (base + b[k] > trust_end) t.counters[6] = 1;
                 n_tok++;
+                const u32 sh = (u32)(reinterpret_cast<uintptr_t>(t.text + pos) & 7u) * 8u;
+                const u64 first8 = sh ? (lo[k] >> sh) | (hi[k] << (64u - sh)) : lo[k];
                 if (len <= SHORT_MAX) {
-                    const u32 sh = (u32)(reinterpret_cast<uintptr_t>(t.text + pos) & 7u) * 8u;
-                    const u64 first8 = sh ? (lo[k] >> sh) | (hi[k] << (64u - sh)) : lo[k];
-                    key = (first8 & low_bytes_mask(len)) | ((u64)len << 56);       // = short_key(p, len)
+                    const u64 key = (first8 & low_bytes_mask(len)) | ((u64)len << 56);       // = short_key(p, len)
                     u32 slot = (((u32)key ^ (u32)(key >> 32)) * 0x9E3779B1u) >> (32 - CNT_SMEM_LG);   // cheap hash for the shared-memory table
-                    to_sq = true;
+                    to_q = true; ent.x = key;
                     for (u32 pr = 0; pr < CNT_SMEM_PROBES; pr++) {
                         u64 kk = s_key[slot];
                         if (kk == 0) { const u64 old = atomicCAS(&s_key[slot], 0ull, key); kk = old ? old : key; }
-                        if (kk == key) { atomicAdd(&s_cnt[slot], 1u); to_sq = false; break; }
+                        if (kk == key) { atomicAdd(&s_cnt[slot], 1u); to_q = false; break; }
                         slot = (slot + 1) & (CNT_SMEM_SLOTS - 1);
                     }
-                } else if (len <= MAX_TOKEN_LEN) to_lq = true;
+                } else if (len <= MED_MAX) {
+                    // bytes 8..14: in the second word already loaded, or (unaligned start) partly in the third one
+                    u64 next8 = sh ? (hi[k] >> sh) : hi[k];
+                    if (sh && len > 16u - sh / 8u) next8 |= reinterpret_cast<const u64 *>(reinterpret_cast<uintptr_t>(t.text + pos) & ~(uintptr_t)7)[2] << (64u - sh);
+                    to_q = true; ent.x = first8; ent.y = (len > 8 ? next8 & low_bytes_mask(len - 8) : 0ull) | ((u64)len << 56);
+                } else if (len <= MAX_TOKEN_LEN) { to_q = true; ent.x = (u64)a[k] | ((u64)len << 32); ent.y = CNT_Q_LONG; }
                 else t.counters[5] = 1;
             }
-            const u32 qs = warp_queue_slot(&s_nq[0], to_sq);
-            if (to_sq) s_sq[qs] = key;
-            const u32 ql = warp_queue_slot(&s_nq[1], to_lq);
-            if (to_lq) s_lq[ql] = make_uint2(a[k], len);
+            const u32 qs = warp_queue_slot(&s_nq[par], to_q);
+            if (to_q) s_q[qs] = ent;
         }
         __syncthreads();
         // ---- phase B ----
-        const u32 nq = s_nq[0], nl = s_nq[1];
-        for (u32 e = threadIdx.x; e < nq; e += CNT_NT) short_add(t, s_sq[e], 1);
-        for (u32 e = threadIdx.x; e < nl; e += CNT_NT) { const uint2 it = s_lq[e]; long_add(t, t.text + base + it.x, it.y, base + it.x, 1); }
+        const u32 nq = s_nq[par];
+        for (u32 e = threadIdx.x; e < nq; e += CNT_NT) {
+            const ulonglong2 ent = s_q[e];
+            if (ent.y == 0) short_add(t, ent.x, 1);
+            else if (ent.y != CNT_Q_LONG) medium_add(t, ent.x, ent.y, 1);
+            else { const u64 off = base + (u32)ent.x; long_add(t, t.text + off, (u32)(ent.x >> 32), off, 1); }
+        }
         __syncthreads();
-        if (threadIdx.x < 2) s_nq[threadIdx.x] = 0;
     }
     // one atomic per warp for the occurrence counter
     for (int d = 16; d; d >>= 1) n_tok += __shfl_down_sync(0xffffffffu, n_tok, d);
@@ -256,6 +302,13 @@ __global__ void __launch_bounds__(256) k_rehash_long(const u64 *__restrict__ ota
     }
 }
 
+__global__ void __launch_bounds__(256) k_rehash_medium(const u64 *__restrict__ otab, const u32 *__restrict__ olist, u64 n_old, CountTables t) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_old; i += (u64)gridDim.x * blockDim.x) {
+        const u64 o = olist[i];
+        medium_add(t, otab[4 * o], otab[4 * o + 1], otab[4 * o + 2]);   // (claims a slot and appends it to the new list: counters[7] was reset)
+    }
+}
+
 // ---- re-homing: copy representatives that still point into the text arena to the pool ---------
 // (only the long words claimed since the last re-homing can point into the arena: list positions [first, n_long))
 __global__ void __launch_bounds__(256) k_rehome_sizes(CountTables t, u64 first, u64 n_long, u64 *__restrict__ need /* [0] */) {
@@ -292,33 +345,54 @@ __global__ void __launch_bounds__(256) k_import_words(CountTables t, const uint8
             for (u32 k = 0; k < (u32)len; k++) key |= (u64)p[k] << (8 * k);
             key |= len << 56;
             short_add(t, key, (u64)counts[i]);
+        } else if (len <= MED_MAX) {
+            u64 k0 = 0, k1 = len << 56;
+            for (u32 k = 0; k < 8; k++) k0 |= (u64)p[k] << (8 * k);
+            for (u32 k = 8; k < (u32)len; k++) k1 |= (u64)p[k] << (8 * (k - 8));
+            medium_add(t, k0, k1, (u64)counts[i]);
         } else if (len <= MAX_TOKEN_LEN) {
             long_add(t, p, (u32)len, (pool_base + o) | META_POOL_BIT, (u64)counts[i]);
         } else t.counters[5] = 1;
     }
 }
 
-// ---- export: (bytes, offs, counts) of every word; word w < n_short is the w-th short word, the others the long ones ----
-__global__ void __launch_bounds__(256) k_export_lens(CountTables t, u64 n_short, u64 n_words, u32 *__restrict__ lens) {
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (u64)gridDim.x * blockDim.x)
-        lens[i] = i < n_short ? (u32)(SKEY(t, t.slist[i]) >> 56) : (u32)(LMETA(t, t.llist[i - n_short]) & META_LEN_MASK);
+// ---- the k-th unique word: short words first, then medium, then long (list order) -------------------------------------
+struct WordRef { u32 len; u64 cnt; const uint8_t *src; uint8_t tmp[16]; };
+__device__ __forceinline__ void word_at(const CountTables &t, const WordCounts &wc, u64 i, WordRef &w) {
+    if (i < wc.n_short) {
+        const u64 sl = t.slist[i], k = SKEY(t, sl);
+        w.len = (u32)(k >> 56); w.cnt = SCNT(t, sl);
+        for (u32 j = 0; j < 8; j++) w.tmp[j] = (uint8_t)(k >> (8 * j));
+        w.src = w.tmp;
+    } else if (i < wc.n_short + wc.n_medium) {
+        const u64 sl = t.mlist[i - wc.n_short], k0 = MK0(t, sl), k1 = MK1(t, sl);
+        w.len = (u32)(k1 >> 56); w.cnt = MCNT(t, sl);
+        for (u32 j = 0; j < 8; j++) { w.tmp[j] = (uint8_t)(k0 >> (8 * j)); w.tmp[8 + j] = (uint8_t)(k1 >> (8 * j)); }
+        w.src = w.tmp;
+    } else {
+        const u64 sl = t.llist[i - wc.n_short - wc.n_medium], m = LMETA(t, sl);
+        w.len = (u32)(m & META_LEN_MASK); w.cnt = LCNT(t, sl); w.src = rep_ptr(t, m);
+    }
 }
-__global__ void __launch_bounds__(256) k_export_write(CountTables t, u64 n_short, u64 n_words, const u32 *__restrict__ lens, const u64 *__restrict__ byte_off,
+__device__ __forceinline__ u32 word_len_at(const CountTables &t, const WordCounts &wc, u64 i) {
+    if (i < wc.n_short) return (u32)(SKEY(t, t.slist[i]) >> 56);
+    if (i < wc.n_short + wc.n_medium) return (u32)(MK1(t, t.mlist[i - wc.n_short]) >> 56);
+    return (u32)(LMETA(t, t.llist[i - wc.n_short - wc.n_medium]) & META_LEN_MASK);
+}
+
+// ---- export: (bytes, offs, counts) of every word ----------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_export_lens(CountTables t, WordCounts wc, u64 n_words, u32 *__restrict__ lens) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (u64)gridDim.x * blockDim.x) lens[i] = word_len_at(t, wc, i);
+}
+__global__ void __launch_bounds__(256) k_export_write(CountTables t, WordCounts wc, u64 n_words, const u64 *__restrict__ byte_off,
                                                      uint8_t *__restrict__ blob, u64 *__restrict__ offs, i64 *__restrict__ counts) {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (u64)gridDim.x * blockDim.x) {
-        const u32 l = lens[i];
+        WordRef w;
+        word_at(t, wc, i, w);
         const u64 o = byte_off[i];
         offs[i] = o;
-        if (i < n_short) {
-            const u64 sl = t.slist[i], k = SKEY(t, sl);
-            for (u32 j = 0; j < l; j++) blob[o + j] = (uint8_t)(k >> (8 * j));
-            counts[i] = (i64)SCNT(t, sl);
-        } else {
-            const u64 sl = t.llist[i - n_short];
-            const uint8_t *src = rep_ptr(t, LMETA(t, sl));
-            for (u32 j = 0; j < l; j++) blob[o + j] = src[j];
-            counts[i] = (i64)LCNT(t, sl);
-        }
+        for (u32 j = 0; j < w.len; j++) blob[o + j] = w.src[j];
+        counts[i] = (i64)w.cnt;
     }
 }
 
@@ -340,19 +414,13 @@ __device__ __forceinline__ bool equals_special(const uint8_t *p, u32 len, const 
 
 // Pretokens equal to a special token are dropped (train.py:25).  Words of one byte carry no pair and are
 // skipped: they can never be touched by the merge loop.
-__global__ void __launch_bounds__(256) k_build_words(CountTables t, u64 n_short, u64 n_unique, Words W, const uint8_t *__restrict__ sp_blob,
+__global__ void __launch_bounds__(256) k_build_words(CountTables t, WordCounts wc, Words W, const uint8_t *__restrict__ sp_blob,
                                                     const u32 *__restrict__ sp_offs, int n_sp) {
+    const u64 n_unique = wc.n_short + wc.n_medium + wc.n_long;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_unique; i += (u64)gridDim.x * blockDim.x) {
-        u32 l = 0; const uint8_t *src = nullptr; uint8_t tmp[8]; u64 c = 0;
-        if (i < n_short) {
-            const u64 sl = t.slist[i], k = SKEY(t, sl);
-            l = (u32)(k >> 56);
-            for (u32 j = 0; j < l; j++) tmp[j] = (uint8_t)(k >> (8 * j));
-            src = tmp; c = SCNT(t, sl);
-        } else {
-            const u64 sl = t.llist[i - n_short], m = LMETA(t, sl);
-            l = (u32)(m & META_LEN_MASK); src = rep_ptr(t, m); c = LCNT(t, sl);
-        }
+        WordRef wr;
+        word_at(t, wc, i, wr);
+        const u32 l = wr.len; const uint8_t *src = wr.src; const u64 c = wr.cnt;
         if (l < 2 || c == 0) continue;
         if (n_sp && equals_special(src, l, sp_blob, sp_offs, n_sp)) continue;
         // word index and symbol space: one atomic per group of threads that arrive here together (12 M words would
@@ -377,19 +445,13 @@ __global__ void __launch_bounds__(256) k_build_words(CountTables t, u64 n_short,
 
 // The dense byte-pair table straight from the count tables (what k_build_words + k_init_pair_counts compute, without
 // materialising the words): the per-rank table of the multi-GPU linearity check.
-__global__ void __launch_bounds__(256) k_dense_pairs(CountTables t, u64 n_short, u64 n_unique, const uint8_t *__restrict__ sp_blob, const u32 *__restrict__ sp_offs,
+__global__ void __launch_bounds__(256) k_dense_pairs(CountTables t, WordCounts wc, const uint8_t *__restrict__ sp_blob, const u32 *__restrict__ sp_offs,
                                                     int n_sp, u64 *__restrict__ dense /* 65536 */) {
+    const u64 n_unique = wc.n_short + wc.n_medium + wc.n_long;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_unique; i += (u64)gridDim.x * blockDim.x) {
-        u32 l = 0; const uint8_t *src = nullptr; uint8_t tmp[8]; u64 c = 0;
-        if (i < n_short) {
-            const u64 sl = t.slist[i], k = SKEY(t, sl);
-            l = (u32)(k >> 56);
-            for (u32 j = 0; j < l; j++) tmp[j] = (uint8_t)(k >> (8 * j));
-            src = tmp; c = SCNT(t, sl);
-        } else {
-            const u64 sl = t.llist[i - n_short], m = LMETA(t, sl);
-            l = (u32)(m & META_LEN_MASK); src = rep_ptr(t, m); c = LCNT(t, sl);
-        }
+        WordRef wr;
+        word_at(t, wc, i, wr);
+        const u32 l = wr.len; const uint8_t *src = wr.src; const u64 c = wr.cnt;
         if (l < 2 || c == 0) continue;
         if (n_sp && equals_special(src, l, sp_blob, sp_offs, n_sp)) continue;
         u32 prev = src[0];
@@ -456,8 +518,9 @@ static CountTables count_tables(bpe_ctx *ctx) {
     CountState *cs = ctx->count;
     CountTables t;
     t.stab = (u64 *)cs->stab.p; t.scap = cs->scap;
+    t.mtab = (u64 *)cs->mtab.p; t.mcap = cs->mcap;
     t.ltab = (u64 *)cs->ltab.p; t.lcap = cs->lcap;
-    t.slist = (u32 *)cs->slist.p; t.llist = (u32 *)cs->llist.p;
+    t.slist = (u32 *)cs->slist.p; t.mlist = (u32 *)cs->mlist.p; t.llist = (u32 *)cs->llist.p;
     t.text = ctx->text.p ? (const uint8_t *)ctx->text.p + BPE_PAD : nullptr;
     t.pool = (const uint8_t *)cs->pool.p;
     t.counters = (u64 *)cs->counters.p;
@@ -467,20 +530,21 @@ static CountTables count_tables(bpe_ctx *ctx) {
 void count_state_free(bpe_ctx *ctx) {
     if (!ctx->count) return;
     CountState *cs = ctx->count;
-    for (DevBuf *b : {&cs->stab, &cs->ltab, &cs->slist, &cs->llist, &cs->pool, &cs->counters}) bpe_buf_free(ctx, *b);
+    for (DevBuf *b : {&cs->stab, &cs->mtab, &cs->ltab, &cs->slist, &cs->mlist, &cs->llist, &cs->pool, &cs->counters}) bpe_buf_free(ctx, *b);
     delete cs;
     ctx->count = nullptr;
 }
 
 static int alloc_exact(bpe_ctx *ctx, DevBuf &b, size_t bytes) { return bpe_buf_alloc(ctx, b, bytes ? bytes : 256); }
 
-static int count_tables_alloc(bpe_ctx *ctx, u64 scap, u64 lcap) {
+static int count_tables_alloc(bpe_ctx *ctx, u64 scap, u64 mcap, u64 lcap) {
     CountState *cs = ctx->count;
-    BPE_TRY(alloc_exact(ctx, cs->stab, scap * 16)); BPE_TRY(alloc_exact(ctx, cs->ltab, lcap * 32));
-    BPE_TRY(alloc_exact(ctx, cs->slist, scap * 4)); BPE_TRY(alloc_exact(ctx, cs->llist, lcap * 4));   // (written before read: no clearing)
+    BPE_TRY(alloc_exact(ctx, cs->stab, scap * 16)); BPE_TRY(alloc_exact(ctx, cs->mtab, mcap * 32)); BPE_TRY(alloc_exact(ctx, cs->ltab, lcap * 32));
+    BPE_TRY(alloc_exact(ctx, cs->slist, scap * 4)); BPE_TRY(alloc_exact(ctx, cs->mlist, mcap * 4)); BPE_TRY(alloc_exact(ctx, cs->llist, lcap * 4));   // (written before read: no clearing)
     cudaStream_t st = ctx->stream;
-    CUDA_TRY(ctx, cudaMemsetAsync(cs->stab.p, 0, scap * 16, st)); CUDA_TRY(ctx, cudaMemsetAsync(cs->ltab.p, 0, lcap * 32, st));
-    cs->scap = scap; cs->lcap = lcap;
+    CUDA_TRY(ctx, cudaMemsetAsync(cs->stab.p, 0, scap * 16, st)); CUDA_TRY(ctx, cudaMemsetAsync(cs->mtab.p, 0, mcap * 32, st));
+    CUDA_TRY(ctx, cudaMemsetAsync(cs->ltab.p, 0, lcap * 32, st));
+    cs->scap = scap; cs->mcap = mcap; cs->lcap = lcap;
     return BPE_OK;
 }
 
@@ -491,7 +555,7 @@ BPE_API int bpe_count_begin(bpe_ctx *ctx) {
     CountState *cs = ctx->count;
     BPE_TRY(bpe_buf_reserve(ctx, cs->counters, 64 * sizeof(u64)));
     CUDA_TRY(ctx, cudaMemsetAsync(cs->counters.p, 0, 64 * sizeof(u64), ctx->stream));
-    BPE_TRY(count_tables_alloc(ctx, 1 << 16, 1 << 14));
+    BPE_TRY(count_tables_alloc(ctx, 1 << 16, 1 << 14, 1 << 14));
     cs->pool_used = 0; cs->active = true; cs->n_pretokens = 0; cs->n_rehomed = 0;
     return BPE_OK;
 }
@@ -504,32 +568,33 @@ static int read_counters(bpe_ctx *ctx, u64 *out, int k) {
     return BPE_OK;
 }
 
-// Make sure the tables can absorb `new_short` / `new_long` more unique words without exceeding 7/8 load.
-static int count_ensure_capacity(bpe_ctx *ctx, u64 n_short, u64 n_long, u64 new_short, u64 new_long) {
+// Make sure the tables can absorb `new_short` / `new_long` more unique words (of <= 7 / >= 8 bytes) without exceeding 7/8 load.
+// c = the counters as read by read_counters(ctx, c, 8).
+static int count_ensure_capacity(bpe_ctx *ctx, const u64 *c, u64 new_short, u64 new_long) {
     CountState *cs = ctx->count;
+    const u64 n_short = c[0], n_long = c[1], n_medium = c[7];
     u64 need_s = next_pow2(std::max<u64>(1 << 16, (n_short + new_short) * 8 / 7 + 64));
-    u64 need_l = next_pow2(std::max<u64>(1 << 14, (n_long + new_long) * 8 / 7 + 64));
-    if (need_s <= cs->scap && need_l <= cs->lcap) return BPE_OK;
-    need_s = std::max(need_s, cs->scap); need_l = std::max(need_l, cs->lcap);
-    // grow: move old tables aside, allocate, re-insert the n_short + n_long words of the old lists
+    u64 need_m = next_pow2(std::max<u64>(1 << 14, (n_medium + new_long) * 8 / 7 + 64));
+    // pretokens of >= 16 bytes: at most bytes / 16 of them in a batch, i.e. half of the bound for >= 8 bytes
+    u64 need_l = next_pow2(std::max<u64>(1 << 14, (n_long + (new_long + 1) / 2) * 8 / 7 + 64));
+    if (need_s <= cs->scap && need_m <= cs->mcap && need_l <= cs->lcap) return BPE_OK;
+    need_s = std::max(need_s, cs->scap); need_m = std::max(need_m, cs->mcap); need_l = std::max(need_l, cs->lcap);
+    // grow: move old tables aside, allocate, re-insert the words of the old lists
     CountState old_view = *cs;                   // shallow copy of the DevBufs
-    cs->stab = DevBuf(); cs->ltab = DevBuf(); cs->slist = DevBuf(); cs->llist = DevBuf();
-    int rc = count_tables_alloc(ctx, need_s, need_l);
+    cs->stab = DevBuf(); cs->mtab = DevBuf(); cs->ltab = DevBuf(); cs->slist = DevBuf(); cs->mlist = DevBuf(); cs->llist = DevBuf();
+    int rc = count_tables_alloc(ctx, need_s, need_m, need_l);
     if (rc != BPE_OK) return rc;
-    // the short rehash re-counts its uniques through short_add: reset [0]; [1],[2] (long) are untouched
+    // the short and medium rehashes re-count their uniques through short_add / medium_add: reset [0] and [7]; [1],[2] (long) are untouched
     CUDA_TRY(ctx, cudaMemsetAsync(cs->counters.p, 0, sizeof(u64), ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync((u64 *)cs->counters.p + 7, 0, sizeof(u64), ctx->stream));
     CountTables t = count_tables(ctx);
-    if (n_short) {
-        unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (n_short + 255) / 256);
-        KLAUNCH(k_rehash_short, grid, 256, 0, ctx->stream, (const u64 *)old_view.stab.p, (const u32 *)old_view.slist.p, n_short, t);
-    }
-    if (n_long) {
-        unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (n_long + 255) / 256);
-        KLAUNCH(k_rehash_long, grid, 256, 0, ctx->stream, (const u64 *)old_view.ltab.p, (const u32 *)old_view.llist.p, n_long, t);
-    }
+    auto grid_for = [&](u64 n) { return (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (n + 255) / 256); };
+    if (n_short) KLAUNCH(k_rehash_short, grid_for(n_short), 256, 0, ctx->stream, (const u64 *)old_view.stab.p, (const u32 *)old_view.slist.p, n_short, t);
+    if (n_medium) KLAUNCH(k_rehash_medium, grid_for(n_medium), 256, 0, ctx->stream, (const u64 *)old_view.mtab.p, (const u32 *)old_view.mlist.p, n_medium, t);
+    if (n_long) KLAUNCH(k_rehash_long, grid_for(n_long), 256, 0, ctx->stream, (const u64 *)old_view.ltab.p, (const u32 *)old_view.llist.p, n_long, t);
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    for (DevBuf *b : {&old_view.stab, &old_view.ltab, &old_view.slist, &old_view.llist}) bpe_buf_free(ctx, *b);
+    for (DevBuf *b : {&old_view.stab, &old_view.mtab, &old_view.ltab, &old_view.slist, &old_view.mlist, &old_view.llist}) bpe_buf_free(ctx, *b);
     return BPE_OK;
 }
 
@@ -565,7 +630,7 @@ static int count_current_text(bpe_ctx *ctx, u64 n, u64 own_begin, u64 own_end, u
         u64 b_lo = w_lo + bi * words_per_batch, b_hi = std::min(w_hi, b_lo + words_per_batch);
         u64 bytes = (b_hi - b_lo) * 32, bw = b_hi - b_lo;
         static const u64 bound_div = getenv("BPE_COUNT_BOUND_DIV") ? std::max(1, atoi(getenv("BPE_COUNT_BOUND_DIV"))) : 1;   // EXPERIMENT ONLY (unsafe)
-        BPE_TRY(count_ensure_capacity(ctx, c[0], c[1], bound[bi] / bound_div, std::min(bound[bi], bytes / (SHORT_MAX + 1) + 1) / bound_div));
+        BPE_TRY(count_ensure_capacity(ctx, c, bound[bi] / bound_div, std::min(bound[bi], bytes / (SHORT_MAX + 1) + 1) / bound_div));
         // ordinals of the batch's pretokens -> explicit offsets
         size_t cnt_b = round_up((bw + 1) * 4, 256), pre_b = round_up((bw + 2) * 8, 256), tmp_b = round_up(scan_tmp_elems_host(bw) * 8, 256);
         size_t off_b = round_up((bound[bi] + 2) * 4, 256);
@@ -670,11 +735,12 @@ BPE_API int bpe_count_add_shard_dev(bpe_ctx *ctx, const uint8_t *text_dev, uint6
 }
 
 // lens[] and the byte offsets of the export live in tmp1 between export_size and export (n_words entries, not table capacity)
-static int count_export_scan(bpe_ctx *ctx, u64 *n_short_out, u64 *n_words_out, u64 *blob_bytes_out) {
+static int count_export_scan(bpe_ctx *ctx, WordCounts *wc_out, u64 *n_words_out, u64 *blob_bytes_out) {
     cudaStream_t st = ctx->stream;
-    u64 c[2];
-    BPE_TRY(read_counters(ctx, c, 2));
-    const u64 n_short = c[0], n_words = c[0] + c[1];
+    u64 c[8];
+    BPE_TRY(read_counters(ctx, c, 8));
+    const WordCounts wc{c[0], c[7], c[1]};
+    const u64 n_words = c[0] + c[7] + c[1];
     CountTables t = count_tables(ctx);
     size_t lens_b = round_up((n_words + 1) * 4, 256), boff_b = round_up((n_words + 2) * 8, 256);
     size_t tmp_b = scan_tmp_elems_host(n_words + 1) * 8;
@@ -686,21 +752,21 @@ static int count_export_scan(bpe_ctx *ctx, u64 *n_short_out, u64 *n_words_out, u
     host[0] = 0;
     if (n_words) {
         unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (n_words + 255) / 256);
-        KLAUNCH(k_export_lens, grid, 256, 0, st, t, n_short, n_words, lens);
+        KLAUNCH(k_export_lens, grid, 256, 0, st, t, wc, n_words, lens);
         launch_scan_u32(lens, n_words, boff, tmp, st);
         CUDA_TRY(ctx, cudaGetLastError());
         CUDA_TRY(ctx, cudaMemcpyAsync(host, boff + n_words, 8, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(ctx, cudaStreamSynchronize(st));
     }
-    *n_short_out = n_short; *n_words_out = n_words; *blob_bytes_out = host[0];
+    *wc_out = wc; *n_words_out = n_words; *blob_bytes_out = host[0];
     return BPE_OK;
 }
 
 BPE_API int bpe_count_export_size(bpe_ctx *ctx, uint64_t *n_words, uint64_t *blob_bytes) {
     if (!ctx || !ctx->count || !n_words || !blob_bytes) return BPE_ERR_ARG;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    u64 ns, nw, nb;
-    BPE_TRY(count_export_scan(ctx, &ns, &nw, &nb));
+    WordCounts wc; u64 nw, nb;
+    BPE_TRY(count_export_scan(ctx, &wc, &nw, &nb));
     *n_words = nw; *blob_bytes = nb;
     return BPE_OK;
 }
@@ -708,13 +774,12 @@ BPE_API int bpe_count_export_size(bpe_ctx *ctx, uint64_t *n_words, uint64_t *blo
 static int count_export(bpe_ctx *ctx, uint8_t *blob, uint64_t *offs, int64_t *counts, bool to_device) {
     if (!ctx || !ctx->count || !offs) return BPE_ERR_ARG;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    u64 ns, nw, nb;
-    BPE_TRY(count_export_scan(ctx, &ns, &nw, &nb));
+    WordCounts wc; u64 nw, nb;
+    BPE_TRY(count_export_scan(ctx, &wc, &nw, &nb));
     cudaStream_t st = ctx->stream;
     CountTables t = count_tables(ctx);
     size_t lens_b = round_up((nw + 1) * 4, 256);
-    u32 *lens = (u32 *)ctx->tmp1.p;
-    u64 *boff = (u64 *)((uint8_t *)lens + lens_b);
+    u64 *boff = (u64 *)((uint8_t *)ctx->tmp1.p + lens_b);
     uint8_t *dblob; u64 *doffs; i64 *dcnt;
     if (to_device) { dblob = blob; doffs = (u64 *)offs; dcnt = (i64 *)counts; }
     else {
@@ -725,7 +790,7 @@ static int count_export(bpe_ctx *ctx, uint8_t *blob, uint64_t *offs, int64_t *co
     if ((nb && !dblob) || (nw && !dcnt)) return BPE_ERR_ARG;
     if (nw) {
         unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (nw + 255) / 256);
-        KLAUNCH(k_export_write, grid, 256, 0, st, t, ns, nw, lens, boff, dblob, doffs, dcnt);
+        KLAUNCH(k_export_write, grid, 256, 0, st, t, wc, nw, boff, dblob, doffs, dcnt);
         CUDA_TRY(ctx, cudaGetLastError());
     }
     if (to_device) {
@@ -778,7 +843,7 @@ static int count_import(bpe_ctx *ctx, const uint8_t *blob, const uint64_t *offs,
     }
     u64 c[8];
     BPE_TRY(read_counters(ctx, c, 8));
-    BPE_TRY(count_ensure_capacity(ctx, c[0], c[1], n_words, n_words));
+    BPE_TRY(count_ensure_capacity(ctx, c, n_words, 2 * n_words));   // (any mix of lengths: the bound for >= 16 bytes is half the one for >= 8)
     CountTables t = count_tables(ctx);
     unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (n_words + 255) / 256);
     KLAUNCH(k_import_words, grid, 256, 0, st, t, (const uint8_t *)cs->pool.p + base, base, doffs, dcnt, n_words);
@@ -809,11 +874,12 @@ BPE_API int bpe_count_pair_table(bpe_ctx *ctx, const uint8_t *specials_blob, con
     BPE_TRY(bpe_buf_reserve(ctx, dense, 65536 * 8));
     CUDA_TRY(ctx, cudaMemsetAsync(dense.p, 0, 65536 * 8, st));
     CountTables t = count_tables(ctx);
-    u64 c[2];
-    BPE_TRY(read_counters(ctx, c, 2));
-    if (c[0] + c[1]) {
-        unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (c[0] + c[1] + 255) / 256);
-        KLAUNCH(k_dense_pairs, grid, 256, 0, st, t, c[0], c[0] + c[1], spb, spo, n_specials, (u64 *)dense.p);
+    u64 c[8];
+    BPE_TRY(read_counters(ctx, c, 8));
+    const WordCounts wc{c[0], c[7], c[1]};
+    if (c[0] + c[7] + c[1]) {
+        unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (c[0] + c[7] + c[1] + 255) / 256);
+        KLAUNCH(k_dense_pairs, grid, 256, 0, st, t, wc, spb, spo, n_specials, (u64 *)dense.p);
     }
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaMemcpyAsync(dense_out, dense.p, 65536 * 8, cudaMemcpyDeviceToHost, st));
@@ -835,10 +901,11 @@ static int run_merges(bpe_ctx *ctx, const uint8_t *sp_blob, const u32 *sp_offs, 
     CountState *cs = ctx->count;
     TrainBufs B;
     struct Guard { TrainBufs &b; bpe_ctx *c; ~Guard() { b.free_all(c); } } guard{B, ctx};
-    u64 c[6];
-    BPE_TRY(read_counters(ctx, c, 6));
-    u64 n_short = c[0], n_long = c[1], long_bytes = c[2];
-    u64 max_words = n_short + n_long, max_syms = n_short * SHORT_MAX + long_bytes;
+    u64 c[8];
+    BPE_TRY(read_counters(ctx, c, 8));
+    const WordCounts wc{c[0], c[7], c[1]};
+    const u64 long_bytes = c[2];
+    u64 max_words = wc.n_short + wc.n_medium + wc.n_long, max_syms = wc.n_short * SHORT_MAX + wc.n_medium * MED_MAX + long_bytes;
     const u64 sym_slots = max_syms + max_words + 2 * SYM_PAD;
     if (sym_slots >= (1ull << 32)) return bpe_set_error(ctx, BPE_ERR_UNSUPPORTED, "more than 2^32 symbols in unique words");
     const uint8_t *spb; const u32 *spo; u32 spmax;
@@ -853,7 +920,7 @@ static int run_merges(bpe_ctx *ctx, const uint8_t *sp_blob, const u32 *sp_offs, 
     CountTables t = count_tables(ctx);
     if (max_words) {
         unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (max_words + 255) / 256);
-        KLAUNCH(k_build_words, grid, 256, 0, st, t, n_short, max_words, W, spb, spo, n_sp);
+        KLAUNCH(k_build_words, grid, 256, 0, st, t, wc, W, spb, spo, n_sp);
         CUDA_TRY(ctx, cudaGetLastError());
     }
     u64 *host = (u64 *)ctx->pinned;
