@@ -45,6 +45,7 @@ struct CountTables {
     // words (re-homing, export, word list, table growth) walks these lists instead of scanning the tables' capacity, which is
     // sized for the worst case (every pretoken of a batch new) and mostly empty
     u32 *slist, *mlist, *llist;
+    ulonglong2 *hot; u64 *hcnt; u64 hot_nb;      // hot table (see below): hot_nb buckets of two 16-byte keys, counts apart; 0 = none
     const uint8_t *text;                         // payload of the current text arena
     const uint8_t *pool;                         // persistent bytes of long words
     u64 *counters;                               // [0]=n_short [1]=n_long [2]=long_bytes [3]=overflow [4]=n_pretokens [5]=too_long
@@ -62,8 +63,10 @@ struct WordCounts { u64 n_short, n_medium, n_long; };
 #define LCNT(t, s) ((t).ltab[4 * (s) + 2])
 
 struct CountState {
-    DevBuf stab, mtab, ltab, slist, mlist, llist, pool, counters;
+    DevBuf stab, mtab, ltab, slist, mlist, llist, pool, counters, hot;
     u64 scap = 0, mcap = 0, lcap = 0, pool_used = 0;
+    u64 hot_nb = 0, hot_seen = 0;                // buckets of the hot table; pretokens counted when it was last built
+    int hot_builds = 0;
     bool active = false;
     u64 n_pretokens = 0;
     u64 n_rehomed = 0;                           // long words [0, n_rehomed) of the list have their bytes in the pool
@@ -143,124 +146,200 @@ __device__ __forceinline__ void long_add(const CountTables &t, const uint8_t *p,
     t.counters[3] = 1;
 }
 
-// Pretoken occurrences i of the batch: bytes [base + offs[i], base + offs[i+1]).  Tiles of CNT_NT x CNT_ITEMS occurrences are
-// handed out by a ticket counter (every CTA is busy until the batch is done, however uneven its items were) and go through two
-// phases, so that threads that hit the shared-memory table never wait in lockstep behind threads that go to HBM:
-//   A  every thread forms the keys of its CNT_ITEMS occurrences (offsets and the first 16 text bytes of all of them in flight
-//      together).  Pretokens of <= 7 bytes are counted in a per-CTA shared-memory table (natural-language text is Zipfian: without
-//      it the few hottest words serialise hundreds of millions of same-address L2 atomics); what does not fit there, and every longer
-//      pretoken, is queued in shared memory.
-//   B  all threads drain the queues: one HBM probe sequence per thread, all in flight at once.
+// Counting straight from the text and its start bits (no per-pretoken offset array, no scan): a lane owns one 16-byte chunk --
+// its 32-byte text window in registers, a 64-bit window of start bits -- and walks the chunk's start bits; a warp takes 32
+// consecutive chunks (512 bytes of text, coalesced 16-byte loads) per step, grid-stride, the next step's loads in flight while
+// this one is worked on.  For every start bit: length = distance to the next start bit (in the window; pretokens of more than
+// ~32 bytes look it up in the bit array), the first 16 bytes of the pretoken are cut out of the register window with selects and
+// funnel shifts (no byte loops, no unaligned loads).
+//   * pretokens of <= 7 bytes are counted in the CTA's shared-memory table (natural-language text is Zipfian: without it the few
+//     hottest words serialise hundreds of millions of same-address L2 atomics);
+//   * what misses there, and every longer pretoken, goes to the warp's queues (compacted with ballots; the queue lengths are
+//     warp-uniform registers: no atomics, no CTA barrier anywhere in the loop), one queue per KIND of work, so that the pass that
+//     drains them runs one code path with all lanes: short keys, medium (k0, k1) keys, long pretokens (offset | len << 32).
+//     A drain takes whole groups of 32 entries: entry e of the short queue and entry e of the medium queue per lane, their first
+//     probes in flight together.
 // The shared-memory table is flushed to the HBM table when the CTA is done.
 #ifndef CNT_NT
 #define CNT_NT 512
 #endif
-#ifndef CNT_ITEMS
-#define CNT_ITEMS 4
-#endif
 #ifndef CNT_SMEM_LG
 #define CNT_SMEM_LG 12
 #endif
-#define CNT_TILE ((u64)CNT_NT * CNT_ITEMS)
 #define CNT_SMEM_SLOTS (1u << CNT_SMEM_LG)
 #ifndef CNT_SMEM_PROBES
-#define CNT_SMEM_PROBES 2u                       // (4 -> 84 ms per 11 GB, 2 -> 81, 1 -> 81)
+#define CNT_SMEM_PROBES 2u
 #endif
-#define CNT_DYN_SMEM ((size_t)CNT_SMEM_SLOTS * 12 + (size_t)CNT_TILE * 16)
-// queue push with one shared-memory atomic per warp
-__device__ __forceinline__ u32 warp_queue_slot(u32 *counter, bool want) {
-    const u32 m = __ballot_sync(0xffffffffu, want);
-    if (!m) return 0;
-    u32 base = 0;
-    if (lane_id() == (u32)(__ffs(m) - 1)) base = atomicAdd(counter, (u32)__popc(m));
-    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-    return base + __popc(m & ((1u << lane_id()) - 1u));
+#define CNT_WARPS (CNT_NT / 32u)
+#define CNT_QCAP 160u                            // entries of the warp's key queue
+#define CNT_QDRAIN 128u                          // drained when it reaches this (a round of the bit loop adds <= 32)
+#define CNT_QL_CAP 64u
+#define CNT_QL_DRAIN 32u
+#define CNT_WARP_SMEM (CNT_QCAP * 16u + CNT_QL_CAP * 8u)
+#define CNT_DYN_SMEM ((size_t)CNT_SMEM_SLOTS * 12 + (size_t)CNT_WARPS * CNT_WARP_SMEM)
+
+// queues of a warp: qe = keys of short pretokens that missed the shared-memory table (k0 = key, k1 = 0) and of medium ones
+// (k0, k1 != 0); ql = long pretokens (offset from base | len << 32)
+struct CountQueues { ulonglong2 *qe; u64 *ql; u32 n, nl; };
+
+// The HOT TABLE.  A probe into the big tables is one random 32-byte sector and its 128-byte L2 line to itself (the tables are
+// sized for the worst case and mostly empty).  Measured on B200 (tools/bench_l2_random.cu, bench_l2_mix.cu): L2 keeps ~0.5 M such
+// lines; a random read + RED pair that misses it runs at 16-20 G pairs/s, one that hits at 60-110 G/s -- and counting 11 GB of
+// web-like text sends 1.1 G pairs to the tables, most of them to words that are neither among the 4 096 the shared-memory table
+// holds nor rare.  So once enough text has been seen, the words counted at least T times are copied into a DENSE table of their
+// own, probed first: a bucket is ONE 32-byte sector holding two 16-byte keys (short and medium words alike: k1 = 0 for a short
+// one), the counts sit in an array beside it -- at most ~1 M words, 50 MB: it stays in L2.  A word whose bucket is full stays with
+// the big tables, so a probe is exactly one sector: no chains, no claims, all lanes of a warp finish together.  The counts are added
+// back to the big tables whenever somebody needs those (count_hot_flush).
+__device__ __forceinline__ u64 hot_bucket_of(const CountTables &t, u64 k0, u64 k1) {
+    return ((mix64(k0 ^ (k1 * 0x9E3779B97F4A7C15ull)) >> 32) * t.hot_nb) >> 32;
 }
-// queue entry (16 bytes): short pretoken that missed the shared table {key, 0}; medium {k0, k1} (k1 != 0: it carries the length);
-// long {offset from base | len << 32, ~0}
-#define CNT_Q_LONG 0xFFFFFFFFFFFFFFFFull
-__global__ void __launch_bounds__(CNT_NT) k_count_pretokens(CountTables t, const u32 *__restrict__ offs, u64 n_items, u64 base,
-                                                           u64 own_begin, u64 own_end, u64 trust_end) {
+
+// Drain the warp's queues: whole groups of 64 keys (everything when `all`), two per lane with their probes in flight together;
+// every long entry.
+__device__ __forceinline__ void count_drain(const CountTables &t, CountQueues &q, u64 base, u32 lane, bool all) {
+    const u32 dn = all ? q.n : q.n & ~63u;
+    __syncwarp();
+#ifdef CNT_KO_DRAIN
+    q.n = q.nl = 0; return;
+#endif
+    for (u32 e0 = 0; e0 < dn; e0 += 64u) {
+        const bool ha = e0 + lane < dn, hb = e0 + 32u + lane < dn;
+        ulonglong2 ka = make_ulonglong2(0, 0), kb = ka;
+        if (ha) ka = q.qe[e0 + lane];
+        if (hb) kb = q.qe[e0 + 32u + lane];
+        bool ta = ha, tb = hb;                   // still to be added to the big tables
+        if (t.hot_nb) {
+            const u64 ba = hot_bucket_of(t, ka.x, ka.y), bb = hot_bucket_of(t, kb.x, kb.y);
+            ulonglong2 a0 = make_ulonglong2(0, 0), a1 = a0, b0 = a0, b1 = a0;
+            if (ha) { a0 = t.hot[2 * ba]; a1 = t.hot[2 * ba + 1]; }
+            if (hb) { b0 = t.hot[2 * bb]; b1 = t.hot[2 * bb + 1]; }
+            if (ha) {
+                const bool m0 = a0.x == ka.x && a0.y == ka.y, m1 = a1.x == ka.x && a1.y == ka.y;
+                if (m0 || m1) { atomicAdd(&t.hcnt[2 * ba + (m1 ? 1 : 0)], 1ull); ta = false; }
+            }
+            if (hb) {
+                const bool m0 = b0.x == kb.x && b0.y == kb.y, m1 = b1.x == kb.x && b1.y == kb.y;
+                if (m0 || m1) { atomicAdd(&t.hcnt[2 * bb + (m1 ? 1 : 0)], 1ull); tb = false; }
+            }
+        }
+        if (ta) { if (ka.y == 0) short_add(t, ka.x, 1); else medium_add(t, ka.x, ka.y, 1); }
+        if (tb) { if (kb.y == 0) short_add(t, kb.x, 1); else medium_add(t, kb.x, kb.y, 1); }
+    }
+    for (u32 e = lane; e < q.nl; e += 32u) {
+        const u64 ent = q.ql[e];
+        const u64 off = base + (u32)ent;
+        long_add(t, t.text + off, (u32)(ent >> 32), off, 1);
+    }
+    q.nl = 0;
+    // the remainder (< 64 keys) moves to the front
+    const u32 r = q.n - dn;
+    ulonglong2 v0 = make_ulonglong2(0, 0), v1 = v0;
+    if (dn && lane < r) v0 = q.qe[dn + lane];
+    if (dn && lane + 32u < r) v1 = q.qe[dn + 32u + lane];
+    __syncwarp();
+    if (dn && lane < r) q.qe[lane] = v0;
+    if (dn && lane + 32u < r) q.qe[32u + lane] = v1;
+    q.n = r;
+    __syncwarp();
+}
+
+// chunks [c_lo, c_hi) (16 bytes each, absolute positions 16 c); `base` <= 16 c_lo is what the 32-bit offsets of the long queue count from
+__global__ void __launch_bounds__(CNT_NT, 2) k_count_pretokens(CountTables t, const u32 *__restrict__ flags, u64 c_lo, u64 c_hi, u64 n, u64 base,
+                                                              u64 own_begin, u64 own_end, u64 trust_end) {
     extern __shared__ __align__(16) unsigned char cnt_smem[];
-    u64 *s_key = reinterpret_cast<u64 *>(cnt_smem);                       // shared-memory table: keys ...
-    ulonglong2 *s_q = reinterpret_cast<ulonglong2 *>(s_key + CNT_SMEM_SLOTS);   // what goes to the HBM tables
-    u32 *s_cnt = reinterpret_cast<u32 *>(s_q + CNT_TILE);                 // ... and counts
-    __shared__ u32 s_nq[2];                      // queue length, alternating between tiles (the other one is cleared meanwhile)
-    __shared__ u64 s_tile[2];
+    const u32 lane = lane_id(), warp = threadIdx.x >> 5;
+    u64 *s_key = reinterpret_cast<u64 *>(cnt_smem);                                        // shared-memory table: keys ...
+    u32 *s_cnt = reinterpret_cast<u32 *>(s_key + CNT_SMEM_SLOTS);                          // ... and counts
+    unsigned char *wq = cnt_smem + (size_t)CNT_SMEM_SLOTS * 12 + (size_t)warp * CNT_WARP_SMEM;
+    CountQueues q;
+    q.qe = reinterpret_cast<ulonglong2 *>(wq); q.ql = reinterpret_cast<u64 *>(wq + CNT_QCAP * 16u);
+    q.n = q.nl = 0;
     for (u32 i = threadIdx.x; i < CNT_SMEM_SLOTS; i += CNT_NT) { s_key[i] = 0; s_cnt[i] = 0; }
-    if (threadIdx.x < 2) s_nq[threadIdx.x] = 0;
-    if (threadIdx.x == 0) s_tile[0] = atomicAdd(&t.counters[16], 1ull);
     __syncthreads();
     u64 n_tok = 0;
-    for (u32 it = 0;; it++) {
-        const u32 par = it & 1u;
-        const u64 tile_lo = s_tile[par] * CNT_TILE;
-        if (tile_lo >= n_items) break;
-        // the ticket of the next tile is fetched while this one is worked on (two CTA barriers per tile, not four)
-        if (threadIdx.x == 0) { s_tile[par ^ 1u] = atomicAdd(&t.counters[16], 1ull); s_nq[par ^ 1u] = 0; }
-        // ---- phase A ----
-        u32 a[CNT_ITEMS], b[CNT_ITEMS];
-        u64 lo[CNT_ITEMS], hi[CNT_ITEMS];
-        bool has[CNT_ITEMS];
-#pragma unroll
-        for (u32 k = 0; k < CNT_ITEMS; k++) {
-            const u64 i = tile_lo + (u64)k * CNT_NT + threadIdx.x;
-            has[k] = i < n_items;
-            a[k] = 0; b[k] = 0;
-            if (has[k]) { a[k] = offs[i]; b[k] = offs[i + 1]; }
-        }
-#pragma unroll
-        for (u32 k = 0; k < CNT_ITEMS; k++) {
-            lo[k] = 0; hi[k] = 0;
-            if (has[k]) { const u64 *q = reinterpret_cast<const u64 *>(reinterpret_cast<uintptr_t>(t.text + base + a[k]) & ~(uintptr_t)7); lo[k] = q[0]; hi[k] = q[1]; }
-        }
-#pragma unroll
-        for (u32 k = 0; k < CNT_ITEMS; k++) {
-            const u64 pos = base + a[k];
-            const u32 len = b[k] - a[k];
-            const bool mine = has[k] && pos >= own_begin && pos < own_end;
-            bool to_q = false;
-            ulonglong2 ent = make_ulonglong2(0, 0);
-            if (mine) {
-                if (base + b[k] > trust_end) t.counters[6] = 1;
-                n_tok++;
-                const u32 sh = (u32)(reinterpret_cast<uintptr_t>(t.text + pos) & 7u) * 8u;
-                const u64 first8 = sh ? (lo[k] >> sh) | (hi[k] << (64u - sh)) : lo[k];
-                if (len <= SHORT_MAX) {
-                    const u64 key = (first8 & low_bytes_mask(len)) | ((u64)len << 56);       // = short_key(p, len)
-                    u32 slot = (((u32)key ^ (u32)(key >> 32)) * 0x9E3779B1u) >> (32 - CNT_SMEM_LG);   // cheap hash for the shared-memory table
-                    to_q = true; ent.x = key;
-                    for (u32 pr = 0; pr < CNT_SMEM_PROBES; pr++) {
-                        u64 kk = s_key[slot];
-                        if (kk == 0) { const u64 old = atomicCAS(&s_key[slot], 0ull, key); kk = old ? old : key; }
-                        if (kk == key) { atomicAdd(&s_cnt[slot], 1u); to_q = false; break; }
-                        slot = (slot + 1) & (CNT_SMEM_SLOTS - 1);
-                    }
-                } else if (len <= MED_MAX) {
-                    // bytes 8..14: in the second word already loaded, or (unaligned start) partly in the third one
-                    u64 next8 = sh ? (hi[k] >> sh) : hi[k];
-                    if (sh && len > 16u - sh / 8u) next8 |= reinterpret_cast<const u64 *>(reinterpret_cast<uintptr_t>(t.text + pos) & ~(uintptr_t)7)[2] << (64u - sh);
-                    to_q = true; ent.x = first8; ent.y = (len > 8 ? next8 & low_bytes_mask(len - 8) : 0ull) | ((u64)len << 56);
-                } else if (len <= MAX_TOKEN_LEN) { to_q = true; ent.x = (u64)a[k] | ((u64)len << 32); ent.y = CNT_Q_LONG; }
-                else t.counters[5] = 1;
-            }
-            const u32 qs = warp_queue_slot(&s_nq[par], to_q);
-            if (to_q) s_q[qs] = ent;
-        }
-        __syncthreads();
-        // ---- phase B ----
-        const u32 nq = s_nq[par];
-        for (u32 e = threadIdx.x; e < nq; e += CNT_NT) {
-            const ulonglong2 ent = s_q[e];
-            if (ent.y == 0) short_add(t, ent.x, 1);
-            else if (ent.y != CNT_Q_LONG) medium_add(t, ent.x, ent.y, 1);
-            else { const u64 off = base + (u32)ent.x; long_add(t, t.text + off, (u32)(ent.x >> 32), off, 1); }
-        }
-        __syncthreads();
+    const u32 lt = (1u << lane) - 1u;
+    const u64 stride = (u64)gridDim.x * CNT_WARPS * 32u;
+    const u64 n_fw = (n + 31) >> 5;              // flag words that hold bits of the text
+    u64 c = c_lo + ((u64)blockIdx.x * CNT_WARPS + warp) * 32u + lane;
+    // loads of a step: the chunk, the 16 bytes after it (the arena is padded), the two flag words that hold its 48..64-bit window
+    uint4 A = make_uint4(0, 0, 0, 0), B = A; u32 f0 = 0, f1 = 0;
+    if (c < c_hi) {
+        const uint4 *tp = reinterpret_cast<const uint4 *>(t.text + c * 16u);
+        A = __ldcs(tp); B = __ldcs(tp + 1);
+        const u64 w = c >> 1; f0 = __ldcs(flags + w); f1 = w + 1 < n_fw ? __ldcs(flags + w + 1) : 0u;
     }
+    for (; __any_sync(0xffffffffu, c < c_hi); c += stride) {
+        const bool live = c < c_hi;
+        const u64 p0 = c * 16u;
+        const u32 W0 = A.x, W1 = A.y, W2 = A.z, W3 = A.w, W4 = B.x, W5 = B.y, W6 = B.z, W7 = B.w;
+        u64 F = (((u64)f1 << 32) | f0) >> (u32)(p0 & 16u);           // bit i: a pretoken starts at byte p0 + i (>= 48 bits)
+        // the next step's loads
+        {
+            const u64 cn = c + stride;
+            if (cn < c_hi) {
+                const uint4 *tp = reinterpret_cast<const uint4 *>(t.text + cn * 16u);
+                A = __ldcs(tp); B = __ldcs(tp + 1);
+                const u64 w = cn >> 1; f0 = __ldcs(flags + w); f1 = w + 1 < n_fw ? __ldcs(flags + w + 1) : 0u;
+            }
+        }
+        if (p0 + 64 > n) F = p0 < n ? F & ((1ull << (n - p0)) - 1ull) : 0ull;   // bits past the end of the text do not count
+        u32 m = live ? (u32)F & 0xFFFFu : 0u;
+        // only the starts inside [own_begin, own_end)
+        if (p0 < own_begin) m = own_begin - p0 >= 16 ? 0u : m & ~((1u << (u32)(own_begin - p0)) - 1u);
+        if (p0 + 16 > own_end) m = own_end <= p0 ? 0u : m & ((1u << (u32)(own_end - p0)) - 1u);
+        n_tok += __popc(m);
+        while (__any_sync(0xffffffffu, m != 0)) {
+            const bool act = m != 0;
+            const u32 j = act ? __ffs(m) - 1u : 0u;
+            m &= m - 1u;
+            const u64 rest = F >> (j + 1u);
+            u32 len = (u32)__ffsll((long long)rest);
+            if (act && len == 0) {               // no further start in the window: a long pretoken, or the last one of the text
+                const u64 e = flags_next_start(flags, p0 + j + 1, n) - (p0 + j);
+                if (e > MAX_TOKEN_LEN) { t.counters[5] = 1; len = MAX_TOKEN_LEN; } else len = (u32)e;
+            }
+            if (act && p0 + j + len > trust_end) t.counters[6] = 1;
+            // bytes j .. j + 15 of the 32-byte window
+            const u32 qd = j >> 2, sh = (j & 3u) * 8u;
+            const bool q2 = qd & 2u, q1 = qd & 1u;
+            const u32 X0 = q2 ? W2 : W0, X1 = q2 ? W3 : W1, X2 = q2 ? W4 : W2, X3 = q2 ? W5 : W3, X4 = q2 ? W6 : W4, X5 = q2 ? W7 : W5;
+            const u32 Y0 = q1 ? X1 : X0, Y1 = q1 ? X2 : X1, Y2 = q1 ? X3 : X2, Y3 = q1 ? X4 : X3, Y4 = q1 ? X5 : X4;
+            const u64 k0 = (u64)__funnelshift_r(Y0, Y1, sh) | ((u64)__funnelshift_r(Y1, Y2, sh) << 32);
+            const u64 k1 = (u64)__funnelshift_r(Y2, Y3, sh) | ((u64)__funnelshift_r(Y3, Y4, sh) << 32);
+            bool q_s = act && len <= SHORT_MAX;
+            const bool q_m = act && len > SHORT_MAX && len <= MED_MAX, q_l = act && len > MED_MAX;
+            const u64 key = (k0 & low_bytes_mask(len)) | ((u64)len << 56);               // (short pretokens)
+#ifdef CNT_KO_SMEM
+            if (false) {
+#else
+            if (q_s) {
+#endif
+                u32 slot = (((u32)key ^ (u32)(key >> 32)) * 0x9E3779B1u) >> (32 - CNT_SMEM_LG);   // cheap hash for the shared-memory table
+#pragma unroll
+                for (u32 pr = 0; pr < CNT_SMEM_PROBES; pr++) {
+                    u64 kk = s_key[slot];
+                    if (kk == 0) { const u64 old = atomicCAS(&s_key[slot], 0ull, key); kk = old ? old : key; }
+#ifdef CNT_KO_ATOM
+                    if (kk == key) { q_s = false; break; }
+#else
+                    if (kk == key) { atomicAdd(&s_cnt[slot], 1u); q_s = false; break; }
+#endif
+                    slot = (slot + 1) & (CNT_SMEM_SLOTS - 1);
+                }
+            }
+            const u32 me = __ballot_sync(0xffffffffu, q_s || q_m), ml = __ballot_sync(0xffffffffu, q_l);
+            if (q_s) q.qe[q.n + __popc(me & lt)] = make_ulonglong2(key, 0ull);
+            if (q_m) q.qe[q.n + __popc(me & lt)] = make_ulonglong2(k0, (len > 8 ? k1 & low_bytes_mask(len - 8) : 0ull) | ((u64)len << 56));
+            if (q_l) q.ql[q.nl + __popc(ml & lt)] = (p0 + j - base) | ((u64)len << 32);
+            q.n += __popc(me); q.nl += __popc(ml);
+            if (q.n >= CNT_QDRAIN || q.nl >= CNT_QL_DRAIN) count_drain(t, q, base, lane, false);
+        }
+    }
+    count_drain(t, q, base, lane, true);
     // one atomic per warp for the occurrence counter
     for (int d = 16; d; d >>= 1) n_tok += __shfl_down_sync(0xffffffffu, n_tok, d);
-    if (lane_id() == 0 && n_tok) atomicAdd(&t.counters[4], n_tok);
+    if (lane == 0 && n_tok) atomicAdd(&t.counters[4], n_tok);
     __syncthreads();
     for (u32 i = threadIdx.x; i < CNT_SMEM_SLOTS; i += CNT_NT)
         if (s_cnt[i]) short_add(t, s_key[i], (u64)s_cnt[i]);
@@ -276,6 +355,48 @@ __global__ void __launch_bounds__(256) k_popc_ranges(const u32 *__restrict__ fla
     for (u64 w = lo + (u64)blockIdx.x * blockDim.x + threadIdx.x; w < hi; w += (u64)gridDim.x * blockDim.x) c += __popc(flags[w]);
     for (int d = 16; d; d >>= 1) c += __shfl_down_sync(0xffffffffu, c, d);
     if (lane_id() == 0 && c) atomicAdd(&out[r], c);
+}
+
+// ---- hot table: histogram of the counts, build, flush ------------------------------------------------------------------
+#define HOT_HIST 64
+__global__ void __launch_bounds__(256) k_hot_hist(CountTables t, u64 n_short, u64 n_medium, u64 *__restrict__ hist /* [HOT_HIST] */) {
+    __shared__ u32 s_h[HOT_HIST];
+    if (threadIdx.x < HOT_HIST) s_h[threadIdx.x] = 0;
+    __syncthreads();
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_short + n_medium; i += (u64)gridDim.x * blockDim.x) {
+        const u64 c = i < n_short ? SCNT(t, t.slist[i]) : MCNT(t, t.mlist[i - n_short]);
+        atomicAdd(&s_h[c < HOT_HIST ? (u32)c : HOT_HIST - 1], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < HOT_HIST && s_h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (u64)s_h[threadIdx.x]);
+}
+// every short / medium word counted at least `thresh` times is placed in its bucket if one of the two slots is free
+// (the keys are distinct: no comparison)
+__global__ void __launch_bounds__(256) k_hot_build(CountTables t, u64 n_short, u64 n_medium, u64 thresh, u64 *__restrict__ placed) {
+    u64 np = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_short + n_medium; i += (u64)gridDim.x * blockDim.x) {
+        u64 k0, k1, c;
+        if (i < n_short) { const u64 s = t.slist[i]; k0 = SKEY(t, s); k1 = 0; c = SCNT(t, s); }
+        else { const u64 s = t.mlist[i - n_short]; k0 = MK0(t, s); k1 = MK1(t, s); c = MCNT(t, s); }
+        if (c < thresh) continue;
+        const u64 b = hot_bucket_of(t, k0, k1);
+        u64 x, y;
+        cas128(reinterpret_cast<u64 *>(&t.hot[2 * b]), 0, 0, k0, k1, x, y);
+        if ((x | y) != 0) cas128(reinterpret_cast<u64 *>(&t.hot[2 * b + 1]), 0, 0, k0, k1, x, y);
+        if ((x | y) == 0) np++;
+    }
+    for (int d = 16; d; d >>= 1) np += __shfl_down_sync(0xffffffffu, np, d);
+    if (lane_id() == 0 && np) atomicAdd(placed, np);
+}
+// counts of the hot table -> big tables (the keys stay, the counts restart at zero)
+__global__ void __launch_bounds__(256) k_hot_flush(CountTables t) {
+    for (u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x; s < 2 * t.hot_nb; s += (u64)gridDim.x * blockDim.x) {
+        const u64 c = t.hcnt[s];
+        if (!c) continue;
+        t.hcnt[s] = 0;
+        const ulonglong2 k = t.hot[s];
+        if (k.y == 0) short_add(t, k.x, c); else medium_add(t, k.x, k.y, c);
+    }
 }
 
 // ---- table growth: re-insert every entry of an old table into a bigger one -------------------
@@ -521,6 +642,7 @@ static CountTables count_tables(bpe_ctx *ctx) {
     t.mtab = (u64 *)cs->mtab.p; t.mcap = cs->mcap;
     t.ltab = (u64 *)cs->ltab.p; t.lcap = cs->lcap;
     t.slist = (u32 *)cs->slist.p; t.mlist = (u32 *)cs->mlist.p; t.llist = (u32 *)cs->llist.p;
+    t.hot = (ulonglong2 *)cs->hot.p; t.hot_nb = cs->hot_nb; t.hcnt = (u64 *)((ulonglong2 *)cs->hot.p + 2 * cs->hot_nb);
     t.text = ctx->text.p ? (const uint8_t *)ctx->text.p + BPE_PAD : nullptr;
     t.pool = (const uint8_t *)cs->pool.p;
     t.counters = (u64 *)cs->counters.p;
@@ -530,7 +652,7 @@ static CountTables count_tables(bpe_ctx *ctx) {
 void count_state_free(bpe_ctx *ctx) {
     if (!ctx->count) return;
     CountState *cs = ctx->count;
-    for (DevBuf *b : {&cs->stab, &cs->mtab, &cs->ltab, &cs->slist, &cs->mlist, &cs->llist, &cs->pool, &cs->counters}) bpe_buf_free(ctx, *b);
+    for (DevBuf *b : {&cs->stab, &cs->mtab, &cs->ltab, &cs->slist, &cs->mlist, &cs->llist, &cs->pool, &cs->counters, &cs->hot}) bpe_buf_free(ctx, *b);
     delete cs;
     ctx->count = nullptr;
 }
@@ -557,6 +679,7 @@ BPE_API int bpe_count_begin(bpe_ctx *ctx) {
     CUDA_TRY(ctx, cudaMemsetAsync(cs->counters.p, 0, 64 * sizeof(u64), ctx->stream));
     BPE_TRY(count_tables_alloc(ctx, 1 << 16, 1 << 14, 1 << 14));
     cs->pool_used = 0; cs->active = true; cs->n_pretokens = 0; cs->n_rehomed = 0;
+    bpe_buf_free(ctx, cs->hot); cs->hot_nb = 0; cs->hot_seen = 0; cs->hot_builds = 0;
     return BPE_OK;
 }
 
@@ -598,6 +721,54 @@ static int count_ensure_capacity(bpe_ctx *ctx, const u64 *c, u64 new_short, u64 
     return BPE_OK;
 }
 
+// Add the counts of the hot table back to the big tables (which then hold everything again).
+static int count_hot_flush(bpe_ctx *ctx) {
+    CountState *cs = ctx->count;
+    if (!cs->hot_nb) return BPE_OK;
+    CountTables t = count_tables(ctx);
+    KLAUNCH(k_hot_flush, (unsigned)std::min<u64>((u64)ctx->sm_count * 16, (2 * cs->hot_nb + 255) / 256), 256, 0, ctx->stream, t);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return BPE_OK;
+}
+// (Re)build the hot table from the counts so far: the words counted at least T times, T the smallest threshold that selects at most
+// BPE_COUNT_HOT_MAX (default 1 M) words.  c = the counters as read by read_counters(ctx, c, 8).
+static int count_hot_rebuild(bpe_ctx *ctx, const u64 *c) {
+    CountState *cs = ctx->count;
+    cudaStream_t st = ctx->stream;
+    static const u64 hot_max = getenv("BPE_COUNT_HOT_MAX") ? (u64)atoll(getenv("BPE_COUNT_HOT_MAX")) : (1ull << 20);
+    const u64 n_short = c[0], n_medium = c[7];
+    BPE_TRY(count_hot_flush(ctx));
+    bpe_buf_free(ctx, cs->hot); cs->hot_nb = 0;
+    cs->hot_builds++; cs->hot_seen = c[4];
+    if (!hot_max || n_short + n_medium < (1u << 16)) return BPE_OK;          // small vocabularies stay in L2 as they are
+    CountTables t = count_tables(ctx);
+    u64 *hist = (u64 *)ctx->scratch.p + 16;
+    CUDA_TRY(ctx, cudaMemsetAsync(hist, 0, HOT_HIST * sizeof(u64), st));
+    const unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 16, (n_short + n_medium + 255) / 256);
+    KLAUNCH(k_hot_hist, grid, 256, 0, st, t, n_short, n_medium, hist);
+    u64 *host = (u64 *)ctx->pinned;
+    CUDA_TRY(ctx, cudaMemcpyAsync(host, hist, HOT_HIST * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    u64 n_hot = 0, thresh = HOT_HIST;
+    for (int k = HOT_HIST - 1; k >= 2; k--) { if (n_hot + host[k] > hot_max) break; n_hot += host[k]; thresh = (u64)k; }
+    if (thresh >= HOT_HIST || n_hot < 1024) return BPE_OK;
+    const u64 nb = n_hot + 64;                   // one bucket (two slots) per selected word: ~10 % of them find theirs full
+    BPE_TRY(alloc_exact(ctx, cs->hot, nb * 48));
+    CUDA_TRY(ctx, cudaMemsetAsync(cs->hot.p, 0, nb * 48, st));
+    cs->hot_nb = nb;
+    t = count_tables(ctx);
+    CUDA_TRY(ctx, cudaMemsetAsync(hist, 0, sizeof(u64), st));
+    KLAUNCH(k_hot_build, grid, 256, 0, st, t, n_short, n_medium, thresh, hist);
+    CUDA_TRY(ctx, cudaGetLastError());
+    static const bool prof = getenv("BPE_COUNT_PROFILE") != nullptr;
+    if (prof) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(host, hist, sizeof(u64), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        fprintf(stderr, "  [hot table: %llu words counted >= %llu times, %llu buckets, %llu placed, after %llu pretokens]\n", (unsigned long long)n_hot, (unsigned long long)thresh, (unsigned long long)nb, (unsigned long long)host[0], (unsigned long long)c[4]);
+    }
+    return BPE_OK;
+}
+
 #include <chrono>
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 #define COUNT_BATCH_BYTES (256ull << 20)
@@ -628,36 +799,29 @@ static int count_current_text(bpe_ctx *ctx, u64 n, u64 own_begin, u64 own_end, u
     for (u64 bi = 0; bi < n_batches; bi++) {
         const double tb0 = prof ? now_ms() : 0;
         u64 b_lo = w_lo + bi * words_per_batch, b_hi = std::min(w_hi, b_lo + words_per_batch);
-        u64 bytes = (b_hi - b_lo) * 32, bw = b_hi - b_lo;
+        u64 bytes = (b_hi - b_lo) * 32;
         static const u64 bound_div = getenv("BPE_COUNT_BOUND_DIV") ? std::max(1, atoi(getenv("BPE_COUNT_BOUND_DIV"))) : 1;   // EXPERIMENT ONLY (unsafe)
         BPE_TRY(count_ensure_capacity(ctx, c, bound[bi] / bound_div, std::min(bound[bi], bytes / (SHORT_MAX + 1) + 1) / bound_div));
-        // ordinals of the batch's pretokens -> explicit offsets
-        size_t cnt_b = round_up((bw + 1) * 4, 256), pre_b = round_up((bw + 2) * 8, 256), tmp_b = round_up(scan_tmp_elems_host(bw) * 8, 256);
-        size_t off_b = round_up((bound[bi] + 2) * 4, 256);
-        BPE_TRY(bpe_buf_reserve(ctx, ctx->tmp1, cnt_b + pre_b + tmp_b + off_b));
-        u32 *wcnt = (u32 *)ctx->tmp1.p;
-        u64 *pre = (u64 *)((uint8_t *)ctx->tmp1.p + cnt_b);
-        u64 *stmp = (u64 *)((uint8_t *)ctx->tmp1.p + cnt_b + pre_b);
-        u32 *offs = (u32 *)((uint8_t *)ctx->tmp1.p + cnt_b + pre_b + tmp_b);
-        const u32 *fl = (const u32 *)ctx->flags.p;
-        launch_popc_words(fl + b_lo, bw, wcnt, ctx->sm_count, st);
-        launch_scan_u32(wcnt, bw, pre, stmp, st);
-        const u64 base = b_lo * 32;
-        // (the end of the batch's last pretoken = first start at or after the batch end, or the end of the text)
-        launch_starts_to_offsets(fl, b_lo, b_hi, n, pre, base, offs, bound[bi], ctx->sm_count, st);
         CountTables t = count_tables(ctx);
         if (bound[bi]) {
             static const int cnt_ctas_per_sm = getenv("BPE_COUNT_CTAS") ? std::max(1, atoi(getenv("BPE_COUNT_CTAS"))) : 2;
-            unsigned g2 = (unsigned)std::min<u64>((u64)ctx->sm_count * cnt_ctas_per_sm, (bound[bi] + CNT_TILE - 1) / CNT_TILE);
-            CUDA_TRY(ctx, cudaMemsetAsync(t.counters + 16, 0, 8, st));
+            const u64 c_lo = b_lo * 2, c_hi = std::min(b_hi * 2, (n + 15) / 16);
+            const u64 steps = (c_hi - c_lo + 32 * CNT_WARPS - 1) / (32 * CNT_WARPS);
+            unsigned g2 = (unsigned)std::min<u64>((u64)ctx->sm_count * cnt_ctas_per_sm, std::max<u64>(steps, 1));
             static bool attr_set = false;
             if (!attr_set) { CUDA_TRY(ctx, cudaFuncSetAttribute((void *)k_count_pretokens, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CNT_DYN_SMEM)); attr_set = true; }
-            KLAUNCH(k_count_pretokens, g2, CNT_NT, CNT_DYN_SMEM, st, t, offs, bound[bi], base, own_begin, own_end, trust_end);
+            KLAUNCH(k_count_pretokens, g2, CNT_NT, CNT_DYN_SMEM, st, t, (const u32 *)ctx->flags.p, c_lo, c_hi, n, b_lo * 32, own_begin, own_end, trust_end);
         }
         CUDA_TRY(ctx, cudaGetLastError());
-        if (bi + 1 < n_batches) BPE_TRY(read_counters(ctx, c, 8));
+        if (bi + 1 < n_batches) {
+            BPE_TRY(read_counters(ctx, c, 8));
+            // the hot table: built once enough text has been seen to tell frequent words from rare ones, rebuilt twice with better counts
+            if ((cs->hot_builds == 0 && c[4] >= (16u << 20)) || (cs->hot_builds >= 1 && cs->hot_builds < 3 && c[4] >= 4 * cs->hot_seen))
+                BPE_TRY(count_hot_rebuild(ctx, c));
+        }
         if (prof) { cudaStreamSynchronize(st); fprintf(stderr, "  [batch %llu: %llu pretokens] %.2f ms (tables %llu + %llu slots)\n", (unsigned long long)bi, (unsigned long long)bound[bi], now_ms() - tb0, (unsigned long long)cs->scap, (unsigned long long)cs->lcap); }
     }
+    BPE_TRY(count_hot_flush(ctx));
     BPE_TRY(read_counters(ctx, c, 8));
     if (c[6]) return bpe_set_error(ctx, BPE_ERR_HALO, "a pretoken that starts in the owned range runs past the right halo");
     if (c[3]) return bpe_set_error(ctx, BPE_ERR_CAPACITY, "pretoken table overflow");
