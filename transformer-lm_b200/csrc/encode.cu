@@ -28,6 +28,8 @@
 #define META_POOL_BIT (1ull << 39)
 #define MAX_TOKEN_LEN ((1u << META_LEN_BITS) - 2)
 #define REF_LONG 0x80000000u
+#define REF_MED 0x40000000u
+#define REF_SLOT(r) ((r) & 0x3FFFFFFFu)
 
 // cached value of a pretoken (u64):
 //   tag = v >> 60
@@ -47,6 +49,7 @@
 
 struct __align__(16) SSlot { u64 key, val; };
 struct __align__(32) LSlot { u64 meta, hash, val, pad; };
+struct __align__(32) MSlot { u64 k0, k1, val, pad; };     // pretokens of 8..15 bytes: the 16-byte key IS the token (k0 = bytes 0-7, k1 = bytes 8-14 | len << 56)
 
 struct EncTables {
     const ulonglong2 *mtab; u64 mmask;           // pair -> {key = a<<32|b, (rank << 32) | result symbol}
@@ -54,13 +57,18 @@ struct EncTables {
     const int32_t *sym_to_id;
     // key and cached value share a slot, so the lookup brings the value in with the key (one 32-byte sector)
     SSlot *stab; u64 scap;                       // pretokens of <= 7 bytes: the key is the token (bytes | len << 56)
-    LSlot *ltab; u64 lcap;                       // longer pretokens: (offset:40 | len:24) of the bytes, 64-bit hash filter
+    MSlot *medtab; u64 medcap;                   // 8..15 bytes: one sector per lookup, claimed and published by one 128-bit CAS (as in training)
+    LSlot *ltab; u64 lcap;                       // >= 16 bytes: (offset:40 | len:24) of the bytes, 64-bit hash filter
     const uint8_t *text;                         // payload of the current text arena
     uint8_t *kpool;                              // persistent key bytes of long pretokens
     u32 *ipool;                                  // token ids of pretokens with more than 3 tokens
     u32 *todo;                                   // slots claimed in this batch (REF_LONG = long table)
+    // hot table (see k_enc_hot_build): hot_nb buckets of two 16-byte keys (one sector), their cached values in hval; 0 = none
+    const ulonglong2 *hot; const u64 *hval; u64 hot_nb;
+    const ulonglong2 *sm_img;                    // LK_SM_SLOTS x {key, value}: image of the lookup kernel's shared-memory value cache (or null)
+    u32 *scnt, *mcnt;                            // per-slot hit counters (short, medium) while the cache is being sampled for the hot table (else null)
     // [0]=n_short [1]=n_long [2]=todo count [3]=table overflow [4]=kpool cursor [5]=ipool cursor [6]=pretoken too long
-    // [7]=smallest text offset of a pretoken whose value is a KeyError
+    // [7]=smallest ordinal (in the text of the call) of a pretoken whose value is a KeyError  [8]=n_medium
     u64 *ctr;
 };
 
@@ -110,12 +118,39 @@ __device__ __forceinline__ u64 enc_short_get(const EncTables &t, u64 key) {
                 atomicAdd(&t.ctr[0], 1ull);
                 u64 q = atomicAdd(&t.ctr[2], 1ull);
                 t.todo[q] = (u32)s;
+                if (t.scnt) atomicAdd(&t.scnt[s], 1u);
                 return (VAL_FWD << 60) | (u32)s;
             }
             k = old;
-            if (k == key) return (VAL_FWD << 60) | (u32)s;          // inserted by another thread just now: not computed yet
+            if (k == key) { if (t.scnt) atomicAdd(&t.scnt[s], 1u); return (VAL_FWD << 60) | (u32)s; }   // inserted by another thread just now: not computed yet
         }
-        if (k == key) return kv.y != VAL_NONE ? kv.y : ((VAL_FWD << 60) | (u32)s);
+        if (k == key) { if (t.scnt) atomicAdd(&t.scnt[s], 1u); return kv.y != VAL_NONE ? kv.y : ((VAL_FWD << 60) | (u32)s); }
+        s = (s + 1) & mask;
+    }
+    t.ctr[3] = 1;
+    return 0;
+}
+
+__device__ __forceinline__ u64 enc_med_get(const EncTables &t, u64 k0, u64 k1) {
+    const u64 mask = t.medcap - 1;
+    u64 s = mix64(k0 ^ (k1 * 0x9E3779B97F4A7C15ull)) & mask;
+    for (u64 probes = 0; probes < t.medcap; probes++) {
+        const ulonglong2 kk = *reinterpret_cast<const ulonglong2 *>(&t.medtab[s]);
+        const u64 vv = t.medtab[s].val;          // (same sector; a value read early can only be "not computed yet")
+        u64 a = kk.x, b = kk.y;
+        if ((a | b) == 0) {                      // (k1 carries the length: a real key is never all zero)
+            asm volatile("{\n .reg .b128 c, n, d;\n mov.b128 c, {%3, %4};\n mov.b128 n, {%5, %6};\n atom.global.cas.b128 d, [%2], c, n;\n mov.b128 {%0, %1}, d;\n}"
+                         : "=l"(a), "=l"(b) : "l"(&t.medtab[s]), "l"(0ull), "l"(0ull), "l"(k0), "l"(k1) : "memory");
+            if ((a | b) == 0) {
+                atomicAdd(&t.ctr[8], 1ull);
+                u64 q = atomicAdd(&t.ctr[2], 1ull);
+                t.todo[q] = (u32)s | REF_MED;
+                if (t.mcnt) atomicAdd(&t.mcnt[s], 1u);
+                return (VAL_FWD << 60) | (u32)s | REF_MED;
+            }
+            if (a == k0 && b == k1) { if (t.mcnt) atomicAdd(&t.mcnt[s], 1u); return (VAL_FWD << 60) | (u32)s | REF_MED; }
+        }
+        if (a == k0 && b == k1) { if (t.mcnt) atomicAdd(&t.mcnt[s], 1u); return vv != VAL_NONE ? vv : ((VAL_FWD << 60) | (u32)s | REF_MED); }
         s = (s + 1) & mask;
     }
     t.ctr[3] = 1;
@@ -155,56 +190,177 @@ __device__ __forceinline__ u64 enc_long_get(const EncTables &t, const uint8_t *p
     return 0;
 }
 
-// One thread per pretoken occurrence i of the batch (bytes [base + offs[i], base + offs[i+1])): vals[i] = its cached
-// value when the cache has it, else a forward reference to its slot (resolved after the BPE kernel).
-#ifndef ENC_LOOKUP_PIPELINE
-#define ENC_LOOKUP_PIPELINE 1
-#endif
-__global__ void __launch_bounds__(256) k_enc_lookup(EncTables t, const u32 *__restrict__ offs, u64 n_items, u64 base,
-                                                   u64 *__restrict__ vals) {
-#if ENC_LOOKUP_PIPELINE
-    // software pipeline over the grid-stride loop (as in k_count_pretokens): the first 16 bytes of item i + stride and the
-    // offsets of item i + 2 stride are in flight while item i is looked up
-    const u64 stride = (u64)gridDim.x * blockDim.x;
-    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    bool h0 = i < n_items, h1 = i + stride < n_items;
-    u32 a0 = 0, b0 = 0, a1 = 0, b1 = 0;
-    if (h0) { a0 = offs[i]; b0 = offs[i + 1]; }
-    if (h1) { a1 = offs[i + stride]; b1 = offs[i + stride + 1]; }
-    u64 lo0 = 0, hi0 = 0;
-    if (h0) { const u64 *q = reinterpret_cast<const u64 *>(reinterpret_cast<uintptr_t>(t.text + base + a0) & ~(uintptr_t)7); lo0 = q[0]; hi0 = q[1]; }
-    for (; h0; i += stride) {
-        const bool h2 = i + 2 * stride < n_items;
-        u32 a2 = 0, b2 = 0;
-        if (h2) { a2 = offs[i + 2 * stride]; b2 = offs[i + 2 * stride + 1]; }
-        u64 lo1 = 0, hi1 = 0;
-        if (h1) { const u64 *q = reinterpret_cast<const u64 *>(reinterpret_cast<uintptr_t>(t.text + base + a1) & ~(uintptr_t)7); lo1 = q[0]; hi1 = q[1]; }
-        const u64 pos = base + a0;
-        const u64 len = base + b0 - pos;
-        const uint8_t *p = t.text + pos;
-        u64 v = 0;
-        if (len <= SHORT_MAX) {
-            const u32 sh = (u32)(reinterpret_cast<uintptr_t>(p) & 7u) * 8u;
-            const u64 first8 = sh ? (lo0 >> sh) | (hi0 << (64u - sh)) : lo0;
-            v = enc_short_get(t, (first8 & low_bytes_mask((u32)len)) | ((u64)len << 56));   // = short_key(p, len)
-        } else if (len <= MAX_TOKEN_LEN) v = enc_long_get(t, p, (u32)len, pos);
-        else t.ctr[6] = 1;
-        vals[i] = v;
-        a0 = a1; b0 = b1; lo0 = lo1; hi0 = hi1; h0 = h1;
-        a1 = a2; b1 = b2; h1 = h2;
+// ---- hot table ---------------------------------------------------------------------------------------------------------
+// A probe into the cache tables is a random 32-byte sector with a 128-byte L2 line to itself (they are sized for the worst case and
+// mostly empty): L2 keeps ~0.5 M such lines, and a lookup that misses it runs at the DRAM random-access rate (~40 G/s on B200,
+// tools/bench_l2_random.cu) -- which is what bulk encoding ran at.  So the pretokens of <= 15 bytes that the first big batch after a
+// cache reset looked up most often (per-slot hit counters, that batch only) are copied, with their values, into a dense table that
+// stays in L2: a bucket is one sector holding two 16-byte keys (k0 = bytes 0-7, k1 = bytes 8-14 | len << 56; k1 = 0 and k0 = the
+// short-table key for <= 7 bytes), the values sit in an array beside it.  A key whose bucket is full simply stays with the big
+// tables, so a probe is exactly one sector.  Values are immutable once computed, so the copy never goes stale.
+__device__ __forceinline__ u64 enc_hot_bucket(u64 nb, u64 k0, u64 k1) { return ((mix64(k0 ^ (k1 * 0x9E3779B97F4A7C15ull)) >> 32) * nb) >> 32; }
+__device__ __forceinline__ bool enc_hot_get(const EncTables &t, u64 k0, u64 k1, u64 *v) {
+    const u64 b = enc_hot_bucket(t.hot_nb, k0, k1);
+    const ulonglong2 a0 = __ldg(&t.hot[2 * b]), a1 = __ldg(&t.hot[2 * b + 1]);
+    const bool m0 = a0.x == k0 && a0.y == k1, m1 = a1.x == k0 && a1.y == k1;
+    if (!(m0 || m1)) return false;
+    *v = __ldg(&t.hval[2 * b + (m1 ? 1 : 0)]);
+    return true;
+}
+
+// ---- lookup: straight from the text and its start bits -------------------------------------------------------------------
+// vals[ordinal of the pretoken in the batch] = its cached value when the cache has it, else a forward reference to its slot
+// (resolved after the BPE kernels).  Same walk as the count stage of training (train.cu, k_count_pretokens): a lane owns one
+// 16-byte chunk -- its 32-byte text window in registers, a 64-bit window of start bits -- and walks the chunk's start bits; a warp
+// takes 32 consecutive chunks per step.  Three levels:
+//   1. pretokens of <= 7 bytes: the CTA's shared-memory copy of the value cache image (the ~3 000 most looked-up short pretokens
+//      of the sampled batch, read-only: LDS and compare, no global traffic) -- six lookups in ten end here;
+//   2. what misses there and pretokens of 8..15 bytes go to the warp's queue and are drained in whole groups of 64 with all lanes:
+//      one probe of the hot table (one sector, L2-resident), value from the array beside it;
+//   3. what misses that, and pretokens of >= 16 bytes: the big tables (lookup or claim, enc_short_get / enc_long_get).
+#define LK_NT 1024
+#define LK_WARPS (LK_NT / 32u)
+#define LK_SM_LG 12
+#define LK_SM_SLOTS (1u << LK_SM_LG)
+#define LK_SM_PROBES 2u
+#define LK_QCAP 96u                              // entries of the warp's key queue
+#define LK_QDRAIN 64u                            // drained when it reaches this (a round of the bit loop adds <= 32)
+#define LK_QL_CAP 64u
+#define LK_QL_DRAIN 32u
+#define LK_WARP_SMEM (LK_QCAP * 24u + LK_QL_CAP * 12u)
+#define LK_DYN_SMEM ((size_t)LK_SM_SLOTS * 16 + (size_t)LK_WARPS * LK_WARP_SMEM)
+__device__ __forceinline__ u32 enc_sm_slot(u64 key) { return (((u32)key ^ (u32)(key >> 32)) * 0x9E3779B1u) >> (32 - LK_SM_LG); }
+
+// queues of a warp: qe = keys (k0, k1; k1 = 0: a short pretoken, k0 its key) with qx = (ordinal, offset from base);
+// ql = long pretokens (offset from base | len << 32) with qlo = ordinal
+struct LookupQueues { ulonglong2 *qe; uint2 *qx; u64 *ql; u32 *qlo; u32 n, nl; };
+
+__device__ __forceinline__ u64 enc_queued_get(const EncTables &t, ulonglong2 k, uint2 x, u64 base) {
+    (void)x; (void)base;
+    return k.y == 0 ? enc_short_get(t, k.x) : enc_med_get(t, k.x, k.y);
+}
+__device__ __forceinline__ void lookup_drain(const EncTables &t, LookupQueues &q, u64 base, u64 *__restrict__ vals, u32 lane, bool all) {
+    const u32 dn = all ? q.n : q.n & ~63u;
+    __syncwarp();
+    for (u32 e0 = 0; e0 < dn; e0 += 64u) {
+        const bool ha = e0 + lane < dn, hb = e0 + 32u + lane < dn;
+        ulonglong2 ka = make_ulonglong2(0, 0), kb = ka;
+        uint2 xa = make_uint2(0, 0), xb = xa;
+        if (ha) { ka = q.qe[e0 + lane]; xa = q.qx[e0 + lane]; }
+        if (hb) { kb = q.qe[e0 + 32u + lane]; xb = q.qx[e0 + 32u + lane]; }
+        bool ta = ha, tb = hb;                   // still to be looked up in the big tables
+        u64 va = 0, vb = 0;
+        if (t.hot_nb) {
+            const u64 ba = enc_hot_bucket(t.hot_nb, ka.x, ka.y), bb = enc_hot_bucket(t.hot_nb, kb.x, kb.y);
+            ulonglong2 a0 = make_ulonglong2(0, 0), a1 = a0, b0 = a0, b1 = a0;
+            if (ha) { a0 = __ldg(&t.hot[2 * ba]); a1 = __ldg(&t.hot[2 * ba + 1]); }
+            if (hb) { b0 = __ldg(&t.hot[2 * bb]); b1 = __ldg(&t.hot[2 * bb + 1]); }
+            if (ha) {
+                const bool m0 = a0.x == ka.x && a0.y == ka.y, m1 = a1.x == ka.x && a1.y == ka.y;
+                if (m0 || m1) { va = __ldg(&t.hval[2 * ba + (m1 ? 1 : 0)]); ta = false; }
+            }
+            if (hb) {
+                const bool m0 = b0.x == kb.x && b0.y == kb.y, m1 = b1.x == kb.x && b1.y == kb.y;
+                if (m0 || m1) { vb = __ldg(&t.hval[2 * bb + (m1 ? 1 : 0)]); tb = false; }
+            }
+        }
+        if (ta) va = enc_queued_get(t, ka, xa, base);
+        if (tb) vb = enc_queued_get(t, kb, xb, base);
+        if (ha) __stcs(&vals[xa.x], va);         // (streaming stores: the value array is written once and read once -- it must not push the hot table out of L2)
+        if (hb) __stcs(&vals[xb.x], vb);
     }
-#else
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += (u64)gridDim.x * blockDim.x) {
-        const u64 pos = base + offs[i];
-        const u64 len = base + offs[i + 1] - pos;
-        const uint8_t *p = t.text + pos;
-        u64 v = 0;
-        if (len <= SHORT_MAX) v = enc_short_get(t, short_key(p, (u32)len));
-        else if (len <= MAX_TOKEN_LEN) v = enc_long_get(t, p, (u32)len, pos);
-        else t.ctr[6] = 1;
-        vals[i] = v;
+    for (u32 e = lane; e < q.nl; e += 32u) {
+        const u64 ent = q.ql[e];
+        const u64 pos = base + (u32)ent;
+        __stcs(&vals[q.qlo[e]], enc_long_get(t, t.text + pos, (u32)(ent >> 32), pos));
     }
-#endif
+    q.nl = 0;
+    // the remainder (< 64 keys) moves to the front
+    const u32 r = q.n - dn;
+    ulonglong2 k0 = make_ulonglong2(0, 0), k1 = k0; uint2 x0 = make_uint2(0, 0), x1 = x0;
+    if (dn && lane < r) { k0 = q.qe[dn + lane]; x0 = q.qx[dn + lane]; }
+    if (dn && lane + 32u < r) { k1 = q.qe[dn + 32u + lane]; x1 = q.qx[dn + 32u + lane]; }
+    __syncwarp();
+    if (dn && lane < r) { q.qe[lane] = k0; q.qx[lane] = x0; }
+    if (dn && lane + 32u < r) { q.qe[32u + lane] = k1; q.qx[32u + lane] = x1; }
+    q.n = r;
+    __syncwarp();
+}
+
+// chunks [c_lo, c_hi) (16 bytes each, absolute positions 16 c; c_lo even); pre[w] = ordinal of the first pretoken of flag word w
+// (pre and flags are indexed by absolute word), ord0 = ordinal of the batch's first pretoken, base = 16 c_lo
+__global__ void __launch_bounds__(LK_NT, 1) k_enc_lookup(EncTables t, const u32 *__restrict__ flags, const u64 *__restrict__ pre, u64 ord0,
+                                                        u64 c_lo, u64 c_hi, u64 n, u64 base, u64 *__restrict__ vals) {
+    extern __shared__ __align__(16) unsigned char lk_smem[];
+    const u32 lane = lane_id(), warp = threadIdx.x >> 5;
+    ulonglong2 *s_kv = reinterpret_cast<ulonglong2 *>(lk_smem);                            // {key, value} image of the value cache
+    unsigned char *wq = lk_smem + (size_t)LK_SM_SLOTS * 16 + (size_t)warp * LK_WARP_SMEM;
+    LookupQueues q;
+    q.qe = reinterpret_cast<ulonglong2 *>(wq); q.qx = reinterpret_cast<uint2 *>(wq + LK_QCAP * 16u);
+    q.ql = reinterpret_cast<u64 *>(wq + LK_QCAP * 24u); q.qlo = reinterpret_cast<u32 *>(wq + LK_QCAP * 24u + LK_QL_CAP * 8u);
+    q.n = q.nl = 0;
+    for (u32 i = threadIdx.x; i < LK_SM_SLOTS; i += LK_NT) s_kv[i] = t.sm_img ? t.sm_img[i] : make_ulonglong2(0, 0);
+    __syncthreads();
+    const u32 lt = (1u << lane) - 1u;
+    const u64 stride = (u64)gridDim.x * LK_WARPS * 32u;
+    const u64 n_fw = (n + 31) >> 5;              // flag words that hold bits of the text
+    u64 c = c_lo + ((u64)blockIdx.x * LK_WARPS + warp) * 32u + lane;
+    for (; __any_sync(0xffffffffu, c < c_hi); c += stride) {
+        const bool live = c < c_hi;
+        const u64 p0 = c * 16u;
+        uint4 A = make_uint4(0, 0, 0, 0), B = A; u32 f0 = 0, f1 = 0; u64 ordw = 0;
+        if (live) {
+            const uint4 *tp = reinterpret_cast<const uint4 *>(t.text + p0);
+            A = __ldcs(tp); B = __ldcs(tp + 1);
+            const u64 w = c >> 1; f0 = __ldcs(flags + w); f1 = w + 1 < n_fw ? __ldcs(flags + w + 1) : 0u; ordw = __ldcs(pre + w);
+        }
+        const u32 W0 = A.x, W1 = A.y, W2 = A.z, W3 = A.w, W4 = B.x, W5 = B.y, W6 = B.z, W7 = B.w;
+        u64 F = (((u64)f1 << 32) | f0) >> (u32)(p0 & 16u);           // bit i: a pretoken starts at byte p0 + i (>= 48 bits)
+        if (p0 + 64 > n) F = p0 < n ? F & ((1ull << (n - p0)) - 1ull) : 0ull;   // bits past the end of the text do not count
+        const u32 mall = live ? (u32)F & 0xFFFFu : 0u;
+        const u32 ordc = (u32)(ordw - ord0) + ((c & 1u) ? __popc(f0 & 0xFFFFu) : 0u);   // ordinal of the chunk's first pretoken in the batch
+        u32 m = mall;
+        while (__any_sync(0xffffffffu, m != 0)) {
+            const bool act = m != 0;
+            const u32 j = act ? __ffs(m) - 1u : 0u;
+            m &= m - 1u;
+            const u32 ord = ordc + __popc(mall & ((1u << j) - 1u));
+            const u64 rest = F >> (j + 1u);
+            u32 len = (u32)__ffsll((long long)rest);
+            if (act && len == 0) {               // no further start in the window: a long pretoken, or the last one of the text
+                const u64 e = flags_next_start(flags, p0 + j + 1, n) - (p0 + j);
+                if (e > MAX_TOKEN_LEN) { t.ctr[6] = 1; len = MAX_TOKEN_LEN; } else len = (u32)e;
+            }
+            // bytes j .. j + 15 of the 32-byte window
+            const u32 qd = j >> 2, sh = (j & 3u) * 8u;
+            const bool q2 = qd & 2u, q1 = qd & 1u;
+            const u32 X0 = q2 ? W2 : W0, X1 = q2 ? W3 : W1, X2 = q2 ? W4 : W2, X3 = q2 ? W5 : W3, X4 = q2 ? W6 : W4, X5 = q2 ? W7 : W5;
+            const u32 Y0 = q1 ? X1 : X0, Y1 = q1 ? X2 : X1, Y2 = q1 ? X3 : X2, Y3 = q1 ? X4 : X3, Y4 = q1 ? X5 : X4;
+            const u64 k0 = (u64)__funnelshift_r(Y0, Y1, sh) | ((u64)__funnelshift_r(Y1, Y2, sh) << 32);
+            const u64 k1 = (u64)__funnelshift_r(Y2, Y3, sh) | ((u64)__funnelshift_r(Y3, Y4, sh) << 32);
+            bool q_s = act && len <= SHORT_MAX;
+            const bool q_m = act && len > SHORT_MAX && len <= 15u, q_l = act && len > 15u;
+            const u64 key = (k0 & low_bytes_mask(len)) | ((u64)len << 56);               // (short pretokens)
+            if (q_s) {
+                u32 slot = enc_sm_slot(key);
+#pragma unroll
+                for (u32 pr = 0; pr < LK_SM_PROBES; pr++) {
+                    const ulonglong2 kv = s_kv[slot];
+                    if (kv.x == key) { __stcs(&vals[ord], kv.y); q_s = false; break; }
+                    slot = (slot + 1) & (LK_SM_SLOTS - 1);
+                }
+            }
+            const u32 me = __ballot_sync(0xffffffffu, q_s || q_m), ml = __ballot_sync(0xffffffffu, q_l);
+            const u32 qi = q.n + __popc(me & lt);
+            if (q_s) q.qe[qi] = make_ulonglong2(key, 0ull);
+            if (q_m) q.qe[qi] = make_ulonglong2(k0, (len > 8 ? k1 & low_bytes_mask(len - 8) : 0ull) | ((u64)len << 56));
+            if (q_s || q_m) q.qx[qi] = make_uint2(ord, (u32)(p0 + j - base));
+            if (q_l) { const u32 li = q.nl + __popc(ml & lt); q.ql[li] = (p0 + j - base) | ((u64)len << 32); q.qlo[li] = ord; }
+            q.n += __popc(me); q.nl += __popc(ml);
+            if (q.n >= LK_QDRAIN || q.nl >= LK_QL_DRAIN) lookup_drain(t, q, base, vals, lane, false);
+        }
+    }
+    lookup_drain(t, q, base, vals, lane, true);
 }
 
 // ---- BPE of the queued pretokens: one warp each ----------------------------------------------------------
@@ -260,10 +416,14 @@ __global__ void __launch_bounds__(BPT_NT) k_enc_bpe_short(EncTables t, u64 n_tod
     u32 *sym = s_sym[threadIdx.x], *rk = s_ids[threadIdx.x];
     for (u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x; q < n_todo; q += (u64)gridDim.x * blockDim.x) {
         const u32 ref = t.todo[q];
-        const bool is_long = ref & REF_LONG;
-        const u32 slot = ref & ~REF_LONG;
+        const bool is_long = ref & REF_LONG, is_med = ref & REF_MED;
+        const u32 slot = REF_SLOT(ref);
         u32 n;
-        if (is_long) {
+        if (is_med) {
+            const u64 k0 = t.medtab[slot].k0, k1 = t.medtab[slot].k1;
+            n = (u32)(k1 >> 56);
+            for (u32 i = 0; i < n; i++) sym[i] = (u32)(((i < 8 ? k0 >> (8 * i) : k1 >> (8 * (i - 8)))) & 0xFFu);
+        } else if (is_long) {
             const u64 m = t.ltab[slot].meta;
             n = (u32)(m & META_LEN_MASK);
             if (n > BPT_MAX) continue;           // the warp kernel's
@@ -315,7 +475,7 @@ __global__ void __launch_bounds__(BPT_NT) k_enc_bpe_short(EncTables t, u64 n_tod
                 value = (VAL_EXT << 60) | (off << 24) | n;
             }
         }
-        if (is_long) t.ltab[slot].val = value; else t.stab[slot].val = value;
+        if (is_med) t.medtab[slot].val = value; else if (is_long) t.ltab[slot].val = value; else t.stab[slot].val = value;
     }
 }
 
@@ -326,9 +486,9 @@ __global__ void __launch_bounds__(256) k_enc_bpe(EncTables t, u64 n_todo) {
     for (u64 q = gwarp; q < n_todo; q += nwarps) {
         const u32 ref = t.todo[q];
         const bool is_long = ref & REF_LONG;
-        const u32 slot = ref & ~REF_LONG;
+        const u32 slot = REF_SLOT(ref);
         u32 len; const uint8_t *p = nullptr; u64 skey = 0;
-        if (!is_long) continue;                  // (<= 7 bytes: k_enc_bpe_short)
+        if (!is_long) continue;                  // (<= 15 bytes: k_enc_bpe_short)
         if (is_long) {
             u64 m = t.ltab[slot].meta;
             len = (u32)(m & META_LEN_MASK);
@@ -422,7 +582,7 @@ __global__ void __launch_bounds__(256) k_enc_bpe(EncTables t, u64 n_todo) {
 }
 
 __device__ __forceinline__ u64 enc_value(const EncTables &t, u32 ref) {
-    return (ref & REF_LONG) ? t.ltab[ref & ~REF_LONG].val : t.stab[ref].val;
+    return (ref & REF_LONG) ? t.ltab[REF_SLOT(ref)].val : (ref & REF_MED) ? t.medtab[REF_SLOT(ref)].val : t.stab[ref].val;
 }
 __device__ __forceinline__ u32 value_count(u64 v) {
     u32 tag = VAL_TAG(v);
@@ -448,7 +608,7 @@ __device__ __forceinline__ u64 warp_sum_u64(u64 v) {
     return v;
 }
 template <typename OutT, bool kEmit>
-__global__ void __launch_bounds__(SE_NT) k_enc_scan_emit(EncTables t, u64 *__restrict__ vals, const u32 *__restrict__ offs, u64 n_items, u64 base,
+__global__ void __launch_bounds__(SE_NT) k_enc_scan_emit(EncTables t, const u64 *__restrict__ vals, u64 n_items, u64 ord_base,
                                                         u64 *tile_state, u32 *ticket, OutT *__restrict__ out, u64 out_base, u64 cap,
                                                         u64 *__restrict__ total_out) {
     __shared__ u32 s_tile;
@@ -461,12 +621,12 @@ __global__ void __launch_bounds__(SE_NT) k_enc_scan_emit(EncTables t, u64 *__res
     u64 v[SE_ITEMS];
     u32 sum = 0;
 #pragma unroll
-    for (u32 k = 0; k < SE_ITEMS; k++) v[k] = first + k < n_items ? vals[first + k] : 0;
+    for (u32 k = 0; k < SE_ITEMS; k++) v[k] = first + k < n_items ? __ldcs(&vals[first + k]) : 0;
 #pragma unroll
     for (u32 k = 0; k < SE_ITEMS; k++) {
         if (first + k >= n_items) continue;
-        if (VAL_TAG(v[k]) == VAL_FWD) { v[k] = enc_value(t, (u32)v[k]); vals[first + k] = v[k]; }   // computed by the BPE kernels meanwhile
-        if (VAL_TAG(v[k]) == VAL_ERR) atomicMin(&t.ctr[7], base + offs[first + k]);               // KeyError: smallest text offset
+        if (VAL_TAG(v[k]) == VAL_FWD) v[k] = enc_value(t, (u32)v[k]);                             // computed by the BPE kernels meanwhile
+        if (VAL_TAG(v[k]) == VAL_ERR) atomicMin(&t.ctr[7], ord_base + first + k);                 // KeyError: the first failing pretoken in text order
         sum += value_count(v[k]);
     }
     u32 tot;
@@ -519,7 +679,7 @@ __global__ void __launch_bounds__(SE_NT) k_enc_scan_emit(EncTables t, u64 *__res
             }
         }
         __syncthreads();
-        for (u32 j = threadIdx.x; j < tot; j += SE_NT) { const u64 d = tile_dst + j; if (d < cap) out[d] = (OutT)s_ids[j]; }
+        for (u32 j = threadIdx.x; j < tot; j += SE_NT) { const u64 d = tile_dst + j; if (d < cap) __stcs(&out[d], (OutT)s_ids[j]); }
         return;
     }
     u64 dst = tile_dst + ex;
@@ -532,6 +692,78 @@ __global__ void __launch_bounds__(SE_NT) k_enc_scan_emit(EncTables t, u64 *__res
             const u32 *src = t.ipool + ((v[k] >> 24) & 0xFFFFFFFFFull);
             const u32 c = (u32)(v[k] & 0xFFFFFFu);
             for (u32 q = 0; q < c; q++) { if (dst < cap) out[dst] = (OutT)src[q]; dst++; }
+        }
+    }
+}
+
+// ---- hot table: histogram of the sampled hit counts, build ----------------------------------------------------------
+#define ENC_HOT_HIST 64
+__global__ void __launch_bounds__(256) k_enc_hot_hist(EncTables t, u64 *__restrict__ hist /* [ENC_HOT_HIST] */) {
+    __shared__ u32 s_h[ENC_HOT_HIST];
+    if (threadIdx.x < ENC_HOT_HIST) s_h[threadIdx.x] = 0;
+    __syncthreads();
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < t.scap + t.medcap; i += (u64)gridDim.x * blockDim.x) {
+        const u32 c = i < t.scap ? t.scnt[i] : t.mcnt[i - t.scap];
+        if (c) atomicAdd(&s_h[c < ENC_HOT_HIST ? c : ENC_HOT_HIST - 1], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < ENC_HOT_HIST && s_h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (u64)s_h[threadIdx.x]);
+}
+// every cached pretoken of <= 15 bytes looked up at least `thresh` times whose value is computed: into its bucket if a slot is free
+__global__ void __launch_bounds__(256) k_enc_hot_build(EncTables t, ulonglong2 *__restrict__ hot, u64 *__restrict__ hval, u64 nb, u32 thresh) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < t.scap + t.medcap; i += (u64)gridDim.x * blockDim.x) {
+        u64 k0, k1, v;
+        if (i < t.scap) {
+            if (t.scnt[i] < thresh) continue;
+            k0 = t.stab[i].key; k1 = 0; v = t.stab[i].val;
+            if (k0 == 0) continue;
+        } else {
+            const u64 s = i - t.scap;
+            if (t.mcnt[s] < thresh) continue;
+            k0 = t.medtab[s].k0; k1 = t.medtab[s].k1; v = t.medtab[s].val;
+            if ((k0 | k1) == 0) continue;
+        }
+        if (v == VAL_NONE || VAL_TAG(v) == VAL_FWD) continue;
+        const u64 b = enc_hot_bucket(nb, k0, k1);
+        u64 x, y; u32 w = 0;
+        asm volatile("{\n .reg .b128 c, n, d;\n mov.b128 c, {%3, %4};\n mov.b128 n, {%5, %6};\n atom.global.cas.b128 d, [%2], c, n;\n mov.b128 {%0, %1}, d;\n}"
+                     : "=l"(x), "=l"(y) : "l"(&hot[2 * b]), "l"(0ull), "l"(0ull), "l"(k0), "l"(k1) : "memory");
+        if ((x | y) != 0) {
+            w = 1;
+            asm volatile("{\n .reg .b128 c, n, d;\n mov.b128 c, {%3, %4};\n mov.b128 n, {%5, %6};\n atom.global.cas.b128 d, [%2], c, n;\n mov.b128 {%0, %1}, d;\n}"
+                         : "=l"(x), "=l"(y) : "l"(&hot[2 * b + 1]), "l"(0ull), "l"(0ull), "l"(k0), "l"(k1) : "memory");
+        }
+        if ((x | y) == 0) hval[2 * b + w] = v;
+    }
+}
+
+// ---- image of the lookup kernel's shared-memory value cache: the most looked-up short pretokens of the sampled batch ----
+__device__ __forceinline__ u32 log_bucket(u32 c) {                   // 8 buckets per power of two
+    if (c < 8) return c;
+    const u32 lz = 31u - __clz(c);
+    return (lz - 2u) * 8u + ((c >> (lz - 3u)) & 7u);
+}
+__global__ void __launch_bounds__(256) k_enc_sm_hist(EncTables t, u64 *__restrict__ hist /* [256] */) {
+    __shared__ u32 s_h[256];
+    s_h[threadIdx.x] = 0;
+    __syncthreads();
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < t.scap; i += (u64)gridDim.x * blockDim.x) {
+        const u32 c = t.scnt[i];
+        if (c) atomicAdd(&s_h[log_bucket(c)], 1u);
+    }
+    __syncthreads();
+    if (s_h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (u64)s_h[threadIdx.x]);
+}
+__global__ void __launch_bounds__(256) k_enc_sm_build(EncTables t, ulonglong2 *__restrict__ img, u32 min_bucket) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < t.scap; i += (u64)gridDim.x * blockDim.x) {
+        const u32 c = t.scnt[i];
+        if (!c || log_bucket(c) < min_bucket) continue;
+        const u64 key = t.stab[i].key, v = t.stab[i].val;
+        if (key == 0 || v == VAL_NONE || VAL_TAG(v) == VAL_FWD) continue;
+        u32 slot = enc_sm_slot(key);
+        for (u32 pr = 0; pr < LK_SM_PROBES; pr++) {
+            if (atomicCAS(&img[slot].x, 0ull, key) == 0ull) { img[slot].y = v; break; }
+            slot = (slot + 1) & (LK_SM_SLOTS - 1);
         }
     }
 }
@@ -565,7 +797,20 @@ __global__ void __launch_bounds__(256) k_enc_rehash_long(const LSlot *__restrict
     }
 }
 
-// empty tables: short {0, VAL_NONE}, long {META_EMPTY, 0, VAL_NONE, 0}
+__global__ void __launch_bounds__(256) k_enc_rehash_med(const MSlot *__restrict__ otab, u64 ocap, EncTables t) {
+    const u64 mask = t.medcap - 1;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < ocap; i += (u64)gridDim.x * blockDim.x) {
+        const u64 k0 = otab[i].k0, k1 = otab[i].k1;
+        if ((k0 | k1) == 0) continue;
+        u64 s = mix64(k0 ^ (k1 * 0x9E3779B97F4A7C15ull)) & mask;
+        for (;;) {                               // keys are unique: claim the k1 word (never 0 for a real key), then fill in
+            if (t.medtab[s].k1 == 0 && atomicCAS(&t.medtab[s].k1, 0ull, k1) == 0ull) { t.medtab[s].k0 = k0; t.medtab[s].val = otab[i].val; break; }
+            s = (s + 1) & mask;
+        }
+    }
+}
+
+// empty tables: short {0, VAL_NONE}, medium {0, 0, VAL_NONE, 0}, long {META_EMPTY, 0, VAL_NONE, 0}
 __global__ void __launch_bounds__(256) k_enc_clear_tables(EncTables t) {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < t.scap; i += (u64)gridDim.x * blockDim.x) {
         *reinterpret_cast<ulonglong2 *>(&t.stab[i]) = make_ulonglong2(0ull, VAL_NONE);
@@ -573,6 +818,10 @@ __global__ void __launch_bounds__(256) k_enc_clear_tables(EncTables t) {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < t.lcap; i += (u64)gridDim.x * blockDim.x) {
         ulonglong2 *q = reinterpret_cast<ulonglong2 *>(&t.ltab[i]);
         q[0] = make_ulonglong2(META_EMPTY, 0ull); q[1] = make_ulonglong2(VAL_NONE, 0ull);
+    }
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < t.medcap; i += (u64)gridDim.x * blockDim.x) {
+        ulonglong2 *q = reinterpret_cast<ulonglong2 *>(&t.medtab[i]);
+        q[0] = make_ulonglong2(0ull, 0ull); q[1] = make_ulonglong2(VAL_NONE, 0ull);
     }
 }
 
@@ -598,6 +847,19 @@ __global__ void k_enc_insert_specials(EncTables t, const u32 *__restrict__ sp_of
             u64 old = atomicCAS(&t.stab[s].key, 0ull, key);
             if (old == 0) { atomicAdd(&t.ctr[0], 1ull); t.stab[s].val = v; return; }
             if (old == key) return;              // duplicate special
+            s = (s + 1) & mask;
+        }
+    } else if (len <= 15) {
+        u64 k0 = 0, k1 = (u64)len << 56;
+        for (u32 k = 0; k < len; k++) { if (k < 8) k0 |= (u64)p[k] << (8 * k); else k1 |= (u64)p[k] << (8 * (k - 8)); }
+        const u64 mask = t.medcap - 1;
+        u64 s = mix64(k0 ^ (k1 * 0x9E3779B97F4A7C15ull)) & mask;
+        for (;;) {
+            u64 a, b;
+            asm volatile("{\n .reg .b128 c, n, d;\n mov.b128 c, {%3, %4};\n mov.b128 n, {%5, %6};\n atom.global.cas.b128 d, [%2], c, n;\n mov.b128 {%0, %1}, d;\n}"
+                         : "=l"(a), "=l"(b) : "l"(&t.medtab[s]), "l"(0ull), "l"(0ull), "l"(k0), "l"(k1) : "memory");
+            if ((a | b) == 0) { atomicAdd(&t.ctr[8], 1ull); t.medtab[s].val = v; return; }
+            if (a == k0 && b == k1) return;      // duplicate special
             s = (s + 1) & mask;
         }
     } else {
@@ -649,9 +911,12 @@ struct bpe_tok {
     std::vector<uint8_t> sym_blob_h; std::vector<u64> sym_offs_h;
     u32 sp_max_len = 0;
     // pretoken cache
-    DevBuf stab, ltab, kpool, ipool, todo, ctr;
-    u64 scap = 0, lcap = 0;
+    DevBuf stab, medtab, ltab, kpool, ipool, todo, ctr;
+    u64 scap = 0, medcap = 0, lcap = 0;
     bool cache_ready = false;
+    DevBuf hot, samp, sm_img;                    // hot table (keys then values); sampling counters of the batch that feeds it; shared-memory cache image
+    u64 hot_nb = 0;
+    bool hot_built = false, sampling = false;
     std::vector<uint8_t> key_error;              // bytes of the last KeyError key
 };
 
@@ -676,20 +941,25 @@ static EncTables enc_tables(bpe_tok *tok) {
     t.mtab = (const ulonglong2 *)tok->mtab.p; t.mmask = tok->mcap - 1;
     t.mpairs = (const int32_t *)tok->mpairs.p; t.sym_to_id = (const int32_t *)tok->sym_to_id.p;
     t.stab = (SSlot *)tok->stab.p; t.scap = tok->scap;
+    t.medtab = (MSlot *)tok->medtab.p; t.medcap = tok->medcap;
     t.ltab = (LSlot *)tok->ltab.p; t.lcap = tok->lcap;
     t.text = tok->ctx->text.p ? (const uint8_t *)tok->ctx->text.p + BPE_PAD : nullptr;
     t.kpool = (uint8_t *)tok->kpool.p; t.ipool = (u32 *)tok->ipool.p; t.todo = (u32 *)tok->todo.p;
     t.ctr = (u64 *)tok->ctr.p;
+    t.hot = (const ulonglong2 *)tok->hot.p; t.hot_nb = tok->hot_nb; t.hval = (const u64 *)((const ulonglong2 *)tok->hot.p + 2 * tok->hot_nb);
+    t.sm_img = tok->hot_built ? (const ulonglong2 *)tok->sm_img.p : nullptr;
+    t.scnt = tok->sampling ? (u32 *)tok->samp.p : nullptr; t.mcnt = tok->sampling ? (u32 *)tok->samp.p + tok->scap : nullptr;
     return t;
 }
 
-static int cache_tables_alloc(bpe_tok *tok, u64 scap, u64 lcap) {
+static int cache_tables_alloc(bpe_tok *tok, u64 scap, u64 medcap, u64 lcap) {
     bpe_ctx *ctx = tok->ctx;
     BPE_TRY(alloc_exact_e(ctx, tok->stab, scap * sizeof(SSlot)));
+    BPE_TRY(alloc_exact_e(ctx, tok->medtab, medcap * sizeof(MSlot)));
     BPE_TRY(alloc_exact_e(ctx, tok->ltab, lcap * sizeof(LSlot)));
-    tok->scap = scap; tok->lcap = lcap;
+    tok->scap = scap; tok->medcap = medcap; tok->lcap = lcap;
     EncTables t = enc_tables(tok);
-    KLAUNCH(k_enc_clear_tables, (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (std::max(scap, lcap) + 255) / 256), 256, 0, ctx->stream, t);
+    KLAUNCH(k_enc_clear_tables, (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (std::max(scap, std::max(medcap, lcap)) + 255) / 256), 256, 0, ctx->stream, t);
     CUDA_TRY(ctx, cudaGetLastError());
     return BPE_OK;
 }
@@ -699,14 +969,14 @@ static int cache_reset(bpe_tok *tok) {
     bpe_ctx *ctx = tok->ctx;
     cudaStream_t st = ctx->stream;
     BPE_TRY(bpe_buf_reserve(ctx, tok->ctr, 64 * sizeof(u64)));
-    BPE_TRY(cache_tables_alloc(tok, 1 << 16, 1 << 14));
+    BPE_TRY(cache_tables_alloc(tok, 1 << 16, 1 << 14, 1 << 14));
     size_t spb = tok->sp_blob_h.size();
     BPE_TRY(bpe_buf_reserve(ctx, tok->kpool, std::max<size_t>(spb, 1) + (1 << 20)));
     BPE_TRY(bpe_buf_reserve(ctx, tok->ipool, ((size_t)tok->n_sp + (1 << 18)) * 4));
     u64 *host = (u64 *)ctx->pinned;
-    for (int i = 0; i < 8; i++) host[i] = 0;
+    for (int i = 0; i < 16; i++) host[i] = 0;
     host[4] = spb; host[7] = ~0ull;
-    CUDA_TRY(ctx, cudaMemcpyAsync(tok->ctr.p, host, 64, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(tok->ctr.p, host, 128, cudaMemcpyHostToDevice, st));
     if (spb) CUDA_TRY(ctx, cudaMemcpyAsync(tok->kpool.p, tok->sp_blob_h.data(), spb, cudaMemcpyHostToDevice, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));    // host[] is reused below
     if (tok->n_sp > 0) {
@@ -715,6 +985,53 @@ static int cache_reset(bpe_tok *tok) {
         CUDA_TRY(ctx, cudaGetLastError());
     }
     tok->cache_ready = true;
+    bpe_buf_free(ctx, tok->hot); bpe_buf_free(ctx, tok->sm_img); tok->hot_nb = 0; tok->hot_built = false; tok->sampling = false;
+    return BPE_OK;
+}
+
+// Build the hot table from the hit counters of the batch just looked up (values are final: the BPE kernels have run).
+#define ENC_HOT_MIN_BATCH (8ull << 20)           // pretokens a batch needs for its hit counts to mean something
+static int cache_build_hot(bpe_tok *tok) {
+    bpe_ctx *ctx = tok->ctx;
+    cudaStream_t st = ctx->stream;
+    static const u64 hot_max = getenv("BPE_ENC_HOT_MAX") ? (u64)atoll(getenv("BPE_ENC_HOT_MAX")) : (1ull << 20);
+    EncTables t = enc_tables(tok);               // (sampling still on: t.scnt / t.lcnt point at the counters)
+    tok->sampling = false; tok->hot_built = true;
+    if (!hot_max) { bpe_buf_free(ctx, tok->samp); return BPE_OK; }
+    u64 *hist = (u64 *)ctx->scratch.p + 16;
+    CUDA_TRY(ctx, cudaMemsetAsync(hist, 0, ENC_HOT_HIST * sizeof(u64), st));
+    const unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * 16, (tok->scap + tok->medcap + 255) / 256);
+    KLAUNCH(k_enc_hot_hist, grid, 256, 0, st, t, hist);
+    u64 *host = (u64 *)ctx->pinned;
+    CUDA_TRY(ctx, cudaMemcpyAsync(host, hist, ENC_HOT_HIST * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    u64 n_hot = 0, thresh = ENC_HOT_HIST;
+    for (int k = ENC_HOT_HIST - 1; k >= 2; k--) { if (n_hot + host[k] > hot_max) break; n_hot += host[k]; thresh = (u64)k; }
+    if (thresh < ENC_HOT_HIST && n_hot >= 1024) {
+        const u64 nb = n_hot + 64;
+        BPE_TRY(alloc_exact_e(ctx, tok->hot, nb * 48));
+        CUDA_TRY(ctx, cudaMemsetAsync(tok->hot.p, 0, nb * 48, st));
+        KLAUNCH(k_enc_hot_build, grid, 256, 0, st, t, (ulonglong2 *)tok->hot.p, (u64 *)((ulonglong2 *)tok->hot.p + 2 * nb), nb, (u32)thresh);
+        CUDA_TRY(ctx, cudaGetLastError());
+        tok->hot_nb = nb;
+    }
+    // image of the lookup kernel's shared-memory cache: the most looked-up short pretokens, about three quarters of its slots
+    {
+        u64 *h2 = (u64 *)ctx->scratch.p + 16;
+        CUDA_TRY(ctx, cudaMemsetAsync(h2, 0, 256 * sizeof(u64), st));
+        const unsigned g = (unsigned)std::min<u64>((u64)ctx->sm_count * 16, (tok->scap + 255) / 256);
+        KLAUNCH(k_enc_sm_hist, g, 256, 0, st, t, h2);
+        CUDA_TRY(ctx, cudaMemcpyAsync(host, h2, 256 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        u64 acc = 0; u32 min_bucket = 256;
+        for (int k = 255; k >= 2; k--) { if (acc + host[k] > LK_SM_SLOTS * 3 / 4) break; acc += host[k]; min_bucket = (u32)k; }
+        BPE_TRY(alloc_exact_e(ctx, tok->sm_img, (size_t)LK_SM_SLOTS * 16));
+        CUDA_TRY(ctx, cudaMemsetAsync(tok->sm_img.p, 0, (size_t)LK_SM_SLOTS * 16, st));
+        if (min_bucket < 256) KLAUNCH(k_enc_sm_build, g, 256, 0, st, t, (ulonglong2 *)tok->sm_img.p, min_bucket);
+        CUDA_TRY(ctx, cudaGetLastError());
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    bpe_buf_free(ctx, tok->samp);
     return BPE_OK;
 }
 
@@ -727,28 +1044,32 @@ static int cache_read_ctr(bpe_tok *tok, u64 *out, int k) {
     return BPE_OK;
 }
 
-static int cache_ensure_capacity(bpe_tok *tok, u64 n_short, u64 n_long, u64 new_short, u64 new_long) {
+// c = the counters (cache_read_ctr(tok, c, 9)); the batch can add up to new_short pretokens of <= 7 bytes and new_long longer ones
+static int cache_ensure_capacity(bpe_tok *tok, const u64 *c, u64 new_short, u64 new_long) {
     bpe_ctx *ctx = tok->ctx;
+    const u64 n_short = c[0], n_long = c[1], n_med = c[8];
     u64 need_s = next_pow2(std::max<u64>(1 << 16, (n_short + new_short) * 8 / 7 + 64));
-    u64 need_l = next_pow2(std::max<u64>(1 << 14, (n_long + new_long) * 8 / 7 + 64));
-    if (need_s >= (1ull << 31) || need_l >= (1ull << 31)) return bpe_set_error(ctx, BPE_ERR_CAPACITY, "pretoken cache would exceed 2^31 slots");
-    if (need_s <= tok->scap && need_l <= tok->lcap) return BPE_OK;
-    need_s = std::max(need_s, tok->scap); need_l = std::max(need_l, tok->lcap);
-    DevBuf ostab = tok->stab, oltab = tok->ltab;
-    u64 oscap = tok->scap, olcap = tok->lcap;
-    tok->stab = DevBuf(); tok->ltab = DevBuf();
-    int rc = cache_tables_alloc(tok, need_s, need_l);
+    u64 need_m = next_pow2(std::max<u64>(1 << 14, (n_med + new_long) * 8 / 7 + 64));
+    // pretokens of >= 16 bytes: at most bytes / 16 of them in a batch, i.e. half of the bound for >= 8 bytes
+    u64 need_l = next_pow2(std::max<u64>(1 << 14, (n_long + (new_long + 1) / 2) * 8 / 7 + 64));
+    if (need_s >= (1ull << 30) || need_m >= (1ull << 30) || need_l >= (1ull << 30)) return bpe_set_error(ctx, BPE_ERR_CAPACITY, "pretoken cache would exceed 2^30 slots");
+    if (need_s <= tok->scap && need_m <= tok->medcap && need_l <= tok->lcap) return BPE_OK;
+    need_s = std::max(need_s, tok->scap); need_m = std::max(need_m, tok->medcap); need_l = std::max(need_l, tok->lcap);
+    DevBuf ostab = tok->stab, omtab = tok->medtab, oltab = tok->ltab;
+    u64 oscap = tok->scap, omcap = tok->medcap, olcap = tok->lcap;
+    tok->stab = DevBuf(); tok->medtab = DevBuf(); tok->ltab = DevBuf();
+    int rc = cache_tables_alloc(tok, need_s, need_m, need_l);
     if (rc == BPE_OK) {
         EncTables t = enc_tables(tok);
-        unsigned grid = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (oscap + 255) / 256);
-        KLAUNCH(k_enc_rehash_short, grid, 256, 0, ctx->stream, (const SSlot *)ostab.p, oscap, t);
-        grid = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (olcap + 255) / 256);
-        KLAUNCH(k_enc_rehash_long, grid, 256, 0, ctx->stream, (const LSlot *)oltab.p, olcap, t);
+        auto grid_for = [&](u64 cap) { return (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (cap + 255) / 256); };
+        KLAUNCH(k_enc_rehash_short, grid_for(oscap), 256, 0, ctx->stream, (const SSlot *)ostab.p, oscap, t);
+        KLAUNCH(k_enc_rehash_med, grid_for(omcap), 256, 0, ctx->stream, (const MSlot *)omtab.p, omcap, t);
+        KLAUNCH(k_enc_rehash_long, grid_for(olcap), 256, 0, ctx->stream, (const LSlot *)oltab.p, olcap, t);
         cudaError_t e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) rc = bpe_set_error(ctx, BPE_ERR_CUDA, "cache rehash: %s", cudaGetErrorString(e));
     }
-    for (DevBuf *b : {&ostab, &oltab}) bpe_buf_free(ctx, *b);
+    for (DevBuf *b : {&ostab, &omtab, &oltab}) bpe_buf_free(ctx, *b);
     return rc;
 }
 
@@ -842,7 +1163,7 @@ BPE_API void bpe_tok_destroy(bpe_tok *tok) {
     if (!tok) return;
     if (tok->ctx) { cudaSetDevice(tok->ctx->device); cudaStreamSynchronize(tok->ctx->stream); }
     for (DevBuf *b : {&tok->mtab, &tok->mpairs, &tok->sym_to_id, &tok->vlen, &tok->voff, &tok->vblob, &tok->sp_offs, &tok->sp_ids,
-                      &tok->stab, &tok->ltab, &tok->kpool, &tok->ipool, &tok->todo, &tok->ctr})
+                      &tok->stab, &tok->medtab, &tok->ltab, &tok->kpool, &tok->ipool, &tok->todo, &tok->ctr, &tok->hot, &tok->samp, &tok->sm_img})
         bpe_buf_free(tok->ctx, *b);
     delete tok;
 }
@@ -901,7 +1222,7 @@ static int encode_core(bpe_tok *tok, u64 n, int out_dtype, void *out_dev, u64 de
 
     float ms_lookup = 0, ms_bpe = 0, ms_emit = 0;
     u64 total_tokens = 0, new_unique = 0;
-    u64 c[8];
+    u64 c[16];
     cudaEvent_t evs[4];
     for (auto &e : evs) CUDA_TRY(ctx, cudaEventCreate(&e));
     struct EvGuard { cudaEvent_t *e; ~EvGuard() { for (int i = 0; i < 4; i++) cudaEventDestroy(e[i]); } } evg{evs};
@@ -909,33 +1230,38 @@ static int encode_core(bpe_tok *tok, u64 n, int out_dtype, void *out_dev, u64 de
         const u64 b_lo = b * words_per_batch, b_hi = std::min(nw, b_lo + words_per_batch);
         const u64 bound = ord[b + 1] - ord[b];
         const u64 bytes = (b_hi - b_lo) * 32;
-        BPE_TRY(cache_read_ctr(tok, c, 8));
-        if (c[0] + c[1] + bound > ENC_CACHE_MAX_ENTRIES && c[0] + c[1] > (u64)tok->n_sp) {
+        BPE_TRY(cache_read_ctr(tok, c, 9));
+        if (c[0] + c[1] + c[8] + bound > ENC_CACHE_MAX_ENTRIES && c[0] + c[1] + c[8] > (u64)tok->n_sp) {
             BPE_TRY(cache_reset(tok));
-            BPE_TRY(cache_read_ctr(tok, c, 8));
+            BPE_TRY(cache_read_ctr(tok, c, 9));
         }
-        BPE_TRY(cache_ensure_capacity(tok, c[0], c[1], bound, std::min(bound, bytes / (SHORT_MAX + 1) + 1)));
+        BPE_TRY(cache_ensure_capacity(tok, c, bound, std::min(bound, bytes / (SHORT_MAX + 1) + 1)));
         BPE_TRY(grow_keep(ctx, tok->kpool, c[4] + bytes + 64, c[4]));
         BPE_TRY(grow_keep(ctx, tok->ipool, (c[5] + bytes + 64) * 4, c[5] * 4));
         BPE_TRY(bpe_buf_reserve(ctx, tok->todo, std::max<size_t>(bound * 4, 16)));
-        // per-pretoken arrays of the batch: offsets, cache slots, token counts, token offsets
-        const u64 bw = b_hi - b_lo;
+        // per-pretoken values of the batch; tile states of the scan
         const u64 n_tiles = (bound + SE_TILE - 1) / SE_TILE;
-        size_t off_b = round_up((bound + 2) * 4, 256), slot_b = round_up((bound + 1) * 8, 256), nt_b = 0;
-        size_t to_b = 0, st_b = round_up((n_tiles + 4) * 8, 256);          // tile states, ticket, batch total
-        BPE_TRY(bpe_buf_reserve(ctx, ctx->tmp1, off_b + slot_b + nt_b + to_b + st_b));
-        u32 *offs = (u32 *)ctx->tmp1.p;
-        u64 *vals = (u64 *)((uint8_t *)ctx->tmp1.p + off_b);
-        u64 *stmp = (u64 *)((uint8_t *)ctx->tmp1.p + off_b + slot_b + nt_b + to_b);
+        size_t slot_b = round_up((bound + 1) * 8, 256), st_b = round_up((n_tiles + 4) * 8, 256);          // tile states, ticket, batch total
+        BPE_TRY(bpe_buf_reserve(ctx, ctx->tmp1, slot_b + st_b));
+        u64 *vals = (u64 *)ctx->tmp1.p;
+        u64 *stmp = (u64 *)((uint8_t *)ctx->tmp1.p + slot_b);
         CUDA_TRY(ctx, cudaMemsetAsync((u64 *)tok->ctr.p + 2, 0, 8, st));
+        if (!tok->hot_built && bound >= ENC_HOT_MIN_BATCH) {      // this batch's lookups are counted per slot; the hot table follows it
+            BPE_TRY(bpe_buf_reserve(ctx, tok->samp, (tok->scap + tok->medcap) * 4));
+            CUDA_TRY(ctx, cudaMemsetAsync(tok->samp.p, 0, (tok->scap + tok->medcap) * 4, st));
+            tok->sampling = true;
+        }
         EncTables t = enc_tables(tok);
         const u64 base = b_lo * 32;
-        const unsigned grid = (unsigned)std::max<u64>(1, std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (bound + 255) / 256));
         CUDA_TRY(ctx, cudaEventRecord(evs[0], st));
-        launch_starts_to_offsets((const u32 *)ctx->flags.p, b_lo, b_hi, n, pre + b_lo, base, offs, bound, ctx->sm_count, st);
-        static const int lk_ctas_per_sm = getenv("BPE_LOOKUP_CTAS") ? std::max(1, atoi(getenv("BPE_LOOKUP_CTAS"))) : 64;
-        const unsigned lgrid = (unsigned)std::max<u64>(1, std::min<u64>((u64)ctx->sm_count * lk_ctas_per_sm, (bound + 255) / 256));
-        if (bound) KLAUNCH(k_enc_lookup, lgrid, 256, 0, st, t, offs, bound, base, vals);
+        if (bound) {
+            const u64 c_lo = b_lo * 2, c_hi = std::min(b_hi * 2, (n + 15) / 16);
+            const u64 steps = (c_hi - c_lo + 32 * LK_WARPS - 1) / (32 * LK_WARPS);
+            static bool attr_set = false;
+            if (!attr_set) { CUDA_TRY(ctx, cudaFuncSetAttribute((void *)k_enc_lookup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LK_DYN_SMEM)); attr_set = true; }
+            const unsigned lgrid = (unsigned)std::max<u64>(1, std::min<u64>((u64)ctx->sm_count, steps));
+            KLAUNCH(k_enc_lookup, lgrid, LK_NT, LK_DYN_SMEM, st, t, (const u32 *)ctx->flags.p, pre, ord[b], c_lo, c_hi, n, base, vals);
+        }
         CUDA_TRY(ctx, cudaGetLastError());
         CUDA_TRY(ctx, cudaEventRecord(evs[1], st));
         BPE_TRY(cache_read_ctr(tok, c, 8));
@@ -950,6 +1276,7 @@ static int encode_core(bpe_tok *tok, u64 n, int out_dtype, void *out_dev, u64 de
             KLAUNCH(k_enc_bpe, g2, 256, 0, st, t, n_todo);
             CUDA_TRY(ctx, cudaGetLastError());
         }
+        if (tok->sampling) BPE_TRY(cache_build_hot(tok));
         CUDA_TRY(ctx, cudaEventRecord(evs[2], st));
         // tokens per pretoken -> offsets -> ids, one pass
         u64 *host = (u64 *)ctx->pinned;
@@ -959,27 +1286,39 @@ static int encode_core(bpe_tok *tok, u64 n, int out_dtype, void *out_dev, u64 de
             CUDA_TRY(ctx, cudaMemsetAsync(stmp, 0, (n_tiles + 4) * 8, st));
             const bool emit = out_dev && total_tokens < dev_cap;
             if (bound) {
-                if (!emit) KLAUNCH((k_enc_scan_emit<uint16_t, false>), (unsigned)n_tiles, SE_NT, 0, st, t, vals, offs, bound, base, tile_state, ticket, (uint16_t *)nullptr, total_tokens, dev_cap, total_dev);
-                else if (out_dtype == BPE_DTYPE_U16) KLAUNCH((k_enc_scan_emit<uint16_t, true>), (unsigned)n_tiles, SE_NT, 0, st, t, vals, offs, bound, base, tile_state, ticket, (uint16_t *)out_dev, total_tokens, dev_cap, total_dev);
-                else KLAUNCH((k_enc_scan_emit<int32_t, true>), (unsigned)n_tiles, SE_NT, 0, st, t, vals, offs, bound, base, tile_state, ticket, (int32_t *)out_dev, total_tokens, dev_cap, total_dev);
+                if (!emit) KLAUNCH((k_enc_scan_emit<uint16_t, false>), (unsigned)n_tiles, SE_NT, 0, st, t, vals, bound, ord[b], tile_state, ticket, (uint16_t *)nullptr, total_tokens, dev_cap, total_dev);
+                else if (out_dtype == BPE_DTYPE_U16) KLAUNCH((k_enc_scan_emit<uint16_t, true>), (unsigned)n_tiles, SE_NT, 0, st, t, vals, bound, ord[b], tile_state, ticket, (uint16_t *)out_dev, total_tokens, dev_cap, total_dev);
+                else KLAUNCH((k_enc_scan_emit<int32_t, true>), (unsigned)n_tiles, SE_NT, 0, st, t, vals, bound, ord[b], tile_state, ticket, (int32_t *)out_dev, total_tokens, dev_cap, total_dev);
             }
             CUDA_TRY(ctx, cudaGetLastError());
             CUDA_TRY(ctx, cudaMemcpyAsync(host, total_dev, 8, cudaMemcpyDeviceToHost, st));
         }
         CUDA_TRY(ctx, cudaMemcpyAsync(host + 1, (u64 *)tok->ctr.p + 7, 8, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(ctx, cudaStreamSynchronize(st));
-        (void)bw;
-        const u64 batch_tokens = host[0], err_pos = host[1];
-        if (err_pos != ~0ull) {
-            // KeyError (tokenizer.py:120,135): report the key of the first failing pretoken in text order
+        const u64 batch_tokens = host[0], err_ord = host[1];
+        if (err_ord != ~0ull) {
+            // KeyError (tokenizer.py:120,135): report the key of the first failing pretoken in text order.  Its byte offset: the
+            // flag word that holds that ordinal (binary search in the scanned word counts), then the matching start bit.
             u64 hv[2] = {0, 0};
-            // its value: find the slot through the ordinal of that pretoken
-            u64 w = err_pos >> 5;
+            u64 lo = 0, hi = nw;                 // largest w with pre[w] <= err_ord
+            while (hi - lo > 1) {
+                const u64 mid = lo + (hi - lo) / 2; u64 pm = 0;
+                CUDA_TRY(ctx, cudaMemcpy(&pm, pre + mid, 8, cudaMemcpyDeviceToHost));
+                if (pm <= err_ord) lo = mid; else hi = mid;
+            }
             u64 hpre = 0; u32 hflags = 0;
-            CUDA_TRY(ctx, cudaMemcpy(&hpre, pre + w, 8, cudaMemcpyDeviceToHost));
-            CUDA_TRY(ctx, cudaMemcpy(&hflags, (const u32 *)ctx->flags.p + w, 4, cudaMemcpyDeviceToHost));
-            u64 o = hpre - ord[b] + __builtin_popcount(hflags & ((1u << (err_pos & 31)) - 1u));
-            CUDA_TRY(ctx, cudaMemcpy(&hv[0], vals + o, 8, cudaMemcpyDeviceToHost));   // (forward references were resolved by k_enc_scan_emit)
+            CUDA_TRY(ctx, cudaMemcpy(&hpre, pre + lo, 8, cudaMemcpyDeviceToHost));
+            CUDA_TRY(ctx, cudaMemcpy(&hflags, (const u32 *)ctx->flags.p + lo, 4, cudaMemcpyDeviceToHost));
+            for (u64 k = hpre; k < err_ord; k++) hflags &= hflags - 1;
+            const u64 err_pos = lo * 32 + (hflags ? (u64)__builtin_ctz(hflags) : 0);
+            CUDA_TRY(ctx, cudaMemcpy(&hv[0], vals + (err_ord - ord[b]), 8, cudaMemcpyDeviceToHost));
+            if (VAL_TAG(hv[0]) == VAL_FWD) {     // a forward reference: the value sits in the slot
+                const u32 ref = (u32)hv[0];
+                const void *src = (ref & REF_LONG) ? (const void *)&((const LSlot *)tok->ltab.p)[REF_SLOT(ref)].val
+                                : (ref & REF_MED) ? (const void *)&((const MSlot *)tok->medtab.p)[REF_SLOT(ref)].val
+                                                  : (const void *)&((const SSlot *)tok->stab.p)[ref].val;
+                CUDA_TRY(ctx, cudaMemcpy(&hv[0], src, 8, cudaMemcpyDeviceToHost));
+            }
             u32 sym = (u32)hv[0];
             tok->key_error.clear();
             if (sym & 0x80000000u) {
