@@ -171,11 +171,11 @@ __device__ __forceinline__ void long_add(const CountTables &t, const uint8_t *p,
 #define CNT_SMEM_PROBES 2u
 #endif
 #define CNT_WARPS (CNT_NT / 32u)
-#define CNT_QCAP 160u                            // entries of the warp's key queue
-#define CNT_QDRAIN 128u                          // drained when it reaches this (a round of the bit loop adds <= 32)
+#define CNT_QCAP 96u                             // entries of the warp's key queue
+#define CNT_QDRAIN 64u                           // drained when it reaches this (a round of 32 pretokens adds <= 32)
 #define CNT_QL_CAP 64u
 #define CNT_QL_DRAIN 32u
-#define CNT_WARP_SMEM (CNT_QCAP * 16u + CNT_QL_CAP * 8u)
+#define CNT_WARP_SMEM (CNT_QCAP * 16u + CNT_QL_CAP * 8u + 528u + 1040u)    // queues, staged text, staged positions
 #define CNT_DYN_SMEM ((size_t)CNT_SMEM_SLOTS * 12 + (size_t)CNT_WARPS * CNT_WARP_SMEM)
 
 // queues of a warp: qe = keys of short pretokens that missed the shared-memory table (k0 = key, k1 = 0) and of medium ones
@@ -244,7 +244,17 @@ __device__ __forceinline__ void count_drain(const CountTables &t, CountQueues &q
     __syncwarp();
 }
 
-// chunks [c_lo, c_hi) (16 bytes each, absolute positions 16 c); `base` <= 16 c_lo is what the 32-bit offsets of the long queue count from
+// chunks [c_lo, c_hi) (16 bytes each, absolute positions 16 c); `base` <= 16 c_lo is what the 32-bit offsets of the long queue count from.
+// A warp step = 32 consecutive chunks.  The lanes first COMPACT the step's start bits into a list of positions in shared memory
+// (warp scan of the popcounts; the 512 + 16 bytes of text are staged beside it), then take the list 32 pretokens at a time: a lane
+// per pretoken, every lane busy, where a lane per chunk left half of them idle (3.5 starts per chunk on average, 7-8 in the fullest
+// chunk of a step).  Length = next position - position; the first 16 bytes of the pretoken = five aligned words of the staged text
+// and four funnel shifts.
+#define CNT_TICKET 8u                            // steps (of 512 bytes) per ticket
+#define CNT_STAGE_TEXT 528u                      // 32 chunks + the 16 bytes after them
+#define CNT_STAGE_POS 520u                       // up to 512 starts + the sentinel (first start after the step), 16-bit each
+#define CNT_POS_OWNED 0x8000u                    // the pretoken starts inside [own_begin, own_end) of this launch's chunks
+#define CNT_POS_UNKNOWN 0xFFFFu                  // sentinel: no start within the bits the last lane holds
 __global__ void __launch_bounds__(CNT_NT, 2) k_count_pretokens(CountTables t, const u32 *__restrict__ flags, u64 c_lo, u64 c_hi, u64 n, u64 base,
                                                               u64 own_begin, u64 own_end, u64 trust_end) {
     extern __shared__ __align__(16) unsigned char cnt_smem[];
@@ -255,56 +265,92 @@ __global__ void __launch_bounds__(CNT_NT, 2) k_count_pretokens(CountTables t, co
     CountQueues q;
     q.qe = reinterpret_cast<ulonglong2 *>(wq); q.ql = reinterpret_cast<u64 *>(wq + CNT_QCAP * 16u);
     q.n = q.nl = 0;
+    u32 *s_text = reinterpret_cast<u32 *>(wq + CNT_QCAP * 16u + CNT_QL_CAP * 8u);
+    unsigned short *s_pos = reinterpret_cast<unsigned short *>(wq + CNT_QCAP * 16u + CNT_QL_CAP * 8u + CNT_STAGE_TEXT);
     for (u32 i = threadIdx.x; i < CNT_SMEM_SLOTS; i += CNT_NT) { s_key[i] = 0; s_cnt[i] = 0; }
     __syncthreads();
     u64 n_tok = 0;
     const u32 lt = (1u << lane) - 1u;
-    const u64 stride = (u64)gridDim.x * CNT_WARPS * 32u;
     const u64 n_fw = (n + 31) >> 5;              // flag words that hold bits of the text
-    u64 c = c_lo + ((u64)blockIdx.x * CNT_WARPS + warp) * 32u + lane;
-    // loads of a step: the chunk, the 16 bytes after it (the arena is padded), the two flag words that hold its 48..64-bit window
+    // Steps are handed out CNT_TICKET at a time by a ticket counter (a warp that met expensive pretokens simply takes fewer tickets:
+    // with a fixed assignment a fifth of all stall samples sat at the barrier that ends the launch); the warp holds the ticket it
+    // works on and the next one, so that the loads of the next step can always be issued a step ahead.
+    const u64 n_steps = (c_hi - c_lo + 31) / 32;
+    u64 tk_cur = 0, tk_next = 0;
+    if (lane == 0) { tk_cur = atomicAdd(&t.counters[16], 1ull); tk_next = atomicAdd(&t.counters[16], 1ull); }
+    tk_cur = __shfl_sync(0xffffffffu, tk_cur, 0); tk_next = __shfl_sync(0xffffffffu, tk_next, 0);
+    u32 sub = 0;                                 // step within the current ticket
+    u64 c = c_lo + (tk_cur * CNT_TICKET) * 32u + lane;
+    // loads of a step: the chunk (lane 31: also the 16 bytes after it; the arena is padded), the two flag words that hold its
+    // 48..64-bit window.  Chunks past c_hi are loaded as well while they are text: their start bits end the last pretokens of the range
     uint4 A = make_uint4(0, 0, 0, 0), B = A; u32 f0 = 0, f1 = 0;
-    if (c < c_hi) {
+    if (tk_cur * CNT_TICKET < n_steps && c * 16u < n) {
         const uint4 *tp = reinterpret_cast<const uint4 *>(t.text + c * 16u);
-        A = __ldcs(tp); B = __ldcs(tp + 1);
+        A = __ldcs(tp); if (lane == 31) B = __ldcs(tp + 1);
         const u64 w = c >> 1; f0 = __ldcs(flags + w); f1 = w + 1 < n_fw ? __ldcs(flags + w + 1) : 0u;
     }
-    for (; __any_sync(0xffffffffu, c < c_hi); c += stride) {
-        const bool live = c < c_hi;
-        const u64 p0 = c * 16u;
-        const u32 W0 = A.x, W1 = A.y, W2 = A.z, W3 = A.w, W4 = B.x, W5 = B.y, W6 = B.z, W7 = B.w;
+    while (tk_cur * CNT_TICKET + sub < n_steps) {
+        c = c_lo + (tk_cur * CNT_TICKET + sub) * 32u + lane;
+        // the step after this one: the next of the ticket, or the first of the next ticket (whose successor is fetched now)
+        u64 cn;
+        if (sub + 1 < CNT_TICKET) { sub++; cn = c + 32u; }
+        else {
+            sub = 0; tk_cur = tk_next;
+            if (lane == 0) tk_next = atomicAdd(&t.counters[16], 1ull);
+            tk_next = __shfl_sync(0xffffffffu, tk_next, 0);
+            cn = c_lo + (tk_cur * CNT_TICKET) * 32u + lane;
+        }
+        const u64 p0 = c * 16u, step_p0 = (c - lane) * 16u;
         u64 F = (((u64)f1 << 32) | f0) >> (u32)(p0 & 16u);           // bit i: a pretoken starts at byte p0 + i (>= 48 bits)
+        reinterpret_cast<uint4 *>(s_text)[lane] = A;
+        if (lane == 31) reinterpret_cast<uint4 *>(s_text)[32] = B;
         // the next step's loads
         {
-            const u64 cn = c + stride;
-            if (cn < c_hi) {
+            if (cn - lane < c_hi && cn * 16u < n) {
                 const uint4 *tp = reinterpret_cast<const uint4 *>(t.text + cn * 16u);
-                A = __ldcs(tp); B = __ldcs(tp + 1);
+                A = __ldcs(tp); if (lane == 31) B = __ldcs(tp + 1);
                 const u64 w = cn >> 1; f0 = __ldcs(flags + w); f1 = w + 1 < n_fw ? __ldcs(flags + w + 1) : 0u;
-            }
+            } else { f0 = 0; f1 = 0; }
         }
         if (p0 + 64 > n) F = p0 < n ? F & ((1ull << (n - p0)) - 1ull) : 0ull;   // bits past the end of the text do not count
-        u32 m = live ? (u32)F & 0xFFFFu : 0u;
-        // only the starts inside [own_begin, own_end)
+        const u32 mall = (u32)F & 0xFFFFu;       // every start of the chunk
+        // the starts this launch counts: chunks of the range, positions inside [own_begin, own_end)
+        u32 m = c < c_hi ? mall : 0u;
         if (p0 < own_begin) m = own_begin - p0 >= 16 ? 0u : m & ~((1u << (u32)(own_begin - p0)) - 1u);
         if (p0 + 16 > own_end) m = own_end <= p0 ? 0u : m & ((1u << (u32)(own_end - p0)) - 1u);
         n_tok += __popc(m);
-        while (__any_sync(0xffffffffu, m != 0)) {
-            const bool act = m != 0;
-            const u32 j = act ? __ffs(m) - 1u : 0u;
-            m &= m - 1u;
-            const u64 rest = F >> (j + 1u);
-            u32 len = (u32)__ffsll((long long)rest);
-            if (act && len == 0) {               // no further start in the window: a long pretoken, or the last one of the text
-                const u64 e = flags_next_start(flags, p0 + j + 1, n) - (p0 + j);
+        // ---- compaction: positions of the step's starts, in text order ----
+        u32 incl = __popc(mall);
+#pragma unroll
+        for (u32 d = 1; d < 32; d <<= 1) { const u32 o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+        const u32 T = __shfl_sync(0xffffffffu, incl, 31);
+        {
+            u32 o = incl - __popc(mall), mm = mall;
+            while (mm) {
+                const u32 j = __ffs(mm) - 1u; mm &= mm - 1u;
+                s_pos[o++] = (unsigned short)((lane * 16u + j) | (((m >> j) & 1u) ? CNT_POS_OWNED : 0u));
+            }
+            if (lane == 31) {                    // the sentinel: the first start after the step, if the window shows it
+                const u32 nx = (u32)__ffsll((long long)(F >> 16));
+                s_pos[T] = (unsigned short)(nx ? 512u + nx - 1u : CNT_POS_UNKNOWN);
+            }
+        }
+        __syncwarp();
+        // ---- the pretokens, 32 at a time ----
+        for (u32 i0 = 0; i0 < T; i0 += 32u) {
+            const u32 i = i0 + lane;
+            const u32 pe = i < T ? s_pos[i] : 0u, pn = i < T ? s_pos[i + 1] : 0u;
+            const bool act = (pe & CNT_POS_OWNED) != 0;
+            const u32 pos = pe & 0x7FFFu;
+            u32 len = (pn & 0x7FFFu) - pos;
+            if (act && pn == CNT_POS_UNKNOWN) {  // no further start in sight: a long pretoken, or the last one of the text
+                const u64 e = flags_next_start(flags, step_p0 + pos + 1, n) - (step_p0 + pos);
                 if (e > MAX_TOKEN_LEN) { t.counters[5] = 1; len = MAX_TOKEN_LEN; } else len = (u32)e;
             }
-            if (act && p0 + j + len > trust_end) t.counters[6] = 1;
-            // bytes j .. j + 15 of the 32-byte window
-            const u32 qd = j >> 2, sh = (j & 3u) * 8u;
-            const bool q2 = qd & 2u, q1 = qd & 1u;
-            const u32 X0 = q2 ? W2 : W0, X1 = q2 ? W3 : W1, X2 = q2 ? W4 : W2, X3 = q2 ? W5 : W3, X4 = q2 ? W6 : W4, X5 = q2 ? W7 : W5;
-            const u32 Y0 = q1 ? X1 : X0, Y1 = q1 ? X2 : X1, Y2 = q1 ? X3 : X2, Y3 = q1 ? X4 : X3, Y4 = q1 ? X5 : X4;
+            if (act && step_p0 + pos + len > trust_end) t.counters[6] = 1;
+            // bytes pos .. pos + 15 of the staged text
+            const u32 w = pos >> 2, sh = (pos & 3u) * 8u;
+            const u32 Y0 = s_text[w], Y1 = s_text[w + 1], Y2 = s_text[w + 2], Y3 = s_text[w + 3], Y4 = s_text[w + 4];
             const u64 k0 = (u64)__funnelshift_r(Y0, Y1, sh) | ((u64)__funnelshift_r(Y1, Y2, sh) << 32);
             const u64 k1 = (u64)__funnelshift_r(Y2, Y3, sh) | ((u64)__funnelshift_r(Y3, Y4, sh) << 32);
             bool q_s = act && len <= SHORT_MAX;
@@ -331,10 +377,11 @@ __global__ void __launch_bounds__(CNT_NT, 2) k_count_pretokens(CountTables t, co
             const u32 me = __ballot_sync(0xffffffffu, q_s || q_m), ml = __ballot_sync(0xffffffffu, q_l);
             if (q_s) q.qe[q.n + __popc(me & lt)] = make_ulonglong2(key, 0ull);
             if (q_m) q.qe[q.n + __popc(me & lt)] = make_ulonglong2(k0, (len > 8 ? k1 & low_bytes_mask(len - 8) : 0ull) | ((u64)len << 56));
-            if (q_l) q.ql[q.nl + __popc(ml & lt)] = (p0 + j - base) | ((u64)len << 32);
+            if (q_l) q.ql[q.nl + __popc(ml & lt)] = (step_p0 + pos - base) | ((u64)len << 32);
             q.n += __popc(me); q.nl += __popc(ml);
             if (q.n >= CNT_QDRAIN || q.nl >= CNT_QL_DRAIN) count_drain(t, q, base, lane, false);
         }
+        __syncwarp();                            // the staged text and positions are free for the next step
     }
     count_drain(t, q, base, lane, true);
     // one atomic per warp for the occurrence counter
@@ -806,8 +853,9 @@ static int count_current_text(bpe_ctx *ctx, u64 n, u64 own_begin, u64 own_end, u
         if (bound[bi]) {
             static const int cnt_ctas_per_sm = getenv("BPE_COUNT_CTAS") ? std::max(1, atoi(getenv("BPE_COUNT_CTAS"))) : 2;
             const u64 c_lo = b_lo * 2, c_hi = std::min(b_hi * 2, (n + 15) / 16);
-            const u64 steps = (c_hi - c_lo + 32 * CNT_WARPS - 1) / (32 * CNT_WARPS);
+            const u64 steps = (c_hi - c_lo + 32 * CNT_WARPS * CNT_TICKET - 1) / (32 * CNT_WARPS * CNT_TICKET);
             unsigned g2 = (unsigned)std::min<u64>((u64)ctx->sm_count * cnt_ctas_per_sm, std::max<u64>(steps, 1));
+            CUDA_TRY(ctx, cudaMemsetAsync(t.counters + 16, 0, 8, st));
             static bool attr_set = false;
             if (!attr_set) { CUDA_TRY(ctx, cudaFuncSetAttribute((void *)k_count_pretokens, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CNT_DYN_SMEM)); attr_set = true; }
             KLAUNCH(k_count_pretokens, g2, CNT_NT, CNT_DYN_SMEM, st, t, (const u32 *)ctx->flags.p, c_lo, c_hi, n, b_lo * 32, own_begin, own_end, trust_end);
