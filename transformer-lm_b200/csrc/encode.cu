@@ -68,7 +68,7 @@ struct EncTables {
     const ulonglong2 *sm_img;                    // LK_SM_SLOTS x {key, value}: image of the lookup kernel's shared-memory value cache (or null)
     u32 *scnt, *mcnt;                            // per-slot hit counters (short, medium) while the cache is being sampled for the hot table (else null)
     // [0]=n_short [1]=n_long [2]=todo count [3]=table overflow [4]=kpool cursor [5]=ipool cursor [6]=pretoken too long
-    // [7]=smallest ordinal (in the text of the call) of a pretoken whose value is a KeyError  [8]=n_medium
+    // [7]=smallest ordinal (in the text of the call) of a pretoken whose value is a KeyError  [8]=n_medium  [9]=step tickets of the lookup kernel
     u64 *ctr;
 };
 
@@ -223,6 +223,7 @@ __device__ __forceinline__ bool enc_hot_get(const EncTables &t, u64 k0, u64 k1, 
 #define LK_SM_LG 12
 #define LK_SM_SLOTS (1u << LK_SM_LG)
 #define LK_SM_PROBES 2u
+#define LK_TICKET 8u                             // steps (of 512 bytes) per ticket
 #define LK_QCAP 96u                              // entries of the warp's key queue
 #define LK_QDRAIN 64u                            // drained when it reaches this (a round of the bit loop adds <= 32)
 #define LK_QL_CAP 64u
@@ -302,10 +303,16 @@ __global__ void __launch_bounds__(LK_NT, 1) k_enc_lookup(EncTables t, const u32 
     for (u32 i = threadIdx.x; i < LK_SM_SLOTS; i += LK_NT) s_kv[i] = t.sm_img ? t.sm_img[i] : make_ulonglong2(0, 0);
     __syncthreads();
     const u32 lt = (1u << lane) - 1u;
-    const u64 stride = (u64)gridDim.x * LK_WARPS * 32u;
     const u64 n_fw = (n + 31) >> 5;              // flag words that hold bits of the text
-    u64 c = c_lo + ((u64)blockIdx.x * LK_WARPS + warp) * 32u + lane;
-    for (; __any_sync(0xffffffffu, c < c_hi); c += stride) {
+    // steps (32 chunks) are handed out LK_TICKET at a time by a ticket counter: a warp that met expensive pretokens takes fewer
+    const u64 n_steps = (c_hi - c_lo + 31) / 32;
+    for (;;) {
+        u64 tk = 0;
+        if (lane == 0) tk = atomicAdd(&t.ctr[9], 1ull);
+        tk = __shfl_sync(0xffffffffu, tk, 0);
+        if (tk * LK_TICKET >= n_steps) break;
+    for (u32 sub = 0; sub < LK_TICKET && tk * LK_TICKET + sub < n_steps; sub++) {
+        const u64 c = c_lo + (tk * LK_TICKET + sub) * 32u + lane;
         const bool live = c < c_hi;
         const u64 p0 = c * 16u;
         uint4 A = make_uint4(0, 0, 0, 0), B = A; u32 f0 = 0, f1 = 0; u64 ordw = 0;
@@ -359,6 +366,7 @@ __global__ void __launch_bounds__(LK_NT, 1) k_enc_lookup(EncTables t, const u32 
             q.n += __popc(me); q.nl += __popc(ml);
             if (q.n >= LK_QDRAIN || q.nl >= LK_QL_DRAIN) lookup_drain(t, q, base, vals, lane, false);
         }
+    }
     }
     lookup_drain(t, q, base, vals, lane, true);
 }
@@ -1256,7 +1264,8 @@ static int encode_core(bpe_tok *tok, u64 n, int out_dtype, void *out_dev, u64 de
         CUDA_TRY(ctx, cudaEventRecord(evs[0], st));
         if (bound) {
             const u64 c_lo = b_lo * 2, c_hi = std::min(b_hi * 2, (n + 15) / 16);
-            const u64 steps = (c_hi - c_lo + 32 * LK_WARPS - 1) / (32 * LK_WARPS);
+            const u64 steps = (c_hi - c_lo + 32 * LK_WARPS * LK_TICKET - 1) / (32 * LK_WARPS * LK_TICKET);
+            CUDA_TRY(ctx, cudaMemsetAsync((u64 *)tok->ctr.p + 9, 0, 8, st));
             static bool attr_set = false;
             if (!attr_set) { CUDA_TRY(ctx, cudaFuncSetAttribute((void *)k_enc_lookup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LK_DYN_SMEM)); attr_set = true; }
             const unsigned lgrid = (unsigned)std::max<u64>(1, std::min<u64>((u64)ctx->sm_count, steps));
