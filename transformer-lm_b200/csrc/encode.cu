@@ -1015,13 +1015,16 @@ static int cache_build_hot(bpe_tok *tok) {
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     u64 n_hot = 0, thresh = ENC_HOT_HIST;
     for (int k = ENC_HOT_HIST - 1; k >= 2; k--) { if (n_hot + host[k] > hot_max) break; n_hot += host[k]; thresh = (u64)k; }
-    if (thresh < ENC_HOT_HIST && n_hot >= 1024) {
+    static const bool hot_test = getenv("BPE_ENC_HOT_TEST") != nullptr;       // test knob: build it however few pretokens qualify
+    if (thresh < ENC_HOT_HIST && (hot_test || n_hot >= 1024)) {
         const u64 nb = n_hot + 64;
         BPE_TRY(alloc_exact_e(ctx, tok->hot, nb * 48));
         CUDA_TRY(ctx, cudaMemsetAsync(tok->hot.p, 0, nb * 48, st));
         KLAUNCH(k_enc_hot_build, grid, 256, 0, st, t, (ulonglong2 *)tok->hot.p, (u64 *)((ulonglong2 *)tok->hot.p + 2 * nb), nb, (u32)thresh);
         CUDA_TRY(ctx, cudaGetLastError());
         tok->hot_nb = nb;
+        static const bool prof = getenv("BPE_ENC_PROFILE") != nullptr;
+        if (prof) fprintf(stderr, "  [encoder hot table: %llu pretokens looked up >= %llu times in the sampled batch, %llu buckets]\n", (unsigned long long)n_hot, (unsigned long long)thresh, (unsigned long long)nb);
     }
     // image of the lookup kernel's shared-memory cache: the most looked-up short pretokens, about three quarters of its slots
     {
@@ -1216,7 +1219,10 @@ static int encode_core(bpe_tok *tok, u64 n, int out_dtype, void *out_dev, u64 de
     launch_popc_words((const u32 *)ctx->flags.p, nw, cnt, ctx->sm_count, st);
     launch_scan_u32(cnt, nw, pre, scan_tmp, st);
     CUDA_TRY(ctx, cudaGetLastError());
-    const u64 words_per_batch = ENC_BATCH_BYTES / 32;
+    // (test knobs: BPE_ENC_BATCH_KB = batch size, BPE_ENC_HOT_MIN = pretokens a batch needs to be sampled for the hot table)
+    static const u64 batch_bytes = getenv("BPE_ENC_BATCH_KB") ? std::max<u64>(1, (u64)atoll(getenv("BPE_ENC_BATCH_KB"))) << 10 : ENC_BATCH_BYTES;
+    static const u64 hot_min_batch = getenv("BPE_ENC_HOT_MIN") ? (u64)atoll(getenv("BPE_ENC_HOT_MIN")) : ENC_HOT_MIN_BATCH;
+    const u64 words_per_batch = batch_bytes / 32;
     const u64 n_batches = (nw + words_per_batch - 1) / words_per_batch;
     std::vector<u64> ord(n_batches + 1, 0);
     for (u64 b = 0; b <= n_batches; b++) {
@@ -1254,7 +1260,7 @@ static int encode_core(bpe_tok *tok, u64 n, int out_dtype, void *out_dev, u64 de
         u64 *vals = (u64 *)ctx->tmp1.p;
         u64 *stmp = (u64 *)((uint8_t *)ctx->tmp1.p + slot_b);
         CUDA_TRY(ctx, cudaMemsetAsync((u64 *)tok->ctr.p + 2, 0, 8, st));
-        if (!tok->hot_built && bound >= ENC_HOT_MIN_BATCH) {      // this batch's lookups are counted per slot; the hot table follows it
+        if (!tok->hot_built && bound >= hot_min_batch) {      // this batch's lookups are counted per slot; the hot table follows it
             BPE_TRY(bpe_buf_reserve(ctx, tok->samp, (tok->scap + tok->medcap) * 4));
             CUDA_TRY(ctx, cudaMemsetAsync(tok->samp.p, 0, (tok->scap + tok->medcap) * 4, st));
             tok->sampling = true;

@@ -787,7 +787,9 @@ static int count_hot_rebuild(bpe_ctx *ctx, const u64 *c) {
     BPE_TRY(count_hot_flush(ctx));
     bpe_buf_free(ctx, cs->hot); cs->hot_nb = 0;
     cs->hot_builds++; cs->hot_seen = c[4];
-    if (!hot_max || n_short + n_medium < (1u << 16)) return BPE_OK;          // small vocabularies stay in L2 as they are
+    // test knob: BPE_COUNT_HOT_TEST=1 builds the table however small the vocabulary is (the parity tests cover it with small corpora)
+    static const bool hot_test = getenv("BPE_COUNT_HOT_TEST") != nullptr;
+    if (!hot_max || (!hot_test && n_short + n_medium < (1u << 16))) return BPE_OK;   // small vocabularies stay in L2 as they are
     CountTables t = count_tables(ctx);
     u64 *hist = (u64 *)ctx->scratch.p + 16;
     CUDA_TRY(ctx, cudaMemsetAsync(hist, 0, HOT_HIST * sizeof(u64), st));
@@ -798,7 +800,7 @@ static int count_hot_rebuild(bpe_ctx *ctx, const u64 *c) {
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     u64 n_hot = 0, thresh = HOT_HIST;
     for (int k = HOT_HIST - 1; k >= 2; k--) { if (n_hot + host[k] > hot_max) break; n_hot += host[k]; thresh = (u64)k; }
-    if (thresh >= HOT_HIST || n_hot < 1024) return BPE_OK;
+    if (thresh >= HOT_HIST || (!hot_test && n_hot < 1024)) return BPE_OK;
     const u64 nb = n_hot + 64;                   // one bucket (two slots) per selected word: ~10 % of them find theirs full
     BPE_TRY(alloc_exact(ctx, cs->hot, nb * 48));
     CUDA_TRY(ctx, cudaMemsetAsync(cs->hot.p, 0, nb * 48, st));
@@ -828,7 +830,10 @@ static int count_current_text(bpe_ctx *ctx, u64 n, u64 own_begin, u64 own_end, u
     if (own_end > n) own_end = n;
     if (own_begin >= own_end) return BPE_OK;
     u64 w_lo = own_begin / 32, w_hi = (own_end + 31) / 32;
-    u64 words_per_batch = COUNT_BATCH_BYTES / 32;
+    // (test knobs: BPE_COUNT_BATCH_KB = batch size, BPE_COUNT_HOT_AFTER = pretokens before the hot table is first built)
+    static const u64 batch_bytes = getenv("BPE_COUNT_BATCH_KB") ? std::max<u64>(1, (u64)atoll(getenv("BPE_COUNT_BATCH_KB"))) << 10 : COUNT_BATCH_BYTES;
+    static const u64 hot_after = getenv("BPE_COUNT_HOT_AFTER") ? (u64)atoll(getenv("BPE_COUNT_HOT_AFTER")) : (16ull << 20);
+    u64 words_per_batch = batch_bytes / 32;
     u64 n_batches = (w_hi - w_lo + words_per_batch - 1) / words_per_batch;
     // per-batch upper bound of new uniques = number of start bits
     BPE_TRY(bpe_buf_reserve(ctx, ctx->tmp0, n_batches * sizeof(u64)));
@@ -864,7 +869,7 @@ static int count_current_text(bpe_ctx *ctx, u64 n, u64 own_begin, u64 own_end, u
         if (bi + 1 < n_batches) {
             BPE_TRY(read_counters(ctx, c, 8));
             // the hot table: built once enough text has been seen to tell frequent words from rare ones, rebuilt twice with better counts
-            if ((cs->hot_builds == 0 && c[4] >= (16u << 20)) || (cs->hot_builds >= 1 && cs->hot_builds < 3 && c[4] >= 4 * cs->hot_seen))
+            if ((cs->hot_builds == 0 && c[4] >= hot_after) || (cs->hot_builds >= 1 && cs->hot_builds < 3 && c[4] >= 4 * cs->hot_seen))
                 BPE_TRY(count_hot_rebuild(ctx, c));
         }
         if (prof) { cudaStreamSynchronize(st); fprintf(stderr, "  [batch %llu: %llu pretokens] %.2f ms (tables %llu + %llu slots)\n", (unsigned long long)bi, (unsigned long long)bound[bi], now_ms() - tb0, (unsigned long long)cs->scap, (unsigned long long)cs->lcap); }
