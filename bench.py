@@ -570,8 +570,8 @@ def run_b200(args):
             "merges_per_grid_step": round(m["merges"] / max(m["merge_steps"], 1), 2), "grid_barrier_floor_us": 1.2,
             "hbm_kernels": {
                 "k_pretok_flags": hbm_kernel("k_pretok_flags", local_bytes * 1.125, pretok_ms, "N text bytes read + N/8 flag bytes written; stage time"),
-                "count stage (k_count_pretokens + offsets)": hbm_kernel("k_count_pretokens", local_bytes * 1.0, count_ms,
-                                                                       "N text bytes read once (table traffic is overhead, SURVEY 8d); stage time incl. table growth"),
+                "count stage (k_count_pretokens)": hbm_kernel("k_count_pretokens", local_bytes * 1.125, count_ms,
+                                                             "N text bytes + N/8 flag bytes read once (table traffic is overhead, SURVEY 8d); stage time incl. table growth and the hot-table builds"),
             },
         }
         line = {

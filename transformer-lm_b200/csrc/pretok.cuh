@@ -161,13 +161,21 @@ __device__ __forceinline__ u32 chunk_patch_non_ascii(const PretokTables *tb, con
     return e;
 }
 
-// 16 info bytes -> eight 16-bit masks packed as {S|L<<16, N|P<<16, B|LEAD<<16, SP|AP<<16}
+// 16 info bytes -> eight 16-bit masks packed as {S|L<<16, N|P<<16, B|LEAD<<16, SP|AP<<16}: bit i of mask k = bit k of info byte i.
+// Two 8 x 8 bit-matrix transposes (three masked swap steps on a 64-bit word each: byte k of the result collects bit k of the eight
+// input bytes), then byte k of both halves side by side is mask k.  ~50 instructions; extracting the eight bit planes one by one
+// with multiply-and-shift cost ~170 and was a third of all instructions of the flags kernel.
+__device__ __forceinline__ u64 transpose8x8(u64 x) {
+    u64 t;
+    t = (x ^ (x >> 7)) & 0x00AA00AA00AA00AAull; x = x ^ t ^ (t << 7);
+    t = (x ^ (x >> 14)) & 0x0000CCCC0000CCCCull; x = x ^ t ^ (t << 14);
+    t = (x ^ (x >> 28)) & 0x00000000F0F0F0F0ull; x = x ^ t ^ (t << 28);
+    return x;
+}
 __device__ __forceinline__ uint4 info_to_masks(uint4 inf) {
-    const u32 w[4] = {inf.x, inf.y, inf.z, inf.w};
-    u32 m[8];
-#pragma unroll
-    for (u32 k = 0; k < 8; k++) m[k] = movemask4(w[0], k) | (movemask4(w[1], k) << 4) | (movemask4(w[2], k) << 8) | (movemask4(w[3], k) << 12);
-    return make_uint4(m[0] | (m[1] << 16), m[2] | (m[3] << 16), m[4] | (m[5] << 16), m[6] | (m[7] << 16));
+    const u64 a = transpose8x8((u64)inf.x | ((u64)inf.y << 32)), b = transpose8x8((u64)inf.z | ((u64)inf.w << 32));
+    const u32 al = (u32)a, ah = (u32)(a >> 32), bl = (u32)b, bh = (u32)(b >> 32);
+    return make_uint4(__byte_perm(al, bl, 0x5140), __byte_perm(al, bl, 0x7362), __byte_perm(ah, bh, 0x5140), __byte_perm(ah, bh, 0x7362));
 }
 // bytes covered by a special-token occurrence become boundary bytes
 __device__ __forceinline__ uint4 masks_apply_boundary(uint4 mk, u32 m16) {
