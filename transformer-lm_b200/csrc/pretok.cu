@@ -235,11 +235,20 @@ __device__ __forceinline__ int special_match_at(const uint8_t *text, u64 n, u64 
 __global__ void __launch_bounds__(256) k_special_candidates(const uint8_t *__restrict__ text, u64 n, SpecialsDev sp,
                                                            u32 *__restrict__ cand, u64 n_words) {
     __shared__ u32 s_first[8];                   // 256-bit set of first bytes of the specials
+    __shared__ u32 s_fb[4], s_nfirst;            // the distinct first bytes when there are at most four (else s_nfirst = 5)
     if (threadIdx.x < 8) s_first[threadIdx.x] = 0;
     __syncthreads();
-    if (threadIdx.x < (u32)sp.n) {
-        u32 o = sp.offs[threadIdx.x];
-        if (sp.offs[threadIdx.x + 1] > o) { u32 b = sp.blob[o]; atomicOr(&s_first[b >> 5], 1u << (b & 31)); }
+    for (u32 i = threadIdx.x; i < (u32)sp.n; i += blockDim.x) {
+        u32 o = sp.offs[i];
+        if (sp.offs[i + 1] > o) { u32 b = sp.blob[o]; atomicOr(&s_first[b >> 5], 1u << (b & 31)); }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 k = 0;
+        for (u32 b = 0; b < 256; b++)
+            if ((s_first[b >> 5] >> (b & 31)) & 1u) { if (k < 4) s_fb[k] = b; k++; }
+        for (u32 i = k; i < 4; i++) s_fb[i] = k ? s_fb[0] : 0xFFu;
+        s_nfirst = k <= 4 ? (k ? k : 1u) : 5u;   // (no special with bytes at all: test for 0xFF, which never occurs)
     }
     __syncthreads();
     for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += (u64)gridDim.x * blockDim.x) {
@@ -247,6 +256,19 @@ __global__ void __launch_bounds__(256) k_special_candidates(const uint8_t *__res
         uint4 a = ld_stream_v4(p), b4 = ld_stream_v4(p + 1);
         u32 ws[8] = {a.x, a.y, a.z, a.w, b4.x, b4.y, b4.z, b4.w};
         u32 bits = 0;
+        // with at most four distinct first bytes (the usual single "<" of "<|endoftext|>"): four SIMD byte tests per word decide
+        // whether the 32 bytes hold a candidate at all -- the per-byte walk below then runs for one word in a few hundred
+        if (s_nfirst <= 4) {
+            bool any = false;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                any |= has_byte(ws[k], s_fb[0]);
+                if (s_nfirst > 1) any |= has_byte(ws[k], s_fb[1]);
+                if (s_nfirst > 2) any |= has_byte(ws[k], s_fb[2]);
+                if (s_nfirst > 3) any |= has_byte(ws[k], s_fb[3]);
+            }
+            if (!any) { cand[w] = 0; continue; }
+        }
 #pragma unroll
         for (int j = 0; j < 32; j++) {
             u32 b = (ws[j >> 2] >> ((j & 3) * 8)) & 0xFFu;

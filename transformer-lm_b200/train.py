@@ -47,16 +47,25 @@ def merges_to_python(vocab: Vocab, pairs: np.ndarray, n_done: int):
     """Symbol-id merge list of the device -> (vocab dict, merges list) of the reference (train.py:190-191, 228): tokens are
     byte strings, `Vocab.add_token` skips a byte string that is already present (vocab.py:28-34)."""
     sym = [bytes([i]) for i in range(256)]
-    merges = []
+    ab = pairs[:n_done]
+    ia, ib = ab[:, 0].tolist(), ab[:, 1].tolist()
+    append = sym.append
+    for x, y in zip(ia, ib):                     # the one loop that cannot be avoided: token j is built from earlier tokens
+        append(sym[x] + sym[y])
+    get = sym.__getitem__
+    merges = list(zip(map(get, ia), map(get, ib)))
     idx_to_token, present = vocab.idx_to_token, vocab._present     # (Vocab.add_token inlined: tens of thousands of calls)
-    for ia, ib in pairs[:n_done].tolist():
-        a, b = sym[ia], sym[ib]
-        t = a + b
-        merges.append((a, b))
-        sym.append(t)
-        if t not in present:
-            present.add(t)
-            idx_to_token[len(idx_to_token)] = t
+    new = sym[256:]
+    fresh = set(new)
+    if len(fresh) == len(new) and present.isdisjoint(fresh):       # the usual case: no byte string twice (A-5 / A-6 never triggered)
+        base = len(idx_to_token)
+        idx_to_token.update(zip(range(base, base + len(new)), new))
+        present |= fresh
+    else:
+        for t in new:
+            if t not in present:
+                present.add(t)
+                idx_to_token[len(idx_to_token)] = t
     return vocab.get_idx_to_token(), merges
 
 
