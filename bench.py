@@ -68,6 +68,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-encode", action="store_true", help="train workloads: skip the secondary encode measurement")
     ap.add_argument("--no-tiny", action="store_true", help="skip the TinyStories-shape training sub-measurement")
+    ap.add_argument("--no-files", action="store_true", help="skip the file-level legs (train_bpe(path), encode_file) at N = 1")
     ap.add_argument("--no-slices", action="store_true", help="skip the same-slice legs")
     ap.add_argument("--no-unsharded-check", action="store_true", help="N > 1: do not re-run the unsharded path on rank 0")
     return ap.parse_args()
@@ -745,6 +746,51 @@ def run_b200(args):
             for k in ("e2e", "unsharded_check"):
                 if k in enc:
                     line[k] = enc[k]
+
+    # ======================= file-level legs (N = 1): train_bpe(path) and encode_file(path -> .bin), SURVEY 8f rows 1-2 =======================
+    if world == 1 and is_train and not args.no_files and not args.bytes:
+        import shutil
+        import tempfile
+        from transformer_lm_b200.train import train_bpe as train_bpe_path
+        from transformer_lm_b200.encode_file import encode_file
+        from transformer_lm_b200.tokenizer import Tokenizer
+        f_shape, f_seed, f_bytes, f_vocab, _ = WORKLOADS["train-tiny"]
+        f_bytes = int(f_bytes) // BLOCK * BLOCK
+        d = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > 3 * f_bytes else tempfile.gettempdir()
+        fdir = tempfile.mkdtemp(prefix="bpe_bench_", dir=d)
+        try:
+            src = os.path.join(fdir, "corpus.txt")
+            t = torch.empty(f_bytes, dtype=torch.uint8, device="cuda")
+            synth_device(f_shape, f_seed, f_bytes, t.data_ptr(), ctx=ctx)
+            t.cpu().numpy().tofile(src)
+            del t
+            walls = []
+            for _ in range(3):                   # (first run: page cache and buffer pools warm up)
+                t0 = time.time()
+                f_vocab_d, f_merges = train_bpe_path(src, f_vocab, SPECIALS, ctx=ctx)
+                walls.append(time.time() - t0)
+            f_sha = merges_sha(f_merges)
+            tok_f = Tokenizer(f_vocab_d, f_merges, SPECIALS, ctx=ctx)
+            dst = os.path.join(fdir, "tokens.bin")
+            ewalls = []
+            for _ in range(2):
+                ctx.check(L.bpe_tok_cache_reset(tok_f._device_tok()))
+                t0 = time.time()
+                n_tok_f = encode_file(tok_f, src, dst, np.uint16)
+                ewalls.append(time.time() - t0)
+            assert os.path.getsize(dst) == 2 * n_tok_f
+            tiny_sha = line.get("train_tiny", {}).get("merges_sha")
+            line["files"] = {
+                "note": "the reference's file-level entry points on a %.2f GB TinyStories-shape file in %s (page cache warm): wall clock, "
+                        "includes reading the file, H2D, kernels, D2H and writing the .bin" % (f_bytes / 1e9, d),
+                "train_bpe(path)": {"wall_s": round(min(walls[1:]), 4), "MBps": round(f_bytes / 1e6 / min(walls[1:]), 1), "merges_sha": f_sha,
+                                    "same_merges_as_device_resident_run": (f_sha == tiny_sha) if tiny_sha else None,
+                                    "api": "transformer_lm_b200.train.train_bpe(path, 10000, ['<|endoftext|>']) (streamed ingest: reader threads -> page-locked buffers -> bpe_count_add_shard)"},
+                "encode_file(path -> .bin)": {"wall_s": round(min(ewalls), 4), "MBps": round(f_bytes / 1e6 / min(ewalls), 1), "tokens": int(n_tok_f),
+                                               "api": "transformer_lm_b200.encode_file.encode_file(tokenizer, path, out.bin, uint16) (reader thread -> bpe_encode -> writer thread)"},
+            }
+        finally:
+            shutil.rmtree(fdir, ignore_errors=True)
 
     # ======================= same bytes, same vocab as the CPU arms (N = 1) =======================
     if world == 1 and not args.no_slices:

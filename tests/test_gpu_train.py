@@ -310,6 +310,9 @@ def test_streamed_file_ingest_equals_in_memory(tmp_path, monkeypatch):
     got = run_train_bpe(path, 800, ["<|endoftext|>"])
     want = oracle.train_bpe_on_bytes(small.tobytes(), 800, ["<|endoftext|>"])
     assert got[1] == want[1] and got[0] == want[0]
+    # O_DIRECT reads (block-aligned ranges around the chunks; buffered where the file system refuses the flag): same result
+    got = T.train_bpe(path, 800, ["<|endoftext|>"], direct_io=True)
+    assert got[1] == want[1] and got[0] == want[0]
     # carriage return -> one-piece path; invalid UTF-8 -> UnicodeDecodeError
     host2 = host[: 100 << 20].copy()
     host2[(70 << 20) + 5] = 0x0D

@@ -53,18 +53,210 @@ def _last_exact_cut(buf: bytes, specials: list[bytes], lo: int) -> int:
     return 0
 
 
-def encode_file(tokenizer, input_path, output_path, dtype=np.uint16, piece_bytes: int = 1 << 30, save_pt: str | None = None,
+def encode_file(tokenizer, input_path, output_path, dtype=np.uint16, piece_bytes: int = 64 << 20, save_pt: str | None = None,
                 byte_range: tuple[int, int] | None = None, distributed: bool = False, group=None) -> int:
     """Encode `input_path` with `tokenizer` into raw little-endian `dtype` ids at `output_path`.  Returns the token count.
 
-    Three stages run concurrently: a reader thread pulls the next block from the file, the calling thread
-    cuts and encodes the current piece (bpe_encode, which itself overlaps upload, kernels and download), a writer thread
-    appends the ids of the previous piece to the output.  byte_range = (lo, hi) restricts the work to those bytes of the file
-    (lo and hi must be exact cut positions: sharded_encode.py); distributed=True shards the file over the ranks of the
+    Three stages run concurrently: a reader thread pulls the next block from the file straight into page-locked
+    memory, the calling thread cuts and encodes the current piece (bpe_encode: upload, kernels, download into page-locked memory), a
+    writer thread appends the ids of the previous piece to the output.  byte_range = (lo, hi) restricts the work to those bytes of
+    the file (lo and hi must be exact cut positions: sharded_encode.py); distributed=True shards the file over the ranks of the
     initialised torch.distributed group."""
     if distributed:
         from .sharded_encode import encode_file_sharded
         return encode_file_sharded(tokenizer, input_path, output_path, dtype, piece_bytes, group)
+    if getattr(tokenizer, "host_only", False):               # (checker-backed tokenizers of the CPU tests: no page-locked staging)
+        total = _encode_file_simple(tokenizer, input_path, output_path, dtype, piece_bytes, byte_range)
+    else:
+        total = _encode_file_pinned(tokenizer, input_path, output_path, dtype, piece_bytes, byte_range)
+    if save_pt:
+        import torch
+        torch.save(np.fromfile(output_path, dtype=np.dtype(dtype)), save_pt, pickle_protocol=4)       # models/tokenizer/encode.py:37-38
+    return total
+
+
+_PIN_CACHE: dict = {}            # page-locked staging buffers, kept between calls (pinning costs ~0.3 s per GB)
+
+
+def _pinned(role: str, nbytes: int):
+    b = _PIN_CACHE.get(role)
+    if b is None or b.nbytes < nbytes:
+        if b is not None:
+            b.free()
+        b = _PIN_CACHE[role] = _lib.PinnedBuffer(nbytes)
+    return b
+
+
+def release_buffers() -> None:
+    """Free the page-locked staging buffers encode_file keeps between calls."""
+    for b in _PIN_CACHE.values():
+        b.free()
+    _PIN_CACHE.clear()
+
+
+def _memchr(arr: np.ndarray, n: int, byte: int) -> bool:
+    import ctypes as C
+    libc = C.CDLL(None)
+    libc.memchr.restype = C.c_void_p
+    libc.memchr.argtypes = [C.c_void_p, C.c_int, C.c_size_t]
+    return n > 0 and libc.memchr(arr.ctypes.data, byte, n) is not None
+
+
+def _find_cut(mv: memoryview, n: int, specials: list[bytes]) -> int:
+    """Largest exact cut position in the second half of mv[:n] (0 = none); looks at the last few MB first."""
+    lo = n // 2
+    ctx = max([len(t) for t in specials] + [2])
+    for window in (4 << 20, n - lo):
+        start = max(lo, n - window)
+        c0 = max(0, start - ctx)
+        cut = _last_exact_cut(bytes(mv[c0:n]), specials, start - c0)
+        if cut:
+            return c0 + cut
+        if start == lo:
+            break
+    return 0
+
+
+def _encode_file_pinned(tokenizer, input_path, output_path, dtype, piece_bytes, byte_range) -> int:
+    """The device path of encode_file: no intermediate Python byte strings.  Two page-locked input buffers (the reader thread's
+    readinto target; a piece = [bytes carried over from the previous block][new block] up to the last exact cut) and two page-locked
+    output buffers (bpe_encode downloads into them, the writer thread writes them out)."""
+    import queue
+    import threading
+    dtype = np.dtype(dtype)
+    specials = [s.encode("utf-8") for s in tokenizer.special_tokens]
+    lo, hi = byte_range if byte_range is not None else (0, os.path.getsize(input_path))
+    span = max(hi - lo, 0)
+    P = max(1, min(int(piece_bytes), max(span, 1)))
+    in_cap = 2 * P + 64
+    inb = [_pinned("in%d" % i, in_cap).array for i in range(2)]
+    outb = [_pinned("out%d" % i, in_cap * dtype.itemsize).array for i in range(2)]
+    out_views = [b[: in_cap * dtype.itemsize].view(dtype) for b in outb]
+    requests: queue.Queue = queue.Queue()
+    filled: queue.Queue = queue.Queue()
+    results: queue.Queue = queue.Queue()
+    free_out: queue.Queue = queue.Queue()
+    for i in range(2):
+        free_out.put(i)
+    failure: list = []
+
+    def reader():
+        try:
+            with open(input_path, "rb", buffering=0) as f:
+                f.seek(lo)
+                while True:
+                    req = requests.get()
+                    if req is None:
+                        return
+                    idx, off, want = req
+                    mv, got = memoryview(inb[idx])[off: off + want], 0
+                    while got < want:
+                        k = f.readinto(mv[got:])
+                        if not k:
+                            break
+                        got += k
+                    filled.put(got)
+        except BaseException as e:            # surfaced in the calling thread
+            failure.append(e)
+            filled.put(0)
+
+    def writer():
+        try:
+            with open(output_path, "wb") as out:
+                while True:
+                    item = results.get()
+                    if item is None:
+                        return
+                    idx, n_tok, ids = item
+                    if ids is not None:
+                        ids.astype(dtype.newbyteorder("<"), copy=False).tofile(out)
+                    else:
+                        out_views[idx][:n_tok].tofile(out)      # (little-endian host: the raw buffer is the file format)
+                        free_out.put(idx)
+        except BaseException as e:
+            failure.append(e)
+            while results.get() is not None:
+                pass
+
+    rt, wt = threading.Thread(target=reader, daemon=True), threading.Thread(target=writer, daemon=True)
+    rt.start(); wt.start()
+    total = 0
+    offset = lo                                  # bytes of the (untranslated) file consumed so far: for error offsets
+    rest_from = None                             # no exact cut in a whole piece: the rest of the file goes through the simple path
+    try:
+        k, carry_len, left = 0, 0, span
+        want = min(P, left)
+        requests.put((0, 0, want))
+        while True:
+            got = filled.get()
+            if failure:
+                raise failure[0]
+            cur = inb[k % 2]
+            n = carry_len + got
+            left -= got
+            eof = left <= 0 or got < want
+            hold = 1 if (not eof and n and cur[n - 1] == 13) else 0     # the "\n" of a "\r\n" may start the next block
+            n_eff = n - hold
+            if eof:
+                cut = n_eff
+            else:
+                cut = _find_cut(memoryview(cur), n_eff, specials)
+                if cut == 0:
+                    rest_from = offset
+                    break
+            next_carry = n - cut
+            if not eof:
+                inb[(k + 1) % 2][:next_carry] = cur[cut:n]
+                want = min(P, left)
+                requests.put(((k + 1) % 2, next_carry, want))
+            if cut:
+                try:
+                    if _memchr(cur, cut, 13):                # text-mode read of the reference (A-2): translate on the host, rare
+                        piece = bytes(memoryview(cur)[:cut]).replace(b"\r\n", b"\n").replace(b"\r", b"\n")
+                        ids = tokenizer.encode_to_numpy(piece, dtype)
+                        results.put((-1, ids.size, ids))
+                        n_tok = ids.size
+                    else:
+                        idx = free_out.get()
+                        n_tok = tokenizer.encode_into(cur[:cut], out_views[idx])
+                        results.put((idx, n_tok, None))
+                except UnicodeDecodeError as e:
+                    raise UnicodeDecodeError(e.encoding, e.object[max(e.start - 8, 0): e.end + 8], min(e.start, 8), min(e.start, 8) + (e.end - e.start),
+                                             e.reason + " (near byte %d of the file)" % (offset + e.start)) from None
+                if failure:
+                    raise failure[0]
+                total += n_tok
+                offset += cut
+            if eof:
+                break
+            carry_len = next_carry
+            k += 1
+    finally:
+        requests.put(None)
+        results.put(None)
+        wt.join()
+        rt.join(timeout=5)
+    if failure:
+        raise failure[0]
+    if rest_from is not None:
+        part = os.fspath(output_path) + ".rest"
+        try:
+            total += _encode_file_simple(tokenizer, input_path, part, dtype, max(piece_bytes, 1 << 20), (rest_from, hi))
+            with open(output_path, "ab") as out, open(part, "rb") as src:
+                while True:
+                    blk = src.read(64 << 20)
+                    if not blk:
+                        break
+                    out.write(blk)
+        finally:
+            if os.path.exists(part):
+                os.remove(part)
+    return total
+
+
+def _encode_file_simple(tokenizer, input_path, output_path, dtype, piece_bytes, byte_range) -> int:
+    """The plain implementation (Python byte strings): checker-backed tokenizers of the CPU tests, and files in which a whole piece
+    holds no exact cut."""
     import queue
     import threading
     dtype = np.dtype(dtype)
@@ -177,9 +369,6 @@ def encode_file(tokenizer, input_path, output_path, dtype=np.uint16, piece_bytes
             pin.free()
     if failure:
         raise failure[0]
-    if save_pt:
-        import torch
-        torch.save(np.fromfile(output_path, dtype=dtype), save_pt, pickle_protocol=4)       # models/tokenizer/encode.py:37-38
     return total
 
 

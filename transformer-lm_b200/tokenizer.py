@@ -168,6 +168,22 @@ class Tokenizer:
         self.last_stats = stats.as_dict()
         return out[: n_out.value]
 
+    def encode_into(self, data, out: np.ndarray) -> int:
+        """encode_to_numpy into a caller-owned array (uint16 or int32; page-locked for PCIe-speed downloads).  Returns the count."""
+        tok = self._device_tok()
+        ctx = self._tok_ctx
+        L = _lib.lib()
+        arr = _lib.as_u8(data)
+        code = {np.dtype(np.uint16): _lib.DTYPE_U16, np.dtype(np.int32): _lib.DTYPE_I32}[out.dtype]
+        n_out = C.c_uint64(0)
+        stats = _lib.EncodeStats()
+        with ctx.lock:
+            rc = L.bpe_encode(tok, _lib.ptr(arr) if arr.size else None, arr.size, code, _lib.ptr(out), out.size, C.byref(n_out), C.byref(stats))
+            if rc != _lib.BPE_OK:
+                self._raise(ctx, rc, arr)
+        self.last_stats = stats.as_dict()
+        return int(n_out.value)
+
     def encode(self, text: str) -> List[int]:
         return self.encode_to_numpy(text.encode("utf-8"), np.int32).tolist()
 

@@ -104,32 +104,60 @@ _STREAM_MIN = 512 << 20          # files at least this big are streamed: read, u
 _STREAM_CHUNK = 256 << 20
 _STREAM_HALO_LEFT = 64
 _STREAM_HALO_RIGHT = 64 << 10
-_READ_THREADS = 4
+_READ_THREADS = int(os.environ.get("BPE_READ_THREADS", "8"))      # (2 -> 0.22 s, 4 -> 0.14 s, 8 -> 0.11 s for a 2 GiB file in tmpfs)
+_PIN_CACHE: list = []            # page-locked chunk buffers of the streamed ingest, kept between calls (pinning costs ~0.3 s per GB)
 
 
-def _pread_into(fd: int, view: memoryview, offset: int) -> None:
+def release_buffers() -> None:
+    """Free the page-locked buffers train_bpe(path) keeps between calls."""
+    while _PIN_CACHE:
+        _PIN_CACHE.pop().free()
+
+
+_DIRECT_ALIGN = 4096             # O_DIRECT: file offsets, lengths and buffer addresses in multiples of the logical block size
+
+
+def _pread_into(fd: int, view: memoryview, offset: int, size: int | None = None) -> None:
+    """Fill `view` from file offset `offset`.  With `size` (the file size; O_DIRECT reads) the view may extend past the end of the
+    file: the read stops there."""
     got = 0
-    while got < len(view):
+    want = len(view) if size is None else min(len(view), size - offset)
+    while got < want:
         k = os.preadv(fd, [view[got:]], offset + got)
         if k <= 0:
             raise OSError("short read at offset %d" % (offset + got))
         got += k
 
 
-def _train_bpe_streamed(input_path, size: int, vocab_size: int, special_tokens: List[str], ctx=None, return_stats: bool = False):
+def _open_for_read(path, direct: bool):
+    """(fd, direct): the file opened O_RDONLY, with O_DIRECT when asked for and the file system takes it (page cache bypassed: the
+    ingest path reads every byte once).  tmpfs and some network file systems refuse O_DIRECT: buffered then."""
+    if direct and hasattr(os, "O_DIRECT"):
+        try:
+            return os.open(os.fspath(path), os.O_RDONLY | os.O_DIRECT), True
+        except OSError:
+            logger.info("O_DIRECT not supported for %s: buffered reads", path)
+    return os.open(os.fspath(path), os.O_RDONLY), False
+
+
+def _train_bpe_streamed(input_path, size: int, vocab_size: int, special_tokens: List[str], ctx=None, return_stats: bool = False,
+                        direct_io: bool | None = None):
     """Ingest path for big files: the file is read in 256 MB chunks, each with a small halo, by a few
     threads into page-locked buffers while the GPU pretokenises and counts the previous chunk (bpe_count_add_shard --
     the same shard contract as the multi-GPU path); then the merge loop runs on the counts.  Returns None when the file
     needs the one-piece path (a carriage return: universal newlines shift offsets; or a pretoken longer than the halo)."""
     import concurrent.futures as cf
     from .sharded import DeviceCounter, align_cut, _raise_decode_error
-    fd = os.open(os.fspath(input_path), os.O_RDONLY)
+    if direct_io is None:
+        direct_io = os.environ.get("BPE_IO_DIRECT", "0") not in ("", "0")
+    fd, direct = _open_for_read(input_path, direct_io)
+    fd_peek = os.open(os.fspath(input_path), os.O_RDONLY) if direct else fd      # (small unaligned reads: cut search, error context)
     bufs = []
     pool = None
     pending: dict = {}
     try:
         def peek(lo, hi):
-            return os.pread(fd, hi - lo, lo)
+            return os.pread(fd_peek, hi - lo, lo)
         cuts = [0]
         p = _STREAM_CHUNK
         while p + _STREAM_CHUNK // 2 < size:
@@ -142,15 +170,24 @@ def _train_bpe_streamed(input_path, size: int, vocab_size: int, special_tokens: 
             rlo = align_cut(peek, max(0, lo - _STREAM_HALO_LEFT), size)
             rhi = align_cut(peek, min(size, hi + _STREAM_HALO_RIGHT), size)
             ranges.append((lo, hi, rlo, rhi))
-        cap = max(r[3] - r[2] for r in ranges)
-        bufs = [_lib.PinnedBuffer(cap) for _ in range(min(3, len(ranges)))]
+        # with O_DIRECT a chunk is read as the block-aligned range around it (the page-locked buffers are page aligned); `skew` =
+        # where the chunk starts inside its buffer
+        A = _DIRECT_ALIGN if direct else 1
+        cap = max(-(-r[3] // A) * A - r[2] // A * A for r in ranges)
+        want_bufs = min(3, len(ranges))
+        while _PIN_CACHE and (_PIN_CACHE[0].nbytes < cap or len(_PIN_CACHE) > want_bufs):
+            _PIN_CACHE.pop(0).free()
+        while len(_PIN_CACHE) < want_bufs:
+            _PIN_CACHE.append(_lib.PinnedBuffer(cap))
+        bufs = list(_PIN_CACHE)
         pool = cf.ThreadPoolExecutor(max_workers=_READ_THREADS)
 
         def submit(k):
             lo, hi, rlo, rhi = ranges[k]
-            mv = memoryview(bufs[k % len(bufs)].array)[: rhi - rlo]
-            step = -(-(rhi - rlo) // _READ_THREADS)
-            return [pool.submit(_pread_into, fd, mv[o: min(o + step, rhi - rlo)], rlo + o) for o in range(0, rhi - rlo, step)]
+            alo, ahi = rlo // A * A, -(-rhi // A) * A
+            mv = memoryview(bufs[k % len(bufs)].array)[: ahi - alo]
+            step = -(-(-(-(ahi - alo) // _READ_THREADS)) // A) * A
+            return [pool.submit(_pread_into, fd, mv[o: min(o + step, ahi - alo)], alo + o, size if direct else None) for o in range(0, ahi - alo, step)]
 
         counter = DeviceCounter(ctx)
         pending = {k: submit(k) for k in range(min(len(bufs) - 1, len(ranges)))}
@@ -160,7 +197,8 @@ def _train_bpe_streamed(input_path, size: int, vocab_size: int, special_tokens: 
                 pending[nxt] = submit(nxt)       # its buffer was consumed by chunk nxt - len(bufs), already counted
             for fut in pending.pop(k):
                 fut.result()
-            status = counter.add(bufs[k % len(bufs)].array[: rhi - rlo], lo - rlo, hi - rlo, rlo == 0, rhi == size)
+            skew = rlo - rlo // A * A
+            status = counter.add(bufs[k % len(bufs)].array[skew: skew + rhi - rlo], lo - rlo, hi - rlo, rlo == 0, rhi == size)
             if status is not None:
                 if status[0] == "utf8":
                     _raise_decode_error(peek, size, rlo + status[1])      # what open(path, encoding="utf-8").read() raises
@@ -177,15 +215,16 @@ def _train_bpe_streamed(input_path, size: int, vocab_size: int, special_tokens: 
                     pass
         if pool is not None:
             pool.shutdown(wait=True)
-        for b in bufs:
-            b.free()
         os.close(fd)
+        if fd_peek != fd:
+            os.close(fd_peek)
 
 
 def train_bpe(input_path, vocab_size: int, special_tokens: List[str] = [], *, distributed: bool = False, **kwargs):
     """Drop-in for models/tokenizer/train.py:142 train_bpe.  Extra keyword arguments are ours (the reference's
-    adapter never passes any): ctx=, return_stats=, and distributed=True to shard the file over the ranks of the
-    initialised torch.distributed group (one process per GPU; see sharded.py)."""
+    adapter never passes any): ctx=, return_stats=, direct_io= (files of >= 512 MB are streamed; True or BPE_IO_DIRECT=1 reads them
+    with O_DIRECT), and distributed=True to shard the file over the ranks of the initialised torch.distributed group (one process
+    per GPU; see sharded.py)."""
     if distributed:
         from .sharded import train_bpe_sharded
         return train_bpe_sharded(input_path, vocab_size, special_tokens, **kwargs)
@@ -193,9 +232,10 @@ def train_bpe(input_path, vocab_size: int, special_tokens: List[str] = [], *, di
     size = os.path.getsize(input_path)           # FileNotFoundError like open() in the reference
     kwargs = dict(kwargs)
     want_stats = kwargs.pop("return_stats", False)
+    direct_io = kwargs.pop("direct_io", None)
     res = None
     if size >= _STREAM_MIN:
-        res = _train_bpe_streamed(input_path, size, vocab_size, special_tokens, return_stats=True, **kwargs)
+        res = _train_bpe_streamed(input_path, size, vocab_size, special_tokens, return_stats=True, direct_io=direct_io, **kwargs)
     if res is None:
         arr, _keep = _read_file(input_path)
         res = train_bpe_on_bytes(arr, vocab_size, special_tokens, return_stats=True, **kwargs)
