@@ -39,7 +39,7 @@ TRAIN_CODE = """
 """
 
 
-@pytest.mark.parametrize("hot_max", ["20000", "300", "0"])
+@pytest.mark.parametrize("hot_max", ["20000", "100000", "0"])
 def test_count_stage_with_hot_table_matches_oracle(hot_max):
     # 2 MB batches: a dozen batches per corpus; the hot table is built after ~0.2 M pretokens and rebuilt at 4x and 16x that
     out, err = _run(TRAIN_CODE, {"BPE_COUNT_BATCH_KB": "2048", "BPE_COUNT_HOT_AFTER": "200000", "BPE_COUNT_HOT_TEST": "1",
@@ -80,7 +80,7 @@ ENCODE_CODE = """
 """
 
 
-@pytest.mark.parametrize("hot_max", ["1048576", "500", "0"])
+@pytest.mark.parametrize("hot_max", ["1048576", "20000", "0"])
 def test_encoder_lookup_with_hot_table_matches_oracle(hot_max):
     out, err = _run(ENCODE_CODE, {"BPE_ENC_BATCH_KB": "512", "BPE_ENC_HOT_MIN": "50000", "BPE_ENC_HOT_TEST": "1", "BPE_ENC_HOT_MAX": hot_max,
                                   "BPE_ENC_PROFILE": "1"})

@@ -107,7 +107,7 @@ BPE_API void bpe_ctx_destroy(bpe_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     count_state_free(ctx);
     if (ctx->s_in) { cudaStreamSynchronize(ctx->s_in); cudaStreamSynchronize(ctx->s_out); }
-    for (DevBuf *b : {&ctx->text, &ctx->flags, &ctx->spmask, &ctx->spstart, &ctx->scratch, &ctx->tmp0, &ctx->tmp1, &ctx->tmp2,
+    for (DevBuf *b : {&ctx->text, &ctx->flags, &ctx->spmask, &ctx->spstart, &ctx->scratch, &ctx->tmp0, &ctx->tmp1, &ctx->tmp2, &ctx->sp_dev,
                       &ctx->text_alt, &ctx->out_a, &ctx->out_b})
         bpe_buf_free(ctx, *b);
     if (ctx->s_in) {
@@ -185,12 +185,21 @@ int ctx_upload_specials(bpe_ctx *ctx, const uint8_t *blob, const u32 *offs, int 
     size_t blob_bytes = offs[n_sp];
     size_t offs_bytes = sizeof(u32) * (n_sp + 1);
     size_t offs_at = round_up(blob_bytes + 1, 16);
-    BPE_TRY(bpe_buf_reserve(ctx, ctx->tmp2, offs_at + offs_bytes));
-    if (blob_bytes) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->tmp2.p, blob, blob_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync((uint8_t *)ctx->tmp2.p + offs_at, offs, offs_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    // the same specials as last time (every chunk of a pipelined encode asks again): nothing to upload -- and nothing queued on the
+    // copy engine behind the chunk that is being uploaded
+    const bool same = ctx->sp_dev.p && ctx->sp_cache_blob.size() == blob_bytes && ctx->sp_cache_offs.size() == (size_t)n_sp + 1 &&
+                      memcmp(ctx->sp_cache_offs.data(), offs, offs_bytes) == 0 && (blob_bytes == 0 || memcmp(ctx->sp_cache_blob.data(), blob, blob_bytes) == 0);
+    if (!same) {
+        ctx->sp_cache_blob.clear(); ctx->sp_cache_offs.clear();
+        BPE_TRY(bpe_buf_reserve(ctx, ctx->sp_dev, offs_at + offs_bytes));
+        if (blob_bytes) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->sp_dev.p, blob, blob_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync((uint8_t *)ctx->sp_dev.p + offs_at, offs, offs_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));           // (the caller's arrays may go away)
+        ctx->sp_cache_blob.assign(blob, blob + blob_bytes); ctx->sp_cache_offs.assign(offs, offs + n_sp + 1);
+    }
     for (int i = 0; i < n_sp; i++) if (offs[i + 1] - offs[i] > *max_len) *max_len = offs[i + 1] - offs[i];
-    *blob_dev = (const uint8_t *)ctx->tmp2.p;
-    *offs_dev = (const u32 *)((uint8_t *)ctx->tmp2.p + offs_at);
+    *blob_dev = (const uint8_t *)ctx->sp_dev.p;
+    *offs_dev = (const u32 *)((uint8_t *)ctx->sp_dev.p + offs_at);
     return BPE_OK;
 }
 
@@ -209,8 +218,7 @@ int ctx_run_flags(bpe_ctx *ctx, u64 *n_io, bool translate_newlines, const uint8_
         const uint8_t *text = (const uint8_t *)ctx->text.p + BPE_PAD;
         u64 fw = flag_words(n);
         BPE_TRY(bpe_buf_reserve(ctx, ctx->flags, fw * sizeof(u32)));
-        host[0] = ~0ull; host[1] = 0;
-        CUDA_TRY(ctx, cudaMemcpyAsync(scr, host, 16, cudaMemcpyHostToDevice, st));
+        { PokeVals pv{}; pv.v[0] = ~0ull; pv.v[1] = 0; launch_poke(scr, pv, 2, st); }
         const u32 *spmask = nullptr, *spstart = nullptr;
         if (n_sp > 0 && sp_max_len > 0) {
             BPE_TRY(bpe_buf_reserve(ctx, ctx->spmask, fw * sizeof(u32)));
@@ -228,8 +236,8 @@ int ctx_run_flags(bpe_ctx *ctx, u64 *n_io, bool translate_newlines, const uint8_
         if (fw > tiles_words)
             CUDA_TRY(ctx, cudaMemsetAsync((u32 *)ctx->flags.p + tiles_words, 0, (fw - tiles_words) * sizeof(u32), st));
         launch_pretok_flags(text, n, spmask, spstart, (u32 *)ctx->flags.p, scr, err_lo, err_hi, ctx->sm_count, st);
+        launch_peek(host, scr, 2, st);
         CUDA_TRY(ctx, cudaGetLastError());
-        CUDA_TRY(ctx, cudaMemcpyAsync(host, scr, 16, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(ctx, cudaStreamSynchronize(st));
         if (pass == 0 && host[0] != ~0ull) {
             ctx->err_detail = (int64_t)host[0];

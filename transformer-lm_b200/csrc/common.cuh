@@ -42,6 +42,8 @@ struct bpe_ctx {
     DevBuf spstart;     // first byte of an accepted special occurrence
     DevBuf scratch;     // small scalars: error words, counters
     DevBuf tmp0, tmp1, tmp2;
+    DevBuf sp_dev;      // the special tokens last uploaded (blob + offsets), with a host copy to tell when they change
+    std::vector<uint8_t> sp_cache_blob; std::vector<uint32_t> sp_cache_offs;
     // double buffering of the host-side entry points: second text arena / output buffers, copy streams, events
     DevBuf text_alt, out_a, out_b;
     cudaStream_t s_in = nullptr, s_out = nullptr;

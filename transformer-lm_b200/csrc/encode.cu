@@ -1055,7 +1055,7 @@ static int cache_build_hot(bpe_tok *tok) {
 static int cache_read_ctr(bpe_tok *tok, u64 *out, int k) {
     bpe_ctx *ctx = tok->ctx;
     u64 *host = (u64 *)ctx->pinned;
-    CUDA_TRY(ctx, cudaMemcpyAsync(host, tok->ctr.p, k * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    launch_peek(host, (const u64 *)tok->ctr.p, k, ctx->stream);
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < k; i++) out[i] = host[i];
     return BPE_OK;
@@ -1231,11 +1231,13 @@ static int encode_core(bpe_tok *tok, u64 n, int out_dtype, void *out_dev, u64 de
     const u64 words_per_batch = batch_bytes / 32;
     const u64 n_batches = (nw + words_per_batch - 1) / words_per_batch;
     std::vector<u64> ord(n_batches + 1, 0);
-    for (u64 b = 0; b <= n_batches; b++) {
-        u64 w = std::min(nw, b * words_per_batch);
-        CUDA_TRY(ctx, cudaMemcpyAsync(&ord[b], pre + w, 8, cudaMemcpyDeviceToHost, st));
+    {
+        u64 *host = (u64 *)ctx->pinned;          // (kernel writes into page-locked memory: no copy engine, see launch_peek)
+        if ((n_batches + 1) * 8 > ctx->pinned_cap) return bpe_set_error(ctx, BPE_ERR_UNSUPPORTED, "text too large for one call (%llu batches)", (unsigned long long)n_batches);
+        for (u64 b = 0; b <= n_batches; b++) launch_peek(host + b, pre + std::min(nw, b * words_per_batch), 1, st);
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        for (u64 b = 0; b <= n_batches; b++) ord[b] = host[b];
     }
-    CUDA_TRY(ctx, cudaStreamSynchronize(st));
     int e2 = tm.mark();
     const u64 n_pretok = ord[n_batches];
     if (!tok->cache_ready) BPE_TRY(cache_reset(tok));
@@ -1312,9 +1314,9 @@ static int encode_core(bpe_tok *tok, u64 n, int out_dtype, void *out_dev, u64 de
                 else KLAUNCH((k_enc_scan_emit<int32_t, true>), (unsigned)n_tiles, SE_NT, 0, st, t, vals, bound, ord[b], tile_state, ticket, (int32_t *)out_dev, total_tokens, dev_cap, total_dev);
             }
             CUDA_TRY(ctx, cudaGetLastError());
-            CUDA_TRY(ctx, cudaMemcpyAsync(host, total_dev, 8, cudaMemcpyDeviceToHost, st));
+            launch_peek(host, total_dev, 1, st);
         }
-        CUDA_TRY(ctx, cudaMemcpyAsync(host + 1, (u64 *)tok->ctr.p + 7, 8, cudaMemcpyDeviceToHost, st));
+        launch_peek(host + 1, (u64 *)tok->ctr.p + 7, 1, st);
         CUDA_TRY(ctx, cudaStreamSynchronize(st));
         const u64 batch_tokens = host[0], err_ord = host[1];
         if (err_ord != ~0ull) {

@@ -17,6 +17,15 @@ void launch_scan_u32(const u32 *in, u64 n, u64 *out, u64 *tmp, cudaStream_t st);
 void launch_starts_to_offsets(const u32 *flags, u64 word_begin, u64 word_end, u64 n, const u64 *pre, u64 base, u32 *offs, u64 n_items,
                               int sm_count, cudaStream_t st);
 size_t scan_tmp_elems_host(u64 n);
+// Small control words WITHOUT the copy engines: while the pipelined entry points stream 256 MB chunks over PCIe, a 16-byte
+// cudaMemcpyAsync on the compute stream queues behind the chunk in flight on the same copy engine and stalls the kernels after it
+// for milliseconds (measured: upload and encode of bpe_encode ran one after the other, 280 ms instead of ~215 per 10 GB).
+//   launch_poke: dst[0..n) = vals (device memory, n <= 8) by a one-thread kernel
+//   launch_peek: host_dst[i] = src[idx ? idx[i] : i] -- the kernel writes straight into page-locked host memory (unified addressing);
+//                valid after the stream has been synchronised
+struct PokeVals { u64 v[8]; };
+void launch_poke(u64 *dst, const PokeVals &vals, int n, cudaStream_t st);
+void launch_peek(u64 *host_dst, const u64 *src, int n, cudaStream_t st);
 
 // Geometry of the padded text arena (see common.cuh): payload at arena + BPE_PAD, 0xFF everywhere else,
 // readable up to arena_bytes(n).

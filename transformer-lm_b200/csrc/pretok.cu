@@ -370,6 +370,14 @@ __global__ void __launch_bounds__(256) k_flags_to_offsets(const u32 *__restrict_
         }
     }
 }
+__global__ void k_poke(u64 *dst, PokeVals vals, int n) { if (threadIdx.x < (u32)n) dst[threadIdx.x] = vals.v[threadIdx.x]; }
+__global__ void k_peek(u64 *host_dst, const u64 *__restrict__ src, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) host_dst[i] = src[i];
+    __threadfence_system();
+}
+void launch_poke(u64 *dst, const PokeVals &vals, int n, cudaStream_t st) { KLAUNCH(k_poke, 1, 32, 0, st, dst, vals, n); }
+void launch_peek(u64 *host_dst, const u64 *src, int n, cudaStream_t st) { KLAUNCH(k_peek, 1, 64, 0, st, host_dst, src, n); }
+
 void launch_popc_words(const u32 *flags, u64 n_words, u32 *cnt, int sm_count, cudaStream_t st) {
     u64 grid = (n_words + 255) / 256, capg = (u64)sm_count * bpe_grid_mult(64);
     if (grid > capg) grid = capg;
