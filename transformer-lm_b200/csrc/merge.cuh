@@ -506,19 +506,36 @@ __device__ __forceinline__ u32 bucket_of(u32 x, u32 lg) { return (x * 0x9E3779B1
 // offsets for the r merges [step0, step0 + r) that wrote it.  Called by every thread of every CTA between two steps; `sync` is
 // the grid barrier.  s_scan: SORT_MAX_BK u32 of shared memory.  parity alternates so that the scratch of the previous sort can
 // be cleared here.
+// Both passes go through SHARED-MEMORY histograms: neighbour tokens are Zipfian, so a tenth of a slice's records can share one
+// bucket, and one global atomic per record serialised on those few addresses (ncu: 31 % of all stall samples of the merge loop sat in
+// this function).  Pass 1: every CTA counts its records (record i belongs to thread i mod gstride in both passes) per bucket in
+// shared memory and reserves its part of every bucket with ONE global atomic per (CTA, non-empty bucket).  Pass 2: slot = bucket
+// start + the CTA's part + a shared-memory cursor.  s_h / s_base: SORT_MAX_BK u32 of shared memory each.
 template <typename SyncFn>
 __device__ __forceinline__ void sort_slice(int step0, u32 r, u64 lo, u32 n, u32 parity, bool leader_cta, u64 gthread, u64 gstride,
-                                           u32 *s_scan, u32 *s_wsum, SyncFn sync) {
+                                           u32 *s_scan, u32 *s_wsum, u32 *s_h, u32 *s_base, SyncFn sync) {
     u32 lg = 4;
     while ((64u << lg) < n && lg < SORT_MAX_LG) lg++;
     const u32 nbk = 1u << lg;
-    u32 *hist = cM.bk_scratch + (size_t)parity * 2 * SORT_MAX_BK, *cur = hist + SORT_MAX_BK;
+    const u32 tid = threadIdx.x;
+    u32 *hist = cM.bk_scratch + (size_t)parity * 2 * SORT_MAX_BK;
     u32 *other = cM.bk_scratch + (size_t)(parity ^ 1u) * 2 * SORT_MAX_BK;
-    for (u64 i = gthread; i < n; i += gstride) atomicAdd(&hist[bucket_of(cM.log[lo + i].x, lg)], 1u);
+    for (u32 i = tid; i < nbk; i += MG_NT) s_h[i] = 0;
+    __syncthreads();
+    {
+        u64 i = gthread;
+        for (; i + 3 * gstride < n; i += 4 * gstride) {              // four records in flight per thread
+            const u32 x0 = cM.log[lo + i].x, x1 = cM.log[lo + i + gstride].x, x2 = cM.log[lo + i + 2 * gstride].x, x3 = cM.log[lo + i + 3 * gstride].x;
+            atomicAdd(&s_h[bucket_of(x0, lg)], 1u); atomicAdd(&s_h[bucket_of(x1, lg)], 1u);
+            atomicAdd(&s_h[bucket_of(x2, lg)], 1u); atomicAdd(&s_h[bucket_of(x3, lg)], 1u);
+        }
+        for (; i < n; i += gstride) atomicAdd(&s_h[bucket_of(cM.log[lo + i].x, lg)], 1u);
+    }
+    __syncthreads();
+    for (u32 i = tid; i < nbk; i += MG_NT) { const u32 c = s_h[i]; s_base[i] = c ? atomicAdd(&hist[i], c) : 0u; s_h[i] = 0; }
     for (u64 i = gthread; i < 2 * SORT_MAX_BK; i += gstride) other[i] = 0;       // last used two barriers ago
     sync();
     // exclusive scan of the histogram, redundantly in every CTA
-    const u32 tid = threadIdx.x;
     const u32 per = (nbk + MG_NT - 1) / MG_NT;   // <= 8
     u32 v[8], sum = 0;
 #pragma unroll
@@ -548,10 +565,19 @@ __device__ __forceinline__ void sort_slice(int step0, u32 r, u64 lo, u32 n, u32 
         for (u32 j = 0; j < r; j++) { cM.bk_start[step0 + j] = pool; cM.bk_lg[step0 + j] = lg; }
     }
     __syncthreads();
-    for (u64 i = gthread; i < n; i += gstride) {
-        const uint4 rec = *reinterpret_cast<const uint4 *>(&cM.log[lo + i]);
-        const u32 bk = bucket_of(rec.x, lg);
-        *reinterpret_cast<uint4 *>(&cM.log2[lo + s_scan[bk] + atomicAdd(&cur[bk], 1u)]) = rec;
+    {
+        u64 i = gthread;
+        for (; i + gstride < n; i += 2 * gstride) {                  // two records in flight per thread
+            const uint4 r0 = *reinterpret_cast<const uint4 *>(&cM.log[lo + i]), r1 = *reinterpret_cast<const uint4 *>(&cM.log[lo + i + gstride]);
+            const u32 b0 = bucket_of(r0.x, lg), b1 = bucket_of(r1.x, lg);
+            *reinterpret_cast<uint4 *>(&cM.log2[lo + s_scan[b0] + s_base[b0] + atomicAdd(&s_h[b0], 1u)]) = r0;
+            *reinterpret_cast<uint4 *>(&cM.log2[lo + s_scan[b1] + s_base[b1] + atomicAdd(&s_h[b1], 1u)]) = r1;
+        }
+        for (; i < n; i += gstride) {
+            const uint4 rec = *reinterpret_cast<const uint4 *>(&cM.log[lo + i]);
+            const u32 bk = bucket_of(rec.x, lg);
+            *reinterpret_cast<uint4 *>(&cM.log2[lo + s_scan[bk] + s_base[bk] + atomicAdd(&s_h[bk], 1u)]) = rec;
+        }
     }
     sync();
 }
@@ -839,7 +865,7 @@ __device__ __forceinline__ void token_bookkeeping(int step0, u32 nw0, const Batc
 #define MG_CACHE_ITERS 4u                        // chunks (of 64 blocks) per warp kept in shared memory; more are read from bmax
 #define MG_CACHE_N (MG_CACHE_ITERS * (MG_NT / 32) * 64u)
 #define MG_LIST_CAP 2048u                        // dirty blocks a CTA lists per step; the overflow is rescanned by the owning warp
-#define MG_DYN_SMEM ((size_t)MG_CACHE_N * 36 + (size_t)MG_LIST_CAP * 4)
+#define MG_DYN_SMEM ((size_t)MG_CACHE_N * 36 + (size_t)MG_LIST_CAP * 4 + (size_t)SORT_MAX_BK * 8)    // cached block maxima, dirty list, the sort's two histograms
 struct BmaxCache { i64 *cnt; u64 *key, *ka, *kb; u32 *sec; };
 __device__ __forceinline__ BmaxCache bmax_cache(unsigned char *base) {
     BmaxCache c;
@@ -892,6 +918,7 @@ __global__ void __launch_bounds__(MG_NT) k_merge_loop() {
     // 64 blocks starting at (it * total_warps + gwarp) * 64); bmax / bsec in global memory are written through for the next launch.
     const BmaxCache sc = bmax_cache(mg_smem);
     u32 *s_list = reinterpret_cast<u32 *>(mg_smem + (size_t)MG_CACHE_N * 36);
+    u32 *s_sort_h = s_list + MG_LIST_CAP, *s_sort_base = s_sort_h + SORT_MAX_BK;
     const u32 n_iter = (cM.n_blocks + total_warps * 64 - 1) / (total_warps * 64);
     for (u32 it = 0; it < n_iter && it < MG_CACHE_ITERS; it++) {
         const u32 base = (it * total_warps + gwarp) * 64, i0 = (it * warps_per_cta + warp) * 64 + lane;
@@ -1031,7 +1058,7 @@ __global__ void __launch_bounds__(MG_NT) k_merge_loop() {
             const u64 pool = *((volatile u64 *)&cM.ctr[9]);
             if (cur - lb >= cM.sort_min && cur <= cM.log_cap && pool + SORT_MAX_BK + 1 <= cM.bk_off_cap) {
                 sort_slice(step, r, lb, (u32)(cur - lb), n_sorts & 1u, blockIdx.x == 0, (u64)blockIdx.x * MG_NT + tid, (u64)G * MG_NT, s_scan, s_wsum,
-                           [&]() { grid_barrier(cM.bar_ctr, G, ++epoch); });
+                           s_sort_h, s_sort_base, [&]() { grid_barrier(cM.bar_ctr, G, ++epoch); });
                 n_sorts++;
             }
         }
