@@ -222,7 +222,12 @@ __device__ __forceinline__ bool enc_hot_get(const EncTables &t, u64 k0, u64 k1, 
 #define LK_WARPS (LK_NT / 32u)
 #define LK_SM_LG 12
 #define LK_SM_SLOTS (1u << LK_SM_LG)
+#ifndef LK_SM_FILL_NUM
+#define LK_SM_FILL_NUM 6u                         // eighths of the image that may be filled
+#endif
+#ifndef LK_SM_PROBES
 #define LK_SM_PROBES 2u
+#endif
 #define LK_TICKET 8u                             // steps (of 512 bytes) per ticket
 #define LK_QCAP 96u                              // entries of the warp's key queue
 #define LK_QDRAIN 64u                            // drained when it reaches this (a round of the bit loop adds <= 32)
@@ -1041,7 +1046,7 @@ static int cache_build_hot(bpe_tok *tok) {
         CUDA_TRY(ctx, cudaMemcpyAsync(host, h2, 256 * sizeof(u64), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(ctx, cudaStreamSynchronize(st));
         u64 acc = 0; u32 min_bucket = 256;
-        for (int k = 255; k >= 2; k--) { if (acc + host[k] > LK_SM_SLOTS * 3 / 4) break; acc += host[k]; min_bucket = (u32)k; }
+        for (int k = 255; k >= 2; k--) { if (acc + host[k] > LK_SM_SLOTS * LK_SM_FILL_NUM / 8) break; acc += host[k]; min_bucket = (u32)k; }
         BPE_TRY(alloc_exact_e(ctx, tok->sm_img, (size_t)LK_SM_SLOTS * 16));
         CUDA_TRY(ctx, cudaMemsetAsync(tok->sm_img.p, 0, (size_t)LK_SM_SLOTS * 16, st));
         if (min_bucket < 256) KLAUNCH(k_enc_sm_build, g, 256, 0, st, t, (ulonglong2 *)tok->sm_img.p, min_bucket);
