@@ -144,7 +144,7 @@ def ncu_traffic(kernel: str, config: dict):
         tj = json.loads((ROOT / "profiles" / "r2_traffic.json").read_text())
         kernel = kernel.split("<")[0]
         for e in tj["captures"]:
-            if e["kernel"] == kernel and all(e["config"].get(k) == v for k, v in config.items() if k in e["config"]) and e["config"].get("n_gpus") == config.get("n_gpus"):
+            if e["kernel"] == kernel and all(k in e["config"] and e["config"][k] == v for k, v in config.items()):
                 return e["dram_bytes_per_step"], "%s; %d launch(es) per step" % (e["source"], e["launches_per_step"])
     except Exception:
         pass
