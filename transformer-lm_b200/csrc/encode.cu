@@ -1234,12 +1234,20 @@ static int encode_core(bpe_tok *tok, u64 n, int out_dtype, void *out_dev, u64 de
     static const u64 batch_bytes = getenv("BPE_ENC_BATCH_KB") ? std::max<u64>(1, (u64)atoll(getenv("BPE_ENC_BATCH_KB"))) << 10 : ENC_BATCH_BYTES;
     static const u64 hot_min_batch = getenv("BPE_ENC_HOT_MIN") ? (u64)atoll(getenv("BPE_ENC_HOT_MIN")) : ENC_HOT_MIN_BATCH;
     const u64 words_per_batch = batch_bytes / 32;
-    const u64 n_batches = (nw + words_per_batch - 1) / words_per_batch;
+    // batch boundaries (flag words).  While the hot table is still to be built the first batch is a small one (64 MB: enough pretokens
+    // to sample), so that the cold start -- every lookup a probe of the big tables -- is over after a quarter of a normal batch.
+    std::vector<u64> bw{0};
+    if (nw) {
+        u64 w = std::min(nw, tok->hot_built ? words_per_batch : std::min<u64>(words_per_batch, (64ull << 20) / 32));
+        bw.push_back(w);
+        while (w < nw) { w = std::min(nw, w + words_per_batch); bw.push_back(w); }
+    }
+    const u64 n_batches = bw.size() - 1;
     std::vector<u64> ord(n_batches + 1, 0);
     {
         u64 *host = (u64 *)ctx->pinned;          // (kernel writes into page-locked memory: no copy engine, see launch_peek)
         if ((n_batches + 1) * 8 > ctx->pinned_cap) return bpe_set_error(ctx, BPE_ERR_UNSUPPORTED, "text too large for one call (%llu batches)", (unsigned long long)n_batches);
-        for (u64 b = 0; b <= n_batches; b++) launch_peek(host + b, pre + std::min(nw, b * words_per_batch), 1, st);
+        for (u64 b = 0; b <= n_batches; b++) launch_peek(host + b, pre + bw[b], 1, st);
         CUDA_TRY(ctx, cudaStreamSynchronize(st));
         for (u64 b = 0; b <= n_batches; b++) ord[b] = host[b];
     }
@@ -1254,7 +1262,7 @@ static int encode_core(bpe_tok *tok, u64 n, int out_dtype, void *out_dev, u64 de
     for (auto &e : evs) CUDA_TRY(ctx, cudaEventCreate(&e));
     struct EvGuard { cudaEvent_t *e; ~EvGuard() { for (int i = 0; i < 4; i++) cudaEventDestroy(e[i]); } } evg{evs};
     for (u64 b = 0; b < n_batches; b++) {
-        const u64 b_lo = b * words_per_batch, b_hi = std::min(nw, b_lo + words_per_batch);
+        const u64 b_lo = bw[b], b_hi = bw[b + 1];
         const u64 bound = ord[b + 1] - ord[b];
         const u64 bytes = (b_hi - b_lo) * 32;
         BPE_TRY(cache_read_ctr(tok, c, 9));

@@ -880,25 +880,38 @@ static int count_current_text(bpe_ctx *ctx, u64 n, u64 own_begin, u64 own_end, u
     u64 w_lo = own_begin / 32, w_hi = (own_end + 31) / 32;
     // (test knobs: BPE_COUNT_BATCH_KB = batch size, BPE_COUNT_HOT_AFTER = pretokens before the hot table is first built)
     static const u64 batch_bytes = getenv("BPE_COUNT_BATCH_KB") ? std::max<u64>(1, (u64)atoll(getenv("BPE_COUNT_BATCH_KB"))) << 10 : COUNT_BATCH_BYTES;
-    static const u64 hot_after = getenv("BPE_COUNT_HOT_AFTER") ? (u64)atoll(getenv("BPE_COUNT_HOT_AFTER")) : (16ull << 20);
-    u64 words_per_batch = batch_bytes / 32;
-    u64 n_batches = (w_hi - w_lo + words_per_batch - 1) / words_per_batch;
-    // per-batch upper bound of new uniques = number of start bits
-    BPE_TRY(bpe_buf_reserve(ctx, ctx->tmp0, n_batches * sizeof(u64)));
-    CUDA_TRY(ctx, cudaMemsetAsync(ctx->tmp0.p, 0, n_batches * sizeof(u64), st));
+    static const u64 hot_after = getenv("BPE_COUNT_HOT_AFTER") ? (u64)atoll(getenv("BPE_COUNT_HOT_AFTER")) : (8ull << 20);
+    const u64 words_per_batch = batch_bytes / 32;
+    // start bits are counted per RANGE (a quarter of a batch): while no hot table exists the first batch is one range only, so that
+    // the cold start -- every queued word a probe of the big tables -- lasts 64 MB instead of 256
+    const u64 words_per_range = words_per_batch % 4 == 0 && words_per_batch >= 4 ? words_per_batch / 4 : words_per_batch;
+    const u64 ranges_per_batch = words_per_batch / words_per_range;
+    const u64 n_ranges = (w_hi - w_lo + words_per_range - 1) / words_per_range;
+    // per-range upper bound of new uniques = number of start bits
+    BPE_TRY(bpe_buf_reserve(ctx, ctx->tmp0, n_ranges * sizeof(u64)));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->tmp0.p, 0, n_ranges * sizeof(u64), st));
     {
-        dim3 grid((unsigned)std::min<u64>(ctx->sm_count * 4, (words_per_batch + 255) / 256), (unsigned)n_batches);
-        KLAUNCH(k_popc_ranges, grid, 256, 0, st, (const u32 *)ctx->flags.p + w_lo, w_hi - w_lo, words_per_batch, (u64 *)ctx->tmp0.p);
+        dim3 grid((unsigned)std::min<u64>(ctx->sm_count * 4, (words_per_range + 255) / 256), (unsigned)n_ranges);
+        KLAUNCH(k_popc_ranges, grid, 256, 0, st, (const u32 *)ctx->flags.p + w_lo, w_hi - w_lo, words_per_range, (u64 *)ctx->tmp0.p);
     }
-    std::vector<u64> bound(n_batches);
-    CUDA_TRY(ctx, cudaMemcpyAsync(bound.data(), ctx->tmp0.p, n_batches * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    std::vector<u64> rbound(n_ranges);
+    CUDA_TRY(ctx, cudaMemcpyAsync(rbound.data(), ctx->tmp0.p, n_ranges * sizeof(u64), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    std::vector<u64> bstart{0}, bound;           // batches: first range index of each, start bits of each
+    for (u64 r0 = 0; r0 < n_ranges;) {
+        const u64 k = (r0 == 0 && cs->hot_builds == 0) ? 1 : ranges_per_batch, r1 = std::min(n_ranges, r0 + k);
+        u64 sum = 0;
+        for (u64 r = r0; r < r1; r++) sum += rbound[r];
+        bound.push_back(sum); bstart.push_back(r1);
+        r0 = r1;
+    }
+    const u64 n_batches = bound.size();
     u64 c[8];
     BPE_TRY(read_counters(ctx, c, 8));
     static const bool prof = getenv("BPE_COUNT_PROFILE") != nullptr;
     for (u64 bi = 0; bi < n_batches; bi++) {
         const double tb0 = prof ? now_ms() : 0;
-        u64 b_lo = w_lo + bi * words_per_batch, b_hi = std::min(w_hi, b_lo + words_per_batch);
+        u64 b_lo = w_lo + bstart[bi] * words_per_range, b_hi = std::min(w_hi, w_lo + bstart[bi + 1] * words_per_range);
         u64 bytes = (b_hi - b_lo) * 32;
         static const u64 bound_div = getenv("BPE_COUNT_BOUND_DIV") ? std::max(1, atoi(getenv("BPE_COUNT_BOUND_DIV"))) : 1;   // EXPERIMENT ONLY (unsafe)
         BPE_TRY(count_ensure_capacity(ctx, c, bound[bi] / bound_div, std::min(bound[bi], bytes / (SHORT_MAX + 1) + 1) / bound_div));
