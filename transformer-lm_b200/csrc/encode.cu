@@ -293,8 +293,8 @@ __device__ __forceinline__ void lookup_drain(const EncTables &t, LookupQueues &q
     __syncwarp();
 }
 
-// chunks [c_lo, c_hi) (16 bytes each, absolute positions 16 c; c_lo even); pre[w] = ordinal of the first pretoken of flag word w
-// (pre and flags are indexed by absolute word), ord0 = ordinal of the batch's first pretoken, base = 16 c_lo
+// chunks [c_lo, c_hi) (16 bytes each, absolute positions 16 c; c_lo a multiple of 32); pre[g] = ordinal of the first pretoken of the
+// g-th group of 32 chunks (absolute), ord0 = ordinal of the batch's first pretoken, base = 16 c_lo
 __global__ void __launch_bounds__(LK_NT, 1) k_enc_lookup(EncTables t, const u32 *__restrict__ flags, const u64 *__restrict__ pre, u64 ord0,
                                                         u64 c_lo, u64 c_hi, u64 n, u64 base, u64 *__restrict__ vals) {
     extern __shared__ __align__(16) unsigned char lk_smem[];
@@ -320,17 +320,22 @@ __global__ void __launch_bounds__(LK_NT, 1) k_enc_lookup(EncTables t, const u32 
         const u64 c = c_lo + (tk * LK_TICKET + sub) * 32u + lane;
         const bool live = c < c_hi;
         const u64 p0 = c * 16u;
-        uint4 A = make_uint4(0, 0, 0, 0), B = A; u32 f0 = 0, f1 = 0; u64 ordw = 0;
+        uint4 A = make_uint4(0, 0, 0, 0), B = A; u32 f0 = 0, f1 = 0;
+        const u64 ordg = __ldcs(pre + ((c - lane) >> 5));            // (one word per step, the same for all lanes)
         if (live) {
             const uint4 *tp = reinterpret_cast<const uint4 *>(t.text + p0);
             A = __ldcs(tp); B = __ldcs(tp + 1);
-            const u64 w = c >> 1; f0 = __ldcs(flags + w); f1 = w + 1 < n_fw ? __ldcs(flags + w + 1) : 0u; ordw = __ldcs(pre + w);
+            const u64 w = c >> 1; f0 = __ldcs(flags + w); f1 = w + 1 < n_fw ? __ldcs(flags + w + 1) : 0u;
         }
         const u32 W0 = A.x, W1 = A.y, W2 = A.z, W3 = A.w, W4 = B.x, W5 = B.y, W6 = B.z, W7 = B.w;
         u64 F = (((u64)f1 << 32) | f0) >> (u32)(p0 & 16u);           // bit i: a pretoken starts at byte p0 + i (>= 48 bits)
         if (p0 + 64 > n) F = p0 < n ? F & ((1ull << (n - p0)) - 1ull) : 0ull;   // bits past the end of the text do not count
         const u32 mall = live ? (u32)F & 0xFFFFu : 0u;
-        const u32 ordc = (u32)(ordw - ord0) + ((c & 1u) ? __popc(f0 & 0xFFFFu) : 0u);   // ordinal of the chunk's first pretoken in the batch
+        // ordinal of the chunk's first pretoken in the batch: the step's + the start bits of the lanes before this one
+        u32 incl = __popc(mall);
+#pragma unroll
+        for (u32 d = 1; d < 32; d <<= 1) { const u32 o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+        const u32 ordc = (u32)(ordg - ord0) + incl - __popc(mall);
         u32 m = mall;
         while (__any_sync(0xffffffffu, m != 0)) {
             const bool act = m != 0;
@@ -1220,15 +1225,16 @@ static int encode_core(bpe_tok *tok, u64 n, int out_dtype, void *out_dev, u64 de
     BPE_TRY(ctx_upload_specials(ctx, tok->sp_blob_h.data(), tok->sp_offs_h.data(), tok->n_sp, &spb, &spo, &spmax));
     u64 nn = n;
     BPE_TRY(ctx_run_flags(ctx, &nn, false, spb, spo, tok->n_sp, spmax));
-    // ordinal of the first pretoken of every flag word
-    const u64 nw = (n + 31) / 32;
-    size_t cnt_b = round_up((nw + 1) * sizeof(u32), 256), pre_b = round_up((nw + 2) * sizeof(u64), 256);
-    BPE_TRY(bpe_buf_reserve(ctx, ctx->tmp0, cnt_b + pre_b + scan_tmp_elems_host(nw) * sizeof(u64)));
+    // ordinal of the first pretoken of every GROUP of 16 flag words (512 bytes of text = one warp step of the lookup kernel, which
+    // gets the ordinals inside a step from a warp scan): a scan over N / 512 entries instead of N / 32
+    const u64 nw = (n + 31) / 32, ng = (nw + 15) / 16;
+    size_t cnt_b = round_up((ng + 1) * sizeof(u32), 256), pre_b = round_up((ng + 2) * sizeof(u64), 256);
+    BPE_TRY(bpe_buf_reserve(ctx, ctx->tmp0, cnt_b + pre_b + scan_tmp_elems_host(ng) * sizeof(u64)));
     u32 *cnt = (u32 *)ctx->tmp0.p;
     u64 *pre = (u64 *)((uint8_t *)ctx->tmp0.p + cnt_b);
     u64 *scan_tmp = (u64 *)((uint8_t *)ctx->tmp0.p + cnt_b + pre_b);
-    launch_popc_words((const u32 *)ctx->flags.p, nw, cnt, ctx->sm_count, st);
-    launch_scan_u32(cnt, nw, pre, scan_tmp, st);
+    launch_popc_words16((const u32 *)ctx->flags.p, ng, cnt, ctx->sm_count, st);
+    launch_scan_u32(cnt, ng, pre, scan_tmp, st);
     CUDA_TRY(ctx, cudaGetLastError());
     // (test knobs: BPE_ENC_BATCH_KB = batch size, BPE_ENC_HOT_MIN = pretokens a batch needs to be sampled for the hot table)
     static const u64 batch_bytes = getenv("BPE_ENC_BATCH_KB") ? std::max<u64>(1, (u64)atoll(getenv("BPE_ENC_BATCH_KB"))) << 10 : ENC_BATCH_BYTES;
@@ -1247,7 +1253,7 @@ static int encode_core(bpe_tok *tok, u64 n, int out_dtype, void *out_dev, u64 de
     {
         u64 *host = (u64 *)ctx->pinned;          // (kernel writes into page-locked memory: no copy engine, see launch_peek)
         if ((n_batches + 1) * 8 > ctx->pinned_cap) return bpe_set_error(ctx, BPE_ERR_UNSUPPORTED, "text too large for one call (%llu batches)", (unsigned long long)n_batches);
-        for (u64 b = 0; b <= n_batches; b++) launch_peek(host + b, pre + bw[b], 1, st);
+        for (u64 b = 0; b <= n_batches; b++) launch_peek(host + b, pre + (bw[b] + 15) / 16, 1, st);   // (boundaries are multiples of 16 words, or the end)
         CUDA_TRY(ctx, cudaStreamSynchronize(st));
         for (u64 b = 0; b <= n_batches; b++) ord[b] = host[b];
     }
@@ -1336,17 +1342,24 @@ static int encode_core(bpe_tok *tok, u64 n, int out_dtype, void *out_dev, u64 de
             // KeyError (tokenizer.py:120,135): report the key of the first failing pretoken in text order.  Its byte offset: the
             // flag word that holds that ordinal (binary search in the scanned word counts), then the matching start bit.
             u64 hv[2] = {0, 0};
-            u64 lo = 0, hi = nw;                 // largest w with pre[w] <= err_ord
+            u64 lo = 0, hi = ng;                 // largest group g with pre[g] <= err_ord
             while (hi - lo > 1) {
                 const u64 mid = lo + (hi - lo) / 2; u64 pm = 0;
                 CUDA_TRY(ctx, cudaMemcpy(&pm, pre + mid, 8, cudaMemcpyDeviceToHost));
                 if (pm <= err_ord) lo = mid; else hi = mid;
             }
-            u64 hpre = 0; u32 hflags = 0;
+            u64 hpre = 0; u32 hfl[16];
             CUDA_TRY(ctx, cudaMemcpy(&hpre, pre + lo, 8, cudaMemcpyDeviceToHost));
-            CUDA_TRY(ctx, cudaMemcpy(&hflags, (const u32 *)ctx->flags.p + lo, 4, cudaMemcpyDeviceToHost));
-            for (u64 k = hpre; k < err_ord; k++) hflags &= hflags - 1;
-            const u64 err_pos = lo * 32 + (hflags ? (u64)__builtin_ctz(hflags) : 0);
+            CUDA_TRY(ctx, cudaMemcpy(hfl, (const u32 *)ctx->flags.p + 16 * lo, sizeof(hfl), cudaMemcpyDeviceToHost));
+            u64 err_pos = 16 * lo * 32, skip = err_ord - hpre;
+            for (int k = 0; k < 16; k++) {
+                const u64 pc = (u64)__builtin_popcount(hfl[k]);
+                if (skip >= pc) { skip -= pc; continue; }
+                u32 f = hfl[k];
+                while (skip--) f &= f - 1;
+                err_pos = (16 * lo + k) * 32 + (u64)__builtin_ctz(f);
+                break;
+            }
             CUDA_TRY(ctx, cudaMemcpy(&hv[0], vals + (err_ord - ord[b]), 8, cudaMemcpyDeviceToHost));
             if (VAL_TAG(hv[0]) == VAL_FWD) {     // a forward reference: the value sits in the slot
                 const u32 ref = (u32)hv[0];

@@ -12,6 +12,7 @@ u64  newline_tiles(u64 n);
 void launch_special_split(const uint8_t *text, u64 n, const uint8_t *sp_blob_dev, const u32 *sp_offs_dev, int n_sp,
                           u32 max_len, u32 *cand, u32 *spstart, u32 *spmask, u64 n_words, int sm_count, cudaStream_t st);
 void launch_popc_words(const u32 *flags, u64 n_words, u32 *cnt, int sm_count, cudaStream_t st);
+void launch_popc_words16(const u32 *flags, u64 n_groups, u32 *cnt, int sm_count, cudaStream_t st);
 void launch_flags_to_offsets(const u32 *flags, u64 n_words, const u64 *pre, u64 *out, u64 cap, int sm_count, cudaStream_t st);
 void launch_scan_u32(const u32 *in, u64 n, u64 *out, u64 *tmp, cudaStream_t st);
 void launch_starts_to_offsets(const u32 *flags, u64 word_begin, u64 word_end, u64 n, const u64 *pre, u64 base, u32 *offs, u64 n_items,

@@ -378,6 +378,23 @@ __global__ void k_peek(u64 *host_dst, const u64 *__restrict__ src, int n) {
 void launch_poke(u64 *dst, const PokeVals &vals, int n, cudaStream_t st) { KLAUNCH(k_poke, 1, 32, 0, st, dst, vals, n); }
 void launch_peek(u64 *host_dst, const u64 *src, int n, cudaStream_t st) { KLAUNCH(k_peek, 1, 64, 0, st, host_dst, src, n); }
 
+// cnt[g] = start bits in flag words [16 g, 16 g + 16) = pretokens that start in 512 bytes of text (one warp step of the encoder's
+// lookup); the caller guarantees that the words up to the next multiple of 16 exist and are zero past the text
+__global__ void __launch_bounds__(256) k_popc_words16(const u32 *__restrict__ flags, u64 n_groups, u32 *__restrict__ cnt) {
+    for (u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += (u64)gridDim.x * blockDim.x) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(flags + 16 * g);
+        u32 c = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const uint4 v = p[k]; c += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w); }
+        cnt[g] = c;
+    }
+}
+void launch_popc_words16(const u32 *flags, u64 n_groups, u32 *cnt, int sm_count, cudaStream_t st) {
+    u64 grid = (n_groups + 255) / 256, cap = (u64)sm_count * bpe_grid_mult(64);
+    if (grid > cap) grid = cap;
+    if (grid) KLAUNCH(k_popc_words16, (unsigned)grid, 256, 0, st, flags, n_groups, cnt);
+}
+
 void launch_popc_words(const u32 *flags, u64 n_words, u32 *cnt, int sm_count, cudaStream_t st) {
     u64 grid = (n_words + 255) / 256, capg = (u64)sm_count * bpe_grid_mult(64);
     if (grid > capg) grid = capg;
