@@ -143,6 +143,14 @@ int bpe_count_pair_table(bpe_ctx *ctx, const uint8_t *specials_blob, const uint3
 /* Merge loop over whatever has been counted/imported so far. */
 int bpe_train_from_counts(bpe_ctx *ctx, const uint8_t *specials_blob, const uint32_t *special_offs, int n_specials,
                           int n_merges, int32_t *merge_pairs_out, int *n_done, bpe_train_stats *stats);
+/* Live view of the merge loop (train.py:183-228 appends to `merges` one pair at a time; a host that has to turn the symbol ids into
+ * its own objects -- the reference's `list[tuple[bytes, bytes]]` and vocab dict -- can do so WHILE the loop runs instead of after it).
+ * During the merge loop of every later bpe_train / bpe_train_dev / bpe_train_from_counts call on this context the kernel stores merge
+ * k's symbol ids into live_pairs[2k], [2k+1] with ONE 8-byte store as soon as the merge is made.  live_pairs must be page-locked host
+ * memory (bpe_host_alloc) of capacity_merges entries; the caller fills it with -1 before the training call and treats an entry as
+ * complete when it is non-negative (entries may become visible out of order).  merge_pairs_out of the training call remains the
+ * authoritative result.  NULL switches it off. */
+int bpe_train_set_live(bpe_ctx *ctx, int32_t *live_pairs, int capacity_merges);
 /* The dense 256 x 256 byte-pair table (calculate_byte_pair_frequencies over single bytes, train.py:35-49) that the last
  * bpe_train / bpe_train_dev / bpe_train_from_counts call on this context built before its first merge: the multi-GPU path
  * checks it against the all-reduced per-rank tables of bpe_count_pair_table without building the table a second time. */

@@ -342,3 +342,28 @@ def test_finish_checks_the_expected_pair_table():
     c.expect_pair_table(bad)
     with pytest.raises(RuntimeError):
         c.finish(500, ["<|endoftext|>"])
+
+
+def test_live_view_of_the_merge_loop():
+    """bpe_train_set_live: the kernel stores every merge into page-locked host memory as it is made (the host builds its Python
+    objects beside the loop); the buffer must be page-locked, and what appears there is the result."""
+    import ctypes as C
+    import numpy as np
+    from transformer_lm_b200 import _lib
+    ctx = _lib.default_context(0)
+    L = _lib.lib()
+    plain = np.zeros(64, dtype=np.int32)
+    assert L.bpe_train_set_live(ctx.handle, _lib.ptr(plain), 32) == _lib.ERR_ARG      # pageable memory is refused
+    n_merges = 300
+    live = _lib.PinnedBuffer(n_merges * 8)
+    live.array[:] = 0xFF
+    ctx.check(L.bpe_train_set_live(ctx.handle, _lib.ptr(live.array), n_merges))
+    data = np.frombuffer((FIXTURES_PATH / "corpus.en").read_bytes(), dtype=np.uint8)
+    pairs = np.zeros((n_merges, 2), dtype=np.int32)
+    n_done = C.c_int(0)
+    sp_blob, sp_offs = _lib.pack_blobs([])
+    ctx.check(L.bpe_train(ctx.handle, _lib.ptr(data), data.size, _lib.ptr(sp_blob), _lib.ptr(sp_offs), 0, n_merges, _lib.ptr(pairs), C.byref(n_done), None))
+    ctx.check(L.bpe_train_set_live(ctx.handle, None, 0))
+    assert n_done.value == n_merges
+    assert np.array_equal(live.array.view(np.int32).reshape(n_merges, 2), pairs)
+    live.free()

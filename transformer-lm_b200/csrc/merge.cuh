@@ -127,6 +127,7 @@ struct MergeState {
     int stop_at;                                 // this launch runs merges [ctr[1], stop_at)
     u32 max_batch;                               // merges per step, <= MG_BATCH (BPE_MERGE_BATCH)
     int32_t *merges_out; i64 *merge_cnt_out; int n_merges;
+    int32_t *live_pairs; int live_cap;           // page-locked HOST memory (or null): the merges as they are made, for the host to follow (bpe_train_set_live)
     // [0]=log cursor [1]=n_done (next merge) [2]=pair keys created [3]=status flags [4]=tok bytes cursor
     // [5]=keys popped since the table was last rebuilt [6]=number of keys still to be popped (the last step's winners, in [16..16+MG_BATCH))
     // [7]=sum over merges of the live pair-table keys (the reference's max() scans that many dict entries, train.py:187-189;
@@ -842,6 +843,10 @@ __device__ __forceinline__ void token_bookkeeping(int step0, u32 nw0, const Batc
                 const int step = step0 + (int)j;
                 cM.merges_out[2 * step] = (int32_t)a; cM.merges_out[2 * step + 1] = (int32_t)b;
                 cM.merge_cnt_out[step] = B->cnt[j];
+                // one posted 8-byte store per merge, no fence (a system-scope fence per step cost 2.5 us of a 24 us step): the host
+                // pre-fills the buffer with -1 and takes an entry as complete when it is non-negative
+                if (cM.live_pairs && step < cM.live_cap)
+                    *reinterpret_cast<volatile long long *>(cM.live_pairs + 2 * step) = (long long)(((u64)b << 32) | a);
             }
             // make sure the winner's block is rescanned so the key gets popped
             if (lane == 1) {

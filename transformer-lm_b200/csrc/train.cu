@@ -1165,6 +1165,19 @@ BPE_API int bpe_count_pair_table(bpe_ctx *ctx, const uint8_t *specials_blob, con
     return BPE_OK;
 }
 
+BPE_API int bpe_train_set_live(bpe_ctx *ctx, int32_t *live_pairs, int capacity_merges) {
+    if (!ctx || capacity_merges < 0) return BPE_ERR_ARG;
+    if (live_pairs) {                            // the kernel writes it directly: it must be page-locked host memory
+        cudaPointerAttributes a{};
+        if (cudaPointerGetAttributes(&a, live_pairs) != cudaSuccess || a.type != cudaMemoryTypeHost) {
+            cudaGetLastError();
+            return bpe_set_error(ctx, BPE_ERR_ARG, "bpe_train_set_live: the buffer must be page-locked host memory (bpe_host_alloc)");
+        }
+    }
+    ctx->live_pairs = live_pairs; ctx->live_cap = live_pairs ? capacity_merges : 0;
+    return BPE_OK;
+}
+
 BPE_API int bpe_last_pair_table(bpe_ctx *ctx, int64_t *dense_out) {
     if (!ctx || !dense_out) return BPE_ERR_ARG;
     if (ctx->last_dense.size() != 65536) return bpe_set_error(ctx, BPE_ERR_ARG, "bpe_last_pair_table: no training call has built a pair table on this context");
@@ -1287,6 +1300,7 @@ static int run_merges(bpe_ctx *ctx, const uint8_t *sp_blob, const u32 *sp_offs, 
     }
     M.tok_off = (u32 *)B.tok_off.p; M.tok_len = (u32 *)B.tok_len.p; M.tok_key = (u64 *)B.tok_key.p; M.tok_bytes = (uint8_t *)B.tok_bytes.p;
     M.tok_bytes_cap = tok_bytes_cap; M.merge_cnt_out = (i64 *)B.merge_cnt.p;
+    M.live_pairs = ctx->live_pairs; M.live_cap = ctx->live_cap;
     M.merges_out = (int32_t *)B.merges.p; M.n_merges = n_merges; M.ctr = (u64 *)B.ctr.p; M.prof = (u64 *)B.prof.p;
     M.step_prof = nullptr;
     M.min_rec = 1;                                   // measured at 11 GB, same box: 32 -> 433 ms, 8 -> 418, 2 -> 409, 1 -> 406

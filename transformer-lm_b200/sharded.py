@@ -130,8 +130,15 @@ class DeviceCounter:
         pairs = np.zeros((max(n_merges, 1), 2), dtype=np.int32)
         n_done = C.c_int(0)
         stats = _lib.TrainStats()
-        self.ctx.check(self.L.bpe_train_from_counts(self.ctx.handle, _lib.ptr(sp_blob), _lib.ptr(sp_offs), len(special_tokens), n_merges,
-                                                    _lib.ptr(pairs), C.byref(n_done), C.byref(stats)))
+        from .train import LiveMerges
+        live = LiveMerges(self.ctx, vocab, n_merges)
+        rc = -1
+        try:
+            rc = self.L.bpe_train_from_counts(self.ctx.handle, _lib.ptr(sp_blob), _lib.ptr(sp_offs), len(special_tokens), n_merges,
+                                              _lib.ptr(pairs), C.byref(n_done), C.byref(stats))
+        finally:
+            out = live.finish(pairs, n_done.value if rc == _lib.BPE_OK else 0)
+        self.ctx.check(rc)
         if stats.duplicate_tokens:
             raise NotImplementedError("two merges produced identical token bytes (SURVEY A-6); not supported")
         if self._expected_pairs is not None:
@@ -142,8 +149,6 @@ class DeviceCounter:
             expected, self._expected_pairs = self._expected_pairs, None
             if not np.array_equal(expected.cpu().numpy(), merged):
                 raise RuntimeError("pair-count all-reduce does not match the merged word table")
-        from .train import merges_to_python
-        out = merges_to_python(vocab, pairs, n_done.value)
         return out + (stats.as_dict(),) if return_stats else out
 
 

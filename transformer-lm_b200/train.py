@@ -11,6 +11,7 @@ from __future__ import annotations
 import ctypes as C
 import logging
 import os
+import threading
 import time
 from typing import List
 
@@ -43,30 +44,103 @@ def _read_file(input_path):
     return np.frombuffer(data, dtype=np.uint8), data
 
 
+class MergeBuilder:
+    """Symbol-id merge list of the device -> (vocab dict, merges list) of the reference (train.py:190-191, 228), fed in order and in
+    pieces: tokens are byte strings, `Vocab.add_token` skips a byte string that is already present (vocab.py:28-34)."""
+
+    def __init__(self, vocab: Vocab):
+        self.vocab = vocab
+        self.sym = [bytes([i]) for i in range(256)]      # symbol id -> bytes: 0..255 the bytes, 256 + k the product of merge k
+        self.merges: list = []
+
+    def feed(self, chunk: np.ndarray) -> None:
+        """The next merges: int32 array [m, 2] of symbol ids."""
+        if not len(chunk):
+            return
+        ia, ib = chunk[:, 0].tolist(), chunk[:, 1].tolist()
+        sym, append = self.sym, self.sym.append
+        n0 = len(sym)
+        for x, y in zip(ia, ib):                 # the one loop that cannot be avoided: token j is built from earlier tokens
+            append(sym[x] + sym[y])
+        get = sym.__getitem__
+        self.merges.extend(zip(map(get, ia), map(get, ib)))
+        new = sym[n0:]
+        idx_to_token, present = self.vocab.idx_to_token, self.vocab._present     # (Vocab.add_token inlined: tens of thousands of calls)
+        fresh = set(new)
+        if len(fresh) == len(new) and present.isdisjoint(fresh):       # the usual case: no byte string twice (A-5 / A-6 never triggered)
+            base = len(idx_to_token)
+            idx_to_token.update(zip(range(base, base + len(new)), new))
+            present |= fresh
+        else:
+            for t in new:
+                if t not in present:
+                    present.add(t)
+                    idx_to_token[len(idx_to_token)] = t
+
+    @property
+    def n_fed(self) -> int:
+        return len(self.merges)
+
+    def result(self):
+        return self.vocab.get_idx_to_token(), self.merges
+
+
+class LiveMerges:
+    """Follows the merge loop from the host (bpe_train_set_live): while the GPU makes merges, a thread feeds the pairs that have
+    appeared so far to a MergeBuilder, so that the reference's Python objects (32 000 byte strings, tuples and dict entries: ~9 ms after
+    an 11 GB / vocab-32 000 run) are nearly complete when the loop ends.  ctypes releases the GIL during the training call, so the
+    thread runs beside it."""
+
+    def __init__(self, ctx, vocab: Vocab, n_merges: int):
+        self.ctx, self.n = ctx, int(n_merges)
+        self.builder = MergeBuilder(vocab)
+        self.active = False
+        if self.n <= 0:
+            return
+        self._pairs = _lib.PinnedBuffer(self.n * 8)
+        self._pairs.array[:] = 0xFF                  # -1, -1: "not made yet" (the kernel stores a pair with one 8-byte write)
+        self.pairs = self._pairs.array.view(np.int32).reshape(self.n, 2)
+        ctx.check(_lib.lib().bpe_train_set_live(ctx.handle, _lib.ptr(self._pairs.array), self.n))
+        self.active = True
+        self._stop = threading.Event()
+        self._thread = threading.Thread(target=self._follow, daemon=True)
+        self._thread.start()
+
+    def _follow(self) -> None:
+        first = self.pairs[:, 0]
+        while not self._stop.is_set():
+            k = self.builder.n_fed
+            if k < self.n and first[k] >= 0:
+                blk = first[k: k + 4096] < 0             # the complete entries in front (they may land out of order)
+                m = int(np.argmax(blk)) if blk.any() else blk.size
+                if m < 64 and k + m < self.n:            # (a handful: wait for more, the per-piece overhead is what we are hiding)
+                    time.sleep(0.0002)
+                    continue
+                self.builder.feed(self.pairs[k: k + m].copy())
+            else:
+                time.sleep(0.0002)
+
+    def finish(self, pairs: np.ndarray, n_done: int):
+        """Stop following and complete the objects from the authoritative `pairs`; returns (vocab dict, merges list)."""
+        if self.active:
+            self._stop.set()
+            self._thread.join()
+            _lib.lib().bpe_train_set_live(self.ctx.handle, None, 0)
+            k = self.builder.n_fed
+            ok = k <= n_done and (k == 0 or np.array_equal(self.pairs[:k], pairs[:k]))
+            self._pairs.free()
+            self.active = False
+            if not ok:
+                raise RuntimeError("the live view of the merge loop disagrees with its result")
+        self.builder.feed(pairs[self.builder.n_fed:n_done])
+        return self.builder.result()
+
+
 def merges_to_python(vocab: Vocab, pairs: np.ndarray, n_done: int):
-    """Symbol-id merge list of the device -> (vocab dict, merges list) of the reference (train.py:190-191, 228): tokens are
-    byte strings, `Vocab.add_token` skips a byte string that is already present (vocab.py:28-34)."""
-    sym = [bytes([i]) for i in range(256)]
-    ab = pairs[:n_done]
-    ia, ib = ab[:, 0].tolist(), ab[:, 1].tolist()
-    append = sym.append
-    for x, y in zip(ia, ib):                     # the one loop that cannot be avoided: token j is built from earlier tokens
-        append(sym[x] + sym[y])
-    get = sym.__getitem__
-    merges = list(zip(map(get, ia), map(get, ib)))
-    idx_to_token, present = vocab.idx_to_token, vocab._present     # (Vocab.add_token inlined: tens of thousands of calls)
-    new = sym[256:]
-    fresh = set(new)
-    if len(fresh) == len(new) and present.isdisjoint(fresh):       # the usual case: no byte string twice (A-5 / A-6 never triggered)
-        base = len(idx_to_token)
-        idx_to_token.update(zip(range(base, base + len(new)), new))
-        present |= fresh
-    else:
-        for t in new:
-            if t not in present:
-                present.add(t)
-                idx_to_token[len(idx_to_token)] = t
-    return vocab.get_idx_to_token(), merges
+    """Symbol-id merge list of the device -> (vocab dict, merges list) of the reference (see MergeBuilder)."""
+    b = MergeBuilder(vocab)
+    b.feed(pairs[:n_done])
+    return b.result()
 
 
 def train_bpe_on_bytes(data, vocab_size: int, special_tokens: List[str] = [], *, ctx=None, return_stats: bool = False,
@@ -80,14 +154,13 @@ def train_bpe_on_bytes(data, vocab_size: int, special_tokens: List[str] = [], *,
     pairs = np.zeros((max(n_merges, 1), 2), dtype=np.int32)
     n_done = C.c_int(0)
     stats = _lib.TrainStats()
-    if device_ptr is not None:
-        rc = L.bpe_train_dev(ctx.handle, C.c_void_p(device_ptr), int(n_bytes), _lib.ptr(sp_blob), _lib.ptr(sp_offs),
-                             len(special_tokens), n_merges, _lib.ptr(pairs), C.byref(n_done), C.byref(stats))
-        arr = None
-    else:
-        arr = _lib.as_u8(data)
-        rc = L.bpe_train(ctx.handle, _lib.ptr(arr) if arr.size else None, arr.size, _lib.ptr(sp_blob), _lib.ptr(sp_offs),
-                         len(special_tokens), n_merges, _lib.ptr(pairs), C.byref(n_done), C.byref(stats))
+    live = LiveMerges(ctx, vocab, n_merges)
+    rc = -1
+    try:
+        rc = _call_train(L, ctx, data, device_ptr, n_bytes, sp_blob, sp_offs, special_tokens, n_merges, pairs, n_done, stats)
+    finally:
+        res = live.finish(pairs, n_done.value if rc == _lib.BPE_OK else 0)
+    arr = None if device_ptr is not None else _lib.as_u8(data)
     if rc == _lib.ERR_UTF8 and arr is not None:
         bytes(arr).decode("utf-8")                                # raises the reference's UnicodeDecodeError
         raise AssertionError("device flagged invalid UTF-8 at %d but CPython accepts the data" % L.bpe_last_error_detail(ctx.handle))
@@ -96,8 +169,19 @@ def train_bpe_on_bytes(data, vocab_size: int, special_tokens: List[str] = [], *,
         # SURVEY A-6: two different merges produced the same byte string while the pair still had a positive
         # count.  The reference would pool the two symbols; this has never been observed and is not implemented.
         raise NotImplementedError("two merges produced identical token bytes (SURVEY A-6); not supported")
-    out = (*merges_to_python(vocab, pairs, n_done.value),)
+    out = (*res,)
     return out + (stats.as_dict(),) if return_stats else out
+
+
+def _call_train(L, ctx, data, device_ptr, n_bytes, sp_blob, sp_offs, special_tokens, n_merges, pairs, n_done, stats):
+    if device_ptr is not None:
+        rc = L.bpe_train_dev(ctx.handle, C.c_void_p(device_ptr), int(n_bytes), _lib.ptr(sp_blob), _lib.ptr(sp_offs),
+                             len(special_tokens), n_merges, _lib.ptr(pairs), C.byref(n_done), C.byref(stats))
+    else:
+        arr = _lib.as_u8(data)
+        rc = L.bpe_train(ctx.handle, _lib.ptr(arr) if arr.size else None, arr.size, _lib.ptr(sp_blob), _lib.ptr(sp_offs),
+                         len(special_tokens), n_merges, _lib.ptr(pairs), C.byref(n_done), C.byref(stats))
+    return rc
 
 
 _STREAM_MIN = 512 << 20          # files at least this big are streamed: read, upload and counting overlap
