@@ -1337,7 +1337,10 @@ static int run_merges(bpe_ctx *ctx, const uint8_t *sp_blob, const u32 *sp_offs, 
         // grid: one CTA per SM for big tables, fewer for small ones (cheaper barriers).  Measured at 11 GB with the counter
         // barrier, same box: G = 148: 449 ms, 112: 464, 96: 463, 80: 481, 64: 485, 48: 535.  (With the per-CTA flag barrier
         // that this replaced, 64 CTAs were the optimum: polling 148 slots cost more than the extra apply threads gave.)
-        int G = std::max(2, (int)std::min<u64>((u64)std::min(ctx->sm_count, (int)MG_MAX_CTAS), std::max<u64>(pcap_natural, M.pcap / 16) / PB / 256 + 1 + (n_words + 4095) / 4096));
+        // Since a step applies several merges the small-table optimum moved up: TinyStories shape (98 K words, 4 M slots), G = 41 (what
+        // the size rule gives): 23.3 ms, 74: 19.5, 96: 19.4, 120: 19.9, 148: 20.5; 11 GB OWT shape: 148: 139.6, 120: 150.9, 96: 160.3.
+        int G = std::max(2, (int)std::min<u64>((u64)std::min(ctx->sm_count, (int)MG_MAX_CTAS),
+                                               std::max<u64>(96, std::max<u64>(pcap_natural, M.pcap / 16) / PB / 256 + 1 + (n_words + 4095) / 4096)));
         if (const char *e = getenv("BPE_MERGE_G")) G = std::max(2, std::min(atoi(e), std::min(ctx->sm_count, (int)MG_MAX_CTAS)));
         g_bpe_launches++;
         CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_merge_loop, dim3(G), dim3(MG_NT), nullptr, MG_DYN_SMEM, st));
