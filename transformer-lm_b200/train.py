@@ -85,6 +85,9 @@ class MergeBuilder:
         return self.vocab.get_idx_to_token(), self.merges
 
 
+_LIVE_BUFFERS: dict = {}         # context id -> page-locked buffer of the live merge view
+
+
 class LiveMerges:
     """Follows the merge loop from the host (bpe_train_set_live): while the GPU makes merges, a thread feeds the pairs that have
     appeared so far to a MergeBuilder, so that the reference's Python objects (32 000 byte strings, tuples and dict entries: ~9 ms after
@@ -95,11 +98,17 @@ class LiveMerges:
         self.ctx, self.n = ctx, int(n_merges)
         self.builder = MergeBuilder(vocab)
         self.active = False
-        if self.n <= 0:
+        if self.n <= 0 or os.environ.get("BPE_LIVE_MERGES", "1") in ("", "0"):
             return
-        self._pairs = _lib.PinnedBuffer(self.n * 8)
-        self._pairs.array[:] = 0xFF                  # -1, -1: "not made yet" (the kernel stores a pair with one 8-byte write)
-        self.pairs = self._pairs.array.view(np.int32).reshape(self.n, 2)
+        # (the buffer is kept between calls: page-locking and unlocking cost milliseconds each when the process holds GBs of pinned memory)
+        buf = _LIVE_BUFFERS.get(id(ctx))
+        if buf is None or buf.nbytes < self.n * 8:
+            if buf is not None:
+                buf.free()
+            buf = _LIVE_BUFFERS[id(ctx)] = _lib.PinnedBuffer(max(self.n * 8, 1 << 20))
+        self._pairs = buf
+        self._pairs.array[: self.n * 8] = 0xFF       # -1, -1: "not made yet" (the kernel stores a pair with one 8-byte write)
+        self.pairs = self._pairs.array[: self.n * 8].view(np.int32).reshape(self.n, 2)
         ctx.check(_lib.lib().bpe_train_set_live(ctx.handle, _lib.ptr(self._pairs.array), self.n))
         self.active = True
         self._stop = threading.Event()
@@ -108,17 +117,18 @@ class LiveMerges:
 
     def _follow(self) -> None:
         first = self.pairs[:, 0]
+        nap = float(os.environ.get("BPE_LIVE_POLL_MS", "1.0")) / 1e3     # (the loop makes ~230 merges per millisecond at 11 GB)
         while not self._stop.is_set():
             k = self.builder.n_fed
             if k < self.n and first[k] >= 0:
                 blk = first[k: k + 4096] < 0             # the complete entries in front (they may land out of order)
                 m = int(np.argmax(blk)) if blk.any() else blk.size
                 if m < 64 and k + m < self.n:            # (a handful: wait for more, the per-piece overhead is what we are hiding)
-                    time.sleep(0.0002)
+                    self._stop.wait(nap)
                     continue
                 self.builder.feed(self.pairs[k: k + m].copy())
             else:
-                time.sleep(0.0002)
+                self._stop.wait(nap if k else 4 * nap)   # (nothing yet: the text is still being uploaded and counted)
 
     def finish(self, pairs: np.ndarray, n_done: int):
         """Stop following and complete the objects from the authoritative `pairs`; returns (vocab dict, merges list)."""
@@ -128,7 +138,6 @@ class LiveMerges:
             _lib.lib().bpe_train_set_live(self.ctx.handle, None, 0)
             k = self.builder.n_fed
             ok = k <= n_done and (k == 0 or np.array_equal(self.pairs[:k], pairs[:k]))
-            self._pairs.free()
             self.active = False
             if not ok:
                 raise RuntimeError("the live view of the merge loop disagrees with its result")
@@ -193,9 +202,12 @@ _PIN_CACHE: list = []            # page-locked chunk buffers of the streamed ing
 
 
 def release_buffers() -> None:
-    """Free the page-locked buffers train_bpe(path) keeps between calls."""
+    """Free the page-locked buffers train_bpe keeps between calls."""
     while _PIN_CACHE:
         _PIN_CACHE.pop().free()
+    for b in _LIVE_BUFFERS.values():
+        b.free()
+    _LIVE_BUFFERS.clear()
 
 
 _DIRECT_ALIGN = 4096             # O_DIRECT: file offsets, lengths and buffer addresses in multiples of the logical block size
