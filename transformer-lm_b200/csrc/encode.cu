@@ -428,13 +428,18 @@ __device__ __forceinline__ u64 make_value(const EncTables &t, u32 n, int32_t id,
 // instructions per pretoken measured.)  Symbols and the ranks of the adjacent pairs live in a private shared-memory row.
 #define BPT_NT 128
 #define BPT_MAX 32u
+// Two instances: pretokens of <= 15 bytes (short and medium table entries -- 98 % of the new pretokens of web-like text) with rows of
+// 16 symbols, i.e. half the shared memory and twice the resident threads of the 32-symbol instance that takes the long-table entries
+// of 16..32 bytes (the kernel waits on dependent L2 lookups of pair ranks: occupancy is what it needs).
+template <u32 ROW, bool LONGS>
 __global__ void __launch_bounds__(BPT_NT) k_enc_bpe_short(EncTables t, u64 n_todo) {
-    __shared__ u32 s_sym[BPT_NT][BPT_MAX + 1];
-    __shared__ u32 s_ids[BPT_NT][BPT_MAX + 1];
+    __shared__ u32 s_sym[BPT_NT][ROW + 1];
+    __shared__ u32 s_ids[BPT_NT][ROW + 1];
     u32 *sym = s_sym[threadIdx.x], *rk = s_ids[threadIdx.x];
     for (u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x; q < n_todo; q += (u64)gridDim.x * blockDim.x) {
         const u32 ref = t.todo[q];
         const bool is_long = ref & REF_LONG, is_med = ref & REF_MED;
+        if (is_long != LONGS) continue;          // the other instance's
         const u32 slot = REF_SLOT(ref);
         u32 n;
         if (is_med) {
@@ -1314,7 +1319,8 @@ static int encode_core(bpe_tok *tok, u64 n, int out_dtype, void *out_dev, u64 de
         if (n_todo) {
             unsigned g2 = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (n_todo + 7) / 8);
             unsigned g1 = (unsigned)std::min<u64>((u64)ctx->sm_count * bpe_grid_mult(64), (n_todo + BPT_NT - 1) / BPT_NT);
-            KLAUNCH(k_enc_bpe_short, g1, BPT_NT, 0, st, t, n_todo);
+            KLAUNCH((k_enc_bpe_short<16u, false>), g1, BPT_NT, 0, st, t, n_todo);
+            KLAUNCH((k_enc_bpe_short<BPT_MAX, true>), g1, BPT_NT, 0, st, t, n_todo);
             KLAUNCH(k_enc_bpe, g2, 256, 0, st, t, n_todo);
             CUDA_TRY(ctx, cudaGetLastError());
         }
