@@ -220,7 +220,9 @@ __device__ __forceinline__ bool enc_hot_get(const EncTables &t, u64 k0, u64 k1, 
 //   3. what misses that, and pretokens of >= 16 bytes: the big tables (lookup or claim, enc_short_get / enc_long_get).
 #define LK_NT 1024
 #define LK_WARPS (LK_NT / 32u)
+#ifndef LK_SM_LG
 #define LK_SM_LG 12
+#endif
 #define LK_SM_SLOTS (1u << LK_SM_LG)
 #ifndef LK_SM_FILL_NUM
 #define LK_SM_FILL_NUM 6u                         // eighths of the image that may be filled
