@@ -230,7 +230,9 @@ __device__ __forceinline__ bool enc_hot_get(const EncTables &t, u64 k0, u64 k1, 
 #ifndef LK_SM_PROBES
 #define LK_SM_PROBES 2u
 #endif
+#ifndef LK_TICKET
 #define LK_TICKET 8u                             // steps (of 512 bytes) per ticket
+#endif
 #define LK_QCAP 96u                              // entries of the warp's key queue
 #define LK_QDRAIN 64u                            // drained when it reaches this (a round of the bit loop adds <= 32)
 #define LK_QL_CAP 64u

@@ -254,7 +254,9 @@ __device__ __forceinline__ void count_drain(const CountTables &t, CountQueues &q
 // per pretoken, every lane busy, where a lane per chunk left half of them idle (3.5 starts per chunk on average, 7-8 in the fullest
 // chunk of a step).  Length = next position - position; the first 16 bytes of the pretoken = five aligned words of the staged text
 // and four funnel shifts.
+#ifndef CNT_TICKET
 #define CNT_TICKET 8u                            // steps (of 512 bytes) per ticket
+#endif
 #define CNT_STAGE_TEXT 528u                      // 32 chunks + the 16 bytes after them
 #define CNT_STAGE_POS 520u                       // up to 512 starts + the sentinel (first start after the step), 16-bit each
 #define CNT_POS_OWNED 0x8000u                    // the pretoken starts inside [own_begin, own_end) of this launch's chunks
