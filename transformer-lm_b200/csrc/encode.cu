@@ -199,14 +199,6 @@ __device__ __forceinline__ u64 enc_long_get(const EncTables &t, const uint8_t *p
 // short-table key for <= 7 bytes), the values sit in an array beside it.  A key whose bucket is full simply stays with the big
 // tables, so a probe is exactly one sector.  Values are immutable once computed, so the copy never goes stale.
 __device__ __forceinline__ u64 enc_hot_bucket(u64 nb, u64 k0, u64 k1) { return ((mix64(k0 ^ (k1 * 0x9E3779B97F4A7C15ull)) >> 32) * nb) >> 32; }
-__device__ __forceinline__ bool enc_hot_get(const EncTables &t, u64 k0, u64 k1, u64 *v) {
-    const u64 b = enc_hot_bucket(t.hot_nb, k0, k1);
-    const ulonglong2 a0 = __ldg(&t.hot[2 * b]), a1 = __ldg(&t.hot[2 * b + 1]);
-    const bool m0 = a0.x == k0 && a0.y == k1, m1 = a1.x == k0 && a1.y == k1;
-    if (!(m0 || m1)) return false;
-    *v = __ldg(&t.hval[2 * b + (m1 ? 1 : 0)]);
-    return true;
-}
 
 // ---- lookup: straight from the text and its start bits -------------------------------------------------------------------
 // vals[ordinal of the pretoken in the batch] = its cached value when the cache has it, else a forward reference to its slot

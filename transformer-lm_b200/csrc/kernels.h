@@ -15,8 +15,6 @@ void launch_popc_words(const u32 *flags, u64 n_words, u32 *cnt, int sm_count, cu
 void launch_popc_words16(const u32 *flags, u64 n_groups, u32 *cnt, int sm_count, cudaStream_t st);
 void launch_flags_to_offsets(const u32 *flags, u64 n_words, const u64 *pre, u64 *out, u64 cap, int sm_count, cudaStream_t st);
 void launch_scan_u32(const u32 *in, u64 n, u64 *out, u64 *tmp, cudaStream_t st);
-void launch_starts_to_offsets(const u32 *flags, u64 word_begin, u64 word_end, u64 n, const u64 *pre, u64 base, u32 *offs, u64 n_items,
-                              int sm_count, cudaStream_t st);
 size_t scan_tmp_elems_host(u64 n);
 // Small control words WITHOUT the copy engines: while the pipelined entry points stream 256 MB chunks over PCIe, a 16-byte
 // cudaMemcpyAsync on the compute stream queues behind the chunk in flight on the same copy engine and stalls the kernels after it

@@ -407,41 +407,3 @@ void launch_flags_to_offsets(const u32 *flags, u64 n_words, const u64 *pre, u64 
 }
 void launch_scan_u32(const u32 *in, u64 n, u64 *out, u64 *tmp, cudaStream_t st) { launch_excl_scan_u32_to_u64(in, n, out, tmp, st); }
 size_t scan_tmp_elems_host(u64 n) { return scan_tmp_elems(n); }
-
-// ---------------------------------------------------------------------------------------------
-// bitmask -> u32 offsets of a batch of flag words (one thread per pretoken downstream)
-// ---------------------------------------------------------------------------------------------
-// Start bits -> explicit offsets (u32, relative to byte `base`): one thread per 32-byte flag word writes the positions
-// of its pretokens at their ordinals.  The kernels that do the per-pretoken work then run one thread per PRETOKEN with
-// coalesced offset loads; the word-per-thread form spent ~10x the instructions in divergence (3 to 16 pretokens per
-// word, short and long paths interleaved).
-__global__ void __launch_bounds__(256) k_starts_to_offsets(const u32 *__restrict__ flags, u64 word_begin, u64 word_end,
-                                                          const u64 *__restrict__ pre, u64 base, u32 *__restrict__ offs) {
-    const u64 base_ord = pre[0];
-    for (u64 w = word_begin + (u64)blockIdx.x * blockDim.x + threadIdx.x; w < word_end; w += (u64)gridDim.x * blockDim.x) {
-        u32 bits = flags[w];
-        u64 o = pre[w - word_begin] - base_ord;
-        while (bits) {
-            u32 j = __ffs(bits) - 1; bits &= bits - 1;
-            offs[o++] = (u32)((w << 5) + j - base);
-        }
-    }
-}
-
-// offs_out[0] = (first pretoken start at byte position >= from, or n) - base
-__global__ void k_next_start_after(const u32 *__restrict__ flags, u64 from, u64 n, u64 base, u32 *__restrict__ offs_out) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) offs_out[0] = (u32)(flags_next_start(flags, from, n) - base);
-}
-
-
-// offs[0 .. n_items] for the pretokens that start in flag words [word_begin, word_end): positions relative to `base`;
-// offs[n_items] = end of the last one.  pre = exclusive scan of the words' popcounts (pre[0] = 0).
-void launch_starts_to_offsets(const u32 *flags, u64 word_begin, u64 word_end, u64 n, const u64 *pre, u64 base, u32 *offs, u64 n_items,
-                              int sm_count, cudaStream_t st) {
-    u64 bw = word_end - word_begin;
-    if (bw) {
-        unsigned grid = (unsigned)((bw + 255) / 256 < (u64)sm_count * bpe_grid_mult(64) ? (bw + 255) / 256 : (u64)sm_count * bpe_grid_mult(64));
-        KLAUNCH(k_starts_to_offsets, grid, 256, 0, st, flags, word_begin, word_end, pre, base, offs);
-    }
-    KLAUNCH(k_next_start_after, 1, 32, 0, st, flags, word_end * 32, n, base, offs + n_items);
-}

@@ -204,9 +204,6 @@ __device__ __forceinline__ u64 hot_bucket_of(const CountTables &t, u64 k0, u64 k
 __device__ __forceinline__ void count_drain(const CountTables &t, CountQueues &q, u64 base, u32 lane, bool all) {
     const u32 dn = all ? q.n : q.n & ~63u;
     __syncwarp();
-#ifdef CNT_KO_DRAIN
-    q.n = q.nl = 0; return;
-#endif
     for (u32 e0 = 0; e0 < dn; e0 += 64u) {
         const bool ha = e0 + lane < dn, hb = e0 + 32u + lane < dn;
         ulonglong2 ka = make_ulonglong2(0, 0), kb = ka;
@@ -362,21 +359,13 @@ __global__ void __launch_bounds__(CNT_NT, 1024 / CNT_NT) k_count_pretokens(Count
             bool q_s = act && len <= SHORT_MAX;
             const bool q_m = act && len > SHORT_MAX && len <= MED_MAX, q_l = act && len > MED_MAX;
             const u64 key = (k0 & low_bytes_mask(len)) | ((u64)len << 56);               // (short pretokens)
-#ifdef CNT_KO_SMEM
-            if (false) {
-#else
             if (q_s) {
-#endif
                 u32 slot = (((u32)key ^ (u32)(key >> 32)) * 0x9E3779B1u) >> (32 - CNT_SMEM_LG);   // cheap hash for the shared-memory table
 #pragma unroll
                 for (u32 pr = 0; pr < CNT_SMEM_PROBES; pr++) {
                     u64 kk = s_key[slot];
                     if (kk == 0) { const u64 old = atomicCAS(&s_key[slot], 0ull, key); kk = old ? old : key; }
-#ifdef CNT_KO_ATOM
-                    if (kk == key) { q_s = false; break; }
-#else
                     if (kk == key) { atomicAdd(&s_cnt[slot], 1u); q_s = false; break; }
-#endif
                     slot = (slot + 1) & (CNT_SMEM_SLOTS - 1);
                 }
             }
@@ -919,8 +908,7 @@ static int count_current_text(bpe_ctx *ctx, u64 n, u64 own_begin, u64 own_end, u
         const double tb0 = prof ? now_ms() : 0;
         u64 b_lo = w_lo + bstart[bi] * words_per_range, b_hi = std::min(w_hi, w_lo + bstart[bi + 1] * words_per_range);
         u64 bytes = (b_hi - b_lo) * 32;
-        static const u64 bound_div = getenv("BPE_COUNT_BOUND_DIV") ? std::max(1, atoi(getenv("BPE_COUNT_BOUND_DIV"))) : 1;   // EXPERIMENT ONLY (unsafe)
-        BPE_TRY(count_ensure_capacity(ctx, c, bound[bi] / bound_div, std::min(bound[bi], bytes / (SHORT_MAX + 1) + 1) / bound_div));
+        BPE_TRY(count_ensure_capacity(ctx, c, bound[bi], std::min(bound[bi], bytes / (SHORT_MAX + 1) + 1)));
         CountTables t = count_tables(ctx);
         if (bound[bi]) {
             static const int cnt_ctas_per_sm = getenv("BPE_COUNT_CTAS") ? std::max(1, atoi(getenv("BPE_COUNT_CTAS"))) : (int)(1024 / CNT_NT);
