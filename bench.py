@@ -398,6 +398,8 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local_rank)
+    # one process per GPU: sit on the GPU's NUMA node before any page-locked buffer is allocated (best effort; reported on the line)
+    numa = _lib.bind_to_gpu_numa_node(local_rank) if world > 1 and not os.environ.get("BPE_NO_NUMA_BIND") else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = _lib.Context(local_rank)
@@ -886,6 +888,12 @@ def run_b200(args):
                     line["encode"]["cpu_baseline"] = enc_cpu
             else:
                 line["cpu_baseline"] = enc_cpu
+    if numa is not None:
+        # every rank's binding result, gathered on rank 0 (host-side objects: one small all_gather_object)
+        allnuma = [None] * world
+        dist.all_gather_object(allnuma, numa)
+        line["numa_binding"] = {"note": "each rank binds itself to the CPUs of its GPU's NUMA node before allocating page-locked buffers (best effort)",
+                                "ranks": allnuma}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

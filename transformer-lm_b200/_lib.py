@@ -224,3 +224,36 @@ class PinnedBuffer:
             self.free()
         except Exception:
             pass
+
+
+def bind_to_gpu_numa_node(device: int = 0) -> dict:
+    """Best effort: run this process (and so allocate its page-locked buffers, first touch) on the CPUs of the NUMA node the GPU hangs
+    off.  With one process per GPU and all of them on node 0, the host ends of the PCIe copies of eight ranks share one memory
+    controller / root complex (round 1: 54 GB/s per GPU at N = 1, 18.7 at N = 8).  Returns what was found and done; never raises."""
+    info = {"device": device, "bound": False}
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(device).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(device), "pci_domain_id", 0)
+        dev_id = getattr(torch.cuda.get_device_properties(device), "pci_device_id", 0)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev_id)
+        node = int(open(path).read().strip())
+        info["numa_node"] = node
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        info["allowed_cpus"] = len(allowed)
+        target = cpus & allowed
+        info["node_cpus_allowed"] = len(target)
+        if target and target != allowed:
+            os.sched_setaffinity(0, target)
+            info["bound"] = True
+        elif target == allowed:
+            info["bound"] = True                     # already there
+    except Exception as e:                           # no sysfs, no permission, ...: leave the process where it is
+        info["error"] = "%s: %s" % (type(e).__name__, e)
+    return info
