@@ -87,3 +87,39 @@ def test_load_batch_shim_has_the_reference_signature_and_no_cpu_path():
     assert params[:5] == ["dataset", "batch_size", "context_length", "device", "generator"]
     with pytest.raises(_lib.BpeError):          # the gather runs on a B200 or not at all
         load_batch(np.arange(100, dtype=np.uint16), 2, 8, "cpu")
+
+
+def test_merge_builder_in_pieces_equals_one_piece_and_dedupes_like_the_reference():
+    """MergeBuilder (what the live follower of the merge loop feeds): symbol-id pairs -> (vocab, merges) of the reference, in one
+    piece or in many, including a merge whose bytes already exist (a special token's bytes, or the same bytes made twice: Vocab.add_token
+    skips them, models/tokenizer/vocab.py:28-34)."""
+    import numpy as np
+    from transformer_lm_b200.train import MergeBuilder, merges_to_python
+    from transformer_lm_b200.vocab import Vocab
+    rng = np.random.default_rng(7)
+    n = 3000
+    pairs = np.zeros((n, 2), dtype=np.int32)
+    for i in range(n):
+        pairs[i] = rng.integers(0, min(256 + i, 900), 2)
+    pairs[5] = (ord("<"), ord("|"))                       # b"<|" is a special token below: already present
+    pairs[9] = pairs[7]                                   # the same bytes twice
+    specials = ["<|", "<|endoftext|>"]
+
+    def reference_way():
+        vocab = Vocab(special_tokens=list(specials))
+        sym = [bytes([i]) for i in range(256)]
+        merges = []
+        for a, b in pairs.tolist():
+            merges.append((sym[a], sym[b]))
+            sym.append(sym[a] + sym[b])
+            vocab.add_token(sym[a] + sym[b])
+        return vocab.get_idx_to_token(), merges
+
+    want = reference_way()
+    assert merges_to_python(Vocab(special_tokens=list(specials)), pairs, n) == want
+    b = MergeBuilder(Vocab(special_tokens=list(specials)))
+    cuts = [0, 1, 2, 6, 7, 10, 700, 701, 2999, 3000]
+    for lo, hi in zip(cuts, cuts[1:]):
+        b.feed(pairs[lo:hi])
+    assert b.n_fed == n and b.result() == want
+    assert len(want[0]) < 256 + len(specials) + n         # the duplicates were skipped
