@@ -194,6 +194,11 @@ typedef struct bpe_encode_stats {
  * returns BPE_ERR_ARG (the reference's np.uint16 cast at models/tokenizer/encode.py:37 would wrap). */
 int bpe_encode(bpe_tok *tok, const uint8_t *text_host, uint64_t n, int out_dtype,
                void *out, uint64_t cap, uint64_t *n_out, bpe_encode_stats *stats);
+/* 1 if the text of the last bpe_encode / bpe_encode_dev call on this tokenizer's context held a carriage return (the flags kernel
+ * sees every byte anyway).  Tokenizer.encode takes a str and keeps '\r' as it is; a caller that reads a FILE in text mode, like the
+ * reference's bulk driver (models/tokenizer/encode.py:31-34, universal newlines), uses this instead of scanning the text on the host:
+ * it translates and encodes the piece again in the rare case. */
+int bpe_tok_saw_cr(bpe_tok *tok);
 /* Device-resident variant: text_dev and out_dev are device pointers on the tokenizer's device. */
 int bpe_encode_dev(bpe_tok *tok, const uint8_t *text_dev, uint64_t n, int out_dtype,
                    void *out_dev, uint64_t cap, uint64_t *n_out, bpe_encode_stats *stats);

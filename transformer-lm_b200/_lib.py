@@ -53,7 +53,7 @@ EXPORTS = [
     "bpe_last_error_detail", "bpe_device_sync", "bpe_utf8_validate", "bpe_pretokenize", "bpe_train", "bpe_train_dev",
     "bpe_count_begin", "bpe_count_add_shard", "bpe_count_add_shard_dev", "bpe_count_export_size", "bpe_count_export",
     "bpe_count_export_dev", "bpe_count_import", "bpe_count_import_dev", "bpe_count_pair_table",
-    "bpe_train_from_counts", "bpe_last_pair_table", "bpe_train_set_live", "bpe_tok_create", "bpe_tok_destroy", "bpe_encode", "bpe_encode_dev", "bpe_tok_key_error",
+    "bpe_train_from_counts", "bpe_last_pair_table", "bpe_train_set_live", "bpe_tok_create", "bpe_tok_destroy", "bpe_encode", "bpe_encode_dev", "bpe_tok_key_error", "bpe_tok_saw_cr",
     "bpe_tok_cache_reset", "bpe_decode", "bpe_decode_batch", "bpe_batch_windows_dev", "bpe_synth_dev", "bpe_synth_host", "bpe_synth_dev_at", "bpe_synth_host_at", "bpe_ctx_set_stream", "bpe_host_alloc", "bpe_host_free", "bpe_launch_count",
 ]
 
@@ -97,6 +97,7 @@ def lib():
             L.bpe_encode_dev.argtypes = L.bpe_encode.argtypes
             L.bpe_tok_key_error.argtypes = [vp, vp, C.c_uint64, u64p]
             L.bpe_tok_cache_reset.argtypes = [vp]
+            L.bpe_tok_saw_cr.argtypes = [vp]
             L.bpe_decode.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, u64p]
             L.bpe_last_pair_table.argtypes = [vp, vp]
             L.bpe_train_set_live.argtypes = [vp, vp, C.c_int]

@@ -52,6 +52,7 @@ struct bpe_ctx {
     struct CountState *count = nullptr;              // pretoken count tables (count.cu)
     uint64_t mem_limit = 0;
     std::vector<DevBuf> pool;                        // cached free device buffers
+    bool saw_cr_encode = false;                      // a '\r' anywhere in the text of the last bpe_encode / bpe_encode_dev call
     bool saw_cr = false;                             // the last flags pass met a '\r'
     int32_t *live_pairs = nullptr; int live_cap = 0;   // bpe_train_set_live: page-locked host buffer the merge loop writes as it goes
     std::vector<unsigned long long> last_dense;      // initial 256 x 256 byte-pair table of the last training call (bpe_last_pair_table)

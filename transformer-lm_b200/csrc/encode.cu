@@ -1204,6 +1204,8 @@ BPE_API int bpe_tok_cache_reset(bpe_tok *tok) {
     return BPE_OK;
 }
 
+BPE_API int bpe_tok_saw_cr(bpe_tok *tok) { return tok && tok->ctx && tok->ctx->saw_cr_encode ? 1 : 0; }
+
 BPE_API int bpe_tok_key_error(bpe_tok *tok, uint8_t *buf, uint64_t cap, uint64_t *len) {
     if (!tok || !len) return BPE_ERR_ARG;
     *len = tok->key_error.size();
@@ -1226,6 +1228,7 @@ static int encode_core(bpe_tok *tok, u64 n, int out_dtype, void *out_dev, u64 de
     BPE_TRY(ctx_upload_specials(ctx, tok->sp_blob_h.data(), tok->sp_offs_h.data(), tok->n_sp, &spb, &spo, &spmax));
     u64 nn = n;
     BPE_TRY(ctx_run_flags(ctx, &nn, false, spb, spo, tok->n_sp, spmax));
+    ctx->saw_cr_encode |= ctx->saw_cr;
     // ordinal of the first pretoken of every GROUP of 16 flag words (512 bytes of text = one warp step of the lookup kernel, which
     // gets the ordinals inside a step from a warp scan): a scan over N / 512 entries instead of N / 32
     const u64 nw = (n + 31) / 32, ng = (nw + 15) / 16;
@@ -1453,6 +1456,7 @@ BPE_API int bpe_encode(bpe_tok *tok, const uint8_t *text_host, uint64_t n, int o
     BPE_TRY(encode_check_args(tok, text_host, n, out_dtype, n_out));
     bpe_ctx *ctx = tok->ctx;
     cudaStream_t st = ctx->stream;
+    ctx->saw_cr_encode = false;
     if (stats) memset(stats, 0, sizeof(*stats));
     const size_t esz = out_dtype == BPE_DTYPE_U16 ? 2 : 4;
     // chunk boundaries
@@ -1532,6 +1536,7 @@ BPE_API int bpe_encode_dev(bpe_tok *tok, const uint8_t *text_dev, uint64_t n, in
                            bpe_encode_stats *stats) {
     BPE_TRY(encode_check_args(tok, text_dev, n, out_dtype, n_out));
     bpe_ctx *ctx = tok->ctx;
+    ctx->saw_cr_encode = false;
     if (stats) memset(stats, 0, sizeof(*stats));
     EvTimer tm(ctx);
     int e0 = tm.mark();

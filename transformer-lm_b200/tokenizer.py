@@ -182,6 +182,7 @@ class Tokenizer:
             if rc != _lib.BPE_OK:
                 self._raise(ctx, rc, arr)
         self.last_stats = stats.as_dict()
+        self.last_saw_cr = bool(L.bpe_tok_saw_cr(tok))
         return int(n_out.value)
 
     def encode(self, text: str) -> List[int]:
