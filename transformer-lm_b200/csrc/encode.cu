@@ -645,8 +645,13 @@ __global__ void __launch_bounds__(SE_NT) k_enc_scan_emit(EncTables t, const u64 
     const u64 first = (u64)tile * SE_TILE + (u64)threadIdx.x * SE_ITEMS;
     u64 v[SE_ITEMS];
     u32 sum = 0;
+    if (first + SE_ITEMS <= n_items) {           // 16-byte loads (vals is 16-byte aligned and `first` a multiple of SE_ITEMS): a sector is fetched by two instructions, not four
 #pragma unroll
-    for (u32 k = 0; k < SE_ITEMS; k++) v[k] = first + k < n_items ? __ldcs(&vals[first + k]) : 0;
+        for (u32 k = 0; k < SE_ITEMS; k += 2) { const ulonglong2 w = __ldcs(reinterpret_cast<const ulonglong2 *>(vals + first + k)); v[k] = w.x; v[k + 1] = w.y; }
+    } else {
+#pragma unroll
+        for (u32 k = 0; k < SE_ITEMS; k++) v[k] = first + k < n_items ? __ldcs(&vals[first + k]) : 0;
+    }
 #pragma unroll
     for (u32 k = 0; k < SE_ITEMS; k++) {
         if (first + k >= n_items) continue;
@@ -656,6 +661,28 @@ __global__ void __launch_bounds__(SE_NT) k_enc_scan_emit(EncTables t, const u64 
     }
     u32 tot;
     const u32 ex = block_excl_scan_u32(sum, &tot, s_warp);
+    // A thread owns SE_ITEMS consecutive pretokens, i.e. ~11 consecutive ids: written straight to global memory, the 32 lanes
+    // of a store instruction would hit ~22 different sectors with 2 bytes each.  The ids of the tile are staged in shared
+    // memory instead and copied out with consecutive threads on consecutive ids (tiles with more ids than the stage holds
+    // -- long pool-resident values -- take the direct path).  The staging needs only the offsets INSIDE the tile, so the warps
+    // do it while warp 0 looks back for the tile's global offset (a third of all stall samples sat behind that look-back).
+    __shared__ u32 s_ids[SE_STAGE];
+    const bool staged = kEmit && tot <= SE_STAGE;
+    auto stage_ids = [&]() {
+        u32 o = ex;
+#pragma unroll
+        for (u32 k = 0; k < SE_ITEMS; k++) {
+            const u32 tag = VAL_TAG(v[k]);
+            if (tag <= 3) {
+                for (u32 q = 0; q < tag; q++) s_ids[o++] = (u32)((v[k] >> (20 * q)) & 0xFFFFFu);
+            } else if (tag == VAL_EXT) {
+                const u32 *src = t.ipool + ((v[k] >> 24) & 0xFFFFFFFFFull);
+                const u32 c = (u32)(v[k] & 0xFFFFFFu);
+                for (u32 q = 0; q < c; q++) s_ids[o++] = src[q];
+            }
+        }
+    };
+    if (threadIdx.x >= 32 && staged) stage_ids();
     if (threadIdx.x < 32) {
         const u32 lane = threadIdx.x;
         u64 run = 0;
@@ -681,29 +708,12 @@ __global__ void __launch_bounds__(SE_NT) k_enc_scan_emit(EncTables t, const u64 
             s_prefix = run;
             if ((u64)(tile + 1) * SE_TILE >= n_items) *total_out = run + tot;
         }
+        if (staged) stage_ids();
     }
     __syncthreads();
     if (!kEmit) return;
-    // A thread owns SE_ITEMS consecutive pretokens, i.e. ~11 consecutive ids: written straight to global memory, the 32 lanes
-    // of a store instruction would hit ~22 different sectors with 2 bytes each.  The ids of the tile are staged in shared
-    // memory instead and copied out with consecutive threads on consecutive ids (tiles with more ids than the stage holds
-    // -- long pool-resident values -- take the direct path).
-    __shared__ u32 s_ids[SE_STAGE];
     const u64 tile_dst = out_base + s_prefix;
-    if (tot <= SE_STAGE) {
-        u32 o = ex;
-#pragma unroll
-        for (u32 k = 0; k < SE_ITEMS; k++) {
-            const u32 tag = VAL_TAG(v[k]);
-            if (tag <= 3) {
-                for (u32 q = 0; q < tag; q++) s_ids[o++] = (u32)((v[k] >> (20 * q)) & 0xFFFFFu);
-            } else if (tag == VAL_EXT) {
-                const u32 *src = t.ipool + ((v[k] >> 24) & 0xFFFFFFFFFull);
-                const u32 c = (u32)(v[k] & 0xFFFFFFu);
-                for (u32 q = 0; q < c; q++) s_ids[o++] = src[q];
-            }
-        }
-        __syncthreads();
+    if (staged) {
         for (u32 j = threadIdx.x; j < tot; j += SE_NT) { const u64 d = tile_dst + j; if (d < cap) __stcs(&out[d], (OutT)s_ids[j]); }
         return;
     }

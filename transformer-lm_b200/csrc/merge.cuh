@@ -59,7 +59,9 @@ __device__ __forceinline__ u32 pair_hash(u64 key) {
 #define MG_NT 512
 #define MG_NEED_GROW 8ull                        // ctr[3] code: pair table more than half full, host must grow it
 #ifndef MG_BATCH
+#ifndef MG_BATCH
 #define MG_BATCH 15u                             // merges per step, at most (<= 30).  Measured at 11 GB with the relaxed rule: 15 -> 143 ms, 20 -> 150, 24 -> 155, 30 -> 164 (fewer steps, but every extra merge of a step costs ~1.5 us of rescans and apply work)
+#endif
 #endif
 
 struct __align__(16) WordMeta {
