@@ -146,19 +146,18 @@ __device__ __forceinline__ void long_add(const CountTables &t, const uint8_t *p,
     t.counters[3] = 1;
 }
 
-// Counting straight from the text and its start bits (no per-pretoken offset array, no scan): a lane owns one 16-byte chunk --
-// its 32-byte text window in registers, a 64-bit window of start bits -- and walks the chunk's start bits; a warp takes 32
-// consecutive chunks (512 bytes of text, coalesced 16-byte loads) per step, grid-stride, the next step's loads in flight while
-// this one is worked on.  For every start bit: length = distance to the next start bit (in the window; pretokens of more than
-// ~32 bytes look it up in the bit array), the first 16 bytes of the pretoken are cut out of the register window with selects and
-// funnel shifts (no byte loops, no unaligned loads).
+// Counting straight from the text and its start bits (no per-pretoken offset array, no scan).  A warp takes 32 consecutive 16-byte
+// chunks (512 bytes of text, coalesced 16-byte loads, the next step's loads in flight) per step, steps handed out by a ticket
+// counter; the step's start bits are compacted into a list of positions in shared memory and the pretokens are taken 32 at a time,
+// a lane each (details at the kernel).  For every pretoken: length = next position - position (pretokens that run past the bits
+// the step holds look it up in the bit array), the first 16 bytes are cut out of the staged text with aligned loads and funnel
+// shifts (no byte loops, no unaligned loads).
 //   * pretokens of <= 7 bytes are counted in the CTA's shared-memory table (natural-language text is Zipfian: without it the few
 //     hottest words serialise hundreds of millions of same-address L2 atomics);
 //   * what misses there, and every longer pretoken, goes to the warp's queues (compacted with ballots; the queue lengths are
-//     warp-uniform registers: no atomics, no CTA barrier anywhere in the loop), one queue per KIND of work, so that the pass that
-//     drains them runs one code path with all lanes: short keys, medium (k0, k1) keys, long pretokens (offset | len << 32).
-//     A drain takes whole groups of 32 entries: entry e of the short queue and entry e of the medium queue per lane, their first
-//     probes in flight together.
+//     warp-uniform registers: no atomics, no CTA barrier anywhere in the loop): keys (short: k0 = key, k1 = 0; medium: k0, k1)
+//     and long pretokens (offset | len << 32).  A drain takes whole groups of 64 keys, two per lane with their probes in flight
+//     together: hot table first, the big tables for what misses it.
 // The shared-memory table is flushed to the HBM table when the CTA is done.
 // One CTA of 1 024 threads per SM with a 1 024-slot table.  Measured on the 11 GB OWT-shape corpus (count stage, ms) with the hot
 // table behind it: 2 CTAs x 512 threads x 4 096 slots 48.4; 1 x 1 024 threads: 8 192 slots 47.0, 4 096 43.8, 2 048 44.4, 1 024 42.0,
@@ -189,7 +188,7 @@ struct CountQueues { ulonglong2 *qe; u64 *ql; u32 n, nl; };
 // The HOT TABLE.  A probe into the big tables is one random 32-byte sector and its 128-byte L2 line to itself (the tables are
 // sized for the worst case and mostly empty).  Measured on B200 (tools/bench_l2_random.cu, bench_l2_mix.cu): L2 keeps ~0.5 M such
 // lines; a random read + RED pair that misses it runs at 16-20 G pairs/s, one that hits at 60-110 G/s -- and counting 11 GB of
-// web-like text sends 1.1 G pairs to the tables, most of them to words that are neither among the 4 096 the shared-memory table
+// web-like text sends 1.1 G pairs to the tables, most of them to words that are neither among the few the shared-memory table
 // holds nor rare.  So once enough text has been seen, the words counted at least T times are copied into a DENSE table of their
 // own, probed first: a bucket is ONE 32-byte sector holding two 16-byte keys (short and medium words alike: k1 = 0 for a short
 // one), the counts sit in an array beside it -- at most ~1 M words, 50 MB: it stays in L2.  A word whose bucket is full stays with
