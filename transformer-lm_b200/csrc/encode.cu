@@ -3,14 +3,16 @@
 // Reference being replaced: models/tokenizer/tokenizer.py:111-138 (encode), 63-90 (segment / pretokenize),
 // 92-109 (merge), 155-157 (decode).
 //
-// Pipeline of one bpe_encode call (all stages on the context's stream):
-//   1. special-token split + GPT-2 pretoken start flags            (pretok.cu, shared with training)
-//   2. k_enc_lookup   every pretoken occurrence is looked up in the tokenizer's device-resident
-//                     pretoken -> token-ids cache (open addressing, exact keys); unseen pretokens
-//                     claim a slot and are queued
-//   3. k_enc_bpe      one warp per queued (new unique) pretoken applies the merges in rank order
-//                     through the pair -> rank table: repeatedly take the lowest-ranked adjacent
-//                     pair and replace all its non-overlapping occurrences left to right
+// Pipeline of one bpe_encode call (all stages on the context's stream), per batch of 256 MB of text:
+//   1. special-token split + GPT-2 pretoken start flags            (pretok.cu, shared with training), pretoken ordinals per
+//                     512-byte group
+//   2. k_enc_lookup   straight from the text and its start bits: every pretoken occurrence gets its cached value -- from the
+//                     CTA's shared-memory image of the most looked-up short pretokens, else from the dense L2-resident hot table,
+//                     else from the tokenizer's device-resident pretoken -> token-ids cache (open addressing, exact keys: short,
+//                     medium and long tables); unseen pretokens claim a slot there and are queued
+//   3. k_enc_bpe_short / k_enc_bpe   the queued (new unique) pretokens: the merges in rank order through the pair -> rank table
+//                     (repeatedly the lowest-ranked adjacent pair, all its non-overlapping occurrences left to right); one thread
+//                     per pretoken of <= 32 bytes, one warp per longer one
 //   4. k_enc_scan_emit  tokens per pretoken -> exclusive offsets -> ids scattered to the uint16 / int32 output, in one
 //                     pass (single-pass scan with decoupled look-back)
 // The reference re-runs BPE for every occurrence (no memoisation, tokenizer.py:118-136); the result per
