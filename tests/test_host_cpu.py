@@ -123,3 +123,15 @@ def test_merge_builder_in_pieces_equals_one_piece_and_dedupes_like_the_reference
         b.feed(pairs[lo:hi])
     assert b.n_fed == n and b.result() == want
     assert len(want[0]) < 256 + len(specials) + n         # the duplicates were skipped
+
+
+def test_numa_binding_is_best_effort():
+    """_lib.bind_to_gpu_numa_node never raises: without a GPU / sysfs it reports why it left the process where it was."""
+    import os
+    from transformer_lm_b200 import _lib
+    before = os.sched_getaffinity(0)
+    info = _lib.bind_to_gpu_numa_node(0)
+    assert isinstance(info, dict) and "bound" in info
+    if not info["bound"]:
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)
