@@ -791,6 +791,8 @@ def run_b200(args):
                 "encode_file(path -> .bin)": {"wall_s": round(min(ewalls), 4), "MBps": round(f_bytes / 1e6 / min(ewalls), 1), "tokens": int(n_tok_f),
                                                "api": "transformer_lm_b200.encode_file.encode_file(tokenizer, path, out.bin, uint16) (reader thread -> bpe_encode -> writer thread)"},
             }
+        except Exception as e:                   # (no room in the scratch directory, ...: the leg is informative, the headline stands)
+            line["files"] = {"error": "%s: %s" % (type(e).__name__, e)}
         finally:
             shutil.rmtree(fdir, ignore_errors=True)
 
