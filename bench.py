@@ -151,6 +151,20 @@ def ncu_traffic(kernel: str, config: dict):
     return None, None
 
 
+def ncu_traffic_sum(kernels, config: dict):
+    """Sum of ncu_traffic over several kernels (every captured instance of each, e.g. both k_enc_bpe_short shapes); None unless the
+    first kernel of the list (the stage's dominant one) has a capture of this configuration."""
+    try:
+        tj = json.loads((ROOT / "profiles" / "r2_traffic.json").read_text())
+        hit = [e for e in tj["captures"] if e["kernel"] in kernels and all(k in e["config"] and e["config"][k] == v for k, v in config.items())]
+        if not any(e["kernel"] == kernels[0] for e in hit):
+            return None, None
+        names = sorted({e["kernel"] for e in hit})
+        return sum(e["dram_bytes_per_step"] for e in hit), "sum over %s; %s" % (", ".join(names), "; ".join(sorted({e["source"] for e in hit})))
+    except Exception:
+        return None, None
+
+
 # ----------------------------------------------------------------------------------------------
 # CPU arms: the reference's own Python implementation (baseline/_ref, installed from /root/reference in the build
 # container, see DESIGN.md section 7) and its C port (oracle/bpe_oracle.c).  Host cores only; these functions never
@@ -674,10 +688,14 @@ def run_b200(args):
         dom = max(("ms_pretok", "ms_lookup", "ms_bpe", "ms_emit"), key=eavg)
         ecfg_key = {"text_bytes": e_bytes, "n_gpus": world}
         stage_alg = {"ms_pretok": n_loc * 1.125, "ms_lookup": float(n_loc), "ms_bpe": None, "ms_emit": 2.0 * tokens_local}
+        stage_kernels = {"ms_pretok": ["k_pretok_flags", "k_special_candidates", "k_special_resolve", "k_popc_words16"],
+                         "ms_lookup": ["k_enc_lookup"], "ms_emit": ["k_enc_scan_emit"]}
+        tr_all, tr_all_src = ncu_traffic_sum(["k_enc_lookup", "k_pretok_flags", "k_special_candidates", "k_special_resolve", "k_popc_words16",
+                                              "k_enc_bpe_short", "k_enc_bpe", "k_enc_scan_emit"], ecfg_key)
         hbm_stages = {}
         for k, kern in (("ms_pretok", "k_pretok_flags<1> + special-token passes"), ("ms_lookup", "k_enc_lookup"), ("ms_emit", "k_enc_scan_emit")):
             ms_k = eavg(k)
-            tr, src = ncu_traffic(kern.split(" ")[0], ecfg_key)
+            tr, src = ncu_traffic_sum(stage_kernels[k], ecfg_key)
             gbs = stage_alg[k] / 1e9 / (ms_k / 1e3) if ms_k else None
             hbm_stages[kern] = {"algorithmic_bytes": stage_alg[k], "ms": round(ms_k, 3), "achieved": round(gbs, 1) if gbs else None,
                                 "frac": round(gbs / peak, 4) if gbs else None, "traffic": tr, "traffic_source": src}
@@ -691,7 +709,7 @@ def run_b200(args):
             "new_unique_pretokens": int(eavg("cache_new_unique")), "pretokens": int(eavg("n_pretokens")),
             "roofline": {"bound": "hbm", "kernel": "whole encode pipeline (flags, lookup, bpe, fused scan+emit); slowest stage: " + dom,
                          "achieved": round(alg / 1e9 / (ems_dev / 1e3), 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(alg / 1e9 / (ems_dev / 1e3) / peak, 4), "traffic": None, "peak_source": peak_src,
+                         "frac": round(alg / 1e9 / (ems_dev / 1e3) / peak, 4), "traffic": tr_all, "traffic_source": tr_all_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg, "algorithmic_bytes_definition": "N text bytes read once + 2 B per token written",
                          "stages": hbm_stages},
             "gpu_launches": int(e_launches), "clocks": eclocks,

@@ -1,6 +1,8 @@
 """profiles/r2_traffic.json from the round's .ncu-rep captures (read on the CPU box): DRAM bytes (read + written) per captured launch
 of every kernel, x the launches a bench step makes (from the launch list of the same command).
-usage: python tools/ncu_traffic.py <launches.csv> <out.json> <rep>:<config json> [<rep>:<config json> ...]"""
+usage: python tools/ncu_traffic.py [--append] <launches.csv> <out.json> <rep>:<config json> [<rep>:<config json> ...]
+--append keeps the entries <out.json> already holds; a config key "_only" (regular expression on the full kernel name, template
+arguments included) restricts a capture file to the kernels it was taken for; "_source" names the script that took it."""
 import csv
 import json
 import re
@@ -27,7 +29,9 @@ def unit_scale(u):
 
 
 def main():
-    launch_csv, out_path, specs = sys.argv[1], sys.argv[2], sys.argv[3:]
+    argv = [a for a in sys.argv[1:] if a != "--append"]
+    append = len(argv) != len(sys.argv) - 1
+    launch_csv, out_path, specs = argv[0], argv[1], argv[2:]
     per_step_div = 1
     counts = launches_per_name(launch_csv)
     caps = []
@@ -35,6 +39,8 @@ def main():
         rep, cfg = spec.split(":", 1)
         cfg = json.loads(cfg)
         steps_in_list = cfg.pop("_steps_in_launch_list", 1)      # the launch list covers warm-up + timed steps of bench.py
+        only = re.compile(cfg.pop("_only", ""))
+        script = cfg.pop("_source", "tools/profile_r2.sh")
         out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(out.splitlines()))
         h, units = rows[0], rows[1]
@@ -42,6 +48,8 @@ def main():
         seen = {}
         for r in rows[2:]:
             name = re.sub(r"^void ", "", r[ki]).split("(")[0]
+            if not only.search(name):
+                continue
             b = float(r[ri]) * unit_scale(units[ri]) + float(r[wi]) * unit_scale(units[wi])
             seen.setdefault(name, []).append((b, float(r[ti]) * {"ms": 1.0, "us": 1e-3, "s": 1e3, "ns": 1e-6}.get(units[ti], 1.0)))
         for name, lst in seen.items():
@@ -50,7 +58,9 @@ def main():
             per_step = max(1, round(counts.get(name, steps_in_list) / steps_in_list))
             caps.append({"kernel": name.split("<")[0], "config": cfg, "dram_bytes_per_launch": round(b, -3), "launches_per_step": per_step,
                          "dram_bytes_per_step": round(b * per_step, -3), "duration_ms": round(ms, 6), "captured_launches": len(lst),
-                         "source": "ncu --set full --clock-control none, %s (round 2, tools/profile_r2.sh)" % rep.split("/")[-1]})
+                         "source": "ncu --set full --clock-control none, %s (round 2, %s)" % (rep.split("/")[-1], script)})
+    if append:
+        caps = json.load(open(out_path))["captures"] + caps
     json.dump({"captures": caps}, open(out_path, "w"), indent=1)
     print("wrote", out_path, len(caps), "entries")
 

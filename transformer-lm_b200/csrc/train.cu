@@ -1384,8 +1384,8 @@ static int run_merges(bpe_ctx *ctx, const uint8_t *sp_blob, const u32 *sp_offs, 
     if (done > 0) CUDA_TRY(ctx, cudaMemcpyAsync(merge_pairs_out, B.merges.p, (size_t)done * 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     *n_done = done;
-    // SURVEY A-6: the reference identifies tokens by their byte string.  Detect (never observed) merges with a
-    // positive count whose product bytes already exist; the host refuses to return a result in that case.
+    // SURVEY A-6: the reference identifies tokens by their byte string.  A merge with a positive count whose product bytes
+    // already exist cannot occur; the count is kept as an invariant check and the host raises on it.
     u64 dup_tokens = 0;
     if (done > 0) {
         std::vector<i64> mc(done);

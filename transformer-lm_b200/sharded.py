@@ -140,7 +140,7 @@ class DeviceCounter:
             out = live.finish(pairs, n_done.value if rc == _lib.BPE_OK else 0)
         self.ctx.check(rc)
         if stats.duplicate_tokens:
-            raise NotImplementedError("two merges produced identical token bytes (SURVEY A-6); not supported")
+            raise AssertionError("invariant violated: a merge with a positive count produced the bytes of an earlier token (SURVEY A-6)")   # see train.py
         if self._expected_pairs is not None:
             # linearity check of the sharded count: the all-reduced per-rank byte-pair tables must equal the table of the
             # merged counts, which the merge phase has just built

@@ -175,9 +175,10 @@ def train_bpe_on_bytes(data, vocab_size: int, special_tokens: List[str] = [], *,
         raise AssertionError("device flagged invalid UTF-8 at %d but CPython accepts the data" % L.bpe_last_error_detail(ctx.handle))
     ctx.check(rc)
     if stats.duplicate_tokens:
-        # SURVEY A-6: two different merges produced the same byte string while the pair still had a positive
-        # count.  The reference would pool the two symbols; this has never been observed and is not implemented.
-        raise NotImplementedError("two merges produced identical token bytes (SURVEY A-6); not supported")
+        # SURVEY A-6: the reference identifies a token by its bytes, the device by its merge index.  The two differ only if a merge
+        # with a positive count produces bytes an earlier merge produced -- which cannot happen (DESIGN.md section 8 has the
+        # argument), so a non-zero counter means the device result is wrong, not that a rare input was met.
+        raise AssertionError("invariant violated: a merge with a positive count produced the bytes of an earlier token (SURVEY A-6)")
     out = (*res,)
     return out + (stats.as_dict(),) if return_stats else out
 
