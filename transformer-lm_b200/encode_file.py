@@ -273,7 +273,13 @@ def _encode_file_pinned(tokenizer, input_path, output_path, dtype, piece_bytes, 
             if cut:
                 try:
                     t0 = _t.perf_counter()
-                    idx = free_out.get()
+                    while True:                              # (a writer that failed hands no buffer back: do not wait for one forever)
+                        try:
+                            idx = free_out.get(timeout=0.2)
+                            break
+                        except queue.Empty:
+                            if failure:
+                                raise failure[0]
                     t1 = _t.perf_counter()
                     n_tok = tokenizer.encode_into(cur[:cut], out_views[idx])
                     acc["wait_out"] += t1 - t0; acc["encode"] += _t.perf_counter() - t1; acc["pieces"] += 1
