@@ -80,7 +80,7 @@ typedef struct bpe_train_stats {
     uint64_t n_pairs_initial;    /* distinct adjacent byte pairs at start */
     uint64_t n_pairs_final;      /* pair-table keys ever created */
     uint64_t log_records;        /* inverted-index records written by the merge loop */
-    uint64_t duplicate_tokens;   /* merges whose product bytes already existed (SURVEY A-6); 0 expected */
+    uint64_t duplicate_tokens;   /* positive-count merges whose product bytes already existed (SURVEY A-6): provably 0, kept as an invariant check */
     uint64_t sum_live_pairs;     /* sum over merges of the live pair-table keys (what the reference's max() scans) */
     uint64_t merge_steps;        /* grid steps of the merge loop (a step applies up to 12 merges, see csrc/merge.cuh) */
     float ms_h2d;                /* host->device copy of the text */

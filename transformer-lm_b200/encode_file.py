@@ -14,6 +14,7 @@ file over the ranks of a torch.distributed group (sharded_encode.py).
 """
 from __future__ import annotations
 
+import errno
 import os
 import re
 
@@ -208,6 +209,14 @@ def _encode_file_pinned(tokenizer, input_path, output_path, dtype, piece_bytes, 
                     arr = ids.astype(dtype.newbyteorder("<"), copy=False) if ids is not None else out_views[idx][:n_tok]   # (little-endian host: the raw buffer is the file format)
                     src = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
                     if out_arr is not None:
+                        # a store into a mapped hole of a full file system is a SIGBUS, not an OSError: look before writing
+                        try:
+                            vfs = os.fstatvfs(fd)
+                            room = vfs.f_bavail * vfs.f_frsize if vfs.f_blocks else None
+                        except OSError:
+                            room = None
+                        if room is not None and room < src.size:
+                            raise OSError(errno.ENOSPC, "no room for %d more bytes of token ids" % src.size, os.fspath(output_path))
                         futs = [io_pool.submit(np.copyto, out_arr[pos + a: pos + b], src[a:b]) for a, b in slices(src.size)]
                     else:
                         mv = memoryview(src)
