@@ -1,0 +1,144 @@
+"""The oracle against the UNMODIFIED reference, run live (CPU; only where /root/reference is mounted, i.e. in the build container --
+it does not exist on the GPU box and the test is skipped there).  The committed goldens (tests/golden, tools/make_golden.py) pin 20
+training and 5 tokenizer set-ups; this differential adds fresh seeded cases on every run of the CPU suite: random small corpora through
+models/tokenizer/train.py:142-231 and random texts through models/tokenizer/tokenizer.py:111-138, compared with oracle/bpe_oracle.c.
+The reference runs in a subprocess (its package is called `models`, like this repository's shim)."""
+import json
+import pathlib
+import random
+import subprocess
+import sys
+
+import pytest
+
+from oracle import oracle
+from tests.common import FIXTURES_PATH
+
+REF = pathlib.Path("/root/reference")
+pytestmark = pytest.mark.skipif(not (REF / "models" / "tokenizer" / "train.py").exists(), reason="the reference is not mounted here")
+
+WORKER = r'''
+import json, sys, logging
+sys.path.insert(0, "/root/reference")
+logging.disable(logging.CRITICAL)
+from models.tokenizer import train as T
+T.tqdm = lambda x, *a, **k: x
+from models.tokenizer.tokenizer import Tokenizer
+jobs = json.load(open(sys.argv[1]))
+out = []
+for job in jobs:
+    if job["kind"] == "train":
+        try:
+            vocab, merges = T.train_bpe(job["path"], job["vocab_size"], job["special_tokens"])
+            out.append({"vocab": {str(k): v.hex() for k, v in vocab.items()}, "merges": [[a.hex(), b.hex()] for a, b in merges]})
+        except UnicodeDecodeError as e:
+            out.append({"error": "UnicodeDecodeError", "start": e.start})
+    else:
+        vocab = {int(k): bytes.fromhex(v) for k, v in job["vocab"].items()}
+        merges = [(bytes.fromhex(a), bytes.fromhex(b)) for a, b in job["merges"]]
+        tok = Tokenizer(vocab, merges, job["special_tokens"])
+        res = []
+        for text in job["texts"]:
+            try:
+                ids = tok.encode(text)
+            except KeyError as e:
+                res.append({"error": "KeyError", "arg": e.args[0].hex() if isinstance(e.args[0], bytes) else repr(e.args[0])})
+                continue
+            try:
+                res.append({"ids": ids, "decoded": tok.decode(ids)})
+            except KeyError as e:           # (a special token the constructor added under a bytes KEY has no id -> bytes entry)
+                res.append({"ids": ids, "decode_error": repr(e.args[0])})
+        out.append(res)
+json.dump(out, open(sys.argv[2], "w"))
+'''
+
+WORDS = ["the", "a", "cat", "it's", "they'll", "we've", "don't", "I'm", "naïve", "café", "日本語", "テスト", "привет", "🙃", "👍🏽", "3.14",
+         "2024", "1,000", "http://x.y/z?q=1", "a_b", "--", "...", "!?", "<|endoftext|>", "<|pad|>", "x²", "١٢٣", "é", "aaa", "abab", "he"]
+SEPS = [" ", " ", " ", "  ", "\n", "\n\n", "\t", " \n", "   ", "", " ", " ", "\r\n", "\r"]
+
+
+def _text(r, n_words, crlf):
+    seps = SEPS if crlf else SEPS[:-2]
+    out = []
+    for _ in range(n_words):
+        w = r.choice(WORDS)
+        out.append(w.capitalize() if r.random() < 0.2 else w)
+        out.append(r.choice(seps))
+        if r.random() < 0.05:
+            out.append(r.choice([".", ",", "'", "\"", "'s", "'re", "'"]))
+    return "".join(out)
+
+
+def _run_reference(tmp_path, jobs):
+    (tmp_path / "worker.py").write_text(WORKER)
+    (tmp_path / "jobs.json").write_text(json.dumps(jobs))
+    subprocess.check_call([sys.executable, str(tmp_path / "worker.py"), str(tmp_path / "jobs.json"), str(tmp_path / "out.json")],
+                          cwd=str(REF), env={"PYTHONDONTWRITEBYTECODE": "1", "PATH": "/usr/bin:/bin"}, timeout=600)
+    return json.loads((tmp_path / "out.json").read_text())
+
+
+def test_train_bpe_equals_the_reference_on_fresh_corpora(tmp_path):
+    r = random.Random(986)
+    jobs, inputs = [], []
+    for k in range(28):
+        flavour = k % 4
+        if flavour == 0:
+            data = "".join(r.choice("ab c") for _ in range(r.randint(1, 300))).encode()
+        elif flavour == 3:
+            data = bytearray(_text(r, r.randint(5, 200), False).encode())
+            data[r.randrange(len(data))] = r.choice([0xFF, 0xC0, 0xE2, 0x80, 0xF5])        # (usually) invalid UTF-8 somewhere
+            data = bytes(data)
+        else:
+            data = _text(r, r.randint(1, 700), crlf=flavour == 2).encode()
+        specials = r.choice([[], ["<|endoftext|>"], ["<|endoftext|>", "<|pad|>"], ["he"], [" the", "<|endoftext|>", "<|endoftext|>"]])
+        vocab_size = r.choice([0, 257, 270, 300, 400, 600, 2000])
+        p = tmp_path / ("c%d.txt" % k)
+        p.write_bytes(data)
+        jobs.append({"kind": "train", "path": str(p), "vocab_size": vocab_size, "special_tokens": specials})
+        inputs.append(data)
+    n_err = 0
+    for job, data, ref in zip(jobs, inputs, _run_reference(tmp_path, jobs)):
+        if "error" in ref:
+            n_err += 1
+            with pytest.raises(UnicodeDecodeError) as e:
+                oracle.train_bpe_on_bytes(data, job["vocab_size"], job["special_tokens"])
+            assert e.value.start == ref["start"]
+            continue
+        vocab, merges = oracle.train_bpe_on_bytes(data, job["vocab_size"], job["special_tokens"])
+        assert [[a.hex(), b.hex()] for a, b in merges] == ref["merges"], job
+        assert {str(k): v.hex() for k, v in vocab.items()} == ref["vocab"], job
+    assert n_err >= 3
+
+
+def test_tokenizer_encode_equals_the_reference_on_fresh_texts(tmp_path):
+    r = random.Random(4711)
+    corpus = (FIXTURES_PATH / "corpus.en").read_bytes()[:80000] + _text(r, 2000, False).encode()
+    set_ups = []
+    for vocab_size, specials in ((700, ["<|endoftext|>"]), (400, []), (900, ["<|endoftext|>", "<|endoftext|><|endoftext|>", "<|pad|>"])):
+        vocab, merges = oracle.train_bpe_on_bytes(corpus, vocab_size, specials[:1])
+        set_ups.append((vocab, merges, specials))
+    holed = {k: v for k, v in set_ups[0][0].items() if v not in (b" the", b"e", b"\xf0")}       # KeyErrors (tokenizer.py:120,135)
+    set_ups.append((holed, set_ups[0][1], ["<|endoftext|>"]))
+    texts = ["", " ", "a", "🙃"] + [_text(r, r.randint(1, 300), crlf=k % 3 == 0) for k in range(30)]
+    jobs = [{"kind": "encode", "vocab": {str(k): v.hex() for k, v in vocab.items()}, "merges": [[a.hex(), b.hex()] for a, b in merges],
+             "special_tokens": specials, "texts": texts} for vocab, merges, specials in set_ups]
+    n_key = n_dec = 0
+    for (vocab, merges, specials), ref in zip(set_ups, _run_reference(tmp_path, jobs)):
+        tok = oracle.OracleTokenizer(dict(vocab), list(merges), list(specials))
+        for text, want in zip(texts, ref):
+            if "error" in want:
+                n_key += 1
+                with pytest.raises(KeyError) as e:
+                    tok.encode(text)
+                arg = e.value.args[0]
+                assert (arg.hex() if isinstance(arg, bytes) else repr(arg)) == want["arg"]
+            else:
+                assert tok.encode(text) == want["ids"], (specials, text)
+                if "decode_error" in want:
+                    n_dec += 1
+                    with pytest.raises(KeyError) as e:
+                        tok.decode(want["ids"])
+                    assert repr(e.value.args[0]) == want["decode_error"]
+                else:
+                    assert tok.decode(want["ids"]) == want["decoded"]
+    assert n_key >= 5 and n_dec >= 1
