@@ -4,6 +4,7 @@ training and 5 tokenizer set-ups; this differential adds fresh seeded cases on e
 models/tokenizer/train.py:142-231 and random texts through models/tokenizer/tokenizer.py:111-138, compared with oracle/bpe_oracle.c.
 The reference runs in a subprocess (its package is called `models`, like this repository's shim)."""
 import json
+import os
 import pathlib
 import random
 import subprocess
@@ -15,6 +16,7 @@ from oracle import oracle
 from tests.common import FIXTURES_PATH
 
 REF = pathlib.Path("/root/reference")
+SEED = int(os.environ.get("BPE_LIVE_SEED", "0"))     # other seeds for longer hunts: BPE_LIVE_SEED=k python -m pytest tests/test_oracle_vs_reference_live.py
 pytestmark = pytest.mark.skipif(not (REF / "models" / "tokenizer" / "train.py").exists(), reason="the reference is not mounted here")
 
 WORKER = r'''
@@ -78,7 +80,7 @@ def _run_reference(tmp_path, jobs):
 
 
 def test_train_bpe_equals_the_reference_on_fresh_corpora(tmp_path):
-    r = random.Random(986)
+    r = random.Random(986 + SEED)
     jobs, inputs = [], []
     for k in range(28):
         flavour = k % 4
@@ -107,11 +109,11 @@ def test_train_bpe_equals_the_reference_on_fresh_corpora(tmp_path):
         vocab, merges = oracle.train_bpe_on_bytes(data, job["vocab_size"], job["special_tokens"])
         assert [[a.hex(), b.hex()] for a, b in merges] == ref["merges"], job
         assert {str(k): v.hex() for k, v in vocab.items()} == ref["vocab"], job
-    assert n_err >= 3
+    assert n_err >= 3 or SEED
 
 
 def test_tokenizer_encode_equals_the_reference_on_fresh_texts(tmp_path):
-    r = random.Random(4711)
+    r = random.Random(4711 + SEED)
     corpus = (FIXTURES_PATH / "corpus.en").read_bytes()[:80000] + _text(r, 2000, False).encode()
     set_ups = []
     for vocab_size, specials in ((700, ["<|endoftext|>"]), (400, []), (900, ["<|endoftext|>", "<|endoftext|><|endoftext|>", "<|pad|>"])):
@@ -141,4 +143,4 @@ def test_tokenizer_encode_equals_the_reference_on_fresh_texts(tmp_path):
                     assert repr(e.value.args[0]) == want["decode_error"]
                 else:
                     assert tok.decode(want["ids"]) == want["decoded"]
-    assert n_key >= 5 and n_dec >= 1
+    assert (n_key >= 5 and n_dec >= 1) or SEED
