@@ -6,14 +6,13 @@ The reference runs in a subprocess (its package is called `models`, like this re
 import json
 import os
 import pathlib
-import random
 import subprocess
 import sys
 
 import pytest
 
 from oracle import oracle
-from tests.common import FIXTURES_PATH
+from tests.helpers import live_shapes
 
 REF = pathlib.Path("/root/reference")
 SEED = int(os.environ.get("BPE_LIVE_SEED", "0"))     # other seeds for longer hunts: BPE_LIVE_SEED=k python -m pytest tests/test_oracle_vs_reference_live.py
@@ -54,23 +53,6 @@ for job in jobs:
 json.dump(out, open(sys.argv[2], "w"))
 '''
 
-WORDS = ["the", "a", "cat", "it's", "they'll", "we've", "don't", "I'm", "naïve", "café", "日本語", "テスト", "привет", "🙃", "👍🏽", "3.14",
-         "2024", "1,000", "http://x.y/z?q=1", "a_b", "--", "...", "!?", "<|endoftext|>", "<|pad|>", "x²", "١٢٣", "é", "aaa", "abab", "he"]
-SEPS = [" ", " ", " ", "  ", "\n", "\n\n", "\t", " \n", "   ", "", " ", " ", "\r\n", "\r"]
-
-
-def _text(r, n_words, crlf):
-    seps = SEPS if crlf else SEPS[:-2]
-    out = []
-    for _ in range(n_words):
-        w = r.choice(WORDS)
-        out.append(w.capitalize() if r.random() < 0.2 else w)
-        out.append(r.choice(seps))
-        if r.random() < 0.05:
-            out.append(r.choice([".", ",", "'", "\"", "'s", "'re", "'"]))
-    return "".join(out)
-
-
 def _run_reference(tmp_path, jobs):
     (tmp_path / "worker.py").write_text(WORKER)
     (tmp_path / "jobs.json").write_text(json.dumps(jobs))
@@ -80,20 +62,8 @@ def _run_reference(tmp_path, jobs):
 
 
 def test_train_bpe_equals_the_reference_on_fresh_corpora(tmp_path):
-    r = random.Random(986 + SEED)
     jobs, inputs = [], []
-    for k in range(28):
-        flavour = k % 4
-        if flavour == 0:
-            data = "".join(r.choice("ab c") for _ in range(r.randint(1, 300))).encode()
-        elif flavour == 3:
-            data = bytearray(_text(r, r.randint(5, 200), False).encode())
-            data[r.randrange(len(data))] = r.choice([0xFF, 0xC0, 0xE2, 0x80, 0xF5])        # (usually) invalid UTF-8 somewhere
-            data = bytes(data)
-        else:
-            data = _text(r, r.randint(1, 700), crlf=flavour == 2).encode()
-        specials = r.choice([[], ["<|endoftext|>"], ["<|endoftext|>", "<|pad|>"], ["he"], [" the", "<|endoftext|>", "<|endoftext|>"]])
-        vocab_size = r.choice([0, 257, 270, 300, 400, 600, 2000])
+    for k, (data, vocab_size, specials) in enumerate(live_shapes.train_cases(SEED)):
         p = tmp_path / ("c%d.txt" % k)
         p.write_bytes(data)
         jobs.append({"kind": "train", "path": str(p), "vocab_size": vocab_size, "special_tokens": specials})
@@ -113,15 +83,7 @@ def test_train_bpe_equals_the_reference_on_fresh_corpora(tmp_path):
 
 
 def test_tokenizer_encode_equals_the_reference_on_fresh_texts(tmp_path):
-    r = random.Random(4711 + SEED)
-    corpus = (FIXTURES_PATH / "corpus.en").read_bytes()[:80000] + _text(r, 2000, False).encode()
-    set_ups = []
-    for vocab_size, specials in ((700, ["<|endoftext|>"]), (400, []), (900, ["<|endoftext|>", "<|endoftext|><|endoftext|>", "<|pad|>"])):
-        vocab, merges = oracle.train_bpe_on_bytes(corpus, vocab_size, specials[:1])
-        set_ups.append((vocab, merges, specials))
-    holed = {k: v for k, v in set_ups[0][0].items() if v not in (b" the", b"e", b"\xf0")}       # KeyErrors (tokenizer.py:120,135)
-    set_ups.append((holed, set_ups[0][1], ["<|endoftext|>"]))
-    texts = ["", " ", "a", "🙃"] + [_text(r, r.randint(1, 300), crlf=k % 3 == 0) for k in range(30)]
+    set_ups, texts = live_shapes.encode_cases(SEED)
     jobs = [{"kind": "encode", "vocab": {str(k): v.hex() for k, v in vocab.items()}, "merges": [[a.hex(), b.hex()] for a, b in merges],
              "special_tokens": specials, "texts": texts} for vocab, merges, specials in set_ups]
     n_key = n_dec = 0
