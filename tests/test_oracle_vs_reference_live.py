@@ -34,6 +34,15 @@ for job in jobs:
             out.append({"vocab": {str(k): v.hex() for k, v in vocab.items()}, "merges": [[a.hex(), b.hex()] for a, b in merges]})
         except UnicodeDecodeError as e:
             out.append({"error": "UnicodeDecodeError", "start": e.start})
+    elif job["kind"] == "iterable":
+        vocab = {int(k): bytes.fromhex(v) for k, v in job["vocab"].items()}
+        merges = [(bytes.fromhex(a), bytes.fromhex(b)) for a, b in job["merges"]]
+        tok = Tokenizer(vocab, merges, job["special_tokens"])
+        import hashlib, struct
+        h, n = hashlib.sha256(), 0
+        for i in tok.encode_iterable(iter(job["lines"])):
+            h.update(struct.pack("<i", i)); n += 1
+        out.append({"n": n, "sha": h.hexdigest()})
     else:
         vocab = {int(k): bytes.fromhex(v) for k, v in job["vocab"].items()}
         merges = [(bytes.fromhex(a), bytes.fromhex(b)) for a, b in job["merges"]]
@@ -106,3 +115,28 @@ def test_tokenizer_encode_equals_the_reference_on_fresh_texts(tmp_path):
                 else:
                     assert tok.decode(want["ids"]) == want["decoded"]
     assert (n_key >= 5 and n_dec >= 1) or SEED
+
+
+def test_encode_iterable_chunk_rule_equals_the_reference(tmp_path):
+    """tokenizer.py:140-153: items are concatenated until the buffer holds >= 2 Mi characters and every buffer is encoded on its own
+    (a pretoken may be cut where two buffers meet, SURVEY A-13).  ~2.3 Mi characters in lines of odd lengths: two buffers."""
+    import hashlib
+    import random
+    import struct
+    r = random.Random(77 + SEED)
+    set_ups, _ = live_shapes.encode_cases(SEED)
+    vocab, merges, specials = set_ups[0]
+    words = ["alpha", "beta", "it's", "naïve", "日本語", "12", "<|endoftext|>", "x"]
+    lines, chars = [], 0
+    while chars < 2_400_000:
+        line = " ".join(r.choice(words) for _ in range(r.randint(1, 40))) + r.choice(["\n", " ", "", "\n\n"])
+        lines.append(line)
+        chars += len(line)
+    job = {"kind": "iterable", "vocab": {str(k): v.hex() for k, v in vocab.items()}, "merges": [[a.hex(), b.hex()] for a, b in merges],
+           "special_tokens": specials, "lines": lines}
+    (ref,) = _run_reference(tmp_path, [job])
+    h, n = hashlib.sha256(), 0
+    for i in oracle.OracleTokenizer(dict(vocab), list(merges), list(specials)).encode_iterable(iter(lines)):
+        h.update(struct.pack("<i", i))
+        n += 1
+    assert (n, h.hexdigest()) == (ref["n"], ref["sha"])
