@@ -605,6 +605,15 @@ def run_b200(args):
         for k in ("unsharded_check", "unsharded_merges_sha", "e2e"):
             if k in m:
                 line[k] = m[k]
+        if world > 1:
+            # strong scaling with a replicated tail: build + merge loop run on every rank, only pretokenise + count shard
+            try:
+                rep = float(m["stages_ms"]["ms_build"]) + float(m["stages_ms"]["ms_merge"])
+                line["scaling_note"] = {"replicated_ms": round(rep, 3), "sharded_ms": round(float(m["ms_per_step"]) - rep, 3),
+                                        "amdahl": "build + merge loop (replicated_ms) run replicated: the step cannot go below them at any N, so the speed-up "
+                                                  "over the 1-GPU step T1 is bounded by T1 / (replicated_ms + (T1 - replicated_ms) / N)"}
+            except Exception:
+                pass
 
         # ---- BASELINE.json configs[2]: TinyStories shape, 2 GiB, vocab 10000 ----
         if primary == "train" and not args.no_tiny and not args.bytes:
