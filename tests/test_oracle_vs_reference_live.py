@@ -66,7 +66,7 @@ def _run_reference(tmp_path, jobs):
     (tmp_path / "worker.py").write_text(WORKER)
     (tmp_path / "jobs.json").write_text(json.dumps(jobs))
     subprocess.check_call([sys.executable, str(tmp_path / "worker.py"), str(tmp_path / "jobs.json"), str(tmp_path / "out.json")],
-                          cwd=str(REF), env={"PYTHONDONTWRITEBYTECODE": "1", "PATH": "/usr/bin:/bin"}, timeout=600)
+                          cwd=str(REF), env={"PYTHONDONTWRITEBYTECODE": "1", "PATH": "/usr/bin:/bin", "PYTHONHASHSEED": os.environ.get("PYTHONHASHSEED", "random")}, timeout=600)
     return json.loads((tmp_path / "out.json").read_text())
 
 
