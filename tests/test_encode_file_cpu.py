@@ -111,6 +111,15 @@ def test_writer_failures_reach_the_caller(tmp_path, fake_pinned, monkeypatch):
     with pytest.raises(OSError):                                   # the output cannot be created
         ef.encode_file(tok, src, tmp_path / "missing_dir" / "t.bin", np.uint16, piece_bytes=3000)
 
+    import mmap
+    probe = tmp_path / "probe"
+    probe.write_bytes(b"\0" * 4096)
+    try:                                                           # (the check guards the memory-mapped output; positional writes fail by themselves)
+        with open(probe, "r+b") as f:
+            mmap.mmap(f.fileno(), 4096).close()
+    except (OSError, ValueError):
+        return
+
     class Full:
         f_bavail, f_frsize, f_blocks = 0, 4096, 1000
 
